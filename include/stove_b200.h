@@ -1,0 +1,187 @@
+/*
+ * stove_b200 -- C ABI of the B200-native (sm_100a) STOVE hot path.
+ *
+ * The reference (jlko/STOVE) has no native code and no plugin ABI: its hot path sits
+ * behind Python nn.Module methods.  This header is therefore the
+ * boundary a maintainer would bind from Python (ctypes); every entry
+ * point names the reference function it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says host.
+ *   - the caller owns every buffer (outputs, workspaces); nothing is allocated inside.
+ *   - all arithmetic is fp32; tensors are dense, row-major, innermost dimension last.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous, no host sync.
+ *   - return 0 on success, negative on error; `stove_last_error()` gives the message.
+ *   - buffers documented "accumulated" must be zeroed by the caller before the first call.
+ */
+#ifndef STOVE_B200_H
+#define STOVE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STOVE_OK 0
+#define STOVE_ERR_ARG (-1)
+#define STOVE_ERR_CUDA (-2)
+#define STOVE_ERR_UNSUPPORTED (-3)
+
+const char* stove_last_error(void);
+int stove_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * bw_transform: sum colour channels, clamp to [0,1]   (model/utils/utils.py:10-15)
+ *   x [n][C][hw] -> y [n][hw]
+ * ---------------------------------------------------------------------------------- */
+int stove_bw_transform(const float* x, float* y, int64_t n, int channels, int64_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * RAT-SPN parameter packing (model/spn/rat_torch.py:85-99 leaf variance,
+ * :209-210 log_softmax of sum weights).
+ *
+ * leaf rows:  means/sigma_params [rows][G]  ->  packed [prow][3][GP] = (mu, 1/(2 var),
+ *             0.5 log var + 0.5 log 2pi), prow = dst_row[row], GP = G rounded up to 4.
+ * sum blocks: raw [nb][K][S] -> wlog/wlin [nb][K][SP] (column-wise log_softmax over K and
+ *             its exp), SP = S rounded up to 4 (or 1 when S == 1).
+ * The *_bwd calls map gradients w.r.t. the packed tensors back to the raw parameters.
+ * ---------------------------------------------------------------------------------- */
+int stove_spn_pack_leaf_fwd(const float* means, const float* sigma_params, const int32_t* dst_row,
+                            int rows, int G, int GP, float min_var, float max_var,
+                            float* packed, void* stream);
+int stove_spn_pack_leaf_bwd(const float* sigma_params, const int32_t* dst_row, int rows, int G, int GP,
+                            float min_var, float max_var, const float* g_packed,
+                            float* g_means, float* g_sigma_params, void* stream);
+int stove_spn_pack_sum_fwd(const float* raw, int nb, int K, int S, int SP,
+                           float* wlog, float* wlin, void* stream);
+int stove_spn_pack_sum_bwd(const float* wlog, int nb, int K, int S, int SP, const float* g_wlog,
+                           float* g_raw, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Object SPN ("D2" structure: R root partitions, each = product of two mid regions,
+ * each mid region = one sum vector over the product of two Gauss leaves), i.e. what
+ * probabilistic_models.py:8-22 builds.  Replaces RatSpn.forward for that structure
+ * (rat_torch.py:333-357; leaves :83-109, products :147-163, sums :202-222).
+ *
+ * Structure tables (int32, device):
+ *   region_scope [2R][pmax]  input indices of region q: leaf-0 pixels first, then leaf-1
+ *   region_n0    [2R]        number of leaf-0 pixels
+ *   region_n     [2R]        number of pixels of the region
+ *   pix_slot     [D][R]      for input p and repetition r: q*pmax + position in region_scope
+ * Region 2r is the first input of root product r, region 2r+1 the second.
+ * Packed parameters: leaf [2R*pmax][3][GP]; wlin/wlog [2R][G*G][SP]; rlin/rlog [R][S*S].
+ * Saved activations: leaf_val [2R*2*G][npad], sum_val [2R*S][npad], npad = N rounded up to 32.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t D, R, G, S, pmax;
+    const int32_t* region_scope;
+    const int32_t* region_n0;
+    const int32_t* region_n;
+    const int32_t* pix_slot;
+} stove_spn2_struct;
+
+int stove_spn2_fwd(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg,
+                   const float* leaf, const float* wlin, const float* wlog,
+                   const float* rlin, const float* rlog,
+                   float* leaf_val, float* sum_val, float* out, void* stream);
+size_t stove_spn2_bwd_workspace(const stove_spn2_struct* st, int64_t N);
+/* g_x / g_marg may be NULL.  g_leaf, g_wlog, g_rlog are accumulated. */
+int stove_spn2_bwd(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg,
+                   const float* leaf, const float* wlin, const float* wlog,
+                   const float* rlin, const float* rlog,
+                   const float* leaf_val, const float* sum_val, const float* out, const float* g_out,
+                   float* g_x, float* g_marg, float* g_leaf, float* g_wlog, float* g_rlog,
+                   void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Background SPN ("D1" structure: R root partitions, each the product of two Gauss
+ * leaves that split all D inputs), probabilistic_models.py:25-39.
+ *   side [D][R]   0/1: which leaf of repetition r owns input p (0 = first product input)
+ * Packed: leaf [D*R][3][GP]; rlin/rlog [R][G*G].  Saved: leaf_val [R*2*G][npad].
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t D, R, G;
+    const int32_t* side;
+} stove_spn1_struct;
+
+size_t stove_spn1_fwd_workspace(const stove_spn1_struct* st, int64_t N);
+int stove_spn1_fwd(const stove_spn1_struct* st, int64_t N, const float* x, const float* marg,
+                   const float* leaf, const float* rlin, const float* rlog,
+                   float* leaf_val, float* out, void* workspace, void* stream);
+size_t stove_spn1_bwd_workspace(const stove_spn1_struct* st, int64_t N);
+int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const float* x, const float* marg,
+                   const float* leaf, const float* rlin, const float* rlog,
+                   const float* leaf_val, const float* out, const float* g_out,
+                   float* g_x, float* g_marg, float* g_leaf, float* g_rlog,
+                   void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Glimpse + marginalisation masks: Supair.patches_from_z (supair.py:241-276) and
+ * Supair.masks_from_z (supair.py:278-356), one launch for all objects of a frame.
+ *   img [F][C][A][B], z [F][O][4] = (sx, sy, x, y)
+ *   patches, marg_patch [F*O][C][pa][pb];  marg_bg [F][C][A][B];  overlap [F][O]
+ * x walks the last image axis, y the second-to-last (supair.py:244-247).
+ * The backward returns d/dz only (frames are data).
+ * ---------------------------------------------------------------------------------- */
+int stove_scene_fwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners,
+                    const float* img, const float* z,
+                    float* patches, float* marg_patch, float* marg_bg, float* overlap, void* stream);
+int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners,
+                    const float* img, const float* z,
+                    const float* g_patches, const float* g_marg_patch, const float* g_marg_bg,
+                    const float* g_overlap, float* g_z, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * GNN dynamics: Dynamics.forward + core (dynamics.py:181-265) for core_idx 0, and the
+ * rollout loop Stove.rollout (stove.py:777-861).
+ *
+ * Weights: one flat buffer, every matrix stored [in][out]; order
+ *   [act_emb W (A x O*4), b]            if action_dim > 0
+ *   enc W (in_dim x cl), b
+ *   self0, self1 (cl x cl)
+ *   rel0|att0 (2cl+1 x 4cl: rel columns first), b (4cl)
+ *   rel1 (2cl x cl), att1 (2cl x cl), rel2 (cl x cl), att2 (cl x 1)
+ *   aff0, aff1, aff2 (cl x cl), out0 (2cl x cl), out1 (cl x cl)
+ *   [rew00, rew02 (cl x cl), rew10 (cl x cl/2), rew12 (cl/2 x cl/4), rew14 (cl/4 x 1)] if reward
+ * each followed by its bias.  `stove_gnn_weight_count` returns the float count.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t num_obj;      /* O */
+    int32_t cl;           /* 32 */
+    int32_t action_dim;   /* A, 0 = not action conditioned */
+    int32_t app_dim;      /* 3 if appearances are concatenated, else 0 */
+    int32_t reward;       /* 1 = reward head present */
+    int32_t lim_enc;      /* raw pass-through dims (2) */
+    int32_t nonlin;       /* 0 = leaky_relu(0.01) (reference default), 1 = elu */
+} stove_gnn_cfg;
+
+int64_t stove_gnn_weight_count(const stove_gnn_cfg* cfg);
+/* float offsets of every weight/bias segment (each padded to a multiple of 4 floats), in the
+ * order act, enc, self0, self1, rel0|att0, rel1, att1, rel2, att2, aff0, aff1, aff2, out0,
+ * out1, rew00, rew02, rew10, rew12, rew14 (w then b each; -1 if absent), then the total.
+ * Returns the number of entries written (39). */
+int stove_gnn_weight_offsets(const stove_gnn_cfg* cfg, int32_t* out, int max_out);
+size_t stove_gnn_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n);
+/* s [n][O][cl/2], actions [n][A] or NULL, app [n][O][app_dim] or NULL
+ * -> out [n][O][cl], reward [n] (sigmoid applied; NULL if no reward head) */
+int stove_gnn_fwd(const stove_gnn_cfg* cfg, int64_t n, const float* s, const float* actions,
+                  const float* app, const float* weights, float* out, float* reward, void* stream);
+/* g_weights is overwritten (not accumulated). g_reward may be NULL. */
+int stove_gnn_bwd(const stove_gnn_cfg* cfg, int64_t n, const float* s, const float* actions,
+                  const float* app, const float* weights, const float* g_out, const float* g_reward,
+                  float* g_s, float* g_weights, void* workspace, void* stream);
+/* z_last [n][O][cl/2+2]; actions [n][L][A] (wrapped modulo L) or NULL; app [n][O][app_dim]
+ * or NULL; noise [n][num][O][cl/2] or NULL (=> mean prediction).
+ * z_out [n][num][O][cl/2+2]; std_out / logq_out [n][num][O][cl/2] or NULL;
+ * rewards [n][num] or NULL. */
+int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, const float* z_last,
+                      const float* actions, int action_len, const float* app, const float* weights,
+                      const float* noise, float pos_var, float vel_std, float latent_std,
+                      float* z_out, float* std_out, float* logq_out, float* rewards, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI declared in include/stove_b200.h.
+
+There is deliberately no fallback: if the library is missing or a call fails, a
+RuntimeError is raised.  Nothing here imports `oracle/`.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libstove_b200.so')
+_lib = None
+
+c_f = C.c_void_p          # device pointers travel as integers
+i32, i64, f32, vp, sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
+
+
+class Spn2Struct(C.Structure):
+    _fields_ = [('D', i32), ('R', i32), ('G', i32), ('S', i32), ('pmax', i32),
+                ('region_scope', vp), ('region_n0', vp), ('region_n', vp), ('pix_slot', vp)]
+
+
+class Spn1Struct(C.Structure):
+    _fields_ = [('D', i32), ('R', i32), ('G', i32), ('side', vp)]
+
+
+class GnnCfg(C.Structure):
+    _fields_ = [('num_obj', i32), ('cl', i32), ('action_dim', i32), ('app_dim', i32),
+                ('reward', i32), ('lim_enc', i32), ('nonlin', i32)]
+
+
+P2, P1, PG = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg)
+
+# name -> (restype, argtypes); must list every symbol of include/stove_b200.h
+SIGNATURES = {
+    'stove_last_error': (C.c_char_p, []),
+    'stove_abi_version': (C.c_int, []),
+    'stove_bw_transform': (C.c_int, [vp, vp, i64, C.c_int, i64, vp]),
+    'stove_spn_pack_leaf_fwd': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp]),
+    'stove_spn_pack_leaf_bwd': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp, vp, vp]),
+    'stove_spn_pack_sum_fwd': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    'stove_spn_pack_sum_bwd': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
+    'stove_spn2_fwd': (C.c_int, [P2, i64] + [vp] * 10 + [vp]),
+    'stove_spn2_bwd_workspace': (sz, [P2, i64]),
+    'stove_spn2_bwd': (C.c_int, [P2, i64] + [vp] * 17 + [vp]),
+    'stove_spn1_fwd_workspace': (sz, [P1, i64]),
+    'stove_spn1_fwd': (C.c_int, [P1, i64] + [vp] * 8 + [vp]),
+    'stove_spn1_bwd_workspace': (sz, [P1, i64]),
+    'stove_spn1_bwd': (C.c_int, [P1, i64] + [vp] * 13 + [vp]),
+    'stove_scene_fwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 6 + [vp]),
+    'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
+    'stove_gnn_weight_count': (i64, [PG]),
+    'stove_gnn_weight_offsets': (C.c_int, [PG, vp, C.c_int]),
+    'stove_gnn_bwd_workspace': (sz, [PG, i64]),
+    'stove_gnn_fwd': (C.c_int, [PG, i64] + [vp] * 6 + [vp]),
+    'stove_gnn_bwd': (C.c_int, [PG, i64] + [vp] * 9 + [vp]),
+    'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
+                                    vp, vp, vp, vp, vp]),
+}
+
+
+def lib():
+    """Load (once) and return the native library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'stove_b200: native library %s is missing -- run `python -m stove_b200.build` '
+                '(there is no CPU / PyTorch fallback for the hot path)' % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('stove_b200 native call failed (%d): %s'
+                           % (rc, lib().stove_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('stove_b200 kernels need CUDA tensors (got a %s tensor); there is no '
+                               'CPU path' % t.device)
+        if t.dtype != torch.float32:
+            raise RuntimeError('stove_b200 kernels compute in fp32 (got %s)' % t.dtype)

@@ -1,0 +1,47 @@
+// Shared helpers for the stove_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/stove_b200.h"
+
+#define HALF_LOG_2PI 0.91893853320467274178f
+// below this a linear-domain mixture sum is recomputed exactly in the log domain
+#define LIN_SUM_FLOOR 1e-30f
+
+void stove_set_error(const char* fmt, ...);
+
+#define STOVE_CHECK_ARG(cond, msg)                                  \
+    do {                                                            \
+        if (!(cond)) {                                              \
+            stove_set_error("%s: %s", __func__, msg);               \
+            return STOVE_ERR_ARG;                                   \
+        }                                                           \
+    } while (0)
+
+#define STOVE_CUDA(call)                                                              \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            stove_set_error("%s: %s -> %s", __func__, #call, cudaGetErrorString(e_)); \
+            return STOVE_ERR_CUDA;                                                    \
+        }                                                                             \
+    } while (0)
+
+#define STOVE_LAUNCH_CHECK() STOVE_CUDA(cudaGetLastError())
+
+static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }

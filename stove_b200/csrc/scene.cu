@@ -1,0 +1,339 @@
+// Glimpse extraction + sequential marginalisation masks, forward and backward (d/dz).
+//
+// Replaces Supair.patches_from_z (model/video_prediction/supair.py:241-276) and
+// Supair.masks_from_z (:278-356): per object  F.affine_grid + F.grid_sample  (bilinear, zero
+// padding) of the frame, of the inverted running background, and of a ones image pasted back
+// with the inverse transform, followed by clamp.  The reference launches 4 grid ops per
+// object and materialises an O-fold copy of every frame (supair.py:262-263); here one CTA
+// owns one frame, keeps the frame and the running background in shared memory and walks the
+// objects in order.  The paste of a ones image is separable -- tent(py) * tent(px) -- so it
+// needs A + B evaluations instead of A * B bilinear samples.
+//
+// Coordinates: x walks the LAST image axis (length B), y the
+// second-to-last (length A).  align_corners selects torch-1.0.1 semantics.
+// Backward formulas: tests/kernel_spec.py (checked against autograd of the oracle).
+#include "common.cuh"
+
+struct SceneDims {
+    int O, C, A, B, pa, pb, align;
+};
+
+__device__ __forceinline__ float base_coord(int k, int n_out, int align) {
+    if (align) return (n_out > 1) ? (2.f * k) / (float)(n_out - 1) - 1.f : -1.f;
+    return (2.f * k + 1.f) / (float)n_out - 1.f;
+}
+__device__ __forceinline__ float unnorm(float g, int L, int align) {
+    return align ? (g + 1.f) * 0.5f * (float)(L - 1) : ((g + 1.f) * (float)L - 1.f) * 0.5f;
+}
+__device__ __forceinline__ float unnorm_slope(int L, int align) {
+    return align ? 0.5f * (float)(L - 1) : 0.5f * (float)L;
+}
+// bilinear sample of an all-ones row of length L with zero padding, and its derivative
+__device__ __forceinline__ void tent(float p, int L, float& val, float& der) {
+    const float x0 = floorf(p);
+    const float f = p - x0;
+    const float in0 = (x0 >= 0.f && x0 <= (float)(L - 1)) ? 1.f : 0.f;
+    const float in1 = (x0 + 1.f >= 0.f && x0 + 1.f <= (float)(L - 1)) ? 1.f : 0.f;
+    val = (1.f - f) * in0 + f * in1;
+    der = in1 - in0;
+}
+
+struct Corner {
+    int y0, x0;
+    float fy, fx;
+    bool oky0, oky1, okx0, okx1;
+};
+__device__ __forceinline__ Corner corners(float py, float px, int A, int B) {
+    Corner c;
+    const float fy0 = floorf(py), fx0 = floorf(px);
+    c.fy = py - fy0;
+    c.fx = px - fx0;
+    // clamp before the int conversion so far-away boxes cannot overflow
+    c.y0 = (int)fminf(fmaxf(fy0, -2.f), (float)A);
+    c.x0 = (int)fminf(fmaxf(fx0, -2.f), (float)B);
+    c.oky0 = c.y0 >= 0 && c.y0 < A;
+    c.oky1 = c.y0 + 1 >= 0 && c.y0 + 1 < A;
+    c.okx0 = c.x0 >= 0 && c.x0 < B;
+    c.okx1 = c.x0 + 1 >= 0 && c.x0 + 1 < B;
+    return c;
+}
+// value and d/dpy, d/dpx of the bilinear sample of `im` (A x B, zero padded); if INVERT the
+// sampled image is (1 - im)
+template <bool INVERT>
+__device__ __forceinline__ void bilinear(const float* im, int B, const Corner& c, float& val, float& dy,
+                                         float& dx) {
+    float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f;
+    if (c.oky0 && c.okx0) v00 = INVERT ? 1.f - im[c.y0 * B + c.x0] : im[c.y0 * B + c.x0];
+    if (c.oky0 && c.okx1) v01 = INVERT ? 1.f - im[c.y0 * B + c.x0 + 1] : im[c.y0 * B + c.x0 + 1];
+    if (c.oky1 && c.okx0) v10 = INVERT ? 1.f - im[(c.y0 + 1) * B + c.x0] : im[(c.y0 + 1) * B + c.x0];
+    if (c.oky1 && c.okx1) v11 = INVERT ? 1.f - im[(c.y0 + 1) * B + c.x0 + 1] : im[(c.y0 + 1) * B + c.x0 + 1];
+    const float top = v00 + c.fx * (v01 - v00), bot = v10 + c.fx * (v11 - v10);
+    val = top + c.fy * (bot - top);
+    dy = bot - top;
+    dx = (1.f - c.fy) * (v01 - v00) + c.fy * (v11 - v10);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nwarp; ++w) t += red[w];
+    return t;
+}
+
+// tents of the paste of object (sx, sy, tx, ty): tX[v], tY[u] (+ derivatives if dX != null)
+__device__ __forceinline__ void paste_tents(const SceneDims& d, float sx, float sy, float tx, float ty,
+                                            float* tX, float* tY, float* dX, float* dY) {
+    const float isx = 1.f / sx, isy = 1.f / sy, cx = -tx / sx, cy = -ty / sy;
+    for (int k = threadIdx.x; k < d.A + d.B; k += blockDim.x) {
+        float val, der;
+        if (k < d.B) {
+            tent(unnorm(isx * base_coord(k, d.B, d.align) + cx, d.B, d.align), d.B, val, der);
+            tX[k] = val;
+            if (dX) dX[k] = der;
+        } else {
+            const int u = k - d.B;
+            tent(unnorm(isy * base_coord(u, d.A, d.align) + cy, d.A, d.align), d.A, val, der);
+            tY[u] = val;
+            if (dY) dY[u] = der;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scene_fwd_kernel(SceneDims d, const float* __restrict__ img,
+                                                        const float* __restrict__ z,
+                                                        float* __restrict__ patches,
+                                                        float* __restrict__ marg_patch,
+                                                        float* __restrict__ marg_bg,
+                                                        float* __restrict__ overlap) {
+    extern __shared__ float smem[];
+    const int AB = d.A * d.B, PP = d.pa * d.pb;
+    float* ims = smem;                 // [C][AB]
+    float* bg = ims + d.C * AB;        // [AB]
+    float* tX = bg + AB;               // [B]
+    float* tY = tX + d.B;              // [A]
+    float* red = tY + d.A;             // [32]
+    const int64_t f = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < d.C * AB; i += blockDim.x) ims[i] = __ldg(img + f * d.C * AB + i);
+    for (int i = tid; i < AB; i += blockDim.x) bg[i] = 0.f;
+    __syncthreads();
+    for (int o = 0; o < d.O; ++o) {
+        const float* zo = z + (f * d.O + o) * 4;
+        const float sx = __ldg(zo), sy = __ldg(zo + 1), tx = __ldg(zo + 2), ty = __ldg(zo + 3);
+        float msum = 0.f;
+        for (int idx = tid; idx < PP; idx += blockDim.x) {
+            const int i = idx / d.pb, j = idx - i * d.pb;
+            const float px = unnorm(sx * base_coord(j, d.pb, d.align) + tx, d.B, d.align);
+            const float py = unnorm(sy * base_coord(i, d.pa, d.align) + ty, d.A, d.align);
+            const Corner c = corners(py, px, d.A, d.B);
+            float val, dy, dx;
+            bilinear<true>(bg, d.B, c, val, dy, dx);
+            const float mg = 1.f - val;
+            msum += mg;
+            const int64_t ob = (f * d.O + o) * d.C;
+            for (int ch = 0; ch < d.C; ++ch) {
+                bilinear<false>(ims + ch * AB, d.B, c, val, dy, dx);
+                patches[(ob + ch) * PP + idx] = val;
+                marg_patch[(ob + ch) * PP + idx] = mg;
+            }
+        }
+        paste_tents(d, sx, sy, tx, ty, tX, tY, nullptr, nullptr);
+        msum = block_sum(msum, red);      // also orders the bg reads / tent writes before the update
+        if (tid == 0) overlap[f * d.O + o] = msum / (float)PP;
+        for (int i = tid; i < AB; i += blockDim.x) {
+            const int u = i / d.B, v = i - u * d.B;
+            bg[i] = fminf(fmaxf(bg[i] + tY[u] * tX[v], 0.f), 1.f);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < d.C * AB; i += blockDim.x) marg_bg[f * d.C * AB + i] = bg[i % AB];
+}
+
+// ------------------------------------------------------------------------------------
+// backward (d/dz)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float* __restrict__ img,
+                                                        const float* __restrict__ z,
+                                                        const float* __restrict__ g_patches,
+                                                        const float* __restrict__ g_marg_patch,
+                                                        const float* __restrict__ g_marg_bg,
+                                                        const float* __restrict__ g_overlap,
+                                                        float* __restrict__ g_z) {
+    extern __shared__ float smem[];
+    const int AB = d.A * d.B, PP = d.pa * d.pb;
+    float* ims = smem;                  // [C][AB]
+    float* bgs = ims + d.C * AB;        // [O][AB] background before object o
+    float* Gb = bgs + d.O * AB;         // [AB] running gradient w.r.t. the background
+    float* tX = Gb + AB;
+    float* dX = tX + d.B;
+    float* gpx = dX + d.B;
+    float* tY = gpx + d.B;
+    float* dY = tY + d.A;
+    float* gpy = dY + d.A;
+    float* red = gpy + d.A;             // [32]
+    const int64_t f = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < d.C * AB; i += blockDim.x) ims[i] = __ldg(img + f * d.C * AB + i);
+    for (int i = tid; i < AB; i += blockDim.x) bgs[i] = 0.f;
+    __syncthreads();
+    // replay the forward background states
+    for (int o = 0; o + 1 < d.O; ++o) {
+        const float* zo = z + (f * d.O + o) * 4;
+        paste_tents(d, __ldg(zo), __ldg(zo + 1), __ldg(zo + 2), __ldg(zo + 3), tX, tY, nullptr, nullptr);
+        __syncthreads();
+        for (int i = tid; i < AB; i += blockDim.x) {
+            const int u = i / d.B, v = i - u * d.B;
+            bgs[(o + 1) * AB + i] = fminf(fmaxf(bgs[o * AB + i] + tY[u] * tX[v], 0.f), 1.f);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < AB; i += blockDim.x) {
+        float g = 0.f;
+        if (g_marg_bg)
+            for (int ch = 0; ch < d.C; ++ch) g += __ldg(g_marg_bg + (f * d.C + ch) * AB + i);
+        Gb[i] = g;
+    }
+    __syncthreads();
+    const float kB = unnorm_slope(d.B, d.align), kA = unnorm_slope(d.A, d.align);
+    for (int o = d.O - 1; o >= 0; --o) {
+        const float* zo = z + (f * d.O + o) * 4;
+        const float sx = __ldg(zo), sy = __ldg(zo + 1), tx = __ldg(zo + 2), ty = __ldg(zo + 3);
+        const float* bgo = bgs + o * AB;
+        paste_tents(d, sx, sy, tx, ty, tX, tY, dX, dY);
+        __syncthreads();
+        // clamp backward: pass where 0 <= bg + paste <= 1
+        for (int i = tid; i < AB; i += blockDim.x) {
+            const int u = i / d.B, v = i - u * d.B;
+            const float pre = bgo[i] + tY[u] * tX[v];
+            if (!(pre >= 0.f && pre <= 1.f)) Gb[i] = 0.f;
+        }
+        __syncthreads();
+        // paste = tY[u] * tX[v]
+        for (int k = tid; k < d.A + d.B; k += blockDim.x) {
+            float acc = 0.f;
+            if (k < d.B) {
+                for (int u = 0; u < d.A; ++u) acc = fmaf(Gb[u * d.B + k], tY[u], acc);
+                gpx[k] = acc * dX[k];
+            } else {
+                const int u = k - d.B;
+                for (int v = 0; v < d.B; ++v) acc = fmaf(Gb[u * d.B + v], tX[v], acc);
+                gpy[u] = acc * dY[u];
+            }
+        }
+        __syncthreads();
+        float gsx = 0.f, gsy = 0.f, gtx = 0.f, gty = 0.f;
+        for (int k = tid; k < d.A + d.B; k += blockDim.x) {
+            if (k < d.B) {
+                const float xb = base_coord(k, d.B, d.align);
+                gsx += gpx[k] * kB * (-(xb - tx) / (sx * sx));
+                gtx += gpx[k] * kB * (-1.f / sx);
+            } else {
+                const int u = k - d.B;
+                const float yb = base_coord(u, d.A, d.align);
+                gsy += gpy[u] * kA * (-(yb - ty) / (sy * sy));
+                gty += gpy[u] * kA * (-1.f / sy);
+            }
+        }
+        // glimpse + mask sampling points
+        const float gov = g_overlap ? __ldg(g_overlap + f * d.O + o) / (float)PP : 0.f;
+        const int64_t ob = (f * d.O + o) * d.C;
+        for (int idx = tid; idx < PP; idx += blockDim.x) {
+            const int i = idx / d.pb, j = idx - i * d.pb;
+            const float xb = base_coord(j, d.pb, d.align), yb = base_coord(i, d.pa, d.align);
+            const float px = unnorm(sx * xb + tx, d.B, d.align), py = unnorm(sy * yb + ty, d.A, d.align);
+            const Corner c = corners(py, px, d.A, d.B);
+            float gm = gov;
+            if (g_marg_patch)
+                for (int ch = 0; ch < d.C; ++ch) gm += __ldg(g_marg_patch + (ob + ch) * PP + idx);
+            float val, my, mx;
+            bilinear<true>(bgo, d.B, c, val, my, mx);
+            float dpx = -gm * mx, dpy = -gm * my;
+            if (g_patches)
+                for (int ch = 0; ch < d.C; ++ch) {
+                    float qy, qx;
+                    bilinear<false>(ims + ch * AB, d.B, c, val, qy, qx);
+                    const float gp = __ldg(g_patches + (ob + ch) * PP + idx);
+                    dpx = fmaf(gp, qx, dpx);
+                    dpy = fmaf(gp, qy, dpy);
+                }
+            gsx += dpx * kB * xb;
+            gtx += dpx * kB;
+            gsy += dpy * kA * yb;
+            gty += dpy * kA;
+            // d marg / d bg_o = + bilinear weights
+            if (gm != 0.f) {
+                const float wy0 = 1.f - c.fy, wy1 = c.fy, wx0 = 1.f - c.fx, wx1 = c.fx;
+                if (c.oky0 && c.okx0) atomicAdd(&Gb[c.y0 * d.B + c.x0], gm * wy0 * wx0);
+                if (c.oky0 && c.okx1) atomicAdd(&Gb[c.y0 * d.B + c.x0 + 1], gm * wy0 * wx1);
+                if (c.oky1 && c.okx0) atomicAdd(&Gb[(c.y0 + 1) * d.B + c.x0], gm * wy1 * wx0);
+                if (c.oky1 && c.okx1) atomicAdd(&Gb[(c.y0 + 1) * d.B + c.x0 + 1], gm * wy1 * wx1);
+            }
+        }
+        gsx = block_sum(gsx, red);
+        gsy = block_sum(gsy, red);
+        gtx = block_sum(gtx, red);
+        gty = block_sum(gty, red);
+        if (tid == 0) {
+            float* dst = g_z + (f * d.O + o) * 4;
+            dst[0] = gsx; dst[1] = gsy; dst[2] = gtx; dst[3] = gty;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+static int scene_check(int64_t F, int O, int C, int A, int B, int pa, int pb) {
+    STOVE_CHECK_ARG(F >= 0 && O > 0 && C > 0 && A > 0 && B > 0 && pa > 0 && pb > 0, "bad sizes");
+    return STOVE_OK;
+}
+
+extern "C" int stove_scene_fwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners,
+                               const float* img, const float* z, float* patches, float* marg_patch,
+                               float* marg_bg, float* overlap, void* stream) {
+    int rc = scene_check(F, O, C, A, B, pa, pb);
+    if (rc) return rc;
+    STOVE_CHECK_ARG(img && z && patches && marg_patch && marg_bg && overlap, "null pointer");
+    if (F == 0) return STOVE_OK;
+    SceneDims d{O, C, A, B, pa, pb, align_corners};
+    const size_t smem = sizeof(float) * ((size_t)(C + 1) * A * B + A + B + 32);
+    if (smem > 227 * 1024) {
+        stove_set_error("stove_scene_fwd: frame too large for shared memory (%zu B)", smem);
+        return STOVE_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+        STOVE_CUDA(cudaFuncSetAttribute(scene_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scene_fwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, patches, marg_patch, marg_bg, overlap);
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners,
+                               const float* img, const float* z, const float* g_patches,
+                               const float* g_marg_patch, const float* g_marg_bg, const float* g_overlap,
+                               float* g_z, void* stream) {
+    int rc = scene_check(F, O, C, A, B, pa, pb);
+    if (rc) return rc;
+    STOVE_CHECK_ARG(img && z && g_z, "null pointer");
+    if (F == 0) return STOVE_OK;
+    SceneDims d{O, C, A, B, pa, pb, align_corners};
+    const size_t smem = sizeof(float) * ((size_t)(C + O + 1) * A * B + 3 * (A + B) + 32);
+    if (smem > 227 * 1024) {
+        stove_set_error("stove_scene_bwd: frame/objects too large for shared memory (%zu B)", smem);
+        return STOVE_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+        STOVE_CUDA(cudaFuncSetAttribute(scene_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scene_bwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, g_patches, g_marg_patch,
+                                                                       g_marg_bg, g_overlap, g_z);
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -1,0 +1,282 @@
+"""torch.autograd wrappers around the C ABI (include/stove_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; all
+arithmetic of the hot path happens in the CUDA kernels of stove_b200/csrc.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+
+def _c(t):
+    return None if t is None else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# bw_transform (model/utils/utils.py:10-15)
+# ----------------------------------------------------------------------------------------
+def bw_transform(x):
+    """(n, T, C, W, H) -> (n, T, 1, W, H): sum colour channels, clamp to [0, 1]."""
+    N.require_cuda_f32(x)
+    x = x.contiguous()
+    n, T, ch, w, h = x.shape
+    y = torch.empty(n, T, 1, w, h, device=x.device, dtype=x.dtype)
+    N.check(N.lib().stove_bw_transform(N.ptr(x), N.ptr(y), n * T, ch, w * h, N.stream()))
+    return y
+
+
+# ----------------------------------------------------------------------------------------
+# SPN parameter packing
+# ----------------------------------------------------------------------------------------
+class PackLeaf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, sigma, dst_row, GP, prow_total, vmin, vmax):
+        means, sigma = means.contiguous(), sigma.contiguous()
+        N.require_cuda_f32(means, sigma)
+        rows, G = means.shape
+        packed = torch.zeros(prow_total, 3, GP, device=means.device, dtype=means.dtype)
+        N.check(N.lib().stove_spn_pack_leaf_fwd(N.ptr(means), N.ptr(sigma), N.ptr(dst_row), rows, G, GP,
+                                                vmin, vmax, N.ptr(packed), N.stream()))
+        ctx.save_for_backward(sigma, dst_row)
+        ctx.meta = (rows, G, GP, vmin, vmax)
+        return packed
+
+    @staticmethod
+    def backward(ctx, g_packed):
+        sigma, dst_row = ctx.saved_tensors
+        rows, G, GP, vmin, vmax = ctx.meta
+        g_packed = g_packed.contiguous()
+        g_means = torch.empty(rows, G, device=sigma.device, dtype=sigma.dtype)
+        g_sigma = torch.empty_like(g_means)
+        N.check(N.lib().stove_spn_pack_leaf_bwd(N.ptr(sigma), N.ptr(dst_row), rows, G, GP, vmin, vmax,
+                                                N.ptr(g_packed), N.ptr(g_means), N.ptr(g_sigma), N.stream()))
+        return g_means, g_sigma, None, None, None, None, None
+
+
+class PackSum(torch.autograd.Function):
+    """raw [nb, K, S] -> (wlog, wlin) [nb, K, SP]; only wlog carries gradient (w.r.t. log-weights)."""
+
+    @staticmethod
+    def forward(ctx, raw, SP):
+        raw = raw.contiguous()
+        N.require_cuda_f32(raw)
+        nb, K, S = raw.shape
+        wlog = torch.zeros(nb, K, SP, device=raw.device, dtype=raw.dtype)
+        wlin = torch.zeros_like(wlog)
+        N.check(N.lib().stove_spn_pack_sum_fwd(N.ptr(raw), nb, K, S, SP, N.ptr(wlog), N.ptr(wlin), N.stream()))
+        ctx.save_for_backward(wlog)
+        ctx.meta = (nb, K, S, SP)
+        ctx.mark_non_differentiable(wlin)
+        return wlog, wlin
+
+    @staticmethod
+    def backward(ctx, g_wlog, _g_wlin):
+        (wlog,) = ctx.saved_tensors
+        nb, K, S, SP = ctx.meta
+        g_wlog = g_wlog.contiguous()
+        g_raw = torch.empty(nb, K, S, device=wlog.device, dtype=wlog.dtype)
+        N.check(N.lib().stove_spn_pack_sum_bwd(N.ptr(wlog), nb, K, S, SP, N.ptr(g_wlog), N.ptr(g_raw), N.stream()))
+        return g_raw, None
+
+
+# ----------------------------------------------------------------------------------------
+# fused SPNs
+# ----------------------------------------------------------------------------------------
+def _npad(n):
+    return (n + 31) // 32 * 32
+
+
+class Spn2(torch.autograd.Function):
+    """Object SPN (D2 structure).  `tables` keeps the int32 structure tensors alive."""
+
+    @staticmethod
+    def forward(ctx, x, marg, leaf, wlog, wlin, rlog, rlin, tables):
+        x, marg = _c(x), _c(marg)
+        N.require_cuda_f32(x, marg, leaf, wlog, wlin, rlog, rlin)
+        st = tables.cstruct
+        n = x.shape[0]
+        npad = _npad(max(n, 1))
+        Q, G, S = 2 * st.R, st.G, st.S
+        leaf_val = torch.empty(Q * 2 * G, npad, device=x.device, dtype=x.dtype)
+        sum_val = torch.empty(Q * S, npad, device=x.device, dtype=x.dtype)
+        out = torch.empty(n, device=x.device, dtype=x.dtype)
+        N.check(N.lib().stove_spn2_fwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(wlin),
+                                       N.ptr(wlog), N.ptr(rlin), N.ptr(rlog), N.ptr(leaf_val),
+                                       N.ptr(sum_val), N.ptr(out), N.stream()))
+        ctx.save_for_backward(x, marg, leaf, wlog, wlin, rlog, rlin, leaf_val, sum_val, out)
+        ctx.tables = tables
+        ctx.has_marg = marg is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, marg, leaf, wlog, wlin, rlog, rlin, leaf_val, sum_val, out = ctx.saved_tensors
+        st = ctx.tables.cstruct
+        n = x.shape[0]
+        g_out = g_out.contiguous()
+        need_x, need_m = ctx.needs_input_grad[0], ctx.has_marg and ctx.needs_input_grad[1]
+        g_x = torch.empty_like(x) if need_x else None
+        g_m = torch.empty_like(marg) if need_m else None
+        g_leaf = torch.zeros_like(leaf)
+        g_wlog = torch.zeros_like(wlog)
+        g_rlog = torch.zeros_like(rlog)
+        ws = torch.empty(max(N.lib().stove_spn2_bwd_workspace(C.byref(st), n), 4) // 4, device=x.device,
+                         dtype=torch.float32)
+        N.check(N.lib().stove_spn2_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(wlin),
+                                       N.ptr(wlog), N.ptr(rlin), N.ptr(rlog), N.ptr(leaf_val), N.ptr(sum_val),
+                                       N.ptr(out), N.ptr(g_out), N.ptr(g_x), N.ptr(g_m), N.ptr(g_leaf),
+                                       N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(ws), N.stream()))
+        return g_x, g_m, g_leaf, g_wlog, None, g_rlog, None, None
+
+
+class Spn1(torch.autograd.Function):
+    """Background SPN (D1 structure)."""
+
+    @staticmethod
+    def forward(ctx, x, marg, leaf, rlog, rlin, tables):
+        x, marg = _c(x), _c(marg)
+        N.require_cuda_f32(x, marg, leaf, rlog, rlin)
+        st = tables.cstruct
+        n = x.shape[0]
+        npad = _npad(max(n, 1))
+        leaf_val = torch.empty(st.R * 2 * st.G, npad, device=x.device, dtype=x.dtype)
+        out = torch.empty(n, device=x.device, dtype=x.dtype)
+        ws = torch.empty(max(N.lib().stove_spn1_fwd_workspace(C.byref(st), n), 4) // 4, device=x.device,
+                         dtype=torch.float32)
+        N.check(N.lib().stove_spn1_fwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(rlin),
+                                       N.ptr(rlog), N.ptr(leaf_val), N.ptr(out), N.ptr(ws), N.stream()))
+        ctx.save_for_backward(x, marg, leaf, rlog, rlin, leaf_val, out)
+        ctx.tables = tables
+        ctx.has_marg = marg is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, marg, leaf, rlog, rlin, leaf_val, out = ctx.saved_tensors
+        st = ctx.tables.cstruct
+        n = x.shape[0]
+        g_out = g_out.contiguous()
+        need_x, need_m = ctx.needs_input_grad[0], ctx.has_marg and ctx.needs_input_grad[1]
+        g_x = torch.empty_like(x) if need_x else None
+        g_m = torch.empty_like(marg) if need_m else None
+        g_leaf = torch.zeros_like(leaf)
+        g_rlog = torch.zeros_like(rlog)
+        ws = torch.empty(max(N.lib().stove_spn1_bwd_workspace(C.byref(st), n), 4) // 4, device=x.device,
+                         dtype=torch.float32)
+        N.check(N.lib().stove_spn1_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(rlin),
+                                       N.ptr(rlog), N.ptr(leaf_val), N.ptr(out), N.ptr(g_out), N.ptr(g_x),
+                                       N.ptr(g_m), N.ptr(g_leaf), N.ptr(g_rlog), N.ptr(ws), N.stream()))
+        return g_x, g_m, g_leaf, g_rlog, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# glimpse + masks
+# ----------------------------------------------------------------------------------------
+class Scene(torch.autograd.Function):
+    """img (F, C, A, B), z (F, O, 4) -> patches (F*O, C, pa, pb), marg_patch (same),
+    marg_bg (F, C, A, B), overlap (F, O).  Differentiable w.r.t. z only."""
+
+    @staticmethod
+    def forward(ctx, img, z, pa, pb, align_corners):
+        img, z = img.contiguous(), z.contiguous()
+        N.require_cuda_f32(img, z)
+        F_, Cc, A, B = img.shape
+        O = z.shape[1]
+        dev, dt = img.device, img.dtype
+        patches = torch.empty(F_ * O, Cc, pa, pb, device=dev, dtype=dt)
+        marg_patch = torch.empty_like(patches)
+        marg_bg = torch.empty(F_, Cc, A, B, device=dev, dtype=dt)
+        overlap = torch.empty(F_, O, device=dev, dtype=dt)
+        N.check(N.lib().stove_scene_fwd(F_, O, Cc, A, B, pa, pb, int(align_corners), N.ptr(img), N.ptr(z),
+                                        N.ptr(patches), N.ptr(marg_patch), N.ptr(marg_bg), N.ptr(overlap),
+                                        N.stream()))
+        ctx.save_for_backward(img, z)
+        ctx.meta = (F_, O, Cc, A, B, pa, pb, int(align_corners))
+        return patches, marg_patch, marg_bg, overlap
+
+    @staticmethod
+    def backward(ctx, g_patches, g_marg_patch, g_marg_bg, g_overlap):
+        img, z = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
+                                      '(frames are data on the STOVE hot path)')
+        F_, O, Cc, A, B, pa, pb, ac = ctx.meta
+        g_z = torch.empty_like(z)
+        N.check(N.lib().stove_scene_bwd(F_, O, Cc, A, B, pa, pb, ac, N.ptr(img), N.ptr(z),
+                                        N.ptr(_c(g_patches)), N.ptr(_c(g_marg_patch)), N.ptr(_c(g_marg_bg)),
+                                        N.ptr(_c(g_overlap)), N.ptr(g_z), N.stream()))
+        return None, g_z, None, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# GNN dynamics
+# ----------------------------------------------------------------------------------------
+GNN_SEGMENTS = ['act', 'enc', 'self0', 'self1', 'ra0', 'rel1', 'att1', 'rel2', 'att2', 'aff0', 'aff1',
+                'aff2', 'out0', 'out1', 'rew00', 'rew02', 'rew10', 'rew12', 'rew14']
+
+
+def gnn_weight_offsets(cfg):
+    """{'enc_w': off, 'enc_b': off, ..., 'total': n} from the library (single source of truth)."""
+    buf = (C.c_int32 * 64)()
+    cnt = N.lib().stove_gnn_weight_offsets(C.byref(cfg), C.cast(buf, C.c_void_p), 64)
+    if cnt < 0:
+        N.check(cnt)
+    names = [s + sfx for s in GNN_SEGMENTS for sfx in ('_w', '_b')] + ['total']
+    assert cnt == len(names), (cnt, len(names))
+    return {k: int(buf[i]) for i, k in enumerate(names)}
+
+
+class GnnStep(torch.autograd.Function):
+    """s (n, O, cl/2) [, actions (n, A), app (n, O, 3)], flat weights -> out (n, O, cl), reward (n, 1)."""
+
+    @staticmethod
+    def forward(ctx, s, actions, app, weights, cfg):
+        s, actions, app = _c(s), _c(actions), _c(app)
+        N.require_cuda_f32(s, actions, app, weights)
+        n, O, _ = s.shape
+        out = torch.empty(n, O, cfg.cl, device=s.device, dtype=s.dtype)
+        reward = torch.empty(n, 1, device=s.device, dtype=s.dtype) if cfg.reward else None
+        N.check(N.lib().stove_gnn_fwd(C.byref(cfg), n, N.ptr(s), N.ptr(actions), N.ptr(app), N.ptr(weights),
+                                      N.ptr(out), N.ptr(reward), N.stream()))
+        ctx.save_for_backward(s, actions, app, weights)
+        ctx.cfg = cfg
+        if reward is None:
+            reward = s.new_zeros(())
+            ctx.mark_non_differentiable(reward)
+        return out, reward
+
+    @staticmethod
+    def backward(ctx, g_out, g_reward):
+        s, actions, app, weights = ctx.saved_tensors
+        cfg = ctx.cfg
+        n = s.shape[0]
+        g_out = g_out.contiguous()
+        g_reward = _c(g_reward) if cfg.reward and g_reward is not None else None
+        g_s = torch.empty_like(s)
+        g_w = torch.empty_like(weights)
+        ws = torch.empty(max(N.lib().stove_gnn_bwd_workspace(C.byref(cfg), n), 4) // 4, device=s.device,
+                         dtype=torch.float32)
+        N.check(N.lib().stove_gnn_bwd(C.byref(cfg), n, N.ptr(s), N.ptr(actions), N.ptr(app), N.ptr(weights),
+                                      N.ptr(g_out), N.ptr(g_reward), N.ptr(g_s), N.ptr(g_w), N.ptr(ws),
+                                      N.stream()))
+        return g_s, None, None, g_w, None
+
+
+def gnn_rollout(cfg, z_last, num, weights, actions=None, app=None, noise=None, pos_var=0.3, vel_std=0.04,
+                latent_std=0.04, want_std=False):
+    """Persistent rollout kernel (stove.py:777-861).  Returns z (n, num, O, cl/2+2), std, logq, rewards."""
+    z_last, actions, app, noise = _c(z_last), _c(actions), _c(app), _c(noise)
+    N.require_cuda_f32(z_last, actions, app, noise, weights)
+    n, O, zd = z_last.shape
+    dev, dt = z_last.device, z_last.dtype
+    z = torch.empty(n, num, O, zd, device=dev, dtype=dt)
+    std = torch.empty(n, num, O, zd - 2, device=dev, dtype=dt) if (want_std or noise is not None) else None
+    logq = torch.empty(n, num, O, zd - 2, device=dev, dtype=dt) if noise is not None else None
+    rewards = torch.empty(n, num, 1, device=dev, dtype=dt) if cfg.reward else None
+    alen = actions.shape[1] if actions is not None else 1
+    N.check(N.lib().stove_gnn_rollout(C.byref(cfg), n, num, N.ptr(z_last), N.ptr(actions), alen, N.ptr(app),
+                                      N.ptr(weights), N.ptr(noise), pos_var, vel_std, latent_std, N.ptr(z),
+                                      N.ptr(std), N.ptr(logq), N.ptr(rewards), N.stream()))
+    return z, std, logq, rewards

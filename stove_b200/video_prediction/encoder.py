@@ -1,0 +1,46 @@
+"""LSTM recognition network (drop-in for model/video_prediction/encoder.py:7-57).
+
+Kept on cuDNN/cuBLAS in this round (SURVEY.md section 8f ranks it first under "next"); the
+one structural change is free: the reference feeds the *same* flattened frame for every one
+of the `num_obj` LSTM steps (encoder.py:50), so `W_ih x + b` is computed once per frame
+instead of once per step (1/3 of the input GEMM at O = 3) and the recurrence runs on the
+small hidden-to-hidden GEMM only.  Parameter names are those of `nn.LSTM`
+(`rnn.weight_ih_l0`, ...) so reference checkpoints load.
+"""
+import torch
+import torch.nn as nn
+
+
+class RnnStates(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.c = config
+        self.z_size = 4
+        self.lstm_size = 256
+        img = self.c.channels * self.c.width * self.c.height
+        self.rnn = nn.LSTM(img, self.lstm_size)
+        self.fc1 = nn.Linear(self.lstm_size, 50)
+        self.fc2 = nn.Linear(50, 2 * self.z_size)
+        nn.init.xavier_uniform_(self.fc1.weight)
+        nn.init.xavier_uniform_(self.fc2.weight)
+        nn.init.constant_(self.fc1.bias, 0.1)
+        nn.init.constant_(self.fc2.bias, 0.1)
+
+    def forward(self, frames):
+        """frames (N, c, w, h) -> (N, O, 8): means and raw stds of (sx, sy/sx, x, y)."""
+        x = frames.flatten(start_dim=1)
+        H = self.lstm_size
+        rnn = self.rnn
+        gates_x = torch.addmm(rnn.bias_ih_l0 + rnn.bias_hh_l0, x, rnn.weight_ih_l0.t())
+        h = x.new_zeros(x.shape[0], H)
+        cell = x.new_zeros(x.shape[0], H)
+        outs = []
+        for _ in range(self.c.num_obj):
+            g = torch.addmm(gates_x, h, rnn.weight_hh_l0.t())
+            i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+            cell = torch.sigmoid(f) * cell + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(cell)
+            outs.append(h)
+        zps = torch.stack(outs, 1)
+        zps = torch.sigmoid(self.fc1(zps))
+        return self.fc2(zps)

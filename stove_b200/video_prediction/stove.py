@@ -1,0 +1,310 @@
+"""STOVE model (drop-in for model/video_prediction/stove.py:11-897).
+
+Same constructor (`Stove(config)`), `forward(x, step_counter, actions=None, pretrain=False)`
+-> `(average_elbo, prop_dict, rewards)`, `rollout(...)`, `prop_dict` keys and `state_dict`
+names as the reference.  The arithmetic of the hot path runs in the sm_100a kernels:
+glimpse/masks + both SPNs inside `Supair.likelihood`, the interaction network inside
+`Dynamics.forward`, and the whole time loop of `rollout` in one persistent kernel.
+The sequence glue (matching, smoothing, Gaussian fusion, ELBO assembly) stays tensor code,
+rewritten without the reference's per-step host synchronisation (stove.py:271-273) so a
+training step can be captured in a CUDA graph.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .dynamics import Dynamics
+from .supair import Supair
+from .. import ops
+from ..utils.utils import bw_transform
+
+_HALF_LOG_2PI = 0.5 * math.log(2.0 * math.pi)
+
+
+def _normal_log_prob(value, mean, std):
+    return -((value - mean) ** 2) / (2 * std ** 2) - torch.log(std) - _HALF_LOG_2PI
+
+
+class Stove(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.c = config
+        self.step_counter = 0
+        self.prop_dict = {}
+        self.sup = Supair(config)
+        self.dyn = Dynamics(config)
+        self.reconstruct_from_z = self.sup.reconstruct_from_z
+        kind = self.c.debug_match_objects
+        if kind == '3_only':
+            if self.c.num_obj != 3:
+                raise ValueError('Matching Function not compatible w/ specified number of objects.')
+            self.match_objects = self._3_only_match_objects
+        elif kind == 'volatile':
+            self.match_objects = self._volatile_match_objects
+        elif kind == 'greedy':
+            self.match_objects = self._greedy_match_objects
+        else:
+            raise ValueError('Specify valid self.c.debug_match_ojects.')
+
+    # -- noise: same shapes in the same order as the reference's rsample() calls ------------
+    def _standard_normal(self, shape, like):
+        return torch.empty(shape, device=like.device, dtype=like.dtype).normal_()
+
+    # -- small sequence helpers ---------------------------------------------------------------
+    def v_from_state(self, z_sup):
+        """(n, T, o, 4) -> (n, T, o, 6): append finite-difference velocities, zeros at t=0."""
+        full = torch.cat([z_sup[:, 1:], z_sup[:, 1:, :, 2:] - z_sup[:, :-1, :, 2:]], -1)
+        return torch.cat([torch.zeros_like(full[:, :1]), full], 1)
+
+    def v_std_from_pos(self, z_sup_std):
+        v_std = torch.sqrt(z_sup_std[:, 1:, :, 2:] ** 2 + z_sup_std[:, :-1, :, 2:] ** 2)
+        full = torch.cat([z_sup_std[:, 1:], v_std], -1)
+        return torch.cat([torch.zeros_like(full[:, :1]), full], 1)
+
+    def full_state(self, z_dyn, std_dyn, z_sup, std_sup):
+        """Fuse the dynamics and SuPAIR Gaussians over (x, v), sample, score (stove.py:103-170)."""
+        c = self.c
+        mean_s, std_s = z_sup[..., :2], std_sup[..., :2]
+        mean_l, std_l = z_dyn[..., 4:], std_dyn[..., 4:]
+        m_sup, s_sup = z_sup[..., 2:6], std_sup[..., 2:6]
+        m_dyn, s_dyn = z_dyn[..., :4], std_dyn[..., :4]
+        v_sup, v_dyn = s_sup ** 2, s_dyn ** 2
+        mean_xv = (v_sup * m_dyn + v_dyn * m_sup) / (v_dyn + v_sup)
+        std_xv = s_dyn * s_sup / torch.sqrt(v_dyn + v_sup)
+        if c.debug_no_latents:
+            mean = torch.cat([mean_s, mean_xv], -1)
+            std = torch.cat([std_s, std_xv], -1)
+            z_s = mean + std * self._standard_normal(mean.shape, mean)
+            log_q = _normal_log_prob(z_s, mean, std)
+            return torch.cat([z_s, torch.zeros_like(mean_l)], -1), log_q, mean, std
+        if c.debug_no_velocity:
+            mean = torch.cat([mean_s, mean_xv[..., :2], torch.zeros_like(mean_xv[..., 2:]), mean_l], -1)
+            std = torch.cat([std_s, std_xv[..., :2], torch.ones_like(std_xv[..., 2:]), std_l], -1)
+        else:
+            mean = torch.cat([mean_s, mean_xv, mean_l], -1)
+            std = torch.cat([std_s, std_xv, std_l], -1)
+        z_s = mean + std * self._standard_normal(mean.shape, mean)
+        return z_s, _normal_log_prob(z_s, mean, std), mean, std
+
+    def transition_lik(self, means, results):
+        return _normal_log_prob(results, means, self.dyn.transition_lik_std.to(results.dtype))
+
+    # -- object matching ------------------------------------------------------------------------
+    def _match_inputs(self, z_sup, z_sup_std, obj_appearances):
+        z = (z_sup + 1) / 2
+        m_idx = [2, 3]
+        if obj_appearances is not None:
+            z = torch.cat([z, obj_appearances], -1)
+            if self.c.debug_match_appearance:
+                m_idx += [4, 5, 6]
+        if z_sup_std is not None:
+            z = torch.cat([z, z_sup_std], -1)
+        return z, m_idx
+
+    @staticmethod
+    def _match_outputs(z_matched, z_sup_std, obj_appearances):
+        z_sup_matched = 2 * z_matched[..., :4] - 1
+        app = z_matched[..., 4:7] if obj_appearances is not None else None
+        if z_sup_std is None and obj_appearances is not None:
+            return z_sup_matched, app
+        if z_sup_std is not None and obj_appearances is None:
+            return z_sup_matched, z_matched[..., 4:8], None
+        if z_sup_std is not None and obj_appearances is not None:
+            return z_sup_matched, z_matched[..., 7:11], app
+        return z_sup_matched
+
+    @staticmethod
+    def _pair_errors(prev, curr):
+        """err[b, a, j] = |prev_a - curr_j|^2 (detached)."""
+        return ((prev.detach().unsqueeze(2) - curr.detach().unsqueeze(1)) ** 2).sum(-1)
+
+    def _3_only_match_objects(self, z_sup, z_sup_std=None, obj_appearances=None):
+        """Nearest-neighbour matching with greedy repair of non-permutations (stove.py:200-329),
+        without the reference's `if num_faults > 0` host sync: the repair is evaluated for every
+        row and selected with a mask."""
+        z, m_idx = self._match_inputs(z_sup, z_sup_std, obj_appearances)
+        O = self.c.num_obj
+        matched = [z[:, 0]]
+        for t in range(1, z.shape[1]):
+            err = self._pair_errors(matched[t - 1][..., m_idx], z[:, t][..., m_idx])
+            idx = err.argmin(-1)
+            valid = (idx[:, 0] != idx[:, 1]) & (idx[:, 1] != idx[:, 2]) & (idx[:, 0] != idx[:, 2])
+            e = err
+            fixed = []
+            for o in range(O):
+                col = e.argmin(-1)[:, o]
+                fixed.append(col)
+                e = e.masked_fill(torch.nn.functional.one_hot(col, O).bool().unsqueeze(1), 1e12)
+            idx = torch.where(valid.unsqueeze(1), idx, torch.stack(fixed, 1))
+            matched.append(torch.gather(z[:, t], 1, idx.unsqueeze(-1).expand(-1, -1, z.shape[-1])))
+        return self._match_outputs(torch.stack(matched, 1), z_sup_std, obj_appearances)
+
+    def _volatile_match_objects(self, z_sup, z_sup_std=None, obj_appearances=None):
+        """Per-object nearest neighbour, no permutation check (stove.py:331-430)."""
+        z, m_idx = self._match_inputs(z_sup, z_sup_std, obj_appearances)
+        matched = [z[:, 0]]
+        for t in range(1, z.shape[1]):
+            err = self._pair_errors(matched[t - 1][..., m_idx], z[:, t][..., m_idx])   # [b, prev, cur]
+            col = err.argmin(-1)
+            matched.append(torch.gather(z[:, t], 1, col.unsqueeze(-1).expand(-1, -1, z.shape[-1])))
+        return self._match_outputs(torch.stack(matched, 1), z_sup_std, obj_appearances)
+
+    def _greedy_match_objects(self, z_sup, z_sup_std=None, obj_appearances=None):
+        """Global greedy bipartite matching (stove.py:432-514)."""
+        z, m_idx = self._match_inputs(z_sup, z_sup_std, obj_appearances)
+        O = self.c.num_obj
+        matched = [z[:, 0]]
+        for t in range(1, z.shape[1]):
+            err = self._pair_errors(matched[t - 1][..., m_idx], z[:, t][..., m_idx])
+            n = err.shape[0]
+            assign = torch.zeros(n, O, dtype=torch.long, device=z.device)
+            for _ in range(O):
+                flat = err.view(n, -1).argmin(1)
+                ix, iy = flat // O, flat % O
+                assign = torch.where(torch.nn.functional.one_hot(ix, O).bool(), iy.unsqueeze(1), assign)
+                big = err.max() + 1
+                err = err.masked_fill(torch.nn.functional.one_hot(ix, O).bool().unsqueeze(2), 0) \
+                    + torch.nn.functional.one_hot(ix, O).unsqueeze(2).to(err.dtype) * big
+                big = err.max() + 1
+                err = err.masked_fill(torch.nn.functional.one_hot(iy, O).bool().unsqueeze(1), 0) \
+                    + torch.nn.functional.one_hot(iy, O).unsqueeze(1).to(err.dtype) * big
+            matched.append(torch.gather(z[:, t], 1, assign.unsqueeze(-1).expand(-1, -1, z.shape[-1])))
+        return self._match_outputs(torch.stack(matched, 1), z_sup_std, obj_appearances)
+
+    def fix_supair(self, z, z_std=None):
+        """Replace states that jump away from both temporal neighbours by their average
+        (stove.py:516-571)."""
+        zz = torch.cat([z, z_std], -1) if z_std is not None else z
+        d = (zz[:, 1:, :, :2] - zz[:, :-1, :, :2]).abs().detach()
+        zero = torch.zeros_like(d[:, :1])
+        flag = (torch.cat([zero, d], 1) > 0.095) & (torch.cat([d, zero], 1) > 0.095)
+        pad = torch.zeros_like(zz[:, :1])
+        smooth = torch.cat([pad, (zz[:, :-2] + zz[:, 2:]) / 2, pad], 1)
+        zz = torch.where(torch.cat(zz.shape[-1] // 2 * [flag], -1), smooth, zz)
+        if z_std is not None:
+            return torch.chunk(zz, 2, dim=-1)
+        return zz
+
+    def object_embedding(self, z, x_color):
+        """Mean colour of each object's glimpse (stove.py:573-597)."""
+        z_patch = self.sup.sy_from_quotient(z[..., :4].detach())
+        patches = self.sup.patches_from_z(x_color.flatten(end_dim=1), z_patch.flatten(end_dim=2))
+        return patches.mean((-1, -2)).view(*z.shape[:-1], 3)
+
+    # -- sequence ELBO ----------------------------------------------------------------------------
+    def stove_forward(self, x, actions=None, x_color=None):
+        c = self.c
+        n, T = x.shape[0], x.shape[1]
+        skip, cl, O = c.skip, c.cl, c.num_obj
+        packed_spn = self.sup.pack()
+        packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
+
+        z_sup = self.sup.encoder(x.flatten(end_dim=1))
+        z_sup, z_sup_std = self.sup.constrain_zp(z_sup.flatten(end_dim=1))
+        z_sup = z_sup.view(n, T, O, 4)
+        z_sup_std = z_sup_std.view(n, T, O, 4)
+        _app = None
+        if c.debug_core_appearance or c.debug_match_appearance:
+            _app = self.object_embedding(z_sup, x_color)
+        z_sup, z_sup_std, obj_appearances = self.match_objects(z_sup, z_sup_std, _app)
+        core_app = obj_appearances.transpose(0, 1) if c.debug_core_appearance else T * [None]
+        if c.debug_fix_supair:
+            z_sup, z_sup_std = self.fix_supair(z_sup, z_sup_std)
+        z_sup_full = self.v_from_state(z_sup)
+        z_sup_std_full = self.v_std_from_pos(z_sup_std)
+
+        prior_shape = (n, O, cl // 2 - 4, 1)
+        lat0 = (0.01 * self._standard_normal(prior_shape, x)).squeeze()
+        init_z = torch.cat([z_sup_full[:, skip - 1], lat0], -1)
+        std0 = (0.1 + 0.01 * self._standard_normal(prior_shape, x)).squeeze()
+        dyn_std_init = torch.cat([z_sup_std_full[:, skip - 1, :, 2:], std0], -1)
+
+        z = {skip - 1: init_z}
+        z_dyn, z_dyn_std, z_std, log_z, rewards = {}, {skip - 1: dyn_std_init}, {}, {}, []
+        z_std[skip - 1] = torch.cat([z_sup_std_full[:, skip - 1, :, :2], dyn_std_init], -1)
+        core_actions = actions.transpose(0, 1) if actions is not None else T * [None]
+        for t in range(skip, T):
+            tmp, reward = self.dyn(z[t - 1][..., 2:], 0, core_actions[t - 1], core_app[t - 1],
+                                   packed=packed_dyn)
+            rewards.append(reward)
+            zd, z_dyn_std[t] = self.dyn.constrain_z_dyn(tmp[..., :cl // 2], tmp[..., cl // 2:])
+            z_dyn[t] = torch.cat([z[t - 1][..., 2:4] + zd[..., :2], zd[..., 2:]], -1)
+            z[t], log_z[t], _, z_std[t] = self.full_state(
+                z_dyn[t], z_dyn_std[t], z_sup_full[:, t], z_sup_std_full[:, t])
+        steps = range(skip, T)
+        z_s = torch.stack([z[t] for t in steps], 1)
+        z_dyn_s = torch.stack([z_dyn[t] for t in steps], 1)
+        log_z_s = torch.stack([log_z[t] for t in steps], 1)
+        z_dyn_std_s = torch.stack([z_dyn_std[t] for t in steps], 1)
+        z_std_s = torch.stack([z_std[t] for t in steps], 1)
+        if c.action_conditioned:
+            rewards = torch.stack(rewards, 1)
+        else:
+            rewards = torch.zeros(len(rewards))
+
+        z_f = self.sup.sy_from_quotient(z_s.flatten(end_dim=2))
+        img_lik, sup_prop = self.sup.likelihood(x[:, skip:], z_f[..., :4], packed=packed_spn)
+        self.prop_dict.update(sup_prop)
+        z_sup_tmp = self.sup.sy_from_quotient(z_sup[:, 1:skip])
+        img_lik_sup, _ = self.sup.likelihood(x[:, 1:skip], z_sup_tmp.flatten(end_dim=2), packed=packed_spn)
+        log_z_f = log_z_s.sum((-2, -1)).flatten()
+        trans_lik = self.transition_lik(means=z_dyn_s, results=z_s[..., 2:]).sum((-2, -1)).flatten(end_dim=1)
+        elbo = trans_lik + img_lik - log_z_f
+        average_elbo = elbo.mean() + img_lik_sup.mean()
+
+        if (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0):
+            p = self.prop_dict
+            p['z'] = self.sup.sy_from_quotient(z_s).detach()
+            p['z_dyn'] = z_dyn_s.detach()
+            p['z_sup'] = self.sup.sy_from_quotient(z_sup_full[:, skip:]).detach()
+            p['z_std'] = z_std_s.mean((0, 1, 2)).detach()
+            p['z_dyn_std'] = torch.cat([z_s.new_full((2,), float('nan')),
+                                        z_dyn_std_s[..., :4].mean((0, 1, 2)).detach()])
+            p['z_sup_std'] = z_sup_std_full[:, skip:].mean((0, 1, 2)).detach()
+            p['log_q'] = log_z_f.mean().detach()
+            p['translik'] = trans_lik.mean().detach()
+            p['obj_appearances'] = obj_appearances[:, skip:].detach() if obj_appearances is not None else None
+            if c.debug and c.debug_extend_plots:
+                p['z_dyn_std_full'] = z_dyn_std_s.detach()
+        return average_elbo, self.prop_dict, rewards
+
+    # -- rollout ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def rollout(self, z_last, num=None, sample=False, return_std=False, actions=None, appearance=None):
+        """Roll the dynamics model out for `num` steps in ONE persistent kernel
+        (stove.py:777-861).  z_last (n, o, cl//2 + 2) holds [sx, sy | x, y | v | latent].
+        Returns (z_full (n, num, o, cl//2+2), rewards) -- or the 3-tuples of the reference for
+        `sample` / `return_std`.  Outputs are detached (inference path)."""
+        c = self.c
+        num = c.num_rollout if num is None else num
+        cfg, weights = self.dyn.pack_weights(0, actions is not None, appearance is not None)
+        noise = None
+        if sample:
+            noise = self._standard_normal((z_last.shape[0], num, c.num_obj, c.cl // 2), z_last)
+        z_full, std, logq, rewards = ops.gnn_rollout(
+            cfg, z_last, num, weights, actions=actions, app=appearance, noise=noise, pos_var=c.pos_var,
+            vel_std=0.04, latent_std=c.debug_latent_q_std, want_std=return_std)
+        if not c.action_conditioned:
+            rewards = torch.zeros(num)
+        if sample:
+            return z_full, logq, rewards
+        if return_std:
+            return z_full, std, rewards
+        return z_full, rewards
+
+    # -- entry point ------------------------------------------------------------------------------------
+    def forward(self, x, step_counter, actions=None, pretrain=False):
+        """x (n, T, 3, w, h) in [0, 1]; returns (average_elbo, prop_dict, rewards) [stove.py:863-897]."""
+        self.step_counter = step_counter
+        self.sup.step_counter = step_counter
+        self.dyn.step_counter = step_counter
+        x_color = x
+        if self.c.debug_bw:
+            x = bw_transform(x)
+        if pretrain:
+            elbo, prop_dict = self.sup(x)
+            return elbo, prop_dict, 0
+        if self.c.debug_core_appearance or self.c.debug_match_appearance:
+            return self.stove_forward(x, actions=actions, x_color=x_color)
+        return self.stove_forward(x, actions=actions)

@@ -1,0 +1,140 @@
+"""GPU parity of the drop-in module: Stove.forward (ELBO, latents, every gradient) and
+Stove.rollout against the reference's golden vectors (fp64), on the same weights, frames
+and noise; then the full BASELINE config-1 size against the fp64 oracle."""
+import pytest
+import torch
+
+from oracle import stove_oracle as so
+from util import Checker, NoiseReplay, VARIANTS, grad_signature, load_golden, make_model
+
+pytestmark = pytest.mark.gpu
+VAL, GRAD = 3e-5, 3e-4
+
+
+@pytest.mark.parametrize('tag', list(VARIANTS))
+def test_stove_golden(tag):
+    kw, seed = VARIANTS[tag]
+    g = load_golden('stove_' + tag)
+    oc, sd, model = make_model(kw, seed, att_gain=float(g['att_gain']))
+    x = (g['x_u8'].float() / 255.0).cuda()
+    n, T = x.shape[0], x.shape[1]
+    noise = [g['noise%d' % i] for i in range(2 + T - oc.skip)]
+    model._standard_normal = NoiseReplay(noise, 'cuda')
+    actions = g['actions'].float().cuda() if 'actions' in g else None
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    elbo, prop, rew = model(x, 0, actions=actions)
+    ck = Checker('stove_' + tag)
+    ck.close('elbo', elbo, g['elbo'], VAL)
+    for k in ('z', 'z_dyn', 'z_sup'):
+        ck.close(k, prop[k], g[k], 2e-5, absolute=True)
+    for k in ('log_q', 'translik', 'bg', 'patch', 'overlap'):
+        ck.close(k, prop[k], g[k], VAL)
+    loss = -elbo
+    if oc.action_conditioned:
+        ck.close('rewards', rew, g['rewards'], 2e-5, absolute=True)
+        ck.close('obj_appearances', prop['obj_appearances'], g['obj_appearances'], 2e-5, absolute=True)
+        tgt = (torch.arange(n * (T - 2)) % 3 == 0).float().view(n, T - 2, 1).cuda()
+        loss = loss + 100.0 * torch.nn.functional.binary_cross_entropy(rew, tgt)
+    model.zero_grad()
+    loss.backward()
+    params = dict(model.named_parameters())
+    for k in g:
+        if k.startswith('g.'):
+            ck.close(k, params[k[2:]].grad, g[k], GRAD)
+        elif k.startswith('gsig.'):
+            sig = grad_signature(params[k[5:]].grad)
+            ck.close(k, sig[[1, 3]], g[k][[1, 3]], GRAD)
+    # rollout from the inferred state
+    z_last = prop['z'][:, -1]
+    steps = g['roll_steps'].tolist()
+    if oc.action_conditioned:
+        zr, rr = model.rollout(z_last, num=92, actions=g['roll_actions'].float().cuda(),
+                               appearance=prop['obj_appearances'][:, -1])
+        ck.close('roll_rewards', rr[:, steps], g['roll_rewards'], 1e-3, absolute=True)
+    else:
+        zr, rr = model.rollout(z_last, num=92)
+    # drift over length: per-step fp32 error compounds through 92 dependent steps
+    for i, st in enumerate(steps):
+        ck.close('roll_z_step%d' % st, zr[:, st], g['roll_z'][:, i], 1e-4 * (1 + st))
+    ck.finish()
+
+
+def test_stove_config1_full_size_vs_oracle():
+    """BASELINE config 1 (billiards, O=3, 32x32, T=8, batch 256): ELBO and gradients against the
+    fp64 oracle on the same seeded synthetic frames and noise."""
+    from stove_b200 import synth
+    kw, seed = VARIANTS['plain']
+    oc, sd, model = make_model(kw, seed, att_gain=0.5)
+    n, T = 256, 8
+    x = synth.billiards(n, T, 3, res=32, seed=5)['x']
+    gen = torch.Generator().manual_seed(9)
+    noise = [torch.randn(n, 3, 12, 1, generator=gen, dtype=torch.float64) for _ in range(2)] + \
+            [torch.randn(n, 3, 18, generator=gen, dtype=torch.float64) for _ in range(T - 2)]
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if 'output_vector' not in k}
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    elbo_o, prop_o, _ = so.stove_forward(oc, P, x.double(), noise)
+    (-elbo_o).backward()
+    model._standard_normal = NoiseReplay(noise, 'cuda')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    elbo, prop, _ = model(x.cuda(), 0)
+    model.zero_grad()
+    (-elbo).backward()
+    ck = Checker('stove_config1_full')
+    ck.close('elbo', elbo, elbo_o, VAL)
+    ck.close('z', prop['z'], prop_o['z'], 3e-5, absolute=True)
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            ck.close('g.' + name, p.grad, P[name].grad, GRAD)
+        else:
+            ck.true('nograd.' + name, P[name].grad is None)
+    zr, _ = model.rollout(prop['z'][:, -1], num=92)
+    with torch.no_grad():
+        zo, _ = so.rollout(oc, P, prop_o['z'][:, -1], num=92)
+    ck.close('rollout_step1', zr[:, 0], zo[:, 0], 1e-4)
+    ck.close('rollout_step92', zr[:, -1], zo[:, -1], 1e-2)
+    ck.finish()
+
+
+def test_rollout_sampling_std_and_batch_independence():
+    """rollout(sample=True / return_std=True) against the oracle with the same noise, and the
+    size-independent property that sequences do not interact (2000 steps x 1024 sequences is the
+    BASELINE config 5 shape; a slice of the batch must reproduce the same trajectories)."""
+    kw, seed = VARIANTS['ac']
+    oc, sd, model = make_model(kw, seed, att_gain=0.5)
+    gen = torch.Generator().manual_seed(4)
+    n, num = 37, 25
+    z_last = torch.cat([0.2 + 0.3 * torch.rand(n, 3, 2, generator=gen, dtype=torch.float64),
+                        torch.rand(n, 3, 16, generator=gen, dtype=torch.float64) - 0.5], -1)
+    app = torch.rand(n, 3, 3, generator=gen, dtype=torch.float64)
+    from stove_b200 import synth
+    actions = synth.random_actions(n, 7, 9, 3).double()
+    noise = torch.randn(n, num, 3, 16, generator=gen, dtype=torch.float64)
+    P = {k: v for k, v in sd.items()}
+    with torch.no_grad():
+        zo, lq, ro = so.rollout(oc, P, z_last, num, actions, app, noise=list(noise.unbind(1)))
+        zo2, so2, _ = so.rollout(oc, P, z_last, num, actions, app, return_std=True)
+    model._standard_normal = lambda shape, like: noise.float().cuda()
+    zg, lg, rg = model.rollout(z_last.float().cuda(), num, sample=True, actions=actions.float().cuda(),
+                               appearance=app.float().cuda())
+    ck = Checker('rollout_sampling')
+    ck.close('z_sample_step1', zg[:, 0], zo[:, 0], 1e-4)
+    ck.close('z_sample', zg, zo, 5e-3)
+    ck.close('logq_step1', lg[:, 0], lq[:, 0], 1e-4)
+    ck.close('rewards_step1', rg[:, 0], ro[:, 0], 1e-4)
+    zs, ss, _ = model.rollout(z_last.float().cuda(), num, return_std=True, actions=actions.float().cuda(),
+                              appearance=app.float().cuda())
+    ck.close('z_mean', zs, zo2, 5e-3)
+    ck.close('std', ss, so2, 5e-3)
+    # config-5 shape: 1024 sequences x 2000 steps; a slice must give identical trajectories
+    n5 = 1024
+    zl = z_last.float().repeat(28, 1, 1)[:n5].cuda() * (1 + 0.01 * torch.arange(n5, device='cuda').view(-1, 1, 1) / n5)
+    ap = app.float().repeat(28, 1, 1)[:n5].cuda()
+    ac = synth.random_actions(n5, 2000, 9, 11).cuda()
+    big, rb = model.rollout(zl, 2000, actions=ac, appearance=ap)
+    sub, rs = model.rollout(zl[100:131], 2000, actions=ac[100:131], appearance=ap[100:131])
+    ck.true('finite', bool(torch.isfinite(big).all()))
+    ck.true('batch_independent', torch.equal(big[100:131], sub) and torch.equal(rb[100:131], rs))
+    ck.true('scale_constant', torch.equal(big[:, -1, :, :2], zl[..., :2]))
+    ck.finish()

@@ -1,0 +1,121 @@
+"""CPU: host-side logic of the package (no kernel launches): C-ABI exports, structure
+tables, state_dict layout, sync-free object matching against the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import stove_oracle as so
+from oracle.params import make_state_dict, param_shapes
+from stove_b200 import Stove, StoveConfig, _native
+from util import VARIANTS, load_structure_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'stove_b200.h')).read()
+    declared = set(re.findall(r'\b(stove_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert _native.lib().stove_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    c = StoveConfig(width=32, height=32, num_obj=3, action_conditioned=False, random_seed=7)
+    m = Stove(c)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m(torch.rand(2, 8, 3, 32, 32), 0)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m.sup.obj_spn(torch.rand(2, 100))
+
+
+def test_product_code_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'stove_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+
+
+@pytest.mark.parametrize('tag', list(VARIANTS))
+def test_state_dict_layout_matches_reference(tag):
+    kw, seed = VARIANTS[tag]
+    oc = so.default_config(**kw)
+    m = Stove(StoveConfig(**vars(oc)))
+    want = param_shapes(oc)
+    got = m.state_dict()
+    assert list(got.keys()) == list(want.keys())
+    assert [tuple(v.shape) for v in got.values()] == list(want.values())
+    m.load_state_dict({k: v.float() for k, v in make_state_dict(oc, seed).items()})
+    # the root sum is reachable under both names (rat_torch.py:331)
+    assert m.sup.obj_spn.output_vector is m.sup.obj_spn.vector_list[4][0]
+
+
+def test_structure_tables():
+    from stove_b200.spn.rat_torch import RatSpn, SpnArgs
+    from stove_b200.spn.region_graph import RegionGraph
+    for tag, g in load_structure_golden().items():
+        rg = RegionGraph(range(g['n']), seed=g['seed'])
+        for p, d in g['splits']:
+            rg.random_split(p, d)
+        a = SpnArgs()
+        a.num_gauss, a.num_sums = g['G'], g['S']
+        spn = RatSpn(1, rg, a, name='t')
+        assert [v.scope for v in spn.vector_list[0]] == g['leaf_scopes']
+        t = spn._tables
+        if tag.startswith('obj'):
+            assert t.kind == 'D2'
+            h = t.host
+            D, R = g['n'], 6
+            for p in range(D):
+                for r in range(R):
+                    q, pos = divmod(int(h['pix_slot'][p, r]), t.meta['pmax'])
+                    assert q // 2 == r and h['region_scope'][q, pos] == p
+            assert sorted(h['dst_row'].tolist()) == sorted(set(h['dst_row'].tolist()))
+        else:
+            assert t.kind == 'D1'
+            assert t.host['side'].sum(0).tolist() == [g['n'] // 2] * 3
+
+
+@pytest.mark.parametrize('kind,O', [('3_only', 3), ('greedy', 6), ('volatile', 4), ('greedy', 3)])
+def test_sync_free_matching_equals_oracle(kind, O):
+    g = torch.Generator().manual_seed(O)
+    oc = so.default_config(num_obj=O if kind != '3_only' else 3, debug_match_objects=kind)
+    O = oc.num_obj
+    m = Stove(StoveConfig(**vars(oc), width=32, height=32) if False else StoveConfig(**vars(oc)))
+    n, T = 64, 8
+    z = torch.rand(n, T, O, 4, generator=g) * 2 - 1
+    z[:8, 3] = z[:8, 3, :1]              # force ambiguous / non-permutation argmins
+    z[8:16, 5, 1] = z[8:16, 5, 0]
+    std = torch.rand(n, T, O, 4, generator=g)
+    for app in (None, torch.rand(n, T, O, 3, generator=g)):
+        want = so.MATCHERS[kind](oc, z.double(), std.double(), app.double() if app is not None else None)
+        got = m.match_objects(z, std, app)
+        for a, b in zip(got, want):
+            if b is None:
+                assert a is None
+            else:
+                assert (a.double() - b).abs().max() < 1e-6
+
+
+def test_fix_supair_and_velocities_equal_oracle():
+    g = torch.Generator().manual_seed(3)
+    oc = so.default_config()
+    m = Stove(StoveConfig(**vars(oc)))
+    z = torch.rand(16, 8, 3, 4, generator=g, dtype=torch.float64)
+    z[:, 4] += 0.5
+    std = torch.rand(16, 8, 3, 4, generator=g, dtype=torch.float64)
+    a, b = m.fix_supair(z, std)
+    a2, b2 = so.fix_supair(z, std)
+    assert torch.equal(a, a2) and torch.equal(b, b2)
+    assert torch.equal(m.v_from_state(z), so.v_from_state(z))
+    assert torch.equal(m.v_std_from_pos(std), so.v_std_from_pos(std))
+    zp = torch.randn(50, 8, generator=g, dtype=torch.float64)
+    for x, y in zip(m.sup.constrain_zp(zp), so.constrain_zp(oc, zp)):
+        assert (x - y).abs().max() < 1e-12

@@ -43,3 +43,66 @@ VARIANTS = {
                 max_obj_scale=0.22), 23),
     'vol': (dict(debug_match_objects='volatile'), 24),
 }
+
+
+class Checker:
+    """Collects (name, error, tolerance) triples, logs them to gpurun_out/parity.jsonl and fails
+    at the end, so one GPU round trip reports every mismatch instead of the first."""
+
+    def __init__(self, test):
+        self.test, self.rows = test, []
+
+    def close(self, name, got, want, tol, absolute=False):
+        got, want = got.detach().double().cpu(), want.detach().double().cpu()
+        if got.shape != want.shape:
+            self.rows.append((name, float('inf'), tol, 'shape %s vs %s' % (tuple(got.shape), tuple(want.shape))))
+            return
+        fin = torch.isfinite(want)
+        bad_nan = bool((torch.isfinite(got) != fin).any())
+        diff = (got - want)[fin].abs().max().item() if fin.any() else 0.0
+        scale = 1.0 if absolute else (want[fin].abs().max().item() + 1e-300 if fin.any() else 1.0)
+        err = float('inf') if bad_nan else diff / scale
+        self.rows.append((name, err, tol, ''))
+
+    def true(self, name, cond):
+        self.rows.append((name, 0.0 if cond else float('inf'), 0.5, ''))
+
+    def finish(self):
+        out = os.path.join(os.path.dirname(GOLDEN.rstrip('/')), '..', 'gpurun_out')
+        try:
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, 'parity.jsonl'), 'a') as f:
+                for name, err, tol, note in self.rows:
+                    f.write(json.dumps({'test': self.test, 'check': name, 'err': err, 'tol': tol,
+                                        'note': note}) + '\n')
+        except OSError:
+            pass
+        bad = [(n, e, t, note) for n, e, t, note in self.rows if not (e <= t)]
+        worst = sorted(self.rows, key=lambda r: -(r[1] / r[2] if r[2] else 0))[:3]
+        assert not bad, 'parity failures (name, err, tol): %s' % bad[:12]
+        return worst
+
+
+class NoiseReplay:
+    """Stands in for Stove._standard_normal: replays a list of draws (shape-checked)."""
+
+    def __init__(self, draws, device):
+        self.draws = [d.to(device=device, dtype=torch.float32) for d in draws]
+
+    def __call__(self, shape, like):
+        d = self.draws.pop(0)
+        assert tuple(d.shape) == tuple(shape), (d.shape, shape)
+        return d
+
+
+def make_model(kw, seed, att_gain=1.0, device='cuda'):
+    """stove_b200.Stove with the deterministic weights of oracle.params.make_state_dict."""
+    from oracle import stove_oracle as so
+    from oracle.params import make_state_dict
+    from stove_b200 import Stove, StoveConfig
+    oc = so.default_config(**kw)
+    sd = make_state_dict(oc, seed, att_gain=att_gain)
+    cfg = StoveConfig(**{k: v for k, v in vars(oc).items()})
+    model = Stove(cfg)
+    model.load_state_dict({k: v.float() for k, v in sd.items()})
+    return oc, sd, model.to(device)
