@@ -350,6 +350,8 @@ class RatSpn(nn.Module):
         return PackedSpn('D2', t, leaf, wlog, wlin, rlog, rlin)
 
     def forward_packed(self, packed, inputs, marginalized=None):
+        if inputs.shape[0] == 0:
+            return inputs.new_zeros(0, self.num_classes)
         if packed.kind == 'D2':
             out = ops.Spn2.apply(inputs, marginalized, packed.leaf, packed.wlog, packed.wlin, packed.rlog,
                                  packed.rlin, packed.tables)

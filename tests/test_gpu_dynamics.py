@@ -6,7 +6,7 @@ from oracle import stove_oracle as so
 from util import Checker, VARIANTS, load_golden, make_model
 
 pytestmark = pytest.mark.gpu
-VAL, GRAD = 2e-5, 2e-4
+VAL, GRAD = 2e-5, 4e-4
 KW = {'plain': {}, 'ac': VARIANTS['ac'][0], 'o6': dict(num_obj=6, debug_match_objects='greedy')}
 
 
