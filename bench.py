@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the STOVE hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this framework on N B200s
+    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on host CPU cores
+
+Headline metric: training sequences/s of the sequence-ELBO forward+backward on BASELINE
+config 1 (billiards, 3 balls, 32x32, 8-frame window, batch 256 per GPU; optimizer excluded,
+gradient all-reduce included when N > 1; weak scaling).  One JSON line is printed by rank 0.
+Extra keys report the rollout workloads of the same metric family (video prediction:
+8-frame inference + 92-frame rollout; MCTS-style long rollouts: 1024 x 2000 frames).
+
+Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on
+both sides, max over ranks.  Inputs rotate through a device-resident pool of batches that
+is larger than L2 (8 x 25 MB > 126 MB), so no step finds its frames in L2.  `e2e` repeats the
+measurement through the public module call with pinned HOST batches (H2D copy of the frames and
+D2H read of the loss inside the timed region).  `roofline` comes from a second pass of K steps
+with per-kernel CUDA events (stove_profile_*); `cpu_baseline` times the oracle port of the
+reference algorithm on the host cores (rank 0, N = 1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, T, O, RES = 256, 8, 3, 32
+POOL = 8                      # device-resident batches: 8 x 25.2 MB > 126 MB L2
+WORKLOAD = 'STOVE billiards, 3 balls, 32x32 frames, 8-frame window, fwd+bwd ELBO, batch 256 per GPU'
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index):
+        self.rows, self.proc, self.idx = [], None, device_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.FIELDS,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v == 'Active'})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p['hbm_gbs'], 'MEASURED_PEAKS.json (measured copy bandwidth)'
+    return 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+
+
+def make_frames(n, seed):
+    from stove_b200 import synth
+    return synth.billiards(n, T, O, res=RES, seed=seed)['x']
+
+
+def build_model(device):
+    from stove_b200 import Stove, StoveConfig
+    torch.manual_seed(0)
+    cfg = StoveConfig(width=RES, height=RES, num_obj=O, action_conditioned=False, action_space=None,
+                      random_seed=7, device=device)
+    return Stove(cfg).to(device)
+
+
+def build_ac_model(device):
+    from stove_b200 import Stove, StoveConfig
+    torch.manual_seed(2)              # a seed whose random-init rollout stays finite (SURVEY hard part 13)
+    cfg = StoveConfig(width=RES, height=RES, num_obj=O, action_conditioned=True, action_space=9,
+                      debug_core_appearance=True, random_seed=7, device=device)
+    m = Stove(cfg).to(device)
+    with torch.no_grad():             # tame exp(attention) of the untrained net
+        for core in m.dyn.att_net:
+            for lin in core:
+                lin.weight.mul_(0.5)
+    return m
+
+
+def dist_setup(n_gpus):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        torch.cuda.set_device(0)
+    return world, int(os.environ.get('RANK', '0')), local
+
+
+def timed(fn, steps, warmup, world, on_start=None):
+    """W warm-up + exactly K timed calls of fn(i); device time, max over ranks (ms total)."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if on_start is not None:
+        on_start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        fn(warmup + i)
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline = oracle port of the reference algorithm (oracle/stove_oracle.py)
+# ----------------------------------------------------------------------------------------
+def cpu_train_baseline(steps, warmup, state_dict, frames, threads=None):
+    """fwd+bwd ELBO of the reference algorithm on the host cores, fp32, full batch-256 steps."""
+    from oracle import stove_oracle as so
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    oc = so.default_config()
+    structs = so.structures(oc)
+    P = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in state_dict.items()
+         if 'output_vector' not in k}
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for i in range(warmup + steps):
+        x = frames[i % len(frames)]
+        noise = [torch.randn(BATCH, O, 12, 1, generator=gen) for _ in range(2)] + \
+                [torch.randn(BATCH, O, 18, generator=gen) for _ in range(T - 2)]
+        for p in P.values():
+            p.grad = None
+        t0 = time.perf_counter()
+        elbo, _, _ = so.stove_forward(oc, P, x, noise, structs=structs)
+        (-elbo).backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return BATCH * len(times) / sum(times), threads, sum(times) / len(times)
+
+
+def cpu_rollout_baseline(state_dict, z_last, actions, app, num, threads=None):
+    from oracle import stove_oracle as so
+    torch.set_num_threads(threads or os.cpu_count())
+    oc = so.default_config(action_conditioned=True, action_space=9, debug_core_appearance=True)
+    P = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    with torch.no_grad():
+        so.rollout(oc, P, z_last[:64], 2, actions[:64], app[:64])
+        t0 = time.perf_counter()
+        so.rollout(oc, P, z_last, num, actions, app)
+        dt = time.perf_counter() - t0
+    return z_last.shape[0] * num / dt
+
+
+# ----------------------------------------------------------------------------------------
+# arms
+# ----------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own algorithm on the host CPU (oracle port; the reference is pure Python
+    and is not on the GPU box).  Rank 0 only."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    model = build_model('cpu')
+    frames = [make_frames(BATCH, 100 + i) for i in range(2)]
+    value, threads, sec = cpu_train_baseline(args.steps, args.warmup, model.state_dict(), frames)
+    line = {
+        'impl': 'reference', 'metric': 'train_seqs_per_sec', 'value': value, 'unit': 'sequences/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_step': BATCH},
+        'cpu_baseline': {'value': value, 'unit': 'sequences/s', 'cores': threads, 'kind': 'port',
+                         'sample': '%d full batch-256 fwd+bwd steps of the oracle port (torch CPU, fp32)' % args.steps},
+        'e2e': {'value': value, 'unit': 'sequences/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from stove_b200 import _native as N
+    from stove_b200 import dp
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device('cuda', local if world > 1 else 0)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model = build_model(dev)
+    engine = dp.DataParallel(model)
+    lib = N.lib()
+
+    # ---- training: device-resident pool (value) -------------------------------------------
+    host_pool = [make_frames(BATCH, 1000 * rank + i).pin_memory() for i in range(POOL)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    losses = []
+    graphed = None
+    if not args.no_graph:
+        graphed = dp.GraphedStep(engine, dev_pool[0])
+
+    def run_step(x):
+        return graphed(x) if graphed is not None else engine.forward_backward(x, step_counter=1)
+
+    def step_resident(i):
+        losses.append(run_step(dev_pool[i % POOL]))
+
+    def step_e2e(i):
+        # public call with HOST frames: H2D copy of the batch + D2H read of the loss inside the step
+        x = host_pool[i % POOL].to(dev, non_blocking=True)
+        losses.append(run_step(x).item())
+
+    with ClockSampler(dev.index or 0) as clocks:
+        ms = timed(step_resident, args.steps, args.warmup, world, on_start=lambda: lib.stove_launch_count(1))
+        launches = lib.stove_launch_count(1)
+        if graphed is not None:       # replays launch the captured kernels without passing the counter
+            launches = graphed.native_launches * args.steps
+        ms_e2e = timed(step_e2e, args.steps, args.warmup, world)
+    clock_summary = clocks.summary()
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel pass (roofline) ----------------------------------------------------------
+    def step_eager(i):
+        engine.forward_backward(dev_pool[i % POOL], step_counter=1)
+
+    lib.stove_profile_enable(1)
+    N.profile_read()
+    timed(step_eager, args.steps, 1, world)      # events cannot be read back from a captured graph
+    lib.stove_profile_enable(0)
+    recs = N.profile_read()
+    per = {}
+    for name, t in recs:
+        per.setdefault(name, []).append(t)
+    n_steps_prof = args.steps + 1
+    share = {k: sum(v) / n_steps_prof for k, v in per.items()}           # ms per step per kernel
+    top = max(share, key=share.get) if share else None
+    peak, peak_src = measured_peaks()
+    roofline = None
+    if top is not None:
+        launches_top = len(per[top]) / n_steps_prof
+        avg_ms = sum(per[top]) / len(per[top])
+        units = kernel_algorithmic_bytes(top, BATCH)
+        achieved = units / (avg_ms * 1e-3) / 1e9 if units else None
+        roofline = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                    'avg_launch_ms': avg_ms, 'launches_per_step': launches_top,
+                    'algorithmic_bytes_per_launch': units, 'peak_source': peak_src,
+                    'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
+                    'native_share_of_step': sum(share.values()) / (ms / args.steps),
+                    'note': 'all hot-path kernels are FP32-issue/latency bound, not HBM bound (DESIGN.md); '
+                            'the HBM fraction is reported because the contract asks for it'}
+
+    # ---- rollouts (no collective: sequences shard over ranks) ----------------------------------
+    extra = {}
+    ac = build_ac_model(dev)
+    from stove_b200 import synth
+    n5, len5 = 1024, 2000
+    gen = torch.Generator().manual_seed(7 + rank)
+    z_last = torch.cat([0.2 + 0.3 * torch.rand(n5, O, 2, generator=gen),
+                        torch.rand(n5, O, 16, generator=gen) - 0.5], -1)
+    app = torch.rand(n5, O, 3, generator=gen)
+    act = synth.random_actions(n5, len5, 9, 11 + rank)
+    zl_d, app_d, act_d = z_last.to(dev), app.to(dev), act.to(dev)
+
+    def roll5(i):
+        ac.rollout(zl_d, len5, actions=act_d, appearance=app_d)
+
+    ms5 = timed(roll5, max(2, args.steps // 5), 1, world)
+    k5 = max(2, args.steps // 5)
+    extra['rollout_long'] = {'workload': 'action-conditioned world-model rollouts, 1024 sequences x 2000 frames per GPU',
+                             'metric': 'rollout_frames_per_sec', 'value': world * n5 * len5 * k5 / (ms5 * 1e-3),
+                             'unit': 'sequence-frames/s', 'ms_per_rollout': ms5 / k5}
+    # video prediction: 8-frame inference + 92-frame rollout (BASELINE configs[1])
+    n2 = 1024
+    x2 = make_frames(n2, 77 + rank).to(dev)
+
+    def predict(i):
+        with torch.no_grad():
+            _, prop, _ = model(x2, 0)
+            model.rollout(prop['z'][:, -1], num=92)
+
+    ms2 = timed(predict, max(2, args.steps // 2), 2, world)
+    k2 = max(2, args.steps // 2)
+    extra['video_prediction'] = {'workload': '8-frame inference + 92-frame rollout, 1024 sequences per GPU, 32x32',
+                                 'metric': 'rollout_frames_per_sec', 'value': world * n2 * 100 * k2 / (ms2 * 1e-3),
+                                 'unit': 'frames/s', 'ms_per_call': ms2 / k2}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        frames = [h.clone() for h in host_pool[:2]]
+        v, threads, sec = cpu_train_baseline(3, 1, model.state_dict(), frames)
+        cpu = {'value': v, 'unit': 'sequences/s', 'cores': threads, 'kind': 'port',
+               'sample': '3 full batch-256 fwd+bwd steps (after 1 warm-up) of the oracle port, torch CPU fp32',
+               'ms_per_step': sec * 1e3}
+        v5 = cpu_rollout_baseline(ac.state_dict(), z_last, act, app, 30)
+        extra['rollout_long']['cpu_baseline'] = {'value': v5, 'unit': 'sequence-frames/s', 'cores': threads,
+                                                 'kind': 'port', 'sample': '1024 sequences x 30 steps'}
+
+    line = {
+        'metric': 'train_seqs_per_sec', 'value': value, 'unit': 'sequences/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
+                   'l2_policy': 'inputs rotate through a %d-batch device pool (%.0f MB > 126 MB L2)'
+                                % (POOL, POOL * BATCH * T * 3 * RES * RES * 4 / 1e6),
+                   'cuda_graph': graphed is not None,
+                   'optimizer': 'excluded (metric is fwd+bwd); flat-bucket NCCL all-reduce included when N>1'},
+        'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': BATCH * T * 3 * RES * RES * 4, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches), 'gpu_launches_per_step': int(launches) // args.steps,
+        'clocks': clock_summary, 'roofline': roofline, 'cpu_baseline': cpu,
+        'loss_finite': bool(all(map(lambda v: v == v, [float(l) for l in losses[-3:]]))),
+    }
+    line.update(extra)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_algorithmic_bytes(kernel, batch):
+    """Minimum HBM traffic of ONE launch of `kernel` in the config-1 training step (DESIGN.md
+    section 4): bytes that must be read/written if every intermediate stayed on chip."""
+    frames = batch * (T - 2)              # the larger of the two likelihood calls per step
+    patches = frames * O
+    D_bg, D_obj = RES * RES, 100
+    table = {
+        'spn1_fwd_leaf': frames * D_bg * 4 * 2,                   # frame + mask in, 36 floats out (negligible)
+        'spn1_bwd_input': frames * D_bg * 4 * 3,                  # frame + mask in, mask gradient out
+        'spn1_bwd_leafparam': frames * D_bg * 4 * 2,
+        'spn2_fwd': patches * D_obj * 4 * 2 + patches * 4,
+        'spn2_bwd_nodes': patches * (240 + 120) * 4,
+        'spn2_bwd_input': patches * D_obj * 4 * 4,
+        'spn2_bwd_leafparam': patches * D_obj * 4 * 2,
+        'spn2_bwd_sumparam': patches * (12 * 30 + 6 * 21) * 4,
+        'scene_fwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
+        'scene_bwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
+        'gnn_fwd': batch * O * (16 + 32) * 4,
+        'gnn_bwd': batch * O * (16 + 32 + 16) * 4,
+        'bw_transform': batch * T * D_bg * 4 * 4,
+    }
+    return table.get(kernel)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='run the training step eagerly (no CUDA graph)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -32,6 +32,18 @@ extern "C" {
 const char* stove_last_error(void);
 int stove_abi_version(void);
 
+/* Launch accounting (measurement support, used by bench.py):
+ *   stove_launch_count   kernels launched by this library since the last reset
+ *   stove_profile_enable bracket every launch with CUDA events on its stream (not while capturing)
+ *   stove_profile_read   HOST arrays ids/ms (max_n entries): waits for the events, returns how many
+ *                        (kernel id, device milliseconds) records were written, clears the log
+ *   stove_kernel_name    name of a kernel id in [0, stove_kernel_count()) */
+int64_t stove_launch_count(int reset);
+int stove_profile_enable(int on);
+int stove_profile_read(int32_t* ids, float* ms, int max_n);
+const char* stove_kernel_name(int id);
+int stove_kernel_count(void);
+
 /* ------------------------------------------------------------------------------------
  * bw_transform: sum colour channels, clamp to [0,1]   (model/utils/utils.py:10-15)
  *   x [n][C][hw] -> y [n][hw]

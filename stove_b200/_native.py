@@ -36,6 +36,11 @@ P2, P1, PG = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg)
 SIGNATURES = {
     'stove_last_error': (C.c_char_p, []),
     'stove_abi_version': (C.c_int, []),
+    'stove_launch_count': (i64, [C.c_int]),
+    'stove_profile_enable': (C.c_int, [C.c_int]),
+    'stove_profile_read': (C.c_int, [vp, vp, C.c_int]),
+    'stove_kernel_name': (C.c_char_p, [C.c_int]),
+    'stove_kernel_count': (C.c_int, []),
     'stove_bw_transform': (C.c_int, [vp, vp, i64, C.c_int, i64, vp]),
     'stove_spn_pack_leaf_fwd': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp]),
     'stove_spn_pack_leaf_bwd': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp, vp, vp]),
@@ -80,6 +85,14 @@ def check(rc):
     if rc != 0:
         raise RuntimeError('stove_b200 native call failed (%d): %s'
                            % (rc, lib().stove_last_error().decode()))
+
+
+def profile_read(max_n=1 << 16):
+    """[(kernel name, device ms), ...] recorded since the last read (profiling must be enabled)."""
+    ids = (C.c_int32 * max_n)()
+    ms = (C.c_float * max_n)()
+    n = lib().stove_profile_read(C.cast(ids, C.c_void_p), C.cast(ms, C.c_void_p), max_n)
+    return [(lib().stove_kernel_name(ids[i]).decode(), float(ms[i])) for i in range(n)]
 
 
 def ptr(t):

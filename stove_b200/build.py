@@ -20,7 +20,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.inc'))]
     deps.append(os.path.join(os.path.dirname(HERE), 'include', 'stove_b200.h'))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -15,6 +15,85 @@ extern "C" const char* stove_last_error(void) { return g_err; }
 extern "C" int stove_abi_version(void) { return 1; }
 
 // ---------------------------------------------------------------------------------------
+// launch accounting + optional per-kernel event timing
+// ---------------------------------------------------------------------------------------
+#include <vector>
+#include <mutex>
+#include "kernel_names.inc"
+
+struct ProfRec {
+    int id;
+    cudaEvent_t a, b;
+};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+static bool g_prof_on = false;
+static int64_t g_launches = 0;
+
+int stove_prof_begin(int id, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ++g_launches;
+    if (!g_prof_on) return -1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return -1;
+    ProfRec r;
+    r.id = id;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!g_pool.empty()) {
+            *e = g_pool.back();
+            g_pool.pop_back();
+        } else if (cudaEventCreate(e) != cudaSuccess) {
+            return -1;
+        }
+    }
+    cudaEventRecord(r.a, s);
+    g_recs.push_back(r);
+    return (int)g_recs.size() - 1;
+}
+
+void stove_prof_end(int slot, cudaStream_t s) {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (slot < (int)g_recs.size()) cudaEventRecord(g_recs[slot].b, s);
+}
+
+extern "C" int stove_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return STOVE_OK;
+}
+
+// host arrays; waits for the recorded events, returns the number of records (and clears them)
+extern "C" int stove_profile_read(int32_t* ids, float* ms, int max_n) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (ProfRec& r : g_recs) {
+        float t = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&t, r.a, r.b);
+        if (n < max_n && ids && ms) {
+            ids[n] = r.id;
+            ms[n] = t;
+            ++n;
+        }
+        g_pool.push_back(r.a);
+        g_pool.push_back(r.b);
+    }
+    g_recs.clear();
+    return n;
+}
+
+extern "C" const char* stove_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : "?"; }
+extern "C" int stove_kernel_count(void) { return K_COUNT; }
+extern "C" int64_t stove_launch_count(int reset) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
 // bw_transform (model/utils/utils.py:10-15): y = clamp(sum_c x[:, c], 0, 1).
 // Pure streaming: reads C*4 B, writes 4 B per pixel; float4 vectorised when hw % 4 == 0.
 // ---------------------------------------------------------------------------------------
@@ -61,9 +140,9 @@ extern "C" int stove_bw_transform(const float* x, float* y, int64_t n, int chann
     int blocks = (int)((items + threads - 1) / threads);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (v4)
-        bw_transform_kernel_v4<<<blocks, threads, 0, st>>>((const float4*)x, (float4*)y, n, channels, hw / 4);
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel_v4<<<blocks, threads, 0, st>>>((const float4*)x, (float4*)y, n, channels, hw / 4));
     else
-        bw_transform_kernel<<<blocks, threads, 0, st>>>(x, y, n, channels, hw);
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<<<blocks, threads, 0, st>>>(x, y, n, channels, hw));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

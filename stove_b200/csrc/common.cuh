@@ -12,6 +12,19 @@
 
 void stove_set_error(const char* fmt, ...);
 
+// every kernel launch goes through STOVE_KERNEL: it counts launches (stove_launch_count) and,
+// when profiling is enabled (stove_profile_enable), brackets the launch with CUDA events on the
+// launching stream so bench.py can report per-kernel device time from the timed region.
+#include "kernel_ids.inc"
+int stove_prof_begin(int id, cudaStream_t s);
+void stove_prof_end(int slot, cudaStream_t s);
+#define STOVE_KERNEL(id, stream, ...)                 \
+    do {                                              \
+        const int ps_ = stove_prof_begin(id, stream); \
+        __VA_ARGS__;                                  \
+        stove_prof_end(ps_, stream);                  \
+    } while (0)
+
 #define STOVE_CHECK_ARG(cond, msg)                                  \
     do {                                                            \
         if (!(cond)) {                                              \

@@ -794,8 +794,8 @@ extern "C" int stove_gnn_fwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     GnnBuf b = gnn_buffers(*cfg, L.in_dim, seq, false);
     const size_t smem = sizeof(float) * ((size_t)b.total + L.total);
     STOVE_CUDA(cudaFuncSetAttribute(gnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gnn_fwd_kernel<<<gnn_target_ctas(n, seq), 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, s, actions, app,
-                                                                                   weights, out, reward);
+    STOVE_KERNEL(K_GNN_FWD, (cudaStream_t)stream, gnn_fwd_kernel<<<gnn_target_ctas(n, seq), 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, s, actions, app,
+                                                                                   weights, out, reward));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -851,10 +851,10 @@ extern "C" int stove_gnn_bwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     STOVE_CUDA(cudaFuncSetAttribute(gnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     // padding floats of the slabs are never written: clear them once so the reduction is clean
     STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
-    gnn_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(*cfg, L, p.seq, n, p.stage, s, actions, app, weights, g_out, g_reward,
-                                                g_s, (float*)workspace);
+    STOVE_KERNEL(K_GNN_BWD, st, gnn_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(*cfg, L, p.seq, n, p.stage, s, actions, app, weights, g_out, g_reward,
+                                                g_s, (float*)workspace));
     STOVE_LAUNCH_CHECK();
-    gnn_reduce_slabs_kernel<<<(L.total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.ctas, L.total, g_weights);
+    STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_kernel<<<(L.total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.ctas, L.total, g_weights));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -885,9 +885,9 @@ extern "C" int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, c
     STOVE_CUDA(cudaFuncSetAttribute(gnn_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t groups = (n + seq - 1) / seq;
     const int ctas = (int)(groups < 148 * 2 ? groups : 148 * 2);
-    gnn_rollout_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, num, z_last, actions, action_len,
+    STOVE_KERNEL(K_GNN_ROLLOUT, (cudaStream_t)stream, gnn_rollout_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, num, z_last, actions, action_len,
                                                                   app, weights, noise, pos_var, vel_std, latent_std,
-                                                                  z_out, std_out, logq_out, rewards);
+                                                                  z_out, std_out, logq_out, rewards));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -311,7 +311,7 @@ extern "C" int stove_scene_fwd(int64_t F, int O, int C, int A, int B, int pa, in
     }
     if (smem > 48 * 1024)
         STOVE_CUDA(cudaFuncSetAttribute(scene_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scene_fwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, patches, marg_patch, marg_bg, overlap);
+    STOVE_KERNEL(K_SCENE_FWD, (cudaStream_t)stream, scene_fwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, patches, marg_patch, marg_bg, overlap));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -332,8 +332,8 @@ extern "C" int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, in
     }
     if (smem > 48 * 1024)
         STOVE_CUDA(cudaFuncSetAttribute(scene_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    scene_bwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, g_patches, g_marg_patch,
-                                                                       g_marg_bg, g_overlap, g_z);
+    STOVE_KERNEL(K_SCENE_BWD, (cudaStream_t)stream, scene_bwd_kernel<<<(unsigned)F, 256, smem, (cudaStream_t)stream>>>(d, img, z, g_patches, g_marg_patch,
+                                                                       g_marg_bg, g_overlap, g_z));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

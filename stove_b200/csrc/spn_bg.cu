@@ -465,12 +465,12 @@ extern "C" int stove_spn1_fwd(const stove_spn1_struct* st, int64_t N, const floa
     dim3 grid(nch, (unsigned)(ppad / BG_FR));
     float* part = (float*)workspace;
     if (marg)
-        spn1_fwd_leaf_kernel<3, 6, true><<<grid, BG_FR, 0, s>>>(st->D, st->side, N, ppad, x, marg, leaf, part);
+        STOVE_KERNEL(K_SPN1_FWD_LEAF, s, spn1_fwd_leaf_kernel<3, 6, true><<<grid, BG_FR, 0, s>>>(st->D, st->side, N, ppad, x, marg, leaf, part));
     else
-        spn1_fwd_leaf_kernel<3, 6, false><<<grid, BG_FR, 0, s>>>(st->D, st->side, N, ppad, x, marg, leaf, part);
+        STOVE_KERNEL(K_SPN1_FWD_LEAF, s, spn1_fwd_leaf_kernel<3, 6, false><<<grid, BG_FR, 0, s>>>(st->D, st->side, N, ppad, x, marg, leaf, part));
     STOVE_LAUNCH_CHECK();
-    spn1_fwd_root_kernel<3, 6><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(nch, N, ppad, npad, part, rlin, rlog,
-                                                                        leaf_val, out);
+    STOVE_KERNEL(K_SPN1_FWD_ROOT, s, spn1_fwd_root_kernel<3, 6><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(nch, N, ppad, npad, part, rlin, rlog,
+                                                                        leaf_val, out));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -510,8 +510,8 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     const int D = st->D;
     const int64_t npad = round_up64(N, 32);
     Spn1Ws w = spn1_ws_layout(st, N, workspace);
-    spn1_bwd_root_kernel<3, 6><<<(unsigned)((npad + 127) / 128), 128, 0, s>>>(N, npad, rlin, rlog, leaf_val, out,
-                                                                           g_out, w.gleaf, w.aux_root, g_rlog);
+    STOVE_KERNEL(K_SPN1_BWD_ROOT, s, spn1_bwd_root_kernel<3, 6><<<(unsigned)((npad + 127) / 128), 128, 0, s>>>(N, npad, rlin, rlog, leaf_val, out,
+                                                                           g_out, w.gleaf, w.aux_root, g_rlog));
     STOVE_LAUNCH_CHECK();
     if (g_x || g_marg) {
         const size_t smem = sizeof(float) * 3 * BG_PXC * (BG_FR + 1);
@@ -519,11 +519,11 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
         if (marg) {
             STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_input_kernel<3, 6, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            spn1_bwd_input_kernel<3, 6, true><<<grid, BG_FR, smem, s>>>(D, st->side, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg);
+            STOVE_KERNEL(K_SPN1_BWD_INPUT, s, spn1_bwd_input_kernel<3, 6, true><<<grid, BG_FR, smem, s>>>(D, st->side, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
         } else {
             STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_input_kernel<3, 6, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            spn1_bwd_input_kernel<3, 6, false><<<grid, BG_FR, smem, s>>>(D, st->side, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg);
+            STOVE_KERNEL(K_SPN1_BWD_INPUT, s, spn1_bwd_input_kernel<3, 6, false><<<grid, BG_FR, smem, s>>>(D, st->side, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
         }
         STOVE_LAUNCH_CHECK();
     }
@@ -533,14 +533,14 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     {
         dim3 grid((D + 127) / 128, nchunk);
         if (marg)
-            spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf);
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         else
-            spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf);
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         STOVE_LAUNCH_CHECK();
     }
     {
         dim3 grid(st->R, nchunk);
-        spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s>>>(N, npad, chunk, rlin, w.aux_root, g_rlog);
+        STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
     return STOVE_OK;

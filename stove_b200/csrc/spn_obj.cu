@@ -649,12 +649,12 @@ static int spn2_fwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     int rc;
     if (marg) {
         if ((rc = set_smem(spn2_fwd_kernel<G, S, true>, smem))) return rc;
-        spn2_fwd_kernel<G, S, true><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
-                                                                  rlog, leaf_val, sum_val, out);
+        STOVE_KERNEL(K_SPN2_FWD, s, spn2_fwd_kernel<G, S, true><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
+                                                                  rlog, leaf_val, sum_val, out));
     } else {
         if ((rc = set_smem(spn2_fwd_kernel<G, S, false>, smem))) return rc;
-        spn2_fwd_kernel<G, S, false><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
-                                                                   rlog, leaf_val, sum_val, out);
+        STOVE_KERNEL(K_SPN2_FWD, s, spn2_fwd_kernel<G, S, false><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
+                                                                   rlog, leaf_val, sum_val, out));
     }
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
@@ -694,19 +694,19 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     {
         const size_t smem = sizeof(float) * (size_t)2 * Q * S * 32;
         if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S>, smem))) return rc;
-        spn2_bwd_nodes_kernel<G, S><<<blocks, 32 * Q, smem, s>>>(d, N, npad, wlin, wlog, rlin, rlog, leaf_val,
+        STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S><<<blocks, 32 * Q, smem, s>>>(d, N, npad, wlin, wlog, rlin, rlog, leaf_val,
                                                                   sum_val, out, g_out, w.gleaf, w.aux_reg,
-                                                                  w.aux_root, g_wlog, g_rlog);
+                                                                  w.aux_root, g_wlog, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
     if (g_x || g_marg) {
         const size_t smem = sizeof(float) * ((size_t)3 * D * 33 + (size_t)Q * 2 * G * 32);
         if (marg) {
             if ((rc = set_smem(spn2_bwd_input_kernel<G, true>, smem))) return rc;
-            spn2_bwd_input_kernel<G, true><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg);
+            STOVE_KERNEL(K_SPN2_BWD_INPUT, s, spn2_bwd_input_kernel<G, true><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
         } else {
             if ((rc = set_smem(spn2_bwd_input_kernel<G, false>, smem))) return rc;
-            spn2_bwd_input_kernel<G, false><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg);
+            STOVE_KERNEL(K_SPN2_BWD_INPUT, s, spn2_bwd_input_kernel<G, false><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
         }
         STOVE_LAUNCH_CHECK();
     }
@@ -721,10 +721,10 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         dim3 grid(Q, nchunk);
         if (marg) {
             if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
-            spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf);
+            STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         } else {
             if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
-            spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf);
+            STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         }
         STOVE_LAUNCH_CHECK();
     }
@@ -732,7 +732,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         const int need = (G * G > S * S) ? G * G : S * S;
         STOVE_CHECK_ARG(need <= 256, "G*G or S*S > 256");
         dim3 grid(Q + st->R, nchunk);
-        spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog);
+        STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
     return STOVE_OK;

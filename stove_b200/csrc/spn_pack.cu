@@ -76,8 +76,8 @@ extern "C" int stove_spn_pack_leaf_fwd(const float* means, const float* sigma_pa
                                        float min_var, float max_var, float* packed, void* stream) {
     STOVE_CHECK_ARG(means && sigma_params && dst_row && packed && rows > 0 && G > 0 && GP >= G, "bad argument");
     int total = rows * G;
-    pack_leaf_fwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        means, sigma_params, dst_row, rows, G, GP, min_var, max_var, packed);
+    STOVE_KERNEL(K_PACK_LEAF_FWD, (cudaStream_t)stream, pack_leaf_fwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        means, sigma_params, dst_row, rows, G, GP, min_var, max_var, packed));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -88,8 +88,8 @@ extern "C" int stove_spn_pack_leaf_bwd(const float* sigma_params, const int32_t*
                                        void* stream) {
     STOVE_CHECK_ARG(sigma_params && dst_row && g_packed && g_means && g_sigma_params && rows > 0, "bad argument");
     int total = rows * G;
-    pack_leaf_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        sigma_params, dst_row, rows, G, GP, min_var, max_var, g_packed, g_means, g_sigma_params);
+    STOVE_KERNEL(K_PACK_LEAF_BWD, (cudaStream_t)stream, pack_leaf_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        sigma_params, dst_row, rows, G, GP, min_var, max_var, g_packed, g_means, g_sigma_params));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -98,7 +98,7 @@ extern "C" int stove_spn_pack_sum_fwd(const float* raw, int nb, int K, int S, in
                                       float* wlin, void* stream) {
     STOVE_CHECK_ARG(raw && wlog && wlin && nb > 0 && K > 0 && S > 0 && SP >= S, "bad argument");
     int warps = nb * S;
-    pack_sum_fwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(raw, nb, K, S, SP, wlog, wlin);
+    STOVE_KERNEL(K_PACK_SUM_FWD, (cudaStream_t)stream, pack_sum_fwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(raw, nb, K, S, SP, wlog, wlin));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -107,7 +107,7 @@ extern "C" int stove_spn_pack_sum_bwd(const float* wlog, int nb, int K, int S, i
                                       const float* g_wlog, float* g_raw, void* stream) {
     STOVE_CHECK_ARG(wlog && g_wlog && g_raw && nb > 0 && K > 0 && S > 0 && SP >= S, "bad argument");
     int warps = nb * S;
-    pack_sum_bwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wlog, nb, K, S, SP, g_wlog, g_raw);
+    STOVE_KERNEL(K_PACK_SUM_BWD, (cudaStream_t)stream, pack_sum_bwd_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wlog, nb, K, S, SP, g_wlog, g_raw));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -1,0 +1,120 @@
+"""Batch-sharded data parallelism for STOVE training (one process per GPU).
+
+The reference is single-process / single-device (model/main.py:140-141); only the batch
+shards naturally.  Every rank holds a full replica, takes its slice of
+the batch, and the ELBO gradient -- the 110 live tensors, 1.41 M floats -- is exchanged as ONE
+flat fp32 bucket in a single NCCL all-reduce per step, before gradient clipping (which needs
+the global norm, model/video_prediction/train.py:471-472) and Adam.  Parameters that never
+receive a gradient (the two unused dynamics cores, SURVEY hard part 10) stay out of the
+bucket and keep `grad = None`, so Adam skips them exactly like the reference.
+Rollouts shard over sequences with no collective at all.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard(t, dim=0):
+    """This rank's contiguous slice of a tensor along `dim` (batch-sharding rule)."""
+    w, r = world(), rank()
+    n = t.shape[dim]
+    lo, hi = (n * r) // w, (n * (r + 1)) // w
+    return t.narrow(dim, lo, hi - lo)
+
+
+class DataParallel:
+    """Minimal DP engine around a `Stove` replica: zero_grad -> forward -> backward ->
+    flat-bucket all-reduce (-> clip -> optimizer step)."""
+
+    def __init__(self, model, reward_factor=0.0, broadcast=True):
+        self.model = model
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.reward_factor = reward_factor
+        self.flat = None
+        self.live = None
+        if broadcast and world() > 1:
+            for p in model.parameters():
+                dist.broadcast(p.data, 0)
+
+    # -- one training iteration (optimizer excluded) ---------------------------------------
+    def forward_backward(self, x, step_counter=1, actions=None, reward_target=None):
+        for p in self.params:
+            p.grad = None
+        elbo, prop, rewards = self.model(x, step_counter, actions=actions)
+        loss = -elbo
+        if reward_target is not None and self.reward_factor:
+            loss = loss + self.reward_factor * torch.nn.functional.binary_cross_entropy(rewards, reward_target)
+        loss.backward()
+        self.all_reduce_gradients()
+        return loss.detach()
+
+    def all_reduce_gradients(self):
+        """Average the gradients over ranks through one flat bucket; afterwards every `p.grad`
+        is a view into that bucket (`self.flat`)."""
+        live = [p for p in self.params if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in live])
+        if world() > 1:
+            dist.all_reduce(flat)
+            flat.mul_(1.0 / world())
+        at = 0
+        for p in live:
+            n = p.numel()
+            p.grad = flat[at:at + n].view_as(p)
+            at += n
+        self.flat, self.live = flat, live
+        return flat
+
+    def clip_and_step(self, optimizer, max_norm=1.0):
+        """Global-norm clipping on the flat bucket (train.py:471-472), then the optimizer."""
+        if max_norm is not None:
+            total = self.flat.norm()
+            self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        optimizer.step()
+
+
+class GraphedStep:
+    """One training iteration (zero_grad -> forward -> backward -> flat-bucket all-reduce)
+    captured in a CUDA graph and replayed per step.
+
+    The reference's step issues ~27 000 ATen ops and is launch bound on a GPU (SURVEY.md section
+    3.1); after fusion the step is still hundreds of short launches, so removing the per-launch
+    host cost matters more than any single kernel.  Capture is possible because the forward has
+    no host synchronisation (the reference's matcher has one per time step, stove.py:271-273).
+    Inputs are copied into static buffers; `loss` and every `p.grad` live at fixed addresses.
+    """
+
+    def __init__(self, engine, example_x, example_actions=None, example_reward_target=None, warmup=3):
+        self.engine = engine
+        self.x = example_x.clone()
+        self.actions = example_actions.clone() if example_actions is not None else None
+        self.target = example_reward_target.clone() if example_reward_target is not None else None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                engine.forward_backward(self.x, 1, self.actions, self.target)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _native
+        before = _native.lib().stove_launch_count(0)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = engine.forward_backward(self.x, 1, self.actions, self.target)
+        # kernels of the native library captured in (hence launched by every replay of) the graph
+        self.native_launches = _native.lib().stove_launch_count(0) - before
+
+    def __call__(self, x, actions=None, reward_target=None):
+        self.x.copy_(x, non_blocking=True)
+        if actions is not None:
+            self.actions.copy_(actions, non_blocking=True)
+        if reward_target is not None:
+            self.target.copy_(reward_target, non_blocking=True)
+        self.graph.replay()
+        return self.loss

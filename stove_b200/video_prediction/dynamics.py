@@ -67,9 +67,13 @@ class Dynamics(nn.Module):
         z_c = 2 * torch.sigmoid(z) - 1
         if z_std is None:
             return z_c, None
-        scale = z_std.new_tensor([self.c.pos_var] * 2 + [0.04] * 2
-                                 + [self.c.debug_latent_q_std] * (z_std.shape[-1] - 4))
-        return z_c, scale * torch.sigmoid(z_std)
+        cache = self.__dict__.setdefault('_const_cache', {})
+        key = (z_std.shape[-1], z_std.device, z_std.dtype)
+        if key not in cache:
+            cache[key] = torch.tensor([self.c.pos_var] * 2 + [0.04] * 2
+                                      + [self.c.debug_latent_q_std] * (z_std.shape[-1] - 4),
+                                      device=z_std.device, dtype=z_std.dtype)
+        return z_c, cache[key] * torch.sigmoid(z_std)
 
     # -- fused path ----------------------------------------------------------------------
     def kernel_cfg(self, with_actions, with_app, lim_enc=2):

@@ -93,11 +93,11 @@ class Stove(nn.Module):
     # -- object matching ------------------------------------------------------------------------
     def _match_inputs(self, z_sup, z_sup_std, obj_appearances):
         z = (z_sup + 1) / 2
-        m_idx = [2, 3]
+        m_idx = slice(2, 4)                 # a slice, not an index list: no H2D copy under graph capture
         if obj_appearances is not None:
             z = torch.cat([z, obj_appearances], -1)
             if self.c.debug_match_appearance:
-                m_idx += [4, 5, 6]
+                m_idx = slice(2, 7)
         if z_sup_std is not None:
             z = torch.cat([z, z_sup_std], -1)
         return z, m_idx

@@ -53,6 +53,14 @@ class Supair(nn.Module):
     def _align(self):
         return bool(getattr(self.c, 'align_corners', False))
 
+    def _const(self, key, values, like):
+        """Small constant tensors, cached per device/dtype (no H2D copy inside a captured step)."""
+        cache = self.__dict__.setdefault('_const_cache', {})
+        k = (key, like.device, like.dtype)
+        if k not in cache:
+            cache[k] = torch.tensor(values, device=like.device, dtype=like.dtype)
+        return cache[k]
+
     # -- likelihood ----------------------------------------------------------------------
     def likelihood(self, x, z_obj, packed=None):
         """x (n, T, c, w, h), z_obj (n*T*O, 4) [sx, sy, x, y] -> (log p(x|z) (n*T,), prop_dict)."""
@@ -96,10 +104,10 @@ class Supair(nn.Module):
         """(nTo, 8) raw encoder output -> means (sx, sy/sx, x, y) and stds, supair.py:112-149."""
         c = self.c
         sig = torch.sigmoid(zp)
-        hi = zp.new_tensor([c.max_obj_scale - c.min_obj_scale, c.max_y_scale - c.min_y_scale,
-                            2 * c.obj_pos_bound, 2 * c.obj_pos_bound])
-        lo = zp.new_tensor([c.min_obj_scale, c.min_y_scale, -c.obj_pos_bound, -c.obj_pos_bound])
-        std_scale = zp.new_tensor([c.scale_var, c.scale_var, c.pos_var, c.pos_var])
+        hi = self._const('hi', [c.max_obj_scale - c.min_obj_scale, c.max_y_scale - c.min_y_scale,
+                                2 * c.obj_pos_bound, 2 * c.obj_pos_bound], zp)
+        lo = self._const('lo', [c.min_obj_scale, c.min_y_scale, -c.obj_pos_bound, -c.obj_pos_bound], zp)
+        std_scale = self._const('std', [c.scale_var, c.scale_var, c.pos_var, c.pos_var], zp)
         return sig[:, :4] * hi + lo, sig[:, 4:8] * std_scale
 
     @staticmethod
