@@ -64,6 +64,13 @@ static GnnLayout gnn_layout(const stove_gnn_cfg* c) {
     return L;
 }
 
+// row stride of a feature-major buffer: multiple of 4, congruent 4 mod 8 (see dense())
+__host__ __device__ static inline int pad_ld(int rows) {
+    int ld = (rows + 3) & ~3;
+    if ((ld & 7) == 0) ld += 4;
+    return ld;
+}
+
 // shared-memory activation buffers for SEQ sequences (float offsets)
 struct GnnBuf {
     int ldo, ldp, lds;     // row strides: object rows, pair rows, sequence rows
@@ -78,9 +85,9 @@ struct GnnBuf {
 __host__ __device__ static inline GnnBuf gnn_buffers(const stove_gnn_cfg& c, int in_dim, int seq, bool bwd) {
     GnnBuf b;
     const int cl = c.cl, O = c.num_obj;
-    b.ldo = (seq * O) | 1;
-    b.ldp = (seq * O * O) | 1;
-    b.lds = seq | 1;
+    b.ldo = pad_ld(seq * O);
+    b.ldp = pad_ld(seq * O * O);
+    b.lds = pad_ld(seq);
     int at = 0;
     auto take = [&](int& off, int feats, int ld) { off = at; at += feats * ld; };
     take(b.sin, in_dim, b.ldo);
@@ -155,39 +162,84 @@ __device__ __forceinline__ float act_grad(float y, int act, int nonlin) {
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Dense layers on feature-major shared-memory activations ([feature][row], row stride ld).
+// ld is a multiple of 4 with ld = 4 (mod 8) (pad_ld): groups of 4 rows are float4-aligned and
+// lanes that walk the feature index hit distinct bank groups.  Register blocking: one item =
+// 4 rows x 4 output features (16 FMA per 2 LDS.128); small layers fall back to 1 x 4 so that
+// more threads take part (these launches are latency bound, not throughput bound).
+// Rows beyond `rows` inside the last group hold garbage; rows never mix, and every reduction
+// over rows below stops at `rows`.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 act4(float4 v, int act, int nonlin) {
+    v.x = apply_act(v.x, act, nonlin);
+    v.y = apply_act(v.y, act, nonlin);
+    v.z = apply_act(v.z, act, nonlin);
+    v.w = apply_act(v.w, act, nonlin);
+    return v;
+}
+
 // out[n][row] = act(b[n] + sum_k W[k][n] in[k][row]) (+ res[n][row]);  W is [K][N]
 __device__ void dense(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
                       const float* in, int ldi, float* out, int ldo, int rows, int act, int nonlin,
                       const float* res, int ldr) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if ((N & 3) == 0) {
-        const int n4 = N >> 2;
+        const int n4 = N >> 2, ngrp = (rows + 3) >> 2;
         const float4* W4 = reinterpret_cast<const float4*>(W);
         const float4* b4 = reinterpret_cast<const float4*>(bias);
-        for (int it = tid; it < rows * n4; it += nt) {
-            const int row = it / n4, c4 = it - row * n4;
-            float4 acc = b4[c4];
-            const float* ip = in + row;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float a = ip[k * ldi];
-                const float4 w = W4[k * n4 + c4];
-                acc.x = fmaf(a, w.x, acc.x);
-                acc.y = fmaf(a, w.y, acc.y);
-                acc.z = fmaf(a, w.z, acc.z);
-                acc.w = fmaf(a, w.w, acc.w);
-            }
-            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        if (ngrp * n4 * 2 >= nt) {
+            for (int it = tid; it < ngrp * n4; it += nt) {
+                const int rg = it / n4, c4 = it - rg * n4;
+                const float4 bv = b4[c4];
+                float4 a0 = make_float4(bv.x, bv.x, bv.x, bv.x), a1 = make_float4(bv.y, bv.y, bv.y, bv.y),
+                       a2 = make_float4(bv.z, bv.z, bv.z, bv.z), a3 = make_float4(bv.w, bv.w, bv.w, bv.w);
+                const float* ip = in + rg * 4;
+#pragma unroll 2
+                for (int k = 0; k < K; ++k) {
+                    const float4 x = *reinterpret_cast<const float4*>(ip + k * ldi);
+                    const float4 w = W4[k * n4 + c4];
+                    a0.x = fmaf(x.x, w.x, a0.x); a0.y = fmaf(x.y, w.x, a0.y); a0.z = fmaf(x.z, w.x, a0.z); a0.w = fmaf(x.w, w.x, a0.w);
+                    a1.x = fmaf(x.x, w.y, a1.x); a1.y = fmaf(x.y, w.y, a1.y); a1.z = fmaf(x.z, w.y, a1.z); a1.w = fmaf(x.w, w.y, a1.w);
+                    a2.x = fmaf(x.x, w.z, a2.x); a2.y = fmaf(x.y, w.z, a2.y); a2.z = fmaf(x.z, w.z, a2.z); a2.w = fmaf(x.w, w.z, a2.w);
+                    a3.x = fmaf(x.x, w.w, a3.x); a3.y = fmaf(x.y, w.w, a3.y); a3.z = fmaf(x.z, w.w, a3.z); a3.w = fmaf(x.w, w.w, a3.w);
+                }
+                float4 y[4] = {act4(a0, act, nonlin), act4(a1, act, nonlin), act4(a2, act, nonlin), act4(a3, act, nonlin)};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float y = apply_act(v[e], act, nonlin);
-                if (res) y += res[(c4 * 4 + e) * ldr + row];
-                out[(c4 * 4 + e) * ldo + row] = y;
+                for (int e = 0; e < 4; ++e) {
+                    if (res) {
+                        const float4 r = *reinterpret_cast<const float4*>(res + (c4 * 4 + e) * ldr + rg * 4);
+                        y[e].x += r.x; y[e].y += r.y; y[e].z += r.z; y[e].w += r.w;
+                    }
+                    *reinterpret_cast<float4*>(out + (c4 * 4 + e) * ldo + rg * 4) = y[e];
+                }
+            }
+        } else {
+            for (int it = tid; it < rows * n4; it += nt) {
+                const int row = it / n4, c4 = it - row * n4;
+                float4 acc = b4[c4];
+                const float* ip = in + row;
+#pragma unroll 4
+                for (int k = 0; k < K; ++k) {
+                    const float a = ip[k * ldi];
+                    const float4 w = W4[k * n4 + c4];
+                    acc.x = fmaf(a, w.x, acc.x);
+                    acc.y = fmaf(a, w.y, acc.y);
+                    acc.z = fmaf(a, w.z, acc.z);
+                    acc.w = fmaf(a, w.w, acc.w);
+                }
+                float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float y = apply_act(v[e], act, nonlin);
+                    if (res) y += res[(c4 * 4 + e) * ldr + row];
+                    out[(c4 * 4 + e) * ldo + row] = y;
+                }
             }
         }
     } else {
         for (int it = tid; it < rows * N; it += nt) {
-            const int row = it / N, n = it - row * N;
+            const int n = it / rows, row = it - n * rows;
             float acc = bias[n];
             for (int k = 0; k < K; ++k) acc = fmaf(in[k * ldi + row], W[k * N + n], acc);
             float y = apply_act(acc, act, nonlin);
@@ -197,31 +249,102 @@ __device__ void dense(const float* __restrict__ W, const float* __restrict__ bia
     }
 }
 
-// gin[k][row] (=, +=) sum_n W[k][n] gp[n][row]
+// gin[k][row] (=, +=) sum_n W[k][n] gp[n][row], optionally scaled by act'(ymul[k][row]);
+// gin may alias ymul (each element is read and written by the same thread)
 __device__ void dense_bwd_input(const float* __restrict__ W, int K, int N, const float* gp, int ldg,
-                                float* gin, int ldi, int rows, bool accumulate) {
-    for (int it = threadIdx.x; it < rows * K; it += blockDim.x) {
-        const int k = it / rows, row = it - k * rows;
-        float acc = 0.f;
-        const float* w = W + k * N;
-#pragma unroll 4
-        for (int n = 0; n < N; ++n) acc = fmaf(w[n], gp[n * ldg + row], acc);
-        if (accumulate) gin[k * ldi + row] += acc;
-        else gin[k * ldi + row] = acc;
+                                float* gin, int ldi, int rows, bool accumulate,
+                                const float* ymul = nullptr, int ldy = 0, int act = ACT_NONE, int nonlin = 0) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if ((N & 3) == 0) {
+        const int ngrp = (rows + 3) >> 2, n4 = N >> 2;
+        for (int it = tid; it < K * ngrp; it += nt) {
+            const int k = it / ngrp, rg = it - k * ngrp;
+            const float4* w4 = reinterpret_cast<const float4*>(W + k * N);
+            const float* g = gp + rg * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int q = 0; q < n4; ++q) {
+                const float4 w = w4[q];
+                const float4 g0 = *reinterpret_cast<const float4*>(g + (4 * q + 0) * ldg);
+                const float4 g1 = *reinterpret_cast<const float4*>(g + (4 * q + 1) * ldg);
+                const float4 g2 = *reinterpret_cast<const float4*>(g + (4 * q + 2) * ldg);
+                const float4 g3 = *reinterpret_cast<const float4*>(g + (4 * q + 3) * ldg);
+                acc.x = fmaf(w.x, g0.x, acc.x); acc.y = fmaf(w.x, g0.y, acc.y); acc.z = fmaf(w.x, g0.z, acc.z); acc.w = fmaf(w.x, g0.w, acc.w);
+                acc.x = fmaf(w.y, g1.x, acc.x); acc.y = fmaf(w.y, g1.y, acc.y); acc.z = fmaf(w.y, g1.z, acc.z); acc.w = fmaf(w.y, g1.w, acc.w);
+                acc.x = fmaf(w.z, g2.x, acc.x); acc.y = fmaf(w.z, g2.y, acc.y); acc.z = fmaf(w.z, g2.z, acc.z); acc.w = fmaf(w.z, g2.w, acc.w);
+                acc.x = fmaf(w.w, g3.x, acc.x); acc.y = fmaf(w.w, g3.y, acc.y); acc.z = fmaf(w.w, g3.z, acc.z); acc.w = fmaf(w.w, g3.w, acc.w);
+            }
+            float* dst = gin + k * ldi + rg * 4;
+            if (ymul) {
+                const float4 y = *reinterpret_cast<const float4*>(ymul + k * ldy + rg * 4);
+                acc.x *= act_grad(y.x, act, nonlin); acc.y *= act_grad(y.y, act, nonlin);
+                acc.z *= act_grad(y.z, act, nonlin); acc.w *= act_grad(y.w, act, nonlin);
+            }
+            if (accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(dst);
+                acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            *reinterpret_cast<float4*>(dst) = acc;
+        }
+    } else {
+        for (int it = tid; it < rows * K; it += nt) {
+            const int k = it / rows, row = it - k * rows;
+            float acc = 0.f;
+            const float* w = W + k * N;
+            for (int n = 0; n < N; ++n) acc = fmaf(w[n], gp[n * ldg + row], acc);
+            if (ymul) acc *= act_grad(ymul[k * ldy + row], act, nonlin);
+            if (accumulate) gin[k * ldi + row] += acc;
+            else gin[k * ldi + row] = acc;
+        }
     }
 }
 
 // slab_w[k][n] (=, +=) sum_row x[k][row] gp[n][row];  slab_b[n] (=, +=) sum_row gp[n][row]
 __device__ void dense_bwd_weight(float* __restrict__ slab_w, float* __restrict__ slab_b, int K, int N,
                                  const float* x, int ldx, const float* gp, int ldg, int rows, bool accumulate) {
-    for (int it = threadIdx.x; it < K * N; it += blockDim.x) {
-        const int n = it / K, k = it - n * K;      // k fastest: x reads stride ldx (odd), gp broadcast
-        float acc = 0.f;
-        for (int row = 0; row < rows; ++row) acc = fmaf(x[k * ldx + row], gp[n * ldg + row], acc);
-        if (accumulate) slab_w[k * N + n] += acc;
-        else slab_w[k * N + n] = acc;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int full = rows >> 2;
+    if ((N & 3) == 0) {
+        const int n4 = N >> 2;
+        for (int it = tid; it < K * n4; it += nt) {
+            const int c4 = it / K, k = it - c4 * K;      // k fastest: x reads hit distinct bank groups
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* xp = x + k * ldx;
+            const float* g = gp + (c4 * 4) * ldg;
+            for (int rg = 0; rg < full; ++rg) {
+                const float4 xv = *reinterpret_cast<const float4*>(xp + rg * 4);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 gv = *reinterpret_cast<const float4*>(g + e * ldg + rg * 4);
+                    acc[e] = fmaf(xv.x, gv.x, acc[e]);
+                    acc[e] = fmaf(xv.y, gv.y, acc[e]);
+                    acc[e] = fmaf(xv.z, gv.z, acc[e]);
+                    acc[e] = fmaf(xv.w, gv.w, acc[e]);
+                }
+            }
+            for (int row = full * 4; row < rows; ++row) {
+                const float xv = xp[row];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] = fmaf(xv, g[e * ldg + row], acc[e]);
+            }
+            float4* dst = reinterpret_cast<float4*>(slab_w + k * N + c4 * 4);
+            float4 v = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if (accumulate) {
+                const float4 o = *dst;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            *dst = v;
+        }
+    } else {
+        for (int it = tid; it < K * N; it += nt) {
+            const int n = it / K, k = it - n * K;
+            float acc = 0.f;
+            for (int row = 0; row < rows; ++row) acc = fmaf(x[k * ldx + row], gp[n * ldg + row], acc);
+            if (accumulate) slab_w[k * N + n] += acc;
+            else slab_w[k * N + n] = acc;
+        }
     }
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    for (int n = tid; n < N; n += nt) {
         float acc = 0.f;
         for (int row = 0; row < rows; ++row) acc += gp[n * ldg + row];
         if (accumulate) slab_b[n] += acc;
@@ -387,6 +510,7 @@ __global__ void __launch_bounds__(256) gnn_fwd_kernel(stove_gnn_cfg c, GnnLayout
     float* sm = smem + L.total;
     const GnnBuf b = gnn_buffers(c, L.in_dim, seq, false);
     stage_weights(weights, Ws, L.total);
+    for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
     const int cl = c.cl, O = c.num_obj;
     const int64_t ngroups = (n + seq - 1) / seq;
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -409,7 +533,7 @@ __global__ void __launch_bounds__(256) gnn_fwd_kernel(stove_gnn_cfg c, GnnLayout
 // rollout kernel: `num` dynamics steps with the state resident in shared memory
 //   (stove.py:823-846 + dynamics.py:147-179 constrain_z_dyn)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gnn_rollout_kernel(
+__global__ void __launch_bounds__(512) gnn_rollout_kernel(
     stove_gnn_cfg c, GnnLayout L, int seq, int64_t n, int num, const float* __restrict__ z_last,
     const float* __restrict__ actions, int action_len, const float* __restrict__ app,
     const float* __restrict__ weights, const float* __restrict__ noise, float pos_var, float vel_std,
@@ -420,6 +544,7 @@ __global__ void __launch_bounds__(256) gnn_rollout_kernel(
     float* sm = smem + L.total;
     const GnnBuf b = gnn_buffers(c, L.in_dim, seq, false);
     stage_weights(weights, Ws, L.total);
+    for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
     const int cl = c.cl, O = c.num_obj, half = cl / 2, zd = half + 2;
     const int64_t ngroups = (n + seq - 1) / seq;
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -490,6 +615,7 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
         sm = smem + L.total;
     }
     const GnnBuf b = gnn_buffers(c, L.in_dim, seq, true);
+    for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
     float* slab = slabs + (int64_t)blockIdx.x * L.total;
     const int cl = c.cl, O = c.num_obj, nl = c.nonlin, half = cl / 2;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -626,17 +752,10 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
         dense_bwd_weight(slab + L.att1_w, slab + L.att1_b, 2 * cl, cl, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, sm + b.g_a1, b.ldp, RP, accum);
         __syncthreads();
         // in place: ra0 <- (W^T g) * act'(ra0)
-        for (int it = tid; it < RP * 4 * cl; it += nt) {
-            const int k = it / RP, p = it - k * RP;
-            const bool is_rel = k < 2 * cl;
-            const float* w = W + (is_rel ? L.rel1_w + k * cl : L.att1_w + (k - 2 * cl) * cl);
-            const float* g = sm + (is_rel ? b.g_r1 : b.g_a1);
-            float acc = 0.f;
-#pragma unroll 4
-            for (int m = 0; m < cl; ++m) acc = fmaf(w[m], g[m * b.ldp + p], acc);
-            const float y = sm[b.ra0 + k * b.ldp + p];
-            sm[b.ra0 + k * b.ldp + p] = acc * act_grad(y, ACT_NL, nl);
-        }
+        dense_bwd_input(W + L.rel1_w, 2 * cl, cl, sm + b.g_r1, b.ldp, sm + b.ra0, b.ldp, RP, false,
+                        sm + b.ra0, b.ldp, ACT_NL, nl);
+        dense_bwd_input(W + L.att1_w, 2 * cl, cl, sm + b.g_a1, b.ldp, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, RP, false,
+                        sm + b.ra0 + 2 * cl * b.ldp, b.ldp, ACT_NL, nl);
         __syncthreads();
         // ---- rel0|att0 (2cl+1 -> 4cl)
         dense_bwd_weight(slab + L.ra0_w, slab + L.ra0_b, 2 * cl + 1, 4 * cl, sm + b.comb, b.ldp, sm + b.ra0, b.ldp, RP, accum);
@@ -885,7 +1004,7 @@ extern "C" int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, c
     STOVE_CUDA(cudaFuncSetAttribute(gnn_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t groups = (n + seq - 1) / seq;
     const int ctas = (int)(groups < 148 * 2 ? groups : 148 * 2);
-    STOVE_KERNEL(K_GNN_ROLLOUT, (cudaStream_t)stream, gnn_rollout_kernel<<<ctas, 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, num, z_last, actions, action_len,
+    STOVE_KERNEL(K_GNN_ROLLOUT, (cudaStream_t)stream, gnn_rollout_kernel<<<ctas, 512, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, num, z_last, actions, action_len,
                                                                   app, weights, noise, pos_var, vel_std, latent_std,
                                                                   z_out, std_out, logq_out, rewards));
     STOVE_LAUNCH_CHECK();
