@@ -146,6 +146,32 @@ int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int a
                     const float* g_overlap, float* g_z, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Sequence glue before the dynamics loop, one launch: Supair.constrain_zp (supair.py:112-149),
+ * Stove.match_objects (stove.py:200-329 / 331-430 / 432-514), Stove.fix_supair
+ * (stove.py:516-571), Stove.v_from_state / v_std_from_pos (stove.py:54-101).
+ *   zp [n][T][O][8] raw encoder output, app [n][T][O][3] or NULL
+ *   -> z_sup [n][T][O][4] (matched + smoothed means), z_full / std_full [n][T][O][6]
+ *      (means / stds with finite-difference velocities, zeros at t = 0), app_out [n][T][O][3]
+ *      (matched appearances, may be NULL), idx / flag [n][T][O] int32 (saved for the backward)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t T, num_obj;
+    int32_t match_kind;          /* 0 = '3_only', 1 = 'greedy', 2 = 'volatile' */
+    int32_t app_dim;             /* 0 or 3 */
+    int32_t match_appearance;    /* debug_match_appearance */
+    int32_t fix_supair;          /* debug_fix_supair */
+    float min_obj_scale, max_obj_scale, min_y_scale, max_y_scale, obj_pos_bound, scale_var, pos_var;
+    float fix_eps;               /* 0.095 in the reference */
+} stove_sup_cfg;
+
+int stove_sup_prepare_fwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, const float* app,
+                          float* z_sup, float* z_full, float* std_full, float* app_out,
+                          int32_t* idx, int32_t* flag, void* stream);
+int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, const int32_t* idx,
+                          const int32_t* flag, const float* std_full, const float* g_z_sup,
+                          const float* g_z_full, const float* g_std_full, float* g_zp, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * GNN dynamics: Dynamics.forward + core (dynamics.py:181-265) for core_idx 0, and the
  * rollout loop Stove.rollout (stove.py:777-861).
  *

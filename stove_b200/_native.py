@@ -25,12 +25,19 @@ class Spn1Struct(C.Structure):
     _fields_ = [('D', i32), ('R', i32), ('G', i32), ('side', vp)]
 
 
+class SupCfg(C.Structure):
+    _fields_ = [('T', i32), ('num_obj', i32), ('match_kind', i32), ('app_dim', i32),
+                ('match_appearance', i32), ('fix_supair', i32), ('min_obj_scale', f32),
+                ('max_obj_scale', f32), ('min_y_scale', f32), ('max_y_scale', f32), ('obj_pos_bound', f32),
+                ('scale_var', f32), ('pos_var', f32), ('fix_eps', f32)]
+
+
 class GnnCfg(C.Structure):
     _fields_ = [('num_obj', i32), ('cl', i32), ('action_dim', i32), ('app_dim', i32),
                 ('reward', i32), ('lim_enc', i32), ('nonlin', i32)]
 
 
-P2, P1, PG = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg)
+P2, P1, PG, PS = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg), C.POINTER(SupCfg)
 
 # name -> (restype, argtypes); must list every symbol of include/stove_b200.h
 SIGNATURES = {
@@ -55,6 +62,8 @@ SIGNATURES = {
     'stove_spn1_bwd': (C.c_int, [P1, i64] + [vp] * 13 + [vp]),
     'stove_scene_fwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 6 + [vp]),
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
+    'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
+    'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_gnn_weight_count': (i64, [PG]),
     'stove_gnn_weight_offsets': (C.c_int, [PG, vp, C.c_int]),
     'stove_gnn_bwd_workspace': (sz, [PG, i64]),

@@ -1,0 +1,313 @@
+// Fused sequence glue of Stove.stove_forward: everything between the encoder output and the
+// dynamics loop, one thread per sequence, forward and backward.
+//
+// Replaces (reference file:line, all in model/video_prediction/):
+//   Supair.constrain_zp                 supair.py:112-149
+//   Stove.match_objects (3 variants)    stove.py:200-329 (3_only), 331-430 (volatile), 432-514 (greedy)
+//   Stove.fix_supair                    stove.py:516-571
+//   Stove.v_from_state / v_std_from_pos stove.py:54-101
+// ~215 ATen launches forward and ~300 backward in the tensor version (and one host sync per
+// time step in the reference, stove.py:271-273) become two launches.  The matching is index
+// arithmetic on detached values; gradients flow through the gather, the smoothing select and
+// the finite differences only.
+#include "common.cuh"
+
+#define SG_MAX_T 16
+#define SG_MAX_O 9
+
+struct SupParams {
+    int T, O, match_kind;     // 0 = 3_only, 1 = greedy, 2 = volatile
+    int app_dim;              // 0 or 3
+    int match_app;            // use appearance in the matching distance
+    float scale_lo, scale_hi, ratio_lo, ratio_hi, pos_bound, scale_var, pos_var, fix_eps;
+    int fix;                  // debug_fix_supair
+};
+
+__device__ __forceinline__ float sq(float v) { return v * v; }
+
+// errors err[a][j] = |prev_a - cur_j|^2 over the matching features
+__device__ void match_errors(const SupParams& p, const float* prev_pos, const float* prev_app,
+                             const float* cur_pos, const float* cur_app, float* err) {
+    for (int a = 0; a < p.O; ++a)
+        for (int j = 0; j < p.O; ++j) {
+            float e = sq(prev_pos[a * 2] - cur_pos[j * 2]) + sq(prev_pos[a * 2 + 1] - cur_pos[j * 2 + 1]);
+            if (p.match_app)
+                for (int c = 0; c < 3; ++c) e += sq(prev_app[a * 3 + c] - cur_app[j * 3 + c]);
+            err[a * p.O + j] = e;
+        }
+}
+
+__device__ void match_step(const SupParams& p, float* err, int* idx) {
+    const int O = p.O;
+    if (p.match_kind == 2) {                         // volatile: argmin over current for each previous
+        for (int a = 0; a < O; ++a) {
+            int best = 0;
+            for (int j = 1; j < O; ++j)
+                if (err[a * O + j] < err[a * O + best]) best = j;
+            idx[a] = best;
+        }
+        return;
+    }
+    if (p.match_kind == 0) {                         // 3_only
+        for (int a = 0; a < O; ++a) {
+            int best = 0;
+            for (int j = 1; j < O; ++j)
+                if (err[a * O + j] < err[a * O + best]) best = j;
+            idx[a] = best;
+        }
+        const bool valid = idx[0] != idx[1] && idx[1] != idx[2] && idx[0] != idx[2];
+        if (valid) return;
+        // greedy repair (stove.py:278-295): row o takes its current argmin, that column is
+        // then knocked out for every row
+        for (int o = 0; o < O; ++o) {
+            int best = 0;
+            for (int j = 1; j < O; ++j)
+                if (err[o * O + j] < err[o * O + best]) best = j;
+            idx[o] = best;
+            for (int a = 0; a < O; ++a) err[a * O + best] = 1e12f;
+        }
+        return;
+    }
+    // greedy bipartite (stove.py:488-494): repeatedly take the global minimum, retire its row/column
+    for (int it = 0; it < O; ++it) {
+        int best = 0;
+        float mx = err[0];
+        for (int q = 1; q < O * O; ++q) {
+            if (err[q] < err[best]) best = q;
+            mx = fmaxf(mx, err[q]);
+        }
+        const int a = best / O, j = best - a * O;
+        idx[a] = j;
+        float big = mx + 1.f;
+        for (int q = 0; q < O; ++q) err[a * O + q] = big;
+        big = big + 1.f;                              // the reference re-evaluates max(errors) + 1
+        for (int q = 0; q < O; ++q) err[q * O + j] = big;
+    }
+}
+
+// raw encoder output zp [n][T][O][8] -> z_sup [n][T][O][4], z_full / std_full [n][T][O][6],
+// app_out [n][T][O][3] (matched appearances), idx [n][T][O] (int32), flag [n][T][O] (bit0, bit1)
+__global__ void sup_prepare_fwd_kernel(SupParams p, int64_t n, const float* __restrict__ zp,
+                                       const float* __restrict__ app, float* __restrict__ z_sup,
+                                       float* __restrict__ z_full, float* __restrict__ std_full,
+                                       float* __restrict__ app_out, int32_t* __restrict__ idx_out,
+                                       int32_t* __restrict__ flag_out) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int T = p.T, O = p.O;
+    float z[SG_MAX_T * SG_MAX_O * 8];                 // constrained (mean 4 | std 4), time-major
+    float zm[SG_MAX_T * SG_MAX_O * 8];                // matched
+    const float* src = zp + b * T * O * 8;
+    for (int q = 0; q < T * O; ++q) {
+        float s[8];
+        for (int f = 0; f < 8; ++f) s[f] = sigmoidf_(src[q * 8 + f]);
+        z[q * 8 + 0] = p.scale_lo + (p.scale_hi - p.scale_lo) * s[0];
+        z[q * 8 + 1] = p.ratio_lo + (p.ratio_hi - p.ratio_lo) * s[1];
+        z[q * 8 + 2] = p.pos_bound * (2.f * s[2] - 1.f);
+        z[q * 8 + 3] = p.pos_bound * (2.f * s[3] - 1.f);
+        z[q * 8 + 4] = p.scale_var * s[4];
+        z[q * 8 + 5] = p.scale_var * s[5];
+        z[q * 8 + 6] = p.pos_var * s[6];
+        z[q * 8 + 7] = p.pos_var * s[7];
+    }
+    // matching on positions scaled to [0, 1] ((z + 1) / 2, stove.py:220), detached
+    int idx[SG_MAX_O];
+    float appm[SG_MAX_T * SG_MAX_O * 3];
+    const float* asrc = app ? app + b * T * O * 3 : nullptr;
+    for (int a = 0; a < O; ++a) {
+        for (int f = 0; f < 8; ++f) zm[a * 8 + f] = z[a * 8 + f];
+        if (asrc) for (int c = 0; c < 3; ++c) appm[a * 3 + c] = asrc[a * 3 + c];
+        idx_out[(b * T) * O + a] = a;
+    }
+    for (int t = 1; t < T; ++t) {
+        float prev_pos[SG_MAX_O * 2], cur_pos[SG_MAX_O * 2], err[SG_MAX_O * SG_MAX_O];
+        for (int a = 0; a < O; ++a)
+            for (int d = 0; d < 2; ++d) {
+                prev_pos[a * 2 + d] = (zm[((t - 1) * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
+                cur_pos[a * 2 + d] = (z[(t * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
+            }
+        match_errors(p, prev_pos, asrc ? appm + (t - 1) * O * 3 : nullptr, cur_pos,
+                     asrc ? asrc + t * O * 3 : nullptr, err);
+        match_step(p, err, idx);
+        for (int a = 0; a < O; ++a) {
+            for (int f = 0; f < 8; ++f) zm[(t * O + a) * 8 + f] = z[(t * O + idx[a]) * 8 + f];
+            if (asrc) for (int c = 0; c < 3; ++c) appm[(t * O + a) * 3 + c] = asrc[(t * O + idx[a]) * 3 + c];
+            idx_out[(b * T + t) * O + a] = idx[a];
+        }
+    }
+    if (app_out && asrc)
+        for (int q = 0; q < T * O * 3; ++q) app_out[b * T * O * 3 + q] = appm[q];
+    // smoothing of glitches (stove.py:516-571): flags from the first two features
+    // (z is reused as the fixed tensor from here on)
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < O; ++a) {
+            int fl = 0;
+            if (p.fix && t >= 1 && t + 1 < T)
+                for (int d = 0; d < 2; ++d) {
+                    const float before = fabsf(zm[(t * O + a) * 8 + d] - zm[((t - 1) * O + a) * 8 + d]);
+                    const float after = fabsf(zm[((t + 1) * O + a) * 8 + d] - zm[(t * O + a) * 8 + d]);
+                    if (before > p.fix_eps && after > p.fix_eps) fl |= 1 << d;
+                }
+            flag_out[(b * T + t) * O + a] = fl;
+            for (int f = 0; f < 8; ++f) {
+                float v = zm[(t * O + a) * 8 + f];
+                if (fl & (1 << (f & 1))) v = 0.5f * (zm[((t - 1) * O + a) * 8 + f] + zm[((t + 1) * O + a) * 8 + f]);
+                z[(t * O + a) * 8 + f] = v;
+            }
+        }
+    // outputs
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < O; ++a) {
+            const int q = t * O + a;
+            const int64_t o4 = (b * T * O + q) * 4, o6 = (b * T * O + q) * 6;
+            for (int f = 0; f < 4; ++f) z_sup[o4 + f] = z[q * 8 + f];
+            if (t == 0) {
+                for (int f = 0; f < 6; ++f) { z_full[o6 + f] = 0.f; std_full[o6 + f] = 0.f; }
+            } else {
+                const int qp = (t - 1) * O + a;
+                for (int f = 0; f < 4; ++f) { z_full[o6 + f] = z[q * 8 + f]; std_full[o6 + f] = z[q * 8 + 4 + f]; }
+                for (int d = 0; d < 2; ++d) {
+                    z_full[o6 + 4 + d] = z[q * 8 + 2 + d] - z[qp * 8 + 2 + d];
+                    std_full[o6 + 4 + d] = sqrtf(sq(z[q * 8 + 6 + d]) + sq(z[qp * 8 + 6 + d]));
+                }
+            }
+        }
+}
+
+__global__ void sup_prepare_bwd_kernel(SupParams p, int64_t n, const float* __restrict__ zp,
+                                       const int32_t* __restrict__ idx_in, const int32_t* __restrict__ flag_in,
+                                       const float* __restrict__ std_full, const float* __restrict__ g_z_sup,
+                                       const float* __restrict__ g_z_full, const float* __restrict__ g_std_full,
+                                       float* __restrict__ g_zp) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int T = p.T, O = p.O;
+    float gf[SG_MAX_T * SG_MAX_O * 8];     // gradient w.r.t. the fixed (smoothed) tensor
+    float gm[SG_MAX_T * SG_MAX_O * 8];     // w.r.t. the matched tensor
+    float sf[SG_MAX_T * SG_MAX_O * 2];     // fixed position stds, recomputed below
+    for (int q = 0; q < T * O * 8; ++q) { gf[q] = 0.f; gm[q] = 0.f; }
+    // recompute the fixed position stds (features 6, 7) needed by the sqrt derivative
+    {
+        const float* src = zp + b * T * O * 8;
+        float sm_[SG_MAX_T * SG_MAX_O * 2];
+        for (int t = 0; t < T; ++t)
+            for (int a = 0; a < O; ++a) {
+                const int j = idx_in[(b * T + t) * O + a];
+                for (int d = 0; d < 2; ++d) sm_[(t * O + a) * 2 + d] = p.pos_var * sigmoidf_(src[(t * O + j) * 8 + 6 + d]);
+            }
+        for (int t = 0; t < T; ++t)
+            for (int a = 0; a < O; ++a) {
+                const int fl = flag_in[(b * T + t) * O + a];
+                for (int d = 0; d < 2; ++d) {
+                    float v = sm_[(t * O + a) * 2 + d];
+                    if (fl & (1 << d)) v = 0.5f * (sm_[((t - 1) * O + a) * 2 + d] + sm_[((t + 1) * O + a) * 2 + d]);
+                    sf[(t * O + a) * 2 + d] = v;
+                }
+            }
+    }
+    // outputs -> fixed tensor
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < O; ++a) {
+            const int q = t * O + a;
+            const int64_t o4 = (b * T * O + q) * 4, o6 = (b * T * O + q) * 6;
+            if (g_z_sup) for (int f = 0; f < 4; ++f) gf[q * 8 + f] += g_z_sup[o4 + f];
+            if (t == 0) continue;
+            const int qp = (t - 1) * O + a;
+            for (int f = 0; f < 4; ++f) {
+                if (g_z_full) gf[q * 8 + f] += g_z_full[o6 + f];
+                if (g_std_full) gf[q * 8 + 4 + f] += g_std_full[o6 + f];
+            }
+            for (int d = 0; d < 2; ++d) {
+                if (g_z_full) {
+                    const float g = g_z_full[o6 + 4 + d];
+                    gf[q * 8 + 2 + d] += g;
+                    gf[qp * 8 + 2 + d] -= g;
+                }
+                if (g_std_full) {
+                    const float v = std_full[o6 + 4 + d];
+                    const float g = g_std_full[o6 + 4 + d] / v;
+                    gf[q * 8 + 6 + d] += g * sf[q * 2 + d];
+                    gf[qp * 8 + 6 + d] += g * sf[qp * 2 + d];
+                }
+            }
+        }
+    // smoothing select -> matched tensor
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < O; ++a) {
+            const int fl = flag_in[(b * T + t) * O + a];
+            for (int f = 0; f < 8; ++f) {
+                const float g = gf[(t * O + a) * 8 + f];
+                if (fl & (1 << (f & 1))) {
+                    gm[((t - 1) * O + a) * 8 + f] += 0.5f * g;
+                    gm[((t + 1) * O + a) * 8 + f] += 0.5f * g;
+                } else {
+                    gm[(t * O + a) * 8 + f] += g;
+                }
+            }
+        }
+    // gather -> constrained tensor (scatter-add: `volatile` matching may pick an object twice)
+    for (int q = 0; q < T * O * 8; ++q) gf[q] = 0.f;
+    for (int t = 0; t < T; ++t)
+        for (int a = 0; a < O; ++a) {
+            const int j = idx_in[(b * T + t) * O + a];
+            for (int f = 0; f < 8; ++f) gf[(t * O + j) * 8 + f] += gm[(t * O + a) * 8 + f];
+        }
+    // constrain_zp: every output is scale * sigmoid(raw) + offset
+    const float* src = zp + b * T * O * 8;
+    const float sc[8] = {p.scale_hi - p.scale_lo, p.ratio_hi - p.ratio_lo, 2.f * p.pos_bound, 2.f * p.pos_bound,
+                         p.scale_var, p.scale_var, p.pos_var, p.pos_var};
+    for (int q = 0; q < T * O; ++q)
+        for (int f = 0; f < 8; ++f) {
+            const float s = sigmoidf_(src[q * 8 + f]);
+            g_zp[b * T * O * 8 + q * 8 + f] = gf[q * 8 + f] * sc[f] * s * (1.f - s);
+        }
+}
+
+static int sup_check(const SupParams& p, int64_t n) {
+    STOVE_CHECK_ARG(n >= 0 && p.T >= 2 && p.T <= SG_MAX_T && p.O >= 1 && p.O <= SG_MAX_O, "T or O out of range");
+    STOVE_CHECK_ARG(p.match_kind >= 0 && p.match_kind <= 2, "bad match kind");
+    STOVE_CHECK_ARG(p.match_kind != 0 || p.O == 3, "3_only matching needs 3 objects");
+    return STOVE_OK;
+}
+
+static SupParams make_params(const stove_sup_cfg* c) {
+    SupParams p;
+    p.T = c->T; p.O = c->num_obj; p.match_kind = c->match_kind; p.app_dim = c->app_dim;
+    p.match_app = c->match_appearance;
+    p.scale_lo = c->min_obj_scale; p.scale_hi = c->max_obj_scale;
+    p.ratio_lo = c->min_y_scale; p.ratio_hi = c->max_y_scale;
+    p.pos_bound = c->obj_pos_bound; p.scale_var = c->scale_var; p.pos_var = c->pos_var;
+    p.fix_eps = c->fix_eps; p.fix = c->fix_supair;
+    return p;
+}
+
+extern "C" int stove_sup_prepare_fwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, const float* app,
+                                     float* z_sup, float* z_full, float* std_full, float* app_out,
+                                     int32_t* idx, int32_t* flag, void* stream) {
+    STOVE_CHECK_ARG(cfg && zp && z_sup && z_full && std_full && idx && flag, "null pointer");
+    SupParams p = make_params(cfg);
+    int rc = sup_check(p, n);
+    if (rc) return rc;
+    STOVE_CHECK_ARG(!(p.match_app && !app), "appearance matching without appearances");
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(
+        p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, const int32_t* idx,
+                                     const int32_t* flag, const float* std_full, const float* g_z_sup,
+                                     const float* g_z_full, const float* g_std_full, float* g_zp, void* stream) {
+    STOVE_CHECK_ARG(cfg && zp && idx && flag && std_full && g_zp, "null pointer");
+    SupParams p = make_params(cfg);
+    int rc = sup_check(p, n);
+    if (rc) return rc;
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_SUP_PREPARE_BWD, s, sup_prepare_bwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(
+        p, n, zp, idx, flag, std_full, g_z_sup, g_z_full, g_std_full, g_zp));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -596,6 +596,220 @@ __global__ void __launch_bounds__(512) gnn_rollout_kernel(
 }
 
 // ------------------------------------------------------------------------------------
+// Backward core: expects the forward activations (gnn_forward_core) and the upstream gradient
+// sm[b.g_out] in shared memory; leaves d/d(s_in) in sm[b.g_sin] (first cl/2 features, raw
+// pass-through already added) and writes this CTA's weight gradients into `slab`.
+// ------------------------------------------------------------------------------------
+__device__ void gnn_backward_core(const stove_gnn_cfg& c, const GnnLayout& L, const GnnBuf& b,
+                                  const float* __restrict__ W, float* sm, float* __restrict__ slab, bool accum,
+                                  int nseq, const float* __restrict__ actions, int64_t act_stride,
+                                  const float* __restrict__ g_reward, int64_t g_reward_stride) {
+    const int cl = c.cl, O = c.num_obj, nl = c.nonlin, half = cl / 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int RO = nseq * O, RP = nseq * O * O;
+    // ---- out1: result = W o1 + b + o1
+    dense_bwd_weight(slab + L.out1_w, slab + L.out1_b, cl, cl, sm + b.o1, b.ldo, sm + b.g_out, b.ldo, RO, accum);
+    dense_bwd_input(W + L.out1_w, cl, cl, sm + b.g_out, b.ldo, sm + b.g_o1, b.ldo, RO, false);
+    __syncthreads();
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        const float y = sm[b.o1 + k * b.ldo + row];
+        sm[b.g_o1 + k * b.ldo + row] = (sm[b.g_o1 + k * b.ldo + row] + sm[b.g_out + k * b.ldo + row]) * (1.f - y * y);
+    }
+    __syncthreads();
+    // ---- out0: o1 = tanh(W cat + b); g_o1 now holds the pre-activation gradient
+    dense_bwd_weight(slab + L.out0_w, slab + L.out0_b, 2 * cl, cl, sm + b.cat, b.ldo, sm + b.g_o1, b.ldo, RO, accum);
+    dense_bwd_input(W + L.out0_w, 2 * cl, cl, sm + b.g_o1, b.ldo, sm + b.g_cat, b.ldo, RO, false);
+    __syncthreads();
+    // g_cat[0:cl] = g_f3 ; g_cat[cl:2cl] -> g_s
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        sm[b.g_s + k * b.ldo + row] = sm[b.g_cat + (cl + k) * b.ldo + row];
+    }
+    // ---- aff2: f3 = W f2 + b
+    dense_bwd_weight(slab + L.aff2_w, slab + L.aff2_b, cl, cl, sm + b.f2, b.ldo, sm + b.g_cat, b.ldo, RO, accum);
+    dense_bwd_input(W + L.aff2_w, cl, cl, sm + b.g_cat, b.ldo, sm + b.g_f2, b.ldo, RO, false);
+    __syncthreads();
+    // ---- aff1: f2 = tanh(W f1 + b) + f1 ; tanh output = f2 - f1
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        const float th = sm[b.f2 + k * b.ldo + row] - sm[b.f1 + k * b.ldo + row];
+        const float g = sm[b.g_f2 + k * b.ldo + row];
+        sm[b.g_f1 + k * b.ldo + row] = g;                       // residual path
+        sm[b.g_f2 + k * b.ldo + row] = g * (1.f - th * th);     // pre-activation gradient
+    }
+    __syncthreads();
+    dense_bwd_weight(slab + L.aff1_w, slab + L.aff1_b, cl, cl, sm + b.f1, b.ldo, sm + b.g_f2, b.ldo, RO, accum);
+    dense_bwd_input(W + L.aff1_w, cl, cl, sm + b.g_f2, b.ldo, sm + b.g_f1, b.ldo, RO, true);
+    __syncthreads();
+    // ---- aff0: f1 = tanh(W d + b)
+    scale_by_act_grad(sm + b.g_f1, b.ldo, sm + b.f1, b.ldo, cl, RO, ACT_TANH, nl);
+    __syncthreads();
+    dense_bwd_weight(slab + L.aff0_w, slab + L.aff0_b, cl, cl, sm + b.d, b.ldo, sm + b.g_f1, b.ldo, RO, accum);
+    dense_bwd_input(W + L.aff0_w, cl, cl, sm + b.g_f1, b.ldo, sm + b.g_d, b.ldo, RO, false);
+    __syncthreads();
+    // ---- reward head (dynamics.py:254-263)
+    if (c.reward) {
+        for (int sq = tid; sq < nseq; sq += nt) {
+            const float r = sm[b.rew + sq];
+            const float g = g_reward ? __ldg(g_reward + sq * g_reward_stride) : 0.f;
+            sm[b.g_rew + sq] = g * r * (1.f - r);
+        }
+        __syncthreads();
+        dense_bwd_weight(slab + L.rew14_w, slab + L.rew14_b, cl / 4, 1, sm + b.r3, b.lds, sm + b.g_rew, b.lds, nseq, accum);
+        dense_bwd_input(W + L.rew14_w, cl / 4, 1, sm + b.g_rew, b.lds, sm + b.g_r3, b.lds, nseq, false);
+        __syncthreads();
+        scale_by_act_grad(sm + b.g_r3, b.lds, sm + b.r3, b.lds, cl / 4, nseq, ACT_RELU, nl);
+        __syncthreads();
+        dense_bwd_weight(slab + L.rew12_w, slab + L.rew12_b, cl / 2, cl / 4, sm + b.r2, b.lds, sm + b.g_r3, b.lds, nseq, accum);
+        dense_bwd_input(W + L.rew12_w, cl / 2, cl / 4, sm + b.g_r3, b.lds, sm + b.g_r2, b.lds, nseq, false);
+        __syncthreads();
+        scale_by_act_grad(sm + b.g_r2, b.lds, sm + b.r2, b.lds, cl / 2, nseq, ACT_RELU, nl);
+        __syncthreads();
+        dense_bwd_weight(slab + L.rew10_w, slab + L.rew10_b, cl, cl / 2, sm + b.rsum, b.lds, sm + b.g_r2, b.lds, nseq, accum);
+        dense_bwd_input(W + L.rew10_w, cl, cl / 2, sm + b.g_r2, b.lds, sm + b.g_rsum, b.lds, nseq, false);
+        __syncthreads();
+        for (int it = tid; it < cl * RO; it += nt) {
+            const int k = it / RO, row = it - k * RO;
+            sm[b.g_rh1 + k * b.ldo + row] = sm[b.g_rsum + k * b.lds + row / O];
+        }
+        __syncthreads();
+        dense_bwd_weight(slab + L.rew02_w, slab + L.rew02_b, cl, cl, sm + b.rh0, b.ldo, sm + b.g_rh1, b.ldo, RO, accum);
+        dense_bwd_input(W + L.rew02_w, cl, cl, sm + b.g_rh1, b.ldo, sm + b.g_rh0, b.ldo, RO, false);
+        __syncthreads();
+        scale_by_act_grad(sm + b.g_rh0, b.ldo, sm + b.rh0, b.ldo, cl, RO, ACT_RELU, nl);
+        __syncthreads();
+        dense_bwd_weight(slab + L.rew00_w, slab + L.rew00_b, cl, cl, sm + b.d, b.ldo, sm + b.g_rh0, b.ldo, RO, accum);
+        dense_bwd_input(W + L.rew00_w, cl, cl, sm + b.g_rh0, b.ldo, sm + b.g_d, b.ldo, RO, true);
+        __syncthreads();
+    }
+    // ---- aggregation: d_i = self_i + sum_j mask rel_ij att_ij
+    for (int p = tid; p < RP; p += nt) {
+        const int sq = p / (O * O), ij = p - sq * O * O, i = ij / O, j = ij - i * O;
+        const float mask = (i == j) ? 0.f : 1.f;
+        float acc = 0.f;
+        for (int k = 0; k < cl; ++k) acc = fmaf(sm[b.g_d + k * b.ldo + sq * O + i], sm[b.rel + k * b.ldp + p], acc);
+        // att = exp(lin): d att / d lin = att
+        sm[b.g_att + p] = acc * mask * sm[b.att + p];
+    }
+    __syncthreads();
+    for (int it = tid; it < cl * RP; it += nt) {
+        const int k = it / RP, p = it - k * RP;
+        const int sq = p / (O * O), ij = p - sq * O * O, i = ij / O, j = ij - i * O;
+        const float mask = (i == j) ? 0.f : 1.f;
+        // overwrite rel with its gradient (rel itself is no longer needed)
+        sm[b.rel + k * b.ldp + p] = sm[b.g_d + k * b.ldo + sq * O + i] * mask * sm[b.att + p];
+    }
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        sm[b.g_self + k * b.ldo + row] = sm[b.g_d + k * b.ldo + row];
+    }
+    __syncthreads();
+    // ---- att2 (cl -> 1, exp) and rel2 (rel = W r1 + b + r1)
+    dense_bwd_weight(slab + L.att2_w, slab + L.att2_b, cl, 1, sm + b.a1, b.ldp, sm + b.g_att, b.ldp, RP, accum);
+    dense_bwd_input(W + L.att2_w, cl, 1, sm + b.g_att, b.ldp, sm + b.g_a1, b.ldp, RP, false);
+    dense_bwd_weight(slab + L.rel2_w, slab + L.rel2_b, cl, cl, sm + b.r1, b.ldp, sm + b.rel, b.ldp, RP, accum);
+    dense_bwd_input(W + L.rel2_w, cl, cl, sm + b.rel, b.ldp, sm + b.g_r1, b.ldp, RP, false);
+    __syncthreads();
+    for (int it = tid; it < cl * RP; it += nt) {
+        const int k = it / RP, p = it - k * RP;
+        sm[b.g_r1 + k * b.ldp + p] = (sm[b.g_r1 + k * b.ldp + p] + sm[b.rel + k * b.ldp + p]) *
+                                     act_grad(sm[b.r1 + k * b.ldp + p], ACT_NL, nl);
+        sm[b.g_a1 + k * b.ldp + p] *= act_grad(sm[b.a1 + k * b.ldp + p], ACT_NL, nl);
+    }
+    __syncthreads();
+    // ---- rel1 / att1 (2cl -> cl); input gradients overwrite... need r0/a0 for the weight
+    // gradient first, so compute weight gradients, then input gradients into comb-sized scratch
+    dense_bwd_weight(slab + L.rel1_w, slab + L.rel1_b, 2 * cl, cl, sm + b.ra0, b.ldp, sm + b.g_r1, b.ldp, RP, accum);
+    dense_bwd_weight(slab + L.att1_w, slab + L.att1_b, 2 * cl, cl, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, sm + b.g_a1, b.ldp, RP, accum);
+    __syncthreads();
+    // in place: ra0 <- (W^T g) * act'(ra0)
+    dense_bwd_input(W + L.rel1_w, 2 * cl, cl, sm + b.g_r1, b.ldp, sm + b.ra0, b.ldp, RP, false,
+                    sm + b.ra0, b.ldp, ACT_NL, nl);
+    dense_bwd_input(W + L.att1_w, 2 * cl, cl, sm + b.g_a1, b.ldp, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, RP, false,
+                    sm + b.ra0 + 2 * cl * b.ldp, b.ldp, ACT_NL, nl);
+    __syncthreads();
+    // ---- rel0|att0 (2cl+1 -> 4cl)
+    dense_bwd_weight(slab + L.ra0_w, slab + L.ra0_b, 2 * cl + 1, 4 * cl, sm + b.comb, b.ldp, sm + b.ra0, b.ldp, RP, accum);
+    __syncthreads();
+    dense_bwd_input(W + L.ra0_w, 2 * cl + 1, 4 * cl, sm + b.ra0, b.ldp, sm + b.comb, b.ldp, RP, false);
+    __syncthreads();
+    // ---- scatter pair-input gradients to the objects (comb now holds g_comb)
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        const int sq = row / O, i = row - sq * O;
+        float acc = 0.f;
+        for (int j = 0; j < O; ++j) {
+            acc += sm[b.comb + k * b.ldp + sq * O * O + i * O + j];            // as first argument
+            acc += sm[b.comb + (cl + k) * b.ldp + sq * O * O + j * O + i];     // as second argument
+        }
+        if (k < 2) {
+            // dist_ij = (x_i-x_j)^2 + (y_i-y_j)^2
+            const float xi = sm[b.s + k * b.ldo + row];
+            for (int j = 0; j < O; ++j) {
+                const float xj = sm[b.s + k * b.ldo + sq * O + j];
+                acc += 2.f * (xi - xj) * (sm[b.comb + 2 * cl * b.ldp + sq * O * O + i * O + j] +
+                                          sm[b.comb + 2 * cl * b.ldp + sq * O * O + j * O + i]);
+            }
+        }
+        sm[b.g_s + k * b.ldo + row] += acc;
+    }
+    // ---- self1: self = W h + b + h
+    dense_bwd_weight(slab + L.self1_w, slab + L.self1_b, cl, cl, sm + b.h, b.ldo, sm + b.g_self, b.ldo, RO, accum);
+    dense_bwd_input(W + L.self1_w, cl, cl, sm + b.g_self, b.ldo, sm + b.g_h, b.ldo, RO, false);
+    __syncthreads();
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        sm[b.g_h + k * b.ldo + row] = (sm[b.g_h + k * b.ldo + row] + sm[b.g_self + k * b.ldo + row]) *
+                                      act_grad(sm[b.h + k * b.ldo + row], ACT_NL, nl);
+    }
+    __syncthreads();
+    // ---- self0: h = phi(W s + b)
+    dense_bwd_weight(slab + L.self0_w, slab + L.self0_b, cl, cl, sm + b.s, b.ldo, sm + b.g_h, b.ldo, RO, accum);
+    dense_bwd_input(W + L.self0_w, cl, cl, sm + b.g_h, b.ldo, sm + b.g_s, b.ldo, RO, true);
+    __syncthreads();
+    // ---- encoder: s = [s_in[:lim], enc(s_in)[lim:]]
+    // g_enc_out = g_s with the first lim rows zeroed (kept aside in g_h, free now)
+    for (int it = tid; it < cl * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        sm[b.g_h + k * b.ldo + row] = (k < c.lim_enc) ? 0.f : sm[b.g_s + k * b.ldo + row];
+    }
+    __syncthreads();
+    dense_bwd_weight(slab + L.enc_w, slab + L.enc_b, L.in_dim, cl, sm + b.sin, b.ldo, sm + b.g_h, b.ldo, RO, accum);
+    dense_bwd_input(W + L.enc_w, L.in_dim, cl, sm + b.g_h, b.ldo, sm + b.g_sin, b.ldo, RO, false);
+    __syncthreads();
+    // raw pass-through of the first lim_enc features
+    for (int it = tid; it < c.lim_enc * RO; it += nt) {
+        const int k = it / RO, row = it - k * RO;
+        sm[b.g_sin + k * b.ldo + row] += sm[b.g_s + k * b.ldo + row];
+    }
+    if (c.action_dim > 0) {
+        // emb = act_W^T a + b ; g_emb[o*4+e][seq] = g_sin[half+e][seq*O+o]
+        for (int it = tid; it < nseq * O * 4; it += nt) {
+            const int sq = it / (O * 4), nn = it - sq * (O * 4);
+            sm[b.g_emb + nn * b.lds + sq] = sm[b.g_sin + (half + (nn & 3)) * b.ldo + sq * O + (nn >> 2)];
+        }
+        __syncthreads();
+        const int NA = O * 4;
+        for (int it = tid; it < c.action_dim * NA; it += nt) {
+            const int k = it / NA, nn = it - k * NA;
+            float acc = 0.f;
+            for (int sq = 0; sq < nseq; ++sq)
+                acc = fmaf(__ldg(actions + sq * act_stride + k), sm[b.g_emb + nn * b.lds + sq], acc);
+            if (accum) slab[L.act_w + k * NA + nn] += acc;
+            else slab[L.act_w + k * NA + nn] = acc;
+        }
+        for (int nn = tid; nn < NA; nn += nt) {
+            float acc = 0.f;
+            for (int sq = 0; sq < nseq; ++sq) acc += sm[b.g_emb + nn * b.lds + sq];
+            if (accum) slab[L.act_b + nn] += acc;
+            else slab[L.act_b + nn] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------
 // backward kernel: recompute forward on chip, then reverse.  slab = per-CTA weight gradients.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout L, int seq, int64_t n,
@@ -635,205 +849,11 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
             sm[b.g_out + k * b.ldo + row] = __ldg(g_out + (seq0 * O + row) * cl + k);
         }
         __syncthreads();
-        // ---- out1: result = W o1 + b + o1
-        dense_bwd_weight(slab + L.out1_w, slab + L.out1_b, cl, cl, sm + b.o1, b.ldo, sm + b.g_out, b.ldo, RO, accum);
-        dense_bwd_input(W + L.out1_w, cl, cl, sm + b.g_out, b.ldo, sm + b.g_o1, b.ldo, RO, false);
-        __syncthreads();
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            const float y = sm[b.o1 + k * b.ldo + row];
-            sm[b.g_o1 + k * b.ldo + row] = (sm[b.g_o1 + k * b.ldo + row] + sm[b.g_out + k * b.ldo + row]) * (1.f - y * y);
-        }
-        __syncthreads();
-        // ---- out0: o1 = tanh(W cat + b); g_o1 now holds the pre-activation gradient
-        dense_bwd_weight(slab + L.out0_w, slab + L.out0_b, 2 * cl, cl, sm + b.cat, b.ldo, sm + b.g_o1, b.ldo, RO, accum);
-        dense_bwd_input(W + L.out0_w, 2 * cl, cl, sm + b.g_o1, b.ldo, sm + b.g_cat, b.ldo, RO, false);
-        __syncthreads();
-        // g_cat[0:cl] = g_f3 ; g_cat[cl:2cl] -> g_s
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            sm[b.g_s + k * b.ldo + row] = sm[b.g_cat + (cl + k) * b.ldo + row];
-        }
-        // ---- aff2: f3 = W f2 + b
-        dense_bwd_weight(slab + L.aff2_w, slab + L.aff2_b, cl, cl, sm + b.f2, b.ldo, sm + b.g_cat, b.ldo, RO, accum);
-        dense_bwd_input(W + L.aff2_w, cl, cl, sm + b.g_cat, b.ldo, sm + b.g_f2, b.ldo, RO, false);
-        __syncthreads();
-        // ---- aff1: f2 = tanh(W f1 + b) + f1 ; tanh output = f2 - f1
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            const float th = sm[b.f2 + k * b.ldo + row] - sm[b.f1 + k * b.ldo + row];
-            const float g = sm[b.g_f2 + k * b.ldo + row];
-            sm[b.g_f1 + k * b.ldo + row] = g;                       // residual path
-            sm[b.g_f2 + k * b.ldo + row] = g * (1.f - th * th);     // pre-activation gradient
-        }
-        __syncthreads();
-        dense_bwd_weight(slab + L.aff1_w, slab + L.aff1_b, cl, cl, sm + b.f1, b.ldo, sm + b.g_f2, b.ldo, RO, accum);
-        dense_bwd_input(W + L.aff1_w, cl, cl, sm + b.g_f2, b.ldo, sm + b.g_f1, b.ldo, RO, true);
-        __syncthreads();
-        // ---- aff0: f1 = tanh(W d + b)
-        scale_by_act_grad(sm + b.g_f1, b.ldo, sm + b.f1, b.ldo, cl, RO, ACT_TANH, nl);
-        __syncthreads();
-        dense_bwd_weight(slab + L.aff0_w, slab + L.aff0_b, cl, cl, sm + b.d, b.ldo, sm + b.g_f1, b.ldo, RO, accum);
-        dense_bwd_input(W + L.aff0_w, cl, cl, sm + b.g_f1, b.ldo, sm + b.g_d, b.ldo, RO, false);
-        __syncthreads();
-        // ---- reward head (dynamics.py:254-263)
-        if (c.reward) {
-            for (int sq = tid; sq < nseq; sq += nt) {
-                const float r = sm[b.rew + sq];
-                const float g = g_reward ? __ldg(g_reward + seq0 + sq) : 0.f;
-                sm[b.g_rew + sq] = g * r * (1.f - r);
-            }
-            __syncthreads();
-            dense_bwd_weight(slab + L.rew14_w, slab + L.rew14_b, cl / 4, 1, sm + b.r3, b.lds, sm + b.g_rew, b.lds, nseq, accum);
-            dense_bwd_input(W + L.rew14_w, cl / 4, 1, sm + b.g_rew, b.lds, sm + b.g_r3, b.lds, nseq, false);
-            __syncthreads();
-            scale_by_act_grad(sm + b.g_r3, b.lds, sm + b.r3, b.lds, cl / 4, nseq, ACT_RELU, nl);
-            __syncthreads();
-            dense_bwd_weight(slab + L.rew12_w, slab + L.rew12_b, cl / 2, cl / 4, sm + b.r2, b.lds, sm + b.g_r3, b.lds, nseq, accum);
-            dense_bwd_input(W + L.rew12_w, cl / 2, cl / 4, sm + b.g_r3, b.lds, sm + b.g_r2, b.lds, nseq, false);
-            __syncthreads();
-            scale_by_act_grad(sm + b.g_r2, b.lds, sm + b.r2, b.lds, cl / 2, nseq, ACT_RELU, nl);
-            __syncthreads();
-            dense_bwd_weight(slab + L.rew10_w, slab + L.rew10_b, cl, cl / 2, sm + b.rsum, b.lds, sm + b.g_r2, b.lds, nseq, accum);
-            dense_bwd_input(W + L.rew10_w, cl, cl / 2, sm + b.g_r2, b.lds, sm + b.g_rsum, b.lds, nseq, false);
-            __syncthreads();
-            for (int it = tid; it < cl * RO; it += nt) {
-                const int k = it / RO, row = it - k * RO;
-                sm[b.g_rh1 + k * b.ldo + row] = sm[b.g_rsum + k * b.lds + row / O];
-            }
-            __syncthreads();
-            dense_bwd_weight(slab + L.rew02_w, slab + L.rew02_b, cl, cl, sm + b.rh0, b.ldo, sm + b.g_rh1, b.ldo, RO, accum);
-            dense_bwd_input(W + L.rew02_w, cl, cl, sm + b.g_rh1, b.ldo, sm + b.g_rh0, b.ldo, RO, false);
-            __syncthreads();
-            scale_by_act_grad(sm + b.g_rh0, b.ldo, sm + b.rh0, b.ldo, cl, RO, ACT_RELU, nl);
-            __syncthreads();
-            dense_bwd_weight(slab + L.rew00_w, slab + L.rew00_b, cl, cl, sm + b.d, b.ldo, sm + b.g_rh0, b.ldo, RO, accum);
-            dense_bwd_input(W + L.rew00_w, cl, cl, sm + b.g_rh0, b.ldo, sm + b.g_d, b.ldo, RO, true);
-            __syncthreads();
-        }
-        // ---- aggregation: d_i = self_i + sum_j mask rel_ij att_ij
-        for (int p = tid; p < RP; p += nt) {
-            const int sq = p / (O * O), ij = p - sq * O * O, i = ij / O, j = ij - i * O;
-            const float mask = (i == j) ? 0.f : 1.f;
-            float acc = 0.f;
-            for (int k = 0; k < cl; ++k) acc = fmaf(sm[b.g_d + k * b.ldo + sq * O + i], sm[b.rel + k * b.ldp + p], acc);
-            // att = exp(lin): d att / d lin = att
-            sm[b.g_att + p] = acc * mask * sm[b.att + p];
-        }
-        __syncthreads();
-        for (int it = tid; it < cl * RP; it += nt) {
-            const int k = it / RP, p = it - k * RP;
-            const int sq = p / (O * O), ij = p - sq * O * O, i = ij / O, j = ij - i * O;
-            const float mask = (i == j) ? 0.f : 1.f;
-            // overwrite rel with its gradient (rel itself is no longer needed)
-            sm[b.rel + k * b.ldp + p] = sm[b.g_d + k * b.ldo + sq * O + i] * mask * sm[b.att + p];
-        }
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            sm[b.g_self + k * b.ldo + row] = sm[b.g_d + k * b.ldo + row];
-        }
-        __syncthreads();
-        // ---- att2 (cl -> 1, exp) and rel2 (rel = W r1 + b + r1)
-        dense_bwd_weight(slab + L.att2_w, slab + L.att2_b, cl, 1, sm + b.a1, b.ldp, sm + b.g_att, b.ldp, RP, accum);
-        dense_bwd_input(W + L.att2_w, cl, 1, sm + b.g_att, b.ldp, sm + b.g_a1, b.ldp, RP, false);
-        dense_bwd_weight(slab + L.rel2_w, slab + L.rel2_b, cl, cl, sm + b.r1, b.ldp, sm + b.rel, b.ldp, RP, accum);
-        dense_bwd_input(W + L.rel2_w, cl, cl, sm + b.rel, b.ldp, sm + b.g_r1, b.ldp, RP, false);
-        __syncthreads();
-        for (int it = tid; it < cl * RP; it += nt) {
-            const int k = it / RP, p = it - k * RP;
-            sm[b.g_r1 + k * b.ldp + p] = (sm[b.g_r1 + k * b.ldp + p] + sm[b.rel + k * b.ldp + p]) *
-                                         act_grad(sm[b.r1 + k * b.ldp + p], ACT_NL, nl);
-            sm[b.g_a1 + k * b.ldp + p] *= act_grad(sm[b.a1 + k * b.ldp + p], ACT_NL, nl);
-        }
-        __syncthreads();
-        // ---- rel1 / att1 (2cl -> cl); input gradients overwrite... need r0/a0 for the weight
-        // gradient first, so compute weight gradients, then input gradients into comb-sized scratch
-        dense_bwd_weight(slab + L.rel1_w, slab + L.rel1_b, 2 * cl, cl, sm + b.ra0, b.ldp, sm + b.g_r1, b.ldp, RP, accum);
-        dense_bwd_weight(slab + L.att1_w, slab + L.att1_b, 2 * cl, cl, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, sm + b.g_a1, b.ldp, RP, accum);
-        __syncthreads();
-        // in place: ra0 <- (W^T g) * act'(ra0)
-        dense_bwd_input(W + L.rel1_w, 2 * cl, cl, sm + b.g_r1, b.ldp, sm + b.ra0, b.ldp, RP, false,
-                        sm + b.ra0, b.ldp, ACT_NL, nl);
-        dense_bwd_input(W + L.att1_w, 2 * cl, cl, sm + b.g_a1, b.ldp, sm + b.ra0 + 2 * cl * b.ldp, b.ldp, RP, false,
-                        sm + b.ra0 + 2 * cl * b.ldp, b.ldp, ACT_NL, nl);
-        __syncthreads();
-        // ---- rel0|att0 (2cl+1 -> 4cl)
-        dense_bwd_weight(slab + L.ra0_w, slab + L.ra0_b, 2 * cl + 1, 4 * cl, sm + b.comb, b.ldp, sm + b.ra0, b.ldp, RP, accum);
-        __syncthreads();
-        dense_bwd_input(W + L.ra0_w, 2 * cl + 1, 4 * cl, sm + b.ra0, b.ldp, sm + b.comb, b.ldp, RP, false);
-        __syncthreads();
-        // ---- scatter pair-input gradients to the objects (comb now holds g_comb)
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            const int sq = row / O, i = row - sq * O;
-            float acc = 0.f;
-            for (int j = 0; j < O; ++j) {
-                acc += sm[b.comb + k * b.ldp + sq * O * O + i * O + j];            // as first argument
-                acc += sm[b.comb + (cl + k) * b.ldp + sq * O * O + j * O + i];     // as second argument
-            }
-            if (k < 2) {
-                // dist_ij = (x_i-x_j)^2 + (y_i-y_j)^2
-                const float xi = sm[b.s + k * b.ldo + row];
-                for (int j = 0; j < O; ++j) {
-                    const float xj = sm[b.s + k * b.ldo + sq * O + j];
-                    acc += 2.f * (xi - xj) * (sm[b.comb + 2 * cl * b.ldp + sq * O * O + i * O + j] +
-                                              sm[b.comb + 2 * cl * b.ldp + sq * O * O + j * O + i]);
-                }
-            }
-            sm[b.g_s + k * b.ldo + row] += acc;
-        }
-        // ---- self1: self = W h + b + h
-        dense_bwd_weight(slab + L.self1_w, slab + L.self1_b, cl, cl, sm + b.h, b.ldo, sm + b.g_self, b.ldo, RO, accum);
-        dense_bwd_input(W + L.self1_w, cl, cl, sm + b.g_self, b.ldo, sm + b.g_h, b.ldo, RO, false);
-        __syncthreads();
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            sm[b.g_h + k * b.ldo + row] = (sm[b.g_h + k * b.ldo + row] + sm[b.g_self + k * b.ldo + row]) *
-                                          act_grad(sm[b.h + k * b.ldo + row], ACT_NL, nl);
-        }
-        __syncthreads();
-        // ---- self0: h = phi(W s + b)
-        dense_bwd_weight(slab + L.self0_w, slab + L.self0_b, cl, cl, sm + b.s, b.ldo, sm + b.g_h, b.ldo, RO, accum);
-        dense_bwd_input(W + L.self0_w, cl, cl, sm + b.g_h, b.ldo, sm + b.g_s, b.ldo, RO, true);
-        __syncthreads();
-        // ---- encoder: s = [s_in[:lim], enc(s_in)[lim:]]
-        // g_enc_out = g_s with the first lim rows zeroed (kept aside in g_h, free now)
-        for (int it = tid; it < cl * RO; it += nt) {
-            const int k = it / RO, row = it - k * RO;
-            sm[b.g_h + k * b.ldo + row] = (k < c.lim_enc) ? 0.f : sm[b.g_s + k * b.ldo + row];
-        }
-        __syncthreads();
-        dense_bwd_weight(slab + L.enc_w, slab + L.enc_b, L.in_dim, cl, sm + b.sin, b.ldo, sm + b.g_h, b.ldo, RO, accum);
-        dense_bwd_input(W + L.enc_w, L.in_dim, cl, sm + b.g_h, b.ldo, sm + b.g_sin, b.ldo, RO, false);
-        __syncthreads();
+        gnn_backward_core(c, L, b, W, sm, slab, accum, nseq, actions ? actions + seq0 * c.action_dim : nullptr,
+                          c.action_dim, g_reward ? g_reward + seq0 : nullptr, 1);
         for (int it = tid; it < RO * half; it += nt) {
             const int row = it / half, k = it - row * half;
-            float g = sm[b.g_sin + k * b.ldo + row];
-            if (k < c.lim_enc) g += sm[b.g_s + k * b.ldo + row];
-            g_s[(seq0 * O + row) * half + k] = g;
-        }
-        if (c.action_dim > 0) {
-            // emb = act_W^T a + b ; g_emb[o*4+e][seq] = g_sin[half+e][seq*O+o]
-            for (int it = tid; it < nseq * O * 4; it += nt) {
-                const int sq = it / (O * 4), nn = it - sq * (O * 4);
-                sm[b.g_emb + nn * b.lds + sq] = sm[b.g_sin + (half + (nn & 3)) * b.ldo + sq * O + (nn >> 2)];
-            }
-            __syncthreads();
-            const int NA = O * 4;
-            for (int it = tid; it < c.action_dim * NA; it += nt) {
-                const int k = it / NA, nn = it - k * NA;
-                float acc = 0.f;
-                for (int sq = 0; sq < nseq; ++sq)
-                    acc = fmaf(__ldg(actions + (seq0 + sq) * c.action_dim + k), sm[b.g_emb + nn * b.lds + sq], acc);
-                if (accum) slab[L.act_w + k * NA + nn] += acc;
-                else slab[L.act_w + k * NA + nn] = acc;
-            }
-            for (int nn = tid; nn < NA; nn += nt) {
-                float acc = 0.f;
-                for (int sq = 0; sq < nseq; ++sq) acc += sm[b.g_emb + nn * b.lds + sq];
-                if (accum) slab[L.act_b + nn] += acc;
-                else slab[L.act_b + nn] = acc;
-            }
+            g_s[(seq0 * O + row) * half + k] = sm[b.g_sin + k * b.ldo + row];
         }
     }
 }

@@ -211,6 +211,47 @@ class Scene(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------
+# fused sequence glue (constrain_zp + matching + fix_supair + velocities)
+# ----------------------------------------------------------------------------------------
+MATCH_KINDS = {'3_only': 0, 'greedy': 1, 'volatile': 2}
+
+
+class SupPrepare(torch.autograd.Function):
+    """zp (n, T, O, 8) [, app (n, T, O, 3)] -> z_sup (n,T,O,4), z_full (n,T,O,6), std_full (n,T,O,6),
+    app_matched (n,T,O,3) | None."""
+
+    @staticmethod
+    def forward(ctx, zp, app, cfg):
+        zp, app = zp.contiguous(), _c(app)
+        N.require_cuda_f32(zp, app)
+        n, T, O, _ = zp.shape
+        dev, dt = zp.device, zp.dtype
+        z_sup = torch.empty(n, T, O, 4, device=dev, dtype=dt)
+        z_full = torch.empty(n, T, O, 6, device=dev, dtype=dt)
+        std_full = torch.empty(n, T, O, 6, device=dev, dtype=dt)
+        app_out = torch.empty(n, T, O, 3, device=dev, dtype=dt) if app is not None else None
+        idx = torch.empty(n, T, O, device=dev, dtype=torch.int32)
+        flag = torch.empty(n, T, O, device=dev, dtype=torch.int32)
+        N.check(N.lib().stove_sup_prepare_fwd(C.byref(cfg), n, N.ptr(zp), N.ptr(app), N.ptr(z_sup), N.ptr(z_full),
+                                              N.ptr(std_full), N.ptr(app_out), N.ptr(idx), N.ptr(flag), N.stream()))
+        ctx.save_for_backward(zp, idx, flag, std_full)
+        ctx.cfg = cfg
+        if app_out is None:
+            app_out = zp.new_zeros(())
+        ctx.mark_non_differentiable(app_out)
+        return z_sup, z_full, std_full, app_out
+
+    @staticmethod
+    def backward(ctx, g_z_sup, g_z_full, g_std_full, _g_app):
+        zp, idx, flag, std_full = ctx.saved_tensors
+        g_zp = torch.empty_like(zp)
+        N.check(N.lib().stove_sup_prepare_bwd(C.byref(ctx.cfg), zp.shape[0], N.ptr(zp), N.ptr(idx), N.ptr(flag),
+                                              N.ptr(std_full), N.ptr(_c(g_z_sup)), N.ptr(_c(g_z_full)),
+                                              N.ptr(_c(g_std_full)), N.ptr(g_zp), N.stream()))
+        return g_zp, None, None
+
+
+# ----------------------------------------------------------------------------------------
 # GNN dynamics
 # ----------------------------------------------------------------------------------------
 GNN_SEGMENTS = ['act', 'enc', 'self0', 'self1', 'ra0', 'rel1', 'att1', 'rel2', 'att2', 'aff0', 'aff1',

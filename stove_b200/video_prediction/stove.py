@@ -47,6 +47,19 @@ class Stove(nn.Module):
         else:
             raise ValueError('Specify valid self.c.debug_match_ojects.')
 
+    def _sup_cfg(self, T):
+        from .. import _native as N
+        c = self.c
+        key = ('sup_cfg', T)
+        cache = self.__dict__.setdefault('_cfg_cache', {})
+        if key not in cache:
+            cache[key] = N.SupCfg(T, c.num_obj, ops.MATCH_KINDS[c.debug_match_objects],
+                                  3 if (c.debug_core_appearance or c.debug_match_appearance) else 0,
+                                  int(bool(c.debug_match_appearance)), int(bool(c.debug_fix_supair)),
+                                  c.min_obj_scale, c.max_obj_scale, c.min_y_scale, c.max_y_scale,
+                                  c.obj_pos_bound, c.scale_var, c.pos_var, 0.095)
+        return cache[key]
+
     # -- noise: same shapes in the same order as the reference's rsample() calls ------------
     def _standard_normal(self, shape, like):
         return torch.empty(shape, device=like.device, dtype=like.dtype).normal_()
@@ -200,19 +213,17 @@ class Stove(nn.Module):
         packed_spn = self.sup.pack()
         packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
 
-        z_sup = self.sup.encoder(x.flatten(end_dim=1))
-        z_sup, z_sup_std = self.sup.constrain_zp(z_sup.flatten(end_dim=1))
-        z_sup = z_sup.view(n, T, O, 4)
-        z_sup_std = z_sup_std.view(n, T, O, 4)
+        # encoder -> (constrain, match, smooth, velocities) in one kernel (csrc/glue.cu)
+        zp = self.sup.encoder(x.flatten(end_dim=1)).view(n, T, O, 8)
         _app = None
         if c.debug_core_appearance or c.debug_match_appearance:
-            _app = self.object_embedding(z_sup, x_color)
-        z_sup, z_sup_std, obj_appearances = self.match_objects(z_sup, z_sup_std, _app)
+            with torch.no_grad():
+                z_raw, _ = self.sup.constrain_zp(zp.flatten(end_dim=2))
+            _app = self.object_embedding(z_raw.view(n, T, O, 4), x_color)
+        z_sup, z_sup_full, z_sup_std_full, obj_appearances = ops.SupPrepare.apply(zp, _app, self._sup_cfg(T))
+        if _app is None:
+            obj_appearances = None
         core_app = obj_appearances.transpose(0, 1) if c.debug_core_appearance else T * [None]
-        if c.debug_fix_supair:
-            z_sup, z_sup_std = self.fix_supair(z_sup, z_sup_std)
-        z_sup_full = self.v_from_state(z_sup)
-        z_sup_std_full = self.v_std_from_pos(z_sup_std)
 
         prior_shape = (n, O, cl // 2 - 4, 1)
         lat0 = (0.01 * self._standard_normal(prior_shape, x)).squeeze()
