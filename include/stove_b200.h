@@ -219,6 +219,48 @@ int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, const float*
                       const float* noise, float pos_var, float vel_std, float latent_std,
                       float* z_out, float* std_out, float* logq_out, float* rewards, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * One step of the dynamics loop of Stove.stove_forward (stove.py:696-713), fused: GNN core
+ * (dynamics.py:181-265) + constrain_z_dyn (dynamics.py:147-179) + position integration +
+ * full_state (Gaussian fusion with the SuPAIR state, reparametrised sample, log q;
+ * stove.py:103-170) + transition_lik of the sample (stove.py:172-198).
+ * Every tensor is addressed as base + sequence * stride (strides in floats) so that time
+ * slices of (n, T, ...) tensors can be passed without copies.  Per sequence:
+ *   z_prev [O][cl/2+2], sup / sup_std [O][6] (sx, sy/sx, x, y, vx, vy), eps [O][cl/2+2],
+ *   actions [A], app [O][app_dim]  ->  z_out [O][cl/2+2], z_dyn / z_dyn_std [O][cl/2],
+ *   z_std [O][cl/2+2] (optional), logq / trans / reward: one float each.
+ * Backward: g_z = g_z_a + g_z_b (either may be NULL), g_logq / g_trans / g_reward one float per
+ * sequence -> g_z_prev [O][cl/2+2], g_sup / g_sup_std [O][6] (overwritten), g_weights
+ * (overwritten or accumulated).  Workspace: stove_gnn_bwd_workspace bytes.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    float pos_var, vel_std, latent_std;   /* constrain_z_dyn scales */
+    float trans_std[32];                  /* transition_lik_std, cl/2 entries used */
+} stove_fuse_cfg;
+
+typedef struct {
+    const float* z_prev; int64_t z_prev_ss;
+    const float* sup; const float* sup_std; int64_t sup_ss;
+    const float* eps; int64_t eps_ss;
+    const float* actions; int64_t act_ss;
+    const float* app; int64_t app_ss;
+    float* z_out; int64_t z_out_ss;
+    float* z_dyn; float* z_dyn_std; int64_t zdyn_ss;
+    float* z_std; int64_t z_std_ss;
+    float* logq; float* trans; float* reward; int64_t sc_ss;
+    const float* g_z_a; int64_t g_z_a_ss;
+    const float* g_z_b; int64_t g_z_b_ss;
+    const float* g_logq; const float* g_trans; const float* g_reward; int64_t g_sc_ss;
+    float* g_z_prev; int64_t g_z_prev_ss;
+    float* g_sup; float* g_sup_std; int64_t g_sup_ss;
+} stove_dynstep_io;
+
+int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                      const stove_dynstep_io* io, const float* weights, void* stream);
+int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                      const stove_dynstep_io* io, const float* weights, float* g_weights,
+                      int accumulate, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

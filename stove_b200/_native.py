@@ -37,6 +37,27 @@ class GnnCfg(C.Structure):
                 ('reward', i32), ('lim_enc', i32), ('nonlin', i32)]
 
 
+class FuseCfg(C.Structure):
+    _fields_ = [('pos_var', f32), ('vel_std', f32), ('latent_std', f32), ('trans_std', f32 * 32)]
+
+
+class DynstepIO(C.Structure):
+    _fields_ = [('z_prev', vp), ('z_prev_ss', i64),
+                ('sup', vp), ('sup_std', vp), ('sup_ss', i64),
+                ('eps', vp), ('eps_ss', i64),
+                ('actions', vp), ('act_ss', i64),
+                ('app', vp), ('app_ss', i64),
+                ('z_out', vp), ('z_out_ss', i64),
+                ('z_dyn', vp), ('z_dyn_std', vp), ('zdyn_ss', i64),
+                ('z_std', vp), ('z_std_ss', i64),
+                ('logq', vp), ('trans', vp), ('reward', vp), ('sc_ss', i64),
+                ('g_z_a', vp), ('g_z_a_ss', i64),
+                ('g_z_b', vp), ('g_z_b_ss', i64),
+                ('g_logq', vp), ('g_trans', vp), ('g_reward', vp), ('g_sc_ss', i64),
+                ('g_z_prev', vp), ('g_z_prev_ss', i64),
+                ('g_sup', vp), ('g_sup_std', vp), ('g_sup_ss', i64)]
+
+
 P2, P1, PG, PS = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg), C.POINTER(SupCfg)
 
 # name -> (restype, argtypes); must list every symbol of include/stove_b200.h
@@ -69,6 +90,8 @@ SIGNATURES = {
     'stove_gnn_bwd_workspace': (sz, [PG, i64]),
     'stove_gnn_fwd': (C.c_int, [PG, i64] + [vp] * 6 + [vp]),
     'stove_gnn_bwd': (C.c_int, [PG, i64] + [vp] * 9 + [vp]),
+    'stove_dynstep_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp]),
+    'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, vp, vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

@@ -858,6 +858,229 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Fused dynamics-loop step of Stove.stove_forward (stove.py:696-713): GNN core, then
+// constrain_z_dyn (dynamics.py:147-179), position integration, Gaussian fusion with the SuPAIR
+// state + reparametrised sample + log q (full_state, stove.py:103-170) and the transition
+// log-likelihood of the sample (transition_lik, stove.py:172-198) -- ~45 tensor ops per time
+// step in the reference -- as the epilogue of the forward kernel and the prologue of the
+// backward kernel.  All tensors are addressed as base + sequence * stride so the caller can
+// pass time slices of (n, T, ...) tensors without copies.
+// ------------------------------------------------------------------------------------
+struct FuseCfg {
+    float scale[3];          // pos_var, 0.04, debug_latent_q_std  (constrain_z_dyn)
+    float trans_std[32];     // transition_lik_std per state feature (cl/2 used)
+};
+
+__device__ __forceinline__ void load_inputs_strided(const stove_gnn_cfg& c, const GnnBuf& b, float* sm, int nseq,
+                                                    const float* __restrict__ z_prev, int64_t zss,
+                                                    const float* __restrict__ app, int64_t ass) {
+    const int cl = c.cl, O = c.num_obj, half = cl / 2, zd = half + 2;
+    for (int it = threadIdx.x; it < nseq * O * half; it += blockDim.x) {
+        const int row = it / half, k = it - row * half;
+        const int sq = row / O, o = row - sq * O;
+        sm[b.sin + k * b.ldo + row] = __ldg(z_prev + sq * zss + o * zd + 2 + k);
+    }
+    if (c.app_dim > 0) {
+        const int a0 = half + (c.action_dim > 0 ? 4 : 0);
+        for (int it = threadIdx.x; it < nseq * O * c.app_dim; it += blockDim.x) {
+            const int row = it / c.app_dim, k = it - row * c.app_dim;
+            const int sq = row / O, o = row - sq * O;
+            sm[b.sin + (a0 + k) * b.ldo + row] = __ldg(app + sq * ass + o * c.app_dim + k);
+        }
+    }
+}
+
+// forward quantities of one (row, feature j) of the fused epilogue
+struct FuseVal {
+    float zd, sd, zdyn, mean, std, m_sup, s_sup, scale;
+};
+__device__ __forceinline__ FuseVal fuse_forward(const stove_gnn_cfg& c, const FuseCfg& f, const GnnBuf& b,
+                                                const float* sm, int row, int j, const float* sup6,
+                                                const float* sstd6) {
+    FuseVal v;
+    const int half = c.cl / 2;
+    if (j < 2) {
+        v.zd = v.sd = v.zdyn = 0.f; v.scale = 1.f; v.m_sup = v.s_sup = 0.f;
+        v.mean = __ldg(sup6 + j);
+        v.std = __ldg(sstd6 + j);
+        return v;
+    }
+    const int i = j - 2;
+    v.scale = f.scale[i < 2 ? 0 : (i < 4 ? 1 : 2)];
+    v.zd = 2.f * sigmoidf_(sm[b.out + i * b.ldo + row]) - 1.f;
+    v.sd = v.scale * sigmoidf_(sm[b.out + (half + i) * b.ldo + row]);
+    v.zdyn = v.zd + (i < 2 ? sm[b.sin + i * b.ldo + row] : 0.f);
+    if (i < 4) {
+        v.m_sup = __ldg(sup6 + 2 + i);
+        v.s_sup = __ldg(sstd6 + 2 + i);
+        const float A = v.s_sup * v.s_sup, B = v.sd * v.sd, D = A + B;
+        v.mean = (A * v.zdyn + B * v.m_sup) / D;
+        v.std = v.sd * v.s_sup / sqrtf(D);
+    } else {
+        v.m_sup = v.s_sup = 0.f;
+        v.mean = v.zdyn;
+        v.std = v.sd;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) dynstep_fwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
+                                                          int64_t n, stove_dynstep_io io,
+                                                          const float* __restrict__ weights) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    float* sm = smem + L.total;
+    const GnnBuf b = gnn_buffers(c, L.in_dim, seq, false);
+    stage_weights(weights, Ws, L.total);
+    for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
+    const int cl = c.cl, O = c.num_obj, half = cl / 2, zdim = half + 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t ngroups = (n + seq - 1) / seq;
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        const int64_t seq0 = grp * seq;
+        const int nseq = (int)min((int64_t)seq, n - seq0);
+        const int RO = nseq * O;
+        __syncthreads();
+        load_inputs_strided(c, b, sm, nseq, io.z_prev + seq0 * io.z_prev_ss, io.z_prev_ss,
+                            io.app ? io.app + seq0 * io.app_ss : nullptr, io.app_ss);
+        __syncthreads();
+        gnn_forward_core(c, L, b, Ws, sm, nseq, io.actions ? io.actions + seq0 * io.act_ss : nullptr, io.act_ss);
+        // epilogue; per-item log q / transition terms go to scratch (the dead `cat` buffer) and are
+        // summed per sequence in a fixed order (deterministic)
+        float* s_lq = sm + b.cat;
+        float* s_tr = s_lq + RO * zdim;
+        for (int it = tid; it < RO * zdim; it += nt) {
+            const int row = it / zdim, j = it - row * zdim;
+            const int sq = row / O, o = row - sq * O;
+            const int64_t gs = seq0 + sq;
+            const FuseVal v = fuse_forward(c, f, b, sm, row, j, io.sup + gs * io.sup_ss + o * 6,
+                                           io.sup_std + gs * io.sup_ss + o * 6);
+            const float e = __ldg(io.eps + gs * io.eps_ss + o * zdim + j);
+            const float z = v.mean + v.std * e;
+            io.z_out[gs * io.z_out_ss + o * zdim + j] = z;
+            if (io.z_std) io.z_std[gs * io.z_std_ss + o * zdim + j] = v.std;
+            s_lq[it] = -0.5f * e * e - logf(v.std) - HALF_LOG_2PI;
+            float tr = 0.f;
+            if (j >= 2) {
+                const int i = j - 2;
+                io.z_dyn[gs * io.zdyn_ss + o * half + i] = v.zdyn;
+                io.z_dyn_std[gs * io.zdyn_ss + o * half + i] = v.sd;
+                const float st = f.trans_std[i], d = z - v.zdyn;
+                tr = -(d * d) / (2.f * st * st) - logf(st) - HALF_LOG_2PI;
+            }
+            s_tr[it] = tr;
+        }
+        __syncthreads();
+        for (int sq = tid; sq < nseq; sq += nt) {
+            float a = 0.f, t = 0.f;
+            for (int q = sq * O * zdim; q < (sq + 1) * O * zdim; ++q) { a += s_lq[q]; t += s_tr[q]; }
+            io.logq[(seq0 + sq) * io.sc_ss] = a;
+            io.trans[(seq0 + sq) * io.sc_ss] = t;
+            if (c.reward && io.reward) io.reward[(seq0 + sq) * io.sc_ss] = sm[b.rew + sq];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
+                                                          int64_t n, int stage_w, stove_dynstep_io io,
+                                                          const float* __restrict__ weights,
+                                                          float* __restrict__ slabs) {
+    extern __shared__ __align__(16) float smem[];
+    const float* W = weights;
+    float* sm = smem;
+    if (stage_w) {
+        stage_weights(weights, smem, L.total);
+        W = smem;
+        sm = smem + L.total;
+    }
+    const GnnBuf b = gnn_buffers(c, L.in_dim, seq, true);
+    for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
+    float* slab = slabs + (int64_t)blockIdx.x * L.total;
+    const int cl = c.cl, O = c.num_obj, half = cl / 2, zdim = half + 2;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int64_t ngroups = (n + seq - 1) / seq;
+    bool accum = false;
+    for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, accum = true) {
+        const int64_t seq0 = grp * seq;
+        const int nseq = (int)min((int64_t)seq, n - seq0);
+        const int RO = nseq * O;
+        __syncthreads();
+        load_inputs_strided(c, b, sm, nseq, io.z_prev + seq0 * io.z_prev_ss, io.z_prev_ss,
+                            io.app ? io.app + seq0 * io.app_ss : nullptr, io.app_ss);
+        __syncthreads();
+        gnn_forward_core(c, L, b, W, sm, nseq, io.actions ? io.actions + seq0 * io.act_ss : nullptr, io.act_ss);
+        // prologue: gradients of (sample, log q, transition lik) -> raw network output, SuPAIR inputs
+        for (int it = tid; it < RO * zdim; it += nt) {
+            const int row = it / zdim, j = it - row * zdim;
+            const int sq = row / O, o = row - sq * O;
+            const int64_t gs = seq0 + sq;
+            const FuseVal v = fuse_forward(c, f, b, sm, row, j, io.sup + gs * io.sup_ss + o * 6,
+                                           io.sup_std + gs * io.sup_ss + o * 6);
+            const float e = __ldg(io.eps + gs * io.eps_ss + o * zdim + j);
+            const float z = v.mean + v.std * e;
+            float gz = 0.f;
+            if (io.g_z_a) gz += __ldg(io.g_z_a + gs * io.g_z_a_ss + o * zdim + j);
+            if (io.g_z_b) gz += __ldg(io.g_z_b + gs * io.g_z_b_ss + o * zdim + j);
+            const float glq = io.g_logq ? __ldg(io.g_logq + gs * io.g_sc_ss) : 0.f;
+            const float gtr = io.g_trans ? __ldg(io.g_trans + gs * io.g_sc_ss) : 0.f;
+            float g_zdyn = 0.f;
+            if (j >= 2) {
+                const float st = f.trans_std[j - 2];
+                const float t = (z - v.zdyn) / (st * st) * gtr;
+                gz -= t;
+                g_zdyn = t;
+            }
+            const float g_mean = gz, g_std = gz * e - glq / v.std;
+            float* gsup = io.g_sup + gs * io.g_sup_ss + o * 6;
+            float* gsst = io.g_sup_std + gs * io.g_sup_ss + o * 6;
+            float* gzp = io.g_z_prev + gs * io.g_z_prev_ss + o * zdim;
+            if (j < 2) {
+                gsup[j] = g_mean;
+                gsst[j] = g_std;
+                gzp[j] = 0.f;
+                continue;
+            }
+            const int i = j - 2;
+            float g_sd;
+            if (i < 4) {
+                const float A = v.s_sup * v.s_sup, B = v.sd * v.sd, D = A + B, rD = 1.f / D, rD15 = rD / sqrtf(D);
+                g_zdyn += g_mean * A * rD;
+                gsup[2 + i] = g_mean * B * rD;
+                const float gA = g_mean * (v.zdyn - v.mean) * rD, gB = g_mean * (v.m_sup - v.mean) * rD;
+                g_sd = g_std * v.s_sup * A * rD15 + gB * 2.f * v.sd;
+                gsst[2 + i] = g_std * v.sd * B * rD15 + gA * 2.f * v.s_sup;
+            } else {
+                g_zdyn += g_mean;
+                g_sd = g_std;
+            }
+            sm[b.g_out + i * b.ldo + row] = g_zdyn * (1.f - v.zd * v.zd) * 0.5f;
+            sm[b.g_out + (half + i) * b.ldo + row] = g_sd * v.sd * (1.f - v.sd / v.scale);
+            if (i < 2) gzp[2 + i] = g_zdyn;          // direct path pos_t = pos_{t-1} + delta
+        }
+        __syncthreads();
+        gnn_backward_core(c, L, b, W, sm, slab, accum, nseq, io.actions ? io.actions + seq0 * io.act_ss : nullptr,
+                          io.act_ss, io.g_reward ? io.g_reward + seq0 * io.g_sc_ss : nullptr, io.g_sc_ss);
+        for (int it = tid; it < RO * half; it += nt) {
+            const int row = it / half, k = it - row * half;
+            const int sq = row / O, o = row - sq * O;
+            float* gzp = io.g_z_prev + (seq0 + sq) * io.g_z_prev_ss + o * zdim + 2 + k;
+            const float g = sm[b.g_sin + k * b.ldo + row];
+            *gzp = (k < 2) ? *gzp + g : g;
+        }
+    }
+}
+
+// g_w[i] (=, +=) sum_b slabs[b][i]
+__global__ void gnn_reduce_slabs_acc_kernel(const float* __restrict__ slabs, int nslab, int total,
+                                            float* __restrict__ g_w, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float acc = accumulate ? g_w[i] : 0.f;
+    for (int s = 0; s < nslab; ++s) acc += slabs[(int64_t)s * total + i];
+    g_w[i] = acc;
+}
+
 // g_w[i] = sum_b slabs[b][i]
 __global__ void gnn_reduce_slabs_kernel(const float* __restrict__ slabs, int nslab, int total,
                                         float* __restrict__ g_w) {
@@ -994,6 +1217,66 @@ extern "C" int stove_gnn_bwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
                                                 g_s, (float*)workspace));
     STOVE_LAUNCH_CHECK();
     STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_kernel<<<(L.total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.ctas, L.total, g_weights));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+static FuseCfg make_fuse(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fc) {
+    FuseCfg f;
+    f.scale[0] = fc->pos_var; f.scale[1] = fc->vel_std; f.scale[2] = fc->latent_std;
+    for (int i = 0; i < 32; ++i) f.trans_std[i] = (i < cfg->cl / 2) ? fc->trans_std[i] : 1.f;
+    return f;
+}
+
+extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                                 const stove_dynstep_io* io, const float* weights, void* stream) {
+    int rc = gnn_check(cfg);
+    if (rc) return rc;
+    STOVE_CHECK_ARG(fuse && io && weights && n >= 0, "null pointer");
+    STOVE_CHECK_ARG(io->z_prev && io->sup && io->sup_std && io->eps && io->z_out && io->z_dyn && io->z_dyn_std &&
+                        io->logq && io->trans, "null tensor in stove_dynstep_io");
+    STOVE_CHECK_ARG((cfg->action_dim > 0) == (io->actions != nullptr), "actions do not match cfg.action_dim");
+    STOVE_CHECK_ARG((cfg->app_dim > 0) == (io->app != nullptr), "appearances do not match cfg.app_dim");
+    STOVE_CHECK_ARG(cfg->cl <= 64, "cl too large");
+    if (n == 0) return STOVE_OK;
+    GnnLayout L = gnn_layout(cfg);
+    int want = (int)((n + 295) / 296);
+    if (want < 1) want = 1;
+    if (want > 8) want = 8;
+    const int seq = pick_seq(cfg, L, false, true, want);
+    if (seq == 0) { stove_set_error("stove_dynstep_fwd: configuration does not fit in shared memory"); return STOVE_ERR_UNSUPPORTED; }
+    GnnBuf b = gnn_buffers(*cfg, L.in_dim, seq, false);
+    const size_t smem = sizeof(float) * ((size_t)b.total + L.total);
+    STOVE_CUDA(cudaFuncSetAttribute(dynstep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t st = (cudaStream_t)stream;
+    STOVE_KERNEL(K_DYNSTEP_FWD, st, dynstep_fwd_kernel<<<gnn_target_ctas(n, seq), 256, smem, st>>>(
+        *cfg, L, make_fuse(cfg, fuse), seq, n, *io, weights));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                                 const stove_dynstep_io* io, const float* weights, float* g_weights,
+                                 int accumulate, void* workspace, void* stream) {
+    int rc = gnn_check(cfg);
+    if (rc) return rc;
+    STOVE_CHECK_ARG(fuse && io && weights && g_weights && workspace && n >= 0, "null pointer");
+    STOVE_CHECK_ARG(io->z_prev && io->sup && io->sup_std && io->eps && io->g_z_prev && io->g_sup && io->g_sup_std,
+                    "null tensor in stove_dynstep_io");
+    STOVE_CHECK_ARG((cfg->action_dim > 0) == (io->actions != nullptr), "actions do not match cfg.action_dim");
+    STOVE_CHECK_ARG((cfg->app_dim > 0) == (io->app != nullptr), "appearances do not match cfg.app_dim");
+    if (n == 0) return STOVE_OK;
+    GnnLayout L = gnn_layout(cfg);
+    GnnBwdPlan p = gnn_bwd_plan(cfg, L, n);
+    if (p.seq == 0) { stove_set_error("stove_dynstep_bwd: configuration does not fit in shared memory"); return STOVE_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    STOVE_CUDA(cudaFuncSetAttribute(dynstep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
+    STOVE_KERNEL(K_DYNSTEP_BWD, st, dynstep_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(
+        *cfg, L, make_fuse(cfg, fuse), p.seq, n, p.stage, *io, weights, (float*)workspace));
+    STOVE_LAUNCH_CHECK();
+    STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_acc_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(
+        (const float*)workspace, p.ctas, L.total, g_weights, accumulate));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -60,6 +60,15 @@ class Stove(nn.Module):
                                   c.obj_pos_bound, c.scale_var, c.pos_var, 0.095)
         return cache[key]
 
+    def _fuse_cfg(self):
+        from .. import _native as N
+        cache = self.__dict__.setdefault('_cfg_cache', {})
+        if 'fuse' not in cache:
+            std = [float(v) for v in self.dyn.transition_lik_std.flatten().tolist()]
+            arr = (N.f32 * 32)(*(std + [1.0] * (32 - len(std))))
+            cache['fuse'] = N.FuseCfg(self.c.pos_var, 0.04, self.c.debug_latent_q_std, arr)
+        return cache['fuse']
+
     # -- noise: same shapes in the same order as the reference's rsample() calls ------------
     def _standard_normal(self, shape, like):
         return torch.empty(shape, device=like.device, dtype=like.dtype).normal_()
@@ -223,44 +232,30 @@ class Stove(nn.Module):
         z_sup, z_sup_full, z_sup_std_full, obj_appearances = ops.SupPrepare.apply(zp, _app, self._sup_cfg(T))
         if _app is None:
             obj_appearances = None
-        core_app = obj_appearances.transpose(0, 1) if c.debug_core_appearance else T * [None]
 
         prior_shape = (n, O, cl // 2 - 4, 1)
         lat0 = (0.01 * self._standard_normal(prior_shape, x)).squeeze()
         init_z = torch.cat([z_sup_full[:, skip - 1], lat0], -1)
-        std0 = (0.1 + 0.01 * self._standard_normal(prior_shape, x)).squeeze()
-        dyn_std_init = torch.cat([z_sup_std_full[:, skip - 1, :, 2:], std0], -1)
+        # the reference also draws the initial dynamics std here (stove.py:677-680); it only feeds
+        # logging, but the draw is kept so the random stream stays aligned with the reference
+        self._standard_normal(prior_shape, x)
 
-        z = {skip - 1: init_z}
-        z_dyn, z_dyn_std, z_std, log_z, rewards = {}, {skip - 1: dyn_std_init}, {}, {}, []
-        z_std[skip - 1] = torch.cat([z_sup_std_full[:, skip - 1, :, :2], dyn_std_init], -1)
-        core_actions = actions.transpose(0, 1) if actions is not None else T * [None]
-        for t in range(skip, T):
-            tmp, reward = self.dyn(z[t - 1][..., 2:], 0, core_actions[t - 1], core_app[t - 1],
-                                   packed=packed_dyn)
-            rewards.append(reward)
-            zd, z_dyn_std[t] = self.dyn.constrain_z_dyn(tmp[..., :cl // 2], tmp[..., cl // 2:])
-            z_dyn[t] = torch.cat([z[t - 1][..., 2:4] + zd[..., :2], zd[..., 2:]], -1)
-            z[t], log_z[t], _, z_std[t] = self.full_state(
-                z_dyn[t], z_dyn_std[t], z_sup_full[:, t], z_sup_std_full[:, t])
-        steps = range(skip, T)
-        z_s = torch.stack([z[t] for t in steps], 1)
-        z_dyn_s = torch.stack([z_dyn[t] for t in steps], 1)
-        log_z_s = torch.stack([log_z[t] for t in steps], 1)
-        z_dyn_std_s = torch.stack([z_dyn_std[t] for t in steps], 1)
-        z_std_s = torch.stack([z_std[t] for t in steps], 1)
-        if c.action_conditioned:
-            rewards = torch.stack(rewards, 1)
-        else:
-            rewards = torch.zeros(len(rewards))
+        # dynamics loop: one fused kernel per time step (csrc/gnn.cu: dynstep_*), chained on the device
+        eps = torch.stack([self._standard_normal((n, O, cl // 2 + 2), x) for _ in range(skip, T)], 0)
+        cfg_dyn, w_dyn = packed_dyn
+        z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
+            init_z, z_sup_full, z_sup_std_full, eps, actions,
+            obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip)
+        if not c.action_conditioned:
+            rewards = torch.zeros(T - skip)
 
         z_f = self.sup.sy_from_quotient(z_s.flatten(end_dim=2))
         img_lik, sup_prop = self.sup.likelihood(x[:, skip:], z_f[..., :4], packed=packed_spn)
         self.prop_dict.update(sup_prop)
         z_sup_tmp = self.sup.sy_from_quotient(z_sup[:, 1:skip])
         img_lik_sup, _ = self.sup.likelihood(x[:, 1:skip], z_sup_tmp.flatten(end_dim=2), packed=packed_spn)
-        log_z_f = log_z_s.sum((-2, -1)).flatten()
-        trans_lik = self.transition_lik(means=z_dyn_s, results=z_s[..., 2:]).sum((-2, -1)).flatten(end_dim=1)
+        log_z_f = log_z_n.flatten()
+        trans_lik = trans_n.flatten()
         elbo = trans_lik + img_lik - log_z_f
         average_elbo = elbo.mean() + img_lik_sup.mean()
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, 'include', 'stove_b200.h')).read()
-    declared = set(re.findall(r'\b(stove_[a-z0-9_]+)\s*\(', header))
+    declared = set(re.findall(r'^(?:int|int64_t|size_t|const char\*)\s+(stove_[a-z0-9_]+)\s*\(', header, re.M))
     assert len(declared) >= 20
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared:
