@@ -230,8 +230,8 @@ int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, const float*
  *   actions [A], app [O][app_dim]  ->  z_out [O][cl/2+2], z_dyn / z_dyn_std [O][cl/2],
  *   z_std [O][cl/2+2] (optional), logq / trans / reward: one float each.
  * Backward: g_z = g_z_a + g_z_b (either may be NULL), g_logq / g_trans / g_reward one float per
- * sequence -> g_z_prev [O][cl/2+2], g_sup / g_sup_std [O][6] (overwritten), g_weights
- * (overwritten or accumulated).  Workspace: stove_gnn_bwd_workspace bytes.
+ * sequence -> g_z_prev [O][cl/2+2], g_sup / g_sup_std [O][6] (overwritten), g_weights.
+ * Workspace: stove_gnn_bwd_workspace bytes.
  * ---------------------------------------------------------------------------------- */
 typedef struct {
     float pos_var, vel_std, latent_std;   /* constrain_z_dyn scales */
@@ -257,9 +257,12 @@ typedef struct {
 
 int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                       const stove_dynstep_io* io, const float* weights, void* stream);
+/* `first` / `last` mark the first and last call of one backward pass over the time steps: the
+ * per-CTA weight-gradient slabs in `workspace` are cleared on the first call, accumulate over
+ * the calls, and are reduced into g_weights (overwritten) on the last. */
 int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                       const stove_dynstep_io* io, const float* weights, float* g_weights,
-                      int accumulate, void* workspace, void* stream);
+                      int first, int last, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,7 +91,7 @@ SIGNATURES = {
     'stove_gnn_fwd': (C.c_int, [PG, i64] + [vp] * 6 + [vp]),
     'stove_gnn_bwd': (C.c_int, [PG, i64] + [vp] * 9 + [vp]),
     'stove_dynstep_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp]),
-    'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, vp, vp]),
+    'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, C.c_int, vp, vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

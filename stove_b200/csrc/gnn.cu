@@ -983,7 +983,8 @@ __global__ void __launch_bounds__(256) dynstep_fwd_kernel(stove_gnn_cfg c, GnnLa
 }
 
 __global__ void __launch_bounds__(256) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
-                                                          int64_t n, int stage_w, stove_dynstep_io io,
+                                                          int64_t n, int stage_w, int slab_accumulate,
+                                                          stove_dynstep_io io,
                                                           const float* __restrict__ weights,
                                                           float* __restrict__ slabs) {
     extern __shared__ __align__(16) float smem[];
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(256) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLa
     const int cl = c.cl, O = c.num_obj, half = cl / 2, zdim = half + 2;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int64_t ngroups = (n + seq - 1) / seq;
-    bool accum = false;
+    bool accum = slab_accumulate != 0;
     for (int64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x, accum = true) {
         const int64_t seq0 = grp * seq;
         const int nseq = (int)min((int64_t)seq, n - seq0);
@@ -1169,7 +1170,7 @@ struct GnnBwdPlan {
 
 static GnnBwdPlan gnn_bwd_plan(const stove_gnn_cfg* cfg, const GnnLayout& L, int64_t n) {
     GnnBwdPlan p;
-    int want = (int)((n + 295) / 296);
+    int want = (int)((n + 147) / 148);
     if (want < 1) want = 1;
     if (want > 4) want = 4;
     p.stage = 1;
@@ -1257,7 +1258,7 @@ extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
 
 extern "C" int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                                  const stove_dynstep_io* io, const float* weights, float* g_weights,
-                                 int accumulate, void* workspace, void* stream) {
+                                 int first, int last, void* workspace, void* stream) {
     int rc = gnn_check(cfg);
     if (rc) return rc;
     STOVE_CHECK_ARG(fuse && io && weights && g_weights && workspace && n >= 0, "null pointer");
@@ -1271,13 +1272,17 @@ extern "C" int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     if (p.seq == 0) { stove_set_error("stove_dynstep_bwd: configuration does not fit in shared memory"); return STOVE_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     STOVE_CUDA(cudaFuncSetAttribute(dynstep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
+    // the per-CTA slabs accumulate over the time steps of one backward pass (same n => same grid):
+    // cleared before the first call, reduced into g_weights after the last
+    if (first) STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
     STOVE_KERNEL(K_DYNSTEP_BWD, st, dynstep_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(
-        *cfg, L, make_fuse(cfg, fuse), p.seq, n, p.stage, *io, weights, (float*)workspace));
+        *cfg, L, make_fuse(cfg, fuse), p.seq, n, p.stage, first ? 0 : 1, *io, weights, (float*)workspace));
     STOVE_LAUNCH_CHECK();
-    STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_acc_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(
-        (const float*)workspace, p.ctas, L.total, g_weights, accumulate));
-    STOVE_LAUNCH_CHECK();
+    if (last) {
+        STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_acc_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(
+            (const float*)workspace, p.ctas, L.total, g_weights, 0));
+        STOVE_LAUNCH_CHECK();
+    }
     return STOVE_OK;
 }
 

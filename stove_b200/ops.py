@@ -407,7 +407,7 @@ class DynamicsLoop(torch.autograd.Function):
             io.g_sup, io.g_sup_ss = _sl(g_sup, t)
             io.g_sup_std = g_sup_std[:, t].data_ptr()
             N.check(lib.stove_dynstep_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
-                                          0 if k == S - 1 else 1, N.ptr(ws), st))
+                                          1 if k == S - 1 else 0, 1 if k == 0 else 0, N.ptr(ws), st))
         return carry[0], g_sup, g_sup_std, None, None, None, g_w, None, None, None
 
 
