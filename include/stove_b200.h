@@ -172,6 +172,17 @@ int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, 
                           const float* g_z_full, const float* g_std_full, float* g_zp, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * LSTM cell of the recognition network (encoder.py:50-51; nn.LSTM gate order i, f, g, o).
+ * The GEMMs stay in cuBLAS; this is the gate/state update:  gates = gx + gh,
+ * c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c').  gx, gh, act, g_gates [n][4H];
+ * c_prev (NULL = zeros), h_out, c_out, g_h, g_c, g_c_prev [n][H].  `act` saves the activated gates.
+ * ---------------------------------------------------------------------------------- */
+int stove_lstm_cell_fwd(int64_t n, int H, const float* gx, const float* gh, const float* c_prev,
+                        float* h_out, float* c_out, float* act, void* stream);
+int stove_lstm_cell_bwd(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
+                        const float* g_h, const float* g_c, float* g_gates, float* g_c_prev, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * GNN dynamics: Dynamics.forward + core (dynamics.py:181-265) for core_idx 0, and the
  * rollout loop Stove.rollout (stove.py:777-861).
  *

@@ -311,3 +311,76 @@ extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const 
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// LSTM cell (encoder.py:50-51, nn.LSTM gate order i, f, g, o): the two GEMMs stay in cuBLAS,
+// the gate non-linearities and state update (10 elementwise launches per step forward, ~25
+// backward in the tensor version) are one kernel each way.
+//   gates = gx + gh (+ bias already inside gx);  c' = sig(f) c + sig(i) tanh(g);  h' = sig(o) tanh(c')
+// ---------------------------------------------------------------------------------------
+__global__ void lstm_cell_fwd_kernel(int64_t n, int H, const float* __restrict__ gx, const float* __restrict__ gh,
+                                     const float* __restrict__ c_prev, float* __restrict__ h_out,
+                                     float* __restrict__ c_out, float* __restrict__ act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    const int64_t b = i / H;
+    const int k = (int)(i - b * H);
+    const float* px = gx + b * 4 * H;
+    const float* ph = gh ? gh + b * 4 * H : nullptr;
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = px[q * H + k] + (ph ? ph[q * H + k] : 0.f);
+    const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    const float c = fg * cp + ig * gg;
+    const float tc = tanhf(c);
+    c_out[i] = c;
+    h_out[i] = og * tc;
+    float* pa = act + b * 4 * H;        // activated gates, saved for the backward
+    pa[k] = ig; pa[H + k] = fg; pa[2 * H + k] = gg; pa[3 * H + k] = og;
+}
+
+__global__ void lstm_cell_bwd_kernel(int64_t n, int H, const float* __restrict__ act,
+                                     const float* __restrict__ c_prev, const float* __restrict__ c_out,
+                                     const float* __restrict__ g_h, const float* __restrict__ g_c,
+                                     float* __restrict__ g_gates, float* __restrict__ g_c_prev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    const int64_t b = i / H;
+    const int k = (int)(i - b * H);
+    const float* pa = act + b * 4 * H;
+    const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
+    const float tc = tanhf(c_out[i]);
+    const float gh = g_h ? g_h[i] : 0.f;
+    const float gc = (g_c ? g_c[i] : 0.f) + gh * og * (1.f - tc * tc);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    float* pg = g_gates + b * 4 * H;
+    pg[k] = gc * gg * ig * (1.f - ig);
+    pg[H + k] = gc * cp * fg * (1.f - fg);
+    pg[2 * H + k] = gc * ig * (1.f - gg * gg);
+    pg[3 * H + k] = gh * tc * og * (1.f - og);
+    g_c_prev[i] = gc * fg;
+}
+
+extern "C" int stove_lstm_cell_fwd(int64_t n, int H, const float* gx, const float* gh, const float* c_prev,
+                                   float* h_out, float* c_out, float* act, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && H > 0 && gx && h_out && c_out && act, "null pointer");
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_LSTM_CELL_FWD, s, lstm_cell_fwd_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
+        n, H, gx, gh, c_prev, h_out, c_out, act));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_lstm_cell_bwd(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
+                                   const float* g_h, const float* g_c, float* g_gates, float* g_c_prev,
+                                   void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_gates && g_c_prev, "null pointer");
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
+        n, H, act, c_prev, c_out, g_h, g_c, g_gates, g_c_prev));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -12,6 +12,7 @@
 // The backward kernel recomputes the forward on-chip (no activation tape in HBM), then walks
 // the layers in reverse; weight gradients go to a per-CTA slab in global memory (plain stores,
 // no atomics) that a second kernel reduces.
+#include <stdlib.h>
 #include "common.cuh"
 
 enum { ACT_NONE = 0, ACT_NL = 1, ACT_TANH = 2, ACT_RELU = 3, ACT_SIGMOID = 4, ACT_EXP = 5 };
@@ -1106,7 +1107,14 @@ static int gnn_check(const stove_gnn_cfg* c) {
 static const size_t kMaxSmem = 227 * 1024;
 
 // largest number of sequences per CTA that fits (optionally with staged weights), <= want
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 static int pick_seq(const stove_gnn_cfg* c, const GnnLayout& L, bool bwd, bool stage, int want) {
+    // tuning override (sequences per CTA): STOVE_GNN_SEQ_FWD / STOVE_GNN_SEQ_BWD
+    want = env_int(bwd ? "STOVE_GNN_SEQ_BWD" : "STOVE_GNN_SEQ_FWD", want);
     for (int seq = want; seq >= 1; --seq) {
         GnnBuf b = gnn_buffers(*c, L.in_dim, seq, bwd);
         size_t bytes = sizeof(float) * ((size_t)b.total + (stage ? L.total : 0));
@@ -1149,7 +1157,7 @@ extern "C" int stove_gnn_fwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     if (n == 0) return STOVE_OK;
     GnnLayout L = gnn_layout(cfg);
     // few sequences per CTA: this launch is latency bound, spread it over the chip
-    int want = (int)((n + 295) / 296);
+    int want = (int)((n + 147) / 148);
     if (want < 1) want = 1;
     if (want > 8) want = 8;
     const int seq = pick_seq(cfg, L, false, true, want);
@@ -1241,7 +1249,7 @@ extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     STOVE_CHECK_ARG(cfg->cl <= 64, "cl too large");
     if (n == 0) return STOVE_OK;
     GnnLayout L = gnn_layout(cfg);
-    int want = (int)((n + 295) / 296);
+    int want = (int)((n + 147) / 148);
     if (want < 1) want = 1;
     if (want > 8) want = 8;
     const int seq = pick_seq(cfg, L, false, true, want);

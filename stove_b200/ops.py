@@ -252,6 +252,38 @@ class SupPrepare(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------
+# LSTM cell
+# ----------------------------------------------------------------------------------------
+class LstmCell(torch.autograd.Function):
+    """gx (n, 4H) [bias included], gh (n, 4H) | None, c_prev (n, H) | None -> h (n, H), c (n, H)."""
+
+    @staticmethod
+    def forward(ctx, gx, gh, c_prev):
+        gx, gh, c_prev = gx.contiguous(), _c(gh), _c(c_prev)
+        N.require_cuda_f32(gx, gh, c_prev)
+        n, H4 = gx.shape
+        H = H4 // 4
+        h = torch.empty(n, H, device=gx.device, dtype=gx.dtype)
+        c = torch.empty_like(h)
+        act = torch.empty_like(gx)
+        N.check(N.lib().stove_lstm_cell_fwd(n, H, N.ptr(gx), N.ptr(gh), N.ptr(c_prev), N.ptr(h), N.ptr(c),
+                                            N.ptr(act), N.stream()))
+        ctx.save_for_backward(act, c_prev, c)
+        ctx.has = (gh is not None, c_prev is not None)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, g_h, g_c):
+        act, c_prev, c = ctx.saved_tensors
+        n, H = c.shape
+        g_gates = torch.empty_like(act)
+        g_c_prev = torch.empty_like(c)
+        N.check(N.lib().stove_lstm_cell_bwd(n, H, N.ptr(act), N.ptr(c_prev), N.ptr(c), N.ptr(_c(g_h)),
+                                            N.ptr(_c(g_c)), N.ptr(g_gates), N.ptr(g_c_prev), N.stream()))
+        return g_gates, (g_gates if ctx.has[0] else None), (g_c_prev if ctx.has[1] else None)
+
+
+# ----------------------------------------------------------------------------------------
 # GNN dynamics
 # ----------------------------------------------------------------------------------------
 GNN_SEGMENTS = ['act', 'enc', 'self0', 'self1', 'ra0', 'rel1', 'att1', 'rel2', 'att2', 'aff0', 'aff1',

@@ -10,6 +10,8 @@ small hidden-to-hidden GEMM only.  Parameter names are those of `nn.LSTM`
 import torch
 import torch.nn as nn
 
+from .. import ops
+
 
 class RnnStates(nn.Module):
     def __init__(self, config):
@@ -32,14 +34,11 @@ class RnnStates(nn.Module):
         H = self.lstm_size
         rnn = self.rnn
         gates_x = torch.addmm(rnn.bias_ih_l0 + rnn.bias_hh_l0, x, rnn.weight_ih_l0.t())
-        h = x.new_zeros(x.shape[0], H)
-        cell = x.new_zeros(x.shape[0], H)
+        h = cell = None                              # zero initial state: first step needs no W_hh GEMM
         outs = []
         for _ in range(self.c.num_obj):
-            g = torch.addmm(gates_x, h, rnn.weight_hh_l0.t())
-            i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
-            cell = torch.sigmoid(f) * cell + torch.sigmoid(i) * torch.tanh(gg)
-            h = torch.sigmoid(o) * torch.tanh(cell)
+            gates_h = torch.mm(h, rnn.weight_hh_l0.t()) if h is not None else None
+            h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
             outs.append(h)
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
