@@ -244,10 +244,19 @@ def run_b200(args):
     def step_resident(i):
         losses.append(run_step(dev_pool[i % POOL]))
 
+    prefetch = dp.HostPrefetcher(lambda i: host_pool[i % POOL], dev)
+
     def step_e2e(i):
-        # public call with HOST frames: H2D copy of the batch + D2H read of the loss inside the step
-        x = host_pool[i % POOL].to(dev, non_blocking=True)
-        losses.append(run_step(x).item())
+        # public call with HOST frames: every step copies its batch from pinned host memory (the copy
+        # of step i+1 overlaps the compute of step i on a side stream) and reads its loss back (D2H)
+        x = prefetch.get(i)
+        if graphed is not None:
+            prefetch.release(i, graphed.load(x))
+            loss = graphed.run()
+        else:
+            loss = engine.forward_backward(x, step_counter=1)
+        prefetch.prefetch(i + 1)
+        losses.append(loss.item())
 
     with ClockSampler(dev.index or 0) as clocks:
         ms = timed(step_resident, args.steps, args.warmup, world, on_start=lambda: lib.stove_launch_count(1))

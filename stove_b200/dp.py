@@ -110,11 +110,62 @@ class GraphedStep:
         # kernels of the native library captured in (hence launched by every replay of) the graph
         self.native_launches = _native.lib().stove_launch_count(0) - before
 
-    def __call__(self, x, actions=None, reward_target=None):
+    def load(self, x, actions=None, reward_target=None):
+        """Copy the step's inputs into the graph's static buffers; returns an event after which
+        the source tensors may be overwritten (used by HostPrefetcher)."""
         self.x.copy_(x, non_blocking=True)
         if actions is not None:
             self.actions.copy_(actions, non_blocking=True)
         if reward_target is not None:
             self.target.copy_(reward_target, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def run(self):
         self.graph.replay()
         return self.loss
+
+    def __call__(self, x, actions=None, reward_target=None):
+        self.load(x, actions, reward_target)
+        return self.run()
+
+
+class HostPrefetcher:
+    """Double-buffered host->device input pipeline: the pinned-host batch of step i+1 is copied on
+    a side stream while step i computes (the reference uploads synchronously inside the step,
+    train.py:436).  `get(i)` returns the device batch of step i and starts the copy of step i+1."""
+
+    def __init__(self, fetch, device):
+        self.fetch, self.device = fetch, device          # fetch(i) -> pinned host tensor
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs, self.events, self.free, self.ready = [None, None], [None, None], [None, None], -1
+
+    def release(self, i, event):
+        """`event`: recorded once the consumer of step i no longer reads its buffer."""
+        self.free[i % 2] = event
+
+    def _start(self, i):
+        host = self.fetch(i)
+        k = i % 2
+        if self.bufs[k] is None or self.bufs[k].shape != host.shape:
+            self.bufs[k] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
+        if self.free[k] is not None:
+            self.stream.wait_event(self.free[k])          # only the last reader of buffer k, not the whole step
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.bufs[k].copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.events[k] = ev
+        self.ready = i
+
+    def get(self, i):
+        if self.ready != i:
+            self._start(i)
+        torch.cuda.current_stream(self.device).wait_event(self.events[i % 2])
+        return self.bufs[i % 2]
+
+    def prefetch(self, i):
+        self._start(i)
