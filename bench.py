@@ -119,6 +119,7 @@ def build_ac_model(device):
 
 def dist_setup(n_gpus):
     import torch.distributed as dist
+    os.environ['NCCL_DEBUG'] = os.environ.get('STOVE_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
@@ -334,10 +335,17 @@ def run_b200(args):
                                  'metric': 'rollout_frames_per_sec', 'value': world * n2 * 100 * k2 / (ms2 * 1e-3),
                                  'unit': 'frames/s', 'ms_per_call': ms2 / k2}
 
-    if rank != 0:
+    def finish():
+        # graphs that captured NCCL work must go before the communicator; a hard exit after the flush
+        # avoids teardown hangs (the measurement is complete at this point)
+        sys.stdout.flush()
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     cpu = None
@@ -368,9 +376,7 @@ def run_b200(args):
     }
     line.update(extra)
     print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 def kernel_algorithmic_bytes(kernel, batch):
