@@ -597,6 +597,256 @@ __global__ void __launch_bounds__(512) gnn_rollout_kernel(
 }
 
 // ------------------------------------------------------------------------------------
+// Warp-per-sequence rollout (O = 3, cl = 32): the fast path of Stove.rollout.
+//
+// ncu on the CTA-wide rollout kernel showed 19 % of cycles in barrier stalls, 46 % issue
+// utilisation and 2x more FFMA slots than useful MACs (idle lanes, padded rows): a single
+// sequence has only 9 pair rows and 3 object rows, so spreading one layer over 512 threads
+// buys little and costs a CTA barrier per layer.  Here one WARP owns one sequence for all
+// time steps: its activations (16 KB) live in its private slice of shared memory, layers are
+// separated by __syncwarp only, and every lane owns output features for ALL rows of the layer
+// (rel0|att0: 4 features x 9 rows = 36 FFMA per 7 shared loads).  Weights (103 KB) are staged
+// once per CTA and shared by its 7 warps.  Summation order per output is unchanged (bias, then
+// k ascending), so results are bitwise identical to the CTA-wide kernel.
+// ------------------------------------------------------------------------------------
+namespace warpk {
+constexpr int O = 3, P = 9, PR = 12, ORW = 4, CL = 32, HALF = 16, ZD = 18;
+constexpr int IN_MAX = 24;
+// per-warp buffer offsets (floats)
+constexpr int SIN = 0, S = SIN + IN_MAX * ORW, H = S + CL * ORW, SELFD = H + CL * ORW, D = SELFD + CL * ORW,
+              F1 = D + CL * ORW, F2 = F1 + CL * ORW, CAT = F2 + CL * ORW, O1 = CAT + 2 * CL * ORW,
+              OUT = O1 + CL * ORW, RH0 = OUT + CL * ORW, RH1 = RH0 + CL * ORW, SMALL = RH1 + CL * ORW,
+              PA = SMALL + 64, PB = PA + 65 * PR + 4 /* keep 16-byte alignment */, TOTAL = PB + 128 * PR;
+static_assert(PA % 4 == 0 && PB % 4 == 0 && TOTAL % 4 == 0, "alignment");
+
+// object-row layer: out[n][r] = act(b[n] + sum_k W[k][n] in[k][r]) (+ res), n = lane, r < 3
+template <int ACT>
+__device__ __forceinline__ void obj32(const float* __restrict__ W, const float* __restrict__ bias, int K,
+                                      const float* in, float* out, const float* res, int nl, int lane) {
+    float a0 = bias[lane], a1 = a0, a2 = a0;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        const float w = W[k * CL + lane];
+        const float4 x = in4[k];
+        a0 = fmaf(x.x, w, a0);
+        a1 = fmaf(x.y, w, a1);
+        a2 = fmaf(x.z, w, a2);
+    }
+    a0 = apply_act(a0, ACT, nl); a1 = apply_act(a1, ACT, nl); a2 = apply_act(a2, ACT, nl);
+    if (res) { a0 += res[lane * ORW]; a1 += res[lane * ORW + 1]; a2 += res[lane * ORW + 2]; }
+    out[lane * ORW] = a0; out[lane * ORW + 1] = a1; out[lane * ORW + 2] = a2;
+}
+
+// pair-row layer with 32 outputs: n = lane, 9 rows
+template <int K, int ACT>
+__device__ __forceinline__ void pair32(const float* __restrict__ W, const float* __restrict__ bias, const float* in,
+                                       float* out, const float* res, int nl, int lane) {
+    float acc[P];
+    const float bv = bias[lane];
+#pragma unroll
+    for (int r = 0; r < P; ++r) acc[r] = bv;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const float w = W[k * CL + lane];
+        const float4 x0 = in4[k * 3], x1 = in4[k * 3 + 1], x2 = in4[k * 3 + 2];
+        acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]);
+        acc[3] = fmaf(x0.w, w, acc[3]); acc[4] = fmaf(x1.x, w, acc[4]); acc[5] = fmaf(x1.y, w, acc[5]);
+        acc[6] = fmaf(x1.z, w, acc[6]); acc[7] = fmaf(x1.w, w, acc[7]); acc[8] = fmaf(x2.x, w, acc[8]);
+    }
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        float y = apply_act(acc[r], ACT, nl);
+        if (res) y += res[lane * PR + r];
+        out[lane * PR + r] = y;
+    }
+}
+
+// one dynamics step of one sequence, executed by one warp; `a` = this warp's activation slice
+__device__ __forceinline__ void forward_step(const stove_gnn_cfg& c, const GnnLayout& L, const float* __restrict__ W,
+                                             float* a, const float* __restrict__ act_row, int lane) {
+    const int nl = c.nonlin;
+    if (c.action_dim > 0) {
+        if (lane < O * 4) {
+            float acc = W[L.act_b + lane];
+            for (int k = 0; k < c.action_dim; ++k) acc = fmaf(__ldg(act_row + k), W[L.act_w + k * O * 4 + lane], acc);
+            a[SIN + (HALF + (lane & 3)) * ORW + (lane >> 2)] = acc;
+        }
+        __syncwarp();
+    }
+    obj32<ACT_NONE>(W + L.enc_w, W + L.enc_b, L.in_dim, a + SIN, a + S, nullptr, nl, lane);
+    __syncwarp();
+    if (lane < c.lim_enc) {
+#pragma unroll
+        for (int r = 0; r < O; ++r) a[S + lane * ORW + r] = a[SIN + lane * ORW + r];
+    }
+    __syncwarp();
+    // pair inputs [s_i, s_j, |p_i - p_j|^2], row p = i*3 + j
+    for (int e = lane; e < (2 * CL + 1) * P; e += 32) {
+        const int k = e / P, pp = e - k * P, i = pp / O, j = pp - i * O;
+        float v;
+        if (k < CL) v = a[S + k * ORW + i];
+        else if (k < 2 * CL) v = a[S + (k - CL) * ORW + j];
+        else {
+            const float dx = a[S + i] - a[S + j], dy = a[S + ORW + i] - a[S + ORW + j];
+            v = dx * dx + dy * dy;
+        }
+        a[PA + k * PR + pp] = v;
+    }
+    obj32<ACT_NL>(W + L.self0_w, W + L.self0_b, CL, a + S, a + H, nullptr, nl, lane);
+    __syncwarp();
+    obj32<ACT_NONE>(W + L.self1_w, W + L.self1_b, CL, a + H, a + SELFD, a + H, nl, lane);
+    {   // rel0|att0: 65 -> 128, lane owns features lane + 32 e
+        float acc[4][P];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float bv = W[L.ra0_b + lane + 32 * e];
+#pragma unroll
+            for (int r = 0; r < P; ++r) acc[e][r] = bv;
+        }
+        const float4* in4 = reinterpret_cast<const float4*>(a + PA);
+        const float* w0 = W + L.ra0_w + lane;
+#pragma unroll 2
+        for (int k = 0; k < 2 * CL + 1; ++k) {
+            const float4 x0 = in4[k * 3], x1 = in4[k * 3 + 1], x2 = in4[k * 3 + 2];
+            const float xr[P] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float w = w0[k * 4 * CL + 32 * e];
+#pragma unroll
+                for (int r = 0; r < P; ++r) acc[e][r] = fmaf(xr[r], w, acc[e][r]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int r = 0; r < P; ++r) a[PB + (lane + 32 * e) * PR + r] = apply_act(acc[e][r], ACT_NL, nl);
+    }
+    __syncwarp();
+    // rel1 / att1 (64 -> 32 each): outputs overwrite the dead pair-input buffer
+    pair32<2 * CL, ACT_NL>(W + L.rel1_w, W + L.rel1_b, a + PB, a + PA, nullptr, nl, lane);
+    pair32<2 * CL, ACT_NL>(W + L.att1_w, W + L.att1_b, a + PB + 2 * CL * PR, a + PA + CL * PR, nullptr, nl, lane);
+    __syncwarp();
+    // rel2 (residual) -> PB rows 0..31 ; att2 (32 -> 1, exp) -> PB row 32
+    pair32<CL, ACT_NONE>(W + L.rel2_w, W + L.rel2_b, a + PA, a + PB, a + PA, nl, lane);
+    if (lane < P) {
+        float acc = W[L.att2_b];
+#pragma unroll 8
+        for (int k = 0; k < CL; ++k) acc = fmaf(a[PA + (CL + k) * PR + lane], W[L.att2_w + k], acc);
+        a[PB + CL * PR + lane] = expf(acc);
+    }
+    __syncwarp();
+    // d_i = self_i + sum_j rel_ij * mask_ij * att_ij (zero mask kept as a multiplication)
+#pragma unroll
+    for (int i = 0; i < O; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < O; ++j)
+            acc += a[PB + lane * PR + i * O + j] * (i == j ? 0.f : 1.f) * a[PB + CL * PR + i * O + j];
+        a[D + lane * ORW + i] = a[SELFD + lane * ORW + i] + acc;
+    }
+    __syncwarp();
+    obj32<ACT_TANH>(W + L.aff0_w, W + L.aff0_b, CL, a + D, a + F1, nullptr, nl, lane);
+    if (c.reward) obj32<ACT_RELU>(W + L.rew00_w, W + L.rew00_b, CL, a + D, a + RH0, nullptr, nl, lane);
+    __syncwarp();
+    obj32<ACT_TANH>(W + L.aff1_w, W + L.aff1_b, CL, a + F1, a + F2, a + F1, nl, lane);
+    if (c.reward) obj32<ACT_NONE>(W + L.rew02_w, W + L.rew02_b, CL, a + RH0, a + RH1, nullptr, nl, lane);
+    __syncwarp();
+    obj32<ACT_NONE>(W + L.aff2_w, W + L.aff2_b, CL, a + F2, a + CAT, nullptr, nl, lane);
+#pragma unroll
+    for (int r = 0; r < O; ++r) a[CAT + (CL + lane) * ORW + r] = a[S + lane * ORW + r];
+    if (c.reward) a[SMALL + lane] = a[RH1 + lane * ORW] + a[RH1 + lane * ORW + 1] + a[RH1 + lane * ORW + 2];
+    __syncwarp();
+    obj32<ACT_TANH>(W + L.out0_w, W + L.out0_b, 2 * CL, a + CAT, a + O1, nullptr, nl, lane);
+    if (c.reward && lane < CL / 2) {
+        float acc = W[L.rew10_b + lane];
+        for (int k = 0; k < CL; ++k) acc = fmaf(a[SMALL + k], W[L.rew10_w + k * (CL / 2) + lane], acc);
+        a[SMALL + 32 + lane] = fmaxf(acc, 0.f);
+    }
+    __syncwarp();
+    obj32<ACT_NONE>(W + L.out1_w, W + L.out1_b, CL, a + O1, a + OUT, a + O1, nl, lane);
+    if (c.reward && lane < CL / 4) {
+        float acc = W[L.rew12_b + lane];
+        for (int k = 0; k < CL / 2; ++k) acc = fmaf(a[SMALL + 32 + k], W[L.rew12_w + k * (CL / 4) + lane], acc);
+        a[SMALL + 48 + lane] = fmaxf(acc, 0.f);
+    }
+    __syncwarp();
+    if (c.reward && lane == 0) {
+        float acc = W[L.rew14_b];
+        for (int k = 0; k < CL / 4; ++k) acc = fmaf(a[SMALL + 48 + k], W[L.rew14_w + k], acc);
+        a[SMALL + 56] = sigmoidf_(acc);
+    }
+    __syncwarp();
+}
+}  // namespace warpk
+
+__global__ void __launch_bounds__(224, 1) gnn_rollout_warp_kernel(
+    stove_gnn_cfg c, GnnLayout L, int64_t n, int num, const float* __restrict__ z_last,
+    const float* __restrict__ actions, int action_len, const float* __restrict__ app,
+    const float* __restrict__ weights, const float* __restrict__ noise, float pos_var, float vel_std,
+    float latent_std, float* __restrict__ z_out, float* __restrict__ std_out, float* __restrict__ logq_out,
+    float* __restrict__ rewards) {
+    using namespace warpk;
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    stage_weights(weights, Ws, L.total);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    float* a = smem + L.total + warp * TOTAL;
+    for (int i = lane; i < TOTAL; i += 32) a[i] = 0.f;
+    __syncthreads();
+    for (int64_t sq = (int64_t)blockIdx.x * wpc + warp; sq < n; sq += (int64_t)gridDim.x * wpc) {
+        // state [x, y, vx, vy, latent x12] of the 3 objects, appearances
+        for (int e = lane; e < O * HALF; e += 32) {
+            const int o = e / HALF, k = e - o * HALF;
+            a[SIN + k * ORW + o] = __ldg(z_last + (sq * O + o) * ZD + 2 + k);
+        }
+        if (c.app_dim > 0) {
+            const int a0 = HALF + (c.action_dim > 0 ? 4 : 0);
+            for (int e = lane; e < O * c.app_dim; e += 32) {
+                const int o = e / c.app_dim, k = e - o * c.app_dim;
+                a[SIN + (a0 + k) * ORW + o] = __ldg(app + (sq * O + o) * c.app_dim + k);
+            }
+        }
+        __syncwarp();
+        for (int t = 0; t < num; ++t) {
+            const float* arow = actions ? actions + (sq * action_len + (t % action_len)) * c.action_dim : nullptr;
+            forward_step(c, L, Ws, a, arow, lane);
+            // constrain (dynamics.py:147-179), integrate positions, optional sampling; the new
+            // state is parked in F1 so that all lanes still read the old positions
+            for (int e = lane; e < O * HALF; e += 32) {
+                const int o = e / HALF, k = e - o * HALF;
+                float m = 2.f * sigmoidf_(a[OUT + k * ORW + o]) - 1.f;
+                if (k < 2) m += a[SIN + k * ORW + o];
+                float val = m;
+                const int64_t o16 = ((sq * num + t) * O + o) * HALF + k;
+                if (noise || std_out) {
+                    const float sd = (k < 2 ? pos_var : (k < 4 ? vel_std : latent_std)) *
+                                     sigmoidf_(a[OUT + (HALF + k) * ORW + o]);
+                    if (std_out) std_out[o16] = sd;
+                    if (noise) {
+                        const float e_ = __ldg(noise + o16);
+                        val = m + sd * e_;
+                        if (logq_out) logq_out[o16] = -0.5f * e_ * e_ - logf(sd) - HALF_LOG_2PI;
+                    }
+                }
+                a[F1 + k * ORW + o] = val;
+                const int64_t oz = ((sq * num + t) * O + o) * ZD;
+                z_out[oz + 2 + k] = val;
+                if (k < 2) z_out[oz + k] = __ldg(z_last + (sq * O + o) * ZD + k);
+            }
+            if (c.reward && rewards && lane == 0) rewards[sq * num + t] = a[SMALL + 56];
+            __syncwarp();
+            for (int e = lane; e < O * HALF; e += 32) {
+                const int o = e / HALF, k = e - o * HALF;
+                a[SIN + k * ORW + o] = a[F1 + k * ORW + o];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Backward core: expects the forward activations (gnn_forward_core) and the upstream gradient
 // sm[b.g_out] in shared memory; leaves d/d(s_in) in sm[b.g_sin] (first cl/2 features, raw
 // pass-through already added) and writes this CTA's weight gradients into `slab`.
@@ -1309,6 +1559,21 @@ extern "C" int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, c
     STOVE_CHECK_ARG(!(logq_out && !noise), "logq_out requires noise");
     if (n == 0 || num == 0) return STOVE_OK;
     GnnLayout L = gnn_layout(cfg);
+    if (cfg->num_obj == 3 && cfg->cl == 32 && L.in_dim <= warpk::IN_MAX && !env_int("STOVE_ROLLOUT_CTA", 0)) {
+        // fast path: one warp per sequence, 7 warps (sequences) per SM
+        const int wpc = 7;
+        const size_t smem = sizeof(float) * ((size_t)L.total + (size_t)wpc * warpk::TOTAL);
+        if (smem <= kMaxSmem) {
+            STOVE_CUDA(cudaFuncSetAttribute(gnn_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t groups = (n + wpc - 1) / wpc;
+            const int ctas = (int)(groups < 148 ? groups : 148);
+            STOVE_KERNEL(K_GNN_ROLLOUT, (cudaStream_t)stream, gnn_rollout_warp_kernel<<<ctas, 32 * wpc, smem, (cudaStream_t)stream>>>(
+                *cfg, L, n, num, z_last, actions, action_len, app, weights, noise, pos_var, vel_std, latent_std,
+                z_out, std_out, logq_out, rewards));
+            STOVE_LAUNCH_CHECK();
+            return STOVE_OK;
+        }
+    }
     // one persistent CTA per SM: spread the sequences evenly over 148 CTAs
     int want = (int)((n + 147) / 148);
     if (want < 1) want = 1;
