@@ -85,182 +85,188 @@ __device__ void match_step(const SupParams& p, float* err, int* idx) {
     }
 }
 
+// One warp per sequence; the warp's working set lives in its slice of shared memory.  Only the
+// matching itself (T-1 tiny assignment problems on detached values) runs on a single lane.
 // raw encoder output zp [n][T][O][8] -> z_sup [n][T][O][4], z_full / std_full [n][T][O][6],
 // app_out [n][T][O][3] (matched appearances), idx [n][T][O] (int32), flag [n][T][O] (bit0, bit1)
-__global__ void sup_prepare_fwd_kernel(SupParams p, int64_t n, const float* __restrict__ zp,
-                                       const float* __restrict__ app, float* __restrict__ z_sup,
-                                       float* __restrict__ z_full, float* __restrict__ std_full,
-                                       float* __restrict__ app_out, int32_t* __restrict__ idx_out,
-                                       int32_t* __restrict__ flag_out) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#define SG_WARPS 4
+__device__ __forceinline__ int sup_smem_floats(int T, int O) { return 2 * T * O * 8 + 2 * T * O; }
+
+__global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
+    SupParams p, int64_t n, const float* __restrict__ zp, const float* __restrict__ app,
+    float* __restrict__ z_sup, float* __restrict__ z_full, float* __restrict__ std_full,
+    float* __restrict__ app_out, int32_t* __restrict__ idx_out, int32_t* __restrict__ flag_out) {
+    extern __shared__ float sg_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
     if (b >= n) return;
-    const int T = p.T, O = p.O;
-    float z[SG_MAX_T * SG_MAX_O * 8];                 // constrained (mean 4 | std 4), time-major
-    float zm[SG_MAX_T * SG_MAX_O * 8];                // matched
-    const float* src = zp + b * T * O * 8;
-    for (int q = 0; q < T * O; ++q) {
-        float s[8];
-        for (int f = 0; f < 8; ++f) s[f] = sigmoidf_(src[q * 8 + f]);
-        z[q * 8 + 0] = p.scale_lo + (p.scale_hi - p.scale_lo) * s[0];
-        z[q * 8 + 1] = p.ratio_lo + (p.ratio_hi - p.ratio_lo) * s[1];
-        z[q * 8 + 2] = p.pos_bound * (2.f * s[2] - 1.f);
-        z[q * 8 + 3] = p.pos_bound * (2.f * s[3] - 1.f);
-        z[q * 8 + 4] = p.scale_var * s[4];
-        z[q * 8 + 5] = p.scale_var * s[5];
-        z[q * 8 + 6] = p.pos_var * s[6];
-        z[q * 8 + 7] = p.pos_var * s[7];
+    const int T = p.T, O = p.O, TO = T * O;
+    float* z = sg_smem + warp * sup_smem_floats(T, O);     // constrained, later the smoothed tensor
+    float* zm = z + TO * 8;                                 // matched
+    int* idx = reinterpret_cast<int*>(zm + TO * 8);         // [T][O]
+    int* flg = idx + TO;
+    const float* src = zp + b * TO * 8;
+    const float* asrc = app ? app + b * TO * 3 : nullptr;
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int f = q & 7;
+        const float sgm = sigmoidf_(__ldg(src + q));
+        float v;
+        if (f == 0) v = p.scale_lo + (p.scale_hi - p.scale_lo) * sgm;
+        else if (f == 1) v = p.ratio_lo + (p.ratio_hi - p.ratio_lo) * sgm;
+        else if (f < 4) v = p.pos_bound * (2.f * sgm - 1.f);
+        else if (f < 6) v = p.scale_var * sgm;
+        else v = p.pos_var * sgm;
+        z[q] = v;
     }
-    // matching on positions scaled to [0, 1] ((z + 1) / 2, stove.py:220), detached
-    int idx[SG_MAX_O];
-    float appm[SG_MAX_T * SG_MAX_O * 3];
-    const float* asrc = app ? app + b * T * O * 3 : nullptr;
-    for (int a = 0; a < O; ++a) {
-        for (int f = 0; f < 8; ++f) zm[a * 8 + f] = z[a * 8 + f];
-        if (asrc) for (int c = 0; c < 3; ++c) appm[a * 3 + c] = asrc[a * 3 + c];
-        idx_out[(b * T) * O + a] = a;
-    }
-    for (int t = 1; t < T; ++t) {
-        float prev_pos[SG_MAX_O * 2], cur_pos[SG_MAX_O * 2], err[SG_MAX_O * SG_MAX_O];
-        for (int a = 0; a < O; ++a)
-            for (int d = 0; d < 2; ++d) {
-                prev_pos[a * 2 + d] = (zm[((t - 1) * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
-                cur_pos[a * 2 + d] = (z[(t * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
-            }
-        match_errors(p, prev_pos, asrc ? appm + (t - 1) * O * 3 : nullptr, cur_pos,
-                     asrc ? asrc + t * O * 3 : nullptr, err);
-        match_step(p, err, idx);
+    __syncwarp();
+    if (lane == 0) {
+        // matching on positions scaled to [0, 1] ((z + 1) / 2, stove.py:220), detached
+        float prev_pos[SG_MAX_O * 2], cur_pos[SG_MAX_O * 2], prev_app[SG_MAX_O * 3], err[SG_MAX_O * SG_MAX_O];
+        int cur[SG_MAX_O];
         for (int a = 0; a < O; ++a) {
-            for (int f = 0; f < 8; ++f) zm[(t * O + a) * 8 + f] = z[(t * O + idx[a]) * 8 + f];
-            if (asrc) for (int c = 0; c < 3; ++c) appm[(t * O + a) * 3 + c] = asrc[(t * O + idx[a]) * 3 + c];
-            idx_out[(b * T + t) * O + a] = idx[a];
+            idx[a] = a;
+            for (int d = 0; d < 2; ++d) prev_pos[a * 2 + d] = (z[a * 8 + 2 + d] + 1.f) * 0.5f;
+            if (asrc) for (int c = 0; c < 3; ++c) prev_app[a * 3 + c] = asrc[a * 3 + c];
+        }
+        for (int t = 1; t < T; ++t) {
+            for (int a = 0; a < O; ++a)
+                for (int d = 0; d < 2; ++d) cur_pos[a * 2 + d] = (z[(t * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
+            match_errors(p, prev_pos, asrc ? prev_app : nullptr, cur_pos, asrc ? asrc + t * O * 3 : nullptr, err);
+            match_step(p, err, cur);
+            for (int a = 0; a < O; ++a) {
+                idx[t * O + a] = cur[a];
+                for (int d = 0; d < 2; ++d) prev_pos[a * 2 + d] = (z[(t * O + cur[a]) * 8 + 2 + d] + 1.f) * 0.5f;
+            }
+            if (asrc)
+                for (int a = 0; a < O; ++a)
+                    for (int c = 0; c < 3; ++c) prev_app[a * 3 + c] = asrc[(t * O + cur[a]) * 3 + c];
         }
     }
+    __syncwarp();
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int ta = q >> 3, f = q & 7, t = ta / O;
+        zm[q] = z[(t * O + idx[ta]) * 8 + f];
+    }
+    for (int q = lane; q < TO; q += 32) idx_out[b * TO + q] = idx[q];
     if (app_out && asrc)
-        for (int q = 0; q < T * O * 3; ++q) app_out[b * T * O * 3 + q] = appm[q];
+        for (int q = lane; q < TO * 3; q += 32) {
+            const int ta = q / 3, c = q - ta * 3, t = ta / O;
+            app_out[b * TO * 3 + q] = asrc[(t * O + idx[ta]) * 3 + c];
+        }
+    __syncwarp();
     // smoothing of glitches (stove.py:516-571): flags from the first two features
-    // (z is reused as the fixed tensor from here on)
-    for (int t = 0; t < T; ++t)
-        for (int a = 0; a < O; ++a) {
-            int fl = 0;
-            if (p.fix && t >= 1 && t + 1 < T)
-                for (int d = 0; d < 2; ++d) {
-                    const float before = fabsf(zm[(t * O + a) * 8 + d] - zm[((t - 1) * O + a) * 8 + d]);
-                    const float after = fabsf(zm[((t + 1) * O + a) * 8 + d] - zm[(t * O + a) * 8 + d]);
-                    if (before > p.fix_eps && after > p.fix_eps) fl |= 1 << d;
-                }
-            flag_out[(b * T + t) * O + a] = fl;
-            for (int f = 0; f < 8; ++f) {
-                float v = zm[(t * O + a) * 8 + f];
-                if (fl & (1 << (f & 1))) v = 0.5f * (zm[((t - 1) * O + a) * 8 + f] + zm[((t + 1) * O + a) * 8 + f]);
-                z[(t * O + a) * 8 + f] = v;
+    for (int q = lane; q < TO; q += 32) {
+        const int t = q / O;
+        int fl = 0;
+        if (p.fix && t >= 1 && t + 1 < T)
+            for (int d = 0; d < 2; ++d) {
+                const float before = fabsf(zm[q * 8 + d] - zm[(q - O) * 8 + d]);
+                const float after = fabsf(zm[(q + O) * 8 + d] - zm[q * 8 + d]);
+                if (before > p.fix_eps && after > p.fix_eps) fl |= 1 << d;
             }
-        }
-    // outputs
-    for (int t = 0; t < T; ++t)
-        for (int a = 0; a < O; ++a) {
-            const int q = t * O + a;
-            const int64_t o4 = (b * T * O + q) * 4, o6 = (b * T * O + q) * 6;
-            for (int f = 0; f < 4; ++f) z_sup[o4 + f] = z[q * 8 + f];
-            if (t == 0) {
-                for (int f = 0; f < 6; ++f) { z_full[o6 + f] = 0.f; std_full[o6 + f] = 0.f; }
+        flg[q] = fl;
+        flag_out[b * TO + q] = fl;
+    }
+    __syncwarp();
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int ta = q >> 3, f = q & 7;
+        float v = zm[q];
+        if (flg[ta] & (1 << (f & 1))) v = 0.5f * (zm[q - O * 8] + zm[q + O * 8]);
+        z[q] = v;
+    }
+    __syncwarp();
+    for (int q = lane; q < TO * 6; q += 32) {
+        const int ta = q / 6, f = q - ta * 6, t = ta / O;
+        const int64_t o6 = (b * TO + ta) * 6 + f;
+        float zf = 0.f, sf = 0.f;
+        if (t > 0) {
+            if (f < 4) {
+                zf = z[ta * 8 + f];
+                sf = z[ta * 8 + 4 + f];
             } else {
-                const int qp = (t - 1) * O + a;
-                for (int f = 0; f < 4; ++f) { z_full[o6 + f] = z[q * 8 + f]; std_full[o6 + f] = z[q * 8 + 4 + f]; }
-                for (int d = 0; d < 2; ++d) {
-                    z_full[o6 + 4 + d] = z[q * 8 + 2 + d] - z[qp * 8 + 2 + d];
-                    std_full[o6 + 4 + d] = sqrtf(sq(z[q * 8 + 6 + d]) + sq(z[qp * 8 + 6 + d]));
-                }
+                const int d = f - 4;
+                zf = z[ta * 8 + 2 + d] - z[(ta - O) * 8 + 2 + d];
+                sf = sqrtf(sq(z[ta * 8 + 6 + d]) + sq(z[(ta - O) * 8 + 6 + d]));
             }
         }
+        z_full[o6] = zf;
+        std_full[o6] = sf;
+        if (f < 4) z_sup[(b * TO + ta) * 4 + f] = z[ta * 8 + f];
+    }
 }
 
-__global__ void sup_prepare_bwd_kernel(SupParams p, int64_t n, const float* __restrict__ zp,
-                                       const int32_t* __restrict__ idx_in, const int32_t* __restrict__ flag_in,
-                                       const float* __restrict__ std_full, const float* __restrict__ g_z_sup,
-                                       const float* __restrict__ g_z_full, const float* __restrict__ g_std_full,
-                                       float* __restrict__ g_zp) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
+    SupParams p, int64_t n, const float* __restrict__ zp, const int32_t* __restrict__ idx_in,
+    const int32_t* __restrict__ flag_in, const float* __restrict__ std_full, const float* __restrict__ g_z_sup,
+    const float* __restrict__ g_z_full, const float* __restrict__ g_std_full, float* __restrict__ g_zp) {
+    extern __shared__ float sg_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
     if (b >= n) return;
-    const int T = p.T, O = p.O;
-    float gf[SG_MAX_T * SG_MAX_O * 8];     // gradient w.r.t. the fixed (smoothed) tensor
-    float gm[SG_MAX_T * SG_MAX_O * 8];     // w.r.t. the matched tensor
-    float sf[SG_MAX_T * SG_MAX_O * 2];     // fixed position stds, recomputed below
-    for (int q = 0; q < T * O * 8; ++q) { gf[q] = 0.f; gm[q] = 0.f; }
-    // recompute the fixed position stds (features 6, 7) needed by the sqrt derivative
-    {
-        const float* src = zp + b * T * O * 8;
-        float sm_[SG_MAX_T * SG_MAX_O * 2];
-        for (int t = 0; t < T; ++t)
-            for (int a = 0; a < O; ++a) {
-                const int j = idx_in[(b * T + t) * O + a];
-                for (int d = 0; d < 2; ++d) sm_[(t * O + a) * 2 + d] = p.pos_var * sigmoidf_(src[(t * O + j) * 8 + 6 + d]);
-            }
-        for (int t = 0; t < T; ++t)
-            for (int a = 0; a < O; ++a) {
-                const int fl = flag_in[(b * T + t) * O + a];
-                for (int d = 0; d < 2; ++d) {
-                    float v = sm_[(t * O + a) * 2 + d];
-                    if (fl & (1 << d)) v = 0.5f * (sm_[((t - 1) * O + a) * 2 + d] + sm_[((t + 1) * O + a) * 2 + d]);
-                    sf[(t * O + a) * 2 + d] = v;
-                }
-            }
+    const int T = p.T, O = p.O, TO = T * O;
+    float* gf = sg_smem + warp * sup_smem_floats(T, O);    // gradient w.r.t. the smoothed tensor
+    float* gm = gf + TO * 8;                                // w.r.t. the matched tensor
+    float* sm_ = gm + TO * 8;                               // matched position stds [TO][2] (reuses the int area)
+    const float* src = zp + b * TO * 8;
+    const int32_t* idx = idx_in + b * TO;
+    const int32_t* flg = flag_in + b * TO;
+    // matched position stds (features 6, 7); their smoothed values are recomputed on the fly
+    for (int q = lane; q < TO * 2; q += 32) {
+        const int ta = q >> 1, d = q & 1, t = ta / O;
+        sm_[q] = p.pos_var * sigmoidf_(__ldg(src + (t * O + idx[ta]) * 8 + 6 + d));
     }
-    // outputs -> fixed tensor
-    for (int t = 0; t < T; ++t)
-        for (int a = 0; a < O; ++a) {
-            const int q = t * O + a;
-            const int64_t o4 = (b * T * O + q) * 4, o6 = (b * T * O + q) * 6;
-            if (g_z_sup) for (int f = 0; f < 4; ++f) gf[q * 8 + f] += g_z_sup[o4 + f];
-            if (t == 0) continue;
-            const int qp = (t - 1) * O + a;
-            for (int f = 0; f < 4; ++f) {
-                if (g_z_full) gf[q * 8 + f] += g_z_full[o6 + f];
-                if (g_std_full) gf[q * 8 + 4 + f] += g_std_full[o6 + f];
-            }
-            for (int d = 0; d < 2; ++d) {
-                if (g_z_full) {
-                    const float g = g_z_full[o6 + 4 + d];
-                    gf[q * 8 + 2 + d] += g;
-                    gf[qp * 8 + 2 + d] -= g;
-                }
-                if (g_std_full) {
-                    const float v = std_full[o6 + 4 + d];
-                    const float g = g_std_full[o6 + 4 + d] / v;
-                    gf[q * 8 + 6 + d] += g * sf[q * 2 + d];
-                    gf[qp * 8 + 6 + d] += g * sf[qp * 2 + d];
-                }
+    __syncwarp();
+    auto fixed_std = [&](int ta, int d) {
+        return (flg[ta] & (1 << d)) ? 0.5f * (sm_[(ta - O) * 2 + d] + sm_[(ta + O) * 2 + d]) : sm_[ta * 2 + d];
+    };
+    // outputs -> smoothed tensor, gather form (each element written once)
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int ta = q >> 3, f = q & 7, t = ta / O;
+        const int64_t o6 = (b * TO + ta) * 6;
+        float g = 0.f;
+        if (f < 4 && g_z_sup) g += __ldg(g_z_sup + (b * TO + ta) * 4 + f);
+        if (t > 0) {
+            if (f < 4 && g_z_full) g += __ldg(g_z_full + o6 + f);
+            if (f >= 4 && g_std_full) g += __ldg(g_std_full + o6 + f - 4);
+        }
+        if (f == 2 || f == 3) {
+            const int d = f - 2;
+            if (g_z_full) {
+                if (t > 0) g += __ldg(g_z_full + o6 + 4 + d);
+                if (t + 1 < T) g -= __ldg(g_z_full + o6 + O * 6 + 4 + d);
             }
         }
+        if (f >= 6 && g_std_full) {
+            const int d = f - 6;
+            const float mine = fixed_std(ta, d);
+            if (t > 0) g += __ldg(g_std_full + o6 + 4 + d) / __ldg(std_full + o6 + 4 + d) * mine;
+            if (t + 1 < T) g += __ldg(g_std_full + o6 + O * 6 + 4 + d) / __ldg(std_full + o6 + O * 6 + 4 + d) * mine;
+        }
+        gf[q] = g;
+    }
+    __syncwarp();
     // smoothing select -> matched tensor
-    for (int t = 0; t < T; ++t)
-        for (int a = 0; a < O; ++a) {
-            const int fl = flag_in[(b * T + t) * O + a];
-            for (int f = 0; f < 8; ++f) {
-                const float g = gf[(t * O + a) * 8 + f];
-                if (fl & (1 << (f & 1))) {
-                    gm[((t - 1) * O + a) * 8 + f] += 0.5f * g;
-                    gm[((t + 1) * O + a) * 8 + f] += 0.5f * g;
-                } else {
-                    gm[(t * O + a) * 8 + f] += g;
-                }
-            }
-        }
-    // gather -> constrained tensor (scatter-add: `volatile` matching may pick an object twice)
-    for (int q = 0; q < T * O * 8; ++q) gf[q] = 0.f;
-    for (int t = 0; t < T; ++t)
-        for (int a = 0; a < O; ++a) {
-            const int j = idx_in[(b * T + t) * O + a];
-            for (int f = 0; f < 8; ++f) gf[(t * O + j) * 8 + f] += gm[(t * O + a) * 8 + f];
-        }
-    // constrain_zp: every output is scale * sigmoid(raw) + offset
-    const float* src = zp + b * T * O * 8;
-    const float sc[8] = {p.scale_hi - p.scale_lo, p.ratio_hi - p.ratio_lo, 2.f * p.pos_bound, 2.f * p.pos_bound,
-                         p.scale_var, p.scale_var, p.pos_var, p.pos_var};
-    for (int q = 0; q < T * O; ++q)
-        for (int f = 0; f < 8; ++f) {
-            const float s = sigmoidf_(src[q * 8 + f]);
-            g_zp[b * T * O * 8 + q * 8 + f] = gf[q * 8 + f] * sc[f] * s * (1.f - s);
-        }
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int ta = q >> 3, f = q & 7, t = ta / O, bit = 1 << (f & 1);
+        float g = (flg[ta] & bit) ? 0.f : gf[q];
+        if (t + 1 < T && (flg[ta + O] & bit)) g += 0.5f * gf[q + O * 8];
+        if (t > 0 && (flg[ta - O] & bit)) g += 0.5f * gf[q - O * 8];
+        gm[q] = g;
+    }
+    __syncwarp();
+    // gather -> constrained tensor (`volatile` matching may pick an object twice), then constrain_zp
+    for (int q = lane; q < TO * 8; q += 32) {
+        const int ta = q >> 3, f = q & 7, t = ta / O, j = ta - t * O;
+        float g = 0.f;
+        for (int a = 0; a < O; ++a)
+            if (idx[t * O + a] == j) g += gm[(t * O + a) * 8 + f];
+        const float sc = f == 0 ? p.scale_hi - p.scale_lo
+                         : f == 1 ? p.ratio_hi - p.ratio_lo
+                         : f < 4 ? 2.f * p.pos_bound
+                         : f < 6 ? p.scale_var : p.pos_var;
+        const float sgm = sigmoidf_(__ldg(src + q));
+        g_zp[b * TO * 8 + q] = g * sc * sgm * (1.f - sgm);
+    }
 }
 
 static int sup_check(const SupParams& p, int64_t n) {
@@ -291,7 +297,8 @@ extern "C" int stove_sup_prepare_fwd(const stove_sup_cfg* cfg, int64_t n, const 
     STOVE_CHECK_ARG(!(p.match_app && !app), "appearance matching without appearances");
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(
+    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
+    STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<<<(unsigned)((n + SG_WARPS - 1) / SG_WARPS), 32 * SG_WARPS, smem, s>>>(
         p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
@@ -306,7 +313,8 @@ extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const 
     if (rc) return rc;
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_SUP_PREPARE_BWD, s, sup_prepare_bwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(
+    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
+    STOVE_KERNEL(K_SUP_PREPARE_BWD, s, sup_prepare_bwd_kernel<<<(unsigned)((n + SG_WARPS - 1) / SG_WARPS), 32 * SG_WARPS, smem, s>>>(
         p, n, zp, idx, flag, std_full, g_z_sup, g_z_full, g_std_full, g_zp));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;

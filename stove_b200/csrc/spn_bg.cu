@@ -140,25 +140,37 @@ __device__ __forceinline__ float bg_shift_exp(const float* L, float (&e)[G]) {
     return m;
 }
 
-// forward: combine chunks, products and root sum; thread = frame
+// forward: combine chunks, products and root sum.  CTA = 32 frames x NI/3 thread groups: the
+// chunk partials are summed by 384 threads (a frame-per-thread loop over 32 chunks x 36 values was
+// latency bound: 38 us for 1536 frames), then one thread per frame does the 3 products + root sum.
+#define BG_ROOT_FR 32
 template <int R, int G>
-__global__ void __launch_bounds__(128) spn1_fwd_root_kernel(
+__global__ void __launch_bounds__(BG_ROOT_FR * (R * 2 * G / 3)) spn1_fwd_root_kernel(
     int nchunks, int64_t N, int64_t ppad, int64_t npad, const float* __restrict__ part,
     const float* __restrict__ rlin, const float* __restrict__ rlog, float* __restrict__ leaf_val,
     float* __restrict__ out) {
     constexpr int NI = R * 2 * G;
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    __shared__ float Ls[NI][BG_ROOT_FR + 1];
+    const int fl = threadIdx.x % BG_ROOT_FR, grp = threadIdx.x / BG_ROOT_FR;
+    const int64_t n = (int64_t)blockIdx.x * BG_ROOT_FR + fl;
+    if (n < N) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int c = 0; c < nchunks; ++c) {          // fixed order: deterministic
+            const float* src = part + ((int64_t)c * NI + grp * 3) * ppad + n;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) acc[i] += src[(int64_t)i * ppad];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Ls[grp * 3 + i][fl] = acc[i];
+            leaf_val[(int64_t)(grp * 3 + i) * npad + n] = acc[i];
+        }
+    }
+    __syncthreads();
+    if (grp != 0 || n >= N) return;
     float L[NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) L[i] = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-        const float* src = part + (int64_t)c * NI * ppad + n;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) L[i] += src[(int64_t)i * ppad];
-    }
-#pragma unroll
-    for (int i = 0; i < NI; ++i) leaf_val[(int64_t)i * npad + n] = L[i];
+    for (int i = 0; i < NI; ++i) L[i] = Ls[i][fl];
     float vals[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -172,12 +184,21 @@ __global__ void __launch_bounds__(128) spn1_fwd_root_kernel(
             for (int i = 0; i < G; ++i) inner = fmaf(eA[i], __ldg(rlin + r * G * G + j * G + i), inner);
             U = fmaf(eB[j], inner, U);
         }
-        if (U > LIN_SUM_FLOOR)
+        if (U > LIN_SUM_FLOOR) {
             vals[r] = mA + mB + logf(U);
-        else
-            vals[r] = bg_slow_logsumexp(leaf_val + (int64_t)((r * 2) * G) * npad + n,
-                                        leaf_val + (int64_t)((r * 2 + 1) * G) * npad + n, npad, G,
-                                        rlog + r * G * G);
+        } else {
+            // exact log-domain value from the shared copy (leaf_val was written by other threads)
+            float M = -INFINITY;
+            for (int j = 0; j < G; ++j)
+                for (int i = 0; i < G; ++i)
+                    M = fmaxf(M, Ls[(r * 2) * G + i][fl] + Ls[(r * 2 + 1) * G + j][fl] + rlog[r * G * G + j * G + i]);
+            float acc = 0.f;
+            if (M > -INFINITY)
+                for (int j = 0; j < G; ++j)
+                    for (int i = 0; i < G; ++i)
+                        acc += expf(Ls[(r * 2) * G + i][fl] + Ls[(r * 2 + 1) * G + j][fl] + rlog[r * G * G + j * G + i] - M);
+            vals[r] = (M > -INFINITY) ? M + logf(acc) : M;
+        }
     }
     float M = vals[0];
 #pragma unroll
@@ -469,7 +490,7 @@ extern "C" int stove_spn1_fwd(const stove_spn1_struct* st, int64_t N, const floa
     else
         STOVE_KERNEL(K_SPN1_FWD_LEAF, s, spn1_fwd_leaf_kernel<3, 6, false><<<grid, BG_FR, 0, s>>>(st->D, st->side, N, ppad, x, marg, leaf, part));
     STOVE_LAUNCH_CHECK();
-    STOVE_KERNEL(K_SPN1_FWD_ROOT, s, spn1_fwd_root_kernel<3, 6><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(nch, N, ppad, npad, part, rlin, rlog,
+    STOVE_KERNEL(K_SPN1_FWD_ROOT, s, spn1_fwd_root_kernel<3, 6><<<(unsigned)((N + BG_ROOT_FR - 1) / BG_ROOT_FR), BG_ROOT_FR * 12, 0, s>>>(nch, N, ppad, npad, part, rlin, rlog,
                                                                         leaf_val, out));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
