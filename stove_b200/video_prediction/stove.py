@@ -249,11 +249,21 @@ class Stove(nn.Module):
         if not c.action_conditioned:
             rewards = torch.zeros(T - skip)
 
-        z_f = self.sup.sy_from_quotient(z_s.flatten(end_dim=2))
-        img_lik, sup_prop = self.sup.likelihood(x[:, skip:], z_f[..., :4], packed=packed_spn)
-        self.prop_dict.update(sup_prop)
-        z_sup_tmp = self.sup.sy_from_quotient(z_sup[:, 1:skip])
-        img_lik_sup, _ = self.sup.likelihood(x[:, 1:skip], z_sup_tmp.flatten(end_dim=2), packed=packed_spn)
+        # p(x_t | z_t) for t >= skip and p(x_t | z_sup_t) for 1 <= t < skip (stove.py:731-736) share one
+        # pass over the frames x[:, 1:]: a single glimpse/mask launch and one launch family per SPN
+        z_all = torch.cat([z_sup[:, 1:skip], z_s[..., :4]], 1)                      # (n, T-1, O, 4) [sx, sy/sx, ..]
+        z_all = self.sup.sy_from_quotient(z_all)
+        bg, patch, ov, extra = self.sup.likelihood_parts(x[:, 1:].flatten(end_dim=1), z_all.flatten(end_dim=1),
+                                                         packed=packed_spn)
+        n_sup = skip - 1
+        bg, patch, ov = bg.view(n, T - 1), patch.view(n, T - 1), ov.view(n, T - 1)
+        if (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0):
+            self.sup._log_parts(bg[:, n_sup:].flatten(), patch[:, n_sup:].flatten(), ov[:, n_sup:].flatten(),
+                                {k: v for k, v in extra.items()})
+            self.prop_dict.update(self.sup.prop_dict)
+        lik = bg + patch + ov
+        img_lik = lik[:, n_sup:].flatten()
+        img_lik_sup = lik[:, :n_sup].flatten()
         log_z_f = log_z_n.flatten()
         trans_lik = trans_n.flatten()
         elbo = trans_lik + img_lik - log_z_f

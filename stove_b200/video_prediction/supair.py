@@ -62,12 +62,12 @@ class Supair(nn.Module):
         return cache[k]
 
     # -- likelihood ----------------------------------------------------------------------
-    def likelihood(self, x, z_obj, packed=None):
-        """x (n, T, c, w, h), z_obj (n*T*O, 4) [sx, sy, x, y] -> (log p(x|z) (n*T,), prop_dict)."""
+    def likelihood_parts(self, x_img, z_img, packed=None):
+        """x_img (F, c, w, h), z_img (F, O, 4) [sx, sy, x, y] -> per-frame (bg, patch, overlap)
+        log-likelihood terms plus the intermediate tensors (one glimpse/mask launch, one launch
+        family per SPN)."""
         c = self.c
         pk_obj, pk_bg = packed if packed is not None else self.pack()
-        x_img = x.flatten(end_dim=1)
-        z_img = z_obj.view(-1, c.num_obj, 4)
         patches, marg_patch, marg_bg, overlap = ops.Scene.apply(
             x_img, z_img, c.patch_width, c.patch_height, self._align())
         img_flat, marg_flat = x_img.flatten(start_dim=1), marg_bg.flatten(start_dim=1)
@@ -80,24 +80,36 @@ class Supair(nn.Module):
             patches_loglik = self.obj_spn.forward_packed(pk_obj, patches_flat, marginalise_flat)[:, 0]
         else:
             patches_loglik = self.obj_spn.forward(patches_flat, marginalise_flat)[:, 0]
-        patches_loglik = (patches_loglik * z_obj[:, 0] * z_obj[:, 1]).view(-1, c.num_obj).sum(1)
+        z_flat = z_img.reshape(-1, 4)
+        patches_loglik = (patches_loglik * z_flat[:, 0] * z_flat[:, 1]).view(-1, c.num_obj).sum(1)
         # log Exponential(beta)(overlap) = log beta - beta * overlap
         overlap_log_liks = (math.log(c.overlap_beta) - c.overlap_beta * overlap).sum(1)
-        log_p_xz = bg_loglik + patches_loglik + overlap_log_liks
+        extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marginalise_flat,
+                     marginalise_bg=marg_bg)
+        return bg_loglik, patches_loglik, overlap_log_liks, extra
 
+    def _log_parts(self, bg_loglik, patches_loglik, overlap_log_liks, extra):
+        c = self.c
         if (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0):
             if c.debug:
                 self.prop_dict['bg'] = bg_loglik.mean().detach()
                 self.prop_dict['patch'] = patches_loglik.mean().detach()
                 self.prop_dict['overlap'] = overlap_log_liks.mean().detach()
             if c.debug and c.debug_extend_plots:
-                self.prop_dict['overlap_ratios'] = overlap.detach()
-                self.prop_dict['patches'] = patches.detach()
-                self.prop_dict['marginalise_flat'] = marginalise_flat.detach()
+                self.prop_dict['overlap_ratios'] = extra['overlap_ratios'].detach()
+                self.prop_dict['patches'] = extra['patches'].detach()
+                self.prop_dict['marginalise_flat'] = extra['marginalise_flat'].detach()
                 self.prop_dict['patches_loglik'] = patches_loglik.detach()
-                self.prop_dict['marginalise_bg'] = marg_bg.detach()
+                self.prop_dict['marginalise_bg'] = extra['marginalise_bg'].detach()
                 self.prop_dict['bg_loglik'] = bg_loglik.detach()
-        return log_p_xz, self.prop_dict
+
+    def likelihood(self, x, z_obj, packed=None):
+        """x (n, T, c, w, h), z_obj (n*T*O, 4) [sx, sy, x, y] -> (log p(x|z) (n*T,), prop_dict)
+        [supair.py:44-110]."""
+        x_img = x.flatten(end_dim=1)
+        bg, patch, ov, extra = self.likelihood_parts(x_img, z_obj.view(-1, self.c.num_obj, 4), packed)
+        self._log_parts(bg, patch, ov, extra)
+        return bg + patch + ov, self.prop_dict
 
     # -- z handling ----------------------------------------------------------------------
     def constrain_zp(self, zp):
