@@ -664,8 +664,12 @@ __device__ __forceinline__ void pair32(const float* __restrict__ W, const float*
 }
 
 // one dynamics step of one sequence, executed by one warp; `a` = this warp's activation slice
+// R1 / A1 / REL / ATT: where the second-level pair activations go (the rollout overwrites dead
+// buffers, the backward keeps everything)
 __device__ __forceinline__ void forward_step(const stove_gnn_cfg& c, const GnnLayout& L, const float* __restrict__ W,
-                                             float* a, const float* __restrict__ act_row, int lane) {
+                                             float* a, const float* __restrict__ act_row, int lane,
+                                             const int R1 = PA, const int A1 = PA + CL * PR, const int REL = PB,
+                                             const int ATT = PB + CL * PR) {
     const int nl = c.nonlin;
     if (c.action_dim > 0) {
         if (lane < O * 4) {
@@ -725,16 +729,16 @@ __device__ __forceinline__ void forward_step(const stove_gnn_cfg& c, const GnnLa
     }
     __syncwarp();
     // rel1 / att1 (64 -> 32 each): outputs overwrite the dead pair-input buffer
-    pair32<2 * CL, ACT_NL>(W + L.rel1_w, W + L.rel1_b, a + PB, a + PA, nullptr, nl, lane);
-    pair32<2 * CL, ACT_NL>(W + L.att1_w, W + L.att1_b, a + PB + 2 * CL * PR, a + PA + CL * PR, nullptr, nl, lane);
+    pair32<2 * CL, ACT_NL>(W + L.rel1_w, W + L.rel1_b, a + PB, a + R1, nullptr, nl, lane);
+    pair32<2 * CL, ACT_NL>(W + L.att1_w, W + L.att1_b, a + PB + 2 * CL * PR, a + A1, nullptr, nl, lane);
     __syncwarp();
     // rel2 (residual) -> PB rows 0..31 ; att2 (32 -> 1, exp) -> PB row 32
-    pair32<CL, ACT_NONE>(W + L.rel2_w, W + L.rel2_b, a + PA, a + PB, a + PA, nl, lane);
+    pair32<CL, ACT_NONE>(W + L.rel2_w, W + L.rel2_b, a + R1, a + REL, a + R1, nl, lane);
     if (lane < P) {
         float acc = W[L.att2_b];
 #pragma unroll 8
-        for (int k = 0; k < CL; ++k) acc = fmaf(a[PA + (CL + k) * PR + lane], W[L.att2_w + k], acc);
-        a[PB + CL * PR + lane] = expf(acc);
+        for (int k = 0; k < CL; ++k) acc = fmaf(a[A1 + k * PR + lane], W[L.att2_w + k], acc);
+        a[ATT + lane] = expf(acc);
     }
     __syncwarp();
     // d_i = self_i + sum_j rel_ij * mask_ij * att_ij (zero mask kept as a multiplication)
@@ -743,7 +747,7 @@ __device__ __forceinline__ void forward_step(const stove_gnn_cfg& c, const GnnLa
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < O; ++j)
-            acc += a[PB + lane * PR + i * O + j] * (i == j ? 0.f : 1.f) * a[PB + CL * PR + i * O + j];
+            acc += a[REL + lane * PR + i * O + j] * (i == j ? 0.f : 1.f) * a[ATT + i * O + j];
         a[D + lane * ORW + i] = a[SELFD + lane * ORW + i] + acc;
     }
     __syncwarp();
