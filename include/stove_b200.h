@@ -275,6 +275,37 @@ int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int6
                       const stove_dynstep_io* io, const float* weights, float* g_weights,
                       int first, int last, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * The WHOLE dynamics loop of Stove.stove_forward (stove.py:696-713) in one call: for every
+ * t in [skip, T) the fused step above, chained through z_t on the device.  For O = 3, cl = 32
+ * (every BASELINE config but multiball) this is one persistent warp-team kernel forward and
+ * three kernels backward (chain, weight gradients, slab reduction; csrc/dynloop.cu); any other
+ * shape runs the per-step kernels above, chained inside the library.
+ *   z_init [n][O][Z] (Z = cl/2 + 2); sup / sup_std [n][T][O][6]; eps [T-skip][n][O][Z];
+ *   actions [n][T][A] or NULL and app [n][T][O][app_dim] or NULL (step t reads index t-1)
+ *   -> z [n][S][O][Z], z_dyn / z_dyn_std [n][S][O][Z-2], z_std [n][S][O][Z] (optional),
+ *      logq / trans / reward [n][S]  (S = T - skip; reward may be NULL)
+ * Backward: g_z [n][S][O][Z], g_logq / g_trans / g_reward [n][S] (each may be NULL)
+ *   -> g_z_init [n][O][Z], g_sup / g_sup_std [n][T][O][6] (fully overwritten), g_weights
+ *      (overwritten).  `z` must hold the forward result.  Workspace: stove_dynloop_bwd_workspace.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t T, skip;
+    const float* z_init; const float* sup; const float* sup_std; const float* eps;
+    const float* actions; const float* app;
+    float* z; float* z_dyn; float* z_dyn_std; float* z_std;
+    float* logq; float* trans; float* reward;
+    const float* g_z; const float* g_logq; const float* g_trans; const float* g_reward;
+    float* g_z_init; float* g_sup; float* g_sup_std;
+} stove_dynloop_io;
+
+int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                      const stove_dynloop_io* io, const float* weights, void* stream);
+size_t stove_dynloop_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
+int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                      const stove_dynloop_io* io, const float* weights, float* g_weights,
+                      void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,15 @@ class DynstepIO(C.Structure):
                 ('g_sup', vp), ('g_sup_std', vp), ('g_sup_ss', i64)]
 
 
+class DynloopIO(C.Structure):
+    _fields_ = [('T', i32), ('skip', i32),
+                ('z_init', vp), ('sup', vp), ('sup_std', vp), ('eps', vp), ('actions', vp), ('app', vp),
+                ('z', vp), ('z_dyn', vp), ('z_dyn_std', vp), ('z_std', vp),
+                ('logq', vp), ('trans', vp), ('reward', vp),
+                ('g_z', vp), ('g_logq', vp), ('g_trans', vp), ('g_reward', vp),
+                ('g_z_init', vp), ('g_sup', vp), ('g_sup_std', vp)]
+
+
 P2, P1, PG, PS = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg), C.POINTER(SupCfg)
 
 # name -> (restype, argtypes); must list every symbol of include/stove_b200.h
@@ -94,6 +103,9 @@ SIGNATURES = {
     'stove_gnn_bwd': (C.c_int, [PG, i64] + [vp] * 9 + [vp]),
     'stove_dynstep_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp]),
     'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, C.c_int, vp, vp]),
+    'stove_dynloop_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp]),
+    'stove_dynloop_bwd_workspace': (sz, [PG, i64, C.c_int, C.c_int]),
+    'stove_dynloop_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

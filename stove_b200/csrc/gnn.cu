@@ -12,58 +12,11 @@
 // The backward kernel recomputes the forward on-chip (no activation tape in HBM), then walks
 // the layers in reverse; weight gradients go to a per-CTA slab in global memory (plain stores,
 // no atomics) that a second kernel reduces.
-#include <stdlib.h>
-#include "common.cuh"
+#include "gnn_common.cuh"
 
-enum { ACT_NONE = 0, ACT_NL = 1, ACT_TANH = 2, ACT_RELU = 3, ACT_SIGMOID = 4, ACT_EXP = 5 };
 
-struct GnnLayout {
-    int in_dim;
-    int act_w, act_b, enc_w, enc_b, self0_w, self0_b, self1_w, self1_b, ra0_w, ra0_b, rel1_w, rel1_b,
-        att1_w, att1_b, rel2_w, rel2_b, att2_w, att2_b, aff0_w, aff0_b, aff1_w, aff1_b, aff2_w, aff2_b,
-        out0_w, out0_b, out1_w, out1_b, rew00_w, rew00_b, rew02_w, rew02_b, rew10_w, rew10_b, rew12_w,
-        rew12_b, rew14_w, rew14_b;
-    int total;
-};
 
-static inline int pad4(int v) { return (v + 3) / 4 * 4; }
 
-static GnnLayout gnn_layout(const stove_gnn_cfg* c) {
-    GnnLayout L;
-    const int cl = c->cl, O = c->num_obj;
-    L.in_dim = cl / 2 + (c->action_dim > 0 ? 4 : 0) + c->app_dim;
-    int at = 0;
-    auto seg = [&](int& w, int& b, int K, int N) {
-        w = at; at += pad4(K * N);
-        b = at; at += pad4(N);
-    };
-    L.act_w = L.act_b = -1;
-    if (c->action_dim > 0) seg(L.act_w, L.act_b, c->action_dim, O * 4);
-    seg(L.enc_w, L.enc_b, L.in_dim, cl);
-    seg(L.self0_w, L.self0_b, cl, cl);
-    seg(L.self1_w, L.self1_b, cl, cl);
-    seg(L.ra0_w, L.ra0_b, 2 * cl + 1, 4 * cl);
-    seg(L.rel1_w, L.rel1_b, 2 * cl, cl);
-    seg(L.att1_w, L.att1_b, 2 * cl, cl);
-    seg(L.rel2_w, L.rel2_b, cl, cl);
-    seg(L.att2_w, L.att2_b, cl, 1);
-    seg(L.aff0_w, L.aff0_b, cl, cl);
-    seg(L.aff1_w, L.aff1_b, cl, cl);
-    seg(L.aff2_w, L.aff2_b, cl, cl);
-    seg(L.out0_w, L.out0_b, 2 * cl, cl);
-    seg(L.out1_w, L.out1_b, cl, cl);
-    L.rew00_w = L.rew00_b = L.rew02_w = L.rew02_b = L.rew10_w = L.rew10_b = L.rew12_w = L.rew12_b =
-        L.rew14_w = L.rew14_b = -1;
-    if (c->reward) {
-        seg(L.rew00_w, L.rew00_b, cl, cl);
-        seg(L.rew02_w, L.rew02_b, cl, cl);
-        seg(L.rew10_w, L.rew10_b, cl, cl / 2);
-        seg(L.rew12_w, L.rew12_b, cl / 2, cl / 4);
-        seg(L.rew14_w, L.rew14_b, cl / 4, 1);
-    }
-    L.total = at;
-    return L;
-}
 
 // row stride of a feature-major buffer: multiple of 4, congruent 4 mod 8 (see dense())
 __host__ __device__ static inline int pad_ld(int rows) {
@@ -141,27 +94,6 @@ __host__ __device__ static inline GnnBuf gnn_buffers(const stove_gnn_cfg& c, int
     return b;
 }
 
-__device__ __forceinline__ float apply_act(float v, int act, int nonlin) {
-    switch (act) {
-        case ACT_NL: return nonlin ? (v > 0.f ? v : expm1f(v)) : (v >= 0.f ? v : 0.01f * v);
-        case ACT_TANH: return tanhf(v);
-        case ACT_RELU: return fmaxf(v, 0.f);
-        case ACT_SIGMOID: return sigmoidf_(v);
-        case ACT_EXP: return expf(v);
-        default: return v;
-    }
-}
-// derivative of the activation expressed through its OUTPUT y
-__device__ __forceinline__ float act_grad(float y, int act, int nonlin) {
-    switch (act) {
-        case ACT_NL: return nonlin ? (y > 0.f ? 1.f : y + 1.f) : (y > 0.f ? 1.f : 0.01f);
-        case ACT_TANH: return 1.f - y * y;
-        case ACT_RELU: return y > 0.f ? 1.f : 0.f;
-        case ACT_SIGMOID: return y * (1.f - y);
-        case ACT_EXP: return y;
-        default: return 1.f;
-    }
-}
 
 // ------------------------------------------------------------------------------------
 // Dense layers on feature-major shared-memory activations ([feature][row], row stride ld).
@@ -597,260 +529,6 @@ __global__ void __launch_bounds__(512) gnn_rollout_kernel(
 }
 
 // ------------------------------------------------------------------------------------
-// Warp-per-sequence rollout (O = 3, cl = 32): the fast path of Stove.rollout.
-//
-// ncu on the CTA-wide rollout kernel showed 19 % of cycles in barrier stalls, 46 % issue
-// utilisation and 2x more FFMA slots than useful MACs (idle lanes, padded rows): a single
-// sequence has only 9 pair rows and 3 object rows, so spreading one layer over 512 threads
-// buys little and costs a CTA barrier per layer.  Here one WARP owns one sequence for all
-// time steps: its activations (16 KB) live in its private slice of shared memory, layers are
-// separated by __syncwarp only, and every lane owns output features for ALL rows of the layer
-// (rel0|att0: 4 features x 9 rows = 36 FFMA per 7 shared loads).  Weights (103 KB) are staged
-// once per CTA and shared by its 7 warps.  Summation order per output is unchanged (bias, then
-// k ascending), so results are bitwise identical to the CTA-wide kernel.
-// ------------------------------------------------------------------------------------
-namespace warpk {
-constexpr int O = 3, P = 9, PR = 12, ORW = 4, CL = 32, HALF = 16, ZD = 18;
-constexpr int IN_MAX = 24;
-// per-warp buffer offsets (floats)
-constexpr int SIN = 0, S = SIN + IN_MAX * ORW, H = S + CL * ORW, SELFD = H + CL * ORW, D = SELFD + CL * ORW,
-              F1 = D + CL * ORW, F2 = F1 + CL * ORW, CAT = F2 + CL * ORW, O1 = CAT + 2 * CL * ORW,
-              OUT = O1 + CL * ORW, RH0 = OUT + CL * ORW, RH1 = RH0 + CL * ORW, SMALL = RH1 + CL * ORW,
-              PA = SMALL + 64, PB = PA + 65 * PR + 4 /* keep 16-byte alignment */, TOTAL = PB + 128 * PR;
-static_assert(PA % 4 == 0 && PB % 4 == 0 && TOTAL % 4 == 0, "alignment");
-
-// object-row layer: out[n][r] = act(b[n] + sum_k W[k][n] in[k][r]) (+ res), n = lane, r < 3
-template <int ACT>
-__device__ __forceinline__ void obj32(const float* __restrict__ W, const float* __restrict__ bias, int K,
-                                      const float* in, float* out, const float* res, int nl, int lane) {
-    float a0 = bias[lane], a1 = a0, a2 = a0;
-    const float4* in4 = reinterpret_cast<const float4*>(in);
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float w = W[k * CL + lane];
-        const float4 x = in4[k];
-        a0 = fmaf(x.x, w, a0);
-        a1 = fmaf(x.y, w, a1);
-        a2 = fmaf(x.z, w, a2);
-    }
-    a0 = apply_act(a0, ACT, nl); a1 = apply_act(a1, ACT, nl); a2 = apply_act(a2, ACT, nl);
-    if (res) { a0 += res[lane * ORW]; a1 += res[lane * ORW + 1]; a2 += res[lane * ORW + 2]; }
-    out[lane * ORW] = a0; out[lane * ORW + 1] = a1; out[lane * ORW + 2] = a2;
-}
-
-// pair-row layer with 32 outputs: n = lane, 9 rows
-template <int K, int ACT>
-__device__ __forceinline__ void pair32(const float* __restrict__ W, const float* __restrict__ bias, const float* in,
-                                       float* out, const float* res, int nl, int lane) {
-    float acc[P];
-    const float bv = bias[lane];
-#pragma unroll
-    for (int r = 0; r < P; ++r) acc[r] = bv;
-    const float4* in4 = reinterpret_cast<const float4*>(in);
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        const float w = W[k * CL + lane];
-        const float4 x0 = in4[k * 3], x1 = in4[k * 3 + 1], x2 = in4[k * 3 + 2];
-        acc[0] = fmaf(x0.x, w, acc[0]); acc[1] = fmaf(x0.y, w, acc[1]); acc[2] = fmaf(x0.z, w, acc[2]);
-        acc[3] = fmaf(x0.w, w, acc[3]); acc[4] = fmaf(x1.x, w, acc[4]); acc[5] = fmaf(x1.y, w, acc[5]);
-        acc[6] = fmaf(x1.z, w, acc[6]); acc[7] = fmaf(x1.w, w, acc[7]); acc[8] = fmaf(x2.x, w, acc[8]);
-    }
-#pragma unroll
-    for (int r = 0; r < P; ++r) {
-        float y = apply_act(acc[r], ACT, nl);
-        if (res) y += res[lane * PR + r];
-        out[lane * PR + r] = y;
-    }
-}
-
-// one dynamics step of one sequence, executed by one warp; `a` = this warp's activation slice
-// R1 / A1 / REL / ATT: where the second-level pair activations go (the rollout overwrites dead
-// buffers, the backward keeps everything)
-__device__ __forceinline__ void forward_step(const stove_gnn_cfg& c, const GnnLayout& L, const float* __restrict__ W,
-                                             float* a, const float* __restrict__ act_row, int lane,
-                                             const int R1 = PA, const int A1 = PA + CL * PR, const int REL = PB,
-                                             const int ATT = PB + CL * PR) {
-    const int nl = c.nonlin;
-    if (c.action_dim > 0) {
-        if (lane < O * 4) {
-            float acc = W[L.act_b + lane];
-            for (int k = 0; k < c.action_dim; ++k) acc = fmaf(__ldg(act_row + k), W[L.act_w + k * O * 4 + lane], acc);
-            a[SIN + (HALF + (lane & 3)) * ORW + (lane >> 2)] = acc;
-        }
-        __syncwarp();
-    }
-    obj32<ACT_NONE>(W + L.enc_w, W + L.enc_b, L.in_dim, a + SIN, a + S, nullptr, nl, lane);
-    __syncwarp();
-    if (lane < c.lim_enc) {
-#pragma unroll
-        for (int r = 0; r < O; ++r) a[S + lane * ORW + r] = a[SIN + lane * ORW + r];
-    }
-    __syncwarp();
-    // pair inputs [s_i, s_j, |p_i - p_j|^2], row p = i*3 + j
-    for (int e = lane; e < (2 * CL + 1) * P; e += 32) {
-        const int k = e / P, pp = e - k * P, i = pp / O, j = pp - i * O;
-        float v;
-        if (k < CL) v = a[S + k * ORW + i];
-        else if (k < 2 * CL) v = a[S + (k - CL) * ORW + j];
-        else {
-            const float dx = a[S + i] - a[S + j], dy = a[S + ORW + i] - a[S + ORW + j];
-            v = dx * dx + dy * dy;
-        }
-        a[PA + k * PR + pp] = v;
-    }
-    obj32<ACT_NL>(W + L.self0_w, W + L.self0_b, CL, a + S, a + H, nullptr, nl, lane);
-    __syncwarp();
-    obj32<ACT_NONE>(W + L.self1_w, W + L.self1_b, CL, a + H, a + SELFD, a + H, nl, lane);
-    {   // rel0|att0: 65 -> 128, lane owns features lane + 32 e
-        float acc[4][P];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float bv = W[L.ra0_b + lane + 32 * e];
-#pragma unroll
-            for (int r = 0; r < P; ++r) acc[e][r] = bv;
-        }
-        const float4* in4 = reinterpret_cast<const float4*>(a + PA);
-        const float* w0 = W + L.ra0_w + lane;
-#pragma unroll 2
-        for (int k = 0; k < 2 * CL + 1; ++k) {
-            const float4 x0 = in4[k * 3], x1 = in4[k * 3 + 1], x2 = in4[k * 3 + 2];
-            const float xr[P] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float w = w0[k * 4 * CL + 32 * e];
-#pragma unroll
-                for (int r = 0; r < P; ++r) acc[e][r] = fmaf(xr[r], w, acc[e][r]);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-#pragma unroll
-            for (int r = 0; r < P; ++r) a[PB + (lane + 32 * e) * PR + r] = apply_act(acc[e][r], ACT_NL, nl);
-    }
-    __syncwarp();
-    // rel1 / att1 (64 -> 32 each): outputs overwrite the dead pair-input buffer
-    pair32<2 * CL, ACT_NL>(W + L.rel1_w, W + L.rel1_b, a + PB, a + R1, nullptr, nl, lane);
-    pair32<2 * CL, ACT_NL>(W + L.att1_w, W + L.att1_b, a + PB + 2 * CL * PR, a + A1, nullptr, nl, lane);
-    __syncwarp();
-    // rel2 (residual) -> PB rows 0..31 ; att2 (32 -> 1, exp) -> PB row 32
-    pair32<CL, ACT_NONE>(W + L.rel2_w, W + L.rel2_b, a + R1, a + REL, a + R1, nl, lane);
-    if (lane < P) {
-        float acc = W[L.att2_b];
-#pragma unroll 8
-        for (int k = 0; k < CL; ++k) acc = fmaf(a[A1 + k * PR + lane], W[L.att2_w + k], acc);
-        a[ATT + lane] = expf(acc);
-    }
-    __syncwarp();
-    // d_i = self_i + sum_j rel_ij * mask_ij * att_ij (zero mask kept as a multiplication)
-#pragma unroll
-    for (int i = 0; i < O; ++i) {
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < O; ++j)
-            acc += a[REL + lane * PR + i * O + j] * (i == j ? 0.f : 1.f) * a[ATT + i * O + j];
-        a[D + lane * ORW + i] = a[SELFD + lane * ORW + i] + acc;
-    }
-    __syncwarp();
-    obj32<ACT_TANH>(W + L.aff0_w, W + L.aff0_b, CL, a + D, a + F1, nullptr, nl, lane);
-    if (c.reward) obj32<ACT_RELU>(W + L.rew00_w, W + L.rew00_b, CL, a + D, a + RH0, nullptr, nl, lane);
-    __syncwarp();
-    obj32<ACT_TANH>(W + L.aff1_w, W + L.aff1_b, CL, a + F1, a + F2, a + F1, nl, lane);
-    if (c.reward) obj32<ACT_NONE>(W + L.rew02_w, W + L.rew02_b, CL, a + RH0, a + RH1, nullptr, nl, lane);
-    __syncwarp();
-    obj32<ACT_NONE>(W + L.aff2_w, W + L.aff2_b, CL, a + F2, a + CAT, nullptr, nl, lane);
-#pragma unroll
-    for (int r = 0; r < O; ++r) a[CAT + (CL + lane) * ORW + r] = a[S + lane * ORW + r];
-    if (c.reward) a[SMALL + lane] = a[RH1 + lane * ORW] + a[RH1 + lane * ORW + 1] + a[RH1 + lane * ORW + 2];
-    __syncwarp();
-    obj32<ACT_TANH>(W + L.out0_w, W + L.out0_b, 2 * CL, a + CAT, a + O1, nullptr, nl, lane);
-    if (c.reward && lane < CL / 2) {
-        float acc = W[L.rew10_b + lane];
-        for (int k = 0; k < CL; ++k) acc = fmaf(a[SMALL + k], W[L.rew10_w + k * (CL / 2) + lane], acc);
-        a[SMALL + 32 + lane] = fmaxf(acc, 0.f);
-    }
-    __syncwarp();
-    obj32<ACT_NONE>(W + L.out1_w, W + L.out1_b, CL, a + O1, a + OUT, a + O1, nl, lane);
-    if (c.reward && lane < CL / 4) {
-        float acc = W[L.rew12_b + lane];
-        for (int k = 0; k < CL / 2; ++k) acc = fmaf(a[SMALL + 32 + k], W[L.rew12_w + k * (CL / 4) + lane], acc);
-        a[SMALL + 48 + lane] = fmaxf(acc, 0.f);
-    }
-    __syncwarp();
-    if (c.reward && lane == 0) {
-        float acc = W[L.rew14_b];
-        for (int k = 0; k < CL / 4; ++k) acc = fmaf(a[SMALL + 48 + k], W[L.rew14_w + k], acc);
-        a[SMALL + 56] = sigmoidf_(acc);
-    }
-    __syncwarp();
-}
-}  // namespace warpk
-
-__global__ void __launch_bounds__(224, 1) gnn_rollout_warp_kernel(
-    stove_gnn_cfg c, GnnLayout L, int64_t n, int num, const float* __restrict__ z_last,
-    const float* __restrict__ actions, int action_len, const float* __restrict__ app,
-    const float* __restrict__ weights, const float* __restrict__ noise, float pos_var, float vel_std,
-    float latent_std, float* __restrict__ z_out, float* __restrict__ std_out, float* __restrict__ logq_out,
-    float* __restrict__ rewards) {
-    using namespace warpk;
-    extern __shared__ __align__(16) float smem[];
-    float* Ws = smem;
-    stage_weights(weights, Ws, L.total);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    float* a = smem + L.total + warp * TOTAL;
-    for (int i = lane; i < TOTAL; i += 32) a[i] = 0.f;
-    __syncthreads();
-    for (int64_t sq = (int64_t)blockIdx.x * wpc + warp; sq < n; sq += (int64_t)gridDim.x * wpc) {
-        // state [x, y, vx, vy, latent x12] of the 3 objects, appearances
-        for (int e = lane; e < O * HALF; e += 32) {
-            const int o = e / HALF, k = e - o * HALF;
-            a[SIN + k * ORW + o] = __ldg(z_last + (sq * O + o) * ZD + 2 + k);
-        }
-        if (c.app_dim > 0) {
-            const int a0 = HALF + (c.action_dim > 0 ? 4 : 0);
-            for (int e = lane; e < O * c.app_dim; e += 32) {
-                const int o = e / c.app_dim, k = e - o * c.app_dim;
-                a[SIN + (a0 + k) * ORW + o] = __ldg(app + (sq * O + o) * c.app_dim + k);
-            }
-        }
-        __syncwarp();
-        for (int t = 0; t < num; ++t) {
-            const float* arow = actions ? actions + (sq * action_len + (t % action_len)) * c.action_dim : nullptr;
-            forward_step(c, L, Ws, a, arow, lane);
-            // constrain (dynamics.py:147-179), integrate positions, optional sampling; the new
-            // state is parked in F1 so that all lanes still read the old positions
-            for (int e = lane; e < O * HALF; e += 32) {
-                const int o = e / HALF, k = e - o * HALF;
-                float m = 2.f * sigmoidf_(a[OUT + k * ORW + o]) - 1.f;
-                if (k < 2) m += a[SIN + k * ORW + o];
-                float val = m;
-                const int64_t o16 = ((sq * num + t) * O + o) * HALF + k;
-                if (noise || std_out) {
-                    const float sd = (k < 2 ? pos_var : (k < 4 ? vel_std : latent_std)) *
-                                     sigmoidf_(a[OUT + (HALF + k) * ORW + o]);
-                    if (std_out) std_out[o16] = sd;
-                    if (noise) {
-                        const float e_ = __ldg(noise + o16);
-                        val = m + sd * e_;
-                        if (logq_out) logq_out[o16] = -0.5f * e_ * e_ - logf(sd) - HALF_LOG_2PI;
-                    }
-                }
-                a[F1 + k * ORW + o] = val;
-                const int64_t oz = ((sq * num + t) * O + o) * ZD;
-                z_out[oz + 2 + k] = val;
-                if (k < 2) z_out[oz + k] = __ldg(z_last + (sq * O + o) * ZD + k);
-            }
-            if (c.reward && rewards && lane == 0) rewards[sq * num + t] = a[SMALL + 56];
-            __syncwarp();
-            for (int e = lane; e < O * HALF; e += 32) {
-                const int o = e / HALF, k = e - o * HALF;
-                a[SIN + k * ORW + o] = a[F1 + k * ORW + o];
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
 // Backward core: expects the forward activations (gnn_forward_core) and the upstream gradient
 // sm[b.g_out] in shared memory; leaves d/d(s_in) in sm[b.g_sin] (first cl/2 features, raw
 // pass-through already added) and writes this CTA's weight gradients into `slab`.
@@ -1122,10 +800,6 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
 // backward kernel.  All tensors are addressed as base + sequence * stride so the caller can
 // pass time slices of (n, T, ...) tensors without copies.
 // ------------------------------------------------------------------------------------
-struct FuseCfg {
-    float scale[3];          // pos_var, 0.04, debug_latent_q_std  (constrain_z_dyn)
-    float trans_std[32];     // transition_lik_std per state feature (cl/2 used)
-};
 
 __device__ __forceinline__ void load_inputs_strided(const stove_gnn_cfg& c, const GnnBuf& b, float* sm, int nseq,
                                                     const float* __restrict__ z_prev, int64_t zss,
@@ -1327,6 +1001,11 @@ __global__ void __launch_bounds__(256) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLa
     }
 }
 
+int stove_team_rollout(const stove_gnn_cfg* cfg, const GnnLayout& L, int64_t n, int num, const float* z_last,
+                       const float* actions, int action_len, const float* app, const float* weights,
+                       const float* noise, float pos_var, float vel_std, float latent_std, float* z_out,
+                       float* std_out, float* logq_out, float* rewards, cudaStream_t st);
+
 // g_w[i] (=, +=) sum_b slabs[b][i]
 __global__ void gnn_reduce_slabs_acc_kernel(const float* __restrict__ slabs, int nslab, int total,
                                             float* __restrict__ g_w, int accumulate) {
@@ -1350,21 +1029,9 @@ __global__ void gnn_reduce_slabs_kernel(const float* __restrict__ slabs, int nsl
 // ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
-static int gnn_check(const stove_gnn_cfg* c) {
-    STOVE_CHECK_ARG(c, "null cfg");
-    STOVE_CHECK_ARG(c->num_obj > 0 && c->num_obj <= 16, "num_obj out of range");
-    STOVE_CHECK_ARG(c->cl >= 8 && c->cl % 8 == 0 && c->cl <= 64, "cl must be a multiple of 8 in [8, 64]");
-    STOVE_CHECK_ARG(c->action_dim >= 0 && c->app_dim >= 0 && c->lim_enc >= 0 && c->lim_enc <= c->cl / 2, "bad cfg");
-    return STOVE_OK;
-}
 
-static const size_t kMaxSmem = 227 * 1024;
 
 // largest number of sequences per CTA that fits (optionally with staged weights), <= want
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
 
 static int pick_seq(const stove_gnn_cfg* c, const GnnLayout& L, bool bwd, bool stage, int want) {
     // tuning override (sequences per CTA): STOVE_GNN_SEQ_FWD / STOVE_GNN_SEQ_BWD
@@ -1484,12 +1151,6 @@ extern "C" int stove_gnn_bwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     return STOVE_OK;
 }
 
-static FuseCfg make_fuse(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fc) {
-    FuseCfg f;
-    f.scale[0] = fc->pos_var; f.scale[1] = fc->vel_std; f.scale[2] = fc->latent_std;
-    for (int i = 0; i < 32; ++i) f.trans_std[i] = (i < cfg->cl / 2) ? fc->trans_std[i] : 1.f;
-    return f;
-}
 
 extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                                  const stove_dynstep_io* io, const float* weights, void* stream) {
@@ -1563,20 +1224,10 @@ extern "C" int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, c
     STOVE_CHECK_ARG(!(logq_out && !noise), "logq_out requires noise");
     if (n == 0 || num == 0) return STOVE_OK;
     GnnLayout L = gnn_layout(cfg);
-    if (cfg->num_obj == 3 && cfg->cl == 32 && L.in_dim <= warpk::IN_MAX && !env_int("STOVE_ROLLOUT_CTA", 0)) {
-        // fast path: one warp per sequence, 7 warps (sequences) per SM
-        const int wpc = 7;
-        const size_t smem = sizeof(float) * ((size_t)L.total + (size_t)wpc * warpk::TOTAL);
-        if (smem <= kMaxSmem) {
-            STOVE_CUDA(cudaFuncSetAttribute(gnn_rollout_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int64_t groups = (n + wpc - 1) / wpc;
-            const int ctas = (int)(groups < 148 ? groups : 148);
-            STOVE_KERNEL(K_GNN_ROLLOUT, (cudaStream_t)stream, gnn_rollout_warp_kernel<<<ctas, 32 * wpc, smem, (cudaStream_t)stream>>>(
-                *cfg, L, n, num, z_last, actions, action_len, app, weights, noise, pos_var, vel_std, latent_std,
-                z_out, std_out, logq_out, rewards));
-            STOVE_LAUNCH_CHECK();
-            return STOVE_OK;
-        }
+    {   // fast path: warp teams (dynloop.cu); returns 1 when the shape is not covered
+        const int frc = stove_team_rollout(cfg, L, n, num, z_last, actions, action_len, app, weights, noise, pos_var,
+                                           vel_std, latent_std, z_out, std_out, logq_out, rewards, (cudaStream_t)stream);
+        if (frc != 1) return frc;
     }
     // one persistent CTA per SM: spread the sequences evenly over 148 CTAs
     int want = (int)((n + 147) / 148);

@@ -337,22 +337,23 @@ class GnnStep(torch.autograd.Function):
         return g_s, None, None, g_w, None
 
 
-def _sl(t, index):
-    """(pointer, sequence stride in floats) of the time slice t[:, index] of a contiguous tensor."""
-    if t is None:
-        return None, 0
-    v = t[:, index]
-    return v.data_ptr(), t.stride(0)
-
-
 class DynamicsLoop(torch.autograd.Function):
-    """The whole dynamics loop of Stove.stove_forward (stove.py:696-713): for every t >= skip one fused
-    kernel (GNN + constrain + fusion with SuPAIR + sample + log q + transition lik), chained through
-    z_t; the backward runs the steps in reverse and keeps the state gradient on the device.
+    """The whole dynamics loop of Stove.stove_forward (stove.py:696-713) in one library call: for
+    every t >= skip the fused step (GNN + constrain + fusion with SuPAIR + sample + log q +
+    transition lik), chained through z_t on the device -- one persistent kernel forward, three
+    kernels backward (csrc/dynloop.cu).
 
     z_init (n, O, Z); sup, sup_std (n, T, O, 6); eps (S, n, O, Z); actions (n, T, A) | None;
     app (n, T, O, 3) | None; weights flat.  Returns z (n, S, O, Z), z_dyn, z_dyn_std (n, S, O, Z-2),
     z_std (n, S, O, Z), logq (n, S), trans (n, S), rewards (n, S, 1)."""
+
+    @staticmethod
+    def _io(T, skip, z_init, sup, sup_std, eps, actions, app):
+        io = N.DynloopIO()
+        io.T, io.skip = T, skip
+        io.z_init, io.sup, io.sup_std, io.eps = N.ptr(z_init), N.ptr(sup), N.ptr(sup_std), N.ptr(eps)
+        io.actions, io.app = N.ptr(actions), N.ptr(app)
+        return io
 
     @staticmethod
     def forward(ctx, z_init, sup, sup_std, eps, actions, app, weights, cfg, fuse, skip):
@@ -370,27 +371,10 @@ class DynamicsLoop(torch.autograd.Function):
         logq = torch.empty(n, S, device=dev, dtype=dt)
         trans = torch.empty(n, S, device=dev, dtype=dt)
         rewards = torch.empty(n, S, 1, device=dev, dtype=dt) if cfg.reward else None
-        lib, st = N.lib(), N.stream()
-        for k in range(S):
-            t = skip + k
-            io = N.DynstepIO()
-            if k == 0:
-                io.z_prev, io.z_prev_ss = z_init.data_ptr(), O * Z
-            else:
-                io.z_prev, io.z_prev_ss = _sl(z, k - 1)
-            io.sup, io.sup_ss = _sl(sup, t)
-            io.sup_std = sup_std[:, t].data_ptr()
-            io.eps, io.eps_ss = eps[k].data_ptr(), O * Z
-            io.actions, io.act_ss = _sl(actions, t - 1)
-            io.app, io.app_ss = _sl(app, t - 1)
-            io.z_out, io.z_out_ss = _sl(z, k)
-            io.z_dyn, io.zdyn_ss = _sl(z_dyn, k)
-            io.z_dyn_std = z_dyn_std[:, k].data_ptr()
-            io.z_std, io.z_std_ss = _sl(z_std, k)
-            io.logq, io.sc_ss = logq[:, k].data_ptr(), S
-            io.trans = trans[:, k].data_ptr()
-            io.reward = rewards[:, k].data_ptr() if rewards is not None else None
-            N.check(lib.stove_dynstep_fwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), st))
+        io = DynamicsLoop._io(T, skip, z_init, sup, sup_std, eps, actions, app)
+        io.z, io.z_dyn, io.z_dyn_std, io.z_std = N.ptr(z), N.ptr(z_dyn), N.ptr(z_dyn_std), N.ptr(z_std)
+        io.logq, io.trans, io.reward = N.ptr(logq), N.ptr(trans), N.ptr(rewards)
+        N.check(N.lib().stove_dynloop_fwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.stream()))
         ctx.save_for_backward(z_init, sup, sup_std, eps, actions, app, weights, z)
         ctx.meta = (cfg, fuse, skip)
         ctx.mark_non_differentiable(z_dyn, z_dyn_std, z_std)
@@ -405,42 +389,22 @@ class DynamicsLoop(torch.autograd.Function):
         cfg, fuse, skip = ctx.meta
         n, O, Z = z_init.shape
         T = sup.shape[1]
-        S = T - skip
         dev, dt = z_init.device, z_init.dtype
         g_z, g_logq, g_trans = _c(g_z), _c(g_logq), _c(g_trans)
         g_rewards = _c(g_rewards) if cfg.reward else None
-        g_sup = torch.zeros_like(sup)
-        g_sup_std = torch.zeros_like(sup_std)
+        g_z_init = torch.empty_like(z_init)
+        g_sup = torch.empty_like(sup)
+        g_sup_std = torch.empty_like(sup_std)
         g_w = torch.empty_like(weights)
-        carry = [torch.empty(n, O, Z, device=dev, dtype=dt) for _ in range(2)]
-        ws = torch.empty(max(N.lib().stove_gnn_bwd_workspace(C.byref(cfg), n), 4) // 4, device=dev, dtype=torch.float32)
-        lib, st = N.lib(), N.stream()
-        for k in reversed(range(S)):
-            t = skip + k
-            io = N.DynstepIO()
-            if k == 0:
-                io.z_prev, io.z_prev_ss = z_init.data_ptr(), O * Z
-            else:
-                io.z_prev, io.z_prev_ss = _sl(z, k - 1)
-            io.sup, io.sup_ss = _sl(sup, t)
-            io.sup_std = sup_std[:, t].data_ptr()
-            io.eps, io.eps_ss = eps[k].data_ptr(), O * Z
-            io.actions, io.act_ss = _sl(actions, t - 1)
-            io.app, io.app_ss = _sl(app, t - 1)
-            if g_z is not None:
-                io.g_z_a, io.g_z_a_ss = _sl(g_z, k)
-            if k < S - 1:
-                io.g_z_b, io.g_z_b_ss = carry[(k + 1) % 2].data_ptr(), O * Z
-            io.g_sc_ss = S
-            io.g_logq = g_logq[:, k].data_ptr() if g_logq is not None else None
-            io.g_trans = g_trans[:, k].data_ptr() if g_trans is not None else None
-            io.g_reward = g_rewards[:, k].data_ptr() if g_rewards is not None else None
-            io.g_z_prev, io.g_z_prev_ss = carry[k % 2].data_ptr(), O * Z
-            io.g_sup, io.g_sup_ss = _sl(g_sup, t)
-            io.g_sup_std = g_sup_std[:, t].data_ptr()
-            N.check(lib.stove_dynstep_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
-                                          1 if k == S - 1 else 0, 1 if k == 0 else 0, N.ptr(ws), st))
-        return carry[0], g_sup, g_sup_std, None, None, None, g_w, None, None, None
+        nbytes = N.lib().stove_dynloop_bwd_workspace(C.byref(cfg), n, T, skip)
+        ws = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
+        io = DynamicsLoop._io(T, skip, z_init, sup, sup_std, eps, actions, app)
+        io.z = N.ptr(z)
+        io.g_z, io.g_logq, io.g_trans, io.g_reward = N.ptr(g_z), N.ptr(g_logq), N.ptr(g_trans), N.ptr(g_rewards)
+        io.g_z_init, io.g_sup, io.g_sup_std = N.ptr(g_z_init), N.ptr(g_sup), N.ptr(g_sup_std)
+        N.check(N.lib().stove_dynloop_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
+                                          N.ptr(ws), N.stream()))
+        return g_z_init, g_sup, g_sup_std, None, None, None, g_w, None, None, None
 
 
 def gnn_rollout(cfg, z_last, num, weights, actions=None, app=None, noise=None, pos_var=0.3, vel_std=0.04,
