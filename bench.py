@@ -291,14 +291,25 @@ def run_b200(args):
         avg_ms = sum(per[top]) / len(per[top])
         units = kernel_algorithmic_bytes(top, BATCH)
         achieved = units / (avg_ms * 1e-3) / 1e9 if units else None
+        flops = kernel_flops(top, BATCH)
+        sm_mhz = clock_summary.get('sm_max_mhz') or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        fp32 = None
+        if flops:
+            fp32 = {'achieved_tflops': flops / (avg_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
+                    'frac': flops / (avg_ms * 1e-3) / 1e12 / fp32_peak,
+                    'peak_source': '148 SMs x 128 FP32 lanes x 2 x max SM clock'}
         roofline = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                    'frac': (achieved / peak) if achieved else None, 'traffic': measured_traffic(top),
+                    'fp32': fp32,
                     'avg_launch_ms': avg_ms, 'launches_per_step': launches_top,
                     'algorithmic_bytes_per_launch': units, 'peak_source': peak_src,
                     'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                     'native_share_of_step': sum(share.values()) / (ms / args.steps),
                     'note': 'all hot-path kernels are FP32-issue/latency bound, not HBM bound (DESIGN.md); '
-                            'the HBM fraction is reported because the contract asks for it'}
+                            'the HBM fraction is reported because the contract asks for it, `fp32` is the '
+                            'bound that applies; `traffic` = DRAM bytes of one launch from the committed ncu '
+                            'capture (profiles/ncu_traffic.json)'}
 
     # ---- rollouts (no collective: sequences shard over ranks) ----------------------------------
     extra = {}
@@ -382,9 +393,10 @@ def run_b200(args):
 def kernel_algorithmic_bytes(kernel, batch):
     """Minimum HBM traffic of ONE launch of `kernel` in the config-1 training step (DESIGN.md
     section 4): bytes that must be read/written if every intermediate stayed on chip."""
-    frames = batch * (T - 2)              # the larger of the two likelihood calls per step
+    frames = batch * (T - 1)              # one likelihood pass over x[:, 1:]
     patches = frames * O
     D_bg, D_obj = RES * RES, 100
+    S, Z, W_DYN = T - 2, 18, 22660        # dynamics steps, state width, GNN weight floats (plain config)
     table = {
         'spn1_fwd_leaf': frames * D_bg * 4 * 2,                   # frame + mask in, 36 floats out (negligible)
         'spn1_bwd_input': frames * D_bg * 4 * 3,                  # frame + mask in, mask gradient out
@@ -396,11 +408,33 @@ def kernel_algorithmic_bytes(kernel, batch):
         'spn2_bwd_sumparam': patches * (12 * 30 + 6 * 21) * 4,
         'scene_fwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
         'scene_bwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
-        'gnn_fwd': batch * O * (16 + 32) * 4,
-        'gnn_bwd': batch * O * (16 + 32 + 16) * 4,
+        # z_init, sup, sup_std, eps in; z, z_std, z_dyn, z_dyn_std, logq, trans out; weights once
+        'dynloop_fwd': 4 * (batch * O * Z + batch * S * O * (12 + Z) + batch * S * (O * (2 * Z + 2 * (Z - 2)) + 2) + W_DYN),
+        # z, sup, sup_std, eps, g_z, g_logq, g_trans in; g_sup, g_sup_std, g_z_init out; weights once
+        'dynloop_bwd': 4 * (batch * S * (O * (Z + 12 + Z + Z) + 2) + batch * S * O * 12 + batch * O * Z + W_DYN),
+        'dynloop_wgrad': 4 * (batch * S * 7824 + 148 * W_DYN),     # its input IS the per-step record stream
         'bw_transform': batch * T * D_bg * 4 * 4,
     }
     return table.get(kernel)
+
+
+def kernel_flops(kernel, batch):
+    """Useful fp32 FLOPs of one launch (2 x FMA count of the factorised GNN)."""
+    S = T - 2
+    step_fwd = 2 * 98208                   # one dynamics step of one sequence, O = 3, cl = 32
+    table = {'dynloop_fwd': batch * S * step_fwd, 'dynloop_bwd': batch * S * 2 * step_fwd,
+             'dynloop_wgrad': batch * S * step_fwd}
+    return table.get(kernel)
+
+
+def measured_traffic(kernel):
+    """DRAM bytes of one launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get(kernel)
+    return (t['dram_read_bytes'] + t['dram_write_bytes']) if t else None
 
 
 def main():

@@ -95,14 +95,36 @@ __device__ __forceinline__ void store3(float* dst, float a, float b, float c) {
     *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, 0.f);
 }
 
+// weights: flat [K][N] in global memory -> row stride ld in shared memory.  4-byte cp.async: no
+// register staging and every copy of the CTA is in flight at once (this runs once per launch, on
+// the critical path of a kernel that only lives for a few time steps).
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void stage_weights(const StageTable& st, const float* __restrict__ weights, float* Ws) {
     for (int s = 0; s < st.count; ++s) {
         const Seg sg = st.seg[s];
-        for (int idx = threadIdx.x; idx < sg.K * sg.N; idx += blockDim.x) {
-            const int k = idx / sg.N, n = idx - k * sg.N;
-            Ws[sg.dst + k * sg.ld + n] = __ldg(weights + sg.src + idx);
+        const int total = sg.K * sg.N;
+        if ((sg.N & (sg.N - 1)) == 0) {
+            const int sh = 31 - __clz(sg.N);
+            for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+                const int k = idx >> sh, n = idx & (sg.N - 1);
+                cp_async4(Ws + sg.dst + k * sg.ld + n, weights + sg.src + idx);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+                const int k = idx / sg.N, n = idx - k * sg.N;
+                cp_async4(Ws + sg.dst + k * sg.ld + n, weights + sg.src + idx);
+            }
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// completes stage_weights (copies overlap whatever the caller does in between)
+__device__ __forceinline__ void stage_weights_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 }
 
 // ---- forward layers -------------------------------------------------------------------------
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(448, 1) dynloop_fwd_kernel(stove_gnn_cfg c, TW
     const int team = warp / NW, part = warp % NW, tpc = (blockDim.x >> 5) / NW, bar = 1 + team;
     float* a = smem + w.total + team * Lay::TOTAL;
     for (int i = lane + 32 * part; i < Lay::TOTAL; i += 32 * NW) a[i] = 0.f;
-    __syncthreads();
+    stage_weights_wait();
     const int T = io.T, S = io.T - io.skip;
     for (int64_t sq = (int64_t)blockIdx.x * tpc + team; sq < n; sq += (int64_t)gridDim.x * tpc) {
         if (part == 0) load_state<Lay>(a, io.z_init + sq * O * ZD, lane);
@@ -465,7 +487,7 @@ __global__ void __launch_bounds__(448, 1) team_rollout_kernel(
     const int team = warp / NW, part = warp % NW, tpc = (blockDim.x >> 5) / NW, bar = 1 + team;
     float* a = smem + w.total + team * Lay::TOTAL;
     for (int i = lane + 32 * part; i < Lay::TOTAL; i += 32 * NW) a[i] = 0.f;
-    __syncthreads();
+    stage_weights_wait();
     for (int64_t sq = (int64_t)blockIdx.x * tpc + team; sq < n; sq += (int64_t)gridDim.x * tpc) {
         if (part == 0) {
             load_state<Lay>(a, z_last + sq * O * ZD, lane);
@@ -563,7 +585,7 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
     const bool p0 = (NW == 1) || part == 0, p1 = (NW == 1) || part == 1;
     float* a = smem + w.total + team * Lay::TOTAL;
     for (int i = lane + 32 * part; i < Lay::TOTAL; i += 32 * NW) a[i] = 0.f;
-    __syncthreads();
+    stage_weights_wait();
     const int T = io.T, S = io.T - io.skip, nl = c.nonlin;
     for (int64_t sq = (int64_t)blockIdx.x * tpc + team; sq < n; sq += (int64_t)gridDim.x * tpc) {
         if (p0)
