@@ -306,6 +306,28 @@ int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int6
                       const stove_dynloop_io* io, const float* weights, float* g_weights,
                       void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * z of every scored frame and the ELBO assembly of Stove.stove_forward (stove.py:731-748,
+ * supair.py:84-110, Supair.sy_from_quotient supair.py:151-158).
+ *   zall: z_sup [n][T][O][4], z_s [n][T-skip][O][Z] ([sx, sy/sx, x, y | ...]) -> z_all [n][T-1][O][4]
+ *         ([sx, sy, x, y] of frames 1 .. T-1: SuPAIR state for t < skip, sampled state after);
+ *         backward overwrites g_z_sup [n][T][O][4] and g_z_s [n][T-skip][O][Z] completely.
+ *   elbo: bg [F], patch [F][O] (raw object-SPN log-likelihoods), z_all [F][O][4], overlap [F][O]
+ *         (F = n (T-1)), logq / trans [n][T-skip] -> stats[8] = {average ELBO, mean bg, mean patch,
+ *         mean overlap prior (frames t >= skip), mean log q, mean transition lik, mean SuPAIR-frame
+ *         likelihood, 0}, elbo_out[1] = the average ELBO again (its own buffer);  backward: g = d loss / d ELBO (one float on the device).
+ * ---------------------------------------------------------------------------------- */
+int stove_zall_fwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,
+                   float* z_all, void* stream);
+int stove_zall_bwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,
+                   const float* g_z_all, float* g_z_sup, float* g_z_s, void* stream);
+int stove_elbo_fwd(int64_t n, int T, int skip, int O, float beta, const float* bg, const float* patch,
+                   const float* z_all, const float* overlap, const float* logq, const float* trans,
+                   float* stats, float* elbo_out, void* stream);
+int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g, const float* patch,
+                   const float* z_all, float* g_bg, float* g_patch, float* g_z_all, float* g_overlap,
+                   float* g_logq, float* g_trans, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

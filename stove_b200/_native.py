@@ -106,6 +106,10 @@ SIGNATURES = {
     'stove_dynloop_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp]),
     'stove_dynloop_bwd_workspace': (sz, [PG, i64, C.c_int, C.c_int]),
     'stove_dynloop_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp]),
+    'stove_zall_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    'stove_zall_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    'stove_elbo_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 8 + [vp]),
+    'stove_elbo_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 9 + [vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

@@ -392,3 +392,194 @@ extern "C" int stove_lstm_cell_bwd(int64_t n, int H, const float* act, const flo
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// z of every scored frame (stove.py:731-736): frames t = 1 .. T-1 use the SuPAIR state for
+// t < skip and the sampled state z_t for t >= skip; [sx, sy/sx, x, y] -> [sx, sy, x, y]
+// (Supair.sy_from_quotient, supair.py:151-158).  Replaces 2 cat + slice + mul + cat + copy
+// forward and ~20 ATen launches backward.
+//   z_sup [n][T][O][4], z_s [n][S][O][Z] (S = T - skip)  ->  z_all [n][T-1][O][4]
+// ------------------------------------------------------------------------------------
+__global__ void zall_fwd_kernel(int64_t n, int T, int skip, int O, int Z, const float* __restrict__ z_sup,
+                                const float* __restrict__ z_s, float* __restrict__ z_all) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, t', o)
+    if (i >= n * (T - 1) * O) return;
+    const int o = (int)(i % O);
+    const int tp = (int)((i / O) % (T - 1));
+    const int64_t b = i / ((int64_t)O * (T - 1));
+    const int t = tp + 1, S = T - skip;
+    const float* src = t < skip ? z_sup + ((b * T + t) * O + o) * 4 : z_s + ((b * S + (t - skip)) * O + o) * Z;
+    const float sx = __ldg(src), q = __ldg(src + 1);
+    reinterpret_cast<float4*>(z_all)[i] = make_float4(sx, sx * q, __ldg(src + 2), __ldg(src + 3));
+}
+
+// g_z_sup and g_z_s are fully written (zeros where z_all does not depend on them)
+__global__ void zall_bwd_kernel(int64_t n, int T, int skip, int O, int Z, const float* __restrict__ z_sup,
+                                const float* __restrict__ z_s, const float* __restrict__ g_z_all,
+                                float* __restrict__ g_z_sup, float* __restrict__ g_z_s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (b, t, o), t = 0 .. T-1
+    if (i >= n * T * O) return;
+    const int o = (int)(i % O);
+    const int t = (int)((i / O) % T);
+    const int64_t b = i / ((int64_t)O * T);
+    const int S = T - skip;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 1) {
+        const float4 ga = reinterpret_cast<const float4*>(g_z_all)[(b * (T - 1) + (t - 1)) * O + o];
+        const float* src = t < skip ? z_sup + ((b * T + t) * O + o) * 4 : z_s + ((b * S + (t - skip)) * O + o) * Z;
+        const float sx = __ldg(src), q = __ldg(src + 1);
+        g = make_float4(ga.x + ga.y * q, ga.y * sx, ga.z, ga.w);
+    }
+    if (t < skip) {
+        reinterpret_cast<float4*>(g_z_sup)[i] = g;
+    } else {
+        reinterpret_cast<float4*>(g_z_sup)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst = g_z_s + ((b * S + (t - skip)) * O + o) * Z;
+        dst[0] = g.x; dst[1] = g.y; dst[2] = g.z; dst[3] = g.w;
+        for (int k = 4; k < Z; ++k) dst[k] = 0.f;
+    }
+}
+
+extern "C" int stove_zall_fwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,
+                              float* z_all, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && T > skip && skip >= 1 && O > 0 && Z >= 4 && z_sup && z_s && z_all, "bad argument");
+    const int64_t items = n * (T - 1) * O;
+    if (items == 0) return STOVE_OK;
+    STOVE_KERNEL(K_ZALL_FWD, (cudaStream_t)stream, zall_fwd_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, T, skip, O, Z, z_sup, z_s, z_all));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_zall_bwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,
+                              const float* g_z_all, float* g_z_sup, float* g_z_s, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && T > skip && skip >= 1 && O > 0 && Z >= 4 && z_sup && z_s && g_z_all && g_z_sup && g_z_s,
+                    "bad argument");
+    const int64_t items = n * T * O;
+    if (items == 0) return STOVE_OK;
+    STOVE_KERNEL(K_ZALL_BWD, (cudaStream_t)stream, zall_bwd_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, T, skip, O, Z, z_sup, z_s, g_z_all, g_z_sup, g_z_s));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// ELBO assembly (supair.py:84-110 + stove.py:737-748):
+//   lik_f = bg_f + sum_o patch_fo * sx_fo * sy_fo + sum_o (log beta - beta * overlap_fo)
+//   elbo  = mean_{t >= skip}(lik_f) + mean(trans - log q) + mean_{1 <= t < skip}(lik_f)
+// One CTA, fixed summation order (deterministic), double accumulation.  stats[8] =
+// {elbo, mean bg, mean patch, mean overlap (t >= skip), mean log q, mean trans, mean lik_sup, 0}.
+// ~40 ATen launches forward + backward become two.
+// ------------------------------------------------------------------------------------
+#define ELBO_THREADS 1024
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(int64_t n, int T, int skip, int O, float beta,
+                                                                const float* __restrict__ bg,
+                                                                const float* __restrict__ patch,
+                                                                const float* __restrict__ z_all,
+                                                                const float* __restrict__ overlap,
+                                                                const float* __restrict__ logq,
+                                                                const float* __restrict__ trans,
+                                                                float* __restrict__ stats,
+                                                                float* __restrict__ elbo_out) {
+    __shared__ double red[6][ELBO_THREADS / 32];
+    double acc[6] = {0., 0., 0., 0., 0., 0.};      // bg, patch, overlap (elbo frames), lik_sup, logq, trans
+    const int S = T - skip, nsup = skip - 1;
+    const float logb = logf(beta);
+    const int64_t frames = n * (T - 1);
+    for (int64_t f = threadIdx.x; f < frames; f += blockDim.x) {
+        const int tp = (int)(f % (T - 1));
+        float p = 0.f, ov = 0.f;
+        for (int o = 0; o < O; ++o) {
+            const float4 z = reinterpret_cast<const float4*>(z_all)[f * O + o];
+            p += __ldg(patch + f * O + o) * z.x * z.y;
+            ov += logb - beta * __ldg(overlap + f * O + o);
+        }
+        const float b = __ldg(bg + f);
+        if (tp >= nsup) { acc[0] += b; acc[1] += p; acc[2] += ov; }
+        else acc[3] += (double)b + p + ov;
+    }
+    for (int64_t i = threadIdx.x; i < n * S; i += blockDim.x) {
+        acc[4] += __ldg(logq + i);
+        acc[5] += __ldg(trans + i);
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[q][wp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[6];
+        for (int q = 0; q < 6; ++q) {
+            double v = 0.;
+            for (int w = 0; w < ELBO_THREADS / 32; ++w) v += red[q][w];
+            tot[q] = v;
+        }
+        const double ne = (double)n * S, ns = (double)n * nsup;
+        const double lik_sup = nsup > 0 ? tot[3] / ns : 0.;
+        stats[0] = (float)((tot[0] + tot[1] + tot[2] + tot[5] - tot[4]) / ne + lik_sup);
+        *elbo_out = stats[0];
+        stats[1] = (float)(tot[0] / ne);
+        stats[2] = (float)(tot[1] / ne);
+        stats[3] = (float)(tot[2] / ne);
+        stats[4] = (float)(tot[4] / ne);
+        stats[5] = (float)(tot[5] / ne);
+        stats[6] = (float)lik_sup;
+        stats[7] = 0.f;
+    }
+}
+
+// g = d loss / d elbo (device scalar)
+__global__ void elbo_bwd_kernel(int64_t n, int T, int skip, int O, float beta, const float* __restrict__ g,
+                                const float* __restrict__ patch, const float* __restrict__ z_all,
+                                float* __restrict__ g_bg, float* __restrict__ g_patch, float* __restrict__ g_z_all,
+                                float* __restrict__ g_overlap, float* __restrict__ g_logq,
+                                float* __restrict__ g_trans) {
+    const int S = T - skip, nsup = skip - 1;
+    const float gv = __ldg(g);
+    const float we = gv / (float)((double)n * S), ws = nsup > 0 ? gv / (float)((double)n * nsup) : 0.f;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t items = n * (T - 1) * O;
+    if (i < items) {
+        const int64_t f = i / O;
+        const int tp = (int)(f % (T - 1));
+        const float w = tp >= nsup ? we : ws;
+        const float4 z = reinterpret_cast<const float4*>(z_all)[i];
+        const float p = __ldg(patch + i);
+        g_patch[i] = w * z.x * z.y;
+        reinterpret_cast<float4*>(g_z_all)[i] = make_float4(w * p * z.y, w * p * z.x, 0.f, 0.f);
+        g_overlap[i] = -beta * w;
+        if (i % O == 0) g_bg[f] = w;
+    }
+    if (i < n * S) {
+        g_logq[i] = -we;
+        g_trans[i] = we;
+    }
+}
+
+extern "C" int stove_elbo_fwd(int64_t n, int T, int skip, int O, float beta, const float* bg, const float* patch,
+                              const float* z_all, const float* overlap, const float* logq, const float* trans,
+                              float* stats, float* elbo_out, void* stream) {
+    STOVE_CHECK_ARG(n > 0 && T > skip && skip >= 1 && O > 0 && bg && patch && z_all && overlap && logq && trans && stats && elbo_out,
+                    "bad argument");
+    STOVE_KERNEL(K_ELBO_FWD, (cudaStream_t)stream, elbo_fwd_kernel<<<1, ELBO_THREADS, 0, (cudaStream_t)stream>>>(
+        n, T, skip, O, beta, bg, patch, z_all, overlap, logq, trans, stats, elbo_out));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g, const float* patch,
+                              const float* z_all, float* g_bg, float* g_patch, float* g_z_all, float* g_overlap,
+                              float* g_logq, float* g_trans, void* stream) {
+    STOVE_CHECK_ARG(n > 0 && T > skip && skip >= 1 && O > 0 && g && patch && z_all && g_bg && g_patch && g_z_all &&
+                        g_overlap && g_logq && g_trans, "bad argument");
+    int64_t items = n * (T - 1) * O;
+    if (n * (T - skip) > items) items = n * (T - skip);
+    STOVE_KERNEL(K_ELBO_BWD, (cudaStream_t)stream, elbo_bwd_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, T, skip, O, beta, g, patch, z_all, g_bg, g_patch, g_z_all, g_overlap, g_logq, g_trans));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -84,6 +84,19 @@ class PackSum(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------
 # fused SPNs
 # ----------------------------------------------------------------------------------------
+def _zeros_views(ref, *shapes):
+    """Zero tensors of the given shapes carved out of ONE buffer (one fill launch instead of one each);
+    every view starts on a 256-byte boundary."""
+    numels = [int(torch.Size(sh).numel()) for sh in shapes]
+    sizes = [(m + 63) // 64 * 64 for m in numels]
+    buf = torch.zeros(sum(sizes), device=ref.device, dtype=ref.dtype)
+    out, at = [], 0
+    for sh, m, sz in zip(shapes, numels, sizes):
+        out.append(buf[at:at + m].view(sh))
+        at += sz
+    return out
+
+
 def _npad(n):
     return (n + 31) // 32 * 32
 
@@ -119,9 +132,7 @@ class Spn2(torch.autograd.Function):
         need_x, need_m = ctx.needs_input_grad[0], ctx.has_marg and ctx.needs_input_grad[1]
         g_x = torch.empty_like(x) if need_x else None
         g_m = torch.empty_like(marg) if need_m else None
-        g_leaf = torch.zeros_like(leaf)
-        g_wlog = torch.zeros_like(wlog)
-        g_rlog = torch.zeros_like(rlog)
+        g_leaf, g_wlog, g_rlog = _zeros_views(leaf, leaf.shape, wlog.shape, rlog.shape)
         ws = torch.empty(max(N.lib().stove_spn2_bwd_workspace(C.byref(st), n), 4) // 4, device=x.device,
                          dtype=torch.float32)
         N.check(N.lib().stove_spn2_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(wlin),
@@ -161,8 +172,7 @@ class Spn1(torch.autograd.Function):
         need_x, need_m = ctx.needs_input_grad[0], ctx.has_marg and ctx.needs_input_grad[1]
         g_x = torch.empty_like(x) if need_x else None
         g_m = torch.empty_like(marg) if need_m else None
-        g_leaf = torch.zeros_like(leaf)
-        g_rlog = torch.zeros_like(rlog)
+        g_leaf, g_rlog = _zeros_views(leaf, leaf.shape, rlog.shape)
         ws = torch.empty(max(N.lib().stove_spn1_bwd_workspace(C.byref(st), n), 4) // 4, device=x.device,
                          dtype=torch.float32)
         N.check(N.lib().stove_spn1_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(rlin),
@@ -343,7 +353,8 @@ class DynamicsLoop(torch.autograd.Function):
     transition lik), chained through z_t on the device -- one persistent kernel forward, three
     kernels backward (csrc/dynloop.cu).
 
-    z_init (n, O, Z); sup, sup_std (n, T, O, 6); eps (S, n, O, Z); actions (n, T, A) | None;
+    sup, sup_std (n, T, O, 6); lat0 (n, O, Z-6) initial latents (noise, no gradient) -- the initial
+    state is [sup[:, skip-1], lat0] (stove.py:672-676); eps (S, n, O, Z); actions (n, T, A) | None;
     app (n, T, O, 3) | None; weights flat.  Returns z (n, S, O, Z), z_dyn, z_dyn_std (n, S, O, Z-2),
     z_std (n, S, O, Z), logq (n, S), trans (n, S), rewards (n, S, 1)."""
 
@@ -356,8 +367,9 @@ class DynamicsLoop(torch.autograd.Function):
         return io
 
     @staticmethod
-    def forward(ctx, z_init, sup, sup_std, eps, actions, app, weights, cfg, fuse, skip):
-        z_init, sup, sup_std, eps = z_init.contiguous(), sup.contiguous(), sup_std.contiguous(), eps.contiguous()
+    def forward(ctx, sup, sup_std, lat0, eps, actions, app, weights, cfg, fuse, skip):
+        sup, sup_std, eps = sup.contiguous(), sup_std.contiguous(), eps.contiguous()
+        z_init = torch.cat([sup[:, skip - 1], lat0], -1)
         actions, app = _c(actions), _c(app)
         N.require_cuda_f32(z_init, sup, sup_std, eps, actions, app, weights)
         n, O, Z = z_init.shape
@@ -404,7 +416,76 @@ class DynamicsLoop(torch.autograd.Function):
         io.g_z_init, io.g_sup, io.g_sup_std = N.ptr(g_z_init), N.ptr(g_sup), N.ptr(g_sup_std)
         N.check(N.lib().stove_dynloop_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
                                           N.ptr(ws), N.stream()))
-        return g_z_init, g_sup, g_sup_std, None, None, None, g_w, None, None, None
+        # the initial state is sup[:, skip-1] (+ noise latents): the loop itself leaves that slice zero
+        g_sup[:, skip - 1].copy_(g_z_init[..., :6])
+        return g_sup, g_sup_std, None, None, None, None, g_w, None, None, None
+
+
+class ZAll(torch.autograd.Function):
+    """z of every scored frame (stove.py:731-736): z_sup (n, T, O, 4) for 1 <= t < skip, the sampled
+    z_s (n, S, O, Z)[..., :4] for t >= skip, converted [sx, sy/sx, x, y] -> [sx, sy, x, y]
+    (supair.py:151-158).  Returns (n, T-1, O, 4)."""
+
+    @staticmethod
+    def forward(ctx, z_sup, z_s, skip):
+        z_sup, z_s = z_sup.contiguous(), z_s.contiguous()
+        N.require_cuda_f32(z_sup, z_s)
+        n, T, O, _ = z_sup.shape
+        Z = z_s.shape[-1]
+        z_all = torch.empty(n, T - 1, O, 4, device=z_sup.device, dtype=z_sup.dtype)
+        N.check(N.lib().stove_zall_fwd(n, T, skip, O, Z, N.ptr(z_sup), N.ptr(z_s), N.ptr(z_all), N.stream()))
+        ctx.save_for_backward(z_sup, z_s)
+        ctx.skip = skip
+        return z_all
+
+    @staticmethod
+    def backward(ctx, g_z_all):
+        z_sup, z_s = ctx.saved_tensors
+        n, T, O, _ = z_sup.shape
+        g_z_sup, g_z_s = torch.empty_like(z_sup), torch.empty_like(z_s)
+        N.check(N.lib().stove_zall_bwd(n, T, ctx.skip, O, z_s.shape[-1], N.ptr(z_sup), N.ptr(z_s),
+                                       N.ptr(g_z_all.contiguous()), N.ptr(g_z_sup), N.ptr(g_z_s), N.stream()))
+        return g_z_sup, g_z_s, None
+
+
+class ElboAssemble(torch.autograd.Function):
+    """Sequence ELBO from the per-frame terms (supair.py:84-110, stove.py:737-748), one launch each way.
+    bg (F,), patch (F*O,) raw object-SPN log-likelihoods, z_all (n, T-1, O, 4), overlap (F, O),
+    logq / trans (n, S).  Returns (average_elbo (), stats (8,)): stats = [elbo, mean bg, mean patch,
+    mean overlap prior, mean log q, mean transition lik, mean SuPAIR-frame lik, 0] for logging."""
+
+    @staticmethod
+    def forward(ctx, bg, patch, z_all, overlap, logq, trans, skip, beta):
+        bg, patch, z_all, overlap = bg.contiguous(), patch.contiguous(), z_all.contiguous(), overlap.contiguous()
+        logq, trans = logq.contiguous(), trans.contiguous()
+        N.require_cuda_f32(bg, patch, z_all, overlap, logq, trans)
+        n, Tm1, O, _ = z_all.shape
+        stats = torch.empty(8, device=bg.device, dtype=bg.dtype)
+        elbo = torch.empty((), device=bg.device, dtype=bg.dtype)
+        N.check(N.lib().stove_elbo_fwd(n, Tm1 + 1, skip, O, beta, N.ptr(bg), N.ptr(patch), N.ptr(z_all),
+                                       N.ptr(overlap), N.ptr(logq), N.ptr(trans), N.ptr(stats), N.ptr(elbo),
+                                       N.stream()))
+        ctx.save_for_backward(patch, z_all)
+        ctx.meta = (skip, beta, bg.shape, overlap.shape, logq.shape)
+        ctx.mark_non_differentiable(stats)
+        return elbo, stats
+
+    @staticmethod
+    def backward(ctx, g_elbo, _g_stats):
+        patch, z_all = ctx.saved_tensors
+        skip, beta, bg_shape, ov_shape, lq_shape = ctx.meta
+        n, Tm1, O, _ = z_all.shape
+        dev, dt = patch.device, patch.dtype
+        g_bg = torch.empty(bg_shape, device=dev, dtype=dt)
+        g_patch = torch.empty_like(patch)
+        g_z_all = torch.empty_like(z_all)
+        g_ov = torch.empty(ov_shape, device=dev, dtype=dt)
+        g_lq = torch.empty(lq_shape, device=dev, dtype=dt)
+        g_tr = torch.empty(lq_shape, device=dev, dtype=dt)
+        N.check(N.lib().stove_elbo_bwd(n, Tm1 + 1, skip, O, beta, N.ptr(g_elbo.contiguous()), N.ptr(patch),
+                                       N.ptr(z_all), N.ptr(g_bg), N.ptr(g_patch), N.ptr(g_z_all), N.ptr(g_ov),
+                                       N.ptr(g_lq), N.ptr(g_tr), N.stream()))
+        return g_bg, g_patch, g_z_all, g_ov, g_lq, g_tr, None, None
 
 
 def gnn_rollout(cfg, z_last, num, weights, actions=None, app=None, noise=None, pos_var=0.3, vel_std=0.04,

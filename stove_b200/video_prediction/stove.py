@@ -73,6 +73,15 @@ class Stove(nn.Module):
     def _standard_normal(self, shape, like):
         return torch.empty(shape, device=like.device, dtype=like.dtype).normal_()
 
+    def _standard_normal_n(self, count, shape, like):
+        """`count` consecutive draws of `shape`, stacked on a new leading axis: one generator launch.
+        A replacement `_standard_normal` that replays recorded draws (tests) sets `stacked = False`
+        and is asked draw by draw, in the reference's order."""
+        fn = self._standard_normal
+        if getattr(fn, 'stacked', True):
+            return fn((count,) + tuple(shape), like)
+        return torch.stack([fn(tuple(shape), like) for _ in range(count)], 0)
+
     # -- small sequence helpers ---------------------------------------------------------------
     def v_from_state(self, z_sup):
         """(n, T, o, 4) -> (n, T, o, 6): append finite-difference velocities, zeros at t=0."""
@@ -233,41 +242,44 @@ class Stove(nn.Module):
         if _app is None:
             obj_appearances = None
 
+        # initial latents ~ N(0, 0.01^2) (stove.py:672-680).  The reference draws a second sample of the
+        # same shape for the initial dynamics std (logging only); both come from one generator launch
         prior_shape = (n, O, cl // 2 - 4, 1)
-        lat0 = (0.01 * self._standard_normal(prior_shape, x)).squeeze()
-        init_z = torch.cat([z_sup_full[:, skip - 1], lat0], -1)
-        # the reference also draws the initial dynamics std here (stove.py:677-680); it only feeds
-        # logging, but the draw is kept so the random stream stays aligned with the reference
-        self._standard_normal(prior_shape, x)
+        pri = self._standard_normal_n(2, prior_shape, x)
+        lat0 = (0.01 * pri[0]).squeeze(-1)
 
-        # dynamics loop: one fused kernel per time step (csrc/gnn.cu: dynstep_*), chained on the device
-        eps = torch.stack([self._standard_normal((n, O, cl // 2 + 2), x) for _ in range(skip, T)], 0)
+        # dynamics loop: the whole loop is one persistent kernel (csrc/dynloop.cu), chained on the device
+        eps = self._standard_normal_n(T - skip, (n, O, cl // 2 + 2), x)
         cfg_dyn, w_dyn = packed_dyn
         z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
-            init_z, z_sup_full, z_sup_std_full, eps, actions,
+            z_sup_full, z_sup_std_full, lat0, eps, actions,
             obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip)
         if not c.action_conditioned:
             rewards = torch.zeros(T - skip)
 
         # p(x_t | z_t) for t >= skip and p(x_t | z_sup_t) for 1 <= t < skip (stove.py:731-736) share one
-        # pass over the frames x[:, 1:]: a single glimpse/mask launch and one launch family per SPN
-        z_all = torch.cat([z_sup[:, 1:skip], z_s[..., :4]], 1)                      # (n, T-1, O, 4) [sx, sy/sx, ..]
-        z_all = self.sup.sy_from_quotient(z_all)
-        bg, patch, ov, extra = self.sup.likelihood_parts(x[:, 1:].flatten(end_dim=1), z_all.flatten(end_dim=1),
-                                                         packed=packed_spn)
-        n_sup = skip - 1
-        bg, patch, ov = bg.view(n, T - 1), patch.view(n, T - 1), ov.view(n, T - 1)
-        if (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0):
-            self.sup._log_parts(bg[:, n_sup:].flatten(), patch[:, n_sup:].flatten(), ov[:, n_sup:].flatten(),
-                                {k: v for k, v in extra.items()})
-            self.prop_dict.update(self.sup.prop_dict)
-        lik = bg + patch + ov
-        img_lik = lik[:, n_sup:].flatten()
-        img_lik_sup = lik[:, :n_sup].flatten()
-        log_z_f = log_z_n.flatten()
-        trans_lik = trans_n.flatten()
-        elbo = trans_lik + img_lik - log_z_f
-        average_elbo = elbo.mean() + img_lik_sup.mean()
+        # pass over the frames x[:, 1:]: a single glimpse/mask launch and one launch family per SPN;
+        # the per-frame terms are reduced to the ELBO by one kernel (csrc/glue.cu)
+        z_all = ops.ZAll.apply(z_sup, z_s, skip)                                    # (n, T-1, O, 4) [sx, sy, x, y]
+        bg, patch_raw, overlap, extra = self.sup.likelihood_raw(x[:, 1:].flatten(end_dim=1),
+                                                                z_all.flatten(end_dim=1), packed=packed_spn)
+        average_elbo, stats = ops.ElboAssemble.apply(bg, patch_raw, z_all, overlap, log_z_n, trans_n, skip,
+                                                     float(c.overlap_beta))
+        logging = (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0)
+        if logging and c.debug:
+            p = self.prop_dict
+            p['bg'], p['patch'], p['overlap'] = stats[1], stats[2], stats[3]
+            if c.debug_extend_plots:
+                n_sup = skip - 1
+                with torch.no_grad():
+                    za = z_all.flatten(end_dim=1)
+                    pl = (patch_raw.view(-1, O) * za[..., 0] * za[..., 1]).sum(1)
+                p['overlap_ratios'] = extra['overlap_ratios'].detach()
+                p['patches'] = extra['patches'].detach()
+                p['marginalise_flat'] = extra['marginalise_flat'].detach()
+                p['patches_loglik'] = pl.view(n, T - 1)[:, n_sup:].flatten()
+                p['marginalise_bg'] = extra['marginalise_bg'].detach()
+                p['bg_loglik'] = bg.detach().view(n, T - 1)[:, n_sup:].flatten()
 
         if (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0):
             p = self.prop_dict
@@ -278,8 +290,8 @@ class Stove(nn.Module):
             p['z_dyn_std'] = torch.cat([z_s.new_full((2,), float('nan')),
                                         z_dyn_std_s[..., :4].mean((0, 1, 2)).detach()])
             p['z_sup_std'] = z_sup_std_full[:, skip:].mean((0, 1, 2)).detach()
-            p['log_q'] = log_z_f.mean().detach()
-            p['translik'] = trans_lik.mean().detach()
+            p['log_q'] = stats[4]
+            p['translik'] = stats[5]
             p['obj_appearances'] = obj_appearances[:, skip:].detach() if obj_appearances is not None else None
             if c.debug and c.debug_extend_plots:
                 p['z_dyn_std_full'] = z_dyn_std_s.detach()

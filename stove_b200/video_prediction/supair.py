@@ -62,10 +62,10 @@ class Supair(nn.Module):
         return cache[k]
 
     # -- likelihood ----------------------------------------------------------------------
-    def likelihood_parts(self, x_img, z_img, packed=None):
-        """x_img (F, c, w, h), z_img (F, O, 4) [sx, sy, x, y] -> per-frame (bg, patch, overlap)
-        log-likelihood terms plus the intermediate tensors (one glimpse/mask launch, one launch
-        family per SPN)."""
+    def likelihood_raw(self, x_img, z_img, packed=None):
+        """x_img (F, c, w, h), z_img (F, O, 4) [sx, sy, x, y] -> background log-likelihood (F,), RAW
+        object-SPN log-likelihoods (F*O,) (not yet weighted by sx * sy), overlap ratios (F, O) and the
+        intermediate tensors: one glimpse/mask launch, one launch family per SPN."""
         c = self.c
         pk_obj, pk_bg = packed if packed is not None else self.pack()
         patches, marg_patch, marg_bg, overlap = ops.Scene.apply(
@@ -80,12 +80,19 @@ class Supair(nn.Module):
             patches_loglik = self.obj_spn.forward_packed(pk_obj, patches_flat, marginalise_flat)[:, 0]
         else:
             patches_loglik = self.obj_spn.forward(patches_flat, marginalise_flat)[:, 0]
+        extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marginalise_flat,
+                     marginalise_bg=marg_bg)
+        return bg_loglik, patches_loglik, overlap, extra
+
+    def likelihood_parts(self, x_img, z_img, packed=None):
+        """Per-frame (bg, patch, overlap) log-likelihood terms of supair.py:84-110 plus the
+        intermediate tensors."""
+        c = self.c
+        bg_loglik, patches_loglik, overlap, extra = self.likelihood_raw(x_img, z_img, packed)
         z_flat = z_img.reshape(-1, 4)
         patches_loglik = (patches_loglik * z_flat[:, 0] * z_flat[:, 1]).view(-1, c.num_obj).sum(1)
         # log Exponential(beta)(overlap) = log beta - beta * overlap
         overlap_log_liks = (math.log(c.overlap_beta) - c.overlap_beta * overlap).sum(1)
-        extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marginalise_flat,
-                     marginalise_bg=marg_bg)
         return bg_loglik, patches_loglik, overlap_log_liks, extra
 
     def _log_parts(self, bg_loglik, patches_loglik, overlap_log_liks, extra):

@@ -84,7 +84,9 @@ class Checker:
 
 
 class NoiseReplay:
-    """Stands in for Stove._standard_normal: replays a list of draws (shape-checked)."""
+    """Stands in for Stove._standard_normal: replays a list of draws (shape-checked), one draw per
+    call in the reference's order (`stacked = False`, see Stove._standard_normal_n)."""
+    stacked = False
 
     def __init__(self, draws, device):
         self.draws = [d.to(device=device, dtype=torch.float32) for d in draws]
