@@ -328,6 +328,10 @@ int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g
                    const float* z_all, float* g_bg, float* g_patch, float* g_z_all, float* g_overlap,
                    float* g_logq, float* g_trans, void* stream);
 
+/* fp32 -> hi (TF32-exact: low 13 mantissa bits cleared) + lo = x - hi, for 3xTF32 library GEMMs of
+ * the recognition LSTM (encoder.py:50-51).  n % 4 == 0, 16-byte aligned pointers. */
+int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,7 @@ SIGNATURES = {
     'stove_zall_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     'stove_elbo_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 8 + [vp]),
     'stove_elbo_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 9 + [vp]),
+    'stove_split_tf32': (C.c_int, [i64, vp, vp, vp, vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

@@ -583,3 +583,33 @@ extern "C" int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, con
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) with hi exactly representable in TF32 (low 13 mantissa bits cleared) and
+// lo = x - hi (exact).  a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi on the TF32 tensor cores keeps
+// fp32-level accuracy (error ~2^-21 relative per product) at a fraction of the SIMT-fp32 GEMM time;
+// used for the recognition LSTM's GEMMs (encoder.py:50-51), which stay library GEMMs.
+// ------------------------------------------------------------------------------------
+__global__ void split_tf32_kernel(int64_t n4, const float4* __restrict__ x, float4* __restrict__ hi,
+                                  float4* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(x + i);
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+}
+
+extern "C" int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && n % 4 == 0 && x && hi && lo, "need n % 4 == 0 and non-null pointers");
+    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "pointers must be 16-byte aligned");
+    if (n == 0) return STOVE_OK;
+    STOVE_KERNEL(K_SPLIT_TF32, (cudaStream_t)stream, split_tf32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n / 4, (const float4*)x, (float4*)hi, (float4*)lo));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

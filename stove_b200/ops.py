@@ -294,6 +294,53 @@ class LstmCell(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------
+# 3xTF32 linear layer (recognition LSTM GEMMs)
+# ----------------------------------------------------------------------------------------
+def split_tf32(x):
+    """x -> (hi, lo): hi exactly representable in TF32, lo = x - hi (no autograd)."""
+    x = x.contiguous()
+    N.require_cuda_f32(x)
+    if x.numel() % 4:
+        raise RuntimeError('split_tf32 needs a multiple of 4 elements')
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    N.check(N.lib().stove_split_tf32(x.numel(), N.ptr(x), N.ptr(hi), N.ptr(lo), N.stream()))
+    return hi, lo
+
+
+def mm3(a, b):
+    """a @ b for split operands a = (a_hi, a_lo), b = (b_hi, b_lo) (any strides): three TF32
+    tensor-core GEMMs, fp32 accumulate; the lo * lo term (2^-22 relative) is dropped."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = torch.mm(a[0], b[1])
+        out.addmm_(a[1], b[0])
+        out.addmm_(a[0], b[0])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
+
+
+class Linear3(torch.autograd.Function):
+    """y = a @ w.t() (a (n, K), w (M, K) as in nn.Linear, no bias) in 3xTF32.  `a_split` / `w_split`
+    are optional precomputed (hi, lo) pairs so operands used several times are split once."""
+
+    @staticmethod
+    def forward(ctx, a, w, a_split, w_split):
+        a_split = a_split if a_split is not None else split_tf32(a)
+        w_split = w_split if w_split is not None else split_tf32(w)
+        ctx.a_split, ctx.w_split = a_split, w_split
+        return mm3(a_split, (w_split[0].t(), w_split[1].t()))
+
+    @staticmethod
+    def backward(ctx, g):
+        g_split = split_tf32(g)
+        g_a = mm3(g_split, ctx.w_split) if ctx.needs_input_grad[0] else None
+        g_w = mm3((g_split[0].t(), g_split[1].t()), ctx.a_split) if ctx.needs_input_grad[1] else None
+        return g_a, g_w, None, None
+
+
+# ----------------------------------------------------------------------------------------
 # GNN dynamics
 # ----------------------------------------------------------------------------------------
 GNN_SEGMENTS = ['act', 'enc', 'self0', 'self1', 'ra0', 'rel1', 'att1', 'rel2', 'att2', 'aff0', 'aff1',

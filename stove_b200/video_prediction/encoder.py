@@ -1,12 +1,16 @@
 """LSTM recognition network (drop-in for model/video_prediction/encoder.py:7-57).
 
-Kept on cuDNN/cuBLAS in this round (SURVEY.md section 8f ranks it first under "next"); the
-one structural change is free: the reference feeds the *same* flattened frame for every one
+The GEMMs stay library GEMMs (SURVEY.md section 8f ranks the encoder first under "next") but run
+as 3xTF32 on the tensor cores (ops.Linear3: fp32-level accuracy, ~3x faster than the SIMT-fp32
+kernels cuBLAS picks when TF32 is off); the gate/state update is a fused kernel.  One structural
+change is free: the reference feeds the *same* flattened frame for every one
 of the `num_obj` LSTM steps (encoder.py:50), so `W_ih x + b` is computed once per frame
 instead of once per step (1/3 of the input GEMM at O = 3) and the recurrence runs on the
 small hidden-to-hidden GEMM only.  Parameter names are those of `nn.LSTM`
 (`rnn.weight_ih_l0`, ...) so reference checkpoints load.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -33,13 +37,25 @@ class RnnStates(nn.Module):
         x = frames.flatten(start_dim=1)
         H = self.lstm_size
         rnn = self.rnn
-        gates_x = torch.addmm(rnn.bias_ih_l0 + rnn.bias_hh_l0, x, rnn.weight_ih_l0.t())
         h = cell = None                              # zero initial state: first step needs no W_hh GEMM
         outs = []
-        for _ in range(self.c.num_obj):
-            gates_h = torch.mm(h, rnn.weight_hh_l0.t()) if h is not None else None
-            h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
-            outs.append(h)
+        if os.environ.get('STOVE_ENCODER_FP32'):     # plain SIMT-fp32 library GEMMs (A/B reference)
+            gates_x = torch.addmm(rnn.bias_ih_l0 + rnn.bias_hh_l0, x, rnn.weight_ih_l0.t())
+            for _ in range(self.c.num_obj):
+                gates_h = torch.mm(h, rnn.weight_hh_l0.t()) if h is not None else None
+                h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
+                outs.append(h)
+        else:
+            # 3xTF32 (ops.Linear3): every operand is split once into a TF32-exact part and a remainder;
+            # three tensor-core GEMMs reproduce the fp32 product to ~4e-6 relative
+            wih = ops.split_tf32(rnn.weight_ih_l0.detach())
+            whh = ops.split_tf32(rnn.weight_hh_l0.detach())
+            x_split = ops.split_tf32(x.detach()) if not x.requires_grad else None
+            gates_x = ops.Linear3.apply(x, rnn.weight_ih_l0, x_split, wih) + (rnn.bias_ih_l0 + rnn.bias_hh_l0)
+            for _ in range(self.c.num_obj):
+                gates_h = ops.Linear3.apply(h, rnn.weight_hh_l0, None, whh) if h is not None else None
+                h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
+                outs.append(h)
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
         return self.fc2(zps)
