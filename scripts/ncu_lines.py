@@ -46,8 +46,8 @@ def main():
     lines = sass_lines(obj, kernel)
     if len(lines) != len(sass):
         print('warning: %d SASS rows in the report vs %d in the object' % (len(sass), len(lines)))
-    src = open(sorted({l for l in re.findall(r'"(/[^"]+\.cu)"', subprocess.run(
-        ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda'], capture_output=True, text=True).stdout)})[0]).read().split('\n')
+    cu = os.path.splitext(obj)[0] + '.cu'
+    src = open(cu).read().split('\n') if os.path.exists(cu) else []
     agg = {}
     for r, l in zip(sass, lines):
         a = agg.setdefault(l, [0, 0, 0])

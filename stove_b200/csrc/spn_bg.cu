@@ -20,6 +20,45 @@ struct GPB_ {
     static constexpr int v = (G + 3) / 4 * 4;
 };
 
+// 16-byte asynchronous global -> shared copies (LDGSTS): every copy of a CTA is in flight at once,
+// so a parameter block costs one memory round trip instead of one per use (ncu: the leaf kernels
+// spent 12-17 cycles per issued instruction waiting on parameter loads from L2).
+__device__ __forceinline__ void bg_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void bg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void bg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// stage the leaf parameters and the side table of one pixel chunk: ps [BG_PXC * R * 3 * GP], ss [BG_PXC * R]
+template <int R, int GP>
+__device__ __forceinline__ void bg_stage_chunk_params(const float* __restrict__ leaf, const int32_t* __restrict__ side,
+                                                      int D, int c0, float* ps, int* ss) {
+    const int npx = min(BG_PXC, D - c0);
+    const int n4 = npx * R * 3 * GP / 4;
+    const float4* src = reinterpret_cast<const float4*>(leaf + (int64_t)c0 * R * 3 * GP);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) bg_cp_async16(reinterpret_cast<float4*>(ps) + i, src + i);
+    bg_cp_async_commit();
+    for (int i = threadIdx.x; i < npx * R; i += blockDim.x) ss[i] = __ldg(side + c0 * R + i);
+}
+
+template <int G>
+__device__ __forceinline__ void bg_params_smem(const float* lp, float (&mu)[GPB_<G>::v], float (&a)[GPB_<G>::v],
+                                               float (&b)[GPB_<G>::v]) {
+    constexpr int GP = GPB_<G>::v;
+    const float4* p4 = reinterpret_cast<const float4*>(lp);
+#pragma unroll
+    for (int v = 0; v < GP / 4; ++v) {
+        float4 t = p4[v];
+        mu[4 * v] = t.x; mu[4 * v + 1] = t.y; mu[4 * v + 2] = t.z; mu[4 * v + 3] = t.w;
+        t = p4[GP / 4 + v];
+        a[4 * v] = t.x; a[4 * v + 1] = t.y; a[4 * v + 2] = t.z; a[4 * v + 3] = t.w;
+        t = p4[2 * (GP / 4) + v];
+        b[4 * v] = t.x; b[4 * v + 1] = t.y; b[4 * v + 2] = t.z; b[4 * v + 3] = t.w;
+    }
+}
+
 template <int G>
 __device__ __forceinline__ void bg_load_params(const float* __restrict__ lp, float (&mu)[GPB_<G>::v],
                                                float (&a)[GPB_<G>::v], float (&b)[GPB_<G>::v]) {
@@ -55,6 +94,7 @@ __device__ __forceinline__ void bg_load_tile(const float* __restrict__ x, const 
                                              float* ms) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int px = c0 + lane;
+#pragma unroll 8
     for (int f = warp; f < BG_FR; f += nwarp) {
         const int64_t n = f0 + f;
         float xv = 0.f, wv = 0.f, mv = 0.f;
@@ -68,8 +108,9 @@ __device__ __forceinline__ void bg_load_tile(const float* __restrict__ x, const 
             }
         }
         xs[lane * (BG_FR + 1) + f] = xv;
-        ws[lane * (BG_FR + 1) + f] = wv;
-        if (KEEP_RAW) ms[lane * (BG_FR + 1) + f] = mv;
+        // KEEP_RAW: the backward needs "mask inside [0, 1]" (derivative of the clamp); it travels in the
+        // sign bit of the weight (-0.0f for a saturated mask) instead of a third tile
+        ws[lane * (BG_FR + 1) + f] = (KEEP_RAW && !(mv >= 0.f && mv <= 1.f)) ? -wv : wv;
     }
 }
 
@@ -84,9 +125,13 @@ __global__ void __launch_bounds__(BG_FR) spn1_fwd_leaf_kernel(
     constexpr int NI = R * 2 * G;
     __shared__ float xs[BG_PXC * (BG_FR + 1)];
     __shared__ float ws[BG_PXC * (BG_FR + 1)];
+    __shared__ __align__(16) float ps[BG_PXC * R * 3 * GP];
+    __shared__ int sides[BG_PXC * R];
     const int chunk = blockIdx.x, c0 = chunk * BG_PXC;
     const int64_t f0 = (int64_t)blockIdx.y * BG_FR;
+    bg_stage_chunk_params<R, GP>(leaf, side, D, c0, ps, sides);
     bg_load_tile<HAS_MARG, false>(x, marg, N, D, f0, c0, xs, ws, nullptr);
+    bg_cp_async_wait<0>();
     __syncthreads();
     const int f = threadIdx.x;
     float acc[R][2][G];
@@ -96,13 +141,12 @@ __global__ void __launch_bounds__(BG_FR) spn1_fwd_leaf_kernel(
         for (int g = 0; g < G; ++g) { acc[r][0][g] = 0.f; acc[r][1][g] = 0.f; }
     const int pend = min(BG_PXC, D - c0);
     for (int p = 0; p < pend; ++p) {
-        const int px = c0 + p;
         const float xv = xs[p * (BG_FR + 1) + f], wv = ws[p * (BG_FR + 1) + f];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int h = __ldg(side + px * R + r);
+            const int h = sides[p * R + r];
             float mu[GP], a[GP], b[GP];
-            bg_load_params<G>(leaf + ((int64_t)px * R + r) * 3 * GP, mu, a, b);
+            bg_params_smem<G>(ps + (p * R + r) * 3 * GP, mu, a, b);
             if (h) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
@@ -303,10 +347,13 @@ __global__ void __launch_bounds__(BG_FR) spn1_bwd_input_kernel(
     extern __shared__ float smem[];
     float* xs = smem;
     float* ws = xs + BG_PXC * (BG_FR + 1);
-    float* ms = ws + BG_PXC * (BG_FR + 1);
+    float* ps = ws + BG_PXC * (BG_FR + 1);                  // 16-byte aligned: 2 * 32 * 129 floats precede it
+    int* sides = reinterpret_cast<int*>(ps + BG_PXC * R * 3 * GP);
     const int chunk = blockIdx.x, c0 = chunk * BG_PXC;
     const int64_t f0 = (int64_t)blockIdx.y * BG_FR;
-    bg_load_tile<HAS_MARG, true>(x, marg, N, D, f0, c0, xs, ws, ms);
+    bg_stage_chunk_params<R, GP>(leaf, side, D, c0, ps, sides);
+    bg_load_tile<HAS_MARG, true>(x, marg, N, D, f0, c0, xs, ws, nullptr);
+    bg_cp_async_wait<0>();
     __syncthreads();
     const int f = threadIdx.x;
     const int64_t n = f0 + f;
@@ -320,14 +367,15 @@ __global__ void __launch_bounds__(BG_FR) spn1_bwd_input_kernel(
                 gl[r][h][g] = (n < N) ? gleaf[(int64_t)((r * 2 + h) * G + g) * npad + n] : 0.f;
     const int pend = min(BG_PXC, D - c0);
     for (int p = 0; p < pend; ++p) {
-        const int px = c0 + p;
-        const float xv = xs[p * (BG_FR + 1) + f], wv = ws[p * (BG_FR + 1) + f], mv = ms[p * (BG_FR + 1) + f];
+        const float xv = xs[p * (BG_FR + 1) + f], wraw = ws[p * (BG_FR + 1) + f];
+        const float wv = fabsf(wraw);
+        const bool inside = !signbit(wraw);
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int h = __ldg(side + px * R + r);
+            const int h = sides[p * R + r];
             float mu[GP], a[GP], b[GP];
-            bg_load_params<G>(leaf + ((int64_t)px * R + r) * 3 * GP, mu, a, b);
+            bg_params_smem<G>(ps + (p * R + r) * 3 * GP, mu, a, b);
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const float d = xv - mu[g];
@@ -338,7 +386,7 @@ __global__ void __launch_bounds__(BG_FR) spn1_bwd_input_kernel(
             }
         }
         xs[p * (BG_FR + 1) + f] = -2.f * wv * t1;
-        ws[p * (BG_FR + 1) + f] = (mv >= 0.f && mv <= 1.f) ? t2 : 0.f;
+        ws[p * (BG_FR + 1) + f] = inside ? t2 : 0.f;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -402,6 +450,110 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_kernel(
                     for (int g = 0; g < G; ++g) {
                         const float d = xv - mu[r][g];
                         const float gw = gls[hoff[r] + g * 33 + pt] * wv;
+                        s1[r][g] = fmaf(gw, d, s1[r][g]);
+                        s2[r][g] = fmaf(gw * d, d, s2[r][g]);
+                        s3[r][g] += gw;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float* dst = g_leaf + ((int64_t)px * R + r) * 3 * GP;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                atomicAdd(dst + g, 2.f * a[r][g] * s1[r][g]);
+                atomicAdd(dst + GP + g, -s2[r][g]);
+                atomicAdd(dst + 2 * GP + g, -s3[r][g]);
+            }
+        }
+    }
+}
+
+// Same mapping, but the [32 frames][128 pixels] frame / mask tiles and the leaf-vector gradients
+// stream through a two-stage cp.async pipeline (needs D % 4 == 0 for 16-byte copies).  The scalar
+// version above waits for two dependent global loads per frame with 4 warps per SM (ncu: 6 %
+// occupancy, 6.3 stall cycles per instruction on the load scoreboard).
+template <int R, int G, bool HAS_MARG>
+__global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
+    int D, const int32_t* __restrict__ side, int64_t N, int64_t npad, int chunk,
+    const float* __restrict__ x, const float* __restrict__ marg, const float* __restrict__ leaf,
+    const float* __restrict__ gleaf, float* __restrict__ g_leaf) {
+    constexpr int GP = GPB_<G>::v;
+    constexpr int NI = R * 2 * G;
+    constexpr int TILE = 32 * 128;
+    extern __shared__ __align__(16) float smem[];
+    float* xt = smem;                       // [2][32][128]
+    float* mt = xt + 2 * TILE;              // [2][32][128]
+    float* gt = mt + 2 * TILE;              // [2][NI][32]
+    const int tid = threadIdx.x;
+    const int px0 = blockIdx.x * 128, px = px0 + tid;
+    const bool active = px < D;
+    const int pxc = active ? px : 0;
+    float mu[R][G], a[R][G];
+    int hoff[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float* lp = leaf + ((int64_t)pxc * R + r) * 3 * GP;
+#pragma unroll
+        for (int g = 0; g < G; ++g) { mu[r][g] = lp[g]; a[r][g] = lp[GP + g]; }
+        hoff[r] = ((r * 2 + side[pxc * R + r]) * G) * 32;
+    }
+    float s1[R][G], s2[R][G], s3[R][G];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int g = 0; g < G; ++g) { s1[r][g] = 0.f; s2[r][g] = 0.f; s3[r][g] = 0.f; }
+    const int64_t c0 = (int64_t)blockIdx.y * chunk;
+    const int64_t c1 = min(c0 + (int64_t)chunk, N);
+    const int nb = (int)((c1 - c0 + 31) / 32);
+    const int cols4 = min(128, D - px0) / 4;          // float4 columns of this CTA's pixel slab
+    auto issue = [&](int b) {
+        const int st = b & 1;
+        const int64_t base = c0 + (int64_t)b * 32;
+        const int rows = (int)min((int64_t)32, c1 - base);
+        for (int i = tid; i < rows * 32; i += 128) {
+            const int pt = i >> 5, c4 = i & 31;
+            if (c4 < cols4) {
+                bg_cp_async16(xt + st * TILE + pt * 128 + c4 * 4, x + (base + pt) * D + px0 + c4 * 4);
+                if (HAS_MARG) bg_cp_async16(mt + st * TILE + pt * 128 + c4 * 4, marg + (base + pt) * D + px0 + c4 * 4);
+            }
+        }
+        // gradients of the leaf vectors: rows of 32 frames (npad is a multiple of 32, so rows past c1 exist)
+        for (int i = tid; i < NI * 8; i += 128) {
+            const int row = i >> 3, c4 = i & 7;
+            bg_cp_async16(gt + st * NI * 32 + row * 32 + c4 * 4, gleaf + (int64_t)row * npad + base + c4 * 4);
+        }
+        bg_cp_async_commit();
+    };
+    if (nb > 0) issue(0);
+    for (int b = 0; b < nb; ++b) {
+        if (b + 1 < nb) {
+            issue(b + 1);
+            bg_cp_async_wait<1>();
+        } else {
+            bg_cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (active) {
+            const int st = b & 1;
+            const int lim = (int)min((int64_t)32, c1 - (c0 + (int64_t)b * 32));
+            const float* xs = xt + st * TILE + tid;
+            const float* ms = mt + st * TILE + tid;
+            const float* gs = gt + st * NI * 32;
+#pragma unroll 2
+            for (int pt = 0; pt < lim; ++pt) {
+                const float xv = xs[pt * 128];
+                const float wv = HAS_MARG ? 1.f - fminf(fmaxf(ms[pt * 128], 0.f), 1.f) : 1.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const float d = xv - mu[r][g];
+                        const float gw = gs[hoff[r] + g * 32 + pt] * wv;
                         s1[r][g] = fmaf(gw, d, s1[r][g]);
                         s2[r][g] = fmaf(gw * d, d, s2[r][g]);
                         s3[r][g] += gw;
@@ -535,7 +687,7 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
                                                                            g_out, w.gleaf, w.aux_root, g_rlog));
     STOVE_LAUNCH_CHECK();
     if (g_x || g_marg) {
-        const size_t smem = sizeof(float) * 3 * BG_PXC * (BG_FR + 1);
+        const size_t smem = sizeof(float) * (2 * BG_PXC * (BG_FR + 1) + BG_PXC * 3 * 3 * 8 + BG_PXC * 3);
         dim3 grid(bg_nchunks(D), (unsigned)((N + BG_FR - 1) / BG_FR));
         if (marg) {
             STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_input_kernel<3, 6, true>,
@@ -553,7 +705,18 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     const int nchunk = (int)((N + chunk - 1) / chunk);
     {
         dim3 grid((D + 127) / 128, nchunk);
-        if (marg)
+        if (D % 4 == 0) {
+            const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 32);
+            if (marg) {
+                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_async_kernel<3, 6, true><<<grid, 128, smem, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_async_kernel<3, 6, false><<<grid, 128, smem, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
+        } else if (marg)
             STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         else
             STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));

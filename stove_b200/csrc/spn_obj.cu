@@ -14,6 +14,7 @@
 //     out[s] = m0 + m1 + log sum_{i,j} e0[i] e1[j] W[j*G+i][s],   e = exp(leaf - max)
 // (20 exp + 10 log instead of 1000 exp); if the linear sum falls below LIN_SUM_FLOOR the
 // value/gradient is recomputed exactly in the log domain (rare slow path).
+#include <stdlib.h>
 #include "common.cuh"
 
 struct Spn2Dev {
@@ -32,33 +33,49 @@ struct GP_ {
 // ------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------
-template <int G>
+// 16-byte asynchronous global -> shared copies.  ncu on the first version of these kernels: 7-13
+// stall cycles per issued instruction on the load scoreboard -- every (pixel, region) step waited
+// for its own leaf-parameter round trip to L2.  The kernels now stage the parameter blocks they
+// will walk through (leaf table, sum weights, scope indices) with cp.async while the patch tile
+// is loaded, and the inner loops read shared memory.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+__host__ __device__ static inline int up4(int v) { return (v + 3) & ~3; }
+
+// SMEM = the parameter block has been staged in shared memory (plain loads), else read-only global loads
+template <int G, bool SMEM = false>
 __device__ __forceinline__ void load_leaf_params(const float* __restrict__ lp, float (&mu)[GP_<G>::v],
                                                  float (&a)[GP_<G>::v], float (&b)[GP_<G>::v]) {
     constexpr int GP = GP_<G>::v;
     const float4* p4 = reinterpret_cast<const float4*>(lp);
 #pragma unroll
     for (int v = 0; v < GP / 4; ++v) {
-        float4 t = __ldg(p4 + v);
+        float4 t = SMEM ? p4[v] : __ldg(p4 + v);
         mu[4 * v] = t.x; mu[4 * v + 1] = t.y; mu[4 * v + 2] = t.z; mu[4 * v + 3] = t.w;
-        t = __ldg(p4 + GP / 4 + v);
+        t = SMEM ? p4[GP / 4 + v] : __ldg(p4 + GP / 4 + v);
         a[4 * v] = t.x; a[4 * v + 1] = t.y; a[4 * v + 2] = t.z; a[4 * v + 3] = t.w;
-        t = __ldg(p4 + 2 * (GP / 4) + v);
+        t = SMEM ? p4[2 * (GP / 4) + v] : __ldg(p4 + 2 * (GP / 4) + v);
         b[4 * v] = t.x; b[4 * v + 1] = t.y; b[4 * v + 2] = t.z; b[4 * v + 3] = t.w;
     }
 }
 
-template <int G>
+template <int G, bool SMEM>
 __device__ __forceinline__ void leaf_accumulate(float (&L)[G], const float* __restrict__ leaf_q,
                                                 const int32_t* __restrict__ sc, int p_begin, int p_end,
                                                 const float* xs, const float* ws, int lane) {
     constexpr int GP = GP_<G>::v;
+#pragma unroll 2
     for (int p = p_begin; p < p_end; ++p) {
-        const int px = __ldg(sc + p);
+        const int px = SMEM ? sc[p] : __ldg(sc + p);
         const float xv = xs[px * 33 + lane];
         const float wv = ws[px * 33 + lane];
         float mu[GP], a[GP], b[GP];
-        load_leaf_params<G>(leaf_q + (int64_t)p * 3 * GP, mu, a, b);
+        load_leaf_params<G, SMEM>(leaf_q + (int64_t)p * 3 * GP, mu, a, b);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const float d = xv - mu[g];
@@ -97,47 +114,67 @@ __device__ __noinline__ float slow_logsumexp(const float* in0, const float* in1,
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
-template <int G, int S, bool HAS_MARG>
-__global__ void __launch_bounds__(512) spn2_fwd_kernel(
+// A CTA owns `tpc` tiles of 32 patches (tpc * 2R warps): with one tile per CTA and the leaf table
+// staged (1 CTA per SM) 168 tiles ran as 148 + 20, i.e. two full CTA latencies; two tiles per CTA
+// share one staged table and finish in one wave.
+template <int G, int S, bool HAS_MARG, bool STAGE>
+__global__ void __launch_bounds__(1024) spn2_fwd_kernel(
     Spn2Dev st, int64_t N, int64_t npad, const float* __restrict__ x, const float* __restrict__ marg,
     const float* __restrict__ leaf, const float* __restrict__ wlin, const float* __restrict__ wlog,
     const float* __restrict__ rlin, const float* __restrict__ rlog, float* __restrict__ leaf_val,
     float* __restrict__ sum_val, float* __restrict__ out) {
     constexpr int GP = GP_<G>::v;
     constexpr int SP = GP_<S>::v;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int D = st.D, R = st.R, Q = 2 * st.R;
-    float* xs = smem;
-    float* ws = xs + D * 33;
-    float* ss = ws + D * 33;          // [Q*S][32]
-    float* vr = ss + Q * S * 32;      // [R][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t base = (int64_t)blockIdx.x * 32;
+    const int tpc = (blockDim.x >> 5) / Q, tile = warp / Q, q = warp - tile * Q;
+    const int per_tile = 2 * up4(D * 33) + Q * S * 32 + R * 32;
+    float* xs = smem + tile * per_tile;
+    float* ws = xs + up4(D * 33);
+    float* ss = ws + up4(D * 33);     // [Q*S][32]
+    float* vr = ss + Q * S * 32;      // [R][32]
+    float* lf = smem + tpc * per_tile;                                // STAGE: [Q][pmax*3*GP] leaf parameters
+    int32_t* scs = reinterpret_cast<int32_t*>(lf + Q * st.pmax * 3 * GP);   // STAGE: [Q][pmax] scope indices
+    const int64_t base = ((int64_t)blockIdx.x * tpc + tile) * 32;
+    const bool tile_ok = base < npad;
 
-    for (int idx = tid; idx < 32 * D; idx += blockDim.x) {
-        const int pt = idx / D, px = idx - pt * D;
-        const int64_t n = base + pt;
-        float xv = 0.f, wv = 1.f;
-        if (n < N) {
-            xv = __ldg(x + n * D + px);
-            if (HAS_MARG) wv = 1.f - fminf(fmaxf(__ldg(marg + n * D + px), 0.f), 1.f);
-        }
-        xs[px * 33 + pt] = xv;
-        ws[px * 33 + pt] = wv;
+    if (STAGE && tile == 0) {
+        // each warp of the first tile fetches the parameter block of its region; in flight during the tile load
+        const float4* src = reinterpret_cast<const float4*>(leaf + (int64_t)q * st.pmax * 3 * GP);
+        float4* dst = reinterpret_cast<float4*>(lf + q * st.pmax * 3 * GP);
+        for (int i = lane; i < st.pmax * 3 * GP / 4; i += 32) cp_async16(dst + i, src + i);
+        cp_async_commit();
+        for (int i = lane; i < st.pmax; i += 32) scs[q * st.pmax + i] = __ldg(st.scope + q * st.pmax + i);
     }
+    if (tile_ok) {
+        const int ttid = tid - tile * Q * 32, tthreads = Q * 32;
+#pragma unroll 4
+        for (int idx = ttid; idx < 32 * D; idx += tthreads) {
+            const int pt = idx / D, px = idx - pt * D;
+            const int64_t n = base + pt;
+            float xv = 0.f, wv = 1.f;
+            if (n < N) {
+                xv = __ldg(x + n * D + px);
+                if (HAS_MARG) wv = 1.f - fminf(fmaxf(__ldg(marg + n * D + px), 0.f), 1.f);
+            }
+            xs[px * 33 + pt] = xv;
+            ws[px * 33 + pt] = wv;
+        }
+    }
+    if (STAGE) cp_async_wait<0>();
     __syncthreads();
 
-    const int64_t n = base + lane;   // < npad always
-    if (warp < Q) {
-        const int q = warp;
+    const int64_t n = base + lane;   // < npad when tile_ok
+    if (tile_ok) {
         const int nq0 = __ldg(st.n0 + q), nq = __ldg(st.nt + q);
-        const int32_t* sc = st.scope + q * st.pmax;
-        const float* leaf_q = leaf + (int64_t)q * st.pmax * 3 * GP;
+        const int32_t* sc = STAGE ? scs + q * st.pmax : st.scope + q * st.pmax;
+        const float* leaf_q = STAGE ? lf + q * st.pmax * 3 * GP : leaf + (int64_t)q * st.pmax * 3 * GP;
         float L0[G], L1[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) { L0[g] = 0.f; L1[g] = 0.f; }
-        leaf_accumulate<G>(L0, leaf_q, sc, 0, nq0, xs, ws, lane);
-        leaf_accumulate<G>(L1, leaf_q, sc, nq0, nq, xs, ws, lane);
+        leaf_accumulate<G, STAGE>(L0, leaf_q, sc, 0, nq0, xs, ws, lane);
+        leaf_accumulate<G, STAGE>(L1, leaf_q, sc, nq0, nq, xs, ws, lane);
         float* lv = leaf_val + (int64_t)(q * 2) * G * npad + n;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -180,8 +217,8 @@ __global__ void __launch_bounds__(512) spn2_fwd_kernel(
         }
     }
     __syncthreads();
-    if (warp < R) {
-        const int r = warp;
+    if (tile_ok && q < R) {
+        const int r = q;
         float A[S], B[S], eA[S], eB[S];
 #pragma unroll
         for (int i = 0; i < S; ++i) {
@@ -208,7 +245,7 @@ __global__ void __launch_bounds__(512) spn2_fwd_kernel(
         vr[r * 32 + lane] = val;
     }
     __syncthreads();
-    if (warp == 0 && n < N) {
+    if (tile_ok && q == 0 && n < N) {
         float M = vr[lane];
         for (int r = 1; r < R; ++r) M = fmaxf(M, vr[r * 32 + lane]);
         float acc = 0.f;
@@ -235,7 +272,7 @@ __device__ __noinline__ void slow_sum_backward(const float* in0, const float* in
         }
 }
 
-template <int G, int S>
+template <int G, int S, bool STAGE>
 __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
     Spn2Dev st, int64_t N, int64_t npad, const float* __restrict__ wlin, const float* __restrict__ wlog,
     const float* __restrict__ rlin, const float* __restrict__ rlog, const float* __restrict__ leaf_val,
@@ -247,14 +284,22 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
     const int R = st.R, Q = 2 * st.R;
     float* ss = smem;                 // [Q*S][32] sum values
     float* gsm = ss + Q * S * 32;     // [Q*S][32] their gradients
+    float* wl = gsm + Q * S * 32;     // STAGE: [Q][G*G*SP] sum weights
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * 32;
     const int64_t n = base + lane;
+    if (STAGE && warp < Q) {
+        const float4* wsrc = reinterpret_cast<const float4*>(wlin + (int64_t)warp * G * G * SP);
+        float4* wdst = reinterpret_cast<float4*>(wl + warp * G * G * SP);
+        for (int i = lane; i < G * G * SP / 4; i += 32) cp_async16(wdst + i, wsrc + i);
+        cp_async_commit();
+    }
 
     for (int idx = tid; idx < Q * S * 32; idx += blockDim.x) {
         const int row = idx >> 5, pt = idx & 31;
         ss[idx] = sum_val[(int64_t)row * npad + base + pt];
     }
+    if (STAGE) cp_async_wait<0>();
     __syncthreads();
     if (warp < R) {
         const int r = warp;
@@ -330,7 +375,8 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
         float T[S], qv[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) T[s] = 0.f;
-        const float4* wq = reinterpret_cast<const float4*>(wlin + (int64_t)q * G * G * SP);
+        const float4* wq = STAGE ? reinterpret_cast<const float4*>(wl + q * G * G * SP)
+                                 : reinterpret_cast<const float4*>(wlin + (int64_t)q * G * G * SP);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
 #pragma unroll
@@ -339,7 +385,7 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
                 const int k = j * G + i;
 #pragma unroll
                 for (int v = 0; v < SP / 4; ++v) {
-                    const float4 w = __ldg(wq + k * (SP / 4) + v);
+                    const float4 w = STAGE ? wq[k * (SP / 4) + v] : __ldg(wq + k * (SP / 4) + v);
                     if (4 * v + 0 < S) T[4 * v + 0] = fmaf(pk, w.x, T[4 * v + 0]);
                     if (4 * v + 1 < S) T[4 * v + 1] = fmaf(pk, w.y, T[4 * v + 1]);
                     if (4 * v + 2 < S) T[4 * v + 2] = fmaf(pk, w.z, T[4 * v + 2]);
@@ -369,7 +415,7 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
                 float v = 0.f;
 #pragma unroll
                 for (int u = 0; u < SP / 4; ++u) {
-                    const float4 w = __ldg(wq + k * (SP / 4) + u);
+                    const float4 w = STAGE ? wq[k * (SP / 4) + u] : __ldg(wq + k * (SP / 4) + u);
                     if (4 * u + 0 < S) v = fmaf(qv[4 * u + 0], w.x, v);
                     if (4 * u + 1 < S) v = fmaf(qv[4 * u + 1], w.y, v);
                     if (4 * u + 2 < S) v = fmaf(qv[4 * u + 2], w.z, v);
@@ -409,68 +455,94 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
 // a pixel belongs to exactly one leaf per repetition (pix_slot), so no atomics.
 //   L = -w (a d^2 + b):  dL/dx = -2 w a d,  dL/dw = -(a d^2 + b),  w = 1 - clamp(m)
 // ------------------------------------------------------------------------------------
-template <int G, bool HAS_MARG>
-__global__ void __launch_bounds__(256) spn2_bwd_input_kernel(
+// A CTA owns `tpc` tiles of 32 patches (16 warps each) that share one staged leaf table.
+template <int G, bool HAS_MARG, bool STAGE>
+__global__ void __launch_bounds__(1024) spn2_bwd_input_kernel(
     Spn2Dev st, int64_t N, int64_t npad, const float* __restrict__ x, const float* __restrict__ marg,
     const float* __restrict__ leaf, const float* __restrict__ gleaf, float* __restrict__ g_x,
     float* __restrict__ g_marg) {
     constexpr int GP = GP_<G>::v;
-    extern __shared__ float smem[];
+    constexpr int TW = 16;                          // warps per tile
+    extern __shared__ __align__(16) float smem[];
     const int D = st.D, R = st.R, Q = 2 * st.R;
-    float* xs = smem;
-    float* ws = xs + D * 33;
-    float* ms = ws + D * 33;
-    float* gl = ms + D * 33;          // [Q*2*G][32]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int64_t base = (int64_t)blockIdx.x * 32;
-
-    for (int idx = tid; idx < 32 * D; idx += blockDim.x) {
-        const int pt = idx / D, px = idx - pt * D;
-        const int64_t n = base + pt;
-        float xv = 0.f, mv = 0.f;
-        if (n < N) {
-            xv = __ldg(x + n * D + px);
-            if (HAS_MARG) mv = __ldg(marg + n * D + px);
-        }
-        xs[px * 33 + pt] = xv;
-        ms[px * 33 + pt] = mv;
-        ws[px * 33 + pt] = 1.f - fminf(fmaxf(mv, 0.f), 1.f);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tpc = (blockDim.x >> 5) / TW, tile = warp / TW, tw = warp - tile * TW;
+    const int per_tile = 2 * up4(D * 33) + Q * 2 * G * 32;
+    float* xs = smem + tile * per_tile;
+    float* ws = xs + up4(D * 33);     // weight 1 - clamp(mask); sign bit set = mask outside [0, 1]
+    float* gl = ws + up4(D * 33);     // [Q*2*G][32]
+    float* lf = smem + tpc * per_tile;   // STAGE: the whole leaf table [Q*pmax][3*GP]
+    int32_t* slots = reinterpret_cast<int32_t*>(lf + Q * st.pmax * 3 * GP);   // STAGE: [D*R] pixel -> slot
+    __shared__ int n0s[16];
+    const int64_t base = ((int64_t)blockIdx.x * tpc + tile) * 32;
+    const bool tile_ok = base < npad;
+    if (tid < Q) n0s[tid] = __ldg(st.n0 + tid);
+    if (STAGE) {
+        const float4* src = reinterpret_cast<const float4*>(leaf);
+        float4* dst = reinterpret_cast<float4*>(lf);
+        for (int i = tid; i < Q * st.pmax * 3 * GP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
+        cp_async_commit();
+        for (int i = tid; i < D * R; i += blockDim.x) slots[i] = __ldg(st.slot + i);
     }
-    for (int idx = tid; idx < Q * 2 * G * 32; idx += blockDim.x) {
-        const int row = idx >> 5, pt = idx & 31;
-        gl[idx] = gleaf[(int64_t)row * npad + base + pt];
-    }
-    __syncthreads();
-    for (int px = warp; px < D; px += nwarp) {
-        const float xv = xs[px * 33 + lane], wv = ws[px * 33 + lane], mv = ms[px * 33 + lane];
-        float t1 = 0.f, t2 = 0.f;
-        for (int r = 0; r < R; ++r) {
-            const int slot = __ldg(st.slot + px * R + r);
-            const int q = slot / st.pmax, p = slot - q * st.pmax;
-            const int h = (p >= __ldg(st.n0 + q)) ? 1 : 0;
-            float mu[GP], a[GP], b[GP];
-            load_leaf_params<G>(leaf + (int64_t)slot * 3 * GP, mu, a, b);
-            const float* glb = gl + ((q * 2 + h) * G) * 32 + lane;
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const float d = xv - mu[g];
-                const float ad = a[g] * d;
-                const float gv = glb[g * 32];
-                t1 = fmaf(gv, ad, t1);
-                t2 = fmaf(gv, fmaf(ad, d, b[g]), t2);
+    const int ttid = tid - tile * TW * 32, tthreads = TW * 32;
+    if (tile_ok) {
+#pragma unroll 4
+        for (int idx = ttid; idx < 32 * D; idx += tthreads) {
+            const int pt = idx / D, px = idx - pt * D;
+            const int64_t n = base + pt;
+            float xv = 0.f, mv = 0.f;
+            if (n < N) {
+                xv = __ldg(x + n * D + px);
+                if (HAS_MARG) mv = __ldg(marg + n * D + px);
             }
+            const float wv = 1.f - fminf(fmaxf(mv, 0.f), 1.f);
+            xs[px * 33 + pt] = xv;
+            ws[px * 33 + pt] = (mv >= 0.f && mv <= 1.f) ? wv : -wv;
         }
-        // reuse the tile in place: every (px, lane) entry is owned by exactly one thread
-        xs[px * 33 + lane] = -2.f * wv * t1;
-        ws[px * 33 + lane] = (mv >= 0.f && mv <= 1.f) ? t2 : 0.f;
+        for (int idx = ttid; idx < Q * 2 * G * 32; idx += tthreads) {
+            const int row = idx >> 5, pt = idx & 31;
+            gl[idx] = gleaf[(int64_t)row * npad + base + pt];
+        }
+    }
+    if (STAGE) cp_async_wait<0>();
+    __syncthreads();
+    if (tile_ok) {
+        for (int px = tw; px < D; px += TW) {
+            const float xv = xs[px * 33 + lane], wraw = ws[px * 33 + lane];
+            const float wv = fabsf(wraw);
+            const bool inside = !signbit(wraw);
+            float t1 = 0.f, t2 = 0.f;
+            for (int r = 0; r < R; ++r) {
+                const int slot = STAGE ? slots[px * R + r] : __ldg(st.slot + px * R + r);
+                const int q = slot / st.pmax, p = slot - q * st.pmax;
+                const int h = (p >= n0s[q]) ? 1 : 0;
+                float mu[GP], a[GP], b[GP];
+                if (STAGE) load_leaf_params<G, true>(lf + slot * 3 * GP, mu, a, b);
+                else load_leaf_params<G, false>(leaf + (int64_t)slot * 3 * GP, mu, a, b);
+                const float* glb = gl + ((q * 2 + h) * G) * 32 + lane;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float d = xv - mu[g];
+                    const float ad = a[g] * d;
+                    const float gv = glb[g * 32];
+                    t1 = fmaf(gv, ad, t1);
+                    t2 = fmaf(gv, fmaf(ad, d, b[g]), t2);
+                }
+            }
+            // reuse the tile in place: every (px, lane) entry is owned by exactly one thread
+            xs[px * 33 + lane] = -2.f * wv * t1;
+            ws[px * 33 + lane] = inside ? t2 : 0.f;
+        }
     }
     __syncthreads();
-    for (int idx = tid; idx < 32 * D; idx += blockDim.x) {
-        const int pt = idx / D, px = idx - pt * D;
-        const int64_t n = base + pt;
-        if (n < N) {
-            if (g_x) g_x[n * D + px] = xs[px * 33 + pt];
-            if (HAS_MARG && g_marg) g_marg[n * D + px] = ws[px * 33 + pt];
+    if (tile_ok) {
+        for (int idx = ttid; idx < 32 * D; idx += tthreads) {
+            const int pt = idx / D, px = idx - pt * D;
+            const int64_t n = base + pt;
+            if (n < N) {
+                if (g_x) g_x[n * D + px] = xs[px * 33 + pt];
+                if (HAS_MARG && g_marg) g_marg[n * D + px] = ws[px * 33 + pt];
+            }
         }
     }
 }
@@ -526,6 +598,87 @@ __global__ void __launch_bounds__(1024) spn2_bwd_leafparam_kernel(
             for (int pt = 0; pt < 32; ++pt) {
                 const float d = xs[pt * (D + 1) + px] - mu;
                 const float gw = gls[hg * 33 + pt] * ws[pt * (D + 1) + px];
+                s1 = fmaf(gw, d, s1);
+                s2 = fmaf(gw * d, d, s2);
+                s3 += gw;
+            }
+        }
+        __syncthreads();
+    }
+    if (active) {
+        float* dst = g_leaf + ((int64_t)q * st.pmax + p) * 3 * GP;
+        atomicAdd(dst + g, 2.f * a * s1);
+        atomicAdd(dst + GP + g, -s2);
+        atomicAdd(dst + 2 * GP + g, -s3);
+    }
+}
+
+// Same mapping with the patch / mask tiles and the leaf-vector gradients streamed through a
+// two-stage cp.async pipeline (needs D % 4 == 0).
+template <int G, bool HAS_MARG>
+__global__ void __launch_bounds__(1024) spn2_bwd_leafparam_async_kernel(
+    Spn2Dev st, int64_t N, int64_t npad, int chunk, const float* __restrict__ x,
+    const float* __restrict__ marg, const float* __restrict__ leaf, const float* __restrict__ gleaf,
+    float* __restrict__ g_leaf) {
+    constexpr int GP = GP_<G>::v;
+    extern __shared__ __align__(16) float smem[];
+    const int D = st.D, TILE = 32 * D;
+    float* xt = smem;                     // [2][32][D]
+    float* mt = xt + 2 * TILE;            // [2][32][D]
+    float* gt = mt + 2 * TILE;            // [2][2G][32]
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nq0 = st.n0[q], nq = st.nt[q];
+    const bool active = tid < nq * G;
+    const int p = active ? tid / G : 0, g = active ? tid - (tid / G) * G : 0;
+    const int px = st.scope[q * st.pmax + p];
+    const int hg = ((p >= nq0) ? G : 0) + g;
+    const float* lp = leaf + ((int64_t)q * st.pmax + p) * 3 * GP;
+    const float mu = lp[g], a = lp[GP + g];
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int64_t c0 = (int64_t)blockIdx.y * chunk;
+    const int64_t c1 = min(c0 + (int64_t)chunk, N);
+    const int nb = (int)((c1 - c0 + 31) / 32);
+    auto issue = [&](int b) {
+        const int stg = b & 1;
+        const int64_t base = c0 + (int64_t)b * 32;
+        const int rows = (int)min((int64_t)32, c1 - base);
+        // rows of a tile are contiguous in x / marg: one linear copy of rows * D floats
+        const float4* xsrc = reinterpret_cast<const float4*>(x + base * D);
+        const float4* msrc = reinterpret_cast<const float4*>(marg + base * D);
+        float4* xdst = reinterpret_cast<float4*>(xt + stg * TILE);
+        float4* mdst = reinterpret_cast<float4*>(mt + stg * TILE);
+        for (int i = tid; i < rows * D / 4; i += blockDim.x) {
+            cp_async16(xdst + i, xsrc + i);
+            if (HAS_MARG) cp_async16(mdst + i, msrc + i);
+        }
+        for (int i = tid; i < 2 * G * 8; i += blockDim.x) {
+            const int row = i >> 3, c4 = i & 7;
+            cp_async16(gt + stg * 2 * G * 32 + row * 32 + c4 * 4,
+                       gleaf + (int64_t)((q * 2) * G + row) * npad + base + c4 * 4);
+        }
+        cp_async_commit();
+    };
+    if (nb > 0) issue(0);
+    for (int b = 0; b < nb; ++b) {
+        if (b + 1 < nb) {
+            issue(b + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (active) {
+            const int stg = b & 1;
+            const int lim = (int)min((int64_t)32, c1 - (c0 + (int64_t)b * 32));
+            const float* xs = xt + stg * TILE + px;
+            const float* ms = mt + stg * TILE + px;
+            const float* gs = gt + stg * 2 * G * 32 + hg * 32;
+#pragma unroll 8
+            for (int pt = 0; pt < lim; ++pt) {
+                const float d = xs[pt * D] - mu;
+                const float wv = HAS_MARG ? 1.f - fminf(fmaxf(ms[pt * D], 0.f), 1.f) : 1.f;
+                const float gw = gs[pt] * wv;
                 s1 = fmaf(gw, d, s1);
                 s2 = fmaf(gw * d, d, s2);
                 s3 += gw;
@@ -643,19 +796,27 @@ static int spn2_fwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
                            const float* rlog, float* leaf_val, float* sum_val, float* out, cudaStream_t s) {
     const int Q = 2 * st->R;
     const int64_t npad = round_up64(N, 32);
-    const size_t smem = sizeof(float) * ((size_t)2 * st->D * 33 + (size_t)Q * S * 32 + (size_t)st->R * 32);
-    const int blocks = (int)(npad / 32), threads = 32 * Q;
+    constexpr int GP = GP_<G>::v;
+    const int ntiles = (int)(npad / 32);
+    const size_t per_tile = sizeof(float) * ((size_t)2 * up4(st->D * 33) + (size_t)Q * S * 32 + (size_t)st->R * 32);
+    const size_t stage_extra = sizeof(float) * ((size_t)Q * st->pmax * 3 * GP + (size_t)Q * st->pmax);
+    // two tiles per CTA once there are more tiles than SMs (one wave instead of 1 + a tail)
+    int tpc = (ntiles > 148 && 2 * Q * 32 <= 1024) ? 2 : 1;
+    if (tpc * per_tile + stage_extra > 227 * 1024) tpc = 1;
+    const bool stage = tpc * per_tile + stage_extra <= 227 * 1024;   // else: parameters straight from L2
+    const size_t smem = tpc * per_tile + (stage ? stage_extra : 0);
+    const int blocks = (ntiles + tpc - 1) / tpc, threads = 32 * Q * tpc;
     Spn2Dev d = to_dev(st);
     int rc;
-    if (marg) {
-        if ((rc = set_smem(spn2_fwd_kernel<G, S, true>, smem))) return rc;
-        STOVE_KERNEL(K_SPN2_FWD, s, spn2_fwd_kernel<G, S, true><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
-                                                                  rlog, leaf_val, sum_val, out));
-    } else {
-        if ((rc = set_smem(spn2_fwd_kernel<G, S, false>, smem))) return rc;
-        STOVE_KERNEL(K_SPN2_FWD, s, spn2_fwd_kernel<G, S, false><<<blocks, threads, smem, s>>>(d, N, npad, x, marg, leaf, wlin, wlog, rlin,
-                                                                   rlog, leaf_val, sum_val, out));
-    }
+#define SPN2_FWD_LAUNCH(M_, ST_)                                                                               \
+    do {                                                                                                       \
+        if ((rc = set_smem(spn2_fwd_kernel<G, S, M_, ST_>, smem))) return rc;                                  \
+        STOVE_KERNEL(K_SPN2_FWD, s, spn2_fwd_kernel<G, S, M_, ST_><<<blocks, threads, smem, s>>>(              \
+            d, N, npad, x, marg, leaf, wlin, wlog, rlin, rlog, leaf_val, sum_val, out));                       \
+    } while (0)
+    if (marg) { if (stage) SPN2_FWD_LAUNCH(true, true); else SPN2_FWD_LAUNCH(true, false); }
+    else { if (stage) SPN2_FWD_LAUNCH(false, true); else SPN2_FWD_LAUNCH(false, false); }
+#undef SPN2_FWD_LAUNCH
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -692,22 +853,42 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     const int blocks = (int)(npad / 32);
     int rc;
     {
-        const size_t smem = sizeof(float) * (size_t)2 * Q * S * 32;
-        if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S>, smem))) return rc;
-        STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S><<<blocks, 32 * Q, smem, s>>>(d, N, npad, wlin, wlog, rlin, rlog, leaf_val,
-                                                                  sum_val, out, g_out, w.gleaf, w.aux_reg,
-                                                                  w.aux_root, g_wlog, g_rlog));
+        constexpr int SP = GP_<S>::v;
+        const size_t base_smem = sizeof(float) * (size_t)2 * Q * S * 32;
+        const size_t stage_smem = base_smem + sizeof(float) * (size_t)Q * G * G * SP;
+        // staging the sum weights is compiled in but not selected: with the weights in shared memory ptxas
+        // hoists all 600 LDS.128 of the two unrolled product loops and spills 7.6 KB per thread (3.7x slower)
+        if (stage_smem <= 227 * 1024 && getenv("STOVE_SPN2_NODES_STAGE")) {
+            if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S, true>, stage_smem))) return rc;
+            STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S, true><<<blocks, 32 * Q, stage_smem, s>>>(
+                d, N, npad, wlin, wlog, rlin, rlog, leaf_val, sum_val, out, g_out, w.gleaf, w.aux_reg, w.aux_root,
+                g_wlog, g_rlog));
+        } else {
+            if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S, false>, base_smem))) return rc;
+            STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S, false><<<blocks, 32 * Q, base_smem, s>>>(
+                d, N, npad, wlin, wlog, rlin, rlog, leaf_val, sum_val, out, g_out, w.gleaf, w.aux_reg, w.aux_root,
+                g_wlog, g_rlog));
+        }
         STOVE_LAUNCH_CHECK();
     }
     if (g_x || g_marg) {
-        const size_t smem = sizeof(float) * ((size_t)3 * D * 33 + (size_t)Q * 2 * G * 32);
-        if (marg) {
-            if ((rc = set_smem(spn2_bwd_input_kernel<G, true>, smem))) return rc;
-            STOVE_KERNEL(K_SPN2_BWD_INPUT, s, spn2_bwd_input_kernel<G, true><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
-        } else {
-            if ((rc = set_smem(spn2_bwd_input_kernel<G, false>, smem))) return rc;
-            STOVE_KERNEL(K_SPN2_BWD_INPUT, s, spn2_bwd_input_kernel<G, false><<<blocks, 256, smem, s>>>(d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));
-        }
+        constexpr int GP = GP_<G>::v;
+        const size_t per_tile = sizeof(float) * ((size_t)2 * up4(D * 33) + (size_t)Q * 2 * G * 32);
+        const size_t stage_extra = sizeof(float) * ((size_t)Q * st->pmax * 3 * GP + (size_t)D * st->R);
+        int tpc = blocks > 148 ? 2 : 1;
+        if (tpc * per_tile + stage_extra > 227 * 1024) tpc = 1;
+        const bool stage = tpc * per_tile + stage_extra <= 227 * 1024;
+        const size_t smem = tpc * per_tile + (stage ? stage_extra : 0);
+        const int in_blocks = (blocks + tpc - 1) / tpc, in_threads = 512 * tpc;
+#define SPN2_BWD_INPUT_LAUNCH(M_, ST_)                                                                      \
+    do {                                                                                                    \
+        if ((rc = set_smem(spn2_bwd_input_kernel<G, M_, ST_>, smem))) return rc;                            \
+        STOVE_KERNEL(K_SPN2_BWD_INPUT, s, spn2_bwd_input_kernel<G, M_, ST_><<<in_blocks, in_threads, smem, s>>>( \
+            d, N, npad, x, marg, leaf, w.gleaf, g_x, g_marg));                                              \
+    } while (0)
+        if (marg) { if (stage) SPN2_BWD_INPUT_LAUNCH(true, true); else SPN2_BWD_INPUT_LAUNCH(true, false); }
+        else { if (stage) SPN2_BWD_INPUT_LAUNCH(false, true); else SPN2_BWD_INPUT_LAUNCH(false, false); }
+#undef SPN2_BWD_INPUT_LAUNCH
         STOVE_LAUNCH_CHECK();
     }
     // chunk the patch axis so that the grid has a few hundred CTAs
@@ -717,14 +898,25 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     {
         const int threads = round_up(st->pmax * G, 32);
         STOVE_CHECK_ARG(threads <= 1024, "region too large for the leaf-gradient kernel");
-        const size_t smem = sizeof(float) * ((size_t)2 * 32 * (D + 1) + (size_t)2 * G * 33);
         dim3 grid(Q, nchunk);
-        if (marg) {
-            if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
-            STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+        const size_t smem_async = sizeof(float) * ((size_t)4 * 32 * D + (size_t)2 * 2 * G * 32);
+        if (D % 4 == 0 && smem_async <= 227 * 1024) {
+            if (marg) {
+                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, true>, smem_async))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_async_kernel<G, true><<<grid, threads, smem_async, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, false>, smem_async))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_async_kernel<G, false><<<grid, threads, smem_async, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
         } else {
-            if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
-            STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            const size_t smem = sizeof(float) * ((size_t)2 * 32 * (D + 1) + (size_t)2 * G * 33);
+            if (marg) {
+                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
         }
         STOVE_LAUNCH_CHECK();
     }
