@@ -84,6 +84,48 @@ extern "C" int stove_profile_read(int32_t* ids, float* ms, int max_n) {
     return n;
 }
 
+// ---- fork/join helper ---------------------------------------------------------------------
+static StoveFork g_forks[16][STOVE_FORK_FAMILIES];
+static bool g_fork_ok[16][STOVE_FORK_FAMILIES];
+
+StoveFork* stove_fork_get(int family) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16 || family < 0 || family >= STOVE_FORK_FAMILIES) {
+        stove_set_error("stove_fork_get: bad device / family");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    StoveFork* f = &g_forks[dev][family];
+    if (!g_fork_ok[dev][family]) {
+        bool ok = true;
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = cudaStreamCreateWithFlags(&f->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&f->join_ev[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        ok = ok && cudaEventCreateWithFlags(&f->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            stove_set_error("stove_fork_get: cannot create side streams");
+            return nullptr;
+        }
+        g_fork_ok[dev][family] = true;
+    }
+    return f;
+}
+
+int stove_fork(StoveFork* f, cudaStream_t s, int nside) {
+    STOVE_CUDA(cudaEventRecord(f->fork_ev, s));
+    for (int i = 0; i < nside; ++i) STOVE_CUDA(cudaStreamWaitEvent(f->side[i], f->fork_ev, 0));
+    return STOVE_OK;
+}
+
+int stove_join(StoveFork* f, cudaStream_t s, int nside) {
+    for (int i = 0; i < nside; ++i) {
+        STOVE_CUDA(cudaEventRecord(f->join_ev[i], f->side[i]));
+        STOVE_CUDA(cudaStreamWaitEvent(s, f->join_ev[i], 0));
+    }
+    return STOVE_OK;
+}
+
 extern "C" const char* stove_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : "?"; }
 extern "C" int stove_kernel_count(void) { return K_COUNT; }
 extern "C" int64_t stove_launch_count(int reset) {

@@ -44,6 +44,20 @@ void stove_prof_end(int slot, cudaStream_t s);
 
 #define STOVE_LAUNCH_CHECK() STOVE_CUDA(cudaGetLastError())
 
+// Fork/join of independent kernels inside one library call: `fork` makes up to two library-owned side
+// streams wait for everything issued so far on the caller's stream, `join` makes the caller's stream
+// wait for them.  Works eagerly and under stream capture (the branches become parallel graph nodes).
+// `family` selects a private set of streams/events (0 = object SPN, 1 = background SPN, ...), so two
+// callers on different streams do not serialise each other.
+#define STOVE_FORK_FAMILIES 4
+struct StoveFork {
+    cudaStream_t side[2];
+    cudaEvent_t fork_ev, join_ev[2];
+};
+StoveFork* stove_fork_get(int family);          // nullptr on failure (error string set)
+int stove_fork(StoveFork* f, cudaStream_t s, int nside);
+int stove_join(StoveFork* f, cudaStream_t s, int nside);
+
 static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 

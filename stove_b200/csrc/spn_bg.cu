@@ -10,6 +10,7 @@
 // parameters are broadcast float4 loads shared by all 128 frames; the frame tile is staged
 // transposed in shared memory.  Partial leaf sums per chunk are combined by a per-frame
 // root kernel in a fixed order (deterministic).
+#include <stdlib.h>
 #include "common.cuh"
 
 #define BG_PXC 32      // pixels per chunk
@@ -686,6 +687,9 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     STOVE_KERNEL(K_SPN1_BWD_ROOT, s, spn1_bwd_root_kernel<3, 6><<<(unsigned)((npad + 127) / 128), 128, 0, s>>>(N, npad, rlin, rlog, leaf_val, out,
                                                                            g_out, w.gleaf, w.aux_root, g_rlog));
     STOVE_LAUNCH_CHECK();
+    StoveFork* fk = getenv("STOVE_NO_FORK") ? nullptr : stove_fork_get(1);
+    if (fk && (rc = stove_fork(fk, s, 2))) return rc;
+    cudaStream_t s_leaf = fk ? fk->side[0] : s, s_root = fk ? fk->side[1] : s;
     if (g_x || g_marg) {
         const size_t smem = sizeof(float) * (2 * BG_PXC * (BG_FR + 1) + BG_PXC * 3 * 3 * 8 + BG_PXC * 3);
         dim3 grid(bg_nchunks(D), (unsigned)((N + BG_FR - 1) / BG_FR));
@@ -710,22 +714,23 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
             if (marg) {
                 STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, true>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_async_kernel<3, 6, true><<<grid, 128, smem, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, true><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             } else {
                 STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, false>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_async_kernel<3, 6, false><<<grid, 128, smem, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, false><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             }
         } else if (marg)
-            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         else
-            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         STOVE_LAUNCH_CHECK();
     }
     {
         dim3 grid(st->R, nchunk);
-        STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
+        STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s_root, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s_root>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
+    if (fk && (rc = stove_join(fk, s, 2))) return rc;
     return STOVE_OK;
 }

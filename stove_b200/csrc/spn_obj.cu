@@ -871,6 +871,11 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         }
         STOVE_LAUNCH_CHECK();
     }
+    // the three remaining kernels only depend on the node pass: input gradients stay on the caller's
+    // stream, the two parameter-gradient kernels run on side streams
+    StoveFork* fk = getenv("STOVE_NO_FORK") ? nullptr : stove_fork_get(0);
+    if (fk && (rc = stove_fork(fk, s, 2))) return rc;
+    cudaStream_t s_leaf = fk ? fk->side[0] : s, s_sum = fk ? fk->side[1] : s;
     if (g_x || g_marg) {
         constexpr int GP = GP_<G>::v;
         const size_t per_tile = sizeof(float) * ((size_t)2 * up4(D * 33) + (size_t)Q * 2 * G * 32);
@@ -903,19 +908,19 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         if (D % 4 == 0 && smem_async <= 227 * 1024) {
             if (marg) {
                 if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, true>, smem_async))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_async_kernel<G, true><<<grid, threads, smem_async, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, true><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             } else {
                 if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, false>, smem_async))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_async_kernel<G, false><<<grid, threads, smem_async, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, false><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             }
         } else {
             const size_t smem = sizeof(float) * ((size_t)2 * 32 * (D + 1) + (size_t)2 * G * 33);
             if (marg) {
                 if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             } else {
                 if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
             }
         }
         STOVE_LAUNCH_CHECK();
@@ -924,9 +929,10 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         const int need = (G * G > S * S) ? G * G : S * S;
         STOVE_CHECK_ARG(need <= 256, "G*G or S*S > 256");
         dim3 grid(Q + st->R, nchunk);
-        STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
+        STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s_sum, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s_sum>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
+    if (fk && (rc = stove_join(fk, s, 2))) return rc;
     return STOVE_OK;
 }
 

@@ -61,6 +61,18 @@ class Supair(nn.Module):
             cache[k] = torch.tensor(values, device=like.device, dtype=like.dtype)
         return cache[k]
 
+    def _side_stream(self, device):
+        """A second CUDA stream (per device) for work that is independent of the main chain: the
+        background SPN runs there while the object SPN runs on the current stream -- both are
+        short, latency-bound launches that leave most SMs idle on their own.  autograd replays
+        each op's backward on the stream of its forward, so the two backward chains overlap too;
+        a CUDA-graph capture records the fork/join as parallel branches."""
+        cache = self.__dict__.setdefault('_streams', {})
+        key = (device.type, device.index)
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(device=device)
+        return cache[key]
+
     # -- likelihood ----------------------------------------------------------------------
     def likelihood_raw(self, x_img, z_img, packed=None):
         """x_img (F, c, w, h), z_img (F, O, 4) [sx, sy, x, y] -> background log-likelihood (F,), RAW
@@ -71,15 +83,21 @@ class Supair(nn.Module):
         patches, marg_patch, marg_bg, overlap = ops.Scene.apply(
             x_img, z_img, c.patch_width, c.patch_height, self._align())
         img_flat, marg_flat = x_img.flatten(start_dim=1), marg_bg.flatten(start_dim=1)
-        if pk_bg is not None:
-            bg_loglik = self.bg_spn.forward_packed(pk_bg, img_flat, marg_flat)[:, 0]
-        else:
-            bg_loglik = self.bg_spn.forward(img_flat, marg_flat)[:, 0]
+        cur = torch.cuda.current_stream(x_img.device)
+        side = self._side_stream(x_img.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            if pk_bg is not None:
+                bg_loglik = self.bg_spn.forward_packed(pk_bg, img_flat, marg_flat)[:, 0]
+            else:
+                bg_loglik = self.bg_spn.forward(img_flat, marg_flat)[:, 0]
         patches_flat, marginalise_flat = patches.flatten(start_dim=1), marg_patch.flatten(start_dim=1)
         if pk_obj is not None:
             patches_loglik = self.obj_spn.forward_packed(pk_obj, patches_flat, marginalise_flat)[:, 0]
         else:
             patches_loglik = self.obj_spn.forward(patches_flat, marginalise_flat)[:, 0]
+        cur.wait_stream(side)
+        bg_loglik.record_stream(cur)
         extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marginalise_flat,
                      marginalise_bg=marg_bg)
         return bg_loglik, patches_loglik, overlap, extra
