@@ -228,8 +228,14 @@ class Stove(nn.Module):
         c = self.c
         n, T = x.shape[0], x.shape[1]
         skip, cl, O = c.skip, c.cl, c.num_obj
-        packed_spn = self.sup.pack()
-        packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
+        # parameter packing (~20 short launches; and its backward) is independent of the frames: it runs
+        # on a side stream next to the encoder and is joined right before the dynamics loop
+        cur = torch.cuda.current_stream(x.device)
+        pack_stream = self.sup._side_stream(x.device, 'pack')
+        pack_stream.wait_stream(cur)
+        with torch.cuda.stream(pack_stream):
+            packed_spn = self.sup.pack()
+            packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
 
         # encoder -> (constrain, match, smooth, velocities) in one kernel (csrc/glue.cu)
         zp = self.sup.encoder(x.flatten(end_dim=1)).view(n, T, O, 8)
@@ -250,7 +256,11 @@ class Stove(nn.Module):
 
         # dynamics loop: the whole loop is one persistent kernel (csrc/dynloop.cu), chained on the device
         eps = self._standard_normal_n(T - skip, (n, O, cl // 2 + 2), x)
+        cur.wait_stream(pack_stream)
         cfg_dyn, w_dyn = packed_dyn
+        for t in (w_dyn,) + tuple(v for pk in packed_spn if pk is not None for v in vars(pk).values()
+                                  if isinstance(v, torch.Tensor)):
+            t.record_stream(cur)
         z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
             z_sup_full, z_sup_std_full, lat0, eps, actions,
             obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip)

@@ -61,14 +61,14 @@ class Supair(nn.Module):
             cache[k] = torch.tensor(values, device=like.device, dtype=like.dtype)
         return cache[k]
 
-    def _side_stream(self, device):
+    def _side_stream(self, device, name='bg'):
         """A second CUDA stream (per device) for work that is independent of the main chain: the
         background SPN runs there while the object SPN runs on the current stream -- both are
         short, latency-bound launches that leave most SMs idle on their own.  autograd replays
         each op's backward on the stream of its forward, so the two backward chains overlap too;
         a CUDA-graph capture records the fork/join as parallel branches."""
         cache = self.__dict__.setdefault('_streams', {})
-        key = (device.type, device.index)
+        key = (device.type, device.index, name)
         if key not in cache:
             cache[key] = torch.cuda.Stream(device=device)
         return cache[key]
