@@ -84,6 +84,23 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
+// sums of four values over the CTA in one pass (two barriers instead of eight); the totals are valid
+// in thread 0 only
+__device__ __forceinline__ float4 block_sum4_t0(float4 v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+    __syncthreads();
+    if (lane == 0) reinterpret_cast<float4*>(red)[warp] = v;
+    __syncthreads();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0)
+        for (int w = 0; w < nwarp; ++w) {
+            const float4 r = reinterpret_cast<const float4*>(red)[w];
+            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+        }
+    return t;
+}
+
 // tents of the paste of object (sx, sy, tx, ty): tX[v], tY[u] (+ derivatives if dX != null)
 __device__ __forceinline__ void paste_tents(const SceneDims& d, float sx, float sy, float tx, float ty,
                                             float* tX, float* tY, float* dX, float* dY) {
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
                                                         const float* __restrict__ g_marg_bg,
                                                         const float* __restrict__ g_overlap,
                                                         float* __restrict__ g_z) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int AB = d.A * d.B, PP = d.pa * d.pb;
     float* ims = smem;                  // [C][AB]
     float* bgs = ims + d.C * AB;        // [O][AB] background before object o
@@ -177,10 +194,16 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
     float* tY = gpx + d.B;
     float* dY = tY + d.A;
     float* gpy = dY + d.A;
-    float* red = gpy + d.A;             // [32]
+    float* red = smem + ((((d.C + d.O + 1) * AB + 3 * (d.A + d.B)) + 3) & ~3);   // [32], 16-byte aligned
     const int64_t f = blockIdx.x;
     const int tid = threadIdx.x;
-    for (int i = tid; i < d.C * AB; i += blockDim.x) ims[i] = __ldg(img + f * d.C * AB + i);
+    const int shB = (d.B & (d.B - 1)) == 0 ? __ffs(d.B) - 1 : -1;      // row index without a division when B = 2^k
+    if ((AB & 3) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(img + f * d.C * AB);
+        for (int i = tid; i < d.C * AB / 4; i += blockDim.x) reinterpret_cast<float4*>(ims)[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < d.C * AB; i += blockDim.x) ims[i] = __ldg(img + f * d.C * AB + i);
+    }
     for (int i = tid; i < AB; i += blockDim.x) bgs[i] = 0.f;
     __syncthreads();
     // replay the forward background states
@@ -189,7 +212,7 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
         paste_tents(d, __ldg(zo), __ldg(zo + 1), __ldg(zo + 2), __ldg(zo + 3), tX, tY, nullptr, nullptr);
         __syncthreads();
         for (int i = tid; i < AB; i += blockDim.x) {
-            const int u = i / d.B, v = i - u * d.B;
+            const int u = shB >= 0 ? i >> shB : i / d.B, v = i - u * d.B;
             bgs[(o + 1) * AB + i] = fminf(fmaxf(bgs[o * AB + i] + tY[u] * tX[v], 0.f), 1.f);
         }
         __syncthreads();
@@ -210,21 +233,27 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
         __syncthreads();
         // clamp backward: pass where 0 <= bg + paste <= 1
         for (int i = tid; i < AB; i += blockDim.x) {
-            const int u = i / d.B, v = i - u * d.B;
+            const int u = shB >= 0 ? i >> shB : i / d.B, v = i - u * d.B;
             const float pre = bgo[i] + tY[u] * tX[v];
             if (!(pre >= 0.f && pre <= 1.f)) Gb[i] = 0.f;
         }
         __syncthreads();
         // paste = tY[u] * tX[v]
-        for (int k = tid; k < d.A + d.B; k += blockDim.x) {
-            float acc = 0.f;
-            if (k < d.B) {
+        // column sums: thread = column (conflict free); row sums: warp = row, lanes stride the row
+        // (a thread per row walks a stride-B column of banks: 54 % of this kernel's shared-memory
+        // wavefronts were bank conflicts)
+        {
+            const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+            for (int u = warp; u < d.A; u += nwarp) {
+                float acc = 0.f;
+                for (int v = lane; v < d.B; v += 32) acc = fmaf(Gb[u * d.B + v], tX[v], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) gpy[u] = acc * dY[u];
+            }
+            for (int k = tid; k < d.B; k += blockDim.x) {
+                float acc = 0.f;
                 for (int u = 0; u < d.A; ++u) acc = fmaf(Gb[u * d.B + k], tY[u], acc);
                 gpx[k] = acc * dX[k];
-            } else {
-                const int u = k - d.B;
-                for (int v = 0; v < d.B; ++v) acc = fmaf(Gb[u * d.B + v], tX[v], acc);
-                gpy[u] = acc * dY[u];
             }
         }
         __syncthreads();
@@ -276,14 +305,8 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
                 if (c.oky1 && c.okx1) atomicAdd(&Gb[(c.y0 + 1) * d.B + c.x0 + 1], gm * wy1 * wx1);
             }
         }
-        gsx = block_sum(gsx, red);
-        gsy = block_sum(gsy, red);
-        gtx = block_sum(gtx, red);
-        gty = block_sum(gty, red);
-        if (tid == 0) {
-            float* dst = g_z + (f * d.O + o) * 4;
-            dst[0] = gsx; dst[1] = gsy; dst[2] = gtx; dst[3] = gty;
-        }
+        const float4 tot = block_sum4_t0(make_float4(gsx, gsy, gtx, gty), red);
+        if (tid == 0) *reinterpret_cast<float4*>(g_z + (f * d.O + o) * 4) = tot;
         __syncthreads();
     }
 }
@@ -325,7 +348,7 @@ extern "C" int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, in
     STOVE_CHECK_ARG(img && z && g_z, "null pointer");
     if (F == 0) return STOVE_OK;
     SceneDims d{O, C, A, B, pa, pb, align_corners};
-    const size_t smem = sizeof(float) * ((size_t)(C + O + 1) * A * B + 3 * (A + B) + 32);
+    const size_t smem = sizeof(float) * ((size_t)(C + O + 1) * A * B + 3 * (A + B) + 4 + 32);
     if (smem > 227 * 1024) {
         stove_set_error("stove_scene_bwd: frame/objects too large for shared memory (%zu B)", smem);
         return STOVE_ERR_UNSUPPORTED;
