@@ -332,6 +332,19 @@ int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g
  * the recognition LSTM (encoder.py:50-51).  n % 4 == 0, 16-byte aligned pointers. */
 int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream);
 
+/* LSTM cell with the launches around it folded in (fused recognition network, encoder.py:28-57):
+ * forward adds `bias` [4H], writes h into a strided output (row stride h_ld floats) and optionally its
+ * TF32 split; backward takes g_h = g_h_a (row stride g_h_a_ld) + g_h_b (may be NULL), writes the TF32
+ * split of the gate gradient [n][4H] (or, if split_acc, of the running sum) and accumulates the gate
+ * gradient into g_acc (acc_mode 0: overwrite, 1: add).  g_c, c_prev, g_c_prev may be NULL. */
+int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
+                          const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
+                          float* h_hi, float* h_lo, void* stream);
+int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
+                          const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
+                          float* g_hi, float* g_lo, float* g_acc, int acc_mode, int split_acc,
+                          float* g_c_prev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -613,3 +613,106 @@ extern "C" int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo,
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// LSTM cell variants for the fused recognition network (video_prediction/encoder.py): the same
+// gate/state update as above, plus what used to be separate launches around it --
+//   forward : bias add, h written straight into the stacked output (row stride h_ld), and the TF32
+//             split (hi, lo) of h for the next step's 3xTF32 hidden GEMM;
+//   backward: g_h = g_h_a (strided slice of the stacked gradient) + g_h_b (from the next step's
+//             hidden GEMM), the TF32 split of the gate gradient for this step's GEMMs, and the
+//             running sum over steps of the gate gradients (what W_ih and the bias see).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+__global__ void lstm_cell_fwd_x_kernel(int64_t n, int H, const float* __restrict__ gx, const float* __restrict__ bias,
+                                       const float* __restrict__ gh, const float* __restrict__ c_prev,
+                                       float* __restrict__ h_out, int64_t h_ld, float* __restrict__ c_out,
+                                       float* __restrict__ act, float* __restrict__ h_hi, float* __restrict__ h_lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    const int64_t b = i / H;
+    const int k = (int)(i - b * H);
+    const float* px = gx + b * 4 * H;
+    const float* ph = gh ? gh + b * 4 * H : nullptr;
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = px[q * H + k] + __ldg(bias + q * H + k) + (ph ? ph[q * H + k] : 0.f);
+    const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    const float c = fg * cp + ig * gg;
+    const float tc = tanhf(c);
+    const float h = og * tc;
+    c_out[i] = c;
+    h_out[b * h_ld + k] = h;
+    if (h_hi) {
+        const float hh = tf32_hi(h);
+        h_hi[i] = hh;
+        h_lo[i] = h - hh;
+    }
+    float* pa = act + b * 4 * H;
+    pa[k] = ig; pa[H + k] = fg; pa[2 * H + k] = gg; pa[3 * H + k] = og;
+}
+
+// acc_mode: 0 = g_acc = g, 1 = g_acc += g.  split_acc: the (hi, lo) outputs hold the split of the
+// accumulated sum instead of this step's gradient.
+__global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict__ act,
+                                       const float* __restrict__ c_prev, const float* __restrict__ c_out,
+                                       const float* __restrict__ g_h_a, int64_t g_h_a_ld,
+                                       const float* __restrict__ g_h_b, const float* __restrict__ g_c,
+                                       float* __restrict__ g_hi, float* __restrict__ g_lo,
+                                       float* __restrict__ g_acc, int acc_mode, int split_acc,
+                                       float* __restrict__ g_c_prev) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    const int64_t b = i / H;
+    const int k = (int)(i - b * H);
+    const float* pa = act + b * 4 * H;
+    const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
+    const float tc = tanhf(c_out[i]);
+    const float gh = g_h_a[b * g_h_a_ld + k] + (g_h_b ? g_h_b[i] : 0.f);
+    const float gc = (g_c ? g_c[i] : 0.f) + gh * og * (1.f - tc * tc);
+    const float cp = c_prev ? c_prev[i] : 0.f;
+    float g[4];
+    g[0] = gc * gg * ig * (1.f - ig);
+    g[1] = gc * cp * fg * (1.f - fg);
+    g[2] = gc * ig * (1.f - gg * gg);
+    g[3] = gh * tc * og * (1.f - og);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t o = b * 4 * H + q * H + k;
+        const float a = acc_mode ? g_acc[o] + g[q] : g[q];
+        g_acc[o] = a;
+        const float v = split_acc ? a : g[q];
+        const float vh = tf32_hi(v);
+        g_hi[o] = vh;
+        g_lo[o] = v - vh;
+    }
+    if (g_c_prev) g_c_prev[i] = gc * fg;
+}
+
+extern "C" int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
+                                     const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
+                                     float* h_hi, float* h_lo, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && H > 0 && gx && bias && h_out && c_out && act && h_ld >= H, "bad argument");
+    STOVE_CHECK_ARG((h_hi == nullptr) == (h_lo == nullptr), "h_hi and h_lo go together");
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_LSTM_CELL_FWD, s, lstm_cell_fwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
+        n, H, gx, bias, gh, c_prev, h_out, h_ld, c_out, act, h_hi, h_lo));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+extern "C" int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
+                                     const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
+                                     float* g_hi, float* g_lo, float* g_acc, int acc_mode, int split_acc,
+                                     float* g_c_prev, void* stream) {
+    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_h_a && g_hi && g_lo && g_acc && g_h_a_ld >= H, "bad argument");
+    if (n == 0) return STOVE_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
+        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_c, g_hi, g_lo, g_acc, acc_mode, split_acc, g_c_prev));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -307,13 +307,17 @@ def split_tf32(x):
     return hi, lo
 
 
-def mm3(a, b):
-    """a @ b for split operands a = (a_hi, a_lo), b = (b_hi, b_lo) (any strides): three TF32
-    tensor-core GEMMs, fp32 accumulate; the lo * lo term (2^-22 relative) is dropped."""
+def mm3(a, b, out=None):
+    """a @ b (added to `out` if given) for split operands a = (a_hi, a_lo), b = (b_hi, b_lo) (any
+    strides): three TF32 tensor-core GEMMs, fp32 accumulate; the lo * lo term (2^-22 relative) is
+    dropped."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        out = torch.mm(a[0], b[1])
+        if out is None:
+            out = torch.mm(a[0], b[1])
+        else:
+            out.addmm_(a[0], b[1])
         out.addmm_(a[1], b[0])
         out.addmm_(a[0], b[0])
     finally:
@@ -338,6 +342,77 @@ class Linear3(torch.autograd.Function):
         g_a = mm3(g_split, ctx.w_split) if ctx.needs_input_grad[0] else None
         g_w = mm3((g_split[0].t(), g_split[1].t()), ctx.a_split) if ctx.needs_input_grad[1] else None
         return g_a, g_w, None, None
+
+
+class LstmEncoder(torch.autograd.Function):
+    """h_1 .. h_steps of a one-layer LSTM that is fed the SAME input x at every step from a zero state
+    (the recognition network, encoder.py:50-51; nn.LSTM gate order and parameter shapes).
+    x (n, K), w_ih (4H, K), w_hh (4H, H), b_ih / b_hh (4H,) -> (n, steps, H).
+
+    One autograd node instead of ~65 launches: the input GEMM is done once, all GEMMs are 3xTF32
+    (`mm3`), the cell kernels add the bias, write h into the stacked output, emit the TF32 splits the
+    next GEMM needs and accumulate the gate gradients that W_ih and the biases see."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps):
+        x, w_ih, w_hh = x.contiguous(), w_ih.contiguous(), w_hh.contiguous()
+        N.require_cuda_f32(x, w_ih, w_hh, b_ih, b_hh)
+        n, H = x.shape[0], w_hh.shape[1]
+        dev, dt = x.device, x.dtype
+        lib, st = N.lib(), N.stream()
+        xs, wih, whh = split_tf32(x), split_tf32(w_ih), split_tf32(w_hh)
+        bias = (b_ih + b_hh).contiguous()
+        gx = mm3(xs, (wih[0].t(), wih[1].t()))
+        out = torch.empty(n, steps, H, device=dev, dtype=dt)
+        acts, cs, hs = [], [], []
+        gh = c_prev = None
+        for t in range(steps):
+            c = torch.empty(n, H, device=dev, dtype=dt)
+            act = torch.empty(n, 4 * H, device=dev, dtype=dt)
+            more = t + 1 < steps
+            h_hi = torch.empty(n, H, device=dev, dtype=dt) if more else None
+            h_lo = torch.empty(n, H, device=dev, dtype=dt) if more else None
+            N.check(lib.stove_lstm_cell_fwd_x(n, H, N.ptr(gx), N.ptr(bias), N.ptr(gh), N.ptr(c_prev),
+                                              out[:, t].data_ptr(), steps * H, N.ptr(c), N.ptr(act),
+                                              N.ptr(h_hi), N.ptr(h_lo), st))
+            acts.append(act)
+            cs.append(c)
+            if more:
+                hs.append((h_hi, h_lo))
+                gh = mm3((h_hi, h_lo), (whh[0].t(), whh[1].t()))
+            c_prev = c
+        ctx.stash = (xs, wih, whh, acts, cs, hs, steps, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xs, wih, whh, acts, cs, hs, steps, H = ctx.stash
+        g_out = g_out.contiguous()
+        n = g_out.shape[0]
+        dev, dt = g_out.device, g_out.dtype
+        lib, st = N.lib(), N.stream()
+        g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
+        g_whh = dh = g_c = None
+        for t in reversed(range(steps)):
+            g_hi = torch.empty(n, 4 * H, device=dev, dtype=dt)
+            g_lo = torch.empty(n, 4 * H, device=dev, dtype=dt)
+            g_c_prev = torch.empty(n, H, device=dev, dtype=dt) if t > 0 else None
+            N.check(lib.stove_lstm_cell_bwd_x(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
+                                              N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
+                                              N.ptr(g_c), N.ptr(g_hi), N.ptr(g_lo), N.ptr(g_sum),
+                                              0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
+            if t > 0:
+                # step t read h_{t-1}: weight gradient and the gradient flowing back into h_{t-1}
+                g_whh = mm3((g_hi.t(), g_lo.t()), hs[t - 1], out=g_whh)
+                dh = mm3((g_hi, g_lo), whh)
+                g_c = g_c_prev
+        # after step 0 (g_hi, g_lo) hold the split of the summed gate gradient
+        g_wih = mm3((g_hi.t(), g_lo.t()), xs) if ctx.needs_input_grad[1] else None
+        g_x = mm3((g_hi, g_lo), wih) if ctx.needs_input_grad[0] else None
+        g_b = g_sum.sum(0)
+        if g_whh is None:
+            g_whh = torch.zeros_like(whh[0])
+        return g_x, g_wih, g_whh, g_b, g_b, None
 
 
 # ----------------------------------------------------------------------------------------

@@ -46,16 +46,12 @@ class RnnStates(nn.Module):
                 h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
                 outs.append(h)
         else:
-            # 3xTF32 (ops.Linear3): every operand is split once into a TF32-exact part and a remainder;
-            # three tensor-core GEMMs reproduce the fp32 product to ~4e-6 relative
-            wih = ops.split_tf32(rnn.weight_ih_l0.detach())
-            whh = ops.split_tf32(rnn.weight_hh_l0.detach())
-            x_split = ops.split_tf32(x.detach()) if not x.requires_grad else None
-            gates_x = ops.Linear3.apply(x, rnn.weight_ih_l0, x_split, wih) + (rnn.bias_ih_l0 + rnn.bias_hh_l0)
-            for _ in range(self.c.num_obj):
-                gates_h = ops.Linear3.apply(h, rnn.weight_hh_l0, None, whh) if h is not None else None
-                h, cell = ops.LstmCell.apply(gates_x, gates_h, cell)
-                outs.append(h)
+            # one fused autograd node (ops.LstmEncoder): 3xTF32 GEMMs (every operand split once into a
+            # TF32-exact part and a remainder; three tensor-core GEMMs reproduce the fp32 product to
+            # ~4e-6 relative) and cell kernels that fold in the bias, the stacking and the splits
+            zps = ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
+                                        self.c.num_obj)
+            return self.fc2(torch.sigmoid(self.fc1(zps)))
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
         return self.fc2(zps)
