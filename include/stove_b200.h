@@ -332,17 +332,25 @@ int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g
  * the recognition LSTM (encoder.py:50-51).  n % 4 == 0, 16-byte aligned pointers. */
 int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream);
 
+/* K-concatenated 3xTF32 operands: x [rows][cols] -> colcat [rows][3*cols] and / or rowcat [3*rows][cols]
+ * (either may be NULL); block order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  Contracting an order-0 operand
+ * with an order-1 operand along the tripled extent gives hi*hi + hi*lo + lo*hi in ONE TF32 GEMM. */
+int stove_split_tf32_cat(int64_t rows, int cols, const float* x, float* colcat, int col_order,
+                         float* rowcat, int row_order, void* stream);
+
 /* LSTM cell with the launches around it folded in (fused recognition network, encoder.py:28-57):
  * forward adds `bias` [4H], writes h into a strided output (row stride h_ld floats) and optionally its
- * TF32 split; backward takes g_h = g_h_a (row stride g_h_a_ld) + g_h_b (may be NULL), writes the TF32
- * split of the gate gradient [n][4H] (or, if split_acc, of the running sum) and accumulates the gate
- * gradient into g_acc (acc_mode 0: overwrite, 1: add).  g_c, c_prev, g_c_prev may be NULL. */
+ * K-concatenated TF32 operands h_col [n][3H] (hi, hi, lo) and h_row [3n][H] (hi, lo, hi); backward takes
+ * g_h = g_h_a (row stride g_h_a_ld) + g_h_b (may be NULL), writes the concatenated operands of the gate
+ * gradient g_col [n][12H] (optional) and g_row [3n][4H], both (hi, hi, lo) -- of the running sum if
+ * split_acc -- and accumulates the gate gradient into g_acc (acc_mode 0: overwrite, 1: add).
+ * g_c, c_prev, g_c_prev may be NULL. */
 int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
                           const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
-                          float* h_hi, float* h_lo, void* stream);
+                          float* h_col, float* h_row, void* stream);
 int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
                           const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
-                          float* g_hi, float* g_lo, float* g_acc, int acc_mode, int split_acc,
+                          float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
                           float* g_c_prev, void* stream);
 
 #ifdef __cplusplus

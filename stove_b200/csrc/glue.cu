@@ -628,7 +628,7 @@ __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__flo
 __global__ void lstm_cell_fwd_x_kernel(int64_t n, int H, const float* __restrict__ gx, const float* __restrict__ bias,
                                        const float* __restrict__ gh, const float* __restrict__ c_prev,
                                        float* __restrict__ h_out, int64_t h_ld, float* __restrict__ c_out,
-                                       float* __restrict__ act, float* __restrict__ h_hi, float* __restrict__ h_lo) {
+                                       float* __restrict__ act, float* __restrict__ h_col, float* __restrict__ h_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * H) return;
     const int64_t b = i / H;
@@ -645,10 +645,13 @@ __global__ void lstm_cell_fwd_x_kernel(int64_t n, int H, const float* __restrict
     const float h = og * tc;
     c_out[i] = c;
     h_out[b * h_ld + k] = h;
-    if (h_hi) {
-        const float hh = tf32_hi(h);
-        h_hi[i] = hh;
-        h_lo[i] = h - hh;
+    if (h_col) {
+        // K-concatenated 3xTF32 operands: [hi | hi | lo] along the columns (left operand of h W_hh^T) and
+        // [hi ; lo ; hi] along the rows (right operand of g^T h)
+        const float hh = tf32_hi(h), hl = h - hh;
+        float* pc = h_col + b * 3 * H + k;
+        pc[0] = hh; pc[H] = hh; pc[2 * H] = hl;
+        h_row[i] = hh; h_row[n * H + i] = hl; h_row[2 * n * H + i] = hh;
     }
     float* pa = act + b * 4 * H;
     pa[k] = ig; pa[H + k] = fg; pa[2 * H + k] = gg; pa[3 * H + k] = og;
@@ -660,7 +663,7 @@ __global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict
                                        const float* __restrict__ c_prev, const float* __restrict__ c_out,
                                        const float* __restrict__ g_h_a, int64_t g_h_a_ld,
                                        const float* __restrict__ g_h_b, const float* __restrict__ g_c,
-                                       float* __restrict__ g_hi, float* __restrict__ g_lo,
+                                       float* __restrict__ g_col, float* __restrict__ g_row,
                                        float* __restrict__ g_acc, int acc_mode, int split_acc,
                                        float* __restrict__ g_c_prev) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,36 +686,81 @@ __global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict
         const int64_t o = b * 4 * H + q * H + k;
         const float a = acc_mode ? g_acc[o] + g[q] : g[q];
         g_acc[o] = a;
+        // K-concatenated 3xTF32 operands, both [hi, hi, lo]: along the columns (left operand of g W_hh)
+        // and along the rows (left operand, transposed, of g^T h and g^T x)
         const float v = split_acc ? a : g[q];
-        const float vh = tf32_hi(v);
-        g_hi[o] = vh;
-        g_lo[o] = v - vh;
+        const float vh = tf32_hi(v), vl = v - vh;
+        if (g_col) {
+            float* pc = g_col + b * 12 * H + q * H + k;
+            pc[0] = vh; pc[4 * H] = vh; pc[8 * H] = vl;
+        }
+        g_row[o] = vh; g_row[n * 4 * H + o] = vh; g_row[2 * n * 4 * H + o] = vl;
     }
     if (g_c_prev) g_c_prev[i] = gc * fg;
 }
 
 extern "C" int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
                                      const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
-                                     float* h_hi, float* h_lo, void* stream) {
+                                     float* h_col, float* h_row, void* stream) {
     STOVE_CHECK_ARG(n >= 0 && H > 0 && gx && bias && h_out && c_out && act && h_ld >= H, "bad argument");
-    STOVE_CHECK_ARG((h_hi == nullptr) == (h_lo == nullptr), "h_hi and h_lo go together");
+    STOVE_CHECK_ARG((h_col == nullptr) == (h_row == nullptr), "h_col and h_row go together");
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     STOVE_KERNEL(K_LSTM_CELL_FWD, s, lstm_cell_fwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, gx, bias, gh, c_prev, h_out, h_ld, c_out, act, h_hi, h_lo));
+        n, H, gx, bias, gh, c_prev, h_out, h_ld, c_out, act, h_col, h_row));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
 
 extern "C" int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
                                      const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
-                                     float* g_hi, float* g_lo, float* g_acc, int acc_mode, int split_acc,
+                                     float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
                                      float* g_c_prev, void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_h_a && g_hi && g_lo && g_acc && g_h_a_ld >= H, "bad argument");
+    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_h_a && g_row && g_acc && g_h_a_ld >= H, "bad argument");
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_c, g_hi, g_lo, g_acc, acc_mode, split_acc, g_c_prev));
+        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_c, g_col, g_row, g_acc, acc_mode, split_acc, g_c_prev));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}
+
+// x [rows][cols] -> K-concatenated 3xTF32 operands: colcat [rows][3*cols] and / or rowcat [3*rows][cols];
+// block order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  A GEMM contracts a (hi, hi, lo) operand with a
+// (hi, lo, hi) one: hi*hi + hi*lo + lo*hi in a single call with 3x the K extent.
+__global__ void split_cat_kernel(int64_t rows, int cols, const float4* __restrict__ x, float* __restrict__ colcat,
+                                 int col_order, float* __restrict__ rowcat, int row_order) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4n = cols >> 2;
+    if (i >= rows * c4n) return;
+    const int64_t r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    const float4 v = __ldg(x + i);
+    float4 h, l;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (colcat) {
+        float* p = colcat + r * 3 * cols + c;
+        *reinterpret_cast<float4*>(p) = h;
+        *reinterpret_cast<float4*>(p + cols) = col_order ? l : h;
+        *reinterpret_cast<float4*>(p + 2 * cols) = col_order ? h : l;
+    }
+    if (rowcat) {
+        float* p = rowcat + r * cols + c;
+        *reinterpret_cast<float4*>(p) = h;
+        *reinterpret_cast<float4*>(p + rows * cols) = row_order ? l : h;
+        *reinterpret_cast<float4*>(p + 2 * rows * cols) = row_order ? h : l;
+    }
+}
+
+extern "C" int stove_split_tf32_cat(int64_t rows, int cols, const float* x, float* colcat, int col_order,
+                                    float* rowcat, int row_order, void* stream) {
+    STOVE_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0 && x && (colcat || rowcat), "need cols % 4 == 0");
+    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)colcat | (uintptr_t)rowcat) & 15) == 0, "pointers must be 16-byte aligned");
+    if (rows == 0) return STOVE_OK;
+    const int64_t items = rows * (cols / 4);
+    STOVE_KERNEL(K_SPLIT_TF32, (cudaStream_t)stream, split_cat_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        rows, cols, (const float4*)x, colcat, col_order, rowcat, row_order));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

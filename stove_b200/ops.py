@@ -344,75 +344,103 @@ class Linear3(torch.autograd.Function):
         return g_a, g_w, None, None
 
 
+def split_tf32_cat(x, col_order=None, row_order=None):
+    """K-concatenated 3xTF32 operands of a 2-D tensor: (colcat (rows, 3 cols) | None, rowcat (3 rows, cols)
+    | None); order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  One TF32 GEMM of an order-0 operand with an
+    order-1 operand over the tripled extent = hi*hi + hi*lo + lo*hi."""
+    x = x.contiguous()
+    N.require_cuda_f32(x)
+    rows, cols = x.shape
+    col = torch.empty(rows, 3 * cols, device=x.device, dtype=x.dtype) if col_order is not None else None
+    row = torch.empty(3 * rows, cols, device=x.device, dtype=x.dtype) if row_order is not None else None
+    N.check(N.lib().stove_split_tf32_cat(rows, cols, N.ptr(x), N.ptr(col), col_order or 0, N.ptr(row),
+                                         row_order or 0, N.stream()))
+    return col, row
+
+
+def _mm_tf32(a, b, out=None):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        return torch.mm(a, b) if out is None else out.addmm_(a, b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 class LstmEncoder(torch.autograd.Function):
     """h_1 .. h_steps of a one-layer LSTM that is fed the SAME input x at every step from a zero state
     (the recognition network, encoder.py:50-51; nn.LSTM gate order and parameter shapes).
     x (n, K), w_ih (4H, K), w_hh (4H, H), b_ih / b_hh (4H,) -> (n, steps, H).
 
-    One autograd node instead of ~65 launches: the input GEMM is done once, all GEMMs are 3xTF32
-    (`mm3`), the cell kernels add the bias, write h into the stacked output, emit the TF32 splits the
-    next GEMM needs and accumulate the gate gradients that W_ih and the biases see."""
+    One autograd node instead of ~65 launches: the input GEMM is done once; every GEMM is ONE TF32
+    tensor-core call over K-concatenated (hi, lo) operands (3xTF32: fp32-level accuracy, in-graph
+    20 us instead of 81 us for the SIMT-fp32 input GEMM); the cell kernels add the bias, write h
+    into the stacked output, emit the concatenated operands the next GEMM needs and accumulate the
+    gate gradients that W_ih and the biases see."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps):
-        x, w_ih, w_hh = x.contiguous(), w_ih.contiguous(), w_hh.contiguous()
         N.require_cuda_f32(x, w_ih, w_hh, b_ih, b_hh)
         n, H = x.shape[0], w_hh.shape[1]
         dev, dt = x.device, x.dtype
         lib, st = N.lib(), N.stream()
-        xs, wih, whh = split_tf32(x), split_tf32(w_ih), split_tf32(w_hh)
+        x_col, x_row = split_tf32_cat(x, 0, 1)             # x as left operand / as right operand of g^T x
+        wih_col, _ = split_tf32_cat(w_ih, 1, None)
+        whh_col, whh_row = split_tf32_cat(w_hh, 1, 1)
         bias = (b_ih + b_hh).contiguous()
-        gx = mm3(xs, (wih[0].t(), wih[1].t()))
+        gx = _mm_tf32(x_col, wih_col.t())
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
-        acts, cs, hs = [], [], []
+        acts, cs, h_rows = [], [], []
         gh = c_prev = None
         for t in range(steps):
             c = torch.empty(n, H, device=dev, dtype=dt)
             act = torch.empty(n, 4 * H, device=dev, dtype=dt)
             more = t + 1 < steps
-            h_hi = torch.empty(n, H, device=dev, dtype=dt) if more else None
-            h_lo = torch.empty(n, H, device=dev, dtype=dt) if more else None
+            h_col = torch.empty(n, 3 * H, device=dev, dtype=dt) if more else None
+            h_row = torch.empty(3 * n, H, device=dev, dtype=dt) if more else None
             N.check(lib.stove_lstm_cell_fwd_x(n, H, N.ptr(gx), N.ptr(bias), N.ptr(gh), N.ptr(c_prev),
                                               out[:, t].data_ptr(), steps * H, N.ptr(c), N.ptr(act),
-                                              N.ptr(h_hi), N.ptr(h_lo), st))
+                                              N.ptr(h_col), N.ptr(h_row), st))
             acts.append(act)
             cs.append(c)
             if more:
-                hs.append((h_hi, h_lo))
-                gh = mm3((h_hi, h_lo), (whh[0].t(), whh[1].t()))
+                h_rows.append(h_row)
+                gh = _mm_tf32(h_col, whh_col.t())
             c_prev = c
-        ctx.stash = (xs, wih, whh, acts, cs, hs, steps, H)
+        ctx.stash = (x_row, wih_col, whh_row, acts, cs, h_rows, steps, H)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        xs, wih, whh, acts, cs, hs, steps, H = ctx.stash
+        x_row, wih_col, whh_row, acts, cs, h_rows, steps, H = ctx.stash
         g_out = g_out.contiguous()
         n = g_out.shape[0]
         dev, dt = g_out.device, g_out.dtype
         lib, st = N.lib(), N.stream()
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
+                                      '(frames are data on the STOVE hot path)')
         g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
         g_whh = dh = g_c = None
         for t in reversed(range(steps)):
-            g_hi = torch.empty(n, 4 * H, device=dev, dtype=dt)
-            g_lo = torch.empty(n, 4 * H, device=dev, dtype=dt)
+            g_col = torch.empty(n, 12 * H, device=dev, dtype=dt) if t > 0 else None
+            g_row = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)
             g_c_prev = torch.empty(n, H, device=dev, dtype=dt) if t > 0 else None
             N.check(lib.stove_lstm_cell_bwd_x(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
                                               N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
-                                              N.ptr(g_c), N.ptr(g_hi), N.ptr(g_lo), N.ptr(g_sum),
+                                              N.ptr(g_c), N.ptr(g_col), N.ptr(g_row), N.ptr(g_sum),
                                               0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
             if t > 0:
                 # step t read h_{t-1}: weight gradient and the gradient flowing back into h_{t-1}
-                g_whh = mm3((g_hi.t(), g_lo.t()), hs[t - 1], out=g_whh)
-                dh = mm3((g_hi, g_lo), whh)
+                g_whh = _mm_tf32(g_row.t(), h_rows[t - 1], out=g_whh)
+                dh = _mm_tf32(g_col, whh_row)
                 g_c = g_c_prev
-        # after step 0 (g_hi, g_lo) hold the split of the summed gate gradient
-        g_wih = mm3((g_hi.t(), g_lo.t()), xs) if ctx.needs_input_grad[1] else None
-        g_x = mm3((g_hi, g_lo), wih) if ctx.needs_input_grad[0] else None
+        # after step 0 g_row holds the concatenated operand of the summed gate gradient
+        g_wih = _mm_tf32(g_row.t(), x_row) if ctx.needs_input_grad[1] else None
         g_b = g_sum.sum(0)
         if g_whh is None:
-            g_whh = torch.zeros_like(whh[0])
-        return g_x, g_wih, g_whh, g_b, g_b, None
+            g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
+        return None, g_wih, g_whh, g_b, g_b, None
 
 
 # ----------------------------------------------------------------------------------------
