@@ -297,11 +297,15 @@ typedef struct {
     float* logq; float* trans; float* reward;
     const float* g_z; const float* g_logq; const float* g_trans; const float* g_reward;
     float* g_z_init; float* g_sup; float* g_sup_std;
+    float* xrec;   /* optional [stove_dynloop_xrec_floats]: forward keeps its activations here and the
+                      backward reloads them instead of recomputing each step (NULL: recompute) */
 } stove_dynloop_io;
 
 int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                       const stove_dynloop_io* io, const float* weights, void* stream);
 size_t stove_dynloop_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
+/* floats of the optional activation buffer `xrec` (0: this shape has no such path) */
+int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
 int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                       const stove_dynloop_io* io, const float* weights, float* g_weights,
                       void* workspace, void* stream);

@@ -64,7 +64,7 @@ class DynloopIO(C.Structure):
                 ('z', vp), ('z_dyn', vp), ('z_dyn_std', vp), ('z_std', vp),
                 ('logq', vp), ('trans', vp), ('reward', vp),
                 ('g_z', vp), ('g_logq', vp), ('g_trans', vp), ('g_reward', vp),
-                ('g_z_init', vp), ('g_sup', vp), ('g_sup_std', vp)]
+                ('g_z_init', vp), ('g_sup', vp), ('g_sup_std', vp), ('xrec', vp)]
 
 
 P2, P1, PG, PS = C.POINTER(Spn2Struct), C.POINTER(Spn1Struct), C.POINTER(GnnCfg), C.POINTER(SupCfg)
@@ -108,6 +108,7 @@ SIGNATURES = {
     'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, C.c_int, vp, vp]),
     'stove_dynloop_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp]),
     'stove_dynloop_bwd_workspace': (sz, [PG, i64, C.c_int, C.c_int]),
+    'stove_dynloop_xrec_floats': (i64, [PG, i64, C.c_int, C.c_int]),
     'stove_dynloop_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp]),
     'stove_zall_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     'stove_zall_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),

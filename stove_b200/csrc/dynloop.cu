@@ -55,25 +55,29 @@ struct FwdLay {
                          RA0 = DIST + 16, R1 = RA0 + 4 * PB, A1 = R1 + PB, REL = RA0, ATT = RA0 + PB,
                          TOTAL = A1 + PB;
 };
-// backward layout: nothing is overwritten; the first REC floats are the record that the
-// weight-gradient kernel consumes (layer inputs, then pre-activation gradients)
+// backward layout: nothing is overwritten.  The first XREC floats are what the forward pass leaves
+// behind for the backward pass (layer inputs, network output, relation / attention values): in
+// training the forward kernel stores them per (sequence, step) and the backward chain reloads them
+// instead of recomputing the step.  [XREC, REC) are the pre-activation gradients; together they
+// are the record the weight-gradient kernel consumes.
 struct BwdLay {
     static constexpr int SIN = 0, S = SIN + IN_MAX * ORW, H = S + OB, D = H + OB, F1 = D + OB, F2 = F1 + OB,
                          CAT = F2 + OB, O1 = CAT + 2 * OB, RH0 = O1 + OB, SMALL = RH0 + OB, ACT = SMALL + 64,
-                         DIST = ACT + A_MAX, RA0 = DIST + 16, R1 = RA0 + 4 * PB, A1 = R1 + PB;
-    static constexpr int G_OUT = A1 + PB, G_O1P = G_OUT + OB, G_F3 = G_O1P + OB, G_F2P = G_F3 + OB,
+                         DIST = ACT + A_MAX, RA0 = DIST + 16, R1 = RA0 + 4 * PB, A1 = R1 + PB, OUT = A1 + PB,
+                         REL = OUT + OB, ATT = REL + PB;
+    static constexpr int XREC = ATT + 16;
+    static constexpr int G_OUT = XREC, G_O1P = G_OUT + OB, G_F3 = G_O1P + OB, G_F2P = G_F3 + OB,
                          G_F1P = G_F2P + OB, G_D = G_F1P + OB, G_HP = G_D + OB, G_ENC = G_HP + OB,
                          G_RH1 = G_ENC + OB, G_RH0P = G_RH1 + OB, G_SMALL = G_RH0P + OB, G_REL = G_SMALL + 64,
                          G_ATT = G_REL + PB, G_R1P = G_ATT + 16, G_A1P = G_R1P + PB, G_RA0P = G_A1P + PB;
-    static constexpr int REC = G_RA0P + 4 * PB;
-    static constexpr int SELFD = REC, OUT = SELFD + OB, RH1 = OUT + OB, REL = RH1 + OB, ATT = REL + PB,
-                         GUV = ATT + 16, GS_A = GUV + 4 * CL * 8, GS_B = GS_A + OB, GDIST = GS_B + OB,
-                         GZ = GDIST + 32, TOTAL = GZ + 64;
+    static constexpr int REC = G_RA0P + 4 * PB, GREC = REC - XREC;
+    static constexpr int SELFD = REC, RH1 = SELFD + OB, GUV = RH1 + OB, GS_A = GUV + 4 * CL * 8, GS_B = GS_A + OB,
+                         GDIST = GS_B + OB, GZ = GDIST + 32, TOTAL = GZ + 64;
 };
 // SMALL: RSUM [32] | R2 [16] | R3 [8] | REW [1];  G_SMALL: g_r2pre [16] | g_r3pre [8] | g_rewpre [1] | pad | g_emb [12]
 constexpr int SM_RSUM = 0, SM_R2 = 32, SM_R3 = 48, SM_REW = 56;
 constexpr int GSM_R2 = 0, GSM_R3 = 16, GSM_REW = 24, GSM_EMB = 32;
-static_assert(FwdLay::TOTAL % 4 == 0 && BwdLay::REC % 4 == 0 && BwdLay::TOTAL % 4 == 0, "alignment");
+static_assert(FwdLay::TOTAL % 4 == 0 && BwdLay::XREC % 4 == 0 && BwdLay::REC % 4 == 0 && BwdLay::TOTAL % 4 == 0, "alignment");
 
 template <int NW>
 __device__ __forceinline__ void team_sync(int bar) {
@@ -102,6 +106,14 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void stage_weights(const StageTable& st, const float* __restrict__ weights, float* Ws) {
     for (int s = 0; s < st.count; ++s) {
         const Seg sg = st.seg[s];
@@ -392,6 +404,7 @@ struct LoopIO {
     float *z, *z_dyn, *z_dyn_std, *z_std, *logq, *trans, *reward;
     const float *g_z, *g_logq, *g_trans, *g_reward;
     float *g_z_init, *g_sup, *g_sup_std;
+    float* xrec;        // [n][S][XREC]: forward activations kept for the backward pass (may be NULL)
 };
 
 template <class Lay>
@@ -413,10 +426,13 @@ __device__ __forceinline__ void load_app(const stove_gnn_cfg& c, float* a, const
 // ---------------------------------------------------------------------------------------------
 // forward: the whole dynamics loop, one team per sequence
 // ---------------------------------------------------------------------------------------------
-template <int NW>
+template <bool B, class X, class Y> struct pick_ { using type = X; };
+template <class X, class Y> struct pick_<false, X, Y> { using type = Y; };
+
+template <int NW, bool SAVE>
 __global__ void __launch_bounds__(448, 1) dynloop_fwd_kernel(stove_gnn_cfg c, TW w, StageTable st, FuseCfg f,
                                                              int64_t n, LoopIO io, const float* __restrict__ weights) {
-    using Lay = FwdLay;
+    using Lay = typename pick_<SAVE, BwdLay, FwdLay>::type;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;
     stage_weights(st, weights, Ws);
@@ -434,6 +450,13 @@ __global__ void __launch_bounds__(448, 1) dynloop_fwd_kernel(stove_gnn_cfg c, TW
             team_sync<NW>(bar);
             forward_step<Lay, NW>(c, w, Ws, a, io.actions ? io.actions + (sq * T + t - 1) * c.action_dim : nullptr,
                                   lane, part, bar);
+            if (SAVE) {
+                // keep this step's activations for the backward pass (before the state is advanced)
+                float4* dst = reinterpret_cast<float4*>(io.xrec + (sq * S + k) * (int64_t)BwdLay::XREC);
+                const float4* src = reinterpret_cast<const float4*>(a);
+                for (int i = lane + 32 * part; i < BwdLay::XREC / 4; i += 32 * NW) dst[i] = src[i];
+                team_sync<NW>(bar);
+            }
             if (part == 0) {
                 // sample z_t ~ q, log q, transition likelihood; the sample is the next step's state
                 float lq = 0.f, tr = 0.f;
@@ -571,10 +594,10 @@ __device__ __forceinline__ void pair_bwd_in2(const float* __restrict__ Wr0, cons
 // ---------------------------------------------------------------------------------------------
 // backward chain: steps in reverse, state gradient carried on chip, one record per (sequence, step)
 // ---------------------------------------------------------------------------------------------
-template <int NW>
+template <int NW, bool SAVED>
 __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW w, StageTable st, FuseCfg f,
                                                              int64_t n, LoopIO io, const float* __restrict__ weights,
-                                                             float* __restrict__ rec) {
+                                                             float* __restrict__ xrec, float* __restrict__ grec) {
     using Lay = BwdLay;
     extern __shared__ __align__(16) float smem[];
     float* Ws = smem;
@@ -592,13 +615,23 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
             for (int e = lane; e < 64; e += 32) a[Lay::GZ + e] = 0.f;
         for (int k = S - 1; k >= 0; --k) {
             const int t = io.skip + k;
-            if (p0) {
-                load_state<Lay>(a, k == 0 ? io.z_init + sq * O * ZD : io.z + ((sq * S + k - 1) * O) * ZD, lane);
-                if (c.app_dim > 0) load_app<Lay>(c, a, io.app + ((sq * T + t - 1) * O) * c.app_dim, lane);
+            if (SAVED) {
+                // the forward kernel kept this step's activations: one asynchronous block copy
+                const float4* src = reinterpret_cast<const float4*>(xrec + (sq * S + k) * (int64_t)Lay::XREC);
+                float4* dst = reinterpret_cast<float4*>(a);
+                for (int i = lane + 32 * part; i < Lay::XREC / 4; i += 32 * NW) cp_async16(dst + i, src + i);
+                cp_async_commit();
+                cp_async_wait<0>();
+                team_sync<NW>(bar);
+            } else {
+                if (p0) {
+                    load_state<Lay>(a, k == 0 ? io.z_init + sq * O * ZD : io.z + ((sq * S + k - 1) * O) * ZD, lane);
+                    if (c.app_dim > 0) load_app<Lay>(c, a, io.app + ((sq * T + t - 1) * O) * c.app_dim, lane);
+                }
+                team_sync<NW>(bar);
+                forward_step<Lay, NW>(c, w, W, a, io.actions ? io.actions + (sq * T + t - 1) * c.action_dim : nullptr,
+                                      lane, part, bar);
             }
-            team_sync<NW>(bar);
-            forward_step<Lay, NW>(c, w, W, a, io.actions ? io.actions + (sq * T + t - 1) * c.action_dim : nullptr,
-                                  lane, part, bar);
             // ---- prologue: d(sample, log q, transition lik) -> raw network output, SuPAIR inputs
             if (p0) {
                 const float glq = io.g_logq ? __ldg(io.g_logq + sq * S + k) : 0.f;
@@ -888,11 +921,17 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
                 }
             }
             team_sync<NW>(bar);
-            // ---- the record of this (sequence, step) for the weight-gradient kernel
+            // ---- the record of this (sequence, step) for the weight-gradient kernel: the gradient half
+            // (and the activation half if the forward pass did not keep it)
             {
-                float4* dst = reinterpret_cast<float4*>(rec + ((sq * S + k) * (int64_t)Lay::REC));
-                const float4* src = reinterpret_cast<const float4*>(a);
-                for (int i = lane + 32 * part; i < Lay::REC / 4; i += 32 * NW) dst[i] = src[i];
+                float4* dst = reinterpret_cast<float4*>(grec + ((sq * S + k) * (int64_t)Lay::GREC));
+                const float4* src = reinterpret_cast<const float4*>(a + Lay::XREC);
+                for (int i = lane + 32 * part; i < Lay::GREC / 4; i += 32 * NW) dst[i] = src[i];
+                if (!SAVED) {
+                    float4* xd = reinterpret_cast<float4*>(xrec + ((sq * S + k) * (int64_t)Lay::XREC));
+                    const float4* xsrc = reinterpret_cast<const float4*>(a);
+                    for (int i = lane + 32 * part; i < Lay::XREC / 4; i += 32 * NW) xd[i] = xsrc[i];
+                }
             }
             team_sync<NW>(bar);
         }
@@ -906,14 +945,6 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
 // weight gradients from the records: every thread owns a fixed set of weight-gradient entries in
 // registers and streams over this CTA's records (double-buffered cp.async); one slab per CTA.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // acc[q] += sum_{r<3} x[w + 16 q][r] g[lane][r]
 template <int NQ>
 __device__ __forceinline__ void wg_obj(const float* x, const float* g, int wp, int lane, float* acc) {
@@ -940,7 +971,8 @@ __device__ __forceinline__ void wg_pair(const float* x, const float* g, int wp, 
 }
 
 __global__ void __launch_bounds__(512, 1) dynloop_wgrad_kernel(stove_gnn_cfg c, GnnLayout L, int64_t nrec,
-                                                               const float* __restrict__ rec,
+                                                               const float* __restrict__ xrec,
+                                                               const float* __restrict__ grec,
                                                                float* __restrict__ slabs) {
     using Lay = BwdLay;
     constexpr int REC = Lay::REC;
@@ -963,9 +995,12 @@ __global__ void __launch_bounds__(512, 1) dynloop_wgrad_kernel(stove_gnn_cfg c, 
     int nmine = 0;
     for (int64_t r = blockIdx.x; r < nrec; r += gridDim.x) ++nmine;
     auto issue = [&](int i) {
-        const float* src = rec + ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * REC;
+        const int64_t r = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        const float* xsrc = xrec + r * Lay::XREC;
+        const float* gsrc = grec + r * Lay::GREC;
         float* dst = smem + (i & 1) * REC;
-        for (int q = tid; q < REC / 4; q += blockDim.x) cp_async16(dst + 4 * q, src + 4 * q);
+        for (int q = tid; q < Lay::XREC / 4; q += blockDim.x) cp_async16(dst + 4 * q, xsrc + 4 * q);
+        for (int q = tid; q < Lay::GREC / 4; q += blockDim.x) cp_async16(dst + Lay::XREC + 4 * q, gsrc + 4 * q);
         cp_async_commit();
     };
     if (nmine > 0) issue(0);
@@ -1203,6 +1238,7 @@ static tk::LoopIO to_loop_io(const stove_dynloop_io* io) {
     l.logq = io->logq; l.trans = io->trans; l.reward = io->reward;
     l.g_z = io->g_z; l.g_logq = io->g_logq; l.g_trans = io->g_trans; l.g_reward = io->g_reward;
     l.g_z_init = io->g_z_init; l.g_sup = io->g_sup; l.g_sup_std = io->g_sup_std;
+    l.xrec = io->xrec;
     return l;
 }
 
@@ -1249,20 +1285,25 @@ extern "C" int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     tk::StageTable tab;
     tk::build_tables(cfg, L, &tw, &tab);
     const int NW = env_int("STOVE_DYNLOOP_NW", 2);
-    const int max_tpc = (int)((kMaxSmem / sizeof(float) - tw.total) / tk::FwdLay::TOTAL);
+    const bool save = io->xrec != nullptr;           // training: keep the activations for the backward pass
+    const int lay_total = save ? tk::BwdLay::TOTAL : tk::FwdLay::TOTAL;
+    const int max_tpc = (int)((kMaxSmem / sizeof(float) - tw.total) / lay_total);
     const int tpc = tk::pick_tpc(n, max_tpc < 7 ? max_tpc : 7);
-    const size_t smem = sizeof(float) * ((size_t)tw.total + (size_t)tpc * tk::FwdLay::TOTAL);
+    const size_t smem = sizeof(float) * ((size_t)tw.total + (size_t)tpc * lay_total);
     const int64_t groups = (n + tpc - 1) / tpc;
     const int ctas = (int)(groups < 148 ? groups : 148);
     const FuseCfg f = make_fuse(cfg, fuse);
     const tk::LoopIO lio = to_loop_io(io);
-    if (NW == 2) {
-        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        STOVE_KERNEL(K_DYNLOOP_FWD, st, tk::dynloop_fwd_kernel<2><<<ctas, 64 * tpc, smem, st>>>(*cfg, tw, tab, f, n, lio, weights));
-    } else {
-        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        STOVE_KERNEL(K_DYNLOOP_FWD, st, tk::dynloop_fwd_kernel<1><<<ctas, 32 * tpc, smem, st>>>(*cfg, tw, tab, f, n, lio, weights));
-    }
+#define DYNLOOP_FWD_LAUNCH(NW_, SAVE_)                                                                          \
+    do {                                                                                                        \
+        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_fwd_kernel<NW_, SAVE_>,                                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+        STOVE_KERNEL(K_DYNLOOP_FWD, st, tk::dynloop_fwd_kernel<NW_, SAVE_><<<ctas, 32 * NW_ * tpc, smem, st>>>( \
+            *cfg, tw, tab, f, n, lio, weights));                                                                \
+    } while (0)
+    if (NW == 2) { if (save) DYNLOOP_FWD_LAUNCH(2, true); else DYNLOOP_FWD_LAUNCH(2, false); }
+    else { if (save) DYNLOOP_FWD_LAUNCH(1, true); else DYNLOOP_FWD_LAUNCH(1, false); }
+#undef DYNLOOP_FWD_LAUNCH
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -1270,7 +1311,7 @@ extern "C" int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
 struct DynloopBwdPlan {
     bool fast;
     int tpc, ctas, wg_ctas;
-    size_t smem, rec_bytes, slab_bytes, carry_bytes, gnn_ws;
+    size_t smem, xrec_bytes, grec_bytes, slab_bytes, carry_bytes, gnn_ws;
 };
 
 extern "C" size_t stove_gnn_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n);
@@ -1295,7 +1336,8 @@ static DynloopBwdPlan dynloop_bwd_plan(const stove_gnn_cfg* cfg, const GnnLayout
     p.ctas = (int)(groups < 148 ? groups : 148);
     const int64_t nrec = n * S;
     p.wg_ctas = (int)(nrec < 148 ? nrec : 148);
-    p.rec_bytes = sizeof(float) * (size_t)nrec * tk::BwdLay::REC;
+    p.xrec_bytes = sizeof(float) * (size_t)nrec * tk::BwdLay::XREC;
+    p.grec_bytes = sizeof(float) * (size_t)nrec * tk::BwdLay::GREC;
     p.slab_bytes = sizeof(float) * (size_t)p.wg_ctas * L.total;
     return p;
 }
@@ -1304,7 +1346,14 @@ extern "C" size_t stove_dynloop_bwd_workspace(const stove_gnn_cfg* cfg, int64_t 
     if (gnn_check(cfg) || n <= 0 || T <= skip) return 0;
     GnnLayout L = gnn_layout(cfg);
     DynloopBwdPlan p = dynloop_bwd_plan(cfg, L, n, T - skip);
-    return p.fast ? p.rec_bytes + p.slab_bytes : p.carry_bytes + p.gnn_ws;
+    return p.fast ? p.xrec_bytes + p.grec_bytes + p.slab_bytes : p.carry_bytes + p.gnn_ws;
+}
+
+extern "C" int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, int skip) {
+    if (gnn_check(cfg) || n <= 0 || T <= skip) return 0;
+    GnnLayout L = gnn_layout(cfg);
+    if (!tk::supported(cfg, L) || env_int("STOVE_DYNLOOP_RECOMPUTE", 0)) return 0;
+    return (int64_t)n * (T - skip) * tk::BwdLay::XREC;
 }
 
 extern "C" int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
@@ -1351,20 +1400,26 @@ extern "C" int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     const int NW = env_int("STOVE_DYNLOOP_NW", 2);
     const FuseCfg f = make_fuse(cfg, fuse);
     const tk::LoopIO lio = to_loop_io(io);
-    float* rec = (float*)workspace;
-    float* slabs = (float*)((char*)workspace + p.rec_bytes);
-    if (NW == 2) {
-        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        STOVE_KERNEL(K_DYNLOOP_BWD, st, tk::dynloop_bwd_kernel<2><<<p.ctas, 64 * p.tpc, p.smem, st>>>(*cfg, tw, tab, f, n, lio, weights, rec));
-    } else {
-        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-        STOVE_KERNEL(K_DYNLOOP_BWD, st, tk::dynloop_bwd_kernel<1><<<p.ctas, 32 * p.tpc, p.smem, st>>>(*cfg, tw, tab, f, n, lio, weights, rec));
-    }
+    // workspace: gradient records | slabs | activation records (only if the forward pass kept none)
+    float* grec = (float*)workspace;
+    float* slabs = (float*)((char*)workspace + p.grec_bytes);
+    const bool saved = io->xrec != nullptr;
+    float* xrec = saved ? io->xrec : (float*)((char*)workspace + p.grec_bytes + p.slab_bytes);
+#define DYNLOOP_BWD_LAUNCH(NW_, SV_)                                                                              \
+    do {                                                                                                          \
+        STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_bwd_kernel<NW_, SV_>,                                         \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));               \
+        STOVE_KERNEL(K_DYNLOOP_BWD, st, tk::dynloop_bwd_kernel<NW_, SV_><<<p.ctas, 32 * NW_ * p.tpc, p.smem, st>>>( \
+            *cfg, tw, tab, f, n, lio, weights, xrec, grec));                                                      \
+    } while (0)
+    if (NW == 2) { if (saved) DYNLOOP_BWD_LAUNCH(2, true); else DYNLOOP_BWD_LAUNCH(2, false); }
+    else { if (saved) DYNLOOP_BWD_LAUNCH(1, true); else DYNLOOP_BWD_LAUNCH(1, false); }
+#undef DYNLOOP_BWD_LAUNCH
     STOVE_LAUNCH_CHECK();
     STOVE_CUDA(cudaMemsetAsync(slabs, 0, p.slab_bytes, st));
     const size_t wg_smem = sizeof(float) * 2 * tk::BwdLay::REC;
     STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-    STOVE_KERNEL(K_DYNLOOP_WGRAD, st, tk::dynloop_wgrad_kernel<<<p.wg_ctas, 512, wg_smem, st>>>(*cfg, L, n * S, rec, slabs));
+    STOVE_KERNEL(K_DYNLOOP_WGRAD, st, tk::dynloop_wgrad_kernel<<<p.wg_ctas, 512, wg_smem, st>>>(*cfg, L, n * S, xrec, grec, slabs));
     STOVE_LAUNCH_CHECK();
     STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, tk::dynloop_reduce_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(slabs, p.wg_ctas, L.total, g_weights));
     STOVE_LAUNCH_CHECK();

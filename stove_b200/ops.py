@@ -536,7 +536,15 @@ class DynamicsLoop(torch.autograd.Function):
         io = DynamicsLoop._io(T, skip, z_init, sup, sup_std, eps, actions, app)
         io.z, io.z_dyn, io.z_dyn_std, io.z_std = N.ptr(z), N.ptr(z_dyn), N.ptr(z_dyn_std), N.ptr(z_std)
         io.logq, io.trans, io.reward = N.ptr(logq), N.ptr(trans), N.ptr(rewards)
+        # training: the forward kernel keeps each step's activations so the backward chain does not recompute
+        xrec = None
+        if any(ctx.needs_input_grad):
+            nx = N.lib().stove_dynloop_xrec_floats(C.byref(cfg), n, T, skip)
+            if nx > 0:
+                xrec = torch.empty(nx, device=dev, dtype=torch.float32)
+        io.xrec = N.ptr(xrec)
         N.check(N.lib().stove_dynloop_fwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.stream()))
+        ctx.xrec = xrec
         ctx.save_for_backward(z_init, sup, sup_std, eps, actions, app, weights, z)
         ctx.meta = (cfg, fuse, skip)
         ctx.mark_non_differentiable(z_dyn, z_dyn_std, z_std)
@@ -564,6 +572,7 @@ class DynamicsLoop(torch.autograd.Function):
         io.z = N.ptr(z)
         io.g_z, io.g_logq, io.g_trans, io.g_reward = N.ptr(g_z), N.ptr(g_logq), N.ptr(g_trans), N.ptr(g_rewards)
         io.g_z_init, io.g_sup, io.g_sup_std = N.ptr(g_z_init), N.ptr(g_sup), N.ptr(g_sup_std)
+        io.xrec = N.ptr(ctx.xrec)
         N.check(N.lib().stove_dynloop_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
                                           N.ptr(ws), N.stream()))
         # the initial state is sup[:, skip-1] (+ noise latents): the loop itself leaves that slice zero

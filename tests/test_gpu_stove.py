@@ -11,8 +11,20 @@ pytestmark = pytest.mark.gpu
 VAL, GRAD = 3e-5, 3e-4
 
 
-@pytest.mark.parametrize('tag', list(VARIANTS))
-def test_stove_golden(tag):
+# alternative code paths of the dynamics-loop kernels (csrc/dynloop.cu), selected by environment
+# variables read at call time: one warp per sequence instead of two, backward recomputing each step
+# instead of reloading the activations kept by the forward pass, the generic CTA-wide kernels
+ALT_PATHS = {'ac@nw1': {'STOVE_DYNLOOP_NW': '1', 'STOVE_ROLLOUT_NW': '1'},
+             'ac@recompute': {'STOVE_DYNLOOP_RECOMPUTE': '1'},
+             'plain@nw1_recompute': {'STOVE_DYNLOOP_NW': '1', 'STOVE_DYNLOOP_RECOMPUTE': '1'},
+             'plain@generic': {'STOVE_DYNLOOP_GENERIC': '1'}}
+
+
+@pytest.mark.parametrize('tag', list(VARIANTS) + list(ALT_PATHS))
+def test_stove_golden(tag, monkeypatch):
+    for k, v in ALT_PATHS.get(tag, {}).items():
+        monkeypatch.setenv(k, v)
+    tag = tag.split('@')[0]
     kw, seed = VARIANTS[tag]
     g = load_golden('stove_' + tag)
     oc, sd, model = make_model(kw, seed, att_gain=float(g['att_gain']))
