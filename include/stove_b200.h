@@ -304,6 +304,12 @@ typedef struct {
 int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                       const stove_dynloop_io* io, const float* weights, void* stream);
 size_t stove_dynloop_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
+/* Same, with the weight-gradient kernels (which nothing on the sequential chain waits for) launched on
+ * `wgrad_stream` after the chain kernel on `stream`; there is NO join: g_weights and the workspace are
+ * valid on `wgrad_stream`.  Shapes without the fast path run everything on `stream`. */
+int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                       const stove_dynloop_io* io, const float* weights, float* g_weights,
+                       void* workspace, void* stream, void* wgrad_stream);
 /* floats of the optional activation buffer `xrec` (0: this shape has no such path) */
 int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
 int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,

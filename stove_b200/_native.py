@@ -108,6 +108,7 @@ SIGNATURES = {
     'stove_dynstep_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynstepIO), vp, vp, C.c_int, C.c_int, vp, vp]),
     'stove_dynloop_fwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp]),
     'stove_dynloop_bwd_workspace': (sz, [PG, i64, C.c_int, C.c_int]),
+    'stove_dynloop_bwd2': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp, vp]),
     'stove_dynloop_xrec_floats': (i64, [PG, i64, C.c_int, C.c_int]),
     'stove_dynloop_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp]),
     'stove_zall_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),

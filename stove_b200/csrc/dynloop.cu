@@ -1356,9 +1356,19 @@ extern "C" int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n
     return (int64_t)n * (T - skip) * tk::BwdLay::XREC;
 }
 
+extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                                  const stove_dynloop_io* io, const float* weights, float* g_weights,
+                                  void* workspace, void* stream, void* wgrad_stream);
+
 extern "C" int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
                                  const stove_dynloop_io* io, const float* weights, float* g_weights,
                                  void* workspace, void* stream) {
+    return stove_dynloop_bwd2(cfg, fuse, n, io, weights, g_weights, workspace, stream, stream);
+}
+
+extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
+                                  const stove_dynloop_io* io, const float* weights, float* g_weights,
+                                  void* workspace, void* stream, void* wgrad_stream) {
     int rc = dynloop_check(cfg, fuse, n, io, weights);
     if (rc) return rc;
     STOVE_CHECK_ARG(io->g_z_init && io->g_sup && io->g_sup_std && g_weights && workspace, "null gradient buffer");
@@ -1416,12 +1426,21 @@ extern "C" int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     else { if (saved) DYNLOOP_BWD_LAUNCH(1, true); else DYNLOOP_BWD_LAUNCH(1, false); }
 #undef DYNLOOP_BWD_LAUNCH
     STOVE_LAUNCH_CHECK();
-    STOVE_CUDA(cudaMemsetAsync(slabs, 0, p.slab_bytes, st));
+    // the weight gradients are not needed by anything downstream on the chain: they may run on
+    // another stream (no join here -- the caller consumes g_weights on that stream)
+    cudaStream_t wst = (cudaStream_t)wgrad_stream;
+    if (wst != st) {
+        StoveFork* fk = stove_fork_get(2);
+        if (!fk) return STOVE_ERR_CUDA;
+        STOVE_CUDA(cudaEventRecord(fk->fork_ev, st));
+        STOVE_CUDA(cudaStreamWaitEvent(wst, fk->fork_ev, 0));
+    }
+    STOVE_CUDA(cudaMemsetAsync(slabs, 0, p.slab_bytes, wst));
     const size_t wg_smem = sizeof(float) * 2 * tk::BwdLay::REC;
     STOVE_CUDA(cudaFuncSetAttribute(tk::dynloop_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-    STOVE_KERNEL(K_DYNLOOP_WGRAD, st, tk::dynloop_wgrad_kernel<<<p.wg_ctas, 512, wg_smem, st>>>(*cfg, L, n * S, xrec, grec, slabs));
+    STOVE_KERNEL(K_DYNLOOP_WGRAD, wst, tk::dynloop_wgrad_kernel<<<p.wg_ctas, 512, wg_smem, wst>>>(*cfg, L, n * S, xrec, grec, slabs));
     STOVE_LAUNCH_CHECK();
-    STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, tk::dynloop_reduce_kernel<<<(L.total + 255) / 256, 256, 0, st>>>(slabs, p.wg_ctas, L.total, g_weights));
+    STOVE_KERNEL(K_GNN_REDUCE_SLABS, wst, tk::dynloop_reduce_kernel<<<(L.total + 255) / 256, 256, 0, wst>>>(slabs, p.wg_ctas, L.total, g_weights));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

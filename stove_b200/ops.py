@@ -358,6 +358,17 @@ def split_tf32_cat(x, col_order=None, row_order=None):
     return col, row
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device):
+    """Library-wide side stream (per device) for work that is off the critical chain of a backward pass."""
+    key = (device.type, device.index)
+    if key not in _AUX_STREAMS:
+        _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _AUX_STREAMS[key]
+
+
 def _mm_tf32(a, b, out=None):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -422,6 +433,7 @@ class LstmEncoder(torch.autograd.Function):
                                       '(frames are data on the STOVE hot path)')
         g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
         g_whh = dh = g_c = None
+        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
         for t in reversed(range(steps)):
             g_col = torch.empty(n, 12 * H, device=dev, dtype=dt) if t > 0 else None
             g_row = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)
@@ -431,8 +443,12 @@ class LstmEncoder(torch.autograd.Function):
                                               N.ptr(g_c), N.ptr(g_col), N.ptr(g_row), N.ptr(g_sum),
                                               0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
             if t > 0:
-                # step t read h_{t-1}: weight gradient and the gradient flowing back into h_{t-1}
-                g_whh = _mm_tf32(g_row.t(), h_rows[t - 1], out=g_whh)
+                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain, the weight
+                # gradient (nothing waits for it until the end) goes to the side stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    g_whh = _mm_tf32(g_row.t(), h_rows[t - 1], out=g_whh)
+                g_row.record_stream(side)
                 dh = _mm_tf32(g_col, whh_row)
                 g_c = g_c_prev
         # after step 0 g_row holds the concatenated operand of the summed gate gradient
@@ -440,6 +456,9 @@ class LstmEncoder(torch.autograd.Function):
         g_b = g_sum.sum(0)
         if g_whh is None:
             g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
+        else:
+            cur.wait_stream(side)
+            g_whh.record_stream(cur)
         return None, g_wih, g_whh, g_b, g_b, None
 
 
@@ -517,7 +536,7 @@ class DynamicsLoop(torch.autograd.Function):
         return io
 
     @staticmethod
-    def forward(ctx, sup, sup_std, lat0, eps, actions, app, weights, cfg, fuse, skip):
+    def forward(ctx, sup, sup_std, lat0, eps, actions, app, weights, cfg, fuse, skip, wgrad_stream=None):
         sup, sup_std, eps = sup.contiguous(), sup_std.contiguous(), eps.contiguous()
         z_init = torch.cat([sup[:, skip - 1], lat0], -1)
         actions, app = _c(actions), _c(app)
@@ -547,6 +566,9 @@ class DynamicsLoop(torch.autograd.Function):
         ctx.xrec = xrec
         ctx.save_for_backward(z_init, sup, sup_std, eps, actions, app, weights, z)
         ctx.meta = (cfg, fuse, skip)
+        # stream on which `weights` was packed: its backward runs there too, so the weight-gradient
+        # kernels can leave the main chain (ops.DynamicsLoop.backward)
+        ctx.wgrad_stream = wgrad_stream
         ctx.mark_non_differentiable(z_dyn, z_dyn_std, z_std)
         if rewards is None:
             rewards = z_init.new_zeros(())
@@ -573,11 +595,19 @@ class DynamicsLoop(torch.autograd.Function):
         io.g_z, io.g_logq, io.g_trans, io.g_reward = N.ptr(g_z), N.ptr(g_logq), N.ptr(g_trans), N.ptr(g_rewards)
         io.g_z_init, io.g_sup, io.g_sup_std = N.ptr(g_z_init), N.ptr(g_sup), N.ptr(g_sup_std)
         io.xrec = N.ptr(ctx.xrec)
-        N.check(N.lib().stove_dynloop_bwd(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
-                                          N.ptr(ws), N.stream()))
+        cur = torch.cuda.current_stream(dev)
+        side = ctx.wgrad_stream if ctx.wgrad_stream is not None else cur
+        N.check(N.lib().stove_dynloop_bwd2(C.byref(cfg), C.byref(fuse), n, C.byref(io), N.ptr(weights), N.ptr(g_w),
+                                           N.ptr(ws), cur.cuda_stream, side.cuda_stream))
+        if side is not cur:
+            # g_w is consumed by the backward of the weight packing, which autograd runs on `side` (the
+            # stream of its forward); everything issued so far on `cur` is ordered before it
+            side.wait_stream(cur)
+            for t in (g_w, ws) + ((ctx.xrec,) if ctx.xrec is not None else ()):
+                t.record_stream(side)
         # the initial state is sup[:, skip-1] (+ noise latents): the loop itself leaves that slice zero
         g_sup[:, skip - 1].copy_(g_z_init[..., :6])
-        return g_sup, g_sup_std, None, None, None, None, g_w, None, None, None
+        return g_sup, g_sup_std, None, None, None, None, g_w, None, None, None, None
 
 
 class ZAll(torch.autograd.Function):

@@ -263,7 +263,8 @@ class Stove(nn.Module):
             t.record_stream(cur)
         z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
             z_sup_full, z_sup_std_full, lat0, eps, actions,
-            obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip)
+            obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip,
+            pack_stream)
         if not c.action_conditioned:
             rewards = torch.zeros(T - skip)
 
