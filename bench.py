@@ -411,8 +411,10 @@ def kernel_algorithmic_bytes(kernel, batch):
         # z_init, sup, sup_std, eps in; z, z_std, z_dyn, z_dyn_std, logq, trans out; weights once
         'dynloop_fwd': 4 * (batch * O * Z + batch * S * O * (12 + Z) + batch * S * (O * (2 * Z + 2 * (Z - 2)) + 2) + W_DYN),
         # z, sup, sup_std, eps, g_z, g_logq, g_trans in; g_sup, g_sup_std, g_z_init out; weights once
+        # (the per-step activation / gradient records are intermediates: 16.7 KB + 16.2 KB per
+        # sequence-step, L2-resident, they show up in `traffic` only)
         'dynloop_bwd': 4 * (batch * S * (O * (Z + 12 + Z + Z) + 2) + batch * S * O * 12 + batch * O * Z + W_DYN),
-        'dynloop_wgrad': 4 * (batch * S * 7824 + 148 * W_DYN),     # its input IS the per-step record stream
+        'dynloop_wgrad': 4 * (batch * S * 8224 + 148 * W_DYN),     # its input IS the per-step record stream
         'bw_transform': batch * T * D_bg * 4 * 4,
     }
     return table.get(kernel)
@@ -422,7 +424,8 @@ def kernel_flops(kernel, batch):
     """Useful fp32 FLOPs of one launch (2 x FMA count of the factorised GNN)."""
     S = T - 2
     step_fwd = 2 * 98208                   # one dynamics step of one sequence, O = 3, cl = 32
-    table = {'dynloop_fwd': batch * S * step_fwd, 'dynloop_bwd': batch * S * 2 * step_fwd,
+    # dynloop_bwd reloads the activations kept by the forward pass: input gradients only
+    table = {'dynloop_fwd': batch * S * step_fwd, 'dynloop_bwd': batch * S * step_fwd,
              'dynloop_wgrad': batch * S * step_fwd}
     return table.get(kernel)
 
