@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns device memory, streams and the autograd tape; 
 arithmetic of the hot path happens in the CUDA kernels of stove_b200/csrc.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -363,6 +364,8 @@ _AUX_STREAMS = {}
 
 def _aux_stream(device):
     """Library-wide side stream (per device) for work that is off the critical chain of a backward pass."""
+    if os.environ.get('STOVE_NO_FORK'):              # serial execution (per-kernel timing passes)
+        return torch.cuda.current_stream(device)
     key = (device.type, device.index)
     if key not in _AUX_STREAMS:
         _AUX_STREAMS[key] = torch.cuda.Stream(device=device)

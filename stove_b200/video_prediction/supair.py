@@ -6,6 +6,7 @@ glimpses and the sequential compositing masks come from one kernel per call
 (csrc/scene.cu), the two SPNs from the fused kernels in csrc/spn_obj.cu / spn_bg.cu.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -67,6 +68,8 @@ class Supair(nn.Module):
         short, latency-bound launches that leave most SMs idle on their own.  autograd replays
         each op's backward on the stream of its forward, so the two backward chains overlap too;
         a CUDA-graph capture records the fork/join as parallel branches."""
+        if os.environ.get('STOVE_NO_FORK'):          # serial execution (per-kernel timing passes)
+            return torch.cuda.current_stream(device)
         cache = self.__dict__.setdefault('_streams', {})
         key = (device.type, device.index, name)
         if key not in cache:
