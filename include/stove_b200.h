@@ -363,6 +363,33 @@ int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_pre
                           float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
                           float* g_c_prev, void* stream);
 
+/* One LSTM step of the recognition network on the tensor cores (encoder.py:50-51; csrc/lstm_tc.cu):
+ * gates = A B^T + addend with a tcgen05 (kind::tf32) GEMM over the K-concatenated 3xTF32 operands
+ * A [n][Kc] = (hi, hi, lo), B [4H][Kc] = (hi, lo, hi) (nn.LSTM gate order i, f, g, o along the rows), then the
+ * LSTM cell in the epilogue.  addend = bias [4H] (addend_is_bias) or the input-GEMM gates [n][4H]; gx_out
+ * (optional) receives GEMM + addend; outputs as stove_lstm_cell_fwd_x.  H % 32 == 0, Kc % 4 == 0. */
+int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t Kc, const float* A, const float* B, const float* addend,
+                             int addend_is_bias, const float* c_prev, float* gx_out, float* h_out, int64_t h_ld,
+                             float* c_out, float* act, float* h_col, float* h_row, void* stream);
+
+/* Output head of the recognition network (encoder.py:53-56): out = fc2(sigmoid(fc1(x))), x [R][K],
+ * w1 [J][K], b1 [J], w2 [P][J], b2 [P] (nn.Linear layouts); hidden [R][J] = sigmoid(fc1(x)) is kept for the
+ * backward pass.  K <= 256 and K % 32 == 0, J <= 64, P <= 16, else STOVE_ERR_UNSUPPORTED.  The backward
+ * call writes g_x [R][K] and the parameter gradients (overwritten, summed in a fixed order); ws =
+ * stove_enc_head_bwd_workspace bytes. */
+int stove_enc_head_fwd(int64_t R, int K, int J, int P, const float* x, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* hidden, float* out, void* stream);
+size_t stove_enc_head_bwd_workspace(int64_t R, int K, int J, int P);
+int stove_enc_head_bwd(int64_t R, int K, int J, int P, const float* x, const float* w1, const float* w2,
+                       const float* hidden, const float* g_out, float* g_x, float* g_w1, float* g_b1,
+                       float* g_w2, float* g_b2, float* ws, void* stream);
+
+/* Gather `count` device tensors into one flat fp32 buffer (the data-parallel gradient bucket):
+ * dst[offsets[i] .. offsets[i] + numels[i]) = srcs[i][0 .. numels[i]).  srcs / offsets / numels are HOST
+ * arrays (device addresses travel as kernel parameters: capturable, no table upload). */
+int stove_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* numels, int count,
+                      float* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

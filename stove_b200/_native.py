@@ -99,6 +99,11 @@ SIGNATURES = {
     'stove_split_tf32_cat': (C.c_int, [i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp]),
     'stove_lstm_cell_fwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     'stove_lstm_cell_bwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+    'stove_enc_head_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 7 + [vp]),
+    'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
+    'stove_enc_head_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 11 + [vp]),
+    'stove_gather_flat': (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     'stove_gnn_weight_count': (i64, [PG]),
     'stove_gnn_weight_offsets': (C.c_int, [PG, vp, C.c_int]),
     'stove_gnn_bwd_workspace': (sz, [PG, i64]),

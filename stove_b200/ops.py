@@ -402,25 +402,32 @@ class LstmEncoder(torch.autograd.Function):
         wih_col, _ = split_tf32_cat(w_ih, 1, None)
         whh_col, whh_row = split_tf32_cat(w_hh, 1, 1)
         bias = (b_ih + b_hh).contiguous()
-        gx = _mm_tf32(x_col, wih_col.t())
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
+        gx = torch.empty(n, 4 * H, device=dev, dtype=dt) if steps > 1 else None
         acts, cs, h_rows = [], [], []
-        gh = c_prev = None
+        h_col = c_prev = None
         for t in range(steps):
+            # one tcgen05 kernel per step (csrc/lstm_tc.cu): gate GEMM over the K-concatenated operands with
+            # the cell as its epilogue; step 0 contracts the frame with W_ih and leaves gx = x W_ih^T + b for
+            # the later steps, which contract h_{t-1} with W_hh and add gx
             c = torch.empty(n, H, device=dev, dtype=dt)
             act = torch.empty(n, 4 * H, device=dev, dtype=dt)
             more = t + 1 < steps
-            h_col = torch.empty(n, 3 * H, device=dev, dtype=dt) if more else None
+            h_col_next = torch.empty(n, 3 * H, device=dev, dtype=dt) if more else None
             h_row = torch.empty(3 * n, H, device=dev, dtype=dt) if more else None
-            N.check(lib.stove_lstm_cell_fwd_x(n, H, N.ptr(gx), N.ptr(bias), N.ptr(gh), N.ptr(c_prev),
-                                              out[:, t].data_ptr(), steps * H, N.ptr(c), N.ptr(act),
-                                              N.ptr(h_col), N.ptr(h_row), st))
+            if t == 0:
+                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, x_col.shape[1], N.ptr(x_col), N.ptr(wih_col), N.ptr(bias), 1,
+                                                     None, N.ptr(gx), out[:, t].data_ptr(), steps * H, N.ptr(c),
+                                                     N.ptr(act), N.ptr(h_col_next), N.ptr(h_row), st))
+            else:
+                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, 3 * H, N.ptr(h_col), N.ptr(whh_col), N.ptr(gx), 0,
+                                                     N.ptr(c_prev), None, out[:, t].data_ptr(), steps * H, N.ptr(c),
+                                                     N.ptr(act), N.ptr(h_col_next), N.ptr(h_row), st))
             acts.append(act)
             cs.append(c)
             if more:
                 h_rows.append(h_row)
-                gh = _mm_tf32(h_col, whh_col.t())
-            c_prev = c
+            h_col, c_prev = h_col_next, c
         ctx.stash = (x_row, wih_col, whh_row, acts, cs, h_rows, steps, H)
         return out
 
@@ -463,6 +470,65 @@ class LstmEncoder(torch.autograd.Function):
             cur.wait_stream(side)
             g_whh.record_stream(cur)
         return None, g_wih, g_whh, g_b, g_b, None
+
+
+class EncHead(torch.autograd.Function):
+    """fc2(sigmoid(fc1(x))) of the recognition network (encoder.py:53-56) in one kernel forward and three
+    backward (csrc/enc_head.cu).  x (..., K); w1 (J, K), b1 (J,), w2 (P, J), b2 (P,) -> (..., P)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+        N.require_cuda_f32(x2, w1, b1, w2, b2)
+        R, K = x2.shape
+        J, P = w1.shape[0], w2.shape[0]
+        hidden = torch.empty(R, J, device=x.device, dtype=x.dtype)
+        out = torch.empty(R, P, device=x.device, dtype=x.dtype)
+        N.check(N.lib().stove_enc_head_fwd(R, K, J, P, N.ptr(x2), N.ptr(w1), N.ptr(b1), N.ptr(w2), N.ptr(b2),
+                                           N.ptr(hidden), N.ptr(out), N.stream()))
+        ctx.save_for_backward(x2, w1, w2, hidden)
+        ctx.lead = lead
+        return out.view(*lead, P)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x2, w1, w2, hidden = ctx.saved_tensors
+        R, K = x2.shape
+        J, P = w1.shape[0], w2.shape[0]
+        g_out = g_out.reshape(R, P).contiguous()
+        dev, dt = x2.device, x2.dtype
+        g_x = torch.empty_like(x2)
+        g_w1, g_b1 = torch.empty_like(w1), torch.empty(J, device=dev, dtype=dt)
+        g_w2, g_b2 = torch.empty_like(w2), torch.empty(P, device=dev, dtype=dt)
+        ws = torch.empty(max(N.lib().stove_enc_head_bwd_workspace(R, K, J, P), 16) // 4, device=dev, dtype=torch.float32)
+        N.check(N.lib().stove_enc_head_bwd(R, K, J, P, N.ptr(x2), N.ptr(w1), N.ptr(w2), N.ptr(hidden), N.ptr(g_out),
+                                           N.ptr(g_x), N.ptr(g_w1), N.ptr(g_b1), N.ptr(g_w2), N.ptr(g_b2), N.ptr(ws),
+                                           N.stream()))
+        return g_x.view(*ctx.lead, K), g_w1, g_b1, g_w2, g_b2
+
+
+def gather_flat(tensors, out=None):
+    """Concatenate the flattened fp32 CUDA tensors into one flat buffer with one or two launches of the
+    library's gather kernel (the data-parallel gradient bucket).  Returns the flat tensor."""
+    tensors = [t.contiguous() for t in tensors]
+    N.require_cuda_f32(*tensors)
+    numels = [t.numel() for t in tensors]
+    total = sum(numels)
+    if out is None:
+        out = torch.empty(total, device=tensors[0].device, dtype=tensors[0].dtype)
+    n = len(tensors)
+    srcs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    offs, at = [], 0
+    for m in numels:
+        offs.append(at)
+        at += m
+    offsets = (C.c_int64 * n)(*offs)
+    nums = (C.c_int64 * n)(*numels)
+    N.check(N.lib().stove_gather_flat(C.cast(srcs, C.c_void_p), C.cast(offsets, C.c_void_p), C.cast(nums, C.c_void_p),
+                                      n, N.ptr(out), N.stream()))
+    return out
 
 
 # ----------------------------------------------------------------------------------------

@@ -51,7 +51,7 @@ class RnnStates(nn.Module):
             # ~4e-6 relative) and cell kernels that fold in the bias, the stacking and the splits
             zps = ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
                                         self.c.num_obj)
-            return self.fc2(torch.sigmoid(self.fc1(zps)))
+            return ops.EncHead.apply(zps, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
         return self.fc2(zps)
