@@ -119,7 +119,10 @@ def build_ac_model(device):
 
 def dist_setup(n_gpus):
     import torch.distributed as dist
-    os.environ['NCCL_DEBUG'] = os.environ.get('STOVE_NCCL_DEBUG', 'WARN')   # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner (and any debug output) to stdout unless told otherwise
+    if 'STOVE_NCCL_DEBUG' in os.environ:
+        os.environ['NCCL_DEBUG'] = os.environ['STOVE_NCCL_DEBUG']
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:

@@ -25,63 +25,93 @@ struct SupParams {
 
 __device__ __forceinline__ float sq(float v) { return v * v; }
 
-// errors err[a][j] = |prev_a - cur_j|^2 over the matching features
-__device__ void match_errors(const SupParams& p, const float* prev_pos, const float* prev_app,
-                             const float* cur_pos, const float* cur_app, float* err) {
-    for (int a = 0; a < p.O; ++a)
-        for (int j = 0; j < p.O; ++j) {
+// errors err[a][j] = |prev_a - cur_j|^2 over the matching features.  OC > 0: compile-time object count
+// (all loops unroll and every array index is static, so the working set stays in registers); OC = 0:
+// run-time count, arrays in local memory.
+template <int OC>
+__device__ __forceinline__ void match_errors(const SupParams& p, const float* prev_pos, const float* prev_app,
+                                             const float* cur_pos, const float* cur_app, float* err) {
+    const int O = OC ? OC : p.O;
+#pragma unroll
+    for (int a = 0; a < O; ++a)
+#pragma unroll
+        for (int j = 0; j < O; ++j) {
             float e = sq(prev_pos[a * 2] - cur_pos[j * 2]) + sq(prev_pos[a * 2 + 1] - cur_pos[j * 2 + 1]);
             if (p.match_app)
+#pragma unroll
                 for (int c = 0; c < 3; ++c) e += sq(prev_app[a * 3 + c] - cur_app[j * 3 + c]);
-            err[a * p.O + j] = e;
+            err[a * O + j] = e;
         }
 }
 
-__device__ void match_step(const SupParams& p, float* err, int* idx) {
-    const int O = p.O;
-    if (p.match_kind == 2) {                         // volatile: argmin over current for each previous
-        for (int a = 0; a < O; ++a) {
-            int best = 0;
-            for (int j = 1; j < O; ++j)
-                if (err[a * O + j] < err[a * O + best]) best = j;
-            idx[a] = best;
+template <int OC>
+__device__ __forceinline__ int row_argmin(const float* err, int a, int O) {
+    int best = 0;
+    float bv = err[a * O];
+#pragma unroll
+    for (int j = 1; j < (OC ? OC : O); ++j)
+        if (err[a * O + j] < bv) {
+            bv = err[a * O + j];
+            best = j;
         }
+    return best;
+}
+
+template <int OC>
+__device__ __forceinline__ void match_step(const SupParams& p, float* err, int* idx) {
+    const int O = OC ? OC : p.O;
+    if (p.match_kind == 2) {                         // volatile: argmin over current for each previous
+#pragma unroll
+        for (int a = 0; a < O; ++a) idx[a] = row_argmin<OC>(err, a, O);
         return;
     }
     if (p.match_kind == 0) {                         // 3_only
-        for (int a = 0; a < O; ++a) {
-            int best = 0;
-            for (int j = 1; j < O; ++j)
-                if (err[a * O + j] < err[a * O + best]) best = j;
-            idx[a] = best;
-        }
+#pragma unroll
+        for (int a = 0; a < O; ++a) idx[a] = row_argmin<OC>(err, a, O);
         const bool valid = idx[0] != idx[1] && idx[1] != idx[2] && idx[0] != idx[2];
         if (valid) return;
         // greedy repair (stove.py:278-295): row o takes its current argmin, that column is
         // then knocked out for every row
+#pragma unroll
         for (int o = 0; o < O; ++o) {
-            int best = 0;
-            for (int j = 1; j < O; ++j)
-                if (err[o * O + j] < err[o * O + best]) best = j;
+            const int best = row_argmin<OC>(err, o, O);
             idx[o] = best;
-            for (int a = 0; a < O; ++a) err[a * O + best] = 1e12f;
+#pragma unroll
+            for (int a = 0; a < O; ++a)
+#pragma unroll
+                for (int j = 0; j < O; ++j)
+                    if (j == best) err[a * O + j] = 1e12f;
         }
         return;
     }
     // greedy bipartite (stove.py:488-494): repeatedly take the global minimum, retire its row/column
+#pragma unroll 1
     for (int it = 0; it < O; ++it) {
-        int best = 0;
-        float mx = err[0];
-        for (int q = 1; q < O * O; ++q) {
-            if (err[q] < err[best]) best = q;
-            mx = fmaxf(mx, err[q]);
-        }
-        const int a = best / O, j = best - a * O;
-        idx[a] = j;
-        float big = mx + 1.f;
-        for (int q = 0; q < O; ++q) err[a * O + q] = big;
-        big = big + 1.f;                              // the reference re-evaluates max(errors) + 1
-        for (int q = 0; q < O; ++q) err[q * O + j] = big;
+        int ba = 0, bj = 0;
+        float bv = err[0], mx = err[0];
+#pragma unroll
+        for (int a = 0; a < O; ++a)
+#pragma unroll
+            for (int j = 0; j < O; ++j) {
+                const float e = err[a * O + j];
+                if (e < bv) {
+                    bv = e;
+                    ba = a;
+                    bj = j;
+                }
+                mx = fmaxf(mx, e);
+            }
+#pragma unroll
+        for (int a = 0; a < O; ++a)
+            if (a == ba) idx[a] = bj;
+        const float big = mx + 1.f, big2 = big + 1.f;      // the reference re-evaluates max(errors) + 1
+#pragma unroll
+        for (int a = 0; a < O; ++a)
+#pragma unroll
+            for (int j = 0; j < O; ++j) {
+                if (a == ba) err[a * O + j] = big;
+                if (j == bj) err[a * O + j] = big2;
+            }
     }
 }
 
@@ -92,6 +122,7 @@ __device__ void match_step(const SupParams& p, float* err, int* idx) {
 #define SG_WARPS 4
 __device__ __forceinline__ int sup_smem_floats(int T, int O) { return 2 * T * O * 8 + 2 * T * O; }
 
+template <int OC>
 __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
     SupParams p, int64_t n, const float* __restrict__ zp, const float* __restrict__ app,
     float* __restrict__ z_sup, float* __restrict__ z_full, float* __restrict__ std_full,
@@ -100,7 +131,7 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
     if (b >= n) return;
-    const int T = p.T, O = p.O, TO = T * O;
+    const int T = p.T, O = OC ? OC : p.O, TO = T * O;
     float* z = sg_smem + warp * sup_smem_floats(T, O);     // constrained, later the smoothed tensor
     float* zm = z + TO * 8;                                 // matched
     int* idx = reinterpret_cast<int*>(zm + TO * 8);         // [T][O]
@@ -121,25 +152,37 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
     __syncwarp();
     if (lane == 0) {
         // matching on positions scaled to [0, 1] ((z + 1) / 2, stove.py:220), detached
-        float prev_pos[SG_MAX_O * 2], cur_pos[SG_MAX_O * 2], prev_app[SG_MAX_O * 3], err[SG_MAX_O * SG_MAX_O];
-        int cur[SG_MAX_O];
+        constexpr int OM = OC ? OC : SG_MAX_O;
+        float prev_pos[OM * 2], cur_pos[OM * 2], prev_app[OM * 3], cur_app[OM * 3], err[OM * OM];
+        int cur[OM];
+#pragma unroll
         for (int a = 0; a < O; ++a) {
             idx[a] = a;
+#pragma unroll
             for (int d = 0; d < 2; ++d) prev_pos[a * 2 + d] = (z[a * 8 + 2 + d] + 1.f) * 0.5f;
-            if (asrc) for (int c = 0; c < 3; ++c) prev_app[a * 3 + c] = asrc[a * 3 + c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) prev_app[a * 3 + c] = asrc ? asrc[a * 3 + c] : 0.f;
         }
+#pragma unroll 1
         for (int t = 1; t < T; ++t) {
-            for (int a = 0; a < O; ++a)
+#pragma unroll
+            for (int a = 0; a < O; ++a) {
+#pragma unroll
                 for (int d = 0; d < 2; ++d) cur_pos[a * 2 + d] = (z[(t * O + a) * 8 + 2 + d] + 1.f) * 0.5f;
-            match_errors(p, prev_pos, asrc ? prev_app : nullptr, cur_pos, asrc ? asrc + t * O * 3 : nullptr, err);
-            match_step(p, err, cur);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cur_app[a * 3 + c] = asrc ? asrc[(t * O + a) * 3 + c] : 0.f;
+            }
+            match_errors<OC>(p, prev_pos, prev_app, cur_pos, cur_app, err);
+            match_step<OC>(p, err, cur);
+#pragma unroll
             for (int a = 0; a < O; ++a) {
                 idx[t * O + a] = cur[a];
+#pragma unroll
                 for (int d = 0; d < 2; ++d) prev_pos[a * 2 + d] = (z[(t * O + cur[a]) * 8 + 2 + d] + 1.f) * 0.5f;
-            }
-            if (asrc)
-                for (int a = 0; a < O; ++a)
+                if (asrc)
+#pragma unroll
                     for (int c = 0; c < 3; ++c) prev_app[a * 3 + c] = asrc[(t * O + cur[a]) * 3 + c];
+            }
         }
     }
     __syncwarp();
@@ -204,16 +247,29 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
     const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
     if (b >= n) return;
     const int T = p.T, O = p.O, TO = T * O;
-    float* gf = sg_smem + warp * sup_smem_floats(T, O);    // gradient w.r.t. the smoothed tensor
+    float* gf = sg_smem + warp * (TO * 48);                 // gradient w.r.t. the smoothed tensor
     float* gm = gf + TO * 8;                                // w.r.t. the matched tensor
-    float* sm_ = gm + TO * 8;                               // matched position stds [TO][2] (reuses the int area)
+    float* sm_ = gm + TO * 8;                               // matched position stds [TO][2]
+    float* gzs = sm_ + TO * 2;                              // staged inputs: every global load of the sequence is
+    float* gzf = gzs + TO * 4;                              // issued up front (independent, coalesced) instead of
+    float* gsf = gzf + TO * 6;                              // one dependent round trip to L2 per use
+    float* sfs = gsf + TO * 6;
+    float* zs = sfs + TO * 6;                               // raw encoder output of the sequence
     const float* src = zp + b * TO * 8;
     const int32_t* idx = idx_in + b * TO;
     const int32_t* flg = flag_in + b * TO;
+    for (int q = lane; q < TO * 4; q += 32) gzs[q] = g_z_sup ? __ldg(g_z_sup + b * TO * 4 + q) : 0.f;
+    for (int q = lane; q < TO * 6; q += 32) {
+        gzf[q] = g_z_full ? __ldg(g_z_full + b * TO * 6 + q) : 0.f;
+        gsf[q] = g_std_full ? __ldg(g_std_full + b * TO * 6 + q) : 0.f;
+        sfs[q] = __ldg(std_full + b * TO * 6 + q);
+    }
+    for (int q = lane; q < TO * 8; q += 32) zs[q] = __ldg(src + q);
+    __syncwarp();
     // matched position stds (features 6, 7); their smoothed values are recomputed on the fly
     for (int q = lane; q < TO * 2; q += 32) {
         const int ta = q >> 1, d = q & 1, t = ta / O;
-        sm_[q] = p.pos_var * sigmoidf_(__ldg(src + (t * O + idx[ta]) * 8 + 6 + d));
+        sm_[q] = p.pos_var * sigmoidf_(zs[(t * O + idx[ta]) * 8 + 6 + d]);
     }
     __syncwarp();
     auto fixed_std = [&](int ta, int d) {
@@ -222,25 +278,23 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
     // outputs -> smoothed tensor, gather form (each element written once)
     for (int q = lane; q < TO * 8; q += 32) {
         const int ta = q >> 3, f = q & 7, t = ta / O;
-        const int64_t o6 = (b * TO + ta) * 6;
+        const int o6 = ta * 6;
         float g = 0.f;
-        if (f < 4 && g_z_sup) g += __ldg(g_z_sup + (b * TO + ta) * 4 + f);
+        if (f < 4) g += gzs[ta * 4 + f];
         if (t > 0) {
-            if (f < 4 && g_z_full) g += __ldg(g_z_full + o6 + f);
-            if (f >= 4 && g_std_full) g += __ldg(g_std_full + o6 + f - 4);
+            if (f < 4) g += gzf[o6 + f];
+            if (f >= 4) g += gsf[o6 + f - 4];
         }
         if (f == 2 || f == 3) {
             const int d = f - 2;
-            if (g_z_full) {
-                if (t > 0) g += __ldg(g_z_full + o6 + 4 + d);
-                if (t + 1 < T) g -= __ldg(g_z_full + o6 + O * 6 + 4 + d);
-            }
+            if (t > 0) g += gzf[o6 + 4 + d];
+            if (t + 1 < T) g -= gzf[o6 + O * 6 + 4 + d];
         }
         if (f >= 6 && g_std_full) {
             const int d = f - 6;
             const float mine = fixed_std(ta, d);
-            if (t > 0) g += __ldg(g_std_full + o6 + 4 + d) / __ldg(std_full + o6 + 4 + d) * mine;
-            if (t + 1 < T) g += __ldg(g_std_full + o6 + O * 6 + 4 + d) / __ldg(std_full + o6 + O * 6 + 4 + d) * mine;
+            if (t > 0) g += gsf[o6 + 4 + d] / sfs[o6 + 4 + d] * mine;
+            if (t + 1 < T) g += gsf[o6 + O * 6 + 4 + d] / sfs[o6 + O * 6 + 4 + d] * mine;
         }
         gf[q] = g;
     }
@@ -264,7 +318,7 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
                          : f == 1 ? p.ratio_hi - p.ratio_lo
                          : f < 4 ? 2.f * p.pos_bound
                          : f < 6 ? p.scale_var : p.pos_var;
-        const float sgm = sigmoidf_(__ldg(src + q));
+        const float sgm = sigmoidf_(zs[q]);
         g_zp[b * TO * 8 + q] = g * sc * sgm * (1.f - sgm);
     }
 }
@@ -298,8 +352,14 @@ extern "C" int stove_sup_prepare_fwd(const stove_sup_cfg* cfg, int64_t n, const 
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * SG_WARPS * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
-    STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<<<(unsigned)((n + SG_WARPS - 1) / SG_WARPS), 32 * SG_WARPS, smem, s>>>(
-        p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
+    const unsigned blocks = (unsigned)((n + SG_WARPS - 1) / SG_WARPS);
+    if (p.O == 3) {
+        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<3><<<blocks, 32 * SG_WARPS, smem, s>>>(
+            p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
+    } else {
+        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<0><<<blocks, 32 * SG_WARPS, smem, s>>>(
+            p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
+    }
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -313,7 +373,8 @@ extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const 
     if (rc) return rc;
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
+    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(48 * p.T * p.O);
+    if (smem > 48 * 1024) STOVE_CUDA(cudaFuncSetAttribute(sup_prepare_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     STOVE_KERNEL(K_SUP_PREPARE_BWD, s, sup_prepare_bwd_kernel<<<(unsigned)((n + SG_WARPS - 1) / SG_WARPS), 32 * SG_WARPS, smem, s>>>(
         p, n, zp, idx, flag, std_full, g_z_sup, g_z_full, g_std_full, g_zp));
     STOVE_LAUNCH_CHECK();
