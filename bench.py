@@ -353,6 +353,21 @@ def run_b200(args):
                                  'metric': 'rollout_frames_per_sec', 'value': world * n2 * 100 * k2 / (ms2 * 1e-3),
                                  'unit': 'frames/s', 'ms_per_call': ms2 / k2}
 
+    # whole training iteration: + global-norm clip + Adam(amsgrad) on the flat bucket (train.py:471-473), one graph
+    if not args.no_graph:
+        from stove_b200.optim import FusedAdam
+        model_o = build_model(dev)
+        model_o.load_state_dict(model.state_dict())
+        engine_o = dp.DataParallel(model_o, broadcast=False)
+        opt = FusedAdam(model_o.parameters(), lr=2e-3, amsgrad=True, max_norm=1.0)
+        graphed_o = dp.GraphedStep(engine_o, dev_pool[0], optimizer=opt)
+        ms_o = timed(lambda i: graphed_o(dev_pool[i % POOL]), args.steps, args.warmup, world)
+        extra['train_step_with_optimizer'] = {
+            'workload': WORKLOAD + ' + clip_grad_norm(1) + Adam(amsgrad) step',
+            'metric': 'train_seqs_per_sec', 'value': world * BATCH * args.steps / (ms_o * 1e-3), 'unit': 'sequences/s',
+            'ms_per_step': ms_o / args.steps, 'loss_finite': bool(torch.isfinite(graphed_o.loss).item())}
+        del graphed_o
+
     def finish():
         # graphs that captured NCCL work must go before the communicator; a hard exit after the flush
         # avoids teardown hangs (the measurement is complete at this point)

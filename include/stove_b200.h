@@ -390,6 +390,19 @@ int stove_enc_head_bwd(int64_t R, int K, int J, int P, const float* x, const flo
 int stove_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* numels, int count,
                       float* dst, void* stream);
 
+/* Optimizer step of the reference trainer on the flat gradient bucket (train.py:46-49 Adam with amsgrad,
+ * :471-473 clip_grad_norm_(parameters, max_norm) then step).  params / offsets / numels are HOST arrays
+ * (count entries): parameter i occupies flat_grad[offsets[i] .. + numels[i]) and is updated in place at
+ * params[i]; exp_avg / exp_avg_sq / max_exp_avg_sq (NULL: no amsgrad) are flat like the bucket; partial
+ * holds stove_adam_workspace_floats() floats; lr and step are DEVICE scalars (step is incremented by the
+ * call, so a captured graph keeps counting); max_norm <= 0 disables clipping.  The clipped gradient is
+ * written back to flat_grad, as clip_grad_norm_ does. */
+int stove_adam_workspace_floats(void);
+int stove_adam_step(const void* const* params, const int64_t* offsets, const int64_t* numels, int count,
+                    int64_t total, float* flat_grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq,
+                    float* partial, const float* lr, float* step, float beta1, float beta2, float eps,
+                    float max_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

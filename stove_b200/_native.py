@@ -104,6 +104,8 @@ SIGNATURES = {
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
     'stove_enc_head_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 11 + [vp]),
     'stove_gather_flat': (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    'stove_adam_workspace_floats': (C.c_int, []),
+    'stove_adam_step': (C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp]),
     'stove_gnn_weight_count': (i64, [PG]),
     'stove_gnn_weight_offsets': (C.c_int, [PG, vp, C.c_int]),
     'stove_gnn_bwd_workspace': (sz, [PG, i64]),

@@ -75,6 +75,13 @@ class DataParallel:
         self.flat, self.live = flat, live
         return flat
 
+    def train_step(self, optimizer, x, step_counter=1, actions=None, reward_target=None):
+        """One full training iteration (train.py:438-473): forward, backward, all-reduce, then the fused
+        global-norm clip + Adam(amsgrad) on the flat bucket (`stove_b200.optim.FusedAdam`)."""
+        loss = self.forward_backward(x, step_counter, actions, reward_target)
+        optimizer.step(self.live, self.flat)
+        return loss
+
     def clip_and_step(self, optimizer, max_norm=1.0):
         """Global-norm clipping on the flat bucket (train.py:471-472), then the optimizer."""
         if max_norm is not None:
@@ -94,8 +101,12 @@ class GraphedStep:
     Inputs are copied into static buffers; `loss` and every `p.grad` live at fixed addresses.
     """
 
-    def __init__(self, engine, example_x, example_actions=None, example_reward_target=None, warmup=3):
+    def __init__(self, engine, example_x, example_actions=None, example_reward_target=None, warmup=3,
+                 optimizer=None):
+        """`optimizer` (a `stove_b200.optim.FusedAdam`): also capture the clip + Adam step, i.e. replay one
+        whole training iteration; its step counter and learning rate are device scalars."""
         self.engine = engine
+        self.optimizer = optimizer
         self.x = example_x.clone()
         self.actions = example_actions.clone() if example_actions is not None else None
         self.target = example_reward_target.clone() if example_reward_target is not None else None
@@ -106,11 +117,16 @@ class GraphedStep:
                 engine.forward_backward(self.x, 1, self.actions, self.target)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if optimizer is not None and optimizer.live is None:
+            optimizer._bind(engine.live, engine.flat)      # state is allocated (and zeroed) outside the graph
         from . import _native
         before = _native.lib().stove_launch_count(0)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss = engine.forward_backward(self.x, 1, self.actions, self.target)
+            if optimizer is not None:
+                self.loss = engine.train_step(optimizer, self.x, 1, self.actions, self.target)
+            else:
+                self.loss = engine.forward_backward(self.x, 1, self.actions, self.target)
         # kernels of the native library captured in (hence launched by every replay of) the graph
         self.native_launches = _native.lib().stove_launch_count(0) - before
 
