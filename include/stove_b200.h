@@ -99,13 +99,16 @@ int stove_spn2_fwd(const stove_spn2_struct* st, int64_t N, const float* x, const
                    const float* rlin, const float* rlog,
                    float* leaf_val, float* sum_val, float* out, void* stream);
 size_t stove_spn2_bwd_workspace(const stove_spn2_struct* st, int64_t N);
-/* g_x / g_marg may be NULL.  g_leaf, g_wlog, g_rlog are accumulated. */
+/* g_x / g_marg may be NULL.  g_leaf, g_wlog, g_rlog are accumulated.  The parameter-gradient kernels run on
+ * library-owned side streams; they are joined into `join_stream` (the stream that consumes the parameter
+ * gradients, e.g. where the packing's backward runs) or, if that is NULL, into `stream`.  With a separate
+ * join_stream the caller's stream only carries the node pass and the input gradients. */
 int stove_spn2_bwd(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg,
                    const float* leaf, const float* wlin, const float* wlog,
                    const float* rlin, const float* rlog,
                    const float* leaf_val, const float* sum_val, const float* out, const float* g_out,
                    float* g_x, float* g_marg, float* g_leaf, float* g_wlog, float* g_rlog,
-                   void* workspace, void* stream);
+                   void* workspace, void* stream, void* join_stream);
 
 /* ------------------------------------------------------------------------------------
  * Background SPN ("D1" structure: R root partitions, each the product of two Gauss
@@ -127,7 +130,7 @@ int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const float* x, const
                    const float* leaf, const float* rlin, const float* rlog,
                    const float* leaf_val, const float* out, const float* g_out,
                    float* g_x, float* g_marg, float* g_leaf, float* g_rlog,
-                   void* workspace, void* stream);
+                   void* workspace, void* stream, void* join_stream);
 
 /* ------------------------------------------------------------------------------------
  * Glimpse + marginalisation masks: Supair.patches_from_z (supair.py:241-276) and
@@ -375,14 +378,17 @@ int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t Kc, const float* A, const
 /* Output head of the recognition network (encoder.py:53-56): out = fc2(sigmoid(fc1(x))), x [R][K],
  * w1 [J][K], b1 [J], w2 [P][J], b2 [P] (nn.Linear layouts); hidden [R][J] = sigmoid(fc1(x)) is kept for the
  * backward pass.  K <= 256 and K % 32 == 0, J <= 64, P <= 16, else STOVE_ERR_UNSUPPORTED.  The backward
- * call writes g_x [R][K] and the parameter gradients (overwritten, summed in a fixed order); ws =
- * stove_enc_head_bwd_workspace bytes. */
+ * pass is two calls sharing ws (stove_enc_head_bwd_workspace bytes): _data writes g_x [R][K] -- what the rest
+ * of the backward chain waits for -- and leaves the pre-activation gradients in ws; _params (after _data, on
+ * any stream ordered behind it) turns them into the parameter gradients (overwritten, fixed summation order). */
 int stove_enc_head_fwd(int64_t R, int K, int J, int P, const float* x, const float* w1, const float* b1,
                        const float* w2, const float* b2, float* hidden, float* out, void* stream);
 size_t stove_enc_head_bwd_workspace(int64_t R, int K, int J, int P);
-int stove_enc_head_bwd(int64_t R, int K, int J, int P, const float* x, const float* w1, const float* w2,
-                       const float* hidden, const float* g_out, float* g_x, float* g_w1, float* g_b1,
-                       float* g_w2, float* g_b2, float* ws, void* stream);
+int stove_enc_head_bwd_data(int64_t R, int K, int J, int P, const float* w1, const float* w2,
+                            const float* hidden, const float* g_out, float* g_x, float* ws, void* stream);
+int stove_enc_head_bwd_params(int64_t R, int K, int J, int P, const float* x, const float* hidden,
+                              const float* g_out, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                              float* ws, void* stream);
 
 /* Gather `count` device tensors into one flat fp32 buffer (the data-parallel gradient bucket):
  * dst[offsets[i] .. offsets[i] + numels[i]) = srcs[i][0 .. numels[i]).  srcs / offsets / numels are HOST

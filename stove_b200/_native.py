@@ -85,11 +85,11 @@ SIGNATURES = {
     'stove_spn_pack_sum_bwd': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
     'stove_spn2_fwd': (C.c_int, [P2, i64] + [vp] * 10 + [vp]),
     'stove_spn2_bwd_workspace': (sz, [P2, i64]),
-    'stove_spn2_bwd': (C.c_int, [P2, i64] + [vp] * 17 + [vp]),
+    'stove_spn2_bwd': (C.c_int, [P2, i64] + [vp] * 17 + [vp, vp]),
     'stove_spn1_fwd_workspace': (sz, [P1, i64]),
     'stove_spn1_fwd': (C.c_int, [P1, i64] + [vp] * 8 + [vp]),
     'stove_spn1_bwd_workspace': (sz, [P1, i64]),
-    'stove_spn1_bwd': (C.c_int, [P1, i64] + [vp] * 13 + [vp]),
+    'stove_spn1_bwd': (C.c_int, [P1, i64] + [vp] * 13 + [vp, vp]),
     'stove_scene_fwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 6 + [vp]),
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
     'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
@@ -102,7 +102,8 @@ SIGNATURES = {
     'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     'stove_enc_head_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 7 + [vp]),
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
-    'stove_enc_head_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 11 + [vp]),
+    'stove_enc_head_bwd_data': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp]),
+    'stove_enc_head_bwd_params': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 8 + [vp]),
     'stove_gather_flat': (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     'stove_adam_workspace_floats': (C.c_int, []),
     'stove_adam_step': (C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp]),

@@ -935,8 +935,15 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
             }
             team_sync<NW>(bar);
         }
-        if (p0)
+        if (p0) {
             for (int e = lane; e < O * ZD; e += 32) io.g_z_init[sq * O * ZD + e] = a[Lay::GZ + e];
+            // the initial state is [sup[:, skip-1], noise latents] (stove.py:672-676): its first six gradient
+            // components belong to g_sup[:, skip-1] (zeroed by the host before the launch)
+            for (int e = lane; e < O * 6; e += 32) {
+                const int o = e / 6, j = e - o * 6;
+                io.g_sup[((sq * T + (io.skip - 1)) * O + o) * 6 + j] = a[Lay::GZ + o * ZD + j];
+            }
+        }
         team_sync<NW>(bar);
     }
 }
@@ -1208,6 +1215,16 @@ static int pick_tpc(int64_t n, int max_tpc) {
     if (t > max_tpc) t = max_tpc;
     return (int)t;
 }
+// g_sup[:, skip-1, :, :6] = g_z_init[..., :6] for the step-by-step path (the loop kernel writes it itself)
+__global__ void init_grad_to_sup_kernel(int64_t n, int T, int skip, int O, int Z, const float* __restrict__ g_z_init,
+                                        float* __restrict__ g_sup) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * O * 6) return;
+    const int j = (int)(i % 6);
+    const int64_t bo = i / 6, b = bo / O;
+    const int o = (int)(bo - b * O);
+    g_sup[((b * T + (skip - 1)) * O + o) * 6 + j] = g_z_init[bo * Z + j];
+}
 }  // namespace tk
 
 // generic per-step kernels (gnn.cu)
@@ -1402,6 +1419,10 @@ extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg
             rc = stove_dynstep_bwd(cfg, fuse, n, &s, weights, g_weights, k == S - 1, k == 0, ws, stream);
             if (rc) return rc;
         }
+        const int64_t items = n * O * 6;
+        STOVE_KERNEL(K_DYNSTEP_BWD, st, tk::init_grad_to_sup_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(
+            n, T, io->skip, O, Z, io->g_z_init, io->g_sup));
+        STOVE_LAUNCH_CHECK();
         return STOVE_OK;
     }
     tk::TW tw;

@@ -12,7 +12,8 @@
 #include "common.cuh"
 
 namespace eh {
-constexpr int KMAX = 256, JP = 64, PMAX = 16, ROWS = 32, THREADS = 256, LDW = JP + 1, PAR_ROWS = 16;
+constexpr int KMAX = 256, JP = 64, PMAX = 16, ROWS = 32, THREADS = 256, LDW = JP + 1, PAR_ROWS = 48;
+constexpr int FROWS = 48, FRW = FROWS / 8;        // forward: rows per CTA (one CTA per SM for 6144 rows) / per warp
 
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
 // staging without a register round trip: every copy of the CTA is in flight at once
@@ -36,10 +37,10 @@ head_fwd_kernel(int64_t R, int K, int J, int P, const float* __restrict__ x, con
     extern __shared__ float sm[];
     float* W1T = sm;                       // [K][LDW]
     float* XS = W1T + K * LDW;             // [ROWS][K]
-    float* W2S = XS + ROWS * K;            // [P][JP]
+    float* W2S = XS + FROWS * K;            // [P][JP]
     float* B1S = W2S + PMAX * JP;          // [JP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t r0 = (int64_t)blockIdx.x * ROWS;
+    const int64_t r0 = (int64_t)blockIdx.x * FROWS;
     // W1 [J][K] -> W1T [k][LDW] (4-byte async copies, coalesced along k); rows j >= J stay zero
     for (int i = tid; i < K * (JP - J); i += THREADS) W1T[(i / (JP - J)) * LDW + J + i % (JP - J)] = 0.f;
     {
@@ -56,27 +57,27 @@ head_fwd_kernel(int64_t R, int K, int J, int P, const float* __restrict__ x, con
     }
     if (tid < JP) B1S[tid] = tid < J ? __ldg(b1 + tid) : 0.f;
     const int K4 = K >> 2;
-    for (int i = tid; i < ROWS * K4; i += THREADS) {
+    for (int i = tid; i < FROWS * K4; i += THREADS) {
         const int r = i / K4, c = i - r * K4;
         if (r0 + r < R) cp16(XS + r * K + 4 * c, x + (r0 + r) * K + 4 * c);
         else reinterpret_cast<float4*>(XS + r * K)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     cp_wait_all();
     __syncthreads();
-    float acc[4][2];
+    float acc[FRW][2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
-    const float* xr = XS + warp * 4 * K;
+    for (int r = 0; r < FRW; ++r) acc[r][0] = acc[r][1] = 0.f;
+    const float* xr = XS + warp * FRW * K;
 #pragma unroll 2
     for (int k = 0; k < K; k += 4) {
-        float4 xv[4];
+        float4 xv[FRW];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) xv[r] = *reinterpret_cast<const float4*>(xr + r * K + k);
+        for (int r = 0; r < FRW; ++r) xv[r] = *reinterpret_cast<const float4*>(xr + r * K + k);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const float wa = W1T[(k + kk) * LDW + lane], wb = W1T[(k + kk) * LDW + lane + 32];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < FRW; ++r) {
                 const float xs = kk == 0 ? xv[r].x : kk == 1 ? xv[r].y : kk == 2 ? xv[r].z : xv[r].w;
                 acc[r][0] = fmaf(xs, wa, acc[r][0]);
                 acc[r][1] = fmaf(xs, wb, acc[r][1]);
@@ -84,8 +85,8 @@ head_fwd_kernel(int64_t R, int K, int J, int P, const float* __restrict__ x, con
         }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int64_t row = r0 + warp * 4 + r;
+    for (int r = 0; r < FRW; ++r) {
+        const int64_t row = r0 + warp * FRW + r;
         const float ha = lane < J ? sigm(acc[r][0] + B1S[lane]) : 0.f;
         const float hb = lane + 32 < J ? sigm(acc[r][1] + B1S[lane + 32]) : 0.f;
         if (row < R) {
@@ -183,10 +184,11 @@ __global__ void __launch_bounds__(THREADS)
 head_bwd_par_kernel(int64_t R, int K, int J, int P, int64_t rows_per_cta, const float* __restrict__ x,
                     const float* __restrict__ hidden, const float* __restrict__ g_out,
                     const float* __restrict__ g_pre, float* __restrict__ slabs) {
-    __shared__ __align__(16) float XS[PAR_ROWS][KMAX];
-    __shared__ __align__(16) float GP[PAR_ROWS][JP];
-    __shared__ float HS[PAR_ROWS][JP];
-    __shared__ float GO[PAR_ROWS][PMAX];
+    extern __shared__ __align__(16) float sm[];
+    float (*XS)[KMAX] = reinterpret_cast<float (*)[KMAX]>(sm);
+    float (*GP)[JP] = reinterpret_cast<float (*)[JP]>(sm + PAR_ROWS * KMAX);
+    float (*HS)[JP] = reinterpret_cast<float (*)[JP]>(sm + PAR_ROWS * (KMAX + JP));
+    float (*GO)[PMAX] = reinterpret_cast<float (*)[PMAX]>(sm + PAR_ROWS * (KMAX + 2 * JP));
     const int tid = threadIdx.x;
     const int64_t lo = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t hi = lo + rows_per_cta < R ? lo + rows_per_cta : R;
@@ -304,15 +306,15 @@ extern "C" int stove_enc_head_fwd(int64_t R, int K, int J, int P, const float* x
     }
     STOVE_CHECK_ARG((((uintptr_t)x) & 15) == 0, "x must be 16-byte aligned");
     if (R == 0) return STOVE_OK;
-    const size_t smem = (size_t)(K * LDW + ROWS * K + PMAX * JP + JP) * sizeof(float);
+    const size_t smem = (size_t)(K * LDW + FROWS * K + PMAX * JP + JP) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         STOVE_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)((KMAX * LDW + ROWS * KMAX + PMAX * JP + JP) * sizeof(float))));
+                                        (int)((KMAX * LDW + FROWS * KMAX + PMAX * JP + JP) * sizeof(float))));
         attr = true;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_ENC_HEAD_FWD, s, head_fwd_kernel<<<(unsigned)((R + ROWS - 1) / ROWS), THREADS, smem, s>>>(
+    STOVE_KERNEL(K_ENC_HEAD_FWD, s, head_fwd_kernel<<<(unsigned)((R + FROWS - 1) / FROWS), THREADS, smem, s>>>(
         R, K, J, P, x, w1, b1, w2, b2, hidden, out));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
@@ -324,26 +326,17 @@ extern "C" size_t stove_enc_head_bwd_workspace(int64_t R, int K, int J, int P) {
     return (size_t)(R * JP + (int64_t)par_ctas(R) * slab_floats(K, J)) * sizeof(float);
 }
 
-extern "C" int stove_enc_head_bwd(int64_t R, int K, int J, int P, const float* x, const float* w1, const float* w2,
-                                  const float* hidden, const float* g_out, float* g_x, float* g_w1, float* g_b1,
-                                  float* g_w2, float* g_b2, float* ws, void* stream) {
+extern "C" int stove_enc_head_bwd_data(int64_t R, int K, int J, int P, const float* w1, const float* w2,
+                                       const float* hidden, const float* g_out, float* g_x, float* ws, void* stream) {
     using namespace eh;
-    STOVE_CHECK_ARG(R >= 0 && x && w1 && w2 && hidden && g_out && g_x && g_w1 && g_b1 && g_w2 && g_b2 && ws, "bad argument");
+    STOVE_CHECK_ARG(R >= 0 && w1 && w2 && hidden && g_out && g_x && ws, "bad argument");
     if (!dims_ok(K, J, P)) {
-        stove_set_error("stove_enc_head_bwd: unsupported head %d -> %d -> %d", K, J, P);
+        stove_set_error("stove_enc_head_bwd_data: unsupported head %d -> %d -> %d", K, J, P);
         return STOVE_ERR_UNSUPPORTED;
     }
-    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)w1 | (uintptr_t)ws) & 15) == 0, "x, w1, ws must be 16-byte aligned");
+    STOVE_CHECK_ARG((((uintptr_t)w1 | (uintptr_t)ws) & 15) == 0, "w1, ws must be 16-byte aligned");
+    if (R == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (R == 0) {
-        STOVE_CUDA(cudaMemsetAsync(g_w1, 0, sizeof(float) * J * K, s));
-        STOVE_CUDA(cudaMemsetAsync(g_b1, 0, sizeof(float) * J, s));
-        STOVE_CUDA(cudaMemsetAsync(g_w2, 0, sizeof(float) * P * J, s));
-        STOVE_CUDA(cudaMemsetAsync(g_b2, 0, sizeof(float) * P, s));
-        return STOVE_OK;
-    }
-    float* g_pre = ws;
-    float* slabs = ws + R * JP;
     const size_t smem = (size_t)(JP * KMAX + PMAX * JP + JP * ROWS) * sizeof(float);
     static bool attr = false;
     if (!attr) {
@@ -351,13 +344,41 @@ extern "C" int stove_enc_head_bwd(int64_t R, int K, int J, int P, const float* x
         attr = true;
     }
     STOVE_KERNEL(K_ENC_HEAD_BWD_DATA, s, head_bwd_data_kernel<<<(unsigned)((R + ROWS - 1) / ROWS), THREADS, smem, s>>>(
-        R, K, J, P, w1, w2, hidden, g_out, g_pre, g_x));
+        R, K, J, P, w1, w2, hidden, g_out, ws, g_x));
     STOVE_LAUNCH_CHECK();
-    cudaStream_t ps = s;
+    return STOVE_OK;
+}
+
+extern "C" int stove_enc_head_bwd_params(int64_t R, int K, int J, int P, const float* x, const float* hidden,
+                                         const float* g_out, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                                         float* ws, void* stream) {
+    using namespace eh;
+    STOVE_CHECK_ARG(R >= 0 && x && hidden && g_out && g_w1 && g_b1 && g_w2 && g_b2 && ws, "bad argument");
+    if (!dims_ok(K, J, P)) {
+        stove_set_error("stove_enc_head_bwd_params: unsupported head %d -> %d -> %d", K, J, P);
+        return STOVE_ERR_UNSUPPORTED;
+    }
+    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)ws) & 15) == 0, "x, ws must be 16-byte aligned");
+    cudaStream_t ps = (cudaStream_t)stream;
+    if (R == 0) {
+        STOVE_CUDA(cudaMemsetAsync(g_w1, 0, sizeof(float) * J * K, ps));
+        STOVE_CUDA(cudaMemsetAsync(g_b1, 0, sizeof(float) * J, ps));
+        STOVE_CUDA(cudaMemsetAsync(g_w2, 0, sizeof(float) * P * J, ps));
+        STOVE_CUDA(cudaMemsetAsync(g_b2, 0, sizeof(float) * P, ps));
+        return STOVE_OK;
+    }
+    const float* g_pre = ws;
+    float* slabs = ws + R * JP;
     const int ctas = par_ctas(R);
     const int64_t rows_per_cta = ((R + ctas - 1) / ctas + PAR_ROWS - 1) / PAR_ROWS * PAR_ROWS;
     const int used = (int)((R + rows_per_cta - 1) / rows_per_cta);
-    STOVE_KERNEL(K_ENC_HEAD_BWD_PAR, ps, head_bwd_par_kernel<<<used, THREADS, 0, ps>>>(
+    const size_t psmem = (size_t)PAR_ROWS * (KMAX + 2 * JP + PMAX) * sizeof(float);
+    static bool pattr = false;
+    if (!pattr) {
+        STOVE_CUDA(cudaFuncSetAttribute(head_bwd_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        pattr = true;
+    }
+    STOVE_KERNEL(K_ENC_HEAD_BWD_PAR, ps, head_bwd_par_kernel<<<used, THREADS, psmem, ps>>>(
         R, K, J, P, rows_per_cta, x, hidden, g_out, g_pre, slabs));
     STOVE_LAUNCH_CHECK();
     const int sf = slab_floats(K, J);

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
     const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
     if (b >= n) return;
     const int T = p.T, O = p.O, TO = T * O;
-    float* gf = sg_smem + warp * (TO * 48);                 // gradient w.r.t. the smoothed tensor
+    float* gf = sg_smem + warp * (TO * 50);                 // gradient w.r.t. the smoothed tensor
     float* gm = gf + TO * 8;                                // w.r.t. the matched tensor
     float* sm_ = gm + TO * 8;                               // matched position stds [TO][2]
     float* gzs = sm_ + TO * 2;                              // staged inputs: every global load of the sequence is
@@ -255,9 +255,13 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_bwd_kernel(
     float* gsf = gzf + TO * 6;                              // one dependent round trip to L2 per use
     float* sfs = gsf + TO * 6;
     float* zs = sfs + TO * 6;                               // raw encoder output of the sequence
+    int* idx = reinterpret_cast<int*>(zs + TO * 8);         // [TO] matching permutation, [TO] smoothing flags
+    int* flg = idx + TO;
     const float* src = zp + b * TO * 8;
-    const int32_t* idx = idx_in + b * TO;
-    const int32_t* flg = flag_in + b * TO;
+    for (int q = lane; q < TO; q += 32) {
+        idx[q] = idx_in[b * TO + q];
+        flg[q] = flag_in[b * TO + q];
+    }
     for (int q = lane; q < TO * 4; q += 32) gzs[q] = g_z_sup ? __ldg(g_z_sup + b * TO * 4 + q) : 0.f;
     for (int q = lane; q < TO * 6; q += 32) {
         gzf[q] = g_z_full ? __ldg(g_z_full + b * TO * 6 + q) : 0.f;
@@ -373,7 +377,7 @@ extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const 
     if (rc) return rc;
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(48 * p.T * p.O);
+    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(50 * p.T * p.O);
     if (smem > 48 * 1024) STOVE_CUDA(cudaFuncSetAttribute(sup_prepare_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     STOVE_KERNEL(K_SUP_PREPARE_BWD, s, sup_prepare_bwd_kernel<<<(unsigned)((n + SG_WARPS - 1) / SG_WARPS), 32 * SG_WARPS, smem, s>>>(
         p, n, zp, idx, flag, std_full, g_z_sup, g_z_full, g_std_full, g_zp));

@@ -673,7 +673,8 @@ extern "C" size_t stove_spn1_bwd_workspace(const stove_spn1_struct* st, int64_t 
 extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const float* x, const float* marg,
                               const float* leaf, const float* rlin, const float* rlog,
                               const float* leaf_val, const float* out, const float* g_out, float* g_x,
-                              float* g_marg, float* g_leaf, float* g_rlog, void* workspace, void* stream) {
+                              float* g_marg, float* g_leaf, float* g_rlog, void* workspace, void* stream,
+                              void* join_stream) {
     int rc = check1(st);
     if (rc) return rc;
     STOVE_CHECK_ARG(N >= 0 && x && leaf && rlin && rlog && leaf_val && out && g_out && g_leaf && g_rlog && workspace,
@@ -731,6 +732,6 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
         STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s_root, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s_root>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
-    if (fk && (rc = stove_join(fk, s, 2))) return rc;
+    if (fk && (rc = stove_join(fk, join_stream ? (cudaStream_t)join_stream : s, 2))) return rc;   // see spn_obj.cu
     return STOVE_OK;
 }

@@ -845,7 +845,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
                            const float* leaf, const float* wlin, const float* wlog, const float* rlin,
                            const float* rlog, const float* leaf_val, const float* sum_val,
                            const float* out, const float* g_out, float* g_x, float* g_marg, float* g_leaf,
-                           float* g_wlog, float* g_rlog, void* workspace, cudaStream_t s) {
+                           float* g_wlog, float* g_rlog, void* workspace, cudaStream_t s, cudaStream_t join_s) {
     const int Q = 2 * st->R, D = st->D;
     const int64_t npad = round_up64(N, 32);
     Spn2Dev d = to_dev(st);
@@ -932,7 +932,10 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s_sum, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s_sum>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
         STOVE_LAUNCH_CHECK();
     }
-    if (fk && (rc = stove_join(fk, s, 2))) return rc;
+    // the parameter gradients are consumed by the backward of the parameter packing: when the caller names the
+    // stream that runs on, the side streams join THERE and the caller's stream continues right after the
+    // input-gradient kernel (what the rest of the backward chain waits for)
+    if (fk && (rc = stove_join(fk, join_s ? join_s : s, 2))) return rc;
     return STOVE_OK;
 }
 
@@ -966,7 +969,8 @@ extern "C" int stove_spn2_bwd(const stove_spn2_struct* st, int64_t N, const floa
                               const float* leaf, const float* wlin, const float* wlog, const float* rlin,
                               const float* rlog, const float* leaf_val, const float* sum_val,
                               const float* out, const float* g_out, float* g_x, float* g_marg,
-                              float* g_leaf, float* g_wlog, float* g_rlog, void* workspace, void* stream) {
+                              float* g_leaf, float* g_wlog, float* g_rlog, void* workspace, void* stream,
+                              void* join_stream) {
     int rc = check_struct(st);
     if (rc) return rc;
     STOVE_CHECK_ARG(N >= 0 && x && leaf && wlin && wlog && rlin && rlog && leaf_val && sum_val && out && g_out &&
@@ -975,7 +979,8 @@ extern "C" int stove_spn2_bwd(const stove_spn2_struct* st, int64_t N, const floa
     if (N == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
 #define CALL(G_, S_) spn2_bwd_launch<G_, S_>(st, N, x, marg, leaf, wlin, wlog, rlin, rlog, leaf_val, sum_val, \
-                                             out, g_out, g_x, g_marg, g_leaf, g_wlog, g_rlog, workspace, s)
+                                             out, g_out, g_x, g_marg, g_leaf, g_wlog, g_rlog, workspace, s, \
+                                             (cudaStream_t)join_stream)
     SPN2_DISPATCH(CALL)
 #undef CALL
 }

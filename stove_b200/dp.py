@@ -110,7 +110,11 @@ class GraphedStep:
         self.x = example_x.clone()
         self.actions = example_actions.clone() if example_actions is not None else None
         self.target = example_reward_target.clone() if example_reward_target is not None else None
-        side = torch.cuda.Stream()
+        # capture on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured
+        # on, and everything the library and the model fork off the chain (parameter-gradient kernels,
+        # parameter packing) runs on default = lowest-priority streams.  Several of those kernels fill every
+        # SM; with equal priorities they delay the next kernel of the chain by their whole duration.
+        side = torch.cuda.Stream(priority=-1)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -122,7 +126,7 @@ class GraphedStep:
         from . import _native
         before = _native.lib().stove_launch_count(0)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             if optimizer is not None:
                 self.loss = engine.train_step(optimizer, self.x, 1, self.actions, self.target)
             else:

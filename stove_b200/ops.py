@@ -102,14 +102,34 @@ def _npad(n):
     return (n + 31) // 32 * 32
 
 
+def _join_handle(stream):
+    """cudaStream_t of the stream that receives the parameter-gradient kernels (None: the current one)."""
+    if stream is None or os.environ.get('STOVE_NO_FORK'):
+        return None
+    return stream.cuda_stream
+
+
+def _keep_for(stream, *tensors):
+    """Kernels joined into `stream` still read / write these after the calling node returns."""
+    if stream is None or os.environ.get('STOVE_NO_FORK'):
+        return
+    for t in tensors:
+        if t is not None:
+            t.record_stream(stream)
+
+
 class Spn2(torch.autograd.Function):
     """Object SPN (D2 structure).  `tables` keeps the int32 structure tensors alive."""
 
     @staticmethod
-    def forward(ctx, x, marg, leaf, wlog, wlin, rlog, rlin, tables):
+    def forward(ctx, x, marg, leaf, wlog, wlin, rlog, rlin, tables, param_stream=None):
+        """`param_stream`: the stream the packed parameters were produced on (their backward runs there):
+        the parameter-gradient kernels of the backward pass are joined into it instead of the caller's
+        stream, which then only carries what the rest of the chain waits for."""
         x, marg = _c(x), _c(marg)
         N.require_cuda_f32(x, marg, leaf, wlog, wlin, rlog, rlin)
         st = tables.cstruct
+        ctx.param_stream = param_stream
         n = x.shape[0]
         npad = _npad(max(n, 1))
         Q, G, S = 2 * st.R, st.G, st.S
@@ -139,18 +159,20 @@ class Spn2(torch.autograd.Function):
         N.check(N.lib().stove_spn2_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(wlin),
                                        N.ptr(wlog), N.ptr(rlin), N.ptr(rlog), N.ptr(leaf_val), N.ptr(sum_val),
                                        N.ptr(out), N.ptr(g_out), N.ptr(g_x), N.ptr(g_m), N.ptr(g_leaf),
-                                       N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(ws), N.stream()))
-        return g_x, g_m, g_leaf, g_wlog, None, g_rlog, None, None
+                                       N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(ws), N.stream(), _join_handle(ctx.param_stream)))
+        _keep_for(ctx.param_stream, x, marg, leaf, wlin, rlin, ws, g_leaf, g_wlog, g_rlog)
+        return g_x, g_m, g_leaf, g_wlog, None, g_rlog, None, None, None
 
 
 class Spn1(torch.autograd.Function):
     """Background SPN (D1 structure)."""
 
     @staticmethod
-    def forward(ctx, x, marg, leaf, rlog, rlin, tables):
+    def forward(ctx, x, marg, leaf, rlog, rlin, tables, param_stream=None):
         x, marg = _c(x), _c(marg)
         N.require_cuda_f32(x, marg, leaf, rlog, rlin)
         st = tables.cstruct
+        ctx.param_stream = param_stream
         n = x.shape[0]
         npad = _npad(max(n, 1))
         leaf_val = torch.empty(st.R * 2 * st.G, npad, device=x.device, dtype=x.dtype)
@@ -178,8 +200,10 @@ class Spn1(torch.autograd.Function):
                          dtype=torch.float32)
         N.check(N.lib().stove_spn1_bwd(C.byref(st), n, N.ptr(x), N.ptr(marg), N.ptr(leaf), N.ptr(rlin),
                                        N.ptr(rlog), N.ptr(leaf_val), N.ptr(out), N.ptr(g_out), N.ptr(g_x),
-                                       N.ptr(g_m), N.ptr(g_leaf), N.ptr(g_rlog), N.ptr(ws), N.stream()))
-        return g_x, g_m, g_leaf, g_rlog, None, None
+                                       N.ptr(g_m), N.ptr(g_leaf), N.ptr(g_rlog), N.ptr(ws), N.stream(),
+                                       _join_handle(ctx.param_stream)))
+        _keep_for(ctx.param_stream, x, marg, leaf, rlin, ws, g_leaf, g_rlog)
+        return g_x, g_m, g_leaf, g_rlog, None, None, None
 
 
 # ----------------------------------------------------------------------------------------
@@ -393,7 +417,10 @@ class LstmEncoder(torch.autograd.Function):
     gate gradients that W_ih and the biases see."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps):
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None):
+        """With the head parameters (fc1 / fc2 of encoder.py:53-56) the node returns fc2(sigmoid(fc1(h_t)))
+        (n, steps, P) instead of h_t: one autograd node for the whole recognition network, whose backward
+        runs every parameter-gradient kernel (head, W_hh, biases) beside the chain h_t -> h_{t-1}."""
         N.require_cuda_f32(x, w_ih, w_hh, b_ih, b_hh)
         n, H = x.shape[0], w_hh.shape[1]
         dev, dt = x.device, x.dtype
@@ -429,6 +456,14 @@ class LstmEncoder(torch.autograd.Function):
                 h_rows.append(h_row)
             h_col, c_prev = h_col_next, c
         ctx.stash = (x_row, wih_col, whh_row, acts, cs, h_rows, steps, H)
+        ctx.head = None
+        if w1 is not None:
+            w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
+            N.require_cuda_f32(w1, b1, w2, b2)
+            hs = out.view(n * steps, H)
+            hidden, zp = _head_fwd(hs, w1, b1, w2, b2)
+            ctx.head = (hs, w1, w2, hidden)
+            return zp.view(n, steps, w2.shape[0])
         return out
 
     @staticmethod
@@ -438,12 +473,23 @@ class LstmEncoder(torch.autograd.Function):
         n = g_out.shape[0]
         dev, dt = g_out.device, g_out.dtype
         lib, st = N.lib(), N.stream()
+        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
+        g_head = (None, None, None, None)
+        if ctx.head is not None:
+            hs, w1, w2, hidden = ctx.head
+            g_zp = g_out.view(n * steps, w2.shape[0])
+            g_hs, ws = _head_bwd_data(hs, w1, w2, hidden, g_zp)       # on the chain: the LSTM backward needs it
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                              # off the chain: joined at the end
+                g_head = _head_bwd_params(hs, w1, w2, hidden, g_zp, ws)
+            for t_ in (ws, g_zp, hs, hidden) + g_head:
+                t_.record_stream(side)
+            g_out = g_hs.view(n, steps, H)
         if ctx.needs_input_grad[0]:
             raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
                                       '(frames are data on the STOVE hot path)')
         g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
         g_whh = dh = g_c = None
-        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
         for t in reversed(range(steps)):
             g_col = torch.empty(n, 12 * H, device=dev, dtype=dt) if t > 0 else None
             g_row = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)
@@ -461,20 +507,61 @@ class LstmEncoder(torch.autograd.Function):
                 g_row.record_stream(side)
                 dh = _mm_tf32(g_col, whh_row)
                 g_c = g_c_prev
-        # after step 0 g_row holds the concatenated operand of the summed gate gradient
+        # after step 0 g_row holds the concatenated operand of the summed gate gradient; the bias gradient
+        # (a column sum of the same tensor) runs beside the W_ih GEMM
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            g_b = g_sum.sum(0)
+            if g_whh is None:
+                g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
+        g_sum.record_stream(side)
         g_wih = _mm_tf32(g_row.t(), x_row) if ctx.needs_input_grad[1] else None
-        g_b = g_sum.sum(0)
-        if g_whh is None:
-            g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
-        else:
-            cur.wait_stream(side)
-            g_whh.record_stream(cur)
-        return None, g_wih, g_whh, g_b, g_b, None
+        cur.wait_stream(side)                      # every gradient is ready on the node's stream when it returns
+        for t_ in (g_whh, g_b) + g_head:
+            if t_ is not None:
+                t_.record_stream(cur)
+        return (None, g_wih, g_whh, g_b, g_b, None) + g_head
+
+
+def _head_fwd(x2, w1, b1, w2, b2):
+    R, K = x2.shape
+    J, P = w1.shape[0], w2.shape[0]
+    hidden = torch.empty(R, J, device=x2.device, dtype=x2.dtype)
+    out = torch.empty(R, P, device=x2.device, dtype=x2.dtype)
+    N.check(N.lib().stove_enc_head_fwd(R, K, J, P, N.ptr(x2), N.ptr(w1), N.ptr(b1), N.ptr(w2), N.ptr(b2),
+                                       N.ptr(hidden), N.ptr(out), N.stream()))
+    return hidden, out
+
+
+def _head_bwd_data(x2, w1, w2, hidden, g_out):
+    """-> (g_x, ws); ws carries the pre-activation gradients to _head_bwd_params."""
+    R, K = x2.shape
+    J, P = w1.shape[0], w2.shape[0]
+    g_x = torch.empty_like(x2)
+    ws = torch.empty(max(N.lib().stove_enc_head_bwd_workspace(R, K, J, P), 16) // 4, device=x2.device,
+                     dtype=torch.float32)
+    N.check(N.lib().stove_enc_head_bwd_data(R, K, J, P, N.ptr(w1), N.ptr(w2), N.ptr(hidden), N.ptr(g_out),
+                                            N.ptr(g_x), N.ptr(ws), N.stream()))
+    return g_x, ws
+
+
+def _head_bwd_params(x2, w1, w2, hidden, g_out, ws):
+    """Parameter gradients of the head on the CURRENT stream (must be ordered behind _head_bwd_data)."""
+    R, K = x2.shape
+    J, P = w1.shape[0], w2.shape[0]
+    dev, dt = x2.device, x2.dtype
+    g_w1, g_b1 = torch.empty_like(w1), torch.empty(J, device=dev, dtype=dt)
+    g_w2, g_b2 = torch.empty_like(w2), torch.empty(P, device=dev, dtype=dt)
+    N.check(N.lib().stove_enc_head_bwd_params(R, K, J, P, N.ptr(x2), N.ptr(hidden), N.ptr(g_out), N.ptr(g_w1),
+                                              N.ptr(g_b1), N.ptr(g_w2), N.ptr(g_b2), N.ptr(ws), N.stream()))
+    return g_w1, g_b1, g_w2, g_b2
 
 
 class EncHead(torch.autograd.Function):
     """fc2(sigmoid(fc1(x))) of the recognition network (encoder.py:53-56) in one kernel forward and three
-    backward (csrc/enc_head.cu).  x (..., K); w1 (J, K), b1 (J,), w2 (P, J), b2 (P,) -> (..., P)."""
+    backward (csrc/enc_head.cu).  x (..., K); w1 (J, K), b1 (J,), w2 (P, J), b2 (P,) -> (..., P).
+    Inside the fused recognition network (LstmEncoder with head parameters) the same kernels are used and the
+    parameter-gradient part runs beside the LSTM backward chain."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
@@ -482,31 +569,18 @@ class EncHead(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
         N.require_cuda_f32(x2, w1, b1, w2, b2)
-        R, K = x2.shape
-        J, P = w1.shape[0], w2.shape[0]
-        hidden = torch.empty(R, J, device=x.device, dtype=x.dtype)
-        out = torch.empty(R, P, device=x.device, dtype=x.dtype)
-        N.check(N.lib().stove_enc_head_fwd(R, K, J, P, N.ptr(x2), N.ptr(w1), N.ptr(b1), N.ptr(w2), N.ptr(b2),
-                                           N.ptr(hidden), N.ptr(out), N.stream()))
+        hidden, out = _head_fwd(x2, w1, b1, w2, b2)
         ctx.save_for_backward(x2, w1, w2, hidden)
         ctx.lead = lead
-        return out.view(*lead, P)
+        return out.view(*lead, w2.shape[0])
 
     @staticmethod
     def backward(ctx, g_out):
         x2, w1, w2, hidden = ctx.saved_tensors
-        R, K = x2.shape
-        J, P = w1.shape[0], w2.shape[0]
-        g_out = g_out.reshape(R, P).contiguous()
-        dev, dt = x2.device, x2.dtype
-        g_x = torch.empty_like(x2)
-        g_w1, g_b1 = torch.empty_like(w1), torch.empty(J, device=dev, dtype=dt)
-        g_w2, g_b2 = torch.empty_like(w2), torch.empty(P, device=dev, dtype=dt)
-        ws = torch.empty(max(N.lib().stove_enc_head_bwd_workspace(R, K, J, P), 16) // 4, device=dev, dtype=torch.float32)
-        N.check(N.lib().stove_enc_head_bwd(R, K, J, P, N.ptr(x2), N.ptr(w1), N.ptr(w2), N.ptr(hidden), N.ptr(g_out),
-                                           N.ptr(g_x), N.ptr(g_w1), N.ptr(g_b1), N.ptr(g_w2), N.ptr(g_b2), N.ptr(ws),
-                                           N.stream()))
-        return g_x.view(*ctx.lead, K), g_w1, g_b1, g_w2, g_b2
+        g_out = g_out.reshape(x2.shape[0], w2.shape[0]).contiguous()
+        g_x, ws = _head_bwd_data(x2, w1, w2, hidden, g_out)
+        g_w1, g_b1, g_w2, g_b2 = _head_bwd_params(x2, w1, w2, hidden, g_out, ws)
+        return g_x.view(*ctx.lead, x2.shape[1]), g_w1, g_b1, g_w2, g_b2
 
 
 def gather_flat(tensors, out=None):
@@ -674,8 +748,7 @@ class DynamicsLoop(torch.autograd.Function):
             side.wait_stream(cur)
             for t in (g_w, ws) + ((ctx.xrec,) if ctx.xrec is not None else ()):
                 t.record_stream(side)
-        # the initial state is sup[:, skip-1] (+ noise latents): the loop itself leaves that slice zero
-        g_sup[:, skip - 1].copy_(g_z_init[..., :6])
+        # (the library also routes g_z_init[..., :6] into g_sup[:, skip-1]: the initial state is that slice)
         return g_sup, g_sup_std, None, None, None, None, g_w, None, None, None, None
 
 

@@ -208,6 +208,9 @@ class PackedSpn:
     def __init__(self, kind, tables, leaf, wlog=None, wlin=None, rlog=None, rlin=None):
         self.kind, self.tables = kind, tables
         self.leaf, self.wlog, self.wlin, self.rlog, self.rlin = leaf, wlog, wlin, rlog, rlin
+        # stream the packing ran on: its backward runs there too, so the parameter-gradient kernels of the
+        # SPN backward can be handed to it and leave the chain of the caller's stream (ops.Spn2 / ops.Spn1)
+        self.stream = torch.cuda.current_stream(leaf.device) if leaf.is_cuda else None
 
 
 class RatSpn(nn.Module):
@@ -352,11 +355,15 @@ class RatSpn(nn.Module):
     def forward_packed(self, packed, inputs, marginalized=None):
         if inputs.shape[0] == 0:
             return inputs.new_zeros(0, self.num_classes)
+        pstream = packed.stream
+        if pstream is not None and pstream == torch.cuda.current_stream(inputs.device):
+            pstream = None
         if packed.kind == 'D2':
             out = ops.Spn2.apply(inputs, marginalized, packed.leaf, packed.wlog, packed.wlin, packed.rlog,
-                                 packed.rlin, packed.tables)
+                                 packed.rlin, packed.tables, pstream)
         else:
-            out = ops.Spn1.apply(inputs, marginalized, packed.leaf, packed.rlog, packed.rlin, packed.tables)
+            out = ops.Spn1.apply(inputs, marginalized, packed.leaf, packed.rlog, packed.rlin, packed.tables,
+                                 pstream)
         return out.unsqueeze(1)
 
     def forward(self, inputs, marginalized=None):

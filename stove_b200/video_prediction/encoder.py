@@ -49,9 +49,9 @@ class RnnStates(nn.Module):
             # one fused autograd node (ops.LstmEncoder): 3xTF32 GEMMs (every operand split once into a
             # TF32-exact part and a remainder; three tensor-core GEMMs reproduce the fp32 product to
             # ~4e-6 relative) and cell kernels that fold in the bias, the stacking and the splits
-            zps = ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
-                                        self.c.num_obj)
-            return ops.EncHead.apply(zps, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+            return ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
+                                         self.c.num_obj, self.fc1.weight, self.fc1.bias, self.fc2.weight,
+                                         self.fc2.bias)
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
         return self.fc2(zps)

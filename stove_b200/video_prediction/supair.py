@@ -71,9 +71,12 @@ class Supair(nn.Module):
         if os.environ.get('STOVE_NO_FORK'):          # serial execution (per-kernel timing passes)
             return torch.cuda.current_stream(device)
         cache = self.__dict__.setdefault('_streams', {})
-        key = (device.type, device.index, name)
+        # 'bg' carries kernels the main chain waits for: same priority as the caller's stream; the others
+        # ('pack') are off the chain: default (= lowest) priority
+        prio = torch.cuda.current_stream(device).priority if name == 'bg' else 0
+        key = (device.type, device.index, name, prio)
         if key not in cache:
-            cache[key] = torch.cuda.Stream(device=device)
+            cache[key] = torch.cuda.Stream(device=device, priority=prio)
         return cache[key]
 
     # -- likelihood ----------------------------------------------------------------------
@@ -88,17 +91,21 @@ class Supair(nn.Module):
         img_flat, marg_flat = x_img.flatten(start_dim=1), marg_bg.flatten(start_dim=1)
         cur = torch.cuda.current_stream(x_img.device)
         side = self._side_stream(x_img.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            if pk_bg is not None:
-                bg_loglik = self.bg_spn.forward_packed(pk_bg, img_flat, marg_flat)[:, 0]
-            else:
-                bg_loglik = self.bg_spn.forward(img_flat, marg_flat)[:, 0]
+        forked = torch.cuda.Event()
+        forked.record(cur)
+        # the object SPN is the longer of the two and is issued first: in the captured step the launch order of
+        # ready graph nodes follows their creation order, and the background kernels fill every SM
         patches_flat, marginalise_flat = patches.flatten(start_dim=1), marg_patch.flatten(start_dim=1)
         if pk_obj is not None:
             patches_loglik = self.obj_spn.forward_packed(pk_obj, patches_flat, marginalise_flat)[:, 0]
         else:
             patches_loglik = self.obj_spn.forward(patches_flat, marginalise_flat)[:, 0]
+        side.wait_event(forked)
+        with torch.cuda.stream(side):
+            if pk_bg is not None:
+                bg_loglik = self.bg_spn.forward_packed(pk_bg, img_flat, marg_flat)[:, 0]
+            else:
+                bg_loglik = self.bg_spn.forward(img_flat, marg_flat)[:, 0]
         cur.wait_stream(side)
         bg_loglik.record_stream(cur)
         extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marginalise_flat,

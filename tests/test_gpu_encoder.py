@@ -90,3 +90,27 @@ def test_gather_flat_equals_cat():
     assert torch.equal(flat, torch.cat([t.reshape(-1) for t in ts]))
     odd = [torch.rand(101, device='cuda')[1:], torch.rand(64, device='cuda')]        # unaligned source
     assert torch.equal(ops.gather_flat(odd), torch.cat(odd))
+
+
+def test_recognition_net_single_node_vs_fp64():
+    """LSTM + head as ONE autograd node (what RnnStates.forward uses): values and every gradient."""
+    from stove_b200 import ops
+    torch.manual_seed(3)
+    n, K, H, steps, J, P = 700, 1024, 256, 3, 50, 8
+    x = torch.rand(n, K, device='cuda') * (torch.rand(n, K, device='cuda') < 0.3)
+    ps = [((torch.rand(4 * H, K, device='cuda') - 0.5) * 0.12), ((torch.rand(4 * H, H, device='cuda') - 0.5) * 0.12),
+          ((torch.rand(4 * H, device='cuda') - 0.5) * 0.1), ((torch.rand(4 * H, device='cuda') - 0.5) * 0.1),
+          ((torch.rand(J, H, device='cuda') - 0.5) * 0.3), (torch.rand(J, device='cuda') - 0.5),
+          ((torch.rand(P, J, device='cuda') - 0.5) * 0.6), (torch.rand(P, device='cuda') - 0.5)]
+    ps = [p.requires_grad_(True) for p in ps]
+    out = ops.LstmEncoder.apply(x, *ps[:4], steps, *ps[4:])
+    wgt = torch.randn_like(out)
+    (out * wgt).sum().backward()
+    pd = [p.detach().double().requires_grad_(True) for p in ps]
+    h = _lstm_ref(x.double(), *pd[:4], steps)
+    ref = torch.sigmoid(h @ pd[4].t() + pd[5]) @ pd[6].t() + pd[7]
+    (ref * wgt.double()).sum().backward()
+    assert out.shape == (n, steps, P)
+    assert _rel(out, ref) < 3e-5
+    for p, q in zip(ps, pd):
+        assert _rel(p.grad, q.grad) < 2e-4
