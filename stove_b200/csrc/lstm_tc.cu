@@ -12,22 +12,22 @@
 // Tiling: CTA = 128 rows x 32 hidden units x all 4 gates.  The B tile is four TMA boxes of 32 weight
 // rows (gate g, hidden j0 .. j0+31), so accumulator column c = 32 g + j: after tcgen05.ld one thread
 // owns, for its row, i/f/g/o of the same hidden unit and the cell update is thread-local.
-//   warp 0     : TMA producer (one elected lane), 4-stage ring of (A 16 KB + B 16 KB); also fetches the
+//   warp 0     : TMA producer (one elected lane), 6- or 4-stage ring of (A 16 KB + B 16 KB); also fetches the
 //                epilogue's inputs (gates of the input GEMM, previous cell state) behind the first tiles
 //   warp 1     : MMA issuer (one elected lane): 4 x tcgen05.mma 128x128x8 per stage, tcgen05.commit
 //                releases the stage / signals the epilogue
-//   warps 2..5 : epilogue, warp w reads TMEM lanes 32 (w % 4) ..; results are staged in swizzled shared-memory
+//   warps 2..9 : epilogue, warp w reads TMEM lanes 32 (w % 4) .. (two warps per quarter, half the columns each); results are staged in swizzled shared-memory
 //                tiles (the operand ring is free by then) and leave with TMA stores
 // Grid = ceil(n / 128) x H / 32 (16 x 8 = 128 CTAs for 2048 frames, H = 256): one wave on 148 SMs.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace lt {
-constexpr int BM = 128, BH = 32, BN = 4 * BH, BK = 32, STAGES = 4, THREADS = 192;
+constexpr int BM = 128, BH = 32, BN = 4 * BH, BK = 32, EPI_WARPS = 8, THREADS = 64 + 32 * EPI_WARPS;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GATE_BYTES = BH * BK * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 5 * BM * BH * 4 + 1024 + 256;
 constexpr uint32_t TMEM_COLS = 128;
 // tcgen05 instruction descriptor, kind::tf32: D = f32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
 // both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24
@@ -83,6 +83,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the epilogue is instruction bound (one warp per scheduler): exp through MUFU.EX2 (__expf, ~2 ulp) and a fast
+// reciprocal; tanh(x) = 2 sigmoid(2x) - 1 keeps the absolute error ~2e-7, far inside the 3e-5 parity bound
+__device__ __forceinline__ float fsigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float ftanh(float v) { return 2.0f * fsigmoid(2.0f * v) - 1.0f; }
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ void ld8(const float* p, float* v) {
     const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -126,17 +130,35 @@ struct CellFwd {
     int64_t n;
     const float* bias;        // [4H] | null: the addend then comes through maps.add
     int has_cprev, has_gx, has_hsplit;
+    int debug;                // timing experiments (STOVE_LSTM_TC_DEBUG): 1 = no TMA stores, 2 = one k-block, 4 = no epilogue
 };
 
 constexpr int TILE_BYTES = BM * BH * 4;      // one [128 rows][32 floats] epilogue tile
-// dedicated epilogue staging behind the operand ring: 4 gate tiles (addend in, activations out) + cell state
-constexpr int OFF_G = STAGES * STAGE_BYTES, OFF_C = OFF_G + 4 * TILE_BYTES, OFF_BAR = OFF_C + TILE_BYTES;
-// the operand ring is free once the accumulator is complete: pre-activations out, h and its TF32 split
-constexpr int OFF_GX = 0, OFF_HF = 4 * TILE_BYTES, OFF_HHI = OFF_HF + TILE_BYTES, OFF_HLO = OFF_HHI + TILE_BYTES;
-static_assert(OFF_HLO + TILE_BYTES <= STAGES * STAGE_BYTES, "epilogue tiles must fit in the operand ring");
+// Shared-memory plan.  The mainloop is bound by the bytes it keeps in flight (ncu: tensor pipe 25 % busy,
+// L2 22 %, 403 MB through the crossbar for the input GEMM), so the operand ring is as deep as the SM allows:
+//   PREFETCH = false (step 0: the addend is the bias, no previous cell state): 6 stages = 192 KB; all
+//     epilogue tiles live in the ring once the accumulator is complete;
+//   PREFETCH = true (later steps): 4 stages + 80 KB behind the ring that receive the gates of the input GEMM
+//     and the previous cell state while the (short, K = 3H) mainloop runs.
+template <bool PREFETCH>
+struct Plan {
+    static constexpr int STAGES = PREFETCH ? 4 : 6;
+    static constexpr int RING = STAGES * STAGE_BYTES;
+    static constexpr int OFF_GX = 0, OFF_HF = 4 * TILE_BYTES, OFF_HHI = OFF_HF + TILE_BYTES, OFF_HLO = OFF_HHI + TILE_BYTES;
+    static constexpr int OFF_G = PREFETCH ? RING : OFF_HLO + TILE_BYTES, OFF_C = OFF_G + 4 * TILE_BYTES;
+    static constexpr int OFF_BAR = PREFETCH ? OFF_C + TILE_BYTES : RING;
+    static constexpr int SMEM = OFF_BAR + 256 + 1024;
+    static_assert(OFF_HLO + TILE_BYTES <= RING, "epilogue tiles must fit in the operand ring");
+    static_assert(PREFETCH || OFF_C + TILE_BYTES <= RING, "epilogue tiles must fit in the operand ring");
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+};
 
+template <bool PREFETCH>
 __global__ void __launch_bounds__(THREADS, 1)
 lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, CellFwd p) {
+    using P_ = Plan<PREFETCH>;
+    constexpr int STAGES = P_::STAGES, OFF_G = P_::OFF_G, OFF_C = P_::OFF_C, OFF_BAR = P_::OFF_BAR, OFF_GX = P_::OFF_GX,
+                  OFF_HF = P_::OFF_HF, OFF_HHI = P_::OFF_HHI, OFF_HLO = P_::OFF_HLO;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle-128B tiles need 1024-byte alignment
@@ -171,7 +193,7 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const bool wait_e = (p.bias == nullptr) || p.has_cprev;
+    const bool wait_e = PREFETCH && ((p.bias == nullptr) || p.has_cprev);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -216,11 +238,13 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
     } else {
         const int q = warp & 3;                        // the TMEM lane quarter this warp may read
         const int r = q * 32 + lane;                   // row of the tile
+        const int jc0 = ((warp - 2) >> 2) * (BH / 8 / (EPI_WARPS / 4));   // two warps per quarter split the columns
         mbar_wait(accum, 0);                           // all MMAs done: accumulator complete, operand ring free
+        if (!(p.debug & 4)) {
         if (wait_e) mbar_wait(ebar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int jc = 0; jc < BH / 8; ++jc) {
+        for (int jc = jc0; jc < jc0 + BH / 8 / (EPI_WARPS / 4); ++jc) {
             float v[4][8];
 #pragma unroll
             for (int g = 0; g < 4; ++g) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BH + jc * 8), v[g]);
@@ -241,8 +265,8 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
                 const float4 cp = p.has_cprev ? lds4(tiles + OFF_C + o) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 ig, fg, gg, og, c, h;
 #define LT_CELL(X)                                                                     \
-    ig.X = sigmoidf_(pre[0].X); fg.X = sigmoidf_(pre[1].X); gg.X = tanhf(pre[2].X);    \
-    og.X = sigmoidf_(pre[3].X); c.X = fg.X * cp.X + ig.X * gg.X; h.X = og.X * tanhf(c.X);
+    ig.X = fsigmoid(pre[0].X); fg.X = fsigmoid(pre[1].X); gg.X = ftanh(pre[2].X);      \
+    og.X = fsigmoid(pre[3].X); c.X = fg.X * cp.X + ig.X * gg.X; h.X = og.X * ftanh(c.X);
                 LT_CELL(x) LT_CELL(y) LT_CELL(z) LT_CELL(w)
 #undef LT_CELL
                 sts4(tiles + OFF_G + 0 * TILE_BYTES + o, ig);
@@ -259,8 +283,8 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to TMA
-        asm volatile("bar.sync 1, 128;" ::: "memory");                    // the four epilogue warps
-        if (warp == 2 && lane == 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // the epilogue warps
+        if (warp == 2 && lane == 0 && !(p.debug & 1)) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) tma_store_2d(&maps.act, tiles + OFF_G + g * TILE_BYTES, g * H + j0, m0);
             tma_store_2d(&maps.c, tiles + OFF_C, j0, m0);
@@ -279,6 +303,7 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the reads
+        }
         }
         __syncwarp();
     }
@@ -356,9 +381,11 @@ extern "C" int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t Kc, const floa
     if (rc == STOVE_OK) rc = make_map(&m.hcol, h_col ? h_col : c_out, n, h_col ? 3 * (int64_t)H : H, h_col ? 3 * (int64_t)H : H, BM);
     if (rc == STOVE_OK) rc = h_row ? make_map(&m.hrow, h_row, n, H, H, BM, 3) : make_map(&m.hrow, c_out, n, H, H, BM);
     if (rc != STOVE_OK) return rc;
+    const bool prefetch = !addend_is_bias || c_prev != nullptr;
     static bool attr_set = false;
     if (!attr_set) {
-        STOVE_CUDA(cudaFuncSetAttribute(lstm_gemm_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        STOVE_CUDA(cudaFuncSetAttribute(lstm_gemm_cell_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<true>::SMEM));
+        STOVE_CUDA(cudaFuncSetAttribute(lstm_gemm_cell_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<false>::SMEM));
         attr_set = true;
     }
     CellFwd p;
@@ -366,8 +393,14 @@ extern "C" int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t Kc, const floa
     p.has_cprev = c_prev != nullptr; p.has_gx = gx_out != nullptr; p.has_hsplit = h_col != nullptr;
     const dim3 grid((unsigned)((n + BM - 1) / BM), (unsigned)(H / BH));
     cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_LSTM_GEMM_CELL_FWD, s, lstm_gemm_cell_fwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(
-        m, (int)((Kc + BK - 1) / BK), p));
+    static const int dbg = getenv("STOVE_LSTM_TC_DEBUG") ? atoi(getenv("STOVE_LSTM_TC_DEBUG")) : 0;
+    p.debug = dbg;
+    const int num_kb = (dbg & 2) ? 1 : (int)((Kc + BK - 1) / BK);
+    if (prefetch) {
+        STOVE_KERNEL(K_LSTM_GEMM_CELL_FWD, s, lstm_gemm_cell_fwd_kernel<true><<<grid, THREADS, Plan<true>::SMEM, s>>>(m, num_kb, p));
+    } else {
+        STOVE_KERNEL(K_LSTM_GEMM_CELL_FWD, s, lstm_gemm_cell_fwd_kernel<false><<<grid, THREADS, Plan<false>::SMEM, s>>>(m, num_kb, p));
+    }
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
