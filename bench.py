@@ -306,17 +306,34 @@ def run_b200(args):
             fp32 = {'achieved_tflops': flops / (avg_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
                     'frac': flops / (avg_ms * 1e-3) / 1e12 / fp32_peak,
                     'peak_source': '148 SMs x 128 FP32 lanes x 2 x max SM clock'}
+        tensor = None
+        tflops = kernel_tensor_flops(top, BATCH)
+        if tflops:
+            # executed TF32 tensor-core FLOPs (3 x the fp32-equivalent product: hi*hi + hi*lo + lo*hi); the TF32
+            # dense peak is half the measured bf16 one
+            tpeak, tsrc = measured_tensor_peak()
+            tensor = {'achieved_tflops': tflops / (avg_ms * 1e-3) / 1e12, 'peak_tflops': tpeak,
+                      'frac': tflops / (avg_ms * 1e-3) / 1e12 / tpeak, 'peak_source': tsrc,
+                      'fp32_equivalent_tflops': tflops / 3 / (avg_ms * 1e-3) / 1e12}
         roofline = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': (achieved / peak) if achieved else None, 'traffic': measured_traffic(top),
-                    'fp32': fp32,
+                    'fp32': fp32, 'tensor': tensor,
                     'avg_launch_ms': avg_ms, 'launches_per_step': launches_top,
                     'algorithmic_bytes_per_launch': units, 'peak_source': peak_src,
                     'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
                     'native_serial_ms_over_step_ms': sum(share.values()) / (ms / args.steps),
-                    'note': 'all hot-path kernels are FP32-issue/latency bound, not HBM bound (DESIGN.md); '
-                            'the HBM fraction is reported because the contract asks for it, `fp32` is the '
-                            'bound that applies; `traffic` = DRAM bytes of one launch from the committed ncu '
-                            'capture (profiles/ncu_traffic.json)'}
+                    'hbm': {'achieved_gbs': achieved, 'peak_gbs': peak, 'frac': (achieved / peak) if achieved else None},
+                    'note': 'the SIMT hot-path kernels are FP32-issue/latency bound, not HBM bound (DESIGN.md): for them '
+                            'the HBM fraction is reported because the contract asks for it and `fp32` is the bound '
+                            'that applies; the recognition-LSTM kernel (tcgen05, 3xTF32) is reported against the '
+                            'tensor pipe; `hbm` always carries the algorithmic-bytes view; `traffic` = DRAM bytes '
+                            'of one launch from the committed ncu capture (profiles/ncu_traffic.json)'}
+
+    if roofline is not None and roofline.get('tensor'):
+        # the dominant kernel is the tcgen05 GEMM + LSTM cell: its bound is the tensor pipe
+        t = roofline['tensor']
+        roofline.update({'bound': 'tensor', 'achieved': t['achieved_tflops'], 'peak': t['peak_tflops'],
+                         'unit': 'TFLOP/s', 'frac': t['frac'], 'peak_source': t['peak_source']})
 
     # ---- rollouts (no collective: sequences shard over ranks) ----------------------------------
     extra = {}
@@ -438,6 +455,15 @@ def kernel_algorithmic_bytes(kernel, batch):
         'dynloop_bwd': 4 * (batch * S * (O * (Z + 12 + Z + Z) + 2) + batch * S * O * 12 + batch * O * Z + W_DYN),
         'dynloop_wgrad': 4 * (batch * S * 8224 + 148 * W_DYN),     # its input IS the per-step record stream
         'bw_transform': batch * T * D_bg * 4 * 4,
+        # recognition LSTM, average launch of the O per step: frames (once) + W_ih + W_hh in; h, c and the saved
+        # gate activations out; gx and the TF32 operand splits are intermediates
+        'lstm_gemm_cell_fwd': 4 * (batch * T * D_bg + 4 * 256 * (D_bg + 256) + O * batch * T * 256 * 6) // O,
+        'enc_head_fwd': 4 * batch * T * O * (256 + 50 + 8),
+        'enc_head_bwd_data': 4 * batch * T * O * (8 + 50 + 256),
+        'enc_head_bwd_par': 4 * batch * T * O * (256 + 50 + 8),
+        'lstm_cell_bwd': 4 * batch * T * 256 * (4 + 2 + 2 + 4),
+        'sup_prepare_fwd': 4 * batch * T * O * (8 + 4 + 6 + 6),
+        'sup_prepare_bwd': 4 * batch * T * O * (8 + 4 + 6 + 6 + 6 + 8),
     }
     return table.get(kernel)
 
@@ -452,6 +478,24 @@ def kernel_flops(kernel, batch):
              'dynloop_wgrad': batch * S * step_fwd,
              'scene_fwd': frames * 345e3, 'scene_bwd': frames * 2 * 345e3}      # 345 kFLOP/frame
     return table.get(kernel)
+
+
+def kernel_tensor_flops(kernel, batch):
+    """Executed tensor-core FLOPs of one (average) launch: the recognition LSTM runs 3xTF32, K-concatenated."""
+    n, H, K = batch * T, 256, RES * RES
+    table = {'lstm_gemm_cell_fwd': 3 * 2.0 * n * 4 * H * (K + (O - 1) * H) / O}
+    return table.get(kernel)
+
+
+def measured_tensor_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        for key in ('bf16_tflops', 'bf16_dense_tflops', 'tensor_bf16_tflops'):
+            if key in p:
+                return p[key] / 2.0, 'MEASURED_PEAKS.json %s / 2 (TF32 runs at half the bf16 rate)' % key
+    return 2250.0 / 2 / 2, 'fallback: nominal 1125 TFLOP/s dense TF32 / 2 (MEASURED_PEAKS.json has no bf16 figure)'
 
 
 def measured_traffic(kernel):
