@@ -257,6 +257,7 @@ class SupPrepare(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, zp, app, cfg):
+        ctx.set_materialize_grads(False)
         zp, app = zp.contiguous(), _c(app)
         N.require_cuda_f32(zp, app)
         n, T, O, _ = zp.shape
@@ -680,6 +681,7 @@ class DynamicsLoop(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sup, sup_std, lat0, eps, actions, app, weights, cfg, fuse, skip, wgrad_stream=None):
+        ctx.set_materialize_grads(False)       # undefined gradients arrive as None, not as zero-filled tensors
         sup, sup_std, eps = sup.contiguous(), sup_std.contiguous(), eps.contiguous()
         z_init = torch.cat([sup[:, skip - 1], lat0], -1)
         actions, app = _c(actions), _c(app)
@@ -726,7 +728,7 @@ class DynamicsLoop(torch.autograd.Function):
         T = sup.shape[1]
         dev, dt = z_init.device, z_init.dtype
         g_z, g_logq, g_trans = _c(g_z), _c(g_logq), _c(g_trans)
-        g_rewards = _c(g_rewards) if cfg.reward else None
+        g_rewards = _c(g_rewards) if (cfg.reward and g_rewards is not None and g_rewards.dim() > 0) else None
         g_z_init = torch.empty_like(z_init)
         g_sup = torch.empty_like(sup)
         g_sup_std = torch.empty_like(sup_std)

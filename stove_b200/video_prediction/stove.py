@@ -228,17 +228,31 @@ class Stove(nn.Module):
         c = self.c
         n, T = x.shape[0], x.shape[1]
         skip, cl, O = c.skip, c.cl, c.num_obj
-        # parameter packing (~20 short launches; and its backward) is independent of the frames: it runs
-        # on a side stream next to the encoder and is joined right before the dynamics loop
+        # Everything that does not depend on the encoder output runs on a side stream next to the encoder and is
+        # joined right before the dynamics loop: parameter packing (~20 short launches, and its backward), the
+        # noise of the step and the contiguous copy of the scored frames x[:, 1:].  The encoder is ISSUED first:
+        # in the captured step, ready graph nodes are launched in creation order, and the short side-stream
+        # launches would otherwise delay the first kernel of the chain by ~10 us.
         cur = torch.cuda.current_stream(x.device)
         pack_stream = self.sup._side_stream(x.device, 'pack')
-        pack_stream.wait_stream(cur)
-        with torch.cuda.stream(pack_stream):
-            packed_spn = self.sup.pack()
-            packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
+        forked = torch.cuda.Event()
+        forked.record(cur)
 
         # encoder -> (constrain, match, smooth, velocities) in one kernel (csrc/glue.cu)
         zp = self.sup.encoder(x.flatten(end_dim=1)).view(n, T, O, 8)
+
+        pack_stream.wait_event(forked)
+        with torch.cuda.stream(pack_stream):
+            packed_spn = self.sup.pack()
+            packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
+            # initial latents ~ N(0, 0.01^2) (stove.py:672-680).  The reference draws a second sample of the same
+            # shape for the initial dynamics std (logging only); both come from one generator launch
+            prior_shape = (n, O, cl // 2 - 4, 1)
+            pri = self._standard_normal_n(2, prior_shape, x)
+            lat0 = (0.01 * pri[0]).squeeze(-1)
+            eps = self._standard_normal_n(T - skip, (n, O, cl // 2 + 2), x)
+            x_scored = x[:, 1:].flatten(end_dim=1).contiguous()
+
         _app = None
         if c.debug_core_appearance or c.debug_match_appearance:
             with torch.no_grad():
@@ -248,18 +262,11 @@ class Stove(nn.Module):
         if _app is None:
             obj_appearances = None
 
-        # initial latents ~ N(0, 0.01^2) (stove.py:672-680).  The reference draws a second sample of the
-        # same shape for the initial dynamics std (logging only); both come from one generator launch
-        prior_shape = (n, O, cl // 2 - 4, 1)
-        pri = self._standard_normal_n(2, prior_shape, x)
-        lat0 = (0.01 * pri[0]).squeeze(-1)
-
         # dynamics loop: the whole loop is one persistent kernel (csrc/dynloop.cu), chained on the device
-        eps = self._standard_normal_n(T - skip, (n, O, cl // 2 + 2), x)
         cur.wait_stream(pack_stream)
         cfg_dyn, w_dyn = packed_dyn
-        for t in (w_dyn,) + tuple(v for pk in packed_spn if pk is not None for v in vars(pk).values()
-                                  if isinstance(v, torch.Tensor)):
+        for t in (w_dyn, lat0, eps, x_scored) + tuple(v for pk in packed_spn if pk is not None
+                                                        for v in vars(pk).values() if isinstance(v, torch.Tensor)):
             t.record_stream(cur)
         z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
             z_sup_full, z_sup_std_full, lat0, eps, actions,
@@ -272,7 +279,7 @@ class Stove(nn.Module):
         # pass over the frames x[:, 1:]: a single glimpse/mask launch and one launch family per SPN;
         # the per-frame terms are reduced to the ELBO by one kernel (csrc/glue.cu)
         z_all = ops.ZAll.apply(z_sup, z_s, skip)                                    # (n, T-1, O, 4) [sx, sy, x, y]
-        bg, patch_raw, overlap, extra = self.sup.likelihood_raw(x[:, 1:].flatten(end_dim=1),
+        bg, patch_raw, overlap, extra = self.sup.likelihood_raw(x_scored,
                                                                 z_all.flatten(end_dim=1), packed=packed_spn)
         average_elbo, stats = ops.ElboAssemble.apply(bg, patch_raw, z_all, overlap, log_z_n, trans_n, skip,
                                                      float(c.overlap_beta))
