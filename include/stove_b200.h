@@ -354,7 +354,7 @@ int stove_split_tf32_cat(int64_t rows, int cols, const float* x, float* colcat, 
 /* LSTM cell with the launches around it folded in (fused recognition network, encoder.py:28-57):
  * forward adds `bias` [4H], writes h into a strided output (row stride h_ld floats) and optionally its
  * K-concatenated TF32 operands h_col [n][3H] (hi, hi, lo) and h_row [3n][H] (hi, lo, hi); backward takes
- * g_h = g_h_a (row stride g_h_a_ld) + g_h_b (may be NULL), writes the concatenated operands of the gate
+ * g_h = g_h_a (row stride g_h_a_ld) + the g_h_b_parts split-K partials g_h_b [parts][n][H] (may be NULL), writes the concatenated operands of the gate
  * gradient g_col [n][12H] (optional) and g_row [3n][4H], both (hi, hi, lo) -- of the running sum if
  * split_acc -- and accumulates the gate gradient into g_acc (acc_mode 0: overwrite, 1: add).
  * g_c, c_prev, g_c_prev may be NULL. */
@@ -362,8 +362,8 @@ int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, 
                           const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
                           float* h_col, float* h_row, void* stream);
 int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
-                          const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
-                          float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
+                          const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, int g_h_b_parts,
+                          const float* g_c, float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
                           float* g_c_prev, void* stream);
 
 /* One LSTM step of the recognition network on the tensor cores (encoder.py:50-51; csrc/lstm_tc.cu):

@@ -98,7 +98,7 @@ SIGNATURES = {
     'stove_lstm_cell_bwd': (C.c_int, [i64, C.c_int] + [vp] * 7 + [vp]),
     'stove_split_tf32_cat': (C.c_int, [i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp]),
     'stove_lstm_cell_fwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
-    'stove_lstm_cell_bwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    'stove_lstm_cell_bwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
     'stove_enc_head_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 7 + [vp]),
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),

@@ -943,6 +943,10 @@ __global__ void __launch_bounds__(192, 1) dynloop_bwd_kernel(stove_gnn_cfg c, TW
                 const int o = e / 6, j = e - o * 6;
                 io.g_sup[((sq * T + (io.skip - 1)) * O + o) * 6 + j] = a[Lay::GZ + o * ZD + j];
             }
+            // time steps before `skip` receive no other gradient through the loop (no host memset: the kernel
+            // owns every element of g_sup / g_sup_std)
+            for (int e = lane; e < (io.skip - 1) * O * 6; e += 32) io.g_sup[sq * T * O * 6 + e] = 0.f;
+            for (int e = lane; e < io.skip * O * 6; e += 32) io.g_sup_std[sq * T * O * 6 + e] = 0.f;
         }
         team_sync<NW>(bar);
     }
@@ -1396,11 +1400,11 @@ extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg
         STOVE_CUDA(cudaMemsetAsync(g_weights, 0, sizeof(float) * L.total, st));
         return STOVE_OK;
     }
-    // time steps before `skip` receive no gradient through the loop
-    STOVE_CUDA(cudaMemsetAsync(io->g_sup, 0, sizeof(float) * (size_t)n * T * O * 6, st));
-    STOVE_CUDA(cudaMemsetAsync(io->g_sup_std, 0, sizeof(float) * (size_t)n * T * O * 6, st));
     DynloopBwdPlan p = dynloop_bwd_plan(cfg, L, n, S);
     if (!p.fast) {
+        // time steps before `skip` receive no gradient through the loop (the loop kernel zeroes them itself)
+        STOVE_CUDA(cudaMemsetAsync(io->g_sup, 0, sizeof(float) * (size_t)n * T * O * 6, st));
+        STOVE_CUDA(cudaMemsetAsync(io->g_sup_std, 0, sizeof(float) * (size_t)n * T * O * 6, st));
         float* carry[2] = {(float*)workspace, (float*)workspace + (size_t)n * O * Z};
         void* ws = (char*)workspace + p.carry_bytes;
         for (int k = S - 1; k >= 0; --k) {

@@ -727,7 +727,7 @@ __global__ void lstm_cell_fwd_x_kernel(int64_t n, int H, const float* __restrict
 __global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict__ act,
                                        const float* __restrict__ c_prev, const float* __restrict__ c_out,
                                        const float* __restrict__ g_h_a, int64_t g_h_a_ld,
-                                       const float* __restrict__ g_h_b, const float* __restrict__ g_c,
+                                       const float* __restrict__ g_h_b, int g_h_b_parts, const float* __restrict__ g_c,
                                        float* __restrict__ g_col, float* __restrict__ g_row,
                                        float* __restrict__ g_acc, int acc_mode, int split_acc,
                                        float* __restrict__ g_c_prev) {
@@ -738,7 +738,9 @@ __global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict
     const float* pa = act + b * 4 * H;
     const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
     const float tc = tanhf(c_out[i]);
-    const float gh = g_h_a[b * g_h_a_ld + k] + (g_h_b ? g_h_b[i] : 0.f);
+    float gh = g_h_a[b * g_h_a_ld + k];
+    if (g_h_b)                                   // split-K partial products of the hidden GEMM, [parts][n][H]
+        for (int part = 0; part < g_h_b_parts; ++part) gh += g_h_b[(int64_t)part * n * H + i];
     const float gc = (g_c ? g_c[i] : 0.f) + gh * og * (1.f - tc * tc);
     const float cp = c_prev ? c_prev[i] : 0.f;
     float g[4];
@@ -778,14 +780,15 @@ extern "C" int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const fl
 }
 
 extern "C" int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
-                                     const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, const float* g_c,
-                                     float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
-                                     float* g_c_prev, void* stream) {
+                                     const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, int g_h_b_parts,
+                                     const float* g_c, float* g_col, float* g_row, float* g_acc, int acc_mode,
+                                     int split_acc, float* g_c_prev, void* stream) {
     STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_h_a && g_row && g_acc && g_h_a_ld >= H, "bad argument");
+    STOVE_CHECK_ARG(!g_h_b || g_h_b_parts >= 1, "g_h_b_parts must be >= 1");
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_c, g_col, g_row, g_acc, acc_mode, split_acc, g_c_prev));
+        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_h_b_parts, g_c, g_col, g_row, g_acc, acc_mode, split_acc, g_c_prev));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -406,6 +406,24 @@ def _mm_tf32(a, b, out=None):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def _bmm_tf32(a, b):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        return torch.bmm(a, b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def _gemm_tn_splitk(a, b, parts):
+    """a^T @ b for a (K, M), b (K, N) as a split-K strided-batched TF32 GEMM + one reduction of the partials."""
+    K = a.shape[0]
+    if parts <= 1 or K % parts:
+        return _mm_tf32(a.t(), b)
+    part = _bmm_tf32(a.view(parts, K // parts, a.shape[1]).transpose(1, 2), b.view(parts, K // parts, b.shape[1]))
+    return part.sum(0)
+
+
 class LstmEncoder(torch.autograd.Function):
     """h_1 .. h_steps of a one-layer LSTM that is fed the SAME input x at every step from a zero state
     (the recognition network, encoder.py:50-51; nn.LSTM gate order and parameter shapes).
@@ -426,13 +444,23 @@ class LstmEncoder(torch.autograd.Function):
         n, H = x.shape[0], w_hh.shape[1]
         dev, dt = x.device, x.dtype
         lib, st = N.lib(), N.stream()
+        # the operand splits of the weights do not depend on the frames: they run beside the split of x
+        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            wih_col, _ = split_tf32_cat(w_ih, 1, None)
+            whh_col, whh_row = split_tf32_cat(w_hh, 1, 1)
+            bias = (b_ih + b_hh).contiguous()
         x_col, x_row = split_tf32_cat(x, 0, 1)             # x as left operand / as right operand of g^T x
-        wih_col, _ = split_tf32_cat(w_ih, 1, None)
-        whh_col, whh_row = split_tf32_cat(w_hh, 1, 1)
-        bias = (b_ih + b_hh).contiguous()
+        cur.wait_stream(side)
+        for t_ in (wih_col, whh_col, whh_row, bias):
+            t_.record_stream(cur)
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
         gx = torch.empty(n, 4 * H, device=dev, dtype=dt) if steps > 1 else None
-        acts, cs, h_rows = [], [], []
+        acts, cs = [], []
+        # row-concatenated TF32 operands of h_0 .. h_{steps-2}, stacked: the backward contracts them with the
+        # stacked gate gradients in ONE GEMM
+        h_rows = torch.empty(max(steps - 1, 0), 3 * n, H, device=dev, dtype=dt)
         h_col = c_prev = None
         for t in range(steps):
             # one tcgen05 kernel per step (csrc/lstm_tc.cu): gate GEMM over the K-concatenated operands with
@@ -442,7 +470,7 @@ class LstmEncoder(torch.autograd.Function):
             act = torch.empty(n, 4 * H, device=dev, dtype=dt)
             more = t + 1 < steps
             h_col_next = torch.empty(n, 3 * H, device=dev, dtype=dt) if more else None
-            h_row = torch.empty(3 * n, H, device=dev, dtype=dt) if more else None
+            h_row = h_rows[t] if more else None
             if t == 0:
                 N.check(lib.stove_lstm_gemm_cell_fwd(n, H, x_col.shape[1], N.ptr(x_col), N.ptr(wih_col), N.ptr(bias), 1,
                                                      None, N.ptr(gx), out[:, t].data_ptr(), steps * H, N.ptr(c),
@@ -453,8 +481,6 @@ class LstmEncoder(torch.autograd.Function):
                                                      N.ptr(act), N.ptr(h_col_next), N.ptr(h_row), st))
             acts.append(act)
             cs.append(c)
-            if more:
-                h_rows.append(h_row)
             h_col, c_prev = h_col_next, c
         ctx.stash = (x_row, wih_col, whh_row, acts, cs, h_rows, steps, H)
         ctx.head = None
@@ -490,33 +516,39 @@ class LstmEncoder(torch.autograd.Function):
             raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
                                       '(frames are data on the STOVE hot path)')
         g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
-        g_whh = dh = g_c = None
+        # The library picks 128 x 64 / 128 x 128 tiles for these GEMMs: 64 CTAs for the hidden-state GEMM
+        # (n x H, K = 12H), 32 for the W_hh gradient, 64 for the W_ih gradient -- a fraction of the 148 SMs.
+        # Splitting K into `parts` batches of one strided-batched GEMM fills the machine; the partial products
+        # are summed by the consumer (the cell kernel) or by one small reduction.
+        kparts = 2 if H % 2 == 0 else 1
+        g_rows = torch.empty(max(steps - 1, 0), 3 * n, 4 * H, device=dev, dtype=dt)   # steps 1 .. steps-1, stacked
+        g_row0 = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)                      # split of the summed gradient
+        dh = g_c = None
         for t in reversed(range(steps)):
             g_col = torch.empty(n, 12 * H, device=dev, dtype=dt) if t > 0 else None
-            g_row = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)
+            g_row = g_rows[t - 1] if t > 0 else g_row0
             g_c_prev = torch.empty(n, H, device=dev, dtype=dt) if t > 0 else None
             N.check(lib.stove_lstm_cell_bwd_x(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
                                               N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
-                                              N.ptr(g_c), N.ptr(g_col), N.ptr(g_row), N.ptr(g_sum),
+                                              kparts, N.ptr(g_c), N.ptr(g_col), N.ptr(g_row), N.ptr(g_sum),
                                               0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
             if t > 0:
-                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain, the weight
-                # gradient (nothing waits for it until the end) goes to the side stream
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    g_whh = _mm_tf32(g_row.t(), h_rows[t - 1], out=g_whh)
-                g_row.record_stream(side)
-                dh = _mm_tf32(g_col, whh_row)
+                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain
+                dh = _bmm_tf32(g_col.view(n, kparts, 12 * H // kparts).transpose(0, 1),
+                               whh_row.view(kparts, 12 * H // kparts, H))
                 g_c = g_c_prev
-        # after step 0 g_row holds the concatenated operand of the summed gate gradient; the bias gradient
-        # (a column sum of the same tensor) runs beside the W_ih GEMM
+        # weight and bias gradients: nothing waits for them until the node returns -> side stream, beside the
+        # W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is one GEMM over the stacked operands.
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             g_b = g_sum.sum(0)
-            if g_whh is None:
+            if steps > 1:
+                g_whh = _gemm_tn_splitk(g_rows.view(-1, 4 * H), h_rows.view(-1, H), 4)
+            else:
                 g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
-        g_sum.record_stream(side)
-        g_wih = _mm_tf32(g_row.t(), x_row) if ctx.needs_input_grad[1] else None
+        for t_ in (g_sum, g_rows, h_rows):
+            t_.record_stream(side)
+        g_wih = _gemm_tn_splitk(g_row0, x_row, 2) if ctx.needs_input_grad[1] else None
         cur.wait_stream(side)                      # every gradient is ready on the node's stream when it returns
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:

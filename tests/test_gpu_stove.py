@@ -158,3 +158,31 @@ def test_rollout_sampling_std_and_batch_independence():
     ck.true('batch_independent', torch.equal(big[100:131], sub) and torch.equal(rb[100:131], rs))
     ck.true('scale_constant', torch.equal(big[:, -1, :, :2], zl[..., :2]))
     ck.finish()
+
+
+def test_mcts_expand_and_rollout_equals_two_reference_calls():
+    """One persistent launch (expansion step + random rollout) = the reference's two rollout calls
+    (mcts_stove.py:94-137), checked against the fp64 oracle."""
+    from stove_b200 import mcts
+    kw = VARIANTS['ac'][0]
+    oc, sd, model = make_model(kw, 17, att_gain=0.5)
+    B, A, depth, O = 5, 9, 12, 3
+    g = torch.Generator().manual_seed(4)
+    leaf = torch.cat([0.2 + 0.3 * torch.rand(B, O, 2, generator=g), torch.rand(B, O, 16, generator=g) - 0.5], -1)
+    app = torch.rand(B, O, 3, generator=g)
+    ract = torch.randint(A, (B * A, depth), generator=g)
+    new_zs, r, r_roll = mcts.expand_and_rollout(model, leaf.cuda(), app.cuda(), A, depth, rollout_actions=ract)
+    assert new_zs.shape == (B * A, 1, O, 18) and r.shape == (B * A, 1, 1) and r_roll.shape == (B * A, depth, 1)
+    # the reference's two calls, in the oracle
+    P = {k: v.double() for k, v in sd.items()}
+    z0 = leaf.double().repeat_interleave(A, 0)
+    app0 = app.double().repeat_interleave(A, 0)
+    exp_act = torch.nn.functional.one_hot(torch.arange(A).repeat(B), A).double().view(B * A, 1, A)
+    with torch.no_grad():
+        z1, r1 = so.rollout(oc, P, z0, 1, exp_act, app0)
+        _, r2 = so.rollout(oc, P, z1[:, -1], depth, torch.nn.functional.one_hot(ract, A).double(), app0)
+    ck = Checker('mcts_expand_and_rollout')
+    ck.close('new_zs', new_zs, z1, 2e-5)
+    ck.close('r', r, r1, 2e-5)
+    ck.close('r_rollout', r_roll, r2, 1e-4 * depth)
+    ck.finish()
