@@ -436,7 +436,23 @@ class LstmEncoder(torch.autograd.Function):
     gate gradients that W_ih and the biases see."""
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None):
+    def prepare(w_ih, w_hh, b_ih, b_hh):
+        """Operand splits of the weights and the summed bias, on the library's side stream.  They depend on the
+        parameters only: issued at the very start of a step (before the frames are even transformed) they are
+        off the chain; pass the result as `prepared`."""
+        dev = w_ih.device
+        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            wih_col, _ = split_tf32_cat(w_ih.detach(), 1, None)
+            whh_col, whh_row = split_tf32_cat(w_hh.detach(), 1, 1)
+            bias = (b_ih.detach() + b_hh.detach()).contiguous()
+            done = torch.cuda.Event()
+            done.record(side)
+        return wih_col, whh_col, whh_row, bias, done
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None, prepared=None):
         """With the head parameters (fc1 / fc2 of encoder.py:53-56) the node returns fc2(sigmoid(fc1(h_t)))
         (n, steps, P) instead of h_t: one autograd node for the whole recognition network, whose backward
         runs every parameter-gradient kernel (head, W_hh, biases) beside the chain h_t -> h_{t-1}."""
@@ -444,15 +460,14 @@ class LstmEncoder(torch.autograd.Function):
         n, H = x.shape[0], w_hh.shape[1]
         dev, dt = x.device, x.dtype
         lib, st = N.lib(), N.stream()
-        # the operand splits of the weights do not depend on the frames: they run beside the split of x
-        cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            wih_col, _ = split_tf32_cat(w_ih, 1, None)
-            whh_col, whh_row = split_tf32_cat(w_hh, 1, 1)
-            bias = (b_ih + b_hh).contiguous()
+        # the operand splits of the weights do not depend on the frames: they run beside the split of x (or
+        # were issued even earlier through LstmEncoder.prepare)
+        cur = torch.cuda.current_stream(dev)
+        if prepared is None:
+            prepared = LstmEncoder.prepare(w_ih, w_hh, b_ih, b_hh)
+        wih_col, whh_col, whh_row, bias, done = prepared
         x_col, x_row = split_tf32_cat(x, 0, 1)             # x as left operand / as right operand of g^T x
-        cur.wait_stream(side)
+        cur.wait_event(done)
         for t_ in (wih_col, whh_col, whh_row, bias):
             t_.record_stream(cur)
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
@@ -537,8 +552,10 @@ class LstmEncoder(torch.autograd.Function):
                 dh = _bmm_tf32(g_col.view(n, kparts, 12 * H // kparts).transpose(0, 1),
                                whh_row.view(kparts, 12 * H // kparts, H))
                 g_c = g_c_prev
-        # weight and bias gradients: nothing waits for them until the node returns -> side stream, beside the
-        # W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is one GEMM over the stacked operands.
+        # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
+        # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands; it
+        # is issued after the chain's last hidden-state GEMM on purpose: started earlier it competes with the
+        # chain for L2 bandwidth (these GEMMs are operand-delivery bound) and the step gets slower.
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             g_b = g_sum.sum(0)
@@ -553,7 +570,7 @@ class LstmEncoder(torch.autograd.Function):
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
                 t_.record_stream(cur)
-        return (None, g_wih, g_whh, g_b, g_b, None) + g_head
+        return (None, g_wih, g_whh, g_b, g_b, None) + g_head + (None,)
 
 
 def _head_fwd(x2, w1, b1, w2, b2):

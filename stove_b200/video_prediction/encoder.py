@@ -32,6 +32,18 @@ class RnnStates(nn.Module):
         nn.init.constant_(self.fc1.bias, 0.1)
         nn.init.constant_(self.fc2.bias, 0.1)
 
+    def prepare(self):
+        """Issue the frame-independent part of the next forward pass (operand splits of the LSTM weights) now,
+        on a side stream; `forward` picks the result up.  Called by Stove.forward before the frames are
+        transformed, so that work is off the chain of the step."""
+        if os.environ.get('STOVE_ENCODER_FP32') or not self.rnn.weight_ih_l0.is_cuda:
+            return
+        rnn = self.rnn
+        ws = (rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
+        # remembered with the parameter versions: a result that has gone stale (in-place update in between)
+        # is dropped by `forward`
+        self._prepared = (tuple(w._version for w in ws), ops.LstmEncoder.prepare(*ws))
+
     def forward(self, frames):
         """frames (N, c, w, h) -> (N, O, 8): means and raw stds of (sx, sy/sx, x, y)."""
         x = frames.flatten(start_dim=1)
@@ -49,9 +61,15 @@ class RnnStates(nn.Module):
             # one fused autograd node (ops.LstmEncoder): 3xTF32 GEMMs (every operand split once into a
             # TF32-exact part and a remainder; three tensor-core GEMMs reproduce the fp32 product to
             # ~4e-6 relative) and cell kernels that fold in the bias, the stacking and the splits
+            prepared, self._prepared = getattr(self, '_prepared', None), None
+            if prepared is not None:
+                versions, prepared = prepared
+                if versions != tuple(w._version for w in (rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0,
+                                                          rnn.bias_hh_l0)):
+                    prepared = None
             return ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
                                          self.c.num_obj, self.fc1.weight, self.fc1.bias, self.fc2.weight,
-                                         self.fc2.bias)
+                                         self.fc2.bias, prepared)
         zps = torch.stack(outs, 1)
         zps = torch.sigmoid(self.fc1(zps))
         return self.fc2(zps)

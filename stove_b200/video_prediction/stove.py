@@ -346,6 +346,8 @@ class Stove(nn.Module):
         self.sup.step_counter = step_counter
         self.dyn.step_counter = step_counter
         x_color = x
+        if not pretrain:
+            self.sup.encoder.prepare()          # frame-independent encoder work, off the chain (side stream)
         if self.c.debug_bw:
             x = bw_transform(x)
         if pretrain:
