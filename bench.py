@@ -219,7 +219,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'sequences/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_b200(args):
@@ -425,7 +425,7 @@ def run_b200(args):
         'loss_finite': bool(all(map(lambda v: v == v, [float(l) for l in losses[-3:]]))),
     }
     line.update(extra)
-    print(json.dumps(line))
+    emit(line)
     finish()
 
 
@@ -508,7 +508,30 @@ def measured_traffic(kernel):
     return (t['dram_read_bytes'] + t['dram_write_bytes']) if t else None
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout to the ONE JSON line: NCCL prints its version banner from C straight to file descriptor 1 (and
+    libraries may print warnings); everything written to fd 1 from here on goes to stderr, the result line is
+    written to the original descriptor by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
