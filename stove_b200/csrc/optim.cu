@@ -11,8 +11,12 @@
 namespace opt {
 constexpr int NORM_CTAS = 128, MAX_T = 128, CHUNK = 4096;
 
+// partial[0 .. NORM_CTAS) = partial sums of squares; partial[NORM_CTAS] = lr / (1 - beta1^k), partial[NORM_CTAS + 1]
+// = sqrt(1 - beta2^k) for the step count k after the increment: the double-precision powers are evaluated ONCE
+// here (FP64 runs at 1/64 rate on this part; per CTA of the update kernel they cost ~5 us of latency each)
 __global__ void __launch_bounds__(256) adam_norm_kernel(const float* __restrict__ g, int64_t total,
-                                                        float* __restrict__ partial, float* __restrict__ step) {
+                                                        float* __restrict__ partial, float* __restrict__ step,
+                                                        const float* __restrict__ lr, float b1, float b2) {
     __shared__ float red[8];
     float s = 0.f;
     const int64_t n4 = total >> 2;
@@ -30,7 +34,12 @@ __global__ void __launch_bounds__(256) adam_norm_kernel(const float* __restrict_
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
         partial[blockIdx.x] = t;
-        if (blockIdx.x == 0) step[0] += 1.f;
+        if (blockIdx.x == 0) {
+            const float k = step[0] + 1.f;
+            step[0] = k;
+            partial[NORM_CTAS] = (float)((double)lr[0] / (1.0 - pow((double)b1, (double)k)));
+            partial[NORM_CTAS + 1] = (float)sqrt(1.0 - pow((double)b2, (double)k));
+        }
     }
 }
 
@@ -46,8 +55,7 @@ struct Hyper {
 
 __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ Table tb, Hyper h, float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v,
-                                                        float* __restrict__ vmax, const float* __restrict__ partial,
-                                                        const float* __restrict__ lr, const float* __restrict__ step) {
+                                                        float* __restrict__ vmax, const float* __restrict__ partial) {
     const int t = blockIdx.y;
     const int64_t num = tb.num[t];
     const int64_t lo = (int64_t)blockIdx.x * CHUNK;
@@ -60,11 +68,9 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ 
         if (threadIdx.x == 0) {
             const float norm = sqrtf(s);
             const float coef = h.max_norm > 0.f ? fminf(h.max_norm / (norm + 1e-6f), 1.f) : 1.f;
-            const double k = (double)step[0];
-            const double bc1 = 1.0 - pow((double)h.b1, k), bc2 = 1.0 - pow((double)h.b2, k);
             sh[0] = coef;
-            sh[1] = (float)((double)lr[0] / bc1);       // step size
-            sh[2] = (float)sqrt(bc2);
+            sh[1] = partial[NORM_CTAS];                 // step size lr / (1 - beta1^k)
+            sh[2] = partial[NORM_CTAS + 1];             // sqrt(1 - beta2^k)
         }
     }
     __syncthreads();
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const __grid_constant__ 
 }
 }  // namespace opt
 
-extern "C" int stove_adam_workspace_floats(void) { return opt::NORM_CTAS; }
+extern "C" int stove_adam_workspace_floats(void) { return opt::NORM_CTAS + 2; }
 
 extern "C" int stove_adam_step(const void* const* params, const int64_t* offsets, const int64_t* numels, int count,
                                int64_t total, float* flat_grad, float* exp_avg, float* exp_avg_sq,
@@ -102,7 +108,7 @@ extern "C" int stove_adam_step(const void* const* params, const int64_t* offsets
                     "bad argument");
     STOVE_CHECK_ARG((((uintptr_t)flat_grad) & 15) == 0, "flat_grad must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    STOVE_KERNEL(K_ADAM_NORM, st, adam_norm_kernel<<<NORM_CTAS, 256, 0, st>>>(flat_grad, total, partial, step));
+    STOVE_KERNEL(K_ADAM_NORM, st, adam_norm_kernel<<<NORM_CTAS, 256, 0, st>>>(flat_grad, total, partial, step, lr, beta1, beta2));
     STOVE_LAUNCH_CHECK();
     Hyper h;
     h.b1 = beta1; h.b2 = beta2; h.eps = eps; h.max_norm = max_norm; h.amsgrad = max_exp_avg_sq != nullptr;
@@ -114,7 +120,7 @@ extern "C" int stove_adam_step(const void* const* params, const int64_t* offsets
             if (k == 0) return STOVE_OK;
             const dim3 grid((unsigned)((mx + CHUNK - 1) / CHUNK), (unsigned)k);
             STOVE_KERNEL(K_ADAM_STEP, st, adam_step_kernel<<<grid, 256, 0, st>>>(tb, h, flat_grad, exp_avg, exp_avg_sq,
-                                                                                 max_exp_avg_sq, partial, lr, step));
+                                                                                 max_exp_avg_sq, partial));
             STOVE_LAUNCH_CHECK();
             k = 0;
             mx = 0;
