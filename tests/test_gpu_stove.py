@@ -186,3 +186,58 @@ def test_mcts_expand_and_rollout_equals_two_reference_calls():
     ck.close('r', r, r1, 2e-5)
     ck.close('r_rollout', r_roll, r2, 1e-4 * depth)
     ck.finish()
+
+
+@pytest.mark.parametrize('tag,kw,n,res,O', [
+    ('o9_multiball', dict(num_obj=9, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0,
+                          max_obj_scale=0.22), 16, 50, 9),                                  # BASELINE configs[3], upper end
+    ('ac_batch512', dict(action_conditioned=True, action_space=9, debug_core_appearance=True), 512, 32, 3),  # configs[2]
+])
+def test_stove_other_baseline_configs_vs_oracle(tag, kw, n, res, O):
+    """The other BASELINE configurations at their stated sizes: 9-object multiball at 50x50 (greedy matching,
+    generic GNN kernels) and the action-conditioned avoidance world model at batch 512 with the reward head in
+    the loss (train.py:452-465), ELBO / rewards / gradients against the fp64 oracle."""
+    from stove_b200 import synth
+    oc, sd, model = make_model(kw, 31, att_gain=0.5)
+    with torch.no_grad():                     # well-conditioned matching, see test_stove_config1_full_size_vs_oracle
+        sd['sup.encoder.rnn.weight_hh_l0'] *= 8
+        sd['sup.encoder.fc2.weight'] *= 25
+        model.load_state_dict({k: v.float() for k, v in sd.items()})
+    T = 8
+    data = synth.billiards(n, T, min(O, 6), res=res, seed=6)
+    x = data['x']
+    actions = synth.random_actions(n, T, 9, 3) if oc.action_conditioned else None
+    gen = torch.Generator().manual_seed(10)
+    noise = [torch.randn(n, O, 12, 1, generator=gen, dtype=torch.float64) for _ in range(2)] + \
+            [torch.randn(n, O, 18, generator=gen, dtype=torch.float64) for _ in range(T - 2)]
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if 'output_vector' not in k}
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    target = (torch.rand(n, T - 2, 1, generator=gen) < 0.3).double()
+    elbo_o, prop_o, rew_o = so.stove_forward(oc, P, x.double(), noise, actions=actions.double() if actions is not None else None)
+    loss_o = -elbo_o
+    if oc.action_conditioned:
+        loss_o = loss_o + 15000.0 * torch.nn.functional.binary_cross_entropy(rew_o, target)
+    loss_o.backward()
+    model._standard_normal = NoiseReplay(noise, 'cuda')
+    elbo, prop, rew = model(x.cuda(), 0, actions=actions.cuda() if actions is not None else None)
+    loss = -elbo
+    if oc.action_conditioned:
+        loss = loss + 15000.0 * torch.nn.functional.binary_cross_entropy(rew, target.float().cuda())
+    model.zero_grad()
+    loss.backward()
+    ck = Checker('stove_' + tag)
+    ck.close('elbo', elbo, elbo_o, VAL)
+    ck.close('z', prop['z'], prop_o['z'], 3e-5, absolute=True)
+    if oc.action_conditioned:
+        ck.close('rewards', rew, rew_o, 1e-4, absolute=True)
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            # Nine recurrent LSTM steps through the deliberately amplified W_hh (x8, see above): the 3xTF32 GEMMs
+            # carry ~1e-5 per product on the tensor cores (truncating addend alignment, DESIGN.md section 4) and the
+            # recurrence multiplies it -- measured 5.7e-4 on the LSTM gradients here, 7e-5 with the SIMT-fp32
+            # library GEMMs (STOVE_ENCODER_FP32=1); three steps (O = 3) stay below 3e-4.
+            tol = 1e-3 if (O > 6 and '.rnn.' in name) else GRAD
+            ck.close('g.' + name, p.grad, P[name].grad, tol)
+        else:
+            ck.true('nograd.' + name, P[name].grad is None)
+    ck.finish()
