@@ -237,6 +237,33 @@ def stove_golden():
               'max|pos|', float(zr[..., 2:4].abs().max()))
 
 
+def supair_only_golden():
+    """Pretraining branch: Stove.forward(x, 0, pretrain=True) -> Supair.forward (supair.py:504-551)."""
+    seed = 25
+    c = so.default_config()
+    sd = make_state_dict(c, seed)
+    ref = rh.build_reference(c, sd)
+    n, T = 3, 8
+    q, x = frames_u8(n, T, c.num_obj, 32, seed, 1.2)
+    torch.manual_seed(seed)
+    with rh.quiet(), rh.NoiseTape() as tape, rh.default_dtype(D):
+        ref.zero_grad()
+        elbo, prop, zero = ref(x, 0, pretrain=True)
+        (-elbo).backward()
+    assert zero == 0 and len(tape.draws) == 1
+    out = {'seed': seed, 'checksum': checksum(sd), 'x_u8': q, 'elbo': elbo.detach(), 'z': prop['z'],
+           'noise0': tape.draws[0]}
+    for name, p in ref.named_parameters():
+        if p.grad is None:
+            continue
+        if p.numel() > 20000:
+            out['gsig.' + name] = grad_signature(p.grad)
+        else:
+            out['g.' + name] = p.grad.clone()
+    np.savez_compressed(os.path.join(OUT, 'supair_only.npz'), **{k: np.asarray(v) for k, v in out.items()})
+    print('supair_only elbo', float(elbo))
+
+
 if __name__ == '__main__':
     assert rh.available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
@@ -246,4 +273,5 @@ if __name__ == '__main__':
     scene_golden()
     dynamics_golden()
     stove_golden()
+    supair_only_golden()
     print({f: os.path.getsize(os.path.join(OUT, f)) for f in sorted(os.listdir(OUT))})

@@ -513,6 +513,30 @@ def stove_forward(c, P, x, noise, actions=None, structs=None, parts=None):
     return average_elbo, prop, rewards
 
 
+def supair_forward(c, P, x, noise, structs=None):
+    """Stove.forward(..., pretrain=True) = bw_transform + Supair.forward, the SuPAIR-only ELBO
+    (stove.py:863-897 pretrain branch, supair.py:504-551, sampling :165-192).
+
+    noise: ONE standard-normal draw (n*T*O, 4) -- the rsample() of get_z_sup_sample.
+    Returns (average_elbo, dict(z (n, T, O, 4), log_q, z_std))."""
+    structs = structs or structures(c)
+    if c.debug_bw:
+        x = bw_transform(x)
+    n, T = x.shape[0], x.shape[1]
+    zp = encoder(c, P, x.flatten(end_dim=1)).flatten(end_dim=1)            # (nTO, 8)
+    zp_mean, zp_std = constrain_zp(c, zp)
+    eps = noise[0] if isinstance(noise, (list, tuple)) else noise
+    z_tmp = zp_mean + zp_std * eps.to(zp_mean.dtype)                       # Normal(mean, std).rsample()
+    log_q = normal_log_prob(z_tmp, zp_mean, zp_std).sum(-1)                # (nTO,)
+    z_obj = sy_from_quotient(z_tmp)
+    log_q = log_q.view(-1, c.num_obj).sum(-1)                              # (nT,)
+    log_p = likelihood(c, P, structs, x, z_obj)
+    log_p = log_p[0] if isinstance(log_p, tuple) else log_p
+    elbo = log_p - log_q
+    return elbo.mean(), dict(z=z_obj.view(n, T, c.num_obj, 4).detach(), log_q=log_q.mean().detach(),
+                             z_std=zp_std.mean(0).detach())
+
+
 def rollout(c, P, z_last, num=None, actions=None, appearance=None, noise=None,
             return_std=False):
     """stove.py:777-861.  `noise`: optional list of (n, O, cl//2) draws => sample=True."""

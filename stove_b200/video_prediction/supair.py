@@ -165,8 +165,13 @@ class Supair(nn.Module):
     def quotient_from_sy(z):
         return torch.cat([z[..., 0:1], z[..., 1:2] / z[..., 0:1], z[..., 2:]], -1)
 
+    def _standard_normal(self, shape, like):
+        """Noise source of get_z_sup_sample (replaced by tests that replay recorded draws)."""
+        return torch.empty(shape, device=like.device, dtype=like.dtype).normal_()
+
     def get_z_sup_sample(self, zp_mean, zp_std):
-        eps = torch.empty_like(zp_mean).normal_()
+        """supair.py:165-192: z ~ N(zp_mean, zp_std) (reparametrised), log q(z) summed over the 4 components."""
+        eps = self._standard_normal(tuple(zp_mean.shape), zp_mean)
         z = zp_mean + zp_std * eps
         log_q = (-0.5 * eps ** 2 - torch.log(zp_std) - 0.5 * math.log(2 * math.pi)).sum(-1)
         return self.sy_from_quotient(z), log_q

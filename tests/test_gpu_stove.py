@@ -241,3 +241,54 @@ def test_stove_other_baseline_configs_vs_oracle(tag, kw, n, res, O):
         else:
             ck.true('nograd.' + name, P[name].grad is None)
     ck.finish()
+
+
+def test_supair_only_elbo_pretrain_branch_vs_oracle():
+    """Stove.forward(..., pretrain=True) -> Supair.forward (supair.py:504-551): ELBO, latents, gradients."""
+    from stove_b200 import synth
+    oc, sd, model = make_model({}, 41)
+    n, T = 24, 8
+    x = synth.billiards(n, T, 3, res=32, seed=8)['x']
+    gen = torch.Generator().manual_seed(12)
+    eps = torch.randn(n * T * 3, 4, generator=gen, dtype=torch.float64)
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if 'output_vector' not in k}
+    elbo_o, prop_o = so.supair_forward(oc, P, x.double(), eps)
+    (-elbo_o).backward()
+    model.sup._standard_normal = lambda shape, like: eps.to(like.device, like.dtype).view(shape)
+    elbo, prop, zero = model(x.cuda(), 0, pretrain=True)
+    model.zero_grad()
+    (-elbo).backward()
+    ck = Checker('supair_only_elbo')
+    ck.true('third_return_is_zero', zero == 0)
+    ck.close('elbo', elbo, elbo_o, VAL)
+    ck.close('z', prop['z'], prop_o['z'], 3e-5, absolute=True)
+    for name, p in model.named_parameters():
+        if p.grad is not None:
+            ck.close('g.' + name, p.grad, P[name].grad, GRAD)
+        else:
+            ck.true('nograd.' + name, P[name].grad is None)
+    ck.finish()
+
+
+def test_supair_only_elbo_golden():
+    """The pretraining branch against the reference-generated golden (tests/golden/supair_only.npz)."""
+    g = load_golden('supair_only')
+    oc, sd, model = make_model({}, int(g['seed']))
+    x = (g['x_u8'].float() / 255.0).cuda()
+    eps = g['noise0']
+    model.sup._standard_normal = lambda shape, like: eps.to(like.device, like.dtype).view(shape)
+    elbo, prop, zero = model(x, 0, pretrain=True)
+    model.zero_grad()
+    (-elbo).backward()
+    ck = Checker('supair_only_golden')
+    ck.true('third_return_is_zero', zero == 0)
+    ck.close('elbo', elbo, g['elbo'], VAL)
+    ck.close('z', prop['z'], g['z'], 2e-5, absolute=True)
+    params = dict(model.named_parameters())
+    for k in g:
+        if k.startswith('g.'):
+            ck.close(k, params[k[2:]].grad, g[k], GRAD)
+        elif k.startswith('gsig.'):
+            sig = grad_signature(params[k[5:]].grad)
+            ck.close(k, sig[[1, 3]], g[k][[1, 3]], GRAD)
+    ck.finish()

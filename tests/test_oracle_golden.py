@@ -136,3 +136,24 @@ def test_stove_forward_backward_rollout(tag):
         else:
             zr, _ = so.rollout(c, P, z_last, num=92)
     assert rel_err(zr[:, steps], g['roll_z']) < 1e-9
+
+
+def test_supair_only_elbo_golden():
+    """Pretraining branch (Stove.forward(..., pretrain=True) -> Supair.forward, supair.py:504-551) against the
+    reference-generated golden."""
+    g = load_golden('supair_only')
+    c = so.default_config()
+    sd = make_state_dict(c, int(g['seed']))
+    assert abs(checksum(sd) - float(g['checksum'])) < 1e-6
+    P = _params(sd)
+    x = g['x_u8'].to(D) / 255.0
+    elbo, prop = so.supair_forward(c, P, x, [g['noise0']])
+    assert rel_err(elbo, g['elbo']) < TOL
+    assert rel_err(prop['z'], g['z']) < TOL
+    (-elbo).backward()
+    for k in g:
+        if k.startswith('g.'):
+            assert rel_err(P[k[2:]].grad, g[k]) < 1e-8, k
+        elif k.startswith('gsig.'):
+            sig = grad_signature(P[k[5:]].grad)
+            assert float((sig - g[k]).abs().max() / g[k].abs().max()) < 1e-8, k

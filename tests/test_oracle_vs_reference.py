@@ -54,3 +54,26 @@ def test_live_fp32_close_to_fp64():
     with rh.quiet(), rh.NoiseTape(replay=tape.draws), rh.default_dtype(torch.float32):
         e32, _, _ = ref32(x.float(), 0)
     assert rel_err(e32, e64.detach()) < 1e-5
+
+
+def test_live_supair_only_elbo():
+    """The pretraining branch Stove.forward(..., pretrain=True) -> Supair.forward (supair.py:504-551)."""
+    c = so.default_config()
+    sd = make_state_dict(c, 91)
+    ref = rh.build_reference(c, sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(3, 8, 3, 32, 32, generator=g, dtype=D) * (torch.rand(3, 8, 3, 32, 32, generator=g) > 0.7)
+    with rh.quiet(), rh.NoiseTape() as tape, rh.default_dtype(D):
+        elbo_r, prop_r, zero = ref(x, 0, pretrain=True)
+        (-elbo_r).backward()
+    assert zero == 0 and len(tape.draws) == 1
+    P = {k: v.clone().requires_grad_(True) for k, v in sd.items() if 'output_vector' not in k}
+    elbo_o, prop_o = so.supair_forward(c, P, x, tape.draws)
+    (-elbo_o).backward()
+    assert rel_err(elbo_o, elbo_r.detach()) < 1e-12
+    assert rel_err(prop_o['z'], prop_r['z']) < 1e-12
+    for name, p in ref.named_parameters():
+        if p.grad is None:
+            assert P[name].grad is None, name
+        else:
+            assert rel_err(P[name].grad, p.grad) < 1e-9, name
