@@ -355,6 +355,20 @@ def run_b200(args):
     extra['rollout_long'] = {'workload': 'action-conditioned world-model rollouts, 1024 sequences x 2000 frames per GPU',
                              'metric': 'rollout_frames_per_sec', 'value': world * n5 * len5 * k5 / (ms5 * 1e-3),
                              'unit': 'sequence-frames/s', 'ms_per_rollout': ms5 / k5}
+    # roofline of the persistent rollout kernel (one launch per call): useful FP32 work of one sequence-step of
+    # the factorised, action-conditioned network against the FP32 pipe; the algorithmic HBM traffic is the state
+    # written per step (+ the action read)
+    step_flops = 2.0 * (98208 + O * (4 * 9 + 7 * 32) + 32 * 32 * 2 + 32 * 16 + 16 * 8 + 8)
+    sm_mhz5 = clock_summary.get('sm_max_mhz') or 1965.0
+    fp32_peak5 = 148 * 128 * 2 * sm_mhz5 * 1e6 / 1e12
+    per_gpu = n5 * len5 * k5 / (ms5 * 1e-3)
+    extra['rollout_long']['roofline'] = {
+        'kernel': 'team_rollout', 'bound': 'fp32',
+        'achieved_tflops': per_gpu * step_flops / 1e12, 'peak_tflops': fp32_peak5,
+        'frac': per_gpu * step_flops / 1e12 / fp32_peak5,
+        'hbm': {'achieved_gbs': per_gpu * (O * 18 * 4 + 4 + 36) / 1e9, 'peak_gbs': peak,
+                'frac': per_gpu * (O * 18 * 4 + 4 + 36) / 1e9 / peak},
+        'note': 'per GPU; %d FLOP and %d algorithmic bytes per sequence-step' % (int(step_flops), O * 18 * 4 + 40)}
     # video prediction: 8-frame inference + 92-frame rollout (BASELINE configs[1])
     n2 = 1024
     x2 = make_frames(n2, 77 + rank).to(dev)

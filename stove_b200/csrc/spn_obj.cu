@@ -620,12 +620,15 @@ __global__ void __launch_bounds__(1024) spn2_bwd_leafparam_async_kernel(
     Spn2Dev st, int64_t N, int64_t npad, int chunk, const float* __restrict__ x,
     const float* __restrict__ marg, const float* __restrict__ leaf, const float* __restrict__ gleaf,
     float* __restrict__ g_leaf) {
-    constexpr int GP = GP_<G>::v;
+    constexpr int GP = GP_<G>::v, GT_LD = 36;
     extern __shared__ __align__(16) float smem[];
     const int D = st.D, TILE = 32 * D;
     float* xt = smem;                     // [2][32][D]
     float* mt = xt + 2 * TILE;            // [2][32][D]
-    float* gt = mt + 2 * TILE;            // [2][2G][32]
+    // rows of the leaf-vector gradients are GT_LD = 36 floats apart: threads of a warp read 10-20 different rows
+    // at the same patch index, which a stride of 32 puts in ONE bank (10- to 20-way conflict on a third of the
+    // shared-memory reads); 36 keeps the 16-byte alignment cp.async needs and leaves at most a 3-way conflict
+    float* gt = mt + 2 * TILE;            // [2][2G][GT_LD]
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     const int nq0 = st.n0[q], nq = st.nt[q];
@@ -654,7 +657,7 @@ __global__ void __launch_bounds__(1024) spn2_bwd_leafparam_async_kernel(
         }
         for (int i = tid; i < 2 * G * 8; i += blockDim.x) {
             const int row = i >> 3, c4 = i & 7;
-            cp_async16(gt + stg * 2 * G * 32 + row * 32 + c4 * 4,
+            cp_async16(gt + stg * 2 * G * GT_LD + row * GT_LD + c4 * 4,
                        gleaf + (int64_t)((q * 2) * G + row) * npad + base + c4 * 4);
         }
         cp_async_commit();
@@ -673,7 +676,7 @@ __global__ void __launch_bounds__(1024) spn2_bwd_leafparam_async_kernel(
             const int lim = (int)min((int64_t)32, c1 - (c0 + (int64_t)b * 32));
             const float* xs = xt + stg * TILE + px;
             const float* ms = mt + stg * TILE + px;
-            const float* gs = gt + stg * 2 * G * 32 + hg * 32;
+            const float* gs = gt + stg * 2 * G * GT_LD + hg * GT_LD;
 #pragma unroll 8
             for (int pt = 0; pt < lim; ++pt) {
                 const float d = xs[pt * D] - mu;
@@ -904,7 +907,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         const int threads = round_up(st->pmax * G, 32);
         STOVE_CHECK_ARG(threads <= 1024, "region too large for the leaf-gradient kernel");
         dim3 grid(Q, nchunk);
-        const size_t smem_async = sizeof(float) * ((size_t)4 * 32 * D + (size_t)2 * 2 * G * 32);
+        const size_t smem_async = sizeof(float) * ((size_t)4 * 32 * D + (size_t)2 * 2 * G * 36);
         if (D % 4 == 0 && smem_async <= 227 * 1024) {
             if (marg) {
                 if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, true>, smem_async))) return rc;
