@@ -486,10 +486,14 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
     constexpr int GP = GPB_<G>::v;
     constexpr int NI = R * 2 * G;
     constexpr int TILE = 32 * 128;
+    // rows of the leaf-vector gradients GT_LD = 36 floats apart: the threads of a warp read two different rows (the
+    // two sides of a split) at the same frame index; with a stride of 32 they share a bank (ncu: 47 % of the
+    // shared-memory wavefronts were conflicts).  36 keeps cp.async's 16-byte alignment.
+    constexpr int GT_LD = 36;
     extern __shared__ __align__(16) float smem[];
     float* xt = smem;                       // [2][32][128]
     float* mt = xt + 2 * TILE;              // [2][32][128]
-    float* gt = mt + 2 * TILE;              // [2][NI][32]
+    float* gt = mt + 2 * TILE;              // [2][NI][GT_LD]
     const int tid = threadIdx.x;
     const int px0 = blockIdx.x * 128, px = px0 + tid;
     const bool active = px < D;
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
         const float* lp = leaf + ((int64_t)pxc * R + r) * 3 * GP;
 #pragma unroll
         for (int g = 0; g < G; ++g) { mu[r][g] = lp[g]; a[r][g] = lp[GP + g]; }
-        hoff[r] = ((r * 2 + side[pxc * R + r]) * G) * 32;
+        hoff[r] = ((r * 2 + side[pxc * R + r]) * G) * GT_LD;
     }
     float s1[R][G], s2[R][G], s3[R][G];
 #pragma unroll
@@ -526,7 +530,7 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
         // gradients of the leaf vectors: rows of 32 frames (npad is a multiple of 32, so rows past c1 exist)
         for (int i = tid; i < NI * 8; i += 128) {
             const int row = i >> 3, c4 = i & 7;
-            bg_cp_async16(gt + st * NI * 32 + row * 32 + c4 * 4, gleaf + (int64_t)row * npad + base + c4 * 4);
+            bg_cp_async16(gt + st * NI * GT_LD + row * GT_LD + c4 * 4, gleaf + (int64_t)row * npad + base + c4 * 4);
         }
         bg_cp_async_commit();
     };
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
             const int lim = (int)min((int64_t)32, c1 - (c0 + (int64_t)b * 32));
             const float* xs = xt + st * TILE + tid;
             const float* ms = mt + st * TILE + tid;
-            const float* gs = gt + st * NI * 32;
+            const float* gs = gt + st * NI * GT_LD;
 #pragma unroll 2
             for (int pt = 0; pt < lim; ++pt) {
                 const float xv = xs[pt * 128];
@@ -554,7 +558,7 @@ __global__ void __launch_bounds__(128) spn1_bwd_leafparam_async_kernel(
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const float d = xv - mu[r][g];
-                        const float gw = gs[hoff[r] + g * 32 + pt] * wv;
+                        const float gw = gs[hoff[r] + g * GT_LD + pt] * wv;
                         s1[r][g] = fmaf(gw, d, s1[r][g]);
                         s2[r][g] = fmaf(gw * d, d, s2[r][g]);
                         s3[r][g] += gw;
@@ -711,7 +715,7 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     {
         dim3 grid((D + 127) / 128, nchunk);
         if (D % 4 == 0) {
-            const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 32);
+            const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 36);
             if (marg) {
                 STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, true>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
