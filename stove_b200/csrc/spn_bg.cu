@@ -713,7 +713,16 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     if (chunk < 32) chunk = 32;
     const int nchunk = (int)((N + chunk - 1) / chunk);
     {
-        dim3 grid((D + 127) / 128, nchunk);
+        // leaf-parameter kernel: CTAs of 4 warps holding 66 KB of shared memory each.  With the chunking above the
+        // grid is ~150 CTAs = one per SM, 6 % of the warp slots (ncu) -- it runs at latency, not throughput.  A
+        // finer frame chunk (two 32-frame tiles per CTA, still pipelined) gives ~3 CTAs per SM.
+        int lchunk = chunk;
+        const int ctas_px = (D + 127) / 128;
+        while (lchunk > 64 && (int64_t)ctas_px * ((N + lchunk - 1) / lchunk) < 3 * 148) lchunk = round_up(lchunk / 2, 32);
+        const int lnchunk = (int)((N + lchunk - 1) / lchunk);
+        dim3 grid(ctas_px, lnchunk);
+        const int chunk_saved = chunk;
+        chunk = lchunk;
         if (D % 4 == 0) {
             const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 36);
             if (marg) {
@@ -730,6 +739,7 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
         else
             STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
         STOVE_LAUNCH_CHECK();
+        chunk = chunk_saved;
     }
     {
         dim3 grid(st->R, nchunk);
