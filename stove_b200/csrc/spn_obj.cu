@@ -42,9 +42,28 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+__device__ __forceinline__ float lds_f1(const float* p) {
+    float v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+// volatile on purpose: with plain shared-memory loads ptxas hoists all 600 LDS.128 of the two unrolled product
+// loops to the top and spills 7.6 KB per thread; pinned in program order the staged kernel keeps 100 registers
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+    float4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
 __host__ __device__ static inline int up4(int v) { return (v + 3) & ~3; }
 
 // SMEM = the parameter block has been staged in shared memory (plain loads), else read-only global loads
@@ -166,15 +185,35 @@ __global__ void __launch_bounds__(1024) spn2_fwd_kernel(
     __syncthreads();
 
     const int64_t n = base + lane;   // < npad when tile_ok
+    float L0[G], L1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { L0[g] = 0.f; L1[g] = 0.f; }
     if (tile_ok) {
         const int nq0 = __ldg(st.n0 + q), nq = __ldg(st.nt + q);
         const int32_t* sc = STAGE ? scs + q * st.pmax : st.scope + q * st.pmax;
         const float* leaf_q = STAGE ? lf + q * st.pmax * 3 * GP : leaf + (int64_t)q * st.pmax * 3 * GP;
-        float L0[G], L1[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { L0[g] = 0.f; L1[g] = 0.f; }
         leaf_accumulate<G, STAGE>(L0, leaf_q, sc, 0, nq0, xs, ws, lane);
         leaf_accumulate<G, STAGE>(L1, leaf_q, sc, nq0, nq, xs, ws, lane);
+    }
+    // The sum and root weights take the place of the leaf table, which is dead once every warp has its leaf
+    // vectors: 300 + 100 broadcast loads per thread from L1/L2 in the unrolled product loops (ncu: 6.2 stall
+    // cycles per issued instruction on the load scoreboard) become shared-memory reads in program order.
+    float* wl = lf;                                   // WSTAGE: [Q][G*G*SP] sum weights
+    float* rws = wl + Q * G * G * SP;                 // WSTAGE: [R][S*S] root weights
+    const bool WSTAGE = STAGE && (Q * G * G * SP + R * S * S <= Q * st.pmax * 3 * GP);
+    if (WSTAGE) {
+        __syncthreads();
+        if (tile == 0) {
+            const float4* wsrc = reinterpret_cast<const float4*>(wlin + (int64_t)q * G * G * SP);
+            float4* wdst = reinterpret_cast<float4*>(wl + q * G * G * SP);
+            for (int i = lane; i < G * G * SP / 4; i += 32) cp_async16(wdst + i, wsrc + i);
+            if (q < R)
+                for (int i = lane; i < S * S; i += 32) cp_async4(rws + q * S * S + i, rlin + q * S * S + i);
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    if (tile_ok) {
         float* lv = leaf_val + (int64_t)(q * 2) * G * npad + n;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -195,7 +234,7 @@ __global__ void __launch_bounds__(1024) spn2_fwd_kernel(
                 const int k = j * G + i;
 #pragma unroll
                 for (int v = 0; v < SP / 4; ++v) {
-                    const float4 w = __ldg(wq + k * (SP / 4) + v);
+                    const float4 w = WSTAGE ? lds_f4(wl + (q * G * G + k) * SP + 4 * v) : __ldg(wq + k * (SP / 4) + v);
                     if (4 * v + 0 < S) T[4 * v + 0] = fmaf(pk, w.x, T[4 * v + 0]);
                     if (4 * v + 1 < S) T[4 * v + 1] = fmaf(pk, w.y, T[4 * v + 1]);
                     if (4 * v + 2 < S) T[4 * v + 2] = fmaf(pk, w.z, T[4 * v + 2]);
@@ -232,7 +271,8 @@ __global__ void __launch_bounds__(1024) spn2_fwd_kernel(
         for (int j = 0; j < S; ++j) {
             float inner = 0.f;
 #pragma unroll
-            for (int i = 0; i < S; ++i) inner = fmaf(eA[i], __ldg(rw + j * S + i), inner);
+            for (int i = 0; i < S; ++i)
+                inner = fmaf(eA[i], WSTAGE ? lds_f1(rws + r * S * S + j * S + i) : __ldg(rw + j * S + i), inner);
             U = fmaf(eB[j], inner, U);
         }
         float val;
@@ -285,6 +325,7 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
     float* ss = smem;                 // [Q*S][32] sum values
     float* gsm = ss + Q * S * 32;     // [Q*S][32] their gradients
     float* wl = gsm + Q * S * 32;     // STAGE: [Q][G*G*SP] sum weights
+    float* rws = wl + Q * G * G * SP;  // STAGE: [R][S*S] root weights
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)blockIdx.x * 32;
     const int64_t n = base + lane;
@@ -292,6 +333,8 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
         const float4* wsrc = reinterpret_cast<const float4*>(wlin + (int64_t)warp * G * G * SP);
         float4* wdst = reinterpret_cast<float4*>(wl + warp * G * G * SP);
         for (int i = lane; i < G * G * SP / 4; i += 32) cp_async16(wdst + i, wsrc + i);
+        if (warp < R)
+            for (int i = lane; i < S * S; i += 32) cp_async4(rws + warp * S * S + i, rlin + warp * S * S + i);
         cp_async_commit();
     }
 
@@ -322,7 +365,8 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
             float inner = 0.f;
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                const float w = __ldg(rw + j * S + i);
+                float w;
+                if constexpr (STAGE) w = lds_f1(rws + r * S * S + j * S + i); else w = __ldg(rw + j * S + i);
                 inner = fmaf(eA[i], w, inner);
                 colA[i] = fmaf(eB[j], w, colA[i]);
             }
@@ -385,7 +429,8 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
                 const int k = j * G + i;
 #pragma unroll
                 for (int v = 0; v < SP / 4; ++v) {
-                    const float4 w = STAGE ? wq[k * (SP / 4) + v] : __ldg(wq + k * (SP / 4) + v);
+                    float4 w;
+                    if constexpr (STAGE) w = lds_f4(wl + (q * G * G + k) * SP + 4 * v); else w = __ldg(wq + k * (SP / 4) + v);
                     if (4 * v + 0 < S) T[4 * v + 0] = fmaf(pk, w.x, T[4 * v + 0]);
                     if (4 * v + 1 < S) T[4 * v + 1] = fmaf(pk, w.y, T[4 * v + 1]);
                     if (4 * v + 2 < S) T[4 * v + 2] = fmaf(pk, w.z, T[4 * v + 2]);
@@ -415,7 +460,8 @@ __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
                 float v = 0.f;
 #pragma unroll
                 for (int u = 0; u < SP / 4; ++u) {
-                    const float4 w = STAGE ? wq[k * (SP / 4) + u] : __ldg(wq + k * (SP / 4) + u);
+                    float4 w;
+                    if constexpr (STAGE) w = lds_f4(wl + (q * G * G + k) * SP + 4 * u); else w = __ldg(wq + k * (SP / 4) + u);
                     if (4 * u + 0 < S) v = fmaf(qv[4 * u + 0], w.x, v);
                     if (4 * u + 1 < S) v = fmaf(qv[4 * u + 1], w.y, v);
                     if (4 * u + 2 < S) v = fmaf(qv[4 * u + 2], w.z, v);
@@ -858,10 +904,11 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     {
         constexpr int SP = GP_<S>::v;
         const size_t base_smem = sizeof(float) * (size_t)2 * Q * S * 32;
-        const size_t stage_smem = base_smem + sizeof(float) * (size_t)Q * G * G * SP;
-        // staging the sum weights is compiled in but not selected: with the weights in shared memory ptxas
-        // hoists all 600 LDS.128 of the two unrolled product loops and spills 7.6 KB per thread (3.7x slower)
-        if (stage_smem <= 227 * 1024 && getenv("STOVE_SPN2_NODES_STAGE")) {
+        const size_t stage_smem = base_smem + sizeof(float) * ((size_t)Q * G * G * SP + (size_t)st->R * S * S);
+        // sum and root weights staged in shared memory (cp.async, read back with pinned-order loads): every
+        // (pair, sum) step otherwise waits for its own broadcast load from L1/L2 (ncu: 7.7 stall cycles per issued
+        // instruction on the load scoreboard); 47 -> 37 us
+        if (stage_smem <= 227 * 1024 && !getenv("STOVE_SPN2_NODES_NOSTAGE")) {
             if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S, true>, stage_smem))) return rc;
             STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S, true><<<blocks, 32 * Q, stage_smem, s>>>(
                 d, N, npad, wlin, wlog, rlin, rlog, leaf_val, sum_val, out, g_out, w.gleaf, w.aux_reg, w.aux_root,
