@@ -558,14 +558,14 @@ class LstmEncoder(torch.autograd.Function):
         # chain for L2 bandwidth (these GEMMs are operand-delivery bound) and the step gets slower.
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            g_b = g_sum.sum(0)
             if steps > 1:
                 g_whh = _gemm_tn_splitk(g_rows.view(-1, 4 * H), h_rows.view(-1, H), 4)
             else:
                 g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
-        for t_ in (g_sum, g_rows, h_rows):
+        for t_ in (g_rows, h_rows):
             t_.record_stream(side)
         g_wih = _gemm_tn_splitk(g_row0, x_row, 2) if ctx.needs_input_grad[1] else None
+        g_b = g_sum.sum(0)                         # behind the W_ih GEMM: the side stream's GEMM is the longer branch
         cur.wait_stream(side)                      # every gradient is ready on the node's stream when it returns
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
