@@ -537,22 +537,23 @@ class LstmEncoder(torch.autograd.Function):
         # (n x H, K = 12H), 32 for the W_hh gradient, 64 for the W_ih gradient -- a fraction of the 148 SMs.
         # Splitting K into `parts` batches of one strided-batched GEMM fills the machine; the partial products
         # are summed by the consumer (the cell kernel) or by one small reduction.
-        kparts = 2 if H % 2 == 0 else 1
         g_rows = torch.empty(max(steps - 1, 0), 3 * n, 4 * H, device=dev, dtype=dt)   # steps 1 .. steps-1, stacked
         g_row0 = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)                      # split of the summed gradient
         dh = g_c = None
         for t in reversed(range(steps)):
-            g_col = torch.empty(n, 12 * H, device=dev, dtype=dt) if t > 0 else None
             g_row = g_rows[t - 1] if t > 0 else g_row0
             g_c_prev = torch.empty(n, H, device=dev, dtype=dt) if t > 0 else None
+            # the cell kernel writes the gate gradient once, row-concatenated [hi ; hi ; lo] (3n x 4H): the same
+            # buffer serves the weight-gradient GEMM (contracted over its rows) and, viewed as three (n x 4H)
+            # blocks, the hidden-state GEMM below -- no second, column-concatenated copy (25 MB per step)
             N.check(lib.stove_lstm_cell_bwd_x(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
                                               N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
-                                              kparts, N.ptr(g_c), N.ptr(g_col), N.ptr(g_row), N.ptr(g_sum),
+                                              3, N.ptr(g_c), None, N.ptr(g_row), N.ptr(g_sum),
                                               0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
             if t > 0:
-                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain
-                dh = _bmm_tf32(g_col.view(n, kparts, 12 * H // kparts).transpose(0, 1),
-                               whh_row.view(kparts, 12 * H // kparts, H))
+                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain.  One batch per
+                # 3xTF32 term (hi*hi, hi*lo, lo*hi) = split-K by 3: 192 CTAs; the next cell kernel sums the parts
+                dh = _bmm_tf32(g_row.view(3, n, 4 * H), whh_row.view(3, 4 * H, H))
                 g_c = g_c_prev
         # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
         # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands; it
