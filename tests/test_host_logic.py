@@ -119,3 +119,23 @@ def test_fix_supair_and_velocities_equal_oracle():
     zp = torch.randn(50, 8, generator=g, dtype=torch.float64)
     for x, y in zip(m.sup.constrain_zp(zp), so.constrain_zp(oc, zp)):
         assert (x - y).abs().max() < 1e-12
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference algorithm on the host cores): exactly one line on stdout, JSON,
+    with the keys of the measurement contract."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'train_seqs_per_sec' and d['unit'] == 'sequences/s'
+    assert d['value'] > 0 and d['higher_is_better'] is True and d['n_gpus'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config']
