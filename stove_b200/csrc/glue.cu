@@ -115,30 +115,29 @@ __device__ __forceinline__ void match_step(const SupParams& p, float* err, int* 
     }
 }
 
-// One warp per sequence; the warp's working set lives in its slice of shared memory.  Only the
+// One CTA per sequence; its working set lives in shared memory.  Only the
 // matching itself (T-1 tiny assignment problems on detached values) runs on a single lane.
 // raw encoder output zp [n][T][O][8] -> z_sup [n][T][O][4], z_full / std_full [n][T][O][6],
 // app_out [n][T][O][3] (matched appearances), idx [n][T][O] (int32), flag [n][T][O] (bit0, bit1)
-#define SG_WARPS 4
-__device__ __forceinline__ int sup_smem_floats(int T, int O) { return 2 * T * O * 8 + 2 * T * O; }
+#define SGB_THREADS 256
 
 template <int OC>
-__global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
+__global__ void __launch_bounds__(SGB_THREADS) sup_prepare_fwd_kernel(
     SupParams p, int64_t n, const float* __restrict__ zp, const float* __restrict__ app,
     float* __restrict__ z_sup, float* __restrict__ z_full, float* __restrict__ std_full,
     float* __restrict__ app_out, int32_t* __restrict__ idx_out, int32_t* __restrict__ flag_out) {
     extern __shared__ float sg_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * SG_WARPS + warp;
-    if (b >= n) return;
+    const int lane = threadIdx.x;              // one CTA per sequence, as in the backward kernel
+    const int64_t b = blockIdx.x;
+    (void)n;
     const int T = p.T, O = OC ? OC : p.O, TO = T * O;
-    float* z = sg_smem + warp * sup_smem_floats(T, O);     // constrained, later the smoothed tensor
+    float* z = sg_smem;                                    // constrained, later the smoothed tensor
     float* zm = z + TO * 8;                                 // matched
     int* idx = reinterpret_cast<int*>(zm + TO * 8);         // [T][O]
     int* flg = idx + TO;
     const float* src = zp + b * TO * 8;
     const float* asrc = app ? app + b * TO * 3 : nullptr;
-    for (int q = lane; q < TO * 8; q += 32) {
+    for (int q = lane; q < TO * 8; q += SGB_THREADS) {
         const int f = q & 7;
         const float sgm = sigmoidf_(__ldg(src + q));
         float v;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
         else v = p.pos_var * sgm;
         z[q] = v;
     }
-    __syncwarp();
+    __syncthreads();
     if (lane == 0) {
         // matching on positions scaled to [0, 1] ((z + 1) / 2, stove.py:220), detached
         constexpr int OM = OC ? OC : SG_MAX_O;
@@ -185,20 +184,20 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
             }
         }
     }
-    __syncwarp();
-    for (int q = lane; q < TO * 8; q += 32) {
+    __syncthreads();
+    for (int q = lane; q < TO * 8; q += SGB_THREADS) {
         const int ta = q >> 3, f = q & 7, t = ta / O;
         zm[q] = z[(t * O + idx[ta]) * 8 + f];
     }
-    for (int q = lane; q < TO; q += 32) idx_out[b * TO + q] = idx[q];
+    for (int q = lane; q < TO; q += SGB_THREADS) idx_out[b * TO + q] = idx[q];
     if (app_out && asrc)
-        for (int q = lane; q < TO * 3; q += 32) {
+        for (int q = lane; q < TO * 3; q += SGB_THREADS) {
             const int ta = q / 3, c = q - ta * 3, t = ta / O;
             app_out[b * TO * 3 + q] = asrc[(t * O + idx[ta]) * 3 + c];
         }
-    __syncwarp();
+    __syncthreads();
     // smoothing of glitches (stove.py:516-571): flags from the first two features
-    for (int q = lane; q < TO; q += 32) {
+    for (int q = lane; q < TO; q += SGB_THREADS) {
         const int t = q / O;
         int fl = 0;
         if (p.fix && t >= 1 && t + 1 < T)
@@ -210,15 +209,15 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
         flg[q] = fl;
         flag_out[b * TO + q] = fl;
     }
-    __syncwarp();
-    for (int q = lane; q < TO * 8; q += 32) {
+    __syncthreads();
+    for (int q = lane; q < TO * 8; q += SGB_THREADS) {
         const int ta = q >> 3, f = q & 7;
         float v = zm[q];
         if (flg[ta] & (1 << (f & 1))) v = 0.5f * (zm[q - O * 8] + zm[q + O * 8]);
         z[q] = v;
     }
-    __syncwarp();
-    for (int q = lane; q < TO * 6; q += 32) {
+    __syncthreads();
+    for (int q = lane; q < TO * 6; q += SGB_THREADS) {
         const int ta = q / 6, f = q - ta * 6, t = ta / O;
         const int64_t o6 = (b * TO + ta) * 6 + f;
         float zf = 0.f, sf = 0.f;
@@ -240,7 +239,6 @@ __global__ void __launch_bounds__(32 * SG_WARPS) sup_prepare_fwd_kernel(
 
 // One CTA per sequence (the warp-per-sequence version ran 2.5 k dependent instructions per warp at 6 % occupancy:
 // 14 us for a few hundred elements per sequence); every phase is one pass over the CTA's threads.
-#define SGB_THREADS 256
 __global__ void __launch_bounds__(SGB_THREADS) sup_prepare_bwd_kernel(
     SupParams p, int64_t n, const float* __restrict__ zp, const int32_t* __restrict__ idx_in,
     const int32_t* __restrict__ flag_in, const float* __restrict__ std_full, const float* __restrict__ g_z_sup,
@@ -358,13 +356,13 @@ extern "C" int stove_sup_prepare_fwd(const stove_sup_cfg* cfg, int64_t n, const 
     STOVE_CHECK_ARG(!(p.match_app && !app), "appearance matching without appearances");
     if (n == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * SG_WARPS * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
-    const unsigned blocks = (unsigned)((n + SG_WARPS - 1) / SG_WARPS);
+    const size_t smem = sizeof(float) * (size_t)(2 * p.T * p.O * 8 + 2 * p.T * p.O);
+    const unsigned blocks = (unsigned)n;
     if (p.O == 3) {
-        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<3><<<blocks, 32 * SG_WARPS, smem, s>>>(
+        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<3><<<blocks, SGB_THREADS, smem, s>>>(
             p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
     } else {
-        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<0><<<blocks, 32 * SG_WARPS, smem, s>>>(
+        STOVE_KERNEL(K_SUP_PREPARE_FWD, s, sup_prepare_fwd_kernel<0><<<blocks, SGB_THREADS, smem, s>>>(
             p, n, zp, app, z_sup, z_full, std_full, app_out, idx, flag));
     }
     STOVE_LAUNCH_CHECK();
