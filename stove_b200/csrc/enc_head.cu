@@ -120,6 +120,11 @@ head_bwd_data_kernel(int64_t R, int K, int J, int P, const float* __restrict__ w
     }
     cp_wait_all();
     __syncthreads();
+    // g_pre of the warp's four rows for hidden units lane and lane + 32, kept in registers and written to the
+    // j-major tile as ONE float4 per unit: with scalar stores all 32 lanes hit one bank (row stride 32: 30 % of the
+    // kernel's shared-memory wavefronts were conflicts); the 4-row group of unit j sits at group position
+    // warp ^ (j & 7), so the eight lanes of a store phase touch eight different bank groups
+    float ga4[4], gb4[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int rl = warp * 4 + r;
@@ -143,9 +148,11 @@ head_bwd_data_kernel(int64_t R, int K, int J, int P, const float* __restrict__ w
             g_pre[row * JP + lane] = ga;
             g_pre[row * JP + lane + 32] = gb;
         }
-        GP[lane * ROWS + rl] = ga;
-        GP[(lane + 32) * ROWS + rl] = gb;
+        ga4[r] = ga;
+        gb4[r] = gb;
     }
+    *reinterpret_cast<float4*>(GP + lane * ROWS + ((warp ^ (lane & 7)) << 2)) = make_float4(ga4[0], ga4[1], ga4[2], ga4[3]);
+    *reinterpret_cast<float4*>(GP + (lane + 32) * ROWS + ((warp ^ (lane & 7)) << 2)) = make_float4(gb4[0], gb4[1], gb4[2], gb4[3]);
     __syncwarp();                                           // a warp only reads back its own four rows
     const int NI = K >> 5;                                  // input features per lane (k = lane + 32 i)
     float acc[4][KMAX / 32];
@@ -154,7 +161,7 @@ head_bwd_data_kernel(int64_t R, int K, int J, int P, const float* __restrict__ w
 #pragma unroll
         for (int i = 0; i < KMAX / 32; ++i) acc[r][i] = 0.f;
     for (int j = 0; j < J; ++j) {
-        const float4 g = *reinterpret_cast<const float4*>(GP + j * ROWS + warp * 4);
+        const float4 g = *reinterpret_cast<const float4*>(GP + j * ROWS + ((warp ^ (j & 7)) << 2));
 #pragma unroll
         for (int i = 0; i < KMAX / 32; ++i) {
             if (i < NI) {
