@@ -48,12 +48,24 @@ class DataParallel:
         for p in self.params:
             p.grad = None
         elbo, prop, rewards = self.model(x, step_counter, actions=actions)
-        loss = -elbo
         if reward_target is not None and self.reward_factor:
-            loss = loss + self.reward_factor * torch.nn.functional.binary_cross_entropy(rewards, reward_target)
-        loss.backward()
+            loss = -elbo + self.reward_factor * torch.nn.functional.binary_cross_entropy(rewards, reward_target)
+            loss.backward()
+            loss = loss.detach()
+        else:
+            # loss = -elbo: seed the backward pass with d loss / d elbo = -1 directly (no negation kernels and
+            # gradient fill between the ELBO kernel and its backward); the loss value is formed afterwards
+            elbo.backward(self._minus_one(elbo))
+            loss = -elbo.detach()
         self.all_reduce_gradients()
-        return loss.detach()
+        return loss
+
+    def _minus_one(self, like):
+        key = (like.device, like.dtype)
+        cache = self.__dict__.setdefault('_neg_one', {})
+        if key not in cache:
+            cache[key] = torch.full((), -1.0, device=like.device, dtype=like.dtype)
+        return cache[key]
 
     def all_reduce_gradients(self):
         """Average the gradients over ranks through one flat bucket; afterwards every `p.grad`

@@ -468,7 +468,9 @@ class LstmEncoder(torch.autograd.Function):
         if prepared is None:
             prepared = LstmEncoder.prepare(w_ih, w_hh, b_ih, b_hh)
         wih_col, whh_col, whh_row, bias, done = prepared
-        x_col, x_row = split_tf32_cat(x, 0, 1)             # x as left operand / as right operand of g^T x
+        x = x.contiguous()
+        x_col, _ = split_tf32_cat(x, 0, None)             # x as left operand; its row-concatenated split (the right
+        # operand of g^T x) is only needed by the backward pass, which builds it off the chain
         cur.wait_event(done)
         for t_ in (wih_col, whh_col, whh_row, bias):
             t_.record_stream(cur)
@@ -499,7 +501,7 @@ class LstmEncoder(torch.autograd.Function):
             acts.append(act)
             cs.append(c)
             h_col, c_prev = h_col_next, c
-        ctx.stash = (x_row, wih_col, whh_row, acts, cs, h_rows, steps, H)
+        ctx.stash = (x, wih_col, whh_row, acts, cs, h_rows, steps, H)
         ctx.head = None
         if w1 is not None:
             w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
@@ -512,12 +514,19 @@ class LstmEncoder(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        x_row, wih_col, whh_row, acts, cs, h_rows, steps, H = ctx.stash
+        x, wih_col, whh_row, acts, cs, h_rows, steps, H = ctx.stash
         g_out = g_out.contiguous()
         n = g_out.shape[0]
         dev, dt = g_out.device, g_out.dtype
         lib, st = N.lib(), N.stream()
         cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
+        x_row = None
+        if ctx.needs_input_grad[1]:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                _, x_row = split_tf32_cat(x, None, 1)      # consumed by the W_ih gradient GEMM at the very end
+                x_row_ready = torch.cuda.Event()
+                x_row_ready.record(side)
         g_head = (None, None, None, None)
         if ctx.head is not None:
             hs, w1, w2, hidden = ctx.head
@@ -567,7 +576,11 @@ class LstmEncoder(torch.autograd.Function):
                 g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
         for t_ in (g_rows, h_rows):
             t_.record_stream(side)
-        g_wih = _gemm_tn_splitk(g_row0, x_row, 2) if ctx.needs_input_grad[1] else None
+        g_wih = None
+        if ctx.needs_input_grad[1]:
+            cur.wait_event(x_row_ready)
+            x_row.record_stream(cur)
+            g_wih = _gemm_tn_splitk(g_row0, x_row, 2)
         # bias gradient (column sums of the summed gate gradient) behind the W_ih GEMM: the side stream's GEMM is
         # the longer branch
         g_b = g_sum.sum(0)
