@@ -111,6 +111,11 @@ class GraphedStep:
     host cost matters more than any single kernel.  Capture is possible because the forward has
     no host synchronisation (the reference's matcher has one per time step, stove.py:271-273).
     Inputs are copied into static buffers; `loss` and every `p.grad` live at fixed addresses.
+
+    Construct it before running eager backward passes of the same model on the default stream (or drop
+    their autograd graphs first): PyTorch binds each parameter's gradient accumulation to the stream of the
+    first autograd forward pass that used it, and the legacy default stream cannot take part in a capture
+    (`cudaErrorStreamCaptureImplicit`).  The warm-up passes here run on the capture stream for that reason.
     """
 
     def __init__(self, engine, example_x, example_actions=None, example_reward_target=None, warmup=3,

@@ -292,3 +292,24 @@ def test_supair_only_elbo_golden():
             sig = grad_signature(params[k[5:]].grad)
             ck.close(k, sig[[1, 3]], g[k][[1, 3]], GRAD)
     ck.finish()
+
+
+def test_readme_quickstart():
+    """The README's usage snippet: module call, rollout, DP engine + fused optimizer in one CUDA graph."""
+    from stove_b200 import Stove, StoveConfig, dp, synth
+    from stove_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    cfg = StoveConfig(width=32, height=32, num_obj=3, action_conditioned=False, action_space=None, device='cuda')
+    model = Stove(cfg).to('cuda')
+    x = synth.billiards(8, 8, 3, res=32, seed=0)['x'].cuda()
+    with torch.no_grad():
+        elbo, prop, _ = model(x, 0)
+        z_future, _ = model.rollout(prop['z'][:, -1], num=92)
+    assert elbo.dim() == 0 and prop['z'].shape == (8, 6, 3, 18) and z_future.shape == (8, 92, 3, 18)
+    engine = dp.DataParallel(model)
+    opt = FusedAdam(model.parameters(), lr=2e-3)
+    step = dp.GraphedStep(engine, x, optimizer=opt)
+    l0 = float(step(x))
+    for _ in range(10):
+        l1 = float(step(x))
+    assert l1 == l1 and l1 < l0
