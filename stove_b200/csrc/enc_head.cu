@@ -44,7 +44,7 @@ head_fwd_kernel(int64_t R, int K, int J, int P, const float* __restrict__ x, con
     // W1 [J][K] -> W1T [k][LDW] (4-byte async copies, coalesced along k); rows j >= J stay zero
     for (int i = tid; i < K * (JP - J); i += THREADS) W1T[(i / (JP - J)) * LDW + J + i % (JP - J)] = 0.f;
     {
-        const int sh = 31 - __clz(K);                  // K is a power of two times ... handle generally below
+        const int sh = 31 - __clz(K);                  // shift / mask indexing when K is a power of two
         if ((K & (K - 1)) == 0) {
             for (int i = tid; i < J * K; i += THREADS) cp4(W1T + (i & (K - 1)) * LDW + (i >> sh), w1 + i);
         } else {
