@@ -175,17 +175,6 @@ int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const float* zp, 
                           const float* g_z_full, const float* g_std_full, float* g_zp, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * LSTM cell of the recognition network (encoder.py:50-51; nn.LSTM gate order i, f, g, o).
- * The GEMMs stay in cuBLAS; this is the gate/state update:  gates = gx + gh,
- * c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c').  gx, gh, act, g_gates [n][4H];
- * c_prev (NULL = zeros), h_out, c_out, g_h, g_c, g_c_prev [n][H].  `act` saves the activated gates.
- * ---------------------------------------------------------------------------------- */
-int stove_lstm_cell_fwd(int64_t n, int H, const float* gx, const float* gh, const float* c_prev,
-                        float* h_out, float* c_out, float* act, void* stream);
-int stove_lstm_cell_bwd(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
-                        const float* g_h, const float* g_c, float* g_gates, float* g_c_prev, void* stream);
-
-/* ------------------------------------------------------------------------------------
  * GNN dynamics: Dynamics.forward + core (dynamics.py:181-265) for core_idx 0, and the
  * rollout loop Stove.rollout (stove.py:777-861).
  *
@@ -341,39 +330,59 @@ int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, const float* g
                    const float* z_all, float* g_bg, float* g_patch, float* g_z_all, float* g_overlap,
                    float* g_logq, float* g_trans, void* stream);
 
-/* fp32 -> hi (TF32-exact: low 13 mantissa bits cleared) + lo = x - hi, for 3xTF32 library GEMMs of
- * the recognition LSTM (encoder.py:50-51).  n % 4 == 0, 16-byte aligned pointers. */
-int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream);
+/* ------------------------------------------------------------------------------------
+ * Recognition LSTM (encoder.py:28-51: nn.LSTM fed the same frame num_obj times) on the tensor cores,
+ * forward and backward (csrc/lstm_tc.cu).  Every contraction is a 3xTF32 product on tcgen05 (kind::tf32,
+ * accumulator in TMEM, operands by TMA): an fp32 operand X [rows][K] is stored once as two PLANES
+ * [2][rows][K] -- hi = X with the low 13 mantissa bits cleared (TF32-exact), lo = X - hi -- and
+ * X Y^T ~= hi hi^T + hi lo^T + lo hi^T accumulates in one fp32 accumulator (fp32-level accuracy).
+ * All pointers 16-byte aligned; leading dimensions / plane strides multiples of 4 floats.
+ * ---------------------------------------------------------------------------------- */
 
-/* K-concatenated 3xTF32 operands: x [rows][cols] -> colcat [rows][3*cols] and / or rowcat [3*rows][cols]
- * (either may be NULL); block order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  Contracting an order-0 operand
- * with an order-1 operand along the tripled extent gives hi*hi + hi*lo + lo*hi in ONE TF32 GEMM. */
-int stove_split_tf32_cat(int64_t rows, int cols, const float* x, float* colcat, int col_order,
-                         float* rowcat, int row_order, void* stream);
+/* x [rows][cols] (row stride ldx) -> pl [2][rows][cols] and / or the transposed planes plT [2][cols][ldT]
+ * (ldT >= rows; columns rows .. ldT-1 are written as zero).  Either output may be NULL. */
+int stove_split_planes(int64_t rows, int cols, const float* x, int64_t ldx, float* pl, float* plT,
+                       int64_t ldT, void* stream);
 
-/* LSTM cell with the launches around it folded in (fused recognition network, encoder.py:28-57):
- * forward adds `bias` [4H], writes h into a strided output (row stride h_ld floats) and optionally its
- * K-concatenated TF32 operands h_col [n][3H] (hi, hi, lo) and h_row [3n][H] (hi, lo, hi); backward takes
- * g_h = g_h_a (row stride g_h_a_ld) + the g_h_b_parts split-K partials g_h_b [parts][n][H] (may be NULL), writes the concatenated operands of the gate
- * gradient g_col [n][12H] (optional) and g_row [3n][4H], both (hi, hi, lo) -- of the running sum if
- * split_acc -- and accumulates the gate gradient into g_acc (acc_mode 0: overwrite, 1: add).
- * g_c, c_prev, g_c_prev may be NULL. */
-int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
-                          const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
-                          float* h_col, float* h_row, void* stream);
-int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
+/* One LSTM step: gates = A B^T + addend (A_pl [2][n][K] = planes of the frame or of h_{t-1}; B_pl [2][4H][K] =
+ * planes of W_ih or W_hh, nn.LSTM gate order i, f, g, o along the rows), then the LSTM cell in the GEMM's
+ * epilogue.  addend = bias [4H] (addend_is_bias) or the input-GEMM gates [n][4H]; c_prev [n][H] or NULL
+ * (zero state); gx_out [n][4H] (optional) receives GEMM + addend; h_out has row stride h_ld (a slice of the
+ * stacked (n, steps, H) output); act [n][4H] keeps the activated gates for the backward pass; h_pl [2][n][H]
+ * (optional) = planes of h for the next step; hT_pl (optional, needs h_pl) = TRANSPOSED planes of h with
+ * row stride ldT and plane stride hT_plane: rows = hidden units, columns 0 .. n-1 = frames, columns
+ * n .. spanT-1 zero (a step's block of a buffer stacked along the columns for the W_hh gradient).
+ * H % 32 == 0, K % 4 == 0. */
+int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t K, const float* A_pl, const float* B_pl, const float* addend,
+                             int addend_is_bias, const float* c_prev, float* gx_out, float* h_out, int64_t h_ld,
+                             float* c_out, float* act, float* h_pl, float* hT_pl, int64_t ldT, int64_t spanT,
+                             int64_t hT_plane, void* stream);
+
+/* D = A B^T over K columns: A_pl [2][M][lda], B_pl [2][N][ldb] (plane strides a_plane / b_plane floats),
+ * written as `parts` split-K partial products D[p][M][ldd] (part stride part_stride floats; the caller sums
+ * them, stove_sum_parts).  The library may lower `parts` (never below 1): stove_tc3_gemm_parts returns the
+ * count it will use for (M, N, K, want).  Used for the hidden-state gradient (gate gradient x W_hh) and for
+ * both weight gradients of the LSTM (contractions over the frames: transposed planes as operands). */
+int stove_tc3_gemm(int64_t M, int64_t N, int64_t K, const float* A_pl, int64_t lda, int64_t a_plane,
+                   const float* B_pl, int64_t ldb, int64_t b_plane, float* D, int64_t ldd, int parts,
+                   int64_t part_stride, void* stream);
+int stove_tc3_gemm_parts(int64_t M, int64_t N, int64_t K, int want);
+
+/* Gate/state backward of one LSTM step.  g_h = g_h_a (row stride g_h_a_ld) + the g_h_b_parts split-K parts
+ * g_h_b [parts][n][H] (NULL: none); g_c, c_prev, g_c_prev may be NULL.  Outputs: g_pl [2][n][4H] = planes of
+ * this step's gate gradient (optional); gT_pl = transposed planes (rows = 4H gate units, row stride ldT,
+ * plane stride gT_plane, columns n .. spanT-1 zero) of this step's gate gradient or, with emit_acc, of the
+ * running sum over the steps (optional); g_acc [n][4H] = running sum (acc_mode 0: start, 1: add; not written
+ * when emit_acc; may be NULL when acc_mode == 0 and emit_acc); bias_part [ceil(max(n, spanT) / 32)][4H] =
+ * column sums of the emitted gradient over blocks of 32 frames (optional; sum them with stove_sum_parts). */
+int stove_lstm_cell_bwd_t(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
                           const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, int g_h_b_parts,
-                          const float* g_c, float* g_col, float* g_row, float* g_acc, int acc_mode, int split_acc,
+                          const float* g_c, float* g_pl, float* gT_pl, int64_t ldT, int64_t spanT,
+                          int64_t gT_plane, float* g_acc, int acc_mode, int emit_acc, float* bias_part,
                           float* g_c_prev, void* stream);
 
-/* One LSTM step of the recognition network on the tensor cores (encoder.py:50-51; csrc/lstm_tc.cu):
- * gates = A B^T + addend with a tcgen05 (kind::tf32) GEMM over the K-concatenated 3xTF32 operands
- * A [n][Kc] = (hi, hi, lo), B [4H][Kc] = (hi, lo, hi) (nn.LSTM gate order i, f, g, o along the rows), then the
- * LSTM cell in the epilogue.  addend = bias [4H] (addend_is_bias) or the input-GEMM gates [n][4H]; gx_out
- * (optional) receives GEMM + addend; outputs as stove_lstm_cell_fwd_x.  H % 32 == 0, Kc % 4 == 0. */
-int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t Kc, const float* A, const float* B, const float* addend,
-                             int addend_is_bias, const float* c_prev, float* gx_out, float* h_out, int64_t h_ld,
-                             float* c_out, float* act, float* h_col, float* h_row, void* stream);
+/* out[i] = sum over p < parts of in[p * stride + i], fixed order; numel % 4 == 0, stride % 4 == 0. */
+int stove_sum_parts(int64_t numel, int parts, int64_t stride, const float* in, float* out, void* stream);
 
 /* Output head of the recognition network (encoder.py:53-56): out = fc2(sigmoid(fc1(x))), x [R][K],
  * w1 [J][K], b1 [J], w2 [P][J], b2 [P] (nn.Linear layouts); hidden [R][J] = sigmoid(fc1(x)) is kept for the

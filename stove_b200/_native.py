@@ -94,12 +94,12 @@ SIGNATURES = {
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
     'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
-    'stove_lstm_cell_fwd': (C.c_int, [i64, C.c_int] + [vp] * 6 + [vp]),
-    'stove_lstm_cell_bwd': (C.c_int, [i64, C.c_int] + [vp] * 7 + [vp]),
-    'stove_split_tf32_cat': (C.c_int, [i64, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp]),
-    'stove_lstm_cell_fwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
-    'stove_lstm_cell_bwd_x': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
-    'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp]),
+    'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, vp]),
+    'stove_split_planes': (C.c_int, [i64, C.c_int, vp, i64, vp, vp, i64, vp]),
+    'stove_tc3_gemm': (C.c_int, [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, C.c_int, i64, vp]),
+    'stove_tc3_gemm_parts': (C.c_int, [i64, i64, i64, C.c_int]),
+    'stove_lstm_cell_bwd_t': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, C.c_int, vp, vp, vp, i64, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp]),
+    'stove_sum_parts': (C.c_int, [i64, C.c_int, i64, vp, vp, vp]),
     'stove_enc_head_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 7 + [vp]),
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
     'stove_enc_head_bwd_data': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp]),
@@ -123,7 +123,6 @@ SIGNATURES = {
     'stove_zall_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     'stove_elbo_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 8 + [vp]),
     'stove_elbo_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 9 + [vp]),
-    'stove_split_tf32': (C.c_int, [i64, vp, vp, vp, vp]),
     'stove_gnn_rollout': (C.c_int, [PG, i64, C.c_int, vp, vp, C.c_int, vp, vp, vp, f32, f32, f32,
                                     vp, vp, vp, vp, vp]),
 }

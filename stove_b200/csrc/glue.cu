@@ -385,79 +385,6 @@ extern "C" int stove_sup_prepare_bwd(const stove_sup_cfg* cfg, int64_t n, const 
     return STOVE_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// LSTM cell (encoder.py:50-51, nn.LSTM gate order i, f, g, o): the two GEMMs stay in cuBLAS,
-// the gate non-linearities and state update (10 elementwise launches per step forward, ~25
-// backward in the tensor version) are one kernel each way.
-//   gates = gx + gh (+ bias already inside gx);  c' = sig(f) c + sig(i) tanh(g);  h' = sig(o) tanh(c')
-// ---------------------------------------------------------------------------------------
-__global__ void lstm_cell_fwd_kernel(int64_t n, int H, const float* __restrict__ gx, const float* __restrict__ gh,
-                                     const float* __restrict__ c_prev, float* __restrict__ h_out,
-                                     float* __restrict__ c_out, float* __restrict__ act) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * H) return;
-    const int64_t b = i / H;
-    const int k = (int)(i - b * H);
-    const float* px = gx + b * 4 * H;
-    const float* ph = gh ? gh + b * 4 * H : nullptr;
-    float g[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) g[q] = px[q * H + k] + (ph ? ph[q * H + k] : 0.f);
-    const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
-    const float cp = c_prev ? c_prev[i] : 0.f;
-    const float c = fg * cp + ig * gg;
-    const float tc = tanhf(c);
-    c_out[i] = c;
-    h_out[i] = og * tc;
-    float* pa = act + b * 4 * H;        // activated gates, saved for the backward
-    pa[k] = ig; pa[H + k] = fg; pa[2 * H + k] = gg; pa[3 * H + k] = og;
-}
-
-__global__ void lstm_cell_bwd_kernel(int64_t n, int H, const float* __restrict__ act,
-                                     const float* __restrict__ c_prev, const float* __restrict__ c_out,
-                                     const float* __restrict__ g_h, const float* __restrict__ g_c,
-                                     float* __restrict__ g_gates, float* __restrict__ g_c_prev) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * H) return;
-    const int64_t b = i / H;
-    const int k = (int)(i - b * H);
-    const float* pa = act + b * 4 * H;
-    const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
-    const float tc = tanhf(c_out[i]);
-    const float gh = g_h ? g_h[i] : 0.f;
-    const float gc = (g_c ? g_c[i] : 0.f) + gh * og * (1.f - tc * tc);
-    const float cp = c_prev ? c_prev[i] : 0.f;
-    float* pg = g_gates + b * 4 * H;
-    pg[k] = gc * gg * ig * (1.f - ig);
-    pg[H + k] = gc * cp * fg * (1.f - fg);
-    pg[2 * H + k] = gc * ig * (1.f - gg * gg);
-    pg[3 * H + k] = gh * tc * og * (1.f - og);
-    g_c_prev[i] = gc * fg;
-}
-
-extern "C" int stove_lstm_cell_fwd(int64_t n, int H, const float* gx, const float* gh, const float* c_prev,
-                                   float* h_out, float* c_out, float* act, void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && H > 0 && gx && h_out && c_out && act, "null pointer");
-    if (n == 0) return STOVE_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_LSTM_CELL_FWD, s, lstm_cell_fwd_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, gx, gh, c_prev, h_out, c_out, act));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
-extern "C" int stove_lstm_cell_bwd(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
-                                   const float* g_h, const float* g_c, float* g_gates, float* g_c_prev,
-                                   void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_gates && g_c_prev, "null pointer");
-    if (n == 0) return STOVE_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, act, c_prev, c_out, g_h, g_c, g_gates, g_c_prev));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
 // ------------------------------------------------------------------------------------
 // z of every scored frame (stove.py:731-736): frames t = 1 .. T-1 use the SuPAIR state for
 // t < skip and the sampled state z_t for t >= skip; [sx, sy/sx, x, y] -> [sx, sy, x, y]
@@ -645,190 +572,6 @@ extern "C" int stove_elbo_bwd(int64_t n, int T, int skip, int O, float beta, con
     if (n * (T - skip) > items) items = n * (T - skip);
     STOVE_KERNEL(K_ELBO_BWD, (cudaStream_t)stream, elbo_bwd_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         n, T, skip, O, beta, g, patch, z_all, g_bg, g_patch, g_z_all, g_overlap, g_logq, g_trans));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
-// ------------------------------------------------------------------------------------
-// fp32 -> (hi, lo) with hi exactly representable in TF32 (low 13 mantissa bits cleared) and
-// lo = x - hi (exact).  a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi on the TF32 tensor cores keeps
-// fp32-level accuracy (error ~2^-21 relative per product) at a fraction of the SIMT-fp32 GEMM time;
-// used for the recognition LSTM's GEMMs (encoder.py:50-51), which stay library GEMMs.
-// ------------------------------------------------------------------------------------
-__global__ void split_tf32_kernel(int64_t n4, const float4* __restrict__ x, float4* __restrict__ hi,
-                                  float4* __restrict__ lo) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const float4 v = __ldg(x + i);
-    float4 h;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-    hi[i] = h;
-    lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-}
-
-extern "C" int stove_split_tf32(int64_t n, const float* x, float* hi, float* lo, void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && n % 4 == 0 && x && hi && lo, "need n % 4 == 0 and non-null pointers");
-    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)hi | (uintptr_t)lo) & 15) == 0, "pointers must be 16-byte aligned");
-    if (n == 0) return STOVE_OK;
-    STOVE_KERNEL(K_SPLIT_TF32, (cudaStream_t)stream, split_tf32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        n / 4, (const float4*)x, (float4*)hi, (float4*)lo));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
-// ------------------------------------------------------------------------------------
-// LSTM cell variants for the fused recognition network (video_prediction/encoder.py): the same
-// gate/state update as above, plus what used to be separate launches around it --
-//   forward : bias add, h written straight into the stacked output (row stride h_ld), and the TF32
-//             split (hi, lo) of h for the next step's 3xTF32 hidden GEMM;
-//   backward: g_h = g_h_a (strided slice of the stacked gradient) + g_h_b (from the next step's
-//             hidden GEMM), the TF32 split of the gate gradient for this step's GEMMs, and the
-//             running sum over steps of the gate gradients (what W_ih and the bias see).
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
-
-__global__ void lstm_cell_fwd_x_kernel(int64_t n, int H, const float* __restrict__ gx, const float* __restrict__ bias,
-                                       const float* __restrict__ gh, const float* __restrict__ c_prev,
-                                       float* __restrict__ h_out, int64_t h_ld, float* __restrict__ c_out,
-                                       float* __restrict__ act, float* __restrict__ h_col, float* __restrict__ h_row) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * H) return;
-    const int64_t b = i / H;
-    const int k = (int)(i - b * H);
-    const float* px = gx + b * 4 * H;
-    const float* ph = gh ? gh + b * 4 * H : nullptr;
-    float g[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) g[q] = px[q * H + k] + __ldg(bias + q * H + k) + (ph ? ph[q * H + k] : 0.f);
-    const float ig = sigmoidf_(g[0]), fg = sigmoidf_(g[1]), gg = tanhf(g[2]), og = sigmoidf_(g[3]);
-    const float cp = c_prev ? c_prev[i] : 0.f;
-    const float c = fg * cp + ig * gg;
-    const float tc = tanhf(c);
-    const float h = og * tc;
-    c_out[i] = c;
-    h_out[b * h_ld + k] = h;
-    if (h_col) {
-        // K-concatenated 3xTF32 operands: [hi | hi | lo] along the columns (left operand of h W_hh^T) and
-        // [hi ; lo ; hi] along the rows (right operand of g^T h)
-        const float hh = tf32_hi(h), hl = h - hh;
-        float* pc = h_col + b * 3 * H + k;
-        pc[0] = hh; pc[H] = hh; pc[2 * H] = hl;
-        h_row[i] = hh; h_row[n * H + i] = hl; h_row[2 * n * H + i] = hh;
-    }
-    float* pa = act + b * 4 * H;
-    pa[k] = ig; pa[H + k] = fg; pa[2 * H + k] = gg; pa[3 * H + k] = og;
-}
-
-// acc_mode: 0 = g_acc = g, 1 = g_acc += g.  split_acc: the (hi, lo) outputs hold the split of the
-// accumulated sum instead of this step's gradient.
-__global__ void lstm_cell_bwd_x_kernel(int64_t n, int H, const float* __restrict__ act,
-                                       const float* __restrict__ c_prev, const float* __restrict__ c_out,
-                                       const float* __restrict__ g_h_a, int64_t g_h_a_ld,
-                                       const float* __restrict__ g_h_b, int g_h_b_parts, const float* __restrict__ g_c,
-                                       float* __restrict__ g_col, float* __restrict__ g_row,
-                                       float* __restrict__ g_acc, int acc_mode, int split_acc,
-                                       float* __restrict__ g_c_prev) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * H) return;
-    const int64_t b = i / H;
-    const int k = (int)(i - b * H);
-    const float* pa = act + b * 4 * H;
-    const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
-    const float tc = tanhf(c_out[i]);
-    float gh = g_h_a[b * g_h_a_ld + k];
-    if (g_h_b)                                   // split-K partial products of the hidden GEMM, [parts][n][H]
-        for (int part = 0; part < g_h_b_parts; ++part) gh += g_h_b[(int64_t)part * n * H + i];
-    const float gc = (g_c ? g_c[i] : 0.f) + gh * og * (1.f - tc * tc);
-    const float cp = c_prev ? c_prev[i] : 0.f;
-    float g[4];
-    g[0] = gc * gg * ig * (1.f - ig);
-    g[1] = gc * cp * fg * (1.f - fg);
-    g[2] = gc * ig * (1.f - gg * gg);
-    g[3] = gh * tc * og * (1.f - og);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int64_t o = b * 4 * H + q * H + k;
-        const float a = acc_mode ? g_acc[o] + g[q] : g[q];
-        g_acc[o] = a;
-        // K-concatenated 3xTF32 operands, both [hi, hi, lo]: along the columns (left operand of g W_hh)
-        // and along the rows (left operand, transposed, of g^T h and g^T x)
-        const float v = split_acc ? a : g[q];
-        const float vh = tf32_hi(v), vl = v - vh;
-        if (g_col) {
-            float* pc = g_col + b * 12 * H + q * H + k;
-            pc[0] = vh; pc[4 * H] = vh; pc[8 * H] = vl;
-        }
-        g_row[o] = vh; g_row[n * 4 * H + o] = vh; g_row[2 * n * 4 * H + o] = vl;
-    }
-    if (g_c_prev) g_c_prev[i] = gc * fg;
-}
-
-extern "C" int stove_lstm_cell_fwd_x(int64_t n, int H, const float* gx, const float* bias, const float* gh,
-                                     const float* c_prev, float* h_out, int64_t h_ld, float* c_out, float* act,
-                                     float* h_col, float* h_row, void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && H > 0 && gx && bias && h_out && c_out && act && h_ld >= H, "bad argument");
-    STOVE_CHECK_ARG((h_col == nullptr) == (h_row == nullptr), "h_col and h_row go together");
-    if (n == 0) return STOVE_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_LSTM_CELL_FWD, s, lstm_cell_fwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, gx, bias, gh, c_prev, h_out, h_ld, c_out, act, h_col, h_row));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
-extern "C" int stove_lstm_cell_bwd_x(int64_t n, int H, const float* act, const float* c_prev, const float* c_out,
-                                     const float* g_h_a, int64_t g_h_a_ld, const float* g_h_b, int g_h_b_parts,
-                                     const float* g_c, float* g_col, float* g_row, float* g_acc, int acc_mode,
-                                     int split_acc, float* g_c_prev, void* stream) {
-    STOVE_CHECK_ARG(n >= 0 && H > 0 && act && c_out && g_h_a && g_row && g_acc && g_h_a_ld >= H, "bad argument");
-    STOVE_CHECK_ARG(!g_h_b || g_h_b_parts >= 1, "g_h_b_parts must be >= 1");
-    if (n == 0) return STOVE_OK;
-    cudaStream_t s = (cudaStream_t)stream;
-    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lstm_cell_bwd_x_kernel<<<(unsigned)((n * H + 255) / 256), 256, 0, s>>>(
-        n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_h_b_parts, g_c, g_col, g_row, g_acc, acc_mode, split_acc, g_c_prev));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
-}
-
-// x [rows][cols] -> K-concatenated 3xTF32 operands: colcat [rows][3*cols] and / or rowcat [3*rows][cols];
-// block order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  A GEMM contracts a (hi, hi, lo) operand with a
-// (hi, lo, hi) one: hi*hi + hi*lo + lo*hi in a single call with 3x the K extent.
-__global__ void split_cat_kernel(int64_t rows, int cols, const float4* __restrict__ x, float* __restrict__ colcat,
-                                 int col_order, float* __restrict__ rowcat, int row_order) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c4n = cols >> 2;
-    if (i >= rows * c4n) return;
-    const int64_t r = i / c4n;
-    const int c = (int)(i - r * c4n) * 4;
-    const float4 v = __ldg(x + i);
-    float4 h, l;
-    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-    l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    if (colcat) {
-        float* p = colcat + r * 3 * cols + c;
-        *reinterpret_cast<float4*>(p) = h;
-        *reinterpret_cast<float4*>(p + cols) = col_order ? l : h;
-        *reinterpret_cast<float4*>(p + 2 * cols) = col_order ? h : l;
-    }
-    if (rowcat) {
-        float* p = rowcat + r * cols + c;
-        *reinterpret_cast<float4*>(p) = h;
-        *reinterpret_cast<float4*>(p + rows * cols) = row_order ? l : h;
-        *reinterpret_cast<float4*>(p + 2 * rows * cols) = row_order ? h : l;
-    }
-}
-
-extern "C" int stove_split_tf32_cat(int64_t rows, int cols, const float* x, float* colcat, int col_order,
-                                    float* rowcat, int row_order, void* stream) {
-    STOVE_CHECK_ARG(rows >= 0 && cols > 0 && cols % 4 == 0 && x && (colcat || rowcat), "need cols % 4 == 0");
-    STOVE_CHECK_ARG((((uintptr_t)x | (uintptr_t)colcat | (uintptr_t)rowcat) & 15) == 0, "pointers must be 16-byte aligned");
-    if (rows == 0) return STOVE_OK;
-    const int64_t items = rows * (cols / 4);
-    STOVE_KERNEL(K_SPLIT_TF32, (cudaStream_t)stream, split_cat_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        rows, cols, (const float4*)x, colcat, col_order, rowcat, row_order));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -288,100 +288,56 @@ class SupPrepare(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------
-# LSTM cell
+# 3xTF32 operands and GEMM of the recognition LSTM (csrc/lstm_tc.cu)
 # ----------------------------------------------------------------------------------------
-class LstmCell(torch.autograd.Function):
-    """gx (n, 4H) [bias included], gh (n, 4H) | None, c_prev (n, H) | None -> h (n, H), c (n, H)."""
-
-    @staticmethod
-    def forward(ctx, gx, gh, c_prev):
-        gx, gh, c_prev = gx.contiguous(), _c(gh), _c(c_prev)
-        N.require_cuda_f32(gx, gh, c_prev)
-        n, H4 = gx.shape
-        H = H4 // 4
-        h = torch.empty(n, H, device=gx.device, dtype=gx.dtype)
-        c = torch.empty_like(h)
-        act = torch.empty_like(gx)
-        N.check(N.lib().stove_lstm_cell_fwd(n, H, N.ptr(gx), N.ptr(gh), N.ptr(c_prev), N.ptr(h), N.ptr(c),
-                                            N.ptr(act), N.stream()))
-        ctx.save_for_backward(act, c_prev, c)
-        ctx.has = (gh is not None, c_prev is not None)
-        return h, c
-
-    @staticmethod
-    def backward(ctx, g_h, g_c):
-        act, c_prev, c = ctx.saved_tensors
-        n, H = c.shape
-        g_gates = torch.empty_like(act)
-        g_c_prev = torch.empty_like(c)
-        N.check(N.lib().stove_lstm_cell_bwd(n, H, N.ptr(act), N.ptr(c_prev), N.ptr(c), N.ptr(_c(g_h)),
-                                            N.ptr(_c(g_c)), N.ptr(g_gates), N.ptr(g_c_prev), N.stream()))
-        return g_gates, (g_gates if ctx.has[0] else None), (g_c_prev if ctx.has[1] else None)
+def _round4(v):
+    return (v + 3) // 4 * 4
 
 
-# ----------------------------------------------------------------------------------------
-# 3xTF32 linear layer (recognition LSTM GEMMs)
-# ----------------------------------------------------------------------------------------
-def split_tf32(x):
-    """x -> (hi, lo): hi exactly representable in TF32, lo = x - hi (no autograd)."""
-    x = x.contiguous()
+def split_planes(x, planes=True, transposed=False):
+    """x (rows, cols) -> (pl (2, rows, cols) | None, plT (2, cols, ldT) | None): the TF32-exact part `hi` of
+    every element and the remainder `lo = x - hi` as two planes; plT holds the transposed planes with
+    ldT = rows rounded up to 4 (pad columns zero).  No autograd."""
     N.require_cuda_f32(x)
-    if x.numel() % 4:
-        raise RuntimeError('split_tf32 needs a multiple of 4 elements')
-    hi, lo = torch.empty_like(x), torch.empty_like(x)
-    N.check(N.lib().stove_split_tf32(x.numel(), N.ptr(x), N.ptr(hi), N.ptr(lo), N.stream()))
-    return hi, lo
+    if x.dim() != 2 or x.stride(1) != 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    pl = torch.empty(2, rows, cols, device=x.device, dtype=x.dtype) if planes else None
+    ldT = _round4(rows)
+    plT = torch.empty(2, cols, ldT, device=x.device, dtype=x.dtype) if transposed else None
+    N.check(N.lib().stove_split_planes(rows, cols, N.ptr(x), x.stride(0), N.ptr(pl), N.ptr(plT), ldT, N.stream()))
+    return pl, plT
 
 
-def mm3(a, b, out=None):
-    """a @ b (added to `out` if given) for split operands a = (a_hi, a_lo), b = (b_hi, b_lo) (any
-    strides): three TF32 tensor-core GEMMs, fp32 accumulate; the lo * lo term (2^-22 relative) is
-    dropped."""
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        if out is None:
-            out = torch.mm(a[0], b[1])
-        else:
-            out.addmm_(a[0], b[1])
-        out.addmm_(a[1], b[0])
-        out.addmm_(a[0], b[0])
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+def tc3_gemm(a_pl, b_pl, K=None, parts=1, out=None):
+    """a_pl (2, M, lda), b_pl (2, N, ldb): (hi, lo) planes -> a @ b.t() over the first K columns as
+    `parts` split-K partial products (parts, M, N) (parts may come back smaller), 3xTF32 on tcgen05."""
+    M, lda = a_pl.shape[1], a_pl.shape[2]
+    Nn, ldb = b_pl.shape[1], b_pl.shape[2]
+    K = min(lda, ldb) if K is None else K
+    parts = N.lib().stove_tc3_gemm_parts(M, Nn, K, parts)
+    if out is None:
+        out = torch.empty(parts, M, Nn, device=a_pl.device, dtype=a_pl.dtype)
+    N.check(N.lib().stove_tc3_gemm(M, Nn, K, N.ptr(a_pl), lda, a_pl.stride(0), N.ptr(b_pl), ldb, b_pl.stride(0),
+                                   N.ptr(out), Nn, parts, M * Nn, N.stream()))
     return out
 
 
-class Linear3(torch.autograd.Function):
-    """y = a @ w.t() (a (n, K), w (M, K) as in nn.Linear, no bias) in 3xTF32.  `a_split` / `w_split`
-    are optional precomputed (hi, lo) pairs so operands used several times are split once."""
-
-    @staticmethod
-    def forward(ctx, a, w, a_split, w_split):
-        a_split = a_split if a_split is not None else split_tf32(a)
-        w_split = w_split if w_split is not None else split_tf32(w)
-        ctx.a_split, ctx.w_split = a_split, w_split
-        return mm3(a_split, (w_split[0].t(), w_split[1].t()))
-
-    @staticmethod
-    def backward(ctx, g):
-        g_split = split_tf32(g)
-        g_a = mm3(g_split, ctx.w_split) if ctx.needs_input_grad[0] else None
-        g_w = mm3((g_split[0].t(), g_split[1].t()), ctx.a_split) if ctx.needs_input_grad[1] else None
-        return g_a, g_w, None, None
+def sum_parts(parts_t, out=None):
+    """(P, ...) -> sum over the first dimension in a fixed order (split-K partials, bias partial sums)."""
+    P = parts_t.shape[0]
+    numel = parts_t[0].numel()
+    if P == 1 and out is None:
+        return parts_t[0]
+    if out is None:
+        out = torch.empty(parts_t.shape[1:], device=parts_t.device, dtype=parts_t.dtype)
+    N.check(N.lib().stove_sum_parts(numel, P, numel, N.ptr(parts_t), N.ptr(out), N.stream()))
+    return out
 
 
-def split_tf32_cat(x, col_order=None, row_order=None):
-    """K-concatenated 3xTF32 operands of a 2-D tensor: (colcat (rows, 3 cols) | None, rowcat (3 rows, cols)
-    | None); order 0 = (hi, hi, lo), 1 = (hi, lo, hi).  One TF32 GEMM of an order-0 operand with an
-    order-1 operand over the tripled extent = hi*hi + hi*lo + lo*hi."""
-    x = x.contiguous()
-    N.require_cuda_f32(x)
-    rows, cols = x.shape
-    col = torch.empty(rows, 3 * cols, device=x.device, dtype=x.dtype) if col_order is not None else None
-    row = torch.empty(3 * rows, cols, device=x.device, dtype=x.dtype) if row_order is not None else None
-    N.check(N.lib().stove_split_tf32_cat(rows, cols, N.ptr(x), N.ptr(col), col_order or 0, N.ptr(row),
-                                         row_order or 0, N.stream()))
-    return col, row
+def _split_k(tiles, num_kb, sms=148):
+    """split-K factor that fills the machine: about one CTA per SM, at least 4 k-blocks per part"""
+    return max(1, min(sms // max(tiles, 1), num_kb // 4))
 
 
 _AUX_STREAMS = {}
@@ -397,61 +353,32 @@ def _aux_stream(device):
     return _AUX_STREAMS[key]
 
 
-def _mm_tf32(a, b, out=None):
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        return torch.mm(a, b) if out is None else out.addmm_(a, b)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
-def _bmm_tf32(a, b):
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        return torch.bmm(a, b)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-
-
-def _gemm_tn_splitk(a, b, parts):
-    """a^T @ b for a (K, M), b (K, N) as a split-K strided-batched TF32 GEMM + one reduction of the partials."""
-    K = a.shape[0]
-    if parts <= 1 or K % parts:
-        return _mm_tf32(a.t(), b)
-    part = _bmm_tf32(a.view(parts, K // parts, a.shape[1]).transpose(1, 2), b.view(parts, K // parts, b.shape[1]))
-    if parts == 2:
-        return torch.add(part[0], part[1])         # one element-wise pass (the generic reduction takes 4x as long)
-    return part.sum(0)
-
-
 class LstmEncoder(torch.autograd.Function):
     """h_1 .. h_steps of a one-layer LSTM that is fed the SAME input x at every step from a zero state
     (the recognition network, encoder.py:50-51; nn.LSTM gate order and parameter shapes).
     x (n, K), w_ih (4H, K), w_hh (4H, H), b_ih / b_hh (4H,) -> (n, steps, H).
 
-    One autograd node instead of ~65 launches: the input GEMM is done once; every GEMM is ONE TF32
-    tensor-core call over K-concatenated (hi, lo) operands (3xTF32: fp32-level accuracy, in-graph
-    20 us instead of 81 us for the SIMT-fp32 input GEMM); the cell kernels add the bias, write h
-    into the stacked output, emit the concatenated operands the next GEMM needs and accumulate the
-    gate gradients that W_ih and the biases see."""
+    One autograd node, every contraction a hand-written tcgen05 kernel (csrc/lstm_tc.cu), 3xTF32 over (hi, lo)
+    operand planes that are written once and read once per tile: the input GEMM is done once (not per
+    step) with the LSTM cell as its epilogue; the backward pass runs cell kernel -> hidden-state GEMM per
+    step, then the two weight-gradient GEMMs (contractions over the frames, fed by the transposed planes the
+    forward / cell kernels emit) as split-K launches with a fixed-order reduction."""
 
     @staticmethod
     def prepare(w_ih, w_hh, b_ih, b_hh):
-        """Operand splits of the weights and the summed bias, on the library's side stream.  They depend on the
+        """Operand planes of the weights and the summed bias, on the library's side stream.  They depend on the
         parameters only: issued at the very start of a step (before the frames are even transformed) they are
         off the chain; pass the result as `prepared`."""
         dev = w_ih.device
         cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side), torch.no_grad():
-            wih_col, _ = split_tf32_cat(w_ih.detach(), 1, None)
-            whh_col, whh_row = split_tf32_cat(w_hh.detach(), 1, 1)
+            wih_pl, _ = split_planes(w_ih.detach())
+            whh_pl, whhT_pl = split_planes(w_hh.detach(), True, True)
             bias = (b_ih.detach() + b_hh.detach()).contiguous()
             done = torch.cuda.Event()
             done.record(side)
-        return wih_col, whh_col, whh_row, bias, done
+        return wih_pl, whh_pl, whhT_pl, bias, done
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None, prepared=None):
@@ -462,46 +389,45 @@ class LstmEncoder(torch.autograd.Function):
         n, H = x.shape[0], w_hh.shape[1]
         dev, dt = x.device, x.dtype
         lib, st = N.lib(), N.stream()
-        # the operand splits of the weights do not depend on the frames: they run beside the split of x (or
-        # were issued even earlier through LstmEncoder.prepare)
         cur = torch.cuda.current_stream(dev)
         if prepared is None:
             prepared = LstmEncoder.prepare(w_ih, w_hh, b_ih, b_hh)
-        wih_col, whh_col, whh_row, bias, done = prepared
+        wih_pl, whh_pl, whhT_pl, bias, done = prepared
         x = x.contiguous()
-        x_col, _ = split_tf32_cat(x, 0, None)             # x as left operand; its row-concatenated split (the right
-        # operand of g^T x) is only needed by the backward pass, which builds it off the chain
+        x_pl, _ = split_planes(x)                          # the transposed planes (right operand of g^T x) are only
+        # needed by the backward pass, which builds them off the chain
         cur.wait_event(done)
-        for t_ in (wih_col, whh_col, whh_row, bias):
+        for t_ in (wih_pl, whh_pl, whhT_pl, bias):
             t_.record_stream(cur)
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
         gx = torch.empty(n, 4 * H, device=dev, dtype=dt) if steps > 1 else None
         acts, cs = [], []
-        # row-concatenated TF32 operands of h_0 .. h_{steps-2}, stacked: the backward contracts them with the
-        # stacked gate gradients in ONE GEMM
-        h_rows = torch.empty(max(steps - 1, 0), 3 * n, H, device=dev, dtype=dt)
-        h_col = c_prev = None
+        # transposed (hi, lo) planes of h_0 .. h_{steps-2}, stacked along the columns: the backward contracts them
+        # with the equally stacked gate gradients in ONE GEMM
+        ldT = _round4(n)
+        ldS = max(steps - 1, 1) * ldT
+        hT_all = torch.empty(2, H, ldS, device=dev, dtype=dt) if steps > 1 else None
+        h_pl = c_prev = None
         for t in range(steps):
-            # one tcgen05 kernel per step (csrc/lstm_tc.cu): gate GEMM over the K-concatenated operands with
-            # the cell as its epilogue; step 0 contracts the frame with W_ih and leaves gx = x W_ih^T + b for
-            # the later steps, which contract h_{t-1} with W_hh and add gx
+            # one tcgen05 kernel per step: gate GEMM with the cell as its epilogue; step 0 contracts the frame
+            # with W_ih and leaves gx = x W_ih^T + b for the later steps, which contract h_{t-1} with W_hh and add gx
             c = torch.empty(n, H, device=dev, dtype=dt)
             act = torch.empty(n, 4 * H, device=dev, dtype=dt)
             more = t + 1 < steps
-            h_col_next = torch.empty(n, 3 * H, device=dev, dtype=dt) if more else None
-            h_row = h_rows[t] if more else None
+            h_pl_next = torch.empty(2, n, H, device=dev, dtype=dt) if more else None
+            hT = hT_all.data_ptr() + 4 * t * ldT if more else None
             if t == 0:
-                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, x_col.shape[1], N.ptr(x_col), N.ptr(wih_col), N.ptr(bias), 1,
+                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, x_pl.shape[2], N.ptr(x_pl), N.ptr(wih_pl), N.ptr(bias), 1,
                                                      None, N.ptr(gx), out[:, t].data_ptr(), steps * H, N.ptr(c),
-                                                     N.ptr(act), N.ptr(h_col_next), N.ptr(h_row), st))
+                                                     N.ptr(act), N.ptr(h_pl_next), hT, ldS, ldT, H * ldS, st))
             else:
-                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, 3 * H, N.ptr(h_col), N.ptr(whh_col), N.ptr(gx), 0,
+                N.check(lib.stove_lstm_gemm_cell_fwd(n, H, H, N.ptr(h_pl), N.ptr(whh_pl), N.ptr(gx), 0,
                                                      N.ptr(c_prev), None, out[:, t].data_ptr(), steps * H, N.ptr(c),
-                                                     N.ptr(act), N.ptr(h_col_next), N.ptr(h_row), st))
+                                                     N.ptr(act), N.ptr(h_pl_next), hT, ldS, ldT, H * ldS, st))
             acts.append(act)
             cs.append(c)
-            h_col, c_prev = h_col_next, c
-        ctx.stash = (x, wih_col, whh_row, acts, cs, h_rows, steps, H)
+            h_pl, c_prev = h_pl_next, c
+        ctx.stash = (x, whhT_pl, acts, cs, hT_all, steps, H)
         ctx.head = None
         if w1 is not None:
             w1, b1, w2, b2 = w1.contiguous(), b1.contiguous(), w2.contiguous(), b2.contiguous()
@@ -514,19 +440,19 @@ class LstmEncoder(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        x, wih_col, whh_row, acts, cs, h_rows, steps, H = ctx.stash
+        x, whhT_pl, acts, cs, hT_all, steps, H = ctx.stash
         g_out = g_out.contiguous()
         n = g_out.shape[0]
         dev, dt = g_out.device, g_out.dtype
         lib, st = N.lib(), N.stream()
         cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
-        x_row = None
+        xT_pl = None
         if ctx.needs_input_grad[1]:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                _, x_row = split_tf32_cat(x, None, 1)      # consumed by the W_ih gradient GEMM at the very end
-                x_row_ready = torch.cuda.Event()
-                x_row_ready.record(side)
+                _, xT_pl = split_planes(x, False, True)    # consumed by the W_ih gradient GEMM at the very end
+                xT_ready = torch.cuda.Event()
+                xT_ready.record(side)
         g_head = (None, None, None, None)
         if ctx.head is not None:
             hs, w1, w2, hidden = ctx.head
@@ -541,49 +467,55 @@ class LstmEncoder(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
                                       '(frames are data on the STOVE hot path)')
-        g_sum = torch.empty(n, 4 * H, device=dev, dtype=dt)          # gate gradients summed over the steps
-        # The library picks 128 x 64 / 128 x 128 tiles for these GEMMs: 64 CTAs for the hidden-state GEMM
-        # (n x H, K = 12H), 32 for the W_hh gradient, 64 for the W_ih gradient -- a fraction of the 148 SMs.
-        # Splitting K into `parts` batches of one strided-batched GEMM fills the machine; the partial products
-        # are summed by the consumer (the cell kernel) or by one small reduction.
-        g_rows = torch.empty(max(steps - 1, 0), 3 * n, 4 * H, device=dev, dtype=dt)   # steps 1 .. steps-1, stacked
-        g_row0 = torch.empty(3 * n, 4 * H, device=dev, dtype=dt)                      # split of the summed gradient
+        H4 = 4 * H
+        ldT = _round4(n)
+        ldS = max(steps - 1, 1) * ldT
+        g_acc = torch.empty(n, H4, device=dev, dtype=dt) if steps > 1 else None   # gate gradients summed over steps
+        gT_all = torch.empty(2, H4, ldS, device=dev, dtype=dt) if steps > 1 else None   # steps 1 .. steps-1, stacked
+        gsumT = torch.empty(2, H4, ldT, device=dev, dtype=dt)        # transposed planes of the summed gradient
+        bias_part = torch.empty((ldT + 31) // 32, H4, device=dev, dtype=dt)
         dh = g_c = None
         for t in reversed(range(steps)):
-            g_row = g_rows[t - 1] if t > 0 else g_row0
             g_c_prev = torch.empty(n, H, device=dev, dtype=dt) if t > 0 else None
-            # the cell kernel writes the gate gradient once, row-concatenated [hi ; hi ; lo] (3n x 4H): the same
-            # buffer serves the weight-gradient GEMM (contracted over its rows) and, viewed as three (n x 4H)
-            # blocks, the hidden-state GEMM below -- no second, column-concatenated copy (25 MB per step)
-            N.check(lib.stove_lstm_cell_bwd_x(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
-                                              N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
-                                              3, N.ptr(g_c), None, N.ptr(g_row), N.ptr(g_sum),
-                                              0 if t == steps - 1 else 1, 1 if t == 0 else 0, N.ptr(g_c_prev), st))
+            g_pl = torch.empty(2, n, H4, device=dev, dtype=dt) if t > 0 else None
             if t > 0:
-                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain.  One batch per
-                # 3xTF32 term (hi*hi, hi*lo, lo*hi) = split-K by 3: 192 CTAs; the next cell kernel sums the parts
-                dh = _bmm_tf32(g_row.view(3, n, 4 * H), whh_row.view(3, 4 * H, H))
+                gT, ld, plane = gT_all.data_ptr() + 4 * (t - 1) * ldT, ldS, H4 * ldS
+            else:
+                gT, ld, plane = gsumT.data_ptr(), ldT, H4 * ldT
+            # the cell kernel writes this step's gate gradient as (hi, lo) planes, row-major for the hidden-state
+            # GEMM below and transposed for the W_hh gradient; the last step processed (t = 0) emits the sum over
+            # the steps instead (what W_ih sees) and the per-block column sums for the bias gradient
+            N.check(lib.stove_lstm_cell_bwd_t(n, H, N.ptr(acts[t]), N.ptr(cs[t - 1]) if t > 0 else None,
+                                              N.ptr(cs[t]), g_out[:, t].data_ptr(), steps * H, N.ptr(dh),
+                                              dh.shape[0] if dh is not None else 0, N.ptr(g_c), N.ptr(g_pl), gT, ld,
+                                              ldT, plane, N.ptr(g_acc), 0 if t == steps - 1 else 1,
+                                              1 if t == 0 else 0, N.ptr(bias_part) if t == 0 else None,
+                                              N.ptr(g_c_prev), st))
+            if t > 0:
+                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain; split-K fills the
+                # machine and the next cell kernel sums the parts
+                dh = tc3_gemm(g_pl, whhT_pl, parts=_split_k(((n + 127) // 128) * ((H + 127) // 128), H4 // 32))
                 g_c = g_c_prev
         # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
-        # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands; it
-        # is issued after the chain's last hidden-state GEMM on purpose: started earlier it competes with the
-        # chain for L2 bandwidth (these GEMMs are operand-delivery bound) and the step gets slower.
+        # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands.
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             if steps > 1:
-                g_whh = _gemm_tn_splitk(g_rows.view(-1, 4 * H), h_rows.view(-1, H), 4)
+                tiles = (H4 // 128) * ((H + 127) // 128)
+                g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
             else:
-                g_whh = torch.zeros(4 * H, H, device=dev, dtype=dt)
-        for t_ in (g_rows, h_rows):
-            t_.record_stream(side)
+                g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
+            g_b = sum_parts(bias_part)
+        for t_ in (gT_all, hT_all, bias_part):
+            if t_ is not None:
+                t_.record_stream(side)
         g_wih = None
         if ctx.needs_input_grad[1]:
-            cur.wait_event(x_row_ready)
-            x_row.record_stream(cur)
-            g_wih = _gemm_tn_splitk(g_row0, x_row, 2)
-        # bias gradient (column sums of the summed gate gradient) behind the W_ih GEMM: the side stream's GEMM is
-        # the longer branch
-        g_b = g_sum.sum(0)
+            cur.wait_event(xT_ready)
+            xT_pl.record_stream(cur)
+            K = x.shape[1]
+            tiles = (H4 // 128) * ((K + 127) // 128)
+            g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
         cur.wait_stream(side)                      # every gradient is ready on the node's stream when it returns
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:

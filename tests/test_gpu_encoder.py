@@ -49,6 +49,25 @@ def test_lstm_encoder_vs_fp64(n, K, H, steps):
         assert _rel(p.grad, q.grad) < 2e-4
 
 
+@pytest.mark.parametrize('M,Nn,K,parts', [(256, 128, 64, 1), (1024, 1024, 2048, 2), (2048, 256, 1024, 4), (100, 36, 40, 1),
+                                          (1024, 2500, 300, 3)])
+def test_tc3_gemm_vs_fp64(M, Nn, K, parts):
+    """the 3xTF32 tcgen05 GEMM over (hi, lo) planes, split-K parts summed in a fixed order, and the transposed planes"""
+    from stove_b200 import ops
+    torch.manual_seed(M + K)
+    a, b = torch.randn(M, K, device='cuda'), torch.randn(Nn, K, device='cuda')
+    a_pl, aT_pl = ops.split_planes(a, True, True)
+    assert torch.equal(a_pl[0] + a_pl[1], a) and torch.equal(a_pl[0], (a.view(torch.int32) & -8192).view(torch.float32))
+    assert torch.equal(aT_pl[:, :, :M], a_pl.transpose(1, 2)) and not aT_pl[:, :, M:].any()
+    d = ops.sum_parts(ops.tc3_gemm(a_pl, ops.split_planes(b)[0], parts=parts))
+    ref = a.double() @ b.double().t()
+    assert _rel(d, ref) < 1e-5
+    if K % 4 == 0 and M % 4 == 0:
+        # contraction over the rows through the transposed planes (the weight-gradient form): a^T a
+        dt = ops.sum_parts(ops.tc3_gemm(ops.split_planes(a.t().contiguous())[0], aT_pl[:, :, :], parts=1))
+        assert _rel(dt, a.double().t() @ a.double()) < 1e-5
+
+
 @pytest.mark.parametrize('R,K,J,P', [(6144, 256, 50, 8), (7, 256, 50, 8), (100, 64, 20, 3), (33, 256, 64, 16)])
 def test_enc_head_vs_fp64(R, K, J, P):
     from stove_b200 import ops
