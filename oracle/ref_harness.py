@@ -1,8 +1,8 @@
 """ORACLE (test infrastructure only): run the *unmodified* reference from /root/reference.
 
-Only usable in the build container (the reference is not on the GPU box); used by
-`oracle/make_golden.py` and by `tests/test_oracle_vs_reference.py` (skipped when the
-reference is absent).  Shims are those of SURVEY.md appendix B: hand-built config,
+Reads /root/reference in the build container, or the staged copy oracle/_ref/ (oracle/build_ref.py;
+git-ignored, shipped by gpurun) on the GPU box; used by `oracle/make_golden.py`,
+`tests/test_oracle_vs_reference.py` (skipped when neither is there) and the reference arm of `bench.py`.  Shims are those of SURVEY.md appendix B: hand-built config,
 distribution argument validation off (torch-1.0.1 behaviour), no `model.main` import.
 """
 import contextlib
@@ -12,7 +12,15 @@ import warnings
 
 import torch
 
-REFERENCE_ROOT = '/root/reference'
+def _find_root():
+    """/root/reference in the build container; the staged copy oracle/_ref (oracle/build_ref.py) on the GPU box"""
+    for root in ('/root/reference', os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')):
+        if os.path.isdir(os.path.join(root, 'model', 'video_prediction')):
+            return root
+    return '/root/reference'
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

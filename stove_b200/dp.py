@@ -22,21 +22,31 @@ def rank():
 
 
 def shard(t, dim=0):
-    """This rank's contiguous slice of a tensor along `dim` (batch-sharding rule)."""
+    """This rank's contiguous slice of a tensor along `dim` (batch-sharding rule).  The batch must divide
+    evenly: the gradient exchange averages per-rank MEAN gradients with equal weights, which equals the
+    single-process full-batch gradient only for equal shards."""
     w, r = world(), rank()
     n = t.shape[dim]
-    lo, hi = (n * r) // w, (n * (r + 1)) // w
-    return t.narrow(dim, lo, hi - lo)
+    if n % w:
+        raise ValueError('batch of %d does not divide over %d ranks' % (n, w))
+    return t.narrow(dim, (n // w) * r, n // w)
 
 
 class DataParallel:
     """Minimal DP engine around a `Stove` replica: zero_grad -> forward -> backward ->
     flat-bucket all-reduce (-> clip -> optimizer step)."""
 
-    def __init__(self, model, reward_factor=0.0, broadcast=True):
+    def __init__(self, model, reward_factor=None, broadcast=True, mse=None):
+        """reward_factor / mse default to the model config's debug_reward_factor / debug_mse (train.py:205-208,
+        :463).  The ramp-up weight min(1, step / debug_reward_rampup) (train.py:458-462) is a DEVICE scalar,
+        `self.reward_weight`, refreshed by `set_reward_weight(step)` so that a captured graph replays it."""
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.reward_factor = reward_factor
+        c = getattr(model, 'c', None)
+        self.reward_factor = getattr(c, 'debug_reward_factor', 0.0) if reward_factor is None else reward_factor
+        self.mse = bool(getattr(c, 'debug_mse', False)) if mse is None else mse
+        self.rampup = getattr(c, 'debug_reward_rampup', False)
+        self.reward_weight = None
         self.flat = None
         self.live = None
         if broadcast and world() > 1:
@@ -49,7 +59,12 @@ class DataParallel:
             p.grad = None
         elbo, prop, rewards = self.model(x, step_counter, actions=actions)
         if reward_target is not None and self.reward_factor:
-            loss = -elbo + self.reward_factor * torch.nn.functional.binary_cross_entropy(rewards, reward_target)
+            # train.py:452-465: reward_target = present_rewards[:, skip:] (the caller slices), both flattened
+            fn = torch.nn.functional.mse_loss if self.mse else torch.nn.functional.binary_cross_entropy
+            reward_loss = fn(rewards.flatten(), reward_target.flatten())
+            if self.reward_weight is None:
+                self.set_reward_weight(step_counter, device=rewards.device)
+            loss = -elbo + (self.reward_factor * self.reward_weight) * reward_loss
             loss.backward()
             loss = loss.detach()
         else:
@@ -59,6 +74,15 @@ class DataParallel:
             loss = -elbo.detach()
         self.all_reduce_gradients()
         return loss
+
+    def set_reward_weight(self, step_counter, device=None):
+        """min(1, step / debug_reward_rampup) (1 when the ramp-up is off) into the device scalar the loss reads."""
+        w = 1.0 if self.rampup is False or not self.rampup else min(1.0, step_counter / self.rampup)
+        if self.reward_weight is None:
+            self.reward_weight = torch.full((), w, device=device, dtype=torch.float32)
+        else:
+            self.reward_weight.fill_(w)
+        return w
 
     def _minus_one(self, like):
         key = (like.device, like.dtype)
@@ -112,6 +136,11 @@ class GraphedStep:
     no host synchronisation (the reference's matcher has one per time step, stove.py:271-273).
     Inputs are copied into static buffers; `loss` and every `p.grad` live at fixed addresses.
 
+    Logging steps: the graph is captured with step_counter = 1, so `prop_dict` is NOT refreshed by replays;
+    a trainer that reads `prop_dict` every `print_every` steps runs those steps eagerly
+    (`engine.forward_backward(x, step)` / `engine.train_step`), which shares parameters and optimizer state
+    with the graph.  With a reward loss call `engine.set_reward_weight(step)` before a replay (device scalar).
+
     Construct it before running eager backward passes of the same model on the default stream (or drop
     their autograd graphs first): PyTorch binds each parameter's gradient accumulation to the stream of the
     first autograd forward pass that used it, and the legacy default stream cannot take part in a capture
@@ -122,6 +151,9 @@ class GraphedStep:
                  optimizer=None):
         """`optimizer` (a `stove_b200.optim.FusedAdam`): also capture the clip + Adam step, i.e. replay one
         whole training iteration; its step counter and learning rate are device scalars."""
+        if optimizer is not None and warmup < 1:
+            raise ValueError('GraphedStep with an optimizer needs warmup >= 1 (the optimizer state binds to the '
+                             'gradient bucket of an eager pass)')
         self.engine = engine
         self.optimizer = optimizer
         self.x = example_x.clone()

@@ -342,6 +342,10 @@ class RatSpn(nn.Module):
         dev = self.output_vector.params.device
         t.to(dev)
         a = self.args
+        if a.gauss_min_sigma >= a.gauss_max_sigma or a.gauss_min_mean is not None or a.gauss_max_mean is not None:
+            # rat_torch.py:83-96 of the reference: constant sigma = 1 / sigmoid-bounded means; not on the hot path
+            raise NotImplementedError('stove_b200.RatSpn: the fused leaf kernels need gauss_min_sigma < gauss_max_sigma '
+                                      'and unbounded means (gauss_min_mean = gauss_max_mean = None)')
         means = torch.cat([v.means for v in t.leaf_order], 0)
         sigma = torch.cat([v.sigma_params for v in t.leaf_order], 0)
         leaf = ops.PackLeaf.apply(means, sigma, t.dev['dst_row'], t.GP, t.prow_total,

@@ -46,6 +46,10 @@ class Stove(nn.Module):
             self.match_objects = self._greedy_match_objects
         else:
             raise ValueError('Specify valid self.c.debug_match_ojects.')
+        if self.c.debug_no_latents or self.c.debug_no_velocity:
+            # the fused dynamics loop (csrc/dynloop.cu) implements the default state fusion of stove.py:103-170 only
+            raise NotImplementedError('stove_b200: debug_no_latents / debug_no_velocity (thesis ablations of '
+                                      'Stove.full_state) are not implemented by the fused dynamics-loop kernels')
 
     def _sup_cfg(self, T):
         from .. import _native as N
