@@ -2,21 +2,30 @@
 """Benchmark of the STOVE hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W          # this framework on N B200s
-    python bench.py --impl reference --steps K --warmup W  # the reference algorithm on host CPU cores
+    python bench.py --impl reference --steps K --warmup W  # the reference's own code on the host CPU cores
 
-Headline metric: training sequences/s of the sequence-ELBO forward+backward on BASELINE
-config 1 (billiards, 3 balls, 32x32, 8-frame window, batch 256 per GPU; optimizer excluded,
-gradient all-reduce included when N > 1; weak scaling).  One JSON line is printed by rank 0.
-Extra keys report the rollout workloads of the same metric family (video prediction:
-8-frame inference + 92-frame rollout; MCTS-style long rollouts: 1024 x 2000 frames).
+Headline metric: training sequences/s of the sequence-ELBO forward+backward on BASELINE config 1
+(billiards, 3 balls, 32x32, 8-frame window, batch 256 per GPU; optimizer excluded, gradient all-reduce
+included when N > 1; weak scaling).  One JSON line is printed by rank 0.  Extra keys carry every other
+BASELINE config as stated (each with `value`, `roofline` and, at N = 1, `cpu_baseline`):
+  video_prediction        cfg 2: 8-frame inference + 92-frame rollout, n = 1024 per GPU at 32x32 (+ `variants`:
+                          n = 300 at 32x32 and at the reference's 50x50)
+  train_ac                cfg 3: action-conditioned world model with appearance + reward head, batch 512 per GPU,
+                          loss = -ELBO + 15000 * rampup * BCE(reward) (train.py:452-465)
+  train_multiball         cfg 4: 6 and 9 objects at 50x50, greedy matching, batch 256 per GPU
+  rollout_long            cfg 5, weak: 1024 sequences x 2000 frames per GPU
+  rollout_long_sharded    cfg 5 as stated: 1024 sequences in total, sharded over the N GPUs
+  train_strong            (N > 1) config 1 with the GLOBAL batch fixed at 256 (strong scaling)
+  train_step_with_optimizer   config 1 + clip_grad_norm + Adam(amsgrad) in the same graph
 
-Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on
-both sides, max over ranks.  Inputs rotate through a device-resident pool of batches that
-is larger than L2 (8 x 25 MB > 126 MB), so no step finds its frames in L2.  `e2e` repeats the
-measurement through the public module call with pinned HOST batches (H2D copy of the frames and
-D2H read of the loss inside the timed region).  `roofline` comes from a second pass of K steps
-with per-kernel CUDA events (stove_profile_*); `cpu_baseline` times the oracle port of the
-reference algorithm on the host cores (rank 0, N = 1 only).
+Timing: CUDA events around exactly K steps after W warm-up steps, barrier + synchronize on both sides, max
+over ranks; the K-step region is repeated until at least ~0.5 s has been measured and the MEDIAN region is
+reported (a 15 ms region is at the mercy of one scheduling hiccup).  Inputs rotate through a device-resident
+pool of batches larger than L2, so no step finds its frames in L2.  `e2e` repeats the measurement through the
+public module call with pinned HOST batches (H2D copy of the frames and D2H read of the loss inside the timed
+region).  `roofline` comes from a further pass of K steps with per-kernel CUDA events (stove_profile_*);
+`cpu_baseline` times the reference's stock code (oracle/_ref, staged by oracle/build_ref.py) -- or the oracle
+port when that copy is absent -- on the host cores (rank 0, N = 1 only), on a bounded sample.
 """
 import argparse
 import json
@@ -34,13 +43,22 @@ sys.path.insert(0, ROOT)
 BATCH, T, O, RES = 256, 8, 3, 32
 POOL = 8                      # device-resident batches: 8 x 25.2 MB > 126 MB L2
 WORKLOAD = 'STOVE billiards, 3 balls, 32x32 frames, 8-frame window, fwd+bwd ELBO, batch 256 per GPU'
+MIN_REGION_S = 0.5            # repeat the K-step region until this much device time has been measured
+
+VARIANT_KW = {
+    'plain': {},
+    'ac': dict(action_conditioned=True, action_space=9, debug_core_appearance=True),
+    'o6': dict(num_obj=6, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0, max_obj_scale=0.22),
+    'o9': dict(num_obj=9, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0, max_obj_scale=0.22),
+    'g50': dict(width=50, height=50),
+}
 
 
 # ----------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
               'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -53,7 +71,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.FIELDS,
-                 '--format=csv,noheader,nounits', '-lms', '200'],
+                 '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -82,35 +100,52 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def measured_peaks():
+def peaks():
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) + the micro-benchmarks of this repo
+    (profiles/r02_microbench.json: FP32 FMA and tcgen05 TF32 peaks measured on the box), else stated fallbacks."""
+    out = {'hbm_gbs': 6650.0, 'hbm_src': 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)',
+           'tf32_tflops': 1590.0 / 2, 'tf32_src': 'fallback: 1.59 PFLOP/s bf16 / 2',
+           'fp32_tflops': 148 * 128 * 2 * 1.965e9 / 1e12, 'fp32_src': 'derived: 148 SMs x 128 lanes x 2 x 1.965 GHz'}
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return p['hbm_gbs'], 'MEASURED_PEAKS.json (measured copy bandwidth)'
-    return 6650.0, 'fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+        out.update(hbm_gbs=p['hbm_gbs'], hbm_src='MEASURED_PEAKS.json (measured copy bandwidth)')
+        if 'bf16_tflops' in p:
+            out.update(tf32_tflops=p['bf16_tflops'] / 2, tf32_src='MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)')
+    path = os.path.join(ROOT, 'profiles', 'r02_microbench.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            m = json.load(f)
+        if m.get('fp32_fma_tflops'):
+            out.update(fp32_tflops=m['fp32_fma_tflops'], fp32_src='profiles/r02_microbench.json (FFMA micro-benchmark on a B200 of this pool)')
+        if m.get('tcgen05_tf32_tflops'):
+            out.update(tf32_mma_tflops=m['tcgen05_tf32_tflops'])
+    return out
 
 
-def make_frames(n, seed):
+def make_frames(n, seed, num_obj=O, res=RES, gravity=False, frames=T):
     from stove_b200 import synth
-    return synth.billiards(n, T, O, res=RES, seed=seed)['x']
+    return synth.billiards(n, frames, num_obj, res=res, seed=seed, gravity=gravity,
+                           radius=1.2 if num_obj <= 3 else 1.0)['x']
+
+
+def build_variant(variant, device, seed=0):
+    from stove_b200 import Stove, StoveConfig
+    torch.manual_seed(seed)
+    kw = dict(width=RES, height=RES, num_obj=O, action_conditioned=False, action_space=None, random_seed=7,
+              device=device)
+    kw.update(VARIANT_KW[variant])
+    return Stove(StoveConfig(**kw)).to(device)
 
 
 def build_model(device):
-    from stove_b200 import Stove, StoveConfig
-    torch.manual_seed(0)
-    cfg = StoveConfig(width=RES, height=RES, num_obj=O, action_conditioned=False, action_space=None,
-                      random_seed=7, device=device)
-    return Stove(cfg).to(device)
+    return build_variant('plain', device)
 
 
 def build_ac_model(device):
-    from stove_b200 import Stove, StoveConfig
-    torch.manual_seed(2)              # a seed whose random-init rollout stays finite (SURVEY hard part 13)
-    cfg = StoveConfig(width=RES, height=RES, num_obj=O, action_conditioned=True, action_space=9,
-                      debug_core_appearance=True, random_seed=7, device=device)
-    m = Stove(cfg).to(device)
-    with torch.no_grad():             # tame exp(attention) of the untrained net
+    m = build_variant('ac', device, seed=2)     # a seed whose random-init rollout stays finite (SURVEY hard part 13)
+    with torch.no_grad():                        # tame exp(attention) of the untrained net (stated in config)
         for core in m.dyn.att_net:
             for lin in core:
                 lin.weight.mul_(0.5)
@@ -133,157 +168,333 @@ def dist_setup(n_gpus):
     return world, int(os.environ.get('RANK', '0')), local
 
 
-def timed(fn, steps, warmup, world, on_start=None):
-    """W warm-up + exactly K timed calls of fn(i); device time, max over ranks (ms total)."""
+def timed(fn, steps, warmup, world, on_start=None, min_seconds=MIN_REGION_S, max_repeats=200):
+    """W warm-up calls, then regions of exactly K timed calls of fn(i), each bracketed by barrier + synchronize;
+    device time, max over ranks per region; regions repeat until `min_seconds` are covered.
+    -> (median region ms, number of regions)."""
     import torch.distributed as dist
     for i in range(warmup):
         fn(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    if on_start is not None:
-        on_start()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(steps):
-        fn(warmup + i)
-    b.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([a.elapsed_time(b)], device='cuda')
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms)
+    regions, at, total = [], warmup, 0.0
+    while True:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if on_start is not None and not regions:
+            on_start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(at + i)
+        b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device='cuda')
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)      # every rank sees the same number -> the same loop count
+        regions.append(float(ms))
+        total += regions[-1] * 1e-3
+        at += steps
+        if total >= min_seconds or len(regions) >= max_repeats:
+            break
+    regions.sort()
+    return regions[len(regions) // 2], len(regions)
 
 
 # ----------------------------------------------------------------------------------------
-# CPU baseline = oracle port of the reference algorithm (oracle/stove_oracle.py)
+# CPU baseline: the reference's own code (oracle/_ref) or the oracle port
 # ----------------------------------------------------------------------------------------
-def cpu_train_baseline(steps, warmup, state_dict, frames, threads=None):
-    """fwd+bwd ELBO of the reference algorithm on the host cores, fp32, full batch-256 steps."""
+def _oracle_config(variant):
+    from oracle import stove_oracle as so
+    return so.default_config(**VARIANT_KW[variant])
+
+
+def reference_available():
+    from oracle import ref_harness as rh
+    return rh.available()
+
+
+def cpu_train(variant, state_dict, x, actions=None, reward_target=None, steps=3, warmup=1, threads=None,
+              dtype=torch.float32, reward_factor=15000.0, reward_weight=1.0 / 20000):
+    """fwd+bwd of the training loss on the host cores.  -> dict(value seq/s, kind, cores, ms_per_step)."""
+    from oracle import ref_harness as rh
     from oracle import stove_oracle as so
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    oc = so.default_config()
-    structs = so.structures(oc)
-    P = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in state_dict.items()
-         if 'output_vector' not in k}
-    gen = torch.Generator().manual_seed(0)
+    oc = _oracle_config(variant)
+    n = x.shape[0]
+    x = x.to(dtype)
+    actions = actions.to(dtype) if actions is not None else None
+    reward_target = reward_target.to(dtype) if reward_target is not None else None
     times = []
-    for i in range(warmup + steps):
-        x = frames[i % len(frames)]
-        noise = [torch.randn(BATCH, O, 12, 1, generator=gen) for _ in range(2)] + \
-                [torch.randn(BATCH, O, 18, generator=gen) for _ in range(T - 2)]
-        for p in P.values():
-            p.grad = None
-        t0 = time.perf_counter()
-        elbo, _, _ = so.stove_forward(oc, P, x, noise, structs=structs)
-        (-elbo).backward()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return BATCH * len(times) / sum(times), threads, sum(times) / len(times)
+    if rh.available():
+        kind = 'reference'
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        ref = rh.build_reference(oc, sd, dtype)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            with rh.default_dtype(dtype), rh.quiet():
+                ref.zero_grad()
+                elbo, _, rewards = ref(x, 1, actions=actions)
+                loss = -elbo
+                if reward_target is not None:      # train.py:452-465
+                    loss = loss + reward_factor * reward_weight * torch.nn.functional.binary_cross_entropy(
+                        rewards.flatten(), reward_target.flatten())
+                loss.backward()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = 'port'
+        structs = so.structures(oc)
+        P = {k: v.detach().to(dtype).cpu().clone().requires_grad_(True) for k, v in state_dict.items()
+             if 'output_vector' not in k}
+        gen = torch.Generator().manual_seed(0)
+        Ov, Tv = oc.num_obj, x.shape[1]
+        for i in range(warmup + steps):
+            noise = [torch.randn(n, Ov, 12, 1, generator=gen).to(dtype) for _ in range(2)] + \
+                    [torch.randn(n, Ov, 18, generator=gen).to(dtype) for _ in range(Tv - 2)]
+            for p in P.values():
+                p.grad = None
+            t0 = time.perf_counter()
+            elbo, _, rewards = so.stove_forward(oc, P, x, noise, actions=actions, structs=structs)
+            loss = -elbo
+            if reward_target is not None:
+                loss = loss + reward_factor * reward_weight * torch.nn.functional.binary_cross_entropy(
+                    rewards.flatten(), reward_target.flatten())
+            loss.backward()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {'value': n / sec, 'unit': 'sequences/s', 'cores': threads, 'kind': kind,
+            'dtype': str(dtype).replace('torch.', ''), 'ms_per_step': sec * 1e3,
+            'sample': '%d fwd+bwd steps of batch %d (after %d warm-up) of %s, torch CPU' % (
+                steps, n, warmup, 'the stock reference code (oracle/_ref)' if kind == 'reference' else 'the oracle port')}
 
 
-def cpu_rollout_baseline(state_dict, z_last, actions, app, num, threads=None):
+def cpu_predict(variant, state_dict, x, num, threads=None, dtype=torch.float32):
+    """8-frame inference + `num`-frame rollout under no_grad on the host cores -> frames/s dict."""
+    from oracle import ref_harness as rh
     from oracle import stove_oracle as so
-    torch.set_num_threads(threads or os.cpu_count())
-    oc = so.default_config(action_conditioned=True, action_space=9, debug_core_appearance=True)
-    P = {k: v.detach().float().cpu() for k, v in state_dict.items()}
-    with torch.no_grad():
-        so.rollout(oc, P, z_last[:64], 2, actions[:64], app[:64])
-        t0 = time.perf_counter()
-        so.rollout(oc, P, z_last, num, actions, app)
-        dt = time.perf_counter() - t0
-    return z_last.shape[0] * num / dt
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    oc = _oracle_config(variant)
+    n, Tv = x.shape[0], x.shape[1]
+    x = x.to(dtype)
+    if rh.available():
+        kind = 'reference'
+        ref = rh.build_reference(oc, {k: v.detach().cpu() for k, v in state_dict.items()}, dtype)
+        with torch.no_grad(), rh.default_dtype(dtype), rh.quiet():
+            ref(x[:8], 0)
+            t0 = time.perf_counter()
+            _, prop, _ = ref(x, 0)
+            ref.rollout(prop['z'][:, -1], num=num)
+            dt = time.perf_counter() - t0
+    else:
+        kind = 'port'
+        P = {k: v.detach().to(dtype).cpu() for k, v in state_dict.items()}
+        gen = torch.Generator().manual_seed(0)
+        noise = [torch.randn(n, oc.num_obj, 12, 1, generator=gen).to(dtype) for _ in range(2)] + \
+                [torch.randn(n, oc.num_obj, 18, generator=gen).to(dtype) for _ in range(Tv - 2)]
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            _, prop, _ = so.stove_forward(oc, P, x, noise)
+            so.rollout(oc, P, prop['z'][:, -1], num=num)
+            dt = time.perf_counter() - t0
+    return {'value': n * (Tv + num) / dt, 'unit': 'frames/s', 'cores': threads, 'kind': kind,
+            'dtype': str(dtype).replace('torch.', ''),
+            'sample': 'one call on %d sequences (%d-frame inference + %d-frame rollout), torch CPU' % (n, Tv, num)}
+
+
+def cpu_rollout(state_dict, z_last, actions, app, num, threads=None):
+    from oracle import ref_harness as rh
+    from oracle import stove_oracle as so
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    oc = _oracle_config('ac')
+    n = z_last.shape[0]
+    if rh.available():
+        kind = 'reference'
+        ref = rh.build_reference(oc, {k: v.detach().cpu() for k, v in state_dict.items()}, torch.float32)
+        with torch.no_grad(), rh.default_dtype(torch.float32), rh.quiet():
+            ref.rollout(z_last[:64], num=2, actions=actions[:64], appearance=app[:64])
+            t0 = time.perf_counter()
+            ref.rollout(z_last, num=num, actions=actions, appearance=app)
+            dt = time.perf_counter() - t0
+    else:
+        kind = 'port'
+        P = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+        with torch.no_grad():
+            so.rollout(oc, P, z_last[:64], 2, actions[:64], app[:64])
+            t0 = time.perf_counter()
+            so.rollout(oc, P, z_last, num, actions, app)
+            dt = time.perf_counter() - t0
+    return {'value': n * num / dt, 'unit': 'sequence-frames/s', 'cores': threads, 'kind': kind, 'dtype': 'float32',
+            'sample': '%d sequences x %d steps' % (n, num)}
 
 
 # ----------------------------------------------------------------------------------------
-# arms
+# reference arm
 # ----------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's own algorithm on the host CPU (oracle port; the reference is pure Python
-    and is not on the GPU box).  Rank 0 only."""
+    """The reference's own CPU implementation of the path on the host cores: the stock `Stove.forward` +
+    backward from oracle/_ref (staged copy of /root/reference, oracle/build_ref.py), else the oracle port.
+    fp32 is the headline (like for like with the fp32 build); the reference's default fp64 (config.py:58) and
+    its default 8 threads (config.py:59) are timed beside it.  Rank 0 only."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
     model = build_model('cpu')
-    frames = [make_frames(BATCH, 100 + i) for i in range(2)]
-    value, threads, sec = cpu_train_baseline(args.steps, args.warmup, model.state_dict(), frames)
+    frames = make_frames(BATCH, 100)
+    sd = model.state_dict()
+    main = cpu_train('plain', sd, frames, steps=args.steps, warmup=args.warmup)
+    extra = {}
+    try:
+        extra['fp64_all_cores'] = cpu_train('plain', sd, frames, steps=max(2, args.steps // 5), warmup=1, dtype=torch.float64)
+        extra['fp32_8_threads'] = cpu_train('plain', sd, frames, steps=max(2, args.steps // 5), warmup=1, threads=8)
+    except Exception as e:                       # noqa: BLE001 -- the headline number stands on its own
+        extra['error'] = repr(e)
     line = {
-        'impl': 'reference', 'metric': 'train_seqs_per_sec', 'value': value, 'unit': 'sequences/s',
-        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'impl': 'reference', 'metric': 'train_seqs_per_sec', 'value': main['value'], 'unit': 'sequences/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': main['ms_per_step'],
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_step': BATCH},
-        'cpu_baseline': {'value': value, 'unit': 'sequences/s', 'cores': threads, 'kind': 'port',
-                         'sample': '%d full batch-256 fwd+bwd steps of the oracle port (torch CPU, fp32)' % args.steps},
-        'e2e': {'value': value, 'unit': 'sequences/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
+        'config': {'workload': WORKLOAD, 'global_batch': BATCH, 'parallelism': 'cpu',
+                   'step': 'one full batch-256 fwd+bwd of the ELBO (zero_grad included, optimizer excluded)'},
+        'cpu_baseline': main,
+        'e2e': {'value': main['value'], 'unit': 'sequences/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0, 'other_settings': extra,
     }
     emit(line)
+
+
+# ----------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------
+class TrainBench:
+    """One training workload: model + DP engine + graphed step over a rotating device pool."""
+
+    def __init__(self, model, batches, world, graph=True, optimizer=False):
+        from stove_b200 import dp
+        self.model, self.world = model, world
+        self.engine = dp.DataParallel(model)
+        self.batches = batches                      # list of tuples (x, actions | None, reward_target | None) on the device
+        x, a, r = batches[0]
+        self.opt = None
+        if optimizer:
+            from stove_b200.optim import FusedAdam
+            self.opt = FusedAdam(model.parameters(), lr=2e-3, amsgrad=True, max_norm=1.0)
+        self.graphed = dp.GraphedStep(self.engine, x, a, r, optimizer=self.opt) if graph else None
+        self.losses = []
+
+    def step(self, i):
+        x, a, r = self.batches[i % len(self.batches)]
+        if self.graphed is not None:
+            loss = self.graphed(x, a, r)
+        elif self.opt is not None:
+            loss = self.engine.train_step(self.opt, x, 1, a, r)
+        else:
+            loss = self.engine.forward_backward(x, 1, a, r)
+        self.losses.append(loss)
+        return loss
+
+    def measure(self, steps, warmup, on_start=None):
+        ms, reps = timed(self.step, steps, warmup, self.world, on_start=on_start)
+        n = self.batches[0][0].shape[0]
+        finite = bool(torch.isfinite(torch.stack([l.detach().float() for l in self.losses[-3:]])).all().item())
+        self.losses = []
+        return {'value': self.world * n * steps / (ms * 1e-3), 'unit': 'sequences/s', 'ms_per_step': ms / steps,
+                'regions': reps, 'loss_finite': finite, 'batch_per_gpu': n}
+
+
+def train_roofline(value_per_gpu, flop_per_seq, bytes_per_seq, pk):
+    """Whole-step view: useful fp32-equivalent FLOPs and algorithmic HBM bytes per sequence."""
+    return {'bound': 'fp32', 'achieved_tflops': value_per_gpu * flop_per_seq / 1e12, 'peak_tflops': pk['fp32_tflops'],
+            'frac': value_per_gpu * flop_per_seq / 1e12 / pk['fp32_tflops'], 'peak_source': pk['fp32_src'],
+            'hbm': {'achieved_gbs': value_per_gpu * bytes_per_seq / 1e9, 'peak_gbs': pk['hbm_gbs'],
+                    'frac': value_per_gpu * bytes_per_seq / 1e9 / pk['hbm_gbs']},
+            'note': 'per GPU, whole step: %.1f MFLOP (fwd+bwd, fp32-equivalent) and %.0f KB algorithmic bytes per sequence'
+                    % (flop_per_seq / 1e6, bytes_per_seq / 1e3)}
+
+
+def step_flops(num_obj, res, frames=T, ac=False):
+    """Useful fwd FLOPs per sequence: encoder + dynamics + scene likelihood; fwd+bwd = 3x."""
+    K, H = res * res, 256
+    enc = 2.0 * frames * (K * 4 * H + (num_obj - 1) * H * 4 * H + num_obj * (H * 50 + 50 * 8))
+    pair, obj = 13472, 8704 + (7 * 32 if ac else 0)
+    dyn = 2.0 * (frames - 2) * (num_obj * num_obj * pair + num_obj * obj)
+    scene = (frames - 1 + 1) * (num_obj * (70e3 + 14e3) + 18.0 * K * 5 + 108 * 3)
+    return enc + dyn + scene
 
 
 def run_b200(args):
     import torch.distributed as dist
     from stove_b200 import _native as N
-    from stove_b200 import dp
+    from stove_b200 import dp, synth
     world, rank, local = dist_setup(args.gpus)
     dev = torch.device('cuda', local if world > 1 else 0)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    model = build_model(dev)
-    engine = dp.DataParallel(model)
     lib = N.lib()
+    pk = peaks()
+    graph = not args.no_graph
 
-    # ---- training: device-resident pool (value) -------------------------------------------
-    host_pool = [make_frames(BATCH, 1000 * rank + i).pin_memory() for i in range(POOL)]
-    dev_pool = [h.to(dev) for h in host_pool]
-    losses = []
-    graphed = None
-    if not args.no_graph:
-        graphed = dp.GraphedStep(engine, dev_pool[0])
+    # ---- config 1: training, device-resident pool (value) ---------------------------------
+    model = build_model(dev)
+    host_pool = [make_frames(BATCH, 1000 * rank + i) for i in range(POOL)]
+    # end-to-end inputs: uint8 RGB frames in pinned host memory (what a video loader holds); the device converts
+    # them in bw_transform (x / 255).  The fp32-host-frame figure is reported beside it.
+    host_u8 = [(h * 255).round().to(torch.uint8).pin_memory() for h in host_pool]
+    host_f32 = [h.pin_memory() for h in host_pool]
+    dev_pool = [(h.to(dev), None, None) for h in host_pool]
+    main = TrainBench(model, dev_pool, world, graph=graph)
+    engine, graphed = main.engine, main.graphed
 
-    def run_step(x):
-        return graphed(x) if graphed is not None else engine.forward_backward(x, step_counter=1)
+    def make_e2e(hosts, example):
+        g = dp.GraphedStep(engine, example) if graph else None
+        prefetch = dp.HostPrefetcher(lambda i: hosts[i % POOL], dev)
+        sink = []
 
-    def step_resident(i):
-        losses.append(run_step(dev_pool[i % POOL]))
-
-    prefetch = dp.HostPrefetcher(lambda i: host_pool[i % POOL], dev)
-
-    def step_e2e(i):
-        # public call with HOST frames: every step copies its batch from pinned host memory (the copy
-        # of step i+1 overlaps the compute of step i on a side stream) and reads its loss back (D2H)
-        x = prefetch.get(i)
-        if graphed is not None:
-            prefetch.release(i, graphed.load(x))
-            loss = graphed.run()
-        else:
-            loss = engine.forward_backward(x, step_counter=1)
-        prefetch.prefetch(i + 1)
-        losses.append(loss.item())
+        def step_e2e(i):
+            # public call with HOST frames: every step copies its batch from pinned host memory (the copy of step
+            # i+1 overlaps the compute of step i on a side stream) and reads its loss back (D2H)
+            x = prefetch.get(i)
+            if g is not None:
+                prefetch.release(i, g.load(x))
+                loss = g.run()
+            else:
+                loss = engine.forward_backward(x, step_counter=1)
+            prefetch.prefetch(i + 1)
+            sink.append(loss.item())
+        return step_e2e, g, sink
 
     with ClockSampler(dev.index or 0) as clocks:
-        ms = timed(step_resident, args.steps, args.warmup, world, on_start=lambda: lib.stove_launch_count(1))
+        res_main = main.measure(args.steps, args.warmup, on_start=lambda: lib.stove_launch_count(1))
         launches = lib.stove_launch_count(1)
         if graphed is not None:       # replays launch the captured kernels without passing the counter
             launches = graphed.native_launches * args.steps
-        ms_e2e = timed(step_e2e, args.steps, args.warmup, world)
+        e2e_fn, e2e_graph, e2e_losses = make_e2e(host_u8, host_u8[0].to(dev))
+        ms_e2e, _ = timed(e2e_fn, args.steps, args.warmup, world)
+        del e2e_graph
+        e2e32_fn, e2e32_graph, _ = make_e2e(host_f32, host_f32[0].to(dev))
+        ms_e2e32, _ = timed(e2e32_fn, args.steps, args.warmup, world)
+        del e2e32_graph
     clock_summary = clocks.summary()
-    value = world * BATCH * args.steps / (ms * 1e-3)
+    value = res_main['value']
+    ms_step = res_main['ms_per_step']
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
 
-    # ---- per-kernel pass (roofline) ----------------------------------------------------------
+    # ---- per-kernel pass (roofline of the dominant kernel) ---------------------------------------
     def step_eager(i):
-        engine.forward_backward(dev_pool[i % POOL], step_counter=1)
+        engine.forward_backward(dev_pool[i % POOL][0], step_counter=1)
 
-    # per-kernel times are taken with the side streams / library forks switched off (STOVE_NO_FORK):
-    # overlapped kernels would each be charged the time they spend waiting for SMs
-    os.environ['STOVE_NO_FORK'] = '1'
+    # per-kernel times are taken with the side streams / library forks switched off: overlapped kernels
+    # would each be charged the time they spend waiting for SMs
+    from stove_b200 import ops
+    ops.set_fork(False)
     lib.stove_profile_enable(1)
     N.profile_read()
-    timed(step_eager, args.steps, 1, world)      # events cannot be read back from a captured graph
+    timed(step_eager, args.steps, 1, world, min_seconds=0.0)      # events cannot be read back from a captured graph
     lib.stove_profile_enable(0)
-    os.environ.pop('STOVE_NO_FORK', None)
+    ops.set_fork(True)
     recs = N.profile_read()
     per = {}
     for name, t in recs:
@@ -291,113 +502,183 @@ def run_b200(args):
     n_steps_prof = args.steps + 1
     share = {k: sum(v) / n_steps_prof for k, v in per.items()}           # ms per step per kernel
     top = max(share, key=share.get) if share else None
-    peak, peak_src = measured_peaks()
     roofline = None
     if top is not None:
-        launches_top = len(per[top]) / n_steps_prof
-        avg_ms = sum(per[top]) / len(per[top])
-        units = kernel_algorithmic_bytes(top, BATCH)
-        achieved = units / (avg_ms * 1e-3) / 1e9 if units else None
-        flops = kernel_flops(top, BATCH)
-        sm_mhz = clock_summary.get('sm_max_mhz') or 1965.0
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        fp32 = None
-        if flops:
-            fp32 = {'achieved_tflops': flops / (avg_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
-                    'frac': flops / (avg_ms * 1e-3) / 1e12 / fp32_peak,
-                    'peak_source': '148 SMs x 128 FP32 lanes x 2 x max SM clock'}
-        tensor = None
-        tflops = kernel_tensor_flops(top, BATCH)
-        if tflops:
-            # executed TF32 tensor-core FLOPs (3 x the fp32-equivalent product: hi*hi + hi*lo + lo*hi); the TF32
-            # dense peak is half the measured bf16 one
-            tpeak, tsrc = measured_tensor_peak()
-            tensor = {'achieved_tflops': tflops / (avg_ms * 1e-3) / 1e12, 'peak_tflops': tpeak,
-                      'frac': tflops / (avg_ms * 1e-3) / 1e12 / tpeak, 'peak_source': tsrc,
-                      'fp32_equivalent_tflops': tflops / 3 / (avg_ms * 1e-3) / 1e12}
-        roofline = {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': (achieved / peak) if achieved else None, 'traffic': measured_traffic(top),
-                    'fp32': fp32, 'tensor': tensor,
-                    'avg_launch_ms': avg_ms, 'launches_per_step': launches_top,
-                    'algorithmic_bytes_per_launch': units, 'peak_source': peak_src,
-                    'kernel_ms_per_step': {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])},
-                    'native_serial_ms_over_step_ms': sum(share.values()) / (ms / args.steps),
-                    'hbm': {'achieved_gbs': achieved, 'peak_gbs': peak, 'frac': (achieved / peak) if achieved else None},
-                    'note': 'the SIMT hot-path kernels are FP32-issue/latency bound, not HBM bound (DESIGN.md): for them '
-                            'the HBM fraction is reported because the contract asks for it and `fp32` is the bound '
-                            'that applies; the recognition-LSTM kernel (tcgen05, 3xTF32) is reported against the '
-                            'tensor pipe; `hbm` always carries the algorithmic-bytes view; `traffic` = DRAM bytes '
-                            'of one launch from the committed ncu capture (profiles/ncu_traffic.json)'}
+        roofline = kernel_roofline(top, per[top], n_steps_prof, pk)
+        roofline['kernel_ms_per_step'] = {k: round(v, 4) for k, v in sorted(share.items(), key=lambda kv: -kv[1])}
+        roofline['native_serial_ms_over_step_ms'] = sum(share.values()) / ms_step
+        roofline['whole_step'] = train_roofline(value / world, 3 * step_flops(O, RES), 142e3, pk)
+        # the other tensor-core kernels of the recognition LSTM, for the record
+        roofline['other_kernels'] = {k: kernel_roofline(k, per[k], n_steps_prof, pk, brief=True)
+                                     for k in ('lstm_gemm_cell_fwd', 'tc3_gemm', 'dynloop_fwd', 'dynloop_bwd', 'scene_bwd')
+                                     if k in per and k != top}
 
-    if roofline is not None and roofline.get('tensor'):
-        # the dominant kernel is the tcgen05 GEMM + LSTM cell: its bound is the tensor pipe
-        t = roofline['tensor']
-        roofline.update({'bound': 'tensor', 'achieved': t['achieved_tflops'], 'peak': t['peak_tflops'],
-                         'unit': 'TFLOP/s', 'frac': t['frac'], 'peak_source': t['peak_source']})
-
-    # ---- rollouts (no collective: sequences shard over ranks) ----------------------------------
     extra = {}
+
+    def guarded(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as e:                   # noqa: BLE001 -- an extra workload must not take the headline down
+            extra[name] = {'error': repr(e)[:300]}
+        torch.cuda.synchronize()
+
+    k_small = max(3, args.steps // 4)
+
+    # ---- config 5: long rollouts (no collective: sequences shard over ranks) -----------------------
     ac = build_ac_model(dev)
-    from stove_b200 import synth
-    n5, len5 = 1024, 2000
-    gen = torch.Generator().manual_seed(7 + rank)
-    z_last = torch.cat([0.2 + 0.3 * torch.rand(n5, O, 2, generator=gen),
-                        torch.rand(n5, O, 16, generator=gen) - 0.5], -1)
-    app = torch.rand(n5, O, 3, generator=gen)
-    act = synth.random_actions(n5, len5, 9, 11 + rank)
-    zl_d, app_d, act_d = z_last.to(dev), app.to(dev), act.to(dev)
+    len5 = 2000
+    step_fl5 = 2.0 * (98208 + O * (4 * 9 + 7 * 32) + 32 * 32 * 2 + 32 * 16 + 16 * 8 + 8)
 
-    def roll5(i):
-        ac.rollout(zl_d, len5, actions=act_d, appearance=app_d)
+    def rollout_inputs(n5, seed):
+        gen = torch.Generator().manual_seed(seed)
+        z_last = torch.cat([0.2 + 0.3 * torch.rand(n5, O, 2, generator=gen),
+                            torch.rand(n5, O, 16, generator=gen) - 0.5], -1)
+        app = torch.rand(n5, O, 3, generator=gen)
+        act = synth.random_actions(n5, len5, 9, seed + 4)
+        return z_last, app, act
 
-    ms5 = timed(roll5, max(2, args.steps // 5), 1, world)
-    k5 = max(2, args.steps // 5)
-    extra['rollout_long'] = {'workload': 'action-conditioned world-model rollouts, 1024 sequences x 2000 frames per GPU',
-                             'metric': 'rollout_frames_per_sec', 'value': world * n5 * len5 * k5 / (ms5 * 1e-3),
-                             'unit': 'sequence-frames/s', 'ms_per_rollout': ms5 / k5}
-    # roofline of the persistent rollout kernel (one launch per call): useful FP32 work of one sequence-step of
-    # the factorised, action-conditioned network against the FP32 pipe; the algorithmic HBM traffic is the state
-    # written per step (+ the action read)
-    step_flops = 2.0 * (98208 + O * (4 * 9 + 7 * 32) + 32 * 32 * 2 + 32 * 16 + 16 * 8 + 8)
-    sm_mhz5 = clock_summary.get('sm_max_mhz') or 1965.0
-    fp32_peak5 = 148 * 128 * 2 * sm_mhz5 * 1e6 / 1e12
-    per_gpu = n5 * len5 * k5 / (ms5 * 1e-3)
-    extra['rollout_long']['roofline'] = {
-        'kernel': 'team_rollout', 'bound': 'fp32',
-        'achieved_tflops': per_gpu * step_flops / 1e12, 'peak_tflops': fp32_peak5,
-        'frac': per_gpu * step_flops / 1e12 / fp32_peak5,
-        'hbm': {'achieved_gbs': per_gpu * (O * 18 * 4 + 4 + 36) / 1e9, 'peak_gbs': peak,
-                'frac': per_gpu * (O * 18 * 4 + 4 + 36) / 1e9 / peak},
-        'note': 'per GPU; %d FLOP and %d algorithmic bytes per sequence-step' % (int(step_flops), O * 18 * 4 + 40)}
-    # video prediction: 8-frame inference + 92-frame rollout (BASELINE configs[1])
-    n2 = 1024
-    x2 = make_frames(n2, 77 + rank).to(dev)
+    def rollout_bench(n5, label):
+        z_last, app, act = rollout_inputs(n5, 7 + rank)
+        zl_d, app_d, act_d = z_last.to(dev), app.to(dev), act.to(dev)
+        ms5, reps = timed(lambda i: ac.rollout(zl_d, len5, actions=act_d, appearance=app_d), max(2, args.steps // 5), 1, world)
+        k5 = max(2, args.steps // 5)
+        per_gpu = n5 * len5 * k5 / (ms5 * 1e-3)
+        out = {'workload': label, 'metric': 'rollout_frames_per_sec', 'value': world * per_gpu,
+               'unit': 'sequence-frames/s', 'ms_per_rollout': ms5 / k5, 'regions': reps, 'sequences_per_gpu': n5,
+               'inputs': 'random z_last / appearance (not config-3 inference output), attention weights of the untrained '
+                         'net halved so 2000 steps stay finite',
+               'roofline': {'kernel': 'team_rollout', 'bound': 'fp32',
+                            'achieved_tflops': per_gpu * step_fl5 / 1e12, 'peak_tflops': pk['fp32_tflops'],
+                            'frac': per_gpu * step_fl5 / 1e12 / pk['fp32_tflops'], 'peak_source': pk['fp32_src'],
+                            'hbm': {'achieved_gbs': per_gpu * (O * 18 * 4 + 40) / 1e9, 'peak_gbs': pk['hbm_gbs'],
+                                    'frac': per_gpu * (O * 18 * 4 + 40) / 1e9 / pk['hbm_gbs']},
+                            'note': 'per GPU; %d FLOP and %d algorithmic bytes per sequence-step; a latency-bound '
+                                    'kernel: 2000 dependent steps' % (int(step_fl5), O * 18 * 4 + 40)}}
+        return out, (z_last, act, app)
 
-    def predict(i):
-        with torch.no_grad():
-            _, prop, _ = model(x2, 0)
-            model.rollout(prop['z'][:, -1], num=92)
+    def cfg5_weak():
+        out, inputs = rollout_bench(1024, 'action-conditioned world-model rollouts, 1024 sequences x 2000 frames per GPU (weak)')
+        if world == 1 and rank == 0 and not args.no_cpu_baseline:
+            z_last, act, app = inputs
+            out['cpu_baseline'] = cpu_rollout(ac.state_dict(), z_last, act[:, :30], app, 30)
+        return out
+    guarded('rollout_long', cfg5_weak)
+    if 1024 % world == 0:
+        guarded('rollout_long_sharded', lambda: rollout_bench(
+            1024 // world, 'BASELINE config 5 as stated: 1024 sequences x 2000 frames in total, sharded over %d GPU(s)' % world)[0])
 
-    ms2 = timed(predict, max(2, args.steps // 2), 2, world)
-    k2 = max(2, args.steps // 2)
-    extra['video_prediction'] = {'workload': '8-frame inference + 92-frame rollout, 1024 sequences per GPU, 32x32',
-                                 'metric': 'rollout_frames_per_sec', 'value': world * n2 * 100 * k2 / (ms2 * 1e-3),
-                                 'unit': 'frames/s', 'ms_per_call': ms2 / k2}
+    # ---- config 2: video prediction = 8-frame inference + 92-frame rollout ---------------------------
+    def predict_bench(n2, res, gravity, variant, label, cpu_n=None):
+        mdl = model if variant == 'plain' else build_variant(variant, dev)
+        x2h = make_frames(n2, 77 + rank, res=res, gravity=gravity)
+        x2 = x2h.to(dev)
 
-    # whole training iteration: + global-norm clip + Adam(amsgrad) on the flat bucket (train.py:471-473), one graph
-    if not args.no_graph:
-        from stove_b200.optim import FusedAdam
-        model_o = build_model(dev)
-        model_o.load_state_dict(model.state_dict())
-        engine_o = dp.DataParallel(model_o, broadcast=False)
-        opt = FusedAdam(model_o.parameters(), lr=2e-3, amsgrad=True, max_norm=1.0)
-        graphed_o = dp.GraphedStep(engine_o, dev_pool[0], optimizer=opt)
-        ms_o = timed(lambda i: graphed_o(dev_pool[i % POOL]), args.steps, args.warmup, world)
-        extra['train_step_with_optimizer'] = {
-            'workload': WORKLOAD + ' + clip_grad_norm(1) + Adam(amsgrad) step',
-            'metric': 'train_seqs_per_sec', 'value': world * BATCH * args.steps / (ms_o * 1e-3), 'unit': 'sequences/s',
-            'ms_per_step': ms_o / args.steps, 'loss_finite': bool(torch.isfinite(graphed_o.loss).item())}
-        del graphed_o
+        def predict(i):
+            with torch.no_grad():
+                _, prop, _ = mdl(x2, 0)
+                mdl.rollout(prop['z'][:, -1], num=92)
+
+        ms2, reps = timed(predict, max(2, args.steps // 2), 2, world)
+        k2 = max(2, args.steps // 2)
+        per_gpu = n2 * 100 * k2 / (ms2 * 1e-3)
+        fl = (step_flops(O, res) + 92 * 2.0 * 147360) / 100          # per frame
+        out = {'workload': label, 'metric': 'rollout_frames_per_sec', 'value': world * per_gpu, 'unit': 'frames/s',
+               'ms_per_call': ms2 / k2, 'regions': reps, 'sequences_per_gpu': n2,
+               'roofline': {'bound': 'fp32', 'achieved_tflops': per_gpu * fl / 1e12, 'peak_tflops': pk['fp32_tflops'],
+                            'frac': per_gpu * fl / 1e12 / pk['fp32_tflops'], 'peak_source': pk['fp32_src'],
+                            'note': 'per GPU; %.2f MFLOP useful per frame (inference amortised over 100 frames); '
+                                    'launch/latency bound: ~60 launches + one persistent rollout kernel per call' % (fl / 1e6)}}
+        if world == 1 and rank == 0 and not args.no_cpu_baseline and cpu_n:
+            out['cpu_baseline'] = cpu_predict(variant, mdl.state_dict(), x2h[:cpu_n], 92)
+        return out
+
+    def cfg2():
+        out = predict_bench(1024, 32, True, 'plain', 'gravity-like frames, 3 balls, 32x32: 8-frame inference + 92-frame rollout, '
+                            '1024 sequences per GPU', cpu_n=300)
+        out['variants'] = {}
+        for tag, (n2, res, variant) in {'n300_32x32': (300, 32, 'plain'), 'n300_50x50': (300, 50, 'g50')}.items():
+            try:
+                out['variants'][tag] = predict_bench(n2, res, True, variant, '%d sequences per GPU at %dx%d' % (n2, res, res))
+            except Exception as e:               # noqa: BLE001
+                out['variants'][tag] = {'error': repr(e)[:300]}
+        return out
+    guarded('video_prediction', cfg2)
+
+    # ---- config 3: action-conditioned training with the reward loss --------------------------------
+    def cfg3():
+        n3 = 512
+        m3 = build_variant('ac', dev, seed=3)
+        batches, hosts = [], []
+        for i in range(3):                       # 3 x 50 MB of frames > L2
+            x = make_frames(n3, 300 + 10 * rank + i)
+            a = synth.random_actions(n3, T, 9, 500 + i)
+            r = (torch.rand(n3, T - 2, 1, generator=torch.Generator().manual_seed(i)) < 0.1).float()
+            hosts.append((x, a, r))
+            batches.append((x.to(dev), a.to(dev), r.to(dev)))
+        tb = TrainBench(m3, batches, world, graph=graph)
+        tb.engine.set_reward_weight(1)           # step 1 of the ramp-up: weight 1 / 20000 (train.py:458-462)
+        res = tb.measure(k_small, 3)
+        res.update({'workload': 'action-conditioned avoidance-style world model (9 actions, appearance, reward head), 32x32, '
+                                'batch 512 per GPU, loss = -ELBO + 15000 * rampup * BCE(reward), fwd+bwd',
+                    'metric': 'train_seqs_per_sec',
+                    'roofline': train_roofline(res['value'] / world, 3 * step_flops(O, RES, ac=True), 142e3 + 3 * 36 * T, pk)})
+        if world == 1 and rank == 0 and not args.no_cpu_baseline:
+            x, a, r = hosts[0]
+            res['cpu_baseline'] = cpu_train('ac', m3.state_dict(), x[:128], a[:128], r[:128], steps=2, warmup=1)
+        return res
+    guarded('train_ac', cfg3)
+
+    # ---- config 4: multiball, 6 and 9 objects at 50x50 -----------------------------------------------
+    def cfg4():
+        out = {'workload': 'multiball billiards at 50x50, greedy matching, overlap_beta 100, max_obj_scale 0.22, batch 256 per '
+                           'GPU, fwd+bwd ELBO', 'metric': 'train_seqs_per_sec', 'objects': {}}
+        for variant, num_obj in (('o6', 6), ('o9', 9)):
+            try:
+                m4 = build_variant(variant, dev, seed=4)
+                hosts = [make_frames(BATCH, 400 + 10 * rank + i, num_obj=num_obj, res=50) for i in range(3)]   # 3 x 61 MB
+                tb = TrainBench(m4, [(h.to(dev), None, None) for h in hosts], world, graph=graph)
+                res = tb.measure(k_small, 3)
+                res['roofline'] = train_roofline(res['value'] / world, 3 * step_flops(num_obj, 50),
+                                                 8 * 3 * 2500 * 4 + 2 * 4 * 3.1e6 / BATCH, pk)
+                if world == 1 and rank == 0 and not args.no_cpu_baseline:
+                    res['cpu_baseline'] = cpu_train(variant, m4.state_dict(), hosts[0][:64], steps=1, warmup=1)
+                out['objects'][str(num_obj)] = res
+                del tb
+            except Exception as e:               # noqa: BLE001
+                out['objects'][str(num_obj)] = {'error': repr(e)[:300]}
+        six = out['objects'].get('6', {})
+        out.update({k: six[k] for k in ('value', 'unit', 'ms_per_step') if k in six})
+        return out
+    guarded('train_multiball', cfg4)
+
+    # ---- strong scaling of config 1: the GLOBAL batch stays 256 ------------------------------------------
+    if world > 1 and BATCH % world == 0:
+        def strong():
+            nb = BATCH // world
+            ms_model = build_model(dev)
+            ms_model.load_state_dict(model.state_dict())
+            pool = [(dev_pool[i][0][rank * nb:(rank + 1) * nb].contiguous(), None, None) for i in range(POOL)]
+            tb = TrainBench(ms_model, pool, world, graph=graph)
+            res = tb.measure(args.steps, args.warmup)
+            res.update({'workload': 'config 1 with the global batch fixed at 256 (%d sequences per GPU)' % nb,
+                        'metric': 'train_seqs_per_sec', 'scaling': 'strong'})
+            return res
+        guarded('train_strong', strong)
+
+    # ---- whole training iteration: + global-norm clip + Adam(amsgrad) (train.py:471-473), one graph -------
+    if graph:
+        def with_opt():
+            model_o = build_model(dev)
+            model_o.load_state_dict(model.state_dict())
+            tb = TrainBench(model_o, dev_pool, world, graph=True, optimizer=True)
+            res = tb.measure(args.steps, args.warmup)
+            res.update({'workload': WORKLOAD + ' + clip_grad_norm(1) + Adam(amsgrad) step', 'metric': 'train_seqs_per_sec'})
+            return res
+        guarded('train_step_with_optimizer', with_opt)
+
+    # ---- N > 1: the sharded gradient equals the single-rank gradient of the concatenated batch -------------
+    if world > 1:
+        guarded('dp_gradient_check', lambda: dp_gradient_check(model, dev, world, rank))
 
     def finish():
         # graphs that captured NCCL work must go before the communicator; a hard exit after the flush
@@ -414,33 +695,104 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        frames = [h.clone() for h in host_pool[:2]]
-        v, threads, sec = cpu_train_baseline(3, 1, model.state_dict(), frames)
-        cpu = {'value': v, 'unit': 'sequences/s', 'cores': threads, 'kind': 'port',
-               'sample': '3 full batch-256 fwd+bwd steps (after 1 warm-up) of the oracle port, torch CPU fp32',
-               'ms_per_step': sec * 1e3}
-        v5 = cpu_rollout_baseline(ac.state_dict(), z_last, act, app, 30)
-        extra['rollout_long']['cpu_baseline'] = {'value': v5, 'unit': 'sequence-frames/s', 'cores': threads,
-                                                 'kind': 'port', 'sample': '1024 sequences x 30 steps'}
+        cpu = cpu_train('plain', model.state_dict(), host_pool[0], steps=6, warmup=1)
+        try:
+            cpu['fp64'] = cpu_train('plain', model.state_dict(), host_pool[0], steps=2, warmup=1, dtype=torch.float64)
+        except Exception as e:                   # noqa: BLE001
+            cpu['fp64'] = {'error': repr(e)[:200]}
 
+    frame_bytes = BATCH * T * 3 * RES * RES
     line = {
         'metric': 'train_seqs_per_sec', 'value': value, 'unit': 'sequences/s', 'n_gpus': world,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': BATCH * world, 'parallelism': 'dp%d' % world,
                    'l2_policy': 'inputs rotate through a %d-batch device pool (%.0f MB > 126 MB L2)'
-                                % (POOL, POOL * BATCH * T * 3 * RES * RES * 4 / 1e6),
+                                % (POOL, POOL * frame_bytes * 4 / 1e6),
+                   'timing': 'median of %d regions of exactly %d steps each (>= %.1f s measured in total), CUDA events, '
+                             'barrier + synchronize on both sides, max over ranks' % (res_main['regions'], args.steps, MIN_REGION_S),
                    'cuda_graph': graphed is not None,
+                   'e2e_input': 'uint8 RGB frames in pinned host memory, scaled by 1/255 inside bw_transform on the device; '
+                                '`e2e_f32_frames` is the same with fp32 host frames (4x the bytes)',
                    'optimizer': 'excluded (metric is fwd+bwd); flat-bucket NCCL all-reduce included when N>1'},
         'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': BATCH * T * 3 * RES * RES * 4, 'd2h_bytes_per_step': 4},
+                'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': 4},
+        'e2e_f32_frames': {'value': world * BATCH * args.steps / (ms_e2e32 * 1e-3), 'unit': 'sequences/s',
+                           'ms_per_step': ms_e2e32 / args.steps, 'h2d_bytes_per_step': frame_bytes * 4, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches), 'gpu_launches_per_step': int(launches) // args.steps,
         'clocks': clock_summary, 'roofline': roofline, 'cpu_baseline': cpu,
-        'loss_finite': bool(all(map(lambda v: v == v, [float(l) for l in losses[-3:]]))),
+        'loss_finite': res_main['loss_finite'] and all(v == v for v in e2e_losses[-3:]),
     }
     line.update(extra)
     emit(line)
     finish()
+
+
+def dp_gradient_check(model, dev, world, rank):
+    """Inside the N > 1 run: all-reduced gradients of the rank-local shards == gradient of the concatenated batch
+    computed by one rank (the ELBO is a batch mean, stove.py:748).  Noise is replayed so both see the same draws."""
+    import torch.distributed as dist
+    from stove_b200 import dp
+    n_loc = 16
+    full = make_frames(n_loc * world, 4242).to(dev)
+    gen = torch.Generator().manual_seed(5)
+    draws = [torch.randn(n_loc * world, O, 12, 1, generator=gen) for _ in range(2)] + \
+            [torch.randn(n_loc * world, O, 18, generator=gen) for _ in range(T - 2)]
+
+    class Replay:
+        stacked = False
+
+        def __init__(self, lo, hi):
+            self.d = [d[lo:hi].to(dev) for d in draws]
+
+        def __call__(self, shape, like):
+            return self.d.pop(0)
+
+    eng = dp.DataParallel(model, broadcast=False)
+    model._standard_normal = Replay(rank * n_loc, (rank + 1) * n_loc)
+    eng.forward_backward(full[rank * n_loc:(rank + 1) * n_loc], 1)
+    sharded = eng.flat.clone()
+    model._standard_normal = Replay(0, n_loc * world)
+    for p in eng.params:
+        p.grad = None
+    elbo, _, _ = model(full, 1)
+    (-elbo).backward()
+    del model._standard_normal
+    ref = torch.cat([p.grad.reshape(-1) for p in eng.live])
+    err = float((sharded - ref).abs().max() / ref.abs().max())
+    t = torch.tensor([err], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {'max_rel_err': float(t), 'tolerance': 1e-4, 'ok': float(t) < 1e-4,
+            'what': 'flat gradient after all-reduce of %d-sequence shards vs. one rank on the %d-sequence batch' % (n_loc, n_loc * world)}
+
+
+def kernel_roofline(kernel, times, n_steps, pk, brief=False):
+    launches = len(times) / n_steps
+    avg_ms = sum(times) / len(times)
+    units = kernel_algorithmic_bytes(kernel, BATCH)
+    achieved = units / (avg_ms * 1e-3) / 1e9 if units else None
+    out = {'kernel': kernel, 'avg_launch_ms': avg_ms, 'launches_per_step': launches}
+    flops = kernel_flops(kernel, BATCH)
+    tflops = kernel_tensor_flops(kernel, BATCH)
+    if tflops:
+        # executed TF32 tensor-core FLOPs = 3 x the fp32-equivalent product (hi*hi + hi*lo + lo*hi)
+        ach = tflops / (avg_ms * 1e-3) / 1e12
+        out.update({'bound': 'tensor', 'achieved': ach, 'peak': pk['tf32_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['tf32_tflops'],
+                    'frac_useful': ach / 3 / pk['tf32_tflops'], 'peak_source': pk['tf32_src'],
+                    'note': '`frac` counts the executed 3xTF32 FLOPs, `frac_useful` the fp32-equivalent product (1/3 of them)'})
+        if pk.get('tf32_mma_tflops'):
+            out['frac_of_measured_tcgen05_tf32_peak'] = ach / pk['tf32_mma_tflops']
+    elif flops:
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        out.update({'bound': 'fp32', 'achieved': ach, 'peak': pk['fp32_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['fp32_tflops'],
+                    'frac_useful': ach / pk['fp32_tflops'], 'peak_source': pk['fp32_src']})
+    else:
+        out.update({'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': (achieved / pk['hbm_gbs']) if achieved else None, 'peak_source': pk['hbm_src']})
+    if not brief:
+        out.update({'traffic': measured_traffic(kernel), 'algorithmic_bytes_per_launch': units,
+                    'hbm': {'achieved_gbs': achieved, 'peak_gbs': pk['hbm_gbs'], 'frac': (achieved / pk['hbm_gbs']) if achieved else None}})
+    return out
 
 
 def kernel_algorithmic_bytes(kernel, batch):
@@ -450,6 +802,7 @@ def kernel_algorithmic_bytes(kernel, batch):
     patches = frames * O
     D_bg, D_obj = RES * RES, 100
     S, Z, W_DYN = T - 2, 18, 22660        # dynamics steps, state width, GNN weight floats (plain config)
+    n, H = batch * T, 256
     table = {
         'spn1_fwd_leaf': frames * D_bg * 4 * 2,                   # frame + mask in, 36 floats out (negligible)
         'spn1_bwd_input': frames * D_bg * 4 * 3,                  # frame + mask in, mask gradient out
@@ -463,19 +816,19 @@ def kernel_algorithmic_bytes(kernel, batch):
         'scene_bwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
         # z_init, sup, sup_std, eps in; z, z_std, z_dyn, z_dyn_std, logq, trans out; weights once
         'dynloop_fwd': 4 * (batch * O * Z + batch * S * O * (12 + Z) + batch * S * (O * (2 * Z + 2 * (Z - 2)) + 2) + W_DYN),
-        # z, sup, sup_std, eps, g_z, g_logq, g_trans in; g_sup, g_sup_std, g_z_init out; weights once
-        # (the per-step activation / gradient records are intermediates: 16.7 KB + 16.2 KB per
-        # sequence-step, L2-resident, they show up in `traffic` only)
         'dynloop_bwd': 4 * (batch * S * (O * (Z + 12 + Z + Z) + 2) + batch * S * O * 12 + batch * O * Z + W_DYN),
         'dynloop_wgrad': 4 * (batch * S * 8224 + 148 * W_DYN),     # its input IS the per-step record stream
         'bw_transform': batch * T * D_bg * 4 * 4,
         # recognition LSTM, average launch of the O per step: frames (once) + W_ih + W_hh in; h, c and the saved
-        # gate activations out; gx and the TF32 operand splits are intermediates
-        'lstm_gemm_cell_fwd': 4 * (batch * T * D_bg + 4 * 256 * (D_bg + 256) + O * batch * T * 256 * 6) // O,
+        # gate activations out; gx and the TF32 operand planes are intermediates
+        'lstm_gemm_cell_fwd': 4 * (n * D_bg + 4 * H * (D_bg + H) + O * n * H * 6) // O,
+        # backward GEMMs, average of the 2 (O - 1) hidden-state + 2 weight-gradient launches: gate gradients in,
+        # weight gradients out (the operand planes are intermediates)
+        'tc3_gemm': 4 * (O * n * 4 * H + 4 * H * (D_bg + H)) // (O + 1),
         'enc_head_fwd': 4 * batch * T * O * (256 + 50 + 8),
         'enc_head_bwd_data': 4 * batch * T * O * (8 + 50 + 256),
         'enc_head_bwd_par': 4 * batch * T * O * (256 + 50 + 8),
-        'lstm_cell_bwd': 4 * batch * T * 256 * (4 + 2 + 2 + 4),
+        'lstm_cell_bwd': 4 * n * H * (4 + 2 + 2 + 4),
         'sup_prepare_fwd': 4 * batch * T * O * (8 + 4 + 6 + 6),
         'sup_prepare_bwd': 4 * batch * T * O * (8 + 4 + 6 + 6 + 6 + 8),
     }
@@ -486,7 +839,6 @@ def kernel_flops(kernel, batch):
     """Useful fp32 FLOPs of one launch (2 x FMA count of the factorised GNN)."""
     S = T - 2
     step_fwd = 2 * 98208                   # one dynamics step of one sequence, O = 3, cl = 32
-    # dynloop_bwd reloads the activations kept by the forward pass: input gradients only
     frames = batch * (T - 1)
     table = {'dynloop_fwd': batch * S * step_fwd, 'dynloop_bwd': batch * S * step_fwd,
              'dynloop_wgrad': batch * S * step_fwd,
@@ -495,21 +847,12 @@ def kernel_flops(kernel, batch):
 
 
 def kernel_tensor_flops(kernel, batch):
-    """Executed tensor-core FLOPs of one (average) launch: the recognition LSTM runs 3xTF32, K-concatenated."""
+    """EXECUTED tensor-core FLOPs of one (average) launch: 3 x the fp32-equivalent product (3xTF32)."""
     n, H, K = batch * T, 256, RES * RES
-    table = {'lstm_gemm_cell_fwd': 3 * 2.0 * n * 4 * H * (K + (O - 1) * H) / O}
+    table = {'lstm_gemm_cell_fwd': 3 * 2.0 * n * 4 * H * (K + (O - 1) * H) / O,
+             # (O - 1) hidden-state GEMMs n x H x 4H, the W_hh gradient 4H x H x (O - 1) n, the W_ih gradient 4H x K x n
+             'tc3_gemm': 3 * 2.0 * n * 4 * H * (2 * (O - 1) * H + K) / (O + 1)}
     return table.get(kernel)
-
-
-def measured_tensor_peak():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(path):
-        with open(path) as f:
-            p = json.load(f)
-        for key in ('bf16_tflops', 'bf16_dense_tflops', 'tensor_bf16_tflops'):
-            if key in p:
-                return p[key] / 2.0, 'MEASURED_PEAKS.json %s / 2 (TF32 runs at half the bf16 rate)' % key
-    return 2250.0 / 2 / 2, 'fallback: nominal 1125 TFLOP/s dense TF32 / 2 (MEASURED_PEAKS.json has no bf16 figure)'
 
 
 def measured_traffic(kernel):

@@ -44,11 +44,24 @@ int stove_profile_read(int32_t* ids, float* ms, int max_n);
 const char* stove_kernel_name(int id);
 int stove_kernel_count(void);
 
+/* Library options: alternative code paths kept for the parity tests and for per-kernel timing passes.
+ * Nothing in the library reads the environment.  Names: "fork" (1: independent kernels of one call run on
+ * library side streams), "spn2_nodes_stage", "dynloop_generic", "dynloop_nw", "dynloop_recompute",
+ * "rollout_cta", "rollout_nw", "gnn_seq_fwd", "gnn_seq_bwd".  set returns the previous value (or a
+ * negative error code for an unknown name). */
+int stove_set_option(const char* name, int value);
+int stove_get_option(const char* name);
+
 /* ------------------------------------------------------------------------------------
  * bw_transform: sum colour channels, clamp to [0,1]   (model/utils/utils.py:10-15)
  *   x [n][C][hw] -> y [n][hw]
  * ---------------------------------------------------------------------------------- */
 int stove_bw_transform(const float* x, float* y, int64_t n, int channels, int64_t hw, void* stream);
+/* The same with uint8 frames accepted (x_is_u8: values are scaled by 1/255 on the fly -- host frames then
+ * cross PCIe at one byte per value) and, optionally, the (hi, lo) TF32 operand planes y_planes [2][n][hw] of
+ * y written in the same pass (the left operand of the recognition LSTM's input GEMM, see below). */
+int stove_bw_transform_ex(const void* x, int x_is_u8, float* y, float* y_planes, int64_t n, int channels,
+                          int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * RAT-SPN parameter packing (model/spn/rat_torch.py:85-99 leaf variance,

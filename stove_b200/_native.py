@@ -78,7 +78,10 @@ SIGNATURES = {
     'stove_profile_read': (C.c_int, [vp, vp, C.c_int]),
     'stove_kernel_name': (C.c_char_p, [C.c_int]),
     'stove_kernel_count': (C.c_int, []),
+    'stove_set_option': (C.c_int, [C.c_char_p, C.c_int]),
+    'stove_get_option': (C.c_int, [C.c_char_p]),
     'stove_bw_transform': (C.c_int, [vp, vp, i64, C.c_int, i64, vp]),
+    'stove_bw_transform_ex': (C.c_int, [vp, C.c_int, vp, vp, i64, C.c_int, i64, vp]),
     'stove_spn_pack_leaf_fwd': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp]),
     'stove_spn_pack_leaf_bwd': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp, vp, vp]),
     'stove_spn_pack_sum_fwd': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
@@ -148,6 +151,14 @@ def check(rc):
     if rc != 0:
         raise RuntimeError('stove_b200 native call failed (%d): %s'
                            % (rc, lib().stove_last_error().decode()))
+
+
+def set_option(name, value):
+    """Library option (include/stove_b200.h: stove_set_option); returns the previous value."""
+    prev = lib().stove_set_option(name.encode(), int(value))
+    if prev < 0:
+        check(prev)
+    return prev
 
 
 def profile_read(max_n=1 << 16):

@@ -1,5 +1,6 @@
 // Error reporting + trivial entry points of the C ABI (include/stove_b200.h).
 #include <stdarg.h>
+#include <string.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -126,6 +127,28 @@ int stove_join(StoveFork* f, cudaStream_t s, int nside) {
     return STOVE_OK;
 }
 
+static int g_options[OPT_COUNT] = {1, 1, 0, 2, 0, 0, 2, 0, 0};
+static const char* const kOptionNames[OPT_COUNT] = {"fork", "spn2_nodes_stage", "dynloop_generic", "dynloop_nw",
+                                                    "dynloop_recompute", "rollout_cta", "rollout_nw", "gnn_seq_fwd",
+                                                    "gnn_seq_bwd"};
+int stove_opt(int id) { return g_options[id]; }
+extern "C" int stove_set_option(const char* name, int value) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (name && strcmp(name, kOptionNames[i]) == 0) {
+            const int prev = g_options[i];
+            g_options[i] = value;
+            return prev;
+        }
+    stove_set_error("stove_set_option: unknown option '%s'", name ? name : "(null)");
+    return STOVE_ERR_ARG;
+}
+extern "C" int stove_get_option(const char* name) {
+    for (int i = 0; i < OPT_COUNT; ++i)
+        if (name && strcmp(name, kOptionNames[i]) == 0) return g_options[i];
+    stove_set_error("stove_get_option: unknown option '%s'", name ? name : "(null)");
+    return STOVE_ERR_ARG;
+}
+
 extern "C" const char* stove_kernel_name(int id) { return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : "?"; }
 extern "C" int stove_kernel_count(void) { return K_COUNT; }
 extern "C" int64_t stove_launch_count(int reset) {
@@ -137,56 +160,88 @@ extern "C" int64_t stove_launch_count(int reset) {
 
 // ---------------------------------------------------------------------------------------
 // bw_transform (model/utils/utils.py:10-15): y = clamp(sum_c x[:, c], 0, 1).
-// Pure streaming: reads C*4 B, writes 4 B per pixel; float4 vectorised when hw % 4 == 0.
+// Pure streaming: reads C*4 B (or C bytes for uint8 frames, scaled by 1/255 on the fly), writes 4 B per
+// pixel; four pixels per thread when hw % 4 == 0.  Optionally also writes the (hi, lo) TF32 operand planes of
+// y (the left operand of the recognition LSTM's input GEMM, csrc/lstm_tc.cu), saving that kernel a pass.
 // ---------------------------------------------------------------------------------------
-__global__ void bw_transform_kernel(const float* __restrict__ x, float* __restrict__ y,
+__device__ __forceinline__ float4 load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4(const uint8_t* p) {
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(p));
+    const float s = 1.0f / 255.0f;
+    return make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+}
+__device__ __forceinline__ float load1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load1(const uint8_t* p) { return __ldg(p) * (1.0f / 255.0f); }
+__device__ __forceinline__ float tf32_hi_(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+template <typename TI, bool V4>
+__global__ void bw_transform_kernel(const TI* __restrict__ x, float* __restrict__ y, float* __restrict__ pl,
                                     int64_t n, int C, int64_t hw) {
-    int64_t total = n * hw;
+    constexpr int W = V4 ? 4 : 1;
+    const int64_t hww = hw / W, total = n * hww, plane = n * hw;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t b = i / hw, p = i - b * hw;
-        const float* src = x + (b * C) * hw + p;
-        float acc = 0.f;
-        for (int c = 0; c < C; ++c) acc += __ldg(src + c * hw);
-        y[i] = fminf(fmaxf(acc, 0.f), 1.f);
+        const int64_t b = i / hww, p = (i - b * hww) * W;
+        const TI* src = x + (b * C) * hw + p;
+        const int64_t o = b * hw + p;
+        if (V4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = 0; c < C; ++c) {
+                const float4 v = load4(src + c * hw);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            acc.x = fminf(fmaxf(acc.x, 0.f), 1.f);
+            acc.y = fminf(fmaxf(acc.y, 0.f), 1.f);
+            acc.z = fminf(fmaxf(acc.z, 0.f), 1.f);
+            acc.w = fminf(fmaxf(acc.w, 0.f), 1.f);
+            *reinterpret_cast<float4*>(y + o) = acc;
+            if (pl) {
+                const float4 hi = make_float4(tf32_hi_(acc.x), tf32_hi_(acc.y), tf32_hi_(acc.z), tf32_hi_(acc.w));
+                *reinterpret_cast<float4*>(pl + o) = hi;
+                *reinterpret_cast<float4*>(pl + plane + o) = make_float4(acc.x - hi.x, acc.y - hi.y, acc.z - hi.z, acc.w - hi.w);
+            }
+        } else {
+            float acc = 0.f;
+            for (int c = 0; c < C; ++c) acc += load1(src + c * hw);
+            acc = fminf(fmaxf(acc, 0.f), 1.f);
+            y[o] = acc;
+            if (pl) {
+                const float hi = tf32_hi_(acc);
+                pl[o] = hi;
+                pl[plane + o] = acc - hi;
+            }
+        }
     }
 }
-__global__ void bw_transform_kernel_v4(const float4* __restrict__ x, float4* __restrict__ y,
-                                       int64_t n, int C, int64_t hw4) {
-    int64_t total = n * hw4;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t b = i / hw4, p = i - b * hw4;
-        const float4* src = x + (b * C) * hw4 + p;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c = 0; c < C; ++c) {
-            float4 v = __ldg(src + c * hw4);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        }
-        acc.x = fminf(fmaxf(acc.x, 0.f), 1.f);
-        acc.y = fminf(fmaxf(acc.y, 0.f), 1.f);
-        acc.z = fminf(fmaxf(acc.z, 0.f), 1.f);
-        acc.w = fminf(fmaxf(acc.w, 0.f), 1.f);
-        y[i] = acc;
-    }
+
+template <typename TI>
+static int bw_launch(const TI* x, float* y, float* pl, int64_t n, int channels, int64_t hw, cudaStream_t st) {
+    const int threads = 256;
+    const bool v4 = (hw % 4 == 0) && (((uintptr_t)x % (4 * sizeof(TI))) == 0) && (((uintptr_t)y | (uintptr_t)pl) % 16 == 0);
+    const int64_t items = v4 ? n * (hw / 4) : n * hw;
+    int blocks = (int)((items + threads - 1) / threads);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (v4)
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, true><<<blocks, threads, 0, st>>>(x, y, pl, n, channels, hw));
+    else
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, false><<<blocks, threads, 0, st>>>(x, y, pl, n, channels, hw));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
 }
 
 extern "C" int stove_bw_transform(const float* x, float* y, int64_t n, int channels, int64_t hw,
                                   void* stream) {
     STOVE_CHECK_ARG(x && y && n >= 0 && channels > 0 && hw > 0, "bad argument");
     if (n == 0) return STOVE_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int threads = 256;
-    bool v4 = (hw % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0);
-    int64_t items = v4 ? n * (hw / 4) : n * hw;
-    int blocks = (int)((items + threads - 1) / threads);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (v4)
-        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel_v4<<<blocks, threads, 0, st>>>((const float4*)x, (float4*)y, n, channels, hw / 4));
-    else
-        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<<<blocks, threads, 0, st>>>(x, y, n, channels, hw));
-    STOVE_LAUNCH_CHECK();
-    return STOVE_OK;
+    return bw_launch<float>(x, y, nullptr, n, channels, hw, (cudaStream_t)stream);
+}
+
+extern "C" int stove_bw_transform_ex(const void* x, int x_is_u8, float* y, float* y_planes, int64_t n,
+                                     int channels, int64_t hw, void* stream) {
+    STOVE_CHECK_ARG(x && y && n >= 0 && channels > 0 && hw > 0, "bad argument");
+    if (n == 0) return STOVE_OK;
+    return x_is_u8 ? bw_launch<uint8_t>((const uint8_t*)x, y, y_planes, n, channels, hw, (cudaStream_t)stream)
+                   : bw_launch<float>((const float*)x, y, y_planes, n, channels, hw, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -58,6 +58,22 @@ StoveFork* stove_fork_get(int family);          // nullptr on failure (error str
 int stove_fork(StoveFork* f, cudaStream_t s, int nside);
 int stove_join(StoveFork* f, cudaStream_t s, int nside);
 
+// Library options (stove_set_option): alternative code paths kept for the parity tests and for per-kernel
+// timing passes.  They are set through the API only -- nothing in the library reads the environment.
+enum StoveOption {
+    OPT_FORK,                 // 1: independent kernels of one call run on library side streams (default); 0: serial
+    OPT_SPN2_NODES_STAGE,     // 1: spn2_bwd_nodes stages the sum weights in shared memory (default)
+    OPT_DYNLOOP_GENERIC,      // 1: dynamics loop through the generic CTA-wide kernels
+    OPT_DYNLOOP_NW,           // warps per sequence of the warp-team dynamics loop (1 or 2; default 2)
+    OPT_DYNLOOP_RECOMPUTE,    // 1: the loop backward recomputes each step instead of reloading activations
+    OPT_ROLLOUT_CTA,          // 1: rollouts through the generic CTA-wide kernel
+    OPT_ROLLOUT_NW,           // warps per sequence of the rollout kernel (1 or 2; default 2)
+    OPT_GNN_SEQ_FWD,          // sequences per CTA of the generic kernels (0 = automatic)
+    OPT_GNN_SEQ_BWD,
+    OPT_COUNT
+};
+int stove_opt(int id);
+
 static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 

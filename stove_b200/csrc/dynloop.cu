@@ -1209,7 +1209,7 @@ static void build_tables(const stove_gnn_cfg* c, const GnnLayout& L, TW* tw, Sta
 
 static bool supported(const stove_gnn_cfg* c, const GnnLayout& L) {
     return c->num_obj == O && c->cl == CL && L.in_dim <= IN_MAX && c->action_dim <= A_MAX &&
-           !env_int("STOVE_DYNLOOP_GENERIC", 0);
+           !stove_opt(OPT_DYNLOOP_GENERIC);
 }
 
 // teams per CTA: spread the sequences over the 148 SMs first, then fill each SM
@@ -1305,7 +1305,7 @@ extern "C" int stove_dynloop_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     tk::TW tw;
     tk::StageTable tab;
     tk::build_tables(cfg, L, &tw, &tab);
-    const int NW = env_int("STOVE_DYNLOOP_NW", 2);
+    const int NW = stove_opt(OPT_DYNLOOP_NW);
     const bool save = io->xrec != nullptr;           // training: keep the activations for the backward pass
     const int lay_total = save ? tk::BwdLay::TOTAL : tk::FwdLay::TOTAL;
     const int max_tpc = (int)((kMaxSmem / sizeof(float) - tw.total) / lay_total);
@@ -1373,7 +1373,7 @@ extern "C" size_t stove_dynloop_bwd_workspace(const stove_gnn_cfg* cfg, int64_t 
 extern "C" int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, int skip) {
     if (gnn_check(cfg) || n <= 0 || T <= skip) return 0;
     GnnLayout L = gnn_layout(cfg);
-    if (!tk::supported(cfg, L) || env_int("STOVE_DYNLOOP_RECOMPUTE", 0)) return 0;
+    if (!tk::supported(cfg, L) || stove_opt(OPT_DYNLOOP_RECOMPUTE)) return 0;
     return (int64_t)n * (T - skip) * tk::BwdLay::XREC;
 }
 
@@ -1432,7 +1432,7 @@ extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg
     tk::TW tw;
     tk::StageTable tab;
     tk::build_tables(cfg, L, &tw, &tab);
-    const int NW = env_int("STOVE_DYNLOOP_NW", 2);
+    const int NW = stove_opt(OPT_DYNLOOP_NW);
     const FuseCfg f = make_fuse(cfg, fuse);
     const tk::LoopIO lio = to_loop_io(io);
     // workspace: gradient records | slabs | activation records (only if the forward pass kept none)
@@ -1475,11 +1475,11 @@ int stove_team_rollout(const stove_gnn_cfg* cfg, const GnnLayout& L, int64_t n, 
                        const float* actions, int action_len, const float* app, const float* weights,
                        const float* noise, float pos_var, float vel_std, float latent_std, float* z_out,
                        float* std_out, float* logq_out, float* rewards, cudaStream_t st) {
-    if (!tk::supported(cfg, L) || env_int("STOVE_ROLLOUT_CTA", 0)) return 1;
+    if (!tk::supported(cfg, L) || stove_opt(OPT_ROLLOUT_CTA)) return 1;
     tk::TW tw;
     tk::StageTable tab;
     tk::build_tables(cfg, L, &tw, &tab);
-    const int NW = env_int("STOVE_ROLLOUT_NW", 2);
+    const int NW = stove_opt(OPT_ROLLOUT_NW);
     const int max_tpc = (int)((kMaxSmem / sizeof(float) - tw.total) / tk::FwdLay::TOTAL);
     const int tpc = tk::pick_tpc(n, max_tpc < 7 ? max_tpc : 7);
     const size_t smem = sizeof(float) * ((size_t)tw.total + (size_t)tpc * tk::FwdLay::TOTAL);

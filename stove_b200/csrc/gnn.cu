@@ -1034,8 +1034,8 @@ __global__ void gnn_reduce_slabs_kernel(const float* __restrict__ slabs, int nsl
 // largest number of sequences per CTA that fits (optionally with staged weights), <= want
 
 static int pick_seq(const stove_gnn_cfg* c, const GnnLayout& L, bool bwd, bool stage, int want) {
-    // tuning override (sequences per CTA): STOVE_GNN_SEQ_FWD / STOVE_GNN_SEQ_BWD
-    want = env_int(bwd ? "STOVE_GNN_SEQ_BWD" : "STOVE_GNN_SEQ_FWD", want);
+    // tuning override (sequences per CTA): options gnn_seq_fwd / gnn_seq_bwd
+    if (stove_opt(bwd ? OPT_GNN_SEQ_BWD : OPT_GNN_SEQ_FWD) > 0) want = stove_opt(bwd ? OPT_GNN_SEQ_BWD : OPT_GNN_SEQ_FWD);
     for (int seq = want; seq >= 1; --seq) {
         GnnBuf b = gnn_buffers(*c, L.in_dim, seq, bwd);
         size_t bytes = sizeof(float) * ((size_t)b.total + (stage ? L.total : 0));

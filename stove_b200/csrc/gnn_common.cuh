@@ -98,7 +98,3 @@ static inline int gnn_check(const stove_gnn_cfg* c) {
 
 static const size_t kMaxSmem = 227 * 1024;
 
-static inline int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}

@@ -602,8 +602,9 @@ __global__ void sum_parts_kernel(int64_t n4, int parts, int64_t stride4, const f
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 a = in[i];
-    for (int p = 1; p < parts; ++p) {
-        const float4 b = in[(int64_t)p * stride4 + i];
+#pragma unroll 8
+    for (int p = 1; p < parts; ++p) {          // independent loads: unrolled so they are in flight together
+        const float4 b = __ldg(in + (int64_t)p * stride4 + i);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     out[i] = a;

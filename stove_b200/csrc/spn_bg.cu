@@ -692,7 +692,7 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
     STOVE_KERNEL(K_SPN1_BWD_ROOT, s, spn1_bwd_root_kernel<3, 6><<<(unsigned)((npad + 127) / 128), 128, 0, s>>>(N, npad, rlin, rlog, leaf_val, out,
                                                                            g_out, w.gleaf, w.aux_root, g_rlog));
     STOVE_LAUNCH_CHECK();
-    StoveFork* fk = getenv("STOVE_NO_FORK") ? nullptr : stove_fork_get(1);
+    StoveFork* fk = !stove_opt(OPT_FORK) ? nullptr : stove_fork_get(1);
     if (fk && (rc = stove_fork(fk, s, 2))) return rc;
     cudaStream_t s_leaf = fk ? fk->side[0] : s, s_root = fk ? fk->side[1] : s;
     if (g_x || g_marg) {

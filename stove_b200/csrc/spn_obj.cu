@@ -908,7 +908,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
         // sum and root weights staged in shared memory (cp.async, read back with pinned-order loads): every
         // (pair, sum) step otherwise waits for its own broadcast load from L1/L2 (ncu: 7.7 stall cycles per issued
         // instruction on the load scoreboard); 47 -> 37 us
-        if (stage_smem <= 227 * 1024 && !getenv("STOVE_SPN2_NODES_NOSTAGE")) {
+        if (stage_smem <= 227 * 1024 && stove_opt(OPT_SPN2_NODES_STAGE)) {
             if ((rc = set_smem(spn2_bwd_nodes_kernel<G, S, true>, stage_smem))) return rc;
             STOVE_KERNEL(K_SPN2_BWD_NODES, s, spn2_bwd_nodes_kernel<G, S, true><<<blocks, 32 * Q, stage_smem, s>>>(
                 d, N, npad, wlin, wlog, rlin, rlog, leaf_val, sum_val, out, g_out, w.gleaf, w.aux_reg, w.aux_root,
@@ -923,7 +923,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
     }
     // the three remaining kernels only depend on the node pass: input gradients stay on the caller's
     // stream, the two parameter-gradient kernels run on side streams
-    StoveFork* fk = getenv("STOVE_NO_FORK") ? nullptr : stove_fork_get(0);
+    StoveFork* fk = !stove_opt(OPT_FORK) ? nullptr : stove_fork_get(0);
     if (fk && (rc = stove_fork(fk, s, 2))) return rc;
     cudaStream_t s_leaf = fk ? fk->side[0] : s, s_sum = fk ? fk->side[1] : s;
     if (g_x || g_marg) {

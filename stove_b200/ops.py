@@ -18,14 +18,21 @@ def _c(t):
 # ----------------------------------------------------------------------------------------
 # bw_transform (model/utils/utils.py:10-15)
 # ----------------------------------------------------------------------------------------
-def bw_transform(x):
-    """(n, T, C, W, H) -> (n, T, 1, W, H): sum colour channels, clamp to [0, 1]."""
-    N.require_cuda_f32(x)
+def bw_transform(x, want_planes=False):
+    """(n, T, C, W, H) -> (n, T, 1, W, H): sum colour channels, clamp to [0, 1] (utils.py:10-15).
+    x: fp32 in [0, 1], or uint8 frames (scaled by 1/255 inside the kernel).  With `want_planes` also returns
+    the (hi, lo) TF32 operand planes (2, n*T, W*H) of the result for the recognition LSTM's input GEMM."""
+    if not x.is_cuda:
+        raise RuntimeError('stove_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path' % x.device)
+    if x.dtype not in (torch.float32, torch.uint8):
+        raise RuntimeError('stove_b200: frames must be float32 in [0, 1] or uint8 (got %s)' % x.dtype)
     x = x.contiguous()
     n, T, ch, w, h = x.shape
-    y = torch.empty(n, T, 1, w, h, device=x.device, dtype=x.dtype)
-    N.check(N.lib().stove_bw_transform(N.ptr(x), N.ptr(y), n * T, ch, w * h, N.stream()))
-    return y
+    y = torch.empty(n, T, 1, w, h, device=x.device, dtype=torch.float32)
+    pl = torch.empty(2, n * T, w * h, device=x.device, dtype=torch.float32) if want_planes else None
+    N.check(N.lib().stove_bw_transform_ex(N.ptr(x), int(x.dtype == torch.uint8), N.ptr(y), N.ptr(pl), n * T, ch,
+                                          w * h, N.stream()))
+    return (y, pl) if want_planes else y
 
 
 # ----------------------------------------------------------------------------------------
@@ -85,6 +92,22 @@ class PackSum(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------
 # fused SPNs
 # ----------------------------------------------------------------------------------------
+_FORK = True
+
+
+def set_fork(enabled):
+    """Side streams on / off, here and in the library (option "fork"): off = every kernel of a step runs on
+    the caller's stream, which is what a per-kernel timing pass needs.  Returns the previous setting."""
+    global _FORK
+    prev, _FORK = _FORK, bool(enabled)
+    N.set_option('fork', int(_FORK))
+    return prev
+
+
+def fork_enabled():
+    return _FORK
+
+
 def _zeros_views(ref, *shapes):
     """Zero tensors of the given shapes carved out of ONE buffer (one fill launch instead of one each);
     every view starts on a 256-byte boundary."""
@@ -104,14 +127,14 @@ def _npad(n):
 
 def _join_handle(stream):
     """cudaStream_t of the stream that receives the parameter-gradient kernels (None: the current one)."""
-    if stream is None or os.environ.get('STOVE_NO_FORK'):
+    if stream is None or not _FORK:
         return None
     return stream.cuda_stream
 
 
 def _keep_for(stream, *tensors):
     """Kernels joined into `stream` still read / write these after the calling node returns."""
-    if stream is None or os.environ.get('STOVE_NO_FORK'):
+    if stream is None or not _FORK:
         return
     for t in tensors:
         if t is not None:
@@ -345,7 +368,7 @@ _AUX_STREAMS = {}
 
 def _aux_stream(device):
     """Library-wide side stream (per device) for work that is off the critical chain of a backward pass."""
-    if os.environ.get('STOVE_NO_FORK'):              # serial execution (per-kernel timing passes)
+    if not _FORK:                                    # serial execution (per-kernel timing passes)
         return torch.cuda.current_stream(device)
     key = (device.type, device.index)
     if key not in _AUX_STREAMS:
@@ -381,7 +404,7 @@ class LstmEncoder(torch.autograd.Function):
         return wih_pl, whh_pl, whhT_pl, bias, done
 
     @staticmethod
-    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None, prepared=None):
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None, prepared=None, x_pl=None):
         """With the head parameters (fc1 / fc2 of encoder.py:53-56) the node returns fc2(sigmoid(fc1(h_t)))
         (n, steps, P) instead of h_t: one autograd node for the whole recognition network, whose backward
         runs every parameter-gradient kernel (head, W_hh, biases) beside the chain h_t -> h_{t-1}."""
@@ -394,8 +417,10 @@ class LstmEncoder(torch.autograd.Function):
             prepared = LstmEncoder.prepare(w_ih, w_hh, b_ih, b_hh)
         wih_pl, whh_pl, whhT_pl, bias, done = prepared
         x = x.contiguous()
-        x_pl, _ = split_planes(x)                          # the transposed planes (right operand of g^T x) are only
-        # needed by the backward pass, which builds them off the chain
+        if x_pl is None:                                   # (bw_transform can emit the planes in its own pass)
+            x_pl, _ = split_planes(x)
+        # the transposed planes (right operand of g^T x) are only needed by the backward pass, which builds them
+        # off the chain
         cur.wait_event(done)
         for t_ in (wih_pl, whh_pl, whhT_pl, bias):
             t_.record_stream(cur)
@@ -520,7 +545,7 @@ class LstmEncoder(torch.autograd.Function):
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
                 t_.record_stream(cur)
-        return (None, g_wih, g_whh, g_b, g_b, None) + g_head + (None,)
+        return (None, g_wih, g_whh, g_b, g_b, None) + g_head + (None, None)
 
 
 def _head_fwd(x2, w1, b1, w2, b2):

@@ -41,8 +41,10 @@ class RnnStates(nn.Module):
         # is dropped by `forward`
         self._prepared = (tuple(w._version for w in ws), ops.LstmEncoder.prepare(*ws))
 
-    def forward(self, frames):
-        """frames (N, c, w, h) -> (N, O, 8): means and raw stds of (sx, sy/sx, x, y)."""
+    def forward(self, frames, planes=None):
+        """frames (N, c, w, h) -> (N, O, 8): means and raw stds of (sx, sy/sx, x, y).  `planes` (optional): the
+        (hi, lo) TF32 operand planes (2, N, c*w*h) of the flattened frames when a producer already wrote them
+        (ops.bw_transform)."""
         x = frames.flatten(start_dim=1)
         rnn = self.rnn
         # one fused autograd node (ops.LstmEncoder) for LSTM + head
@@ -54,4 +56,4 @@ class RnnStates(nn.Module):
                 prepared = None
         return ops.LstmEncoder.apply(x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0,
                                      self.c.num_obj, self.fc1.weight, self.fc1.bias, self.fc2.weight,
-                                     self.fc2.bias, prepared)
+                                     self.fc2.bias, prepared, planes)

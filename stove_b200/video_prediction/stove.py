@@ -228,7 +228,7 @@ class Stove(nn.Module):
         return patches.mean((-1, -2)).view(*z.shape[:-1], 3)
 
     # -- sequence ELBO ----------------------------------------------------------------------------
-    def stove_forward(self, x, actions=None, x_color=None):
+    def stove_forward(self, x, actions=None, x_color=None, x_planes=None):
         c = self.c
         n, T = x.shape[0], x.shape[1]
         skip, cl, O = c.skip, c.cl, c.num_obj
@@ -243,7 +243,7 @@ class Stove(nn.Module):
         forked.record(cur)
 
         # encoder -> (constrain, match, smooth, velocities) in one kernel (csrc/glue.cu)
-        zp = self.sup.encoder(x.flatten(end_dim=1)).view(n, T, O, 8)
+        zp = self.sup.encoder(x.flatten(end_dim=1), planes=x_planes).view(n, T, O, 8)
 
         pack_stream.wait_event(forked)
         with torch.cuda.stream(pack_stream):
@@ -349,14 +349,23 @@ class Stove(nn.Module):
         self.step_counter = step_counter
         self.sup.step_counter = step_counter
         self.dyn.step_counter = step_counter
-        x_color = x
+        x_color, x_planes = x, None
         if not pretrain:
             self.sup.encoder.prepare()          # frame-independent encoder work, off the chain (side stream)
         if self.c.debug_bw:
-            x = bw_transform(x)
+            # one pass: channel sum + clamp (uint8 frames are scaled by 1/255 here) and, for the sequence model,
+            # the TF32 operand planes of the frames for the recognition LSTM's input GEMM
+            if pretrain or not x.is_cuda:
+                x = bw_transform(x)
+            else:
+                x, x_planes = ops.bw_transform(x, want_planes=True)
+        elif x.dtype == torch.uint8:
+            x = x.float() / 255
         if pretrain:
             elbo, prop_dict = self.sup(x)
             return elbo, prop_dict, 0
         if self.c.debug_core_appearance or self.c.debug_match_appearance:
-            return self.stove_forward(x, actions=actions, x_color=x_color)
-        return self.stove_forward(x, actions=actions)
+            if x_color.dtype == torch.uint8:
+                x_color = x_color.float() / 255
+            return self.stove_forward(x, actions=actions, x_color=x_color, x_planes=x_planes)
+        return self.stove_forward(x, actions=actions, x_planes=x_planes)

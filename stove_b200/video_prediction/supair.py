@@ -68,7 +68,7 @@ class Supair(nn.Module):
         short, latency-bound launches that leave most SMs idle on their own.  autograd replays
         each op's backward on the stream of its forward, so the two backward chains overlap too;
         a CUDA-graph capture records the fork/join as parallel branches."""
-        if os.environ.get('STOVE_NO_FORK'):          # serial execution (per-kernel timing passes)
+        if not ops.fork_enabled():                   # serial execution (per-kernel timing passes)
             return torch.cuda.current_stream(device)
         cache = self.__dict__.setdefault('_streams', {})
         # 'bg' carries kernels the main chain waits for: same priority as the caller's stream; the others

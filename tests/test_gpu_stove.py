@@ -11,19 +11,32 @@ pytestmark = pytest.mark.gpu
 VAL, GRAD = 3e-5, 3e-4
 
 
-# alternative code paths of the dynamics-loop kernels (csrc/dynloop.cu), selected by environment
-# variables read at call time: one warp per sequence instead of two, backward recomputing each step
+# alternative code paths of the dynamics-loop kernels (csrc/dynloop.cu), selected through the library's
+# option API (stove_set_option): one warp per sequence instead of two, backward recomputing each step
 # instead of reloading the activations kept by the forward pass, the generic CTA-wide kernels
-ALT_PATHS = {'ac@nw1': {'STOVE_DYNLOOP_NW': '1', 'STOVE_ROLLOUT_NW': '1'},
-             'ac@recompute': {'STOVE_DYNLOOP_RECOMPUTE': '1'},
-             'plain@nw1_recompute': {'STOVE_DYNLOOP_NW': '1', 'STOVE_DYNLOOP_RECOMPUTE': '1'},
-             'plain@generic': {'STOVE_DYNLOOP_GENERIC': '1'}}
+ALT_PATHS = {'ac@nw1': {'dynloop_nw': 1, 'rollout_nw': 1},
+             'ac@recompute': {'dynloop_recompute': 1},
+             'plain@nw1_recompute': {'dynloop_nw': 1, 'dynloop_recompute': 1},
+             'plain@generic': {'dynloop_generic': 1}}
+
+
+@pytest.fixture
+def options():
+    """set library options for one test, restore them afterwards"""
+    from stove_b200 import _native as N
+    saved = []
+
+    def apply(opts):
+        for k, v in opts.items():
+            saved.append((k, N.set_option(k, v)))
+    yield apply
+    for k, v in reversed(saved):
+        N.set_option(k, v)
 
 
 @pytest.mark.parametrize('tag', list(VARIANTS) + list(ALT_PATHS))
-def test_stove_golden(tag, monkeypatch):
-    for k, v in ALT_PATHS.get(tag, {}).items():
-        monkeypatch.setenv(k, v)
+def test_stove_golden(tag, options):
+    options(ALT_PATHS.get(tag, {}))
     tag = tag.split('@')[0]
     kw, seed = VARIANTS[tag]
     g = load_golden('stove_' + tag)

@@ -136,6 +136,7 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'train_seqs_per_sec' and d['unit'] == 'sequences/s'
     assert d['value'] > 0 and d['higher_is_better'] is True and d['n_gpus'] == 1
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    from oracle import ref_harness as rh
+    assert d['cpu_baseline']['kind'] == ('reference' if rh.available() else 'port') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and 'model' not in d['config']
