@@ -749,9 +749,14 @@ def dp_gradient_check(model, dev, world, rank):
             return self.d.pop(0)
 
     eng = dp.DataParallel(model, broadcast=False)
-    model._standard_normal = Replay(rank * n_loc, (rank + 1) * n_loc)
-    eng.forward_backward(full[rank * n_loc:(rank + 1) * n_loc], 1)
-    sharded = eng.flat.clone()
+    shard = full[rank * n_loc:(rank + 1) * n_loc]
+    flats = []
+    for _ in range(3):                 # pass 1: one all-reduce of the whole bucket; passes 2, 3: overlapped pieces
+        model._standard_normal = Replay(rank * n_loc, (rank + 1) * n_loc)
+        eng.forward_backward(shard, 1)
+        flats.append(eng.flat.clone())
+    sharded = flats[-1]
+    piecewise_vs_whole = float((flats[-1] - flats[0]).abs().max() / flats[0].abs().max())
     model._standard_normal = Replay(0, n_loc * world)
     for p in eng.params:
         p.grad = None
@@ -760,10 +765,14 @@ def dp_gradient_check(model, dev, world, rank):
     del model._standard_normal
     ref = torch.cat([p.grad.reshape(-1) for p in eng.live])
     err = float((sharded - ref).abs().max() / ref.abs().max())
-    t = torch.tensor([err], device=dev)
+    t = torch.tensor([err, piecewise_vs_whole], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {'max_rel_err': float(t), 'tolerance': 1e-4, 'ok': float(t) < 1e-4,
-            'what': 'flat gradient after all-reduce of %d-sequence shards vs. one rank on the %d-sequence batch' % (n_loc, n_loc * world)}
+    err, piecewise_vs_whole = float(t[0]), float(t[1])
+    return {'max_rel_err': err, 'tolerance': 1e-4, 'ok': err < 1e-4 and piecewise_vs_whole < 1e-5,
+            'overlapped_vs_single_allreduce': piecewise_vs_whole, 'overlap_active': eng._overlap is not None,
+            'what': 'flat gradient after the (overlapped, piecewise) all-reduce of %d-sequence shards vs. one rank on the '
+                    '%d-sequence batch' % (n_loc, n_loc * world)}
+
 
 
 def kernel_roofline(kernel, times, n_steps, pk, brief=False):

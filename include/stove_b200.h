@@ -209,6 +209,9 @@ typedef struct {
     int32_t reward;       /* 1 = reward head present */
     int32_t lim_enc;      /* raw pass-through dims (2) */
     int32_t nonlin;       /* 0 = leaky_relu(0.01) (reference default), 1 = elu */
+    int32_t state_dim;    /* width of the state rows fed to the encoder; 0 = cl/2 (the STOVE model).  Other
+                           * values (supairvised/dynamics.py:24-25: enc_input_size 16 with lim_enc 4) are
+                           * served by the single-step kernels stove_gnn_fwd / stove_gnn_bwd only */
 } stove_gnn_cfg;
 
 int64_t stove_gnn_weight_count(const stove_gnn_cfg* cfg);
@@ -218,7 +221,7 @@ int64_t stove_gnn_weight_count(const stove_gnn_cfg* cfg);
  * Returns the number of entries written (39). */
 int stove_gnn_weight_offsets(const stove_gnn_cfg* cfg, int32_t* out, int max_out);
 size_t stove_gnn_bwd_workspace(const stove_gnn_cfg* cfg, int64_t n);
-/* s [n][O][cl/2], actions [n][A] or NULL, app [n][O][app_dim] or NULL
+/* s [n][O][state_dim or cl/2], actions [n][A] or NULL, app [n][O][app_dim] or NULL
  * -> out [n][O][cl], reward [n] (sigmoid applied; NULL if no reward head) */
 int stove_gnn_fwd(const stove_gnn_cfg* cfg, int64_t n, const float* s, const float* actions,
                   const float* app, const float* weights, float* out, float* reward, void* stream);
@@ -317,10 +320,6 @@ int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int
                        void* workspace, void* stream, void* wgrad_stream);
 /* floats of the optional activation buffer `xrec` (0: this shape has no such path) */
 int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, int skip);
-int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
-                      const stove_dynloop_io* io, const float* weights, float* g_weights,
-                      void* workspace, void* stream);
-
 /* ------------------------------------------------------------------------------------
  * z of every scored frame and the ELBO assembly of Stove.stove_forward (stove.py:731-748,
  * supair.py:84-110, Supair.sy_from_quotient supair.py:151-158).
@@ -414,9 +413,10 @@ int stove_enc_head_bwd_params(int64_t R, int K, int J, int P, const float* x, co
 
 /* Gather `count` device tensors into one flat fp32 buffer (the data-parallel gradient bucket):
  * dst[offsets[i] .. offsets[i] + numels[i]) = srcs[i][0 .. numels[i]).  srcs / offsets / numels are HOST
- * arrays (device addresses travel as kernel parameters: capturable, no table upload). */
+ * arrays (device addresses travel as kernel parameters: capturable, no table upload).  Every value is
+ * multiplied by `scale` on the way (1 / world size folds the averaging of the all-reduce into the gather). */
 int stove_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* numels, int count,
-                      float* dst, void* stream);
+                      float* dst, float scale, void* stream);
 
 /* Optimizer step of the reference trainer on the flat gradient bucket (train.py:46-49 Adam with amsgrad,
  * :471-473 clip_grad_norm_(parameters, max_norm) then step).  params / offsets / numels are HOST arrays

@@ -34,7 +34,7 @@ class SupCfg(C.Structure):
 
 class GnnCfg(C.Structure):
     _fields_ = [('num_obj', i32), ('cl', i32), ('action_dim', i32), ('app_dim', i32),
-                ('reward', i32), ('lim_enc', i32), ('nonlin', i32)]
+                ('reward', i32), ('lim_enc', i32), ('nonlin', i32), ('state_dim', i32)]
 
 
 class FuseCfg(C.Structure):
@@ -107,7 +107,7 @@ SIGNATURES = {
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
     'stove_enc_head_bwd_data': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp]),
     'stove_enc_head_bwd_params': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 8 + [vp]),
-    'stove_gather_flat': (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    'stove_gather_flat': (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_float, vp]),
     'stove_adam_workspace_floats': (C.c_int, []),
     'stove_adam_step': (C.c_int, [vp, vp, vp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp]),
     'stove_gnn_weight_count': (i64, [PG]),
@@ -121,7 +121,6 @@ SIGNATURES = {
     'stove_dynloop_bwd_workspace': (sz, [PG, i64, C.c_int, C.c_int]),
     'stove_dynloop_bwd2': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp, vp]),
     'stove_dynloop_xrec_floats': (i64, [PG, i64, C.c_int, C.c_int]),
-    'stove_dynloop_bwd': (C.c_int, [PG, C.POINTER(FuseCfg), i64, C.POINTER(DynloopIO), vp, vp, vp, vp]),
     'stove_zall_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
     'stove_zall_bwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     'stove_elbo_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int, f32] + [vp] * 8 + [vp]),

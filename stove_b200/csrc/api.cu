@@ -256,7 +256,7 @@ struct GatherArgs {
     int64_t num[GATHER_MAX];
 };
 
-__global__ void gather_flat_kernel(const __grid_constant__ GatherArgs a, float* __restrict__ dst) {
+__global__ void gather_flat_kernel(const __grid_constant__ GatherArgs a, float* __restrict__ dst, float scale) {
     const int t = blockIdx.y;
     const int64_t num = a.num[t];
     const int64_t lo = (int64_t)blockIdx.x * GATHER_CHUNK;
@@ -266,16 +266,19 @@ __global__ void gather_flat_kernel(const __grid_constant__ GatherArgs a, float* 
     float* __restrict__ d = dst + a.off[t];
     if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
         const int64_t v_hi = lo + ((hi - lo) & ~(int64_t)3);
-        for (int64_t i = lo + 4 * threadIdx.x; i < v_hi; i += 4 * blockDim.x)
-            *reinterpret_cast<float4*>(d + i) = __ldg(reinterpret_cast<const float4*>(s + i));
-        for (int64_t i = v_hi + threadIdx.x; i < hi; i += blockDim.x) d[i] = __ldg(s + i);
+        for (int64_t i = lo + 4 * threadIdx.x; i < v_hi; i += 4 * blockDim.x) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(s + i));
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;      // scale = 1 is exact
+            *reinterpret_cast<float4*>(d + i) = v;
+        }
+        for (int64_t i = v_hi + threadIdx.x; i < hi; i += blockDim.x) d[i] = __ldg(s + i) * scale;
     } else {
-        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = __ldg(s + i);
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) d[i] = __ldg(s + i) * scale;
     }
 }
 
 extern "C" int stove_gather_flat(const void* const* srcs, const int64_t* offsets, const int64_t* numels, int count,
-                                 float* dst, void* stream) {
+                                 float* dst, float scale, void* stream) {
     STOVE_CHECK_ARG(count >= 0 && (count == 0 || (srcs && offsets && numels && dst)), "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     // two classes so that a few large tensors do not force thousands of empty CTAs on the small ones
@@ -286,7 +289,7 @@ extern "C" int stove_gather_flat(const void* const* srcs, const int64_t* offsets
         auto flush = [&]() -> int {
             if (k == 0) return STOVE_OK;
             const dim3 grid((unsigned)((mx + GATHER_CHUNK - 1) / GATHER_CHUNK), (unsigned)k);
-            STOVE_KERNEL(K_GATHER_FLAT, st, gather_flat_kernel<<<grid, 256, 0, st>>>(a, dst));
+            STOVE_KERNEL(K_GATHER_FLAT, st, gather_flat_kernel<<<grid, 256, 0, st>>>(a, dst, scale));
             STOVE_LAUNCH_CHECK();
             k = 0;
             mx = 0;

@@ -1208,7 +1208,7 @@ static void build_tables(const stove_gnn_cfg* c, const GnnLayout& L, TW* tw, Sta
 }
 
 static bool supported(const stove_gnn_cfg* c, const GnnLayout& L) {
-    return c->num_obj == O && c->cl == CL && L.in_dim <= IN_MAX && c->action_dim <= A_MAX &&
+    return c->num_obj == O && c->cl == CL && gnn_default_state(c) && L.in_dim <= IN_MAX && c->action_dim <= A_MAX &&
            !stove_opt(OPT_DYNLOOP_GENERIC);
 }
 
@@ -1241,6 +1241,7 @@ static int dynloop_check(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, i
                          const float* weights) {
     int rc = gnn_check(cfg);
     if (rc) return rc;
+    STOVE_CHECK_ARG(gnn_default_state(cfg), "state_dim != cl/2 is served by stove_gnn_fwd / stove_gnn_bwd only");
     STOVE_CHECK_ARG(fuse && io && weights && n >= 0, "null pointer");
     STOVE_CHECK_ARG(io->T > io->skip && io->skip >= 1, "need T > skip >= 1");
     STOVE_CHECK_ARG(io->z_init && io->sup && io->sup_std && io->eps && io->z, "null tensor in stove_dynloop_io");
@@ -1375,16 +1376,6 @@ extern "C" int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n
     GnnLayout L = gnn_layout(cfg);
     if (!tk::supported(cfg, L) || stove_opt(OPT_DYNLOOP_RECOMPUTE)) return 0;
     return (int64_t)n * (T - skip) * tk::BwdLay::XREC;
-}
-
-extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
-                                  const stove_dynloop_io* io, const float* weights, float* g_weights,
-                                  void* workspace, void* stream, void* wgrad_stream);
-
-extern "C" int stove_dynloop_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,
-                                 const stove_dynloop_io* io, const float* weights, float* g_weights,
-                                 void* workspace, void* stream) {
-    return stove_dynloop_bwd2(cfg, fuse, n, io, weights, g_weights, workspace, stream, stream);
 }
 
 extern "C" int stove_dynloop_bwd2(const stove_gnn_cfg* cfg, const stove_fuse_cfg* fuse, int64_t n,

@@ -318,7 +318,7 @@ __device__ void gnn_forward_core(const stove_gnn_cfg& c, const GnnLayout& L, con
         for (int it = tid; it < nseq * O * 4; it += nt) {
             const int sq = it / (O * 4), n = it - sq * (O * 4);
             const int o = n >> 2, e = n & 3;
-            sm[b.sin + (cl / 2 + e) * b.ldo + sq * O + o] = sm[b.emb + n * b.lds + sq];
+            sm[b.sin + (gnn_sdim(c) + e) * b.ldo + sq * O + o] = sm[b.emb + n * b.lds + sq];
         }
         __syncthreads();
     }
@@ -415,7 +415,7 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ weights,
 __device__ __forceinline__ void load_inputs(const stove_gnn_cfg& c, const GnnBuf& b, float* sm, int64_t seq0,
                                             int nseq, const float* __restrict__ s, int sdim, int soff,
                                             const float* __restrict__ app) {
-    const int cl = c.cl, O = c.num_obj, half = cl / 2;
+    const int O = c.num_obj, half = gnn_sdim(c);
     for (int it = threadIdx.x; it < nseq * O * half; it += blockDim.x) {
         const int row = it / half, k = it - row * half;
         sm[b.sin + k * b.ldo + row] = __ldg(s + (seq0 * O + row) * sdim + soff + k);
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(256) gnn_fwd_kernel(stove_gnn_cfg c, GnnLayout
         const int64_t seq0 = grp * seq;
         const int nseq = (int)min((int64_t)seq, n - seq0);
         __syncthreads();
-        load_inputs(c, b, sm, seq0, nseq, s, cl / 2, 0, app);
+        load_inputs(c, b, sm, seq0, nseq, s, gnn_sdim(c), 0, app);
         __syncthreads();
         gnn_forward_core(c, L, b, Ws, sm, nseq, actions ? actions + seq0 * c.action_dim : nullptr, c.action_dim);
         for (int it = threadIdx.x; it < nseq * O * cl; it += blockDim.x) {
@@ -720,7 +720,7 @@ __device__ void gnn_backward_core(const stove_gnn_cfg& c, const GnnLayout& L, co
         // emb = act_W^T a + b ; g_emb[o*4+e][seq] = g_sin[half+e][seq*O+o]
         for (int it = tid; it < nseq * O * 4; it += nt) {
             const int sq = it / (O * 4), nn = it - sq * (O * 4);
-            sm[b.g_emb + nn * b.lds + sq] = sm[b.g_sin + (half + (nn & 3)) * b.ldo + sq * O + (nn >> 2)];
+            sm[b.g_emb + nn * b.lds + sq] = sm[b.g_sin + (gnn_sdim(c) + (nn & 3)) * b.ldo + sq * O + (nn >> 2)];
         }
         __syncthreads();
         const int NA = O * 4;
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout
     const GnnBuf b = gnn_buffers(c, L.in_dim, seq, true);
     for (int i = threadIdx.x; i < b.total; i += blockDim.x) sm[i] = 0.f;
     float* slab = slabs + (int64_t)blockIdx.x * L.total;
-    const int cl = c.cl, O = c.num_obj, nl = c.nonlin, half = cl / 2;
+    const int cl = c.cl, O = c.num_obj, nl = c.nonlin, half = gnn_sdim(c);
     const int tid = threadIdx.x, nt = blockDim.x;
     const int64_t ngroups = (n + seq - 1) / seq;
     bool accum = false;
@@ -1156,6 +1156,7 @@ extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
                                  const stove_dynstep_io* io, const float* weights, void* stream) {
     int rc = gnn_check(cfg);
     if (rc) return rc;
+    STOVE_CHECK_ARG(gnn_default_state(cfg), "state_dim != cl/2 is served by stove_gnn_fwd / stove_gnn_bwd only");
     STOVE_CHECK_ARG(fuse && io && weights && n >= 0, "null pointer");
     STOVE_CHECK_ARG(io->z_prev && io->sup && io->sup_std && io->eps && io->z_out && io->z_dyn && io->z_dyn_std &&
                         io->logq && io->trans, "null tensor in stove_dynstep_io");
@@ -1184,6 +1185,7 @@ extern "C" int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
                                  int first, int last, void* workspace, void* stream) {
     int rc = gnn_check(cfg);
     if (rc) return rc;
+    STOVE_CHECK_ARG(gnn_default_state(cfg), "state_dim != cl/2 is served by stove_gnn_fwd / stove_gnn_bwd only");
     STOVE_CHECK_ARG(fuse && io && weights && g_weights && workspace && n >= 0, "null pointer");
     STOVE_CHECK_ARG(io->z_prev && io->sup && io->sup_std && io->eps && io->g_z_prev && io->g_sup && io->g_sup_std,
                     "null tensor in stove_dynstep_io");
@@ -1216,6 +1218,7 @@ extern "C" int stove_gnn_rollout(const stove_gnn_cfg* cfg, int64_t n, int num, c
                                  float* rewards, void* stream) {
     int rc = gnn_check(cfg);
     if (rc) return rc;
+    STOVE_CHECK_ARG(gnn_default_state(cfg), "state_dim != cl/2 is served by stove_gnn_fwd / stove_gnn_bwd only");
     STOVE_CHECK_ARG(n >= 0 && num >= 0 && z_last && weights && z_out, "null pointer");
     STOVE_CHECK_ARG(((uintptr_t)weights & 15) == 0, "weights must be 16-byte aligned");
     STOVE_CHECK_ARG((cfg->action_dim > 0) == (actions != nullptr), "actions do not match cfg.action_dim");

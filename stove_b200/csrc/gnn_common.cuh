@@ -16,11 +16,13 @@ struct GnnLayout {
 };
 
 static inline int pad4(int v) { return (v + 3) / 4 * 4; }
+// width of the state rows: cl/2 for the STOVE model, enc_input_size for the supervised ablation
+__host__ __device__ static inline int gnn_sdim(const stove_gnn_cfg& c) { return c.state_dim > 0 ? c.state_dim : c.cl / 2; }
 
 static inline GnnLayout gnn_layout(const stove_gnn_cfg* c) {
     GnnLayout L;
     const int cl = c->cl, O = c->num_obj;
-    L.in_dim = cl / 2 + (c->action_dim > 0 ? 4 : 0) + c->app_dim;
+    L.in_dim = gnn_sdim(*c) + (c->action_dim > 0 ? 4 : 0) + c->app_dim;
     int at = 0;
     auto seg = [&](int& w, int& b, int K, int N) {
         w = at; at += pad4(K * N);
@@ -88,11 +90,15 @@ static inline FuseCfg make_fuse(const stove_gnn_cfg* cfg, const stove_fuse_cfg* 
     return f;
 }
 
+// the loop / rollout kernels integrate the state themselves: they need the STOVE state layout
+static inline bool gnn_default_state(const stove_gnn_cfg* c) { return c->state_dim == 0 || c->state_dim == c->cl / 2; }
+
 static inline int gnn_check(const stove_gnn_cfg* c) {
     STOVE_CHECK_ARG(c, "null cfg");
     STOVE_CHECK_ARG(c->num_obj > 0 && c->num_obj <= 16, "num_obj out of range");
     STOVE_CHECK_ARG(c->cl >= 8 && c->cl % 8 == 0 && c->cl <= 64, "cl must be a multiple of 8 in [8, 64]");
-    STOVE_CHECK_ARG(c->action_dim >= 0 && c->app_dim >= 0 && c->lim_enc >= 0 && c->lim_enc <= c->cl / 2, "bad cfg");
+    STOVE_CHECK_ARG(c->state_dim >= 0 && c->state_dim <= c->cl, "state_dim must be in [0, cl]");
+    STOVE_CHECK_ARG(c->action_dim >= 0 && c->app_dim >= 0 && c->lim_enc >= 0 && c->lim_enc <= gnn_sdim(*c), "bad cfg");
     return STOVE_OK;
 }
 

@@ -36,7 +36,7 @@ class DataParallel:
     """Minimal DP engine around a `Stove` replica: zero_grad -> forward -> backward ->
     flat-bucket all-reduce (-> clip -> optimizer step)."""
 
-    def __init__(self, model, reward_factor=None, broadcast=True, mse=None):
+    def __init__(self, model, reward_factor=None, broadcast=True, mse=None, overlap=True):
         """reward_factor / mse default to the model config's debug_reward_factor / debug_mse (train.py:205-208,
         :463).  The ramp-up weight min(1, step / debug_reward_rampup) (train.py:458-462) is a DEVICE scalar,
         `self.reward_weight`, refreshed by `set_reward_weight(step)` so that a captured graph replays it."""
@@ -47,6 +47,8 @@ class DataParallel:
         self.mse = bool(getattr(c, 'debug_mse', False)) if mse is None else mse
         self.rampup = getattr(c, 'debug_reward_rampup', False)
         self.reward_weight = None
+        self.overlap = overlap          # R > 1 on CUDA: exchange the bucket in pieces under the backward pass
+        self._overlap = None
         self.flat = None
         self.live = None
         if broadcast and world() > 1:
@@ -57,6 +59,8 @@ class DataParallel:
     def forward_backward(self, x, step_counter=1, actions=None, reward_target=None):
         for p in self.params:
             p.grad = None
+        if self._overlap is not None:
+            self._overlap.begin()
         elbo, prop, rewards = self.model(x, step_counter, actions=actions)
         if reward_target is not None and self.reward_factor:
             # train.py:452-465: reward_target = present_rewards[:, skip:] (the caller slices), both flattened
@@ -91,18 +95,35 @@ class DataParallel:
             cache[key] = torch.full((), -1.0, device=like.device, dtype=like.dtype)
         return cache[key]
 
+    # -- gradient exchange -----------------------------------------------------------------------------
     def all_reduce_gradients(self):
         """Average the gradients over ranks through one flat bucket; afterwards every `p.grad`
-        is a view into that bucket (`self.flat`)."""
+        is a view into that bucket (`self.flat`).
+
+        One rank / CPU tensors / the first pass: gather everything, one all-reduce (the 1 / R of the average is
+        folded into the gather).  Later CUDA passes with R > 1 exchange the bucket in pieces WHILE the backward
+        pass is still running (`_Overlap`): what was already sent is skipped here."""
         live = [p for p in self.params if p.grad is not None]
-        if live[0].grad.is_cuda:
-            from . import ops
-            flat = ops.gather_flat([p.grad for p in live])      # one or two launches instead of a 110-way cat
+        R = world()
+        ov = self._overlap
+        if ov is not None and ov.active:
+            flat = ov.finish(live)
         else:
-            flat = torch.cat([p.grad.reshape(-1) for p in live])
-        if world() > 1:
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world())
+            if R > 1 and live[0].grad.is_cuda and self.overlap and ov is None:
+                # the set of parameters that receive gradients is known now: fix the bucket layout of the
+                # overlapped exchange (used from the next pass on) and use the same order for this pass
+                ov = self._overlap = _Overlap(self, live)
+            if ov is not None:
+                live = list(ov.order)
+            if live[0].grad.is_cuda:
+                from . import ops
+                flat = ops.gather_flat([p.grad for p in live], scale=1.0 / R)   # one or two launches, not a 110-way cat
+            else:
+                flat = torch.cat([p.grad.reshape(-1) for p in live])
+                if R > 1:
+                    flat.mul_(1.0 / R)
+            if R > 1:
+                dist.all_reduce(flat)
         at = 0
         for p in live:
             n = p.numel()
@@ -124,6 +145,124 @@ class DataParallel:
             total = self.flat.norm()
             self.flat.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
         optimizer.step()
+
+
+class _Overlap:
+    """Piecewise exchange of the flat gradient bucket under the backward pass (R > 1, CUDA).
+
+    Bucket order: [early | encoder rest | W_ih rows].  `early` = every parameter outside the recognition network
+    (SPN, GNN): their gradients are complete long before the LSTM backward ends; a post-accumulate hook counts
+    them in and the last one starts gather + all-reduce of that range on the communication stream.  The
+    recognition network hands its gradients over from inside its backward node (ops.LstmEncoder.grad_sink): head,
+    W_hh and biases first, then W_ih in two row blocks, each sent while the next GEMM runs.  Whatever did not
+    arrive through a hook or the sink is exchanged at the end (`finish`).  Works eagerly and under CUDA-graph
+    capture (the communication stream forks from / joins the producing streams through events)."""
+
+    def __init__(self, engine, live):
+        from . import ops
+        self.ops = ops
+        self.engine = engine
+        self.R = world()
+        enc = getattr(getattr(engine.model, 'sup', None), 'encoder', None)
+        names = {}
+        if enc is not None and hasattr(enc, 'rnn'):
+            names = {'w_hh': enc.rnn.weight_hh_l0, 'b_ih': enc.rnn.bias_ih_l0, 'b_hh': enc.rnn.bias_hh_l0,
+                     'w1': enc.fc1.weight, 'b1': enc.fc1.bias, 'w2': enc.fc2.weight, 'b2': enc.fc2.bias,
+                     'w_ih': enc.rnn.weight_ih_l0}
+        live_ids = {id(p) for p in live}
+        self.by_name = {k: p for k, p in names.items() if id(p) in live_ids}
+        enc_ids = {id(p) for p in self.by_name.values()}
+        early = [p for p in live if id(p) not in enc_ids]
+        rest = [p for k, p in self.by_name.items() if k != 'w_ih']
+        last = [self.by_name['w_ih']] if 'w_ih' in self.by_name else []
+        self.order = early + rest + last                    # the bucket layout (== engine.live from now on)
+        self.offset, at = {}, 0
+        for p in self.order:
+            self.offset[id(p)] = at
+            at += p.numel()
+        self.total = at
+        self.early, self.n_early = early, sum(p.numel() for p in early)
+        dev = live[0].device
+        self.comm = torch.cuda.Stream(device=dev, priority=-1)
+        self.flat = None
+        self.active = False
+        self.pending, self.queue, self.sent = 0, [], set()
+        for p in early:
+            p.register_post_accumulate_grad_hook(self._early_hook)
+
+    # -- per pass ---------------------------------------------------------------------------------------
+    def begin(self):
+        dev = self.order[0].device
+        self.flat = torch.empty(self.total, device=dev, dtype=torch.float32)
+        self.pending, self.queue, self.sent = len(self.early), [], set()
+        self.active = True
+        self.ops.LstmEncoder.grad_sink = self
+
+    def _early_hook(self, p):
+        if not self.active:
+            return
+        # the hook runs on the stream that produced this gradient: the exchange must wait for it
+        self.comm.wait_stream(torch.cuda.current_stream(p.device))
+        self.pending -= 1
+        if self.pending == 0:
+            self._send([(q.grad, self.offset[id(q)], q.numel()) for q in self.early], 0, self.n_early, wait=False)
+            self.sent.update(id(q) for q in self.early)
+
+    def __call__(self, name, tensor, row_lo=None, row_hi=None):       # ops.LstmEncoder.grad_sink
+        p = self.by_name.get(name)
+        if p is None or not self.active:
+            return
+        off = self.offset[id(p)]
+        if row_lo is None:
+            self.queue.append((tensor, off, p.numel()))
+            self.sent.add(id(p))
+        else:
+            cols = p.shape[1]
+            self.queue.append((tensor[row_lo:row_hi], off + row_lo * cols, (row_hi - row_lo) * cols))
+            if row_hi == p.shape[0]:
+                self.sent.add(id(p))
+
+    def flush(self):
+        if not self.queue:
+            return
+        lo = min(q[1] for q in self.queue)
+        hi = max(q[1] + q[2] for q in self.queue)
+        assert sum(q[2] for q in self.queue) == hi - lo, 'sink pieces must tile a contiguous bucket range'
+        self._send(self.queue, lo, hi)
+        self.queue = []
+
+    def _send(self, pieces, lo, hi, wait=True):
+        dev = self.flat.device
+        if wait:
+            self.comm.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.comm):
+            self.ops.gather_flat([t for t, _, _ in pieces], out=self.flat, offsets=[o for _, o, _ in pieces],
+                                 scale=1.0 / self.R)
+            dist.all_reduce(self.flat[lo:hi])
+        for t, _, _ in pieces:
+            t.record_stream(self.comm)
+
+    def finish(self, live):
+        """after the backward pass: send what is left, join the communication stream -> the flat bucket"""
+        self.ops.LstmEncoder.grad_sink = None
+        self.active = False
+        left = [p for p in self.order if id(p) not in self.sent]
+        cur = torch.cuda.current_stream(self.flat.device)
+        # contiguous runs of what is left
+        run = []
+        for p in left + [None]:
+            if run and (p is None or self.offset[id(p)] != self.offset[id(run[-1])] + run[-1].numel()):
+                lo = self.offset[id(run[0])]
+                hi = self.offset[id(run[-1])] + run[-1].numel()
+                self._send([(q.grad, self.offset[id(q)], q.numel()) for q in run], lo, hi)
+                run = []
+            if p is not None:
+                run.append(p)
+        cur.wait_stream(self.comm)
+        self.flat.record_stream(cur)
+        # the bucket order is the engine's `live` order from now on
+        live[:] = self.order
+        return self.flat
 
 
 class GraphedStep:

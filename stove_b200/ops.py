@@ -387,6 +387,21 @@ class LstmEncoder(torch.autograd.Function):
     step, then the two weight-gradient GEMMs (contractions over the frames, fed by the transposed planes the
     forward / cell kernels emit) as split-K launches with a fixed-order reduction."""
 
+    # data-parallel engines set this: an object with __call__(name, tensor, row_lo=None, row_hi=None) and flush();
+    # names: w_ih (possibly in row blocks), w_hh, b_ih, b_hh, w1, b1, w2, b2 (stove_b200.dp.DataParallel)
+    grad_sink = None
+
+    @staticmethod
+    def _recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt):
+        """W_hh and bias gradients on the current stream"""
+        H4 = 4 * H
+        if steps > 1:
+            tiles = (H4 // 128) * ((H + 127) // 128)
+            g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
+        else:
+            g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
+        return g_whh, sum_parts(bias_part)
+
     @staticmethod
     def prepare(w_ih, w_hh, b_ih, b_hh):
         """Operand planes of the weights and the summed bias, on the library's side stream.  They depend on the
@@ -521,27 +536,51 @@ class LstmEncoder(torch.autograd.Function):
                 # machine and the next cell kernel sums the parts
                 dh = tc3_gemm(g_pl, whhT_pl, parts=_split_k(((n + 127) // 128) * ((H + 127) // 128), H4 // 32))
                 g_c = g_c_prev
-        # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
-        # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands.
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            if steps > 1:
-                tiles = (H4 // 128) * ((H + 127) // 128)
-                g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
-            else:
-                g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
-            g_b = sum_parts(bias_part)
-        for t_ in (gT_all, hT_all, bias_part):
-            if t_ is not None:
-                t_.record_stream(side)
-        g_wih = None
-        if ctx.needs_input_grad[1]:
-            cur.wait_event(xT_ready)
-            xT_pl.record_stream(cur)
-            K = x.shape[1]
-            tiles = (H4 // 128) * ((K + 127) // 128)
-            g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
-        cur.wait_stream(side)                      # every gradient is ready on the node's stream when it returns
+        sink = LstmEncoder.grad_sink
+        K = x.shape[1]
+        if sink is None:
+            # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
+            # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands.
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                g_whh, g_b = LstmEncoder._recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt)
+            for t_ in (gT_all, hT_all, bias_part):
+                if t_ is not None:
+                    t_.record_stream(side)
+            g_wih = None
+            if ctx.needs_input_grad[1]:
+                cur.wait_event(xT_ready)
+                xT_pl.record_stream(cur)
+                tiles = (H4 // 128) * ((K + 127) // 128)
+                g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
+            cur.wait_stream(side)                  # every gradient is ready on the node's stream when it returns
+        else:
+            # data-parallel run: gradients are handed to the engine's sink the moment they exist, so their
+            # all-reduce overlaps what is still being computed.  These GEMMs are bound by L2 bandwidth, so running
+            # them one after the other costs nothing: W_hh / biases / head first, then W_ih in two halves -- the
+            # first half is on the wire while the second is computed; only the last 2 MB are exposed.
+            cur.wait_stream(side)                  # head gradients
+            g_whh, g_b = LstmEncoder._recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt)
+            sink('w_hh', g_whh)
+            sink('b_ih', g_b)
+            sink('b_hh', g_b)
+            for name, t_ in zip(('w1', 'b1', 'w2', 'b2'), g_head):
+                if t_ is not None:
+                    sink(name, t_)
+            sink.flush()
+            g_wih = None
+            if ctx.needs_input_grad[1]:
+                cur.wait_event(xT_ready)
+                xT_pl.record_stream(cur)
+                g_wih = torch.empty(H4, K, device=dev, dtype=dt)
+                half = (H4 // 2 + 127) // 128 * 128
+                for lo, hi in ((0, half), (half, H4)):
+                    if lo >= hi:
+                        continue
+                    tiles = ((hi - lo + 127) // 128) * ((K + 127) // 128)
+                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)), out=g_wih[lo:hi])
+                    sink('w_ih', g_wih, lo, hi)
+                    sink.flush()
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
                 t_.record_stream(cur)
@@ -608,25 +647,26 @@ class EncHead(torch.autograd.Function):
         return g_x.view(*ctx.lead, x2.shape[1]), g_w1, g_b1, g_w2, g_b2
 
 
-def gather_flat(tensors, out=None):
-    """Concatenate the flattened fp32 CUDA tensors into one flat buffer with one or two launches of the
-    library's gather kernel (the data-parallel gradient bucket).  Returns the flat tensor."""
+def gather_flat(tensors, out=None, offsets=None, scale=1.0):
+    """Copy the flattened fp32 CUDA tensors into one flat buffer with one or two launches of the library's gather
+    kernel (the data-parallel gradient bucket), multiplying by `scale` on the way.  `offsets` (floats, one per
+    tensor) places them inside `out`; default: back to back from 0.  Returns the flat tensor."""
     tensors = [t.contiguous() for t in tensors]
     N.require_cuda_f32(*tensors)
     numels = [t.numel() for t in tensors]
-    total = sum(numels)
+    if offsets is None:
+        offsets, at = [], 0
+        for m in numels:
+            offsets.append(at)
+            at += m
     if out is None:
-        out = torch.empty(total, device=tensors[0].device, dtype=tensors[0].dtype)
+        out = torch.empty(sum(numels), device=tensors[0].device, dtype=tensors[0].dtype)
     n = len(tensors)
     srcs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
-    offs, at = [], 0
-    for m in numels:
-        offs.append(at)
-        at += m
-    offsets = (C.c_int64 * n)(*offs)
+    offs = (C.c_int64 * n)(*offsets)
     nums = (C.c_int64 * n)(*numels)
-    N.check(N.lib().stove_gather_flat(C.cast(srcs, C.c_void_p), C.cast(offsets, C.c_void_p), C.cast(nums, C.c_void_p),
-                                      n, N.ptr(out), N.stream()))
+    N.check(N.lib().stove_gather_flat(C.cast(srcs, C.c_void_p), C.cast(offs, C.c_void_p), C.cast(nums, C.c_void_p),
+                                      n, N.ptr(out), float(scale), N.stream()))
     return out
 
 

@@ -17,10 +17,13 @@ class Dynamics(nn.Module):
         self.step_counter = 0
         self.prop_dict = {}
         cl = self.c.cl
-        if enc_input_size is not None and enc_input_size != cl // 2:
-            raise NotImplementedError('stove_b200.Dynamics: enc_input_size != cl//2 (supervised ablation) '
-                                      'is outside the fused kernel')
-        enc_in = cl // 2
+        # enc_input_size: width of the state rows `forward` receives (dynamics.py:24-26); the supervised
+        # ablation passes 16 with lim_enc = 4 (supairvised/dynamics.py:24-25, 75-77).  Any width up to cl runs
+        # through the single-step kernels; the fused loop / rollout kernels need the STOVE layout (cl // 2).
+        self.enc_input_size = cl // 2 if enc_input_size is None else int(enc_input_size)
+        if not 0 < self.enc_input_size <= cl:
+            raise ValueError('enc_input_size must be in (0, cl]')
+        enc_in = self.enc_input_size
         if self.c.action_conditioned:
             self.n_action_enc = 4
             self.action_embedding_layer = nn.Linear(self.c.action_space, self.c.num_obj * self.n_action_enc)
@@ -80,7 +83,8 @@ class Dynamics(nn.Module):
         nonlin = 1 if self.c.debug_nonlinear == 'leaky_relu' else 0     # inverted selector, dynamics.py:109
         return N.GnnCfg(self.c.num_obj, self.c.cl, self.c.action_space if with_actions else 0,
                         self.c.debug_appearance_dim if with_app else 0,
-                        1 if self.c.action_conditioned else 0, lim_enc, nonlin)
+                        1 if self.c.action_conditioned else 0, lim_enc, nonlin,
+                        0 if self.enc_input_size == self.c.cl // 2 else self.enc_input_size)
 
     def _segments(self, core_idx):
         """name -> (weight [out, in] or list of them to concatenate along out, bias)."""
@@ -111,7 +115,7 @@ class Dynamics(nn.Module):
 
     def _perm(self, cfg, core_idx, device):
         """Gather map raw-parameter-concat -> kernel layout ([in][out] matrices, padded)."""
-        key = (cfg.action_dim, cfg.app_dim, cfg.lim_enc, core_idx, str(device))
+        key = (cfg.action_dim, cfg.app_dim, cfg.lim_enc, cfg.state_dim, core_idx, str(device))
         if key in self._perm_cache:
             return self._perm_cache[key]
         off = ops.gnn_weight_offsets(cfg)
@@ -149,7 +153,7 @@ class Dynamics(nn.Module):
         with_actions = self.c.action_conditioned if with_actions is None else with_actions
         with_app = self.c.debug_core_appearance if with_app is None else with_app
         cfg = self.kernel_cfg(with_actions, with_app, lim_enc)
-        in_dim = self.c.cl // 2 + (4 if with_actions else 0) + (self.c.debug_appearance_dim if with_app else 0)
+        in_dim = self.enc_input_size + (4 if with_actions else 0) + (self.c.debug_appearance_dim if with_app else 0)
         if in_dim != self.state_enc.in_features:
             raise ValueError('dynamics input has %d features but state_enc expects %d (actions / '
                              'appearances must match the configuration)' % (in_dim, self.state_enc.in_features))
@@ -161,7 +165,7 @@ class Dynamics(nn.Module):
         return cfg, torch.cat(flat).index_select(0, perm)
 
     def forward(self, s, core_idx, actions=None, obj_appearances=None, lim_enc=2, packed=None):
-        """s (n, O, cl//2) -> (result (n, O, cl), reward (n, 1) | 0)   [dynamics.py:220-265]."""
+        """s (n, O, enc_input_size = cl//2) -> (result (n, O, cl), reward (n, 1) | 0)   [dynamics.py:220-265]."""
         if self.c.action_conditioned and actions is None:
             raise ValueError('action-conditioned dynamics needs actions')
         if packed is None:

@@ -62,3 +62,39 @@ def test_dynamics_batch_sizes_vs_oracle(n):
         if p.grad is not None:
             ck.close('g.' + name, p.grad, P['dyn.' + name].grad, GRAD)
     ck.finish()
+
+
+@pytest.mark.parametrize('cl,enc,lim,ac', [(16, 16, 4, False), (16, 16, 4, True), (32, 16, 2, False), (24, 20, 4, False)])
+def test_dynamics_parametric_shapes_vs_oracle(cl, enc, lim, ac):
+    """Other widths through the single-step kernels: the supervised ablation builds
+    Dynamics(config, enc_input_size=16) on cl = 16 and calls forward(..., lim_enc=4)
+    (supairvised/dynamics.py:24-25, 75-77)."""
+    from stove_b200 import Dynamics, StoveConfig
+    kw = dict(cl=cl, num_obj=3, width=32, height=32)
+    if ac:
+        kw.update(action_conditioned=True, action_space=9, debug_core_appearance=True)
+    else:
+        kw.update(action_conditioned=False, action_space=None)
+    torch.manual_seed(cl + enc)
+    dyn = Dynamics(StoveConfig(**kw), enc_input_size=enc).cuda()
+    oc = so.default_config(**kw)
+    P = {'dyn.' + k: v.detach().double().cpu().clone().requires_grad_(True) for k, v in dyn.state_dict().items()}
+    n = 77
+    gen = torch.Generator().manual_seed(n)
+    s = torch.rand(n, 3, enc, generator=gen, dtype=torch.float64) * 1.6 - 0.8
+    a = torch.nn.functional.one_hot(torch.randint(9, (n,), generator=gen), 9).double() if ac else None
+    app = torch.rand(n, 3, 3, generator=gen, dtype=torch.float64) if ac else None
+    so_s = s.clone().requires_grad_(True)
+    ro, rr = so.dynamics_forward(oc, P, so_s, 0, a, app, lim_enc=lim)
+    w = torch.sin(torch.arange(ro.numel(), dtype=torch.float64)).view_as(ro)
+    ((ro * w).sum() + (rr.sum() if ac else 0)).backward()
+    sg = s.float().cuda().requires_grad_(True)
+    out, rew = dyn(sg, 0, a.float().cuda() if ac else None, app.float().cuda() if ac else None, lim_enc=lim)
+    ((out * w.float().cuda()).sum() + (rew.sum() if ac else 0)).backward()
+    ck = Checker('dynamics_cl%d_enc%d' % (cl, enc))
+    ck.close('out', out, ro, VAL)
+    ck.close('gs', sg.grad, so_s.grad, GRAD)
+    for name, p in dyn.named_parameters():
+        if p.grad is not None:
+            ck.close('g.' + name, p.grad, P['dyn.' + name].grad, GRAD)
+    ck.finish()

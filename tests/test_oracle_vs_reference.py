@@ -77,3 +77,25 @@ def test_live_supair_only_elbo():
             assert P[name].grad is None, name
         else:
             assert rel_err(P[name].grad, p.grad) < 1e-9, name
+
+
+@pytest.mark.parametrize('cl,enc,lim', [(16, 16, 4), (32, 16, 2)])
+def test_live_dynamics_parametric_shapes(cl, enc, lim):
+    """Dynamics(config, enc_input_size) with lim_enc: the shape of the supervised ablation
+    (supairvised/dynamics.py:24-25, 75-77) through the unmodified reference class."""
+    import sys
+    rh._import()
+    from model.video_prediction.dynamics import Dynamics as RefDynamics
+    c = so.default_config(cl=cl)
+    rc = rh.reference_config(c)
+    with rh.default_dtype(D):
+        torch.manual_seed(cl + enc)
+        ref = RefDynamics(rc, enc).type(D)
+    P = {'dyn.' + k: v.detach().clone() for k, v in ref.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    s = torch.rand(6, 3, enc, generator=g, dtype=D) * 1.6 - 0.8
+    with rh.quiet(), rh.default_dtype(D):
+        out_r, rew_r = ref(s, 0, lim_enc=lim)
+    out_o, rew_o = so.dynamics_forward(c, P, s, 0, lim_enc=lim)
+    assert rew_r == 0 and rew_o == 0
+    assert rel_err(out_o, out_r.detach()) < 1e-12
