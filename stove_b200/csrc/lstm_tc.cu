@@ -85,17 +85,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// one k-block (32 floats of K) of the 3xTF32 product: the small cross terms first, hi*hi last
-__device__ __forceinline__ void mma_kblock_3x(uint32_t tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                              uint32_t idesc, bool first) {
+// one k-block (32 floats of K) of the 3xTF32 product.  TWO accumulators: hi*hi goes to `tmem_big`, the cross
+// terms lo*hi + hi*lo (2^-11 of the product) to `tmem_small`; the epilogue adds them in fp32.  The tensor cores
+// align addends by truncation, a bias of ~0.5 ulp of the ACCUMULATOR per MMA step: keeping the small terms out
+// of the big accumulator cuts the biased steps on it to a third and makes their own truncation 2^-11 smaller
+// (measured on the nine-step recurrence of the multiball parity test: LSTM gradient error 5.7e-4 -> see
+// profiles/r02_parity_*.jsonl).
+__device__ __forceinline__ void mma_kblock_3x(uint32_t tmem_big, uint32_t tmem_small, uint32_t a_hi, uint32_t a_lo,
+                                              uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first) {
     const uint64_t ah = smem_desc(a_hi), al = smem_desc(a_lo), bh = smem_desc(b_hi), bl = smem_desc(b_lo);
 #pragma unroll
     for (int k = 0; k < BK / 8; ++k) {         // 8 TF32 = 32 bytes per MMA: +2 in the (addr >> 4) field
-        mma_tf32(tmem, al + 2 * k, bh + 2 * k, idesc, (uint32_t)(!first || k != 0));
-        mma_tf32(tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
-        mma_tf32(tmem, ah + 2 * k, bh + 2 * k, idesc, 1u);
+        const uint32_t acc = (uint32_t)(!first || k != 0);
+        mma_tf32(tmem_small, al + 2 * k, bh + 2 * k, idesc, acc);
+        mma_tf32(tmem_small, ah + 2 * k, bl + 2 * k, idesc, 1u);
+        mma_tf32(tmem_big, ah + 2 * k, bh + 2 * k, idesc, acc);
     }
 }
+
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -106,6 +113,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// accumulator read-back: big + small
+__device__ __forceinline__ void tmem_ld8_sum(uint32_t t_big, uint32_t t_small, float* v) {
+    float w[8];
+    tmem_ld8(t_big, v);
+    tmem_ld8(t_small, w);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += w[i];
 }
 // the epilogue is instruction bound (one warp per scheduler): exp through MUFU.EX2 (__expf, ~2 ulp) and a fast
 // reciprocal; tanh(x) = 2 sigmoid(2x) - 1 keeps the absolute error ~2e-7, far inside the 3e-5 parity bound
@@ -178,7 +194,7 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
     using P_ = Plan<PREFETCH>;
     constexpr int STAGES = P_::STAGES, OFF_G = P_::OFF_G, OFF_C = P_::OFF_C, OFF_BAR = P_::OFF_BAR, OFF_GX = P_::OFF_GX,
                   OFF_HF = P_::OFF_HF, OFF_HHI = P_::OFF_HHI, OFF_HLO = P_::OFF_HLO;
-    constexpr uint32_t TMEM_COLS = 128, IDESC = idesc_for(128);
+    constexpr uint32_t TMEM_COLS = 256, IDESC = idesc_for(128);      // accumulators: big at column 0, small at 128
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle-128B tiles need 1024-byte alignment
@@ -250,7 +266,7 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = tiles + s * STAGE_BYTES;
-                mma_kblock_3x(tmem, sa, sa + TILE_BYTES, sa + 2 * TILE_BYTES, sa + 3 * TILE_BYTES, IDESC, kb == 0);
+                mma_kblock_3x(tmem, tmem + 128, sa, sa + TILE_BYTES, sa + 2 * TILE_BYTES, sa + 3 * TILE_BYTES, IDESC, kb == 0);
                 mma_commit(empty0 + 8 * s);            // implies tcgen05.fence::before_thread_sync
             }
             mma_commit(accum);
@@ -268,8 +284,10 @@ lstm_gemm_cell_fwd_kernel(const __grid_constant__ CellMaps maps, int num_kb, Cel
         for (int jc = jc0; jc < jc0 + BH / 8 / (EPI_WARPS / 4); ++jc) {
             float v[4][8];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BH + jc * 8), v[g]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int g = 0; g < 4; ++g) {
+                const uint32_t t = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BH + jc * 8);
+                tmem_ld8_sum(t, t + 128, v[g]);
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int ch = jc * 2 + half;
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 tc3_gemm_kernel(const __grid_constant__ GemmMaps maps, int num_kb, int kb_per) {
     using P_ = GemmPlan<BN>;
     constexpr int STAGES = P_::STAGES, STAGE = P_::STAGE, B_BYTES = P_::B_BYTES, OFF_BAR = P_::OFF_BAR;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN, IDESC = idesc_for(BN);
+    constexpr uint32_t TMEM_COLS = 2 * BN, IDESC = idesc_for(BN);      // accumulators: big at column 0, small at BN
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -424,7 +442,7 @@ tc3_gemm_kernel(const __grid_constant__ GemmMaps maps, int num_kb, int kb_per) {
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = tiles + s * STAGE, sb = sa + 2 * TILE_BYTES;
-                mma_kblock_3x(tmem, sa, sa + TILE_BYTES, sb, sb + B_BYTES, IDESC, it == 0);
+                mma_kblock_3x(tmem, tmem + BN, sa, sa + TILE_BYTES, sb, sb + B_BYTES, IDESC, it == 0);
                 mma_commit(empty0 + 8 * s);
             }
             mma_commit(accum);
@@ -440,9 +458,9 @@ tc3_gemm_kernel(const __grid_constant__ GemmMaps maps, int num_kb, int kb_per) {
 #pragma unroll 1
         for (int c8 = c0; c8 < c0 + CH_PER_WARP; c8 += 2) {
             float v[2][8];
-            tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c8 * 8), v[0]);
-            if (CH_PER_WARP > 1) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c8 * 8 + 8), v[1]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t t = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c8 * 8);
+            tmem_ld8_sum(t, t + BN, v[0]);
+            if (CH_PER_WARP > 1) tmem_ld8_sum(t + 8, t + BN + 8, v[1]);
 #pragma unroll
             for (int u = 0; u < (CH_PER_WARP > 1 ? 2 : 1); ++u) {
                 const int col = (c8 + u) * 8;                      // column of the tile

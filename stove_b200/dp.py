@@ -148,15 +148,19 @@ class DataParallel:
 
 
 class _Overlap:
-    """Piecewise exchange of the flat gradient bucket under the backward pass (R > 1, CUDA).
+    """Exchange of the flat gradient bucket in TWO pieces, the first one under the tail of the backward pass
+    (R > 1, CUDA).
 
     Bucket order: [early | encoder rest | W_ih rows].  `early` = every parameter outside the recognition network
     (SPN, GNN): their gradients are complete long before the LSTM backward ends; a post-accumulate hook counts
-    them in and the last one starts gather + all-reduce of that range on the communication stream.  The
-    recognition network hands its gradients over from inside its backward node (ops.LstmEncoder.grad_sink): head,
-    W_hh and biases first, then W_ih in two row blocks, each sent while the next GEMM runs.  Whatever did not
-    arrive through a hook or the sink is exchanged at the end (`finish`).  Works eagerly and under CUDA-graph
-    capture (the communication stream forks from / joins the producing streams through events)."""
+    them in and the last one gathers them into the bucket on the communication stream.  The recognition network
+    hands its gradients over from inside its backward node (ops.LstmEncoder.grad_sink): head, W_hh and biases
+    first, then W_ih in two row blocks.  An all-reduce costs ~20 us however small it is (profiles/
+    r02_timeline_dp2_v1_four_pieces.txt: four pieces made the exchange LONGER than the compute it hides
+    behind), so there are exactly two: everything up to the first W_ih block goes on the wire while the second
+    block's GEMM runs; the second block (2 MB) is the only exposed transfer.  Whatever did not arrive through a
+    hook or the sink is exchanged at the end (`finish`).  Works eagerly and under CUDA-graph capture (the
+    communication stream forks from / joins the producing streams through events)."""
 
     def __init__(self, engine, live):
         from . import ops
@@ -195,6 +199,7 @@ class _Overlap:
         dev = self.order[0].device
         self.flat = torch.empty(self.total, device=dev, dtype=torch.float32)
         self.pending, self.queue, self.sent = len(self.early), [], set()
+        self.gathered_to = self.reduced_to = 0        # the bucket is gathered / all-reduced up to these offsets
         self.active = True
         self.ops.LstmEncoder.grad_sink = self
 
@@ -205,7 +210,8 @@ class _Overlap:
         self.comm.wait_stream(torch.cuda.current_stream(p.device))
         self.pending -= 1
         if self.pending == 0:
-            self._send([(q.grad, self.offset[id(q)], q.numel()) for q in self.early], 0, self.n_early, wait=False)
+            self._gather([(q.grad, self.offset[id(q)], q.numel()) for q in self.early], wait=False)
+            self.gathered_to = self.n_early
             self.sent.update(id(q) for q in self.early)
 
     def __call__(self, name, tensor, row_lo=None, row_hi=None):       # ops.LstmEncoder.grad_sink
@@ -222,23 +228,29 @@ class _Overlap:
             if row_hi == p.shape[0]:
                 self.sent.add(id(p))
 
-    def flush(self):
-        if not self.queue:
-            return
-        lo = min(q[1] for q in self.queue)
-        hi = max(q[1] + q[2] for q in self.queue)
-        assert sum(q[2] for q in self.queue) == hi - lo, 'sink pieces must tile a contiguous bucket range'
-        self._send(self.queue, lo, hi)
-        self.queue = []
+    def flush(self, send=False):
+        """gather what the sink queued into the bucket; `send`: also all-reduce everything gathered so far that is
+        not on the wire yet (the bucket fills front to back)"""
+        if self.queue:
+            lo = min(q[1] for q in self.queue)
+            hi = max(q[1] + q[2] for q in self.queue)
+            assert sum(q[2] for q in self.queue) == hi - lo, 'sink pieces must tile a contiguous bucket range'
+            self._gather(self.queue)
+            if lo == self.gathered_to:
+                self.gathered_to = hi
+            self.queue = []
+        if send and self.gathered_to > self.reduced_to:
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.flat[self.reduced_to:self.gathered_to])
+            self.reduced_to = self.gathered_to
 
-    def _send(self, pieces, lo, hi, wait=True):
+    def _gather(self, pieces, wait=True):
         dev = self.flat.device
         if wait:
             self.comm.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self.comm):
             self.ops.gather_flat([t for t, _, _ in pieces], out=self.flat, offsets=[o for _, o, _ in pieces],
                                  scale=1.0 / self.R)
-            dist.all_reduce(self.flat[lo:hi])
         for t, _, _ in pieces:
             t.record_stream(self.comm)
 
@@ -248,18 +260,15 @@ class _Overlap:
         self.active = False
         left = [p for p in self.order if id(p) not in self.sent]
         cur = torch.cuda.current_stream(self.flat.device)
-        # contiguous runs of what is left
-        run = []
-        for p in left + [None]:
-            if run and (p is None or self.offset[id(p)] != self.offset[id(run[-1])] + run[-1].numel()):
-                lo = self.offset[id(run[0])]
-                hi = self.offset[id(run[-1])] + run[-1].numel()
-                self._send([(q.grad, self.offset[id(q)], q.numel()) for q in run], lo, hi)
-                run = []
-            if p is not None:
-                run.append(p)
+        if left:
+            self._gather([(q.grad, self.offset[id(q)], q.numel()) for q in left])
+        if self.reduced_to < self.total:
+            # (a gap between what the hooks / the sink delivered front to back and what arrived here is covered
+            # by reducing the whole remainder; delivered-but-unreduced ranges are inside it)
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.flat[self.reduced_to:])
+            self.reduced_to = self.total
         cur.wait_stream(self.comm)
-        self.flat.record_stream(cur)
         # the bucket order is the engine's `live` order from now on
         live[:] = self.order
         return self.flat

@@ -567,7 +567,7 @@ class LstmEncoder(torch.autograd.Function):
             for name, t_ in zip(('w1', 'b1', 'w2', 'b2'), g_head):
                 if t_ is not None:
                     sink(name, t_)
-            sink.flush()
+            sink.flush()                           # gathered into the bucket; nothing on the wire yet
             g_wih = None
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
@@ -580,7 +580,7 @@ class LstmEncoder(torch.autograd.Function):
                     tiles = ((hi - lo + 127) // 128) * ((K + 127) // 128)
                     sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)), out=g_wih[lo:hi])
                     sink('w_ih', g_wih, lo, hi)
-                    sink.flush()
+                    sink.flush(send=True)          # all-reduce of everything gathered so far
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
                 t_.record_stream(cur)

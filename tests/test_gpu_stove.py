@@ -173,6 +173,50 @@ def test_rollout_sampling_std_and_batch_independence():
     ck.finish()
 
 
+def test_rollout_drift_over_2000_steps_vs_fp64_oracle():
+    """BASELINE config 5 length: 2000 dependent steps.  Drift of the fp32 kernel against the fp64 oracle at steps
+    1, 10, 92, 500, 1000, 2000 on a seed whose rollout stays finite (SURVEY hard part 13), next to the drift of the
+    reference algorithm itself when run in fp32 on the CPU (the oracle in fp32).  The table goes to
+    gpurun_out/rollout_drift.json (committed under profiles/).  Bound: relative to the largest state magnitude
+    at that step, 1e-4 per step accumulated as 1e-4 * sqrt(t) -- and never more than 20x what fp32 arithmetic
+    costs the reference itself."""
+    import json
+    import os
+    from stove_b200 import synth
+    kw, seed = VARIANTS['ac']
+    oc, sd, model = make_model(kw, seed, att_gain=0.5)
+    gen = torch.Generator().manual_seed(4)
+    n, num = 32, 2000
+    z_last = torch.cat([0.2 + 0.3 * torch.rand(n, 3, 2, generator=gen, dtype=torch.float64),
+                        torch.rand(n, 3, 16, generator=gen, dtype=torch.float64) - 0.5], -1)
+    app = torch.rand(n, 3, 3, generator=gen, dtype=torch.float64)
+    actions = synth.random_actions(n, num, 9, 3).double()
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        z64, r64 = so.rollout(oc, dict(sd), z_last, num, actions, app)
+        z32, _ = so.rollout(oc, {k: v.float() for k, v in sd.items()}, z_last.float(), num, actions.float(), app.float())
+    zg, rg = model.rollout(z_last.float().cuda(), num, actions=actions.float().cuda(), appearance=app.float().cuda())
+    zg, rg = zg.double().cpu(), rg.double().cpu()
+    ck = Checker('rollout_drift_2000')
+    ck.true('finite', bool(torch.isfinite(zg).all()) and bool(torch.isfinite(z64).all()))
+    table = []
+    for t in (1, 10, 92, 500, 1000, 2000):
+        scale = float(z64[:, t - 1].abs().max())
+        gpu = float((zg[:, t - 1] - z64[:, t - 1]).abs().max())
+        cpu32 = float((z32[:, t - 1].double() - z64[:, t - 1]).abs().max())
+        rew = float((rg[:, t - 1] - r64[:, t - 1]).abs().max())
+        table.append({'step': t, 'state_max_abs': scale, 'gpu_fp32_max_abs_err': gpu, 'gpu_fp32_rel_err': gpu / scale,
+                      'reference_fp32_on_cpu_max_abs_err': cpu32, 'reward_max_abs_err': rew})
+        ck.close('z_step%d' % t, zg[:, t - 1], z64[:, t - 1], 1e-4 * t ** 0.5)
+        ck.true('within_20x_of_fp32_reference_step%d' % t, gpu <= 20 * cpu32 + 1e-6)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, 'rollout_drift.json'), 'w') as f:
+        json.dump({'what': 'Stove.rollout, action-conditioned + appearance, 32 sequences x 2000 steps, fp32 kernel vs fp64 oracle',
+                   'table': table}, f, indent=1)
+    ck.finish()
+
+
 def test_mcts_expand_and_rollout_equals_two_reference_calls():
     """One persistent launch (expansion step + random rollout) = the reference's two rollout calls
     (mcts_stove.py:94-137), checked against the fp64 oracle."""
@@ -203,7 +247,9 @@ def test_mcts_expand_and_rollout_equals_two_reference_calls():
 
 @pytest.mark.parametrize('tag,kw,n,res,O', [
     ('o9_multiball', dict(num_obj=9, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0,
-                          max_obj_scale=0.22), 16, 50, 9),                                  # BASELINE configs[3], upper end
+                          max_obj_scale=0.22), 256, 50, 9),                                 # BASELINE configs[3], upper end, batch 256
+    ('o6_multiball', dict(num_obj=6, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0,
+                          max_obj_scale=0.22), 256, 50, 6),                                 # configs[3], the reference's 6 balls
     ('ac_batch512', dict(action_conditioned=True, action_space=9, debug_core_appearance=True), 512, 32, 3),  # configs[2]
 ])
 def test_stove_other_baseline_configs_vs_oracle(tag, kw, n, res, O):
@@ -245,12 +291,9 @@ def test_stove_other_baseline_configs_vs_oracle(tag, kw, n, res, O):
         ck.close('rewards', rew, rew_o, 1e-4, absolute=True)
     for name, p in model.named_parameters():
         if p.grad is not None:
-            # Nine recurrent LSTM steps through the deliberately amplified W_hh (x8, see above): the 3xTF32 GEMMs
-            # carry ~1e-5 per product on the tensor cores (truncating addend alignment) and the
-            # recurrence multiplies it -- measured 5.7e-4 on the LSTM gradients here, 7e-5 with the SIMT-fp32
-            # library GEMMs (STOVE_ENCODER_FP32=1); three steps (O = 3) stay below 3e-4.
-            tol = 1e-3 if (O > 6 and '.rnn.' in name) else GRAD
-            ck.close('g.' + name, p.grad, P[name].grad, tol)
+            # (nine recurrent LSTM steps through the deliberately amplified W_hh: the 3xTF32 GEMMs keep the cross terms
+            # in their own TMEM accumulator, csrc/lstm_tc.cu, which holds the LSTM gradients inside the common bound)
+            ck.close('g.' + name, p.grad, P[name].grad, GRAD)
         else:
             ck.true('nograd.' + name, P[name].grad is None)
     ck.finish()
