@@ -431,6 +431,22 @@ int stove_adam_step(const void* const* params, const int64_t* offsets, const int
                     float* partial, const float* lr, float* step, float beta1, float beta2, float eps,
                     float max_norm, void* stream);
 
+/* Renderer: frames from states (Supair.reconstruct_from_z, supair.py:425-501):
+ *   out [F][C][A][B] = clamp(bg + sum_o paste(patches[f, o], z[f, o]), 0, 1),
+ * paste = F.grid_sample(patch, F.affine_grid(inverse of [[sx,0,x],[0,sy,y]], (A, B))), bilinear, zero padding.
+ * bg [C][A][B] (or [F][C][A][B] if bg_per_frame); patches [O][C][pa][pb] (or [F][O][C][pa][pb] if
+ * patches_per_frame); z [F][O][4] = (sx, sy, x, y).  No gradient. */
+int stove_render(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners, const float* bg,
+                 int bg_per_frame, const float* patches, int patches_per_frame, const float* z, float* out,
+                 void* stream);
+
+/* Measurement infrastructure (csrc/microbench.cu; not on the product path): the roofline denominators that
+ * MEASURED_PEAKS.json does not carry.  FP32 FMA throughput of ctas x 1024 threads x iters x 16 independent FMAs,
+ * and the issue peak of tcgen05.mma kind::tf32 128 x n_cols x 8 (n_cols 128 or 256) with operands resident in
+ * shared memory, both in TFLOP/s; scripts/microbench.py writes them to profiles/r02_microbench.json. */
+int stove_microbench_ffma(int ctas, int iters, float* scratch, double* tflops, void* stream);
+int stove_microbench_tf32(int ctas, int iters, int n_cols, double* tflops, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

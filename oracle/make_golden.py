@@ -172,21 +172,51 @@ def dynamics_golden():
     np.savez_compressed(os.path.join(OUT, 'dynamics.npz'), **{k: np.asarray(v) for k, v in res.items()})
 
 
-def stove_golden():
+def env_frames_u8(n, T, seed):
+    """Frames from the reference's own simulator + renderer: BillardsEnv(n=3, r=1.2, m=1, hw=10, granularity=10,
+    res=32, t=1, fc=0) through generate_fitting_run (model/envs/envs.py:588-653, 829-835),
+    imported with the stubs of SURVEY appendix B (imageio / spriteworld are not needed by this path).
+    -> (uint8 frames (n, T, 3, 32, 32), the same as float64 / 255)."""
+    import sys
+    import types
+    for m in ['imageio', 'spriteworld', 'spriteworld.renderers', 'spriteworld.sprite']:
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['spriteworld'].renderers = sys.modules['spriteworld.renderers']
+    sys.modules['spriteworld.sprite'].Sprite = object
+    if rh.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, rh.REFERENCE_ROOT)
+    from model.envs import envs
+    envs.tqdm = lambda it, *a, **k: it                    # quiet
+    np.random.seed(seed)
+    imgs, _ = envs.generate_fitting_run(envs.BillardsEnv, run_len=T, run_num=n, max_tries=100 * n, res=32, n=3,
+                                        r=1.2, dt=1, granularity=10, fc=0, hw=10, m=1.)
+    assert imgs.shape == (n, T, 32, 32, 3), imgs.shape
+    x = np.transpose(imgs, (0, 1, 4, 2, 3))                # the loader's (n, T, c, w, h) layout (load_data.py)
+    q = np.clip(np.round(x * 255.0), 0, 255).astype(np.uint8)
+    return torch.from_numpy(q), torch.from_numpy(q.astype(np.float64) / 255.0)
+
+
+def stove_golden(only=None):
     variants = (
         ('plain', {}, 4, 32, 1.2, 21),
         ('ac', dict(action_conditioned=True, action_space=9, debug_core_appearance=True), 4, 32, 1.0, 22),
         ('o6', dict(num_obj=6, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0,
                     max_obj_scale=0.22), 2, 50, 1.0, 23),
         ('vol', dict(debug_match_objects='volatile'), 3, 32, 1.2, 24),
+        ('envs', {}, 4, 32, 1.2, 26),          # frames rendered by the reference's own BillardsEnv
     )
     for tag, kw, n, res_px, radius, seed in variants:
+        if only is not None and tag not in only:
+            continue
         c = so.default_config(**kw)
         # att_gain < 1 keeps exp(attention) tame so long rollouts stay finite (SURVEY hard part 13)
         sd = make_state_dict(c, seed, att_gain=0.5)
         ref = rh.build_reference(c, sd)
         T = 8
-        q, x = frames_u8(n, T, c.num_obj, res_px, seed, radius, use_colours=(c.num_obj <= 3))
+        if tag == 'envs':
+            q, x = env_frames_u8(n, T, seed)
+        else:
+            q, x = frames_u8(n, T, c.num_obj, res_px, seed, radius, use_colours=(c.num_obj <= 3))
         actions = None
         if c.action_conditioned:
             actions = synth.random_actions(n, T, 9, seed).to(D)
@@ -268,6 +298,9 @@ if __name__ == '__main__':
     assert rh.available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:                      # e.g. `python oracle/make_golden.py envs`: only these stove variants
+        stove_golden(only=sys.argv[1:])
+        sys.exit(0)
     structure_golden()
     spn_golden()
     scene_golden()

@@ -78,6 +78,9 @@ SIGNATURES = {
     'stove_profile_read': (C.c_int, [vp, vp, C.c_int]),
     'stove_kernel_name': (C.c_char_p, [C.c_int]),
     'stove_kernel_count': (C.c_int, []),
+    'stove_microbench_ffma': (C.c_int, [C.c_int, C.c_int, vp, C.POINTER(C.c_double), vp]),
+    'stove_microbench_tf32': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), vp]),
+    'stove_render': (C.c_int, [i64] + [C.c_int] * 7 + [vp, C.c_int, vp, C.c_int, vp, vp, vp]),
     'stove_set_option': (C.c_int, [C.c_char_p, C.c_int]),
     'stove_get_option': (C.c_int, [C.c_char_p]),
     'stove_bw_transform': (C.c_int, [vp, vp, i64, C.c_int, i64, vp]),

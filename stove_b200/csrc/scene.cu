@@ -360,3 +360,56 @@ extern "C" int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, in
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// ------------------------------------------------------------------------------------
+// Renderer: frames from states (Supair.reconstruct_from_z, supair.py:425-501; the same paste that
+// draw_balls of the simulator performs with analytic blobs, envs.py:310-339).
+//   out[f] = clamp(bg + sum_o sample(patch[f, o], inverse affine of z[f, o]), 0, 1)
+// where sample = F.grid_sample(patch, F.affine_grid(theta^-1, (A, B))), bilinear, zero padded.  The
+// reference issues 2 grid ops + an add per object over an O-fold repeated canvas; here one thread owns one
+// output pixel and walks the objects (patches are tiny and L1/L2 resident).  No gradient (visualisation,
+// MCTS frame generation).
+// ------------------------------------------------------------------------------------
+__global__ void render_kernel(SceneDims d, int64_t F, const float* __restrict__ bg, int bg_per_frame,
+                              const float* __restrict__ patches, int64_t patch_frame_stride,
+                              const float* __restrict__ z, float* __restrict__ out) {
+    const int64_t total = F * d.C * d.A * d.B;
+    const int pp = d.pa * d.pb;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % d.B);
+        const int u = (int)((i / d.B) % d.A);
+        const int ch = (int)((i / ((int64_t)d.A * d.B)) % d.C);
+        const int64_t f = i / ((int64_t)d.C * d.A * d.B);
+        float acc = bg[(bg_per_frame ? f * d.C * d.A * d.B : 0) + (ch * d.A + u) * d.B + v];
+        const float gx = base_coord(v, d.B, d.align), gy = base_coord(u, d.A, d.align);
+        for (int o = 0; o < d.O; ++o) {
+            const float4 zz = __ldg(reinterpret_cast<const float4*>(z + (f * d.O + o) * 4));
+            // inverse transform (supair.py:218-239): [1/sx, 1/sy, -x/sx, -y/sy]
+            const float px = unnorm(gx / zz.x - zz.z / zz.x, d.pb, d.align);
+            const float py = unnorm(gy / zz.y - zz.w / zz.y, d.pa, d.align);
+            const Corner c = corners(py, px, d.pa, d.pb);
+            float val, dy, dx;
+            bilinear<false>(patches + f * patch_frame_stride + (int64_t)(o * d.C + ch) * pp, d.pb, c, val, dy, dx);
+            acc += val;
+        }
+        out[i] = fminf(fmaxf(acc, 0.f), 1.f);
+    }
+}
+
+extern "C" int stove_render(int64_t F, int O, int C, int A, int B, int pa, int pb, int align_corners,
+                            const float* bg, int bg_per_frame, const float* patches, int patches_per_frame,
+                            const float* z, float* out, void* stream) {
+    STOVE_CHECK_ARG(F >= 0 && O > 0 && C > 0 && A > 0 && B > 0 && pa > 0 && pb > 0 && bg && patches && z && out,
+                    "bad argument");
+    STOVE_CHECK_ARG(((uintptr_t)z & 15) == 0, "z must be 16-byte aligned");
+    if (F == 0) return STOVE_OK;
+    SceneDims d{O, C, A, B, pa, pb, align_corners};
+    const int64_t total = F * C * A * B;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_RENDER, s, render_kernel<<<blocks, 256, 0, s>>>(d, F, bg, bg_per_frame, patches,
+                                                                  patches_per_frame ? (int64_t)O * C * pa * pb : 0, z, out));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

@@ -35,6 +35,21 @@ def bw_transform(x, want_planes=False):
     return (y, pl) if want_planes else y
 
 
+def render(bg, patches, z, width, height, align_corners=False):
+    """Frames from states: clamp(bg + sum_o paste(patches[:, o], z[:, o]), 0, 1) (supair.py:425-501, the paste loop).
+    bg (C, A, B) or (F, C, A, B); patches (O, C, pa, pb) or (F, O, C, pa, pb); z (F, O, 4) = (sx, sy, x, y)
+    -> (F, C, A, B).  No autograd."""
+    z = z.detach().contiguous()
+    bg, patches = bg.detach().contiguous(), patches.detach().contiguous()
+    N.require_cuda_f32(z, bg, patches)
+    F, O = z.shape[0], z.shape[1]
+    Cc, pa, pb = patches.shape[-3], patches.shape[-2], patches.shape[-1]
+    out = torch.empty(F, Cc, width, height, device=z.device, dtype=z.dtype)
+    N.check(N.lib().stove_render(F, O, Cc, width, height, pa, pb, int(bool(align_corners)), N.ptr(bg), int(bg.dim() == 4),
+                                 N.ptr(patches), int(patches.dim() == 5), N.ptr(z), N.ptr(out), N.stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # SPN parameter packing
 # ----------------------------------------------------------------------------------------

@@ -219,8 +219,8 @@ class Supair(nn.Module):
         return torch.stack(recons, 0).clamp(0., 1.).view(x.shape[0], self.c.num_obj, -1)
 
     def reconstruct_from_z(self, z, x=None, max_activation=True, single_image=True):
-        """Render states z (n, T, o, >=4) with the SPNs' most probable appearance
-        (supair.py:425-501); visualisation only."""
+        """Render states z (n, T, o, >=4) with the SPNs' most probable appearance (supair.py:425-501).  On the
+        GPU the paste loop is one kernel (ops.render); CPU tensors take the reference's grid_sample loop."""
         import torch.nn.functional as F
         c = self.c
         z = z[..., :4]
@@ -238,6 +238,10 @@ class Supair(nn.Module):
             if single_image:
                 obj = obj.unsqueeze(1).repeat(1, z.shape[1], 1, 1, 1, 1).flatten(end_dim=1)
         z_img = z.flatten(end_dim=1)
+        if z_img.is_cuda:
+            # one kernel for the whole paste loop (csrc/scene.cu: render_kernel)
+            out = ops.render(canvas, obj, z_img, w, h, self._align())
+            return out.view(*z.shape[:2], c.channels, w, h)
         ac = self._align()
         for o in range(c.num_obj):
             theta = self.expand_z(self.invert_z(z_img[:, o]))

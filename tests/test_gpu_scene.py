@@ -60,3 +60,42 @@ def test_scene_kernel_vs_oracle(kw):
         ck.close(name, a, b, 2e-5, absolute=True)
     ck.close('gz', zg.grad, zo.grad, GRAD)
     ck.finish()
+
+
+@pytest.mark.parametrize('align', [False, True])
+def test_render_vs_grid_sample_and_oracle(align):
+    """The renderer kernel (Supair.reconstruct_from_z's paste loop, supair.py:482-501) against the same loop written
+    with F.affine_grid / F.grid_sample in fp64, per-frame and shared patches / backgrounds, boxes partly outside."""
+    import torch.nn.functional as F
+    from stove_b200 import ops
+    torch.manual_seed(3)
+    Fr, O, C, A, B, pa, pb = 37, 3, 1, 32, 32, 10, 10
+    z = torch.cat([0.1 + 0.7 * torch.rand(Fr, O, 2), 2.2 * torch.rand(Fr, O, 2) - 1.1], -1).double()
+    for per_frame in (False, True):
+        bg = (torch.rand(Fr, C, A, B) if per_frame else torch.rand(C, A, B)).double() * 0.3
+        patches = (torch.rand(Fr, O, C, pa, pb) if per_frame else torch.rand(O, C, pa, pb)).double()
+        canvas = (bg if per_frame else bg.unsqueeze(0).repeat(Fr, 1, 1, 1)).clone()
+        pf = patches if per_frame else patches.unsqueeze(0).repeat(Fr, 1, 1, 1, 1)
+        for o in range(O):
+            zz = z[:, o]
+            inv = torch.stack([1 / zz[:, 0], 1 / zz[:, 1], -zz[:, 2] / zz[:, 0], -zz[:, 3] / zz[:, 1]], 1)
+            zero = torch.zeros_like(inv[:, 0])
+            theta = torch.stack([inv[:, 0], zero, inv[:, 2], zero, inv[:, 1], inv[:, 3]], 1).view(-1, 2, 3)
+            grid = F.affine_grid(theta, torch.Size((Fr, C, A, B)), align_corners=align)
+            canvas = canvas + F.grid_sample(pf[:, o], grid, align_corners=align)
+        ref = canvas.clamp(0, 1)
+        out = ops.render(bg.float().cuda(), patches.float().cuda(), z.float().cuda(), A, B, align)
+        assert out.shape == ref.shape
+        assert float((out.double().cpu() - ref).abs().max()) < 2e-5
+
+
+def test_reconstruct_from_z_uses_the_renderer():
+    """Supair.reconstruct_from_z on the GPU (renderer kernel) == the reference's grid_sample loop on the CPU copy."""
+    from util import make_model
+    oc, sd, model = make_model({}, 5)
+    g = torch.Generator().manual_seed(1)
+    z = torch.cat([0.15 + 0.5 * torch.rand(4, 6, 3, 2, generator=g), 1.6 * torch.rand(4, 6, 3, 2, generator=g) - 0.8], -1)
+    gpu = model.sup.reconstruct_from_z(z.cuda())
+    cpu = model.cpu().sup.reconstruct_from_z(z)
+    assert gpu.shape == (4, 6, 1, 32, 32)
+    assert float((gpu.cpu() - cpu).abs().max()) < 2e-5

@@ -42,6 +42,7 @@ VARIANTS = {
     'o6': (dict(num_obj=6, width=50, height=50, debug_match_objects='greedy', overlap_beta=100.0,
                 max_obj_scale=0.22), 23),
     'vol': (dict(debug_match_objects='volatile'), 24),
+    'envs': ({}, 26),      # frames rendered by the reference's own BillardsEnv (oracle/make_golden.py: env_frames_u8)
 }
 
 
