@@ -714,7 +714,11 @@ def run_b200(args):
                    'cuda_graph': graphed is not None,
                    'e2e_input': 'uint8 RGB frames in pinned host memory, scaled by 1/255 inside bw_transform on the device; '
                                 '`e2e_f32_frames` is the same with fp32 host frames (4x the bytes)',
-                   'optimizer': 'excluded (metric is fwd+bwd); flat-bucket NCCL all-reduce included when N>1'},
+                   'optimizer': 'excluded (metric is fwd+bwd); gradient all-reduce of the flat bucket included when N>1',
+                   'dp_exchange': None if world == 1 else (
+                       'two pieces overlapped with the LSTM backward; ' +
+                       ('NVLS multimem all-reduce on a symmetric-memory bucket' if getattr(engine._overlap, 'symm', None)
+                        else 'NCCL all-reduce'))},
         'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': 4},
         'e2e_f32_frames': {'value': world * BATCH * args.steps / (ms_e2e32 * 1e-3), 'unit': 'sequences/s',
@@ -770,6 +774,7 @@ def dp_gradient_check(model, dev, world, rank):
     err, piecewise_vs_whole = float(t[0]), float(t[1])
     return {'max_rel_err': err, 'tolerance': 1e-4, 'ok': err < 1e-4 and piecewise_vs_whole < 1e-5,
             'overlapped_vs_single_allreduce': piecewise_vs_whole, 'overlap_active': eng._overlap is not None,
+            'symmetric_memory': bool(getattr(eng._overlap, 'symm', None)),
             'what': 'flat gradient after the (overlapped, piecewise) all-reduce of %d-sequence shards vs. one rank on the '
                     '%d-sequence batch' % (n_loc, n_loc * world)}
 
