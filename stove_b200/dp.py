@@ -295,11 +295,13 @@ class _Overlap:
             if lo == self.gathered_to:
                 self.gathered_to = hi
             self.queue = []
-        hi = self.gathered_to // _ALIGN * _ALIGN       # piece boundaries stay aligned for the multimem kernels
+        # piece boundaries stay aligned for the multimem kernels; the last piece takes the padding with it
+        done = self.gathered_to == self.total
+        hi = (self.total_padded if self.symm is not None else self.total) if done else self.gathered_to // _ALIGN * _ALIGN
         if send and hi > self.reduced_to:
             with torch.cuda.stream(self.comm):
                 self._all_reduce(self.reduced_to, hi)
-            self.reduced_to = hi
+            self.reduced_to = self.total if done else hi
 
     def _gather(self, pieces, wait=True):
         dev = self.flat.device
