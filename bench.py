@@ -458,8 +458,9 @@ def run_b200(args):
             # i+1 overlaps the compute of step i on a side stream) and reads its loss back (D2H)
             x = prefetch.get(i)
             if g is not None:
-                prefetch.release(i, g.load(x))
+                ev = g.load(x)
                 loss = g.run()
+                prefetch.release(i, ev if ev is not None else g.done)     # frames read in place: free after the replay
             else:
                 loss = engine.forward_backward(x, step_counter=1)
             prefetch.prefetch(i + 1)

@@ -59,9 +59,12 @@ int stove_get_option(const char* name);
 int stove_bw_transform(const float* x, float* y, int64_t n, int channels, int64_t hw, void* stream);
 /* The same with uint8 frames accepted (x_is_u8: values are scaled by 1/255 on the fly -- host frames then
  * cross PCIe at one byte per value) and, optionally, the (hi, lo) TF32 operand planes y_planes [2][n][hw] of
- * y written in the same pass (the left operand of the recognition LSTM's input GEMM, see below). */
-int stove_bw_transform_ex(const void* x, int x_is_u8, float* y, float* y_planes, int64_t n, int channels,
-                          int64_t hw, void* stream);
+ * y written in the same pass (the left operand of the recognition LSTM's input GEMM, see below).
+ * x_is_cell: x is not the frames but a DEVICE cell holding their (16-byte aligned) address, read when the
+ * kernel runs -- a captured CUDA graph is re-pointed at the next batch by writing 8 bytes instead of copying
+ * the batch into a static buffer. */
+int stove_bw_transform_ex(const void* x, int x_is_u8, int x_is_cell, float* y, float* y_planes, int64_t n,
+                          int channels, int64_t hw, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * RAT-SPN parameter packing (model/spn/rat_torch.py:85-99 leaf variance,

@@ -84,7 +84,7 @@ SIGNATURES = {
     'stove_set_option': (C.c_int, [C.c_char_p, C.c_int]),
     'stove_get_option': (C.c_int, [C.c_char_p]),
     'stove_bw_transform': (C.c_int, [vp, vp, i64, C.c_int, i64, vp]),
-    'stove_bw_transform_ex': (C.c_int, [vp, C.c_int, vp, vp, i64, C.c_int, i64, vp]),
+    'stove_bw_transform_ex': (C.c_int, [vp, C.c_int, C.c_int, vp, vp, i64, C.c_int, i64, vp]),
     'stove_spn_pack_leaf_fwd': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp]),
     'stove_spn_pack_leaf_bwd': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, f32, f32, vp, vp, vp, vp]),
     'stove_spn_pack_sum_fwd': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]),

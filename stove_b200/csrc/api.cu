@@ -175,9 +175,12 @@ __device__ __forceinline__ float load1(const uint8_t* p) { return __ldg(p) * (1.
 __device__ __forceinline__ float tf32_hi_(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 
 template <typename TI, bool V4>
-__global__ void bw_transform_kernel(const TI* __restrict__ x, float* __restrict__ y, float* __restrict__ pl,
-                                    int64_t n, int C, int64_t hw) {
+__global__ void bw_transform_kernel(const TI* __restrict__ x, const void* const* __restrict__ x_cell,
+                                    float* __restrict__ y, float* __restrict__ pl, int64_t n, int C, int64_t hw) {
     constexpr int W = V4 ? 4 : 1;
+    // indirect input: the frames' address is read from a device cell at run time, so a captured graph can be
+    // pointed at a different batch without copying it into a static buffer
+    if (x_cell) x = reinterpret_cast<const TI*>(*x_cell);
     const int64_t hww = hw / W, total = n * hww, plane = n * hw;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -215,16 +218,18 @@ __global__ void bw_transform_kernel(const TI* __restrict__ x, float* __restrict_
 }
 
 template <typename TI>
-static int bw_launch(const TI* x, float* y, float* pl, int64_t n, int channels, int64_t hw, cudaStream_t st) {
+static int bw_launch(const TI* x, const void* const* x_cell, float* y, float* pl, int64_t n, int channels, int64_t hw,
+                     cudaStream_t st) {
     const int threads = 256;
-    const bool v4 = (hw % 4 == 0) && (((uintptr_t)x % (4 * sizeof(TI))) == 0) && (((uintptr_t)y | (uintptr_t)pl) % 16 == 0);
+    // (an indirect source must be 16-byte aligned: the caller guarantees it)
+    const bool v4 = (hw % 4 == 0) && (x_cell || ((uintptr_t)x % (4 * sizeof(TI))) == 0) && (((uintptr_t)y | (uintptr_t)pl) % 16 == 0);
     const int64_t items = v4 ? n * (hw / 4) : n * hw;
     int blocks = (int)((items + threads - 1) / threads);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (v4)
-        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, true><<<blocks, threads, 0, st>>>(x, y, pl, n, channels, hw));
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, true><<<blocks, threads, 0, st>>>(x, x_cell, y, pl, n, channels, hw));
     else
-        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, false><<<blocks, threads, 0, st>>>(x, y, pl, n, channels, hw));
+        STOVE_KERNEL(K_BW_TRANSFORM, st, bw_transform_kernel<TI, false><<<blocks, threads, 0, st>>>(x, x_cell, y, pl, n, channels, hw));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
@@ -233,15 +238,16 @@ extern "C" int stove_bw_transform(const float* x, float* y, int64_t n, int chann
                                   void* stream) {
     STOVE_CHECK_ARG(x && y && n >= 0 && channels > 0 && hw > 0, "bad argument");
     if (n == 0) return STOVE_OK;
-    return bw_launch<float>(x, y, nullptr, n, channels, hw, (cudaStream_t)stream);
+    return bw_launch<float>(x, nullptr, y, nullptr, n, channels, hw, (cudaStream_t)stream);
 }
 
-extern "C" int stove_bw_transform_ex(const void* x, int x_is_u8, float* y, float* y_planes, int64_t n,
+extern "C" int stove_bw_transform_ex(const void* x, int x_is_u8, int x_is_cell, float* y, float* y_planes, int64_t n,
                                      int channels, int64_t hw, void* stream) {
     STOVE_CHECK_ARG(x && y && n >= 0 && channels > 0 && hw > 0, "bad argument");
     if (n == 0) return STOVE_OK;
-    return x_is_u8 ? bw_launch<uint8_t>((const uint8_t*)x, y, y_planes, n, channels, hw, (cudaStream_t)stream)
-                   : bw_launch<float>((const float*)x, y, y_planes, n, channels, hw, (cudaStream_t)stream);
+    const void* const* cell = x_is_cell ? (const void* const*)x : nullptr;
+    return x_is_u8 ? bw_launch<uint8_t>(x_is_cell ? nullptr : (const uint8_t*)x, cell, y, y_planes, n, channels, hw, (cudaStream_t)stream)
+                   : bw_launch<float>(x_is_cell ? nullptr : (const float*)x, cell, y, y_planes, n, channels, hw, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------

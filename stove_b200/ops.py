@@ -18,20 +18,46 @@ def _c(t):
 # ----------------------------------------------------------------------------------------
 # bw_transform (model/utils/utils.py:10-15)
 # ----------------------------------------------------------------------------------------
+class IndirectFrames:
+    """Frames addressed through a device cell: `cell` (int64[1], CUDA) holds the address of a contiguous
+    (n, T, C, W, H) batch of `dtype` (float32 or uint8).  A captured CUDA graph whose first kernel
+    (bw_transform) reads its input through the cell is re-pointed at the next batch with `point_at(x)` -- an
+    8-byte write -- instead of a copy of the batch into a static buffer (dp.GraphedStep)."""
+
+    def __init__(self, example):
+        self.shape, self.dtype, self.device = tuple(example.shape), example.dtype, example.device
+        self.cell = torch.zeros(1, dtype=torch.int64, device=example.device)
+        self._keep = None
+        self.point_at(example)
+
+    def point_at(self, x):
+        if tuple(x.shape) != self.shape or x.dtype != self.dtype or not x.is_contiguous() or x.data_ptr() % 16:
+            raise ValueError('IndirectFrames: batch must be contiguous, 16-byte aligned, %s %s' % (self.shape, self.dtype))
+        self._keep = x                         # the batch must stay alive until the consumer has run
+        self.cell.fill_(x.data_ptr())
+
+    @property
+    def is_cuda(self):
+        return True
+
+
 def bw_transform(x, want_planes=False):
     """(n, T, C, W, H) -> (n, T, 1, W, H): sum colour channels, clamp to [0, 1] (utils.py:10-15).
-    x: fp32 in [0, 1], or uint8 frames (scaled by 1/255 inside the kernel).  With `want_planes` also returns
-    the (hi, lo) TF32 operand planes (2, n*T, W*H) of the result for the recognition LSTM's input GEMM."""
+    x: fp32 in [0, 1], or uint8 frames (scaled by 1/255 inside the kernel), or an IndirectFrames.  With
+    `want_planes` also returns the (hi, lo) TF32 operand planes (2, n*T, W*H) of the result for the recognition
+    LSTM's input GEMM."""
+    ind = isinstance(x, IndirectFrames)
     if not x.is_cuda:
         raise RuntimeError('stove_b200 kernels need CUDA tensors (got a %s tensor); there is no CPU path' % x.device)
     if x.dtype not in (torch.float32, torch.uint8):
         raise RuntimeError('stove_b200: frames must be float32 in [0, 1] or uint8 (got %s)' % x.dtype)
-    x = x.contiguous()
+    if not ind:
+        x = x.contiguous()
     n, T, ch, w, h = x.shape
     y = torch.empty(n, T, 1, w, h, device=x.device, dtype=torch.float32)
     pl = torch.empty(2, n * T, w * h, device=x.device, dtype=torch.float32) if want_planes else None
-    N.check(N.lib().stove_bw_transform_ex(N.ptr(x), int(x.dtype == torch.uint8), N.ptr(y), N.ptr(pl), n * T, ch,
-                                          w * h, N.stream()))
+    N.check(N.lib().stove_bw_transform_ex(N.ptr(x.cell) if ind else N.ptr(x), int(x.dtype == torch.uint8), int(ind),
+                                          N.ptr(y), N.ptr(pl), n * T, ch, w * h, N.stream()))
     return (y, pl) if want_planes else y
 
 

@@ -350,6 +350,9 @@ class Stove(nn.Module):
         self.sup.step_counter = step_counter
         self.dyn.step_counter = step_counter
         x_color, x_planes = x, None
+        if isinstance(x, ops.IndirectFrames) and (pretrain or not self.c.debug_bw or self.c.debug_core_appearance
+                                                  or self.c.debug_match_appearance):
+            raise ValueError('IndirectFrames are only consumed by bw_transform (debug_bw, no appearances, no pretrain)')
         if not pretrain:
             self.sup.encoder.prepare()          # frame-independent encoder work, off the chain (side stream)
         if self.c.debug_bw:

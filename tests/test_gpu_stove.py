@@ -389,3 +389,42 @@ def test_readme_quickstart():
     for _ in range(10):
         l1 = float(step(x))
     assert l1 == l1 and l1 < l0
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.uint8])
+def test_graphed_step_reads_frames_in_place(dtype):
+    """GraphedStep re-points the captured step at each batch through a device cell (no copy into a static buffer):
+    replays on two different batches must reproduce the eager losses of exactly those batches, for fp32 and for
+    uint8 frames (scaled by 1/255 inside bw_transform)."""
+    from stove_b200 import Stove, StoveConfig, dp, synth
+    torch.manual_seed(0)
+    model = Stove(StoveConfig(width=32, height=32, num_obj=3, action_conditioned=False, action_space=None, device='cuda')).to('cuda')
+    xs = [synth.billiards(8, 8, 3, res=32, seed=s)['x'] for s in (1, 2)]
+    if dtype == torch.uint8:
+        xs = [(x * 255).round().to(torch.uint8) for x in xs]
+    xs = [x.cuda() for x in xs]
+    gen = torch.Generator().manual_seed(3)
+    noise = [torch.randn(8, 3, 12, 1, generator=gen) for _ in range(2)] + [torch.randn(8, 3, 18, generator=gen) for _ in range(6)]
+
+    class Fixed:                     # the same draws in every pass, eager or replayed
+        stacked = False
+
+        def __init__(self):
+            self.d = [t.cuda() for t in noise]
+            self.i = 0
+
+        def __call__(self, shape, like):
+            t = self.d[self.i % len(self.d)]
+            self.i += 1
+            return t
+
+    model._standard_normal = Fixed()
+    engine = dp.DataParallel(model)
+    step = dp.GraphedStep(engine, xs[0])
+    assert step.indirect
+    got = [float(step(x)) for x in (xs[1], xs[0], xs[1])]
+    model._standard_normal = Fixed()
+    want = [float(engine.forward_backward(x.float() / 255 if dtype == torch.uint8 else x, 1)) for x in (xs[1], xs[0], xs[1])]
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 2e-5 * abs(w), (got, want)
+    assert abs(got[0] - got[1]) > 1e-3 * abs(got[0])          # the two batches really differ
