@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(1024) spn2_fwd_kernel(
             if (q < R)
                 for (int i = lane; i < S * S; i += 32) cp_async4(rws + q * S * S + i, rlin + q * S * S + i);
         }
+        cp_async_commit();      // wait_group only covers COMMITTED copies (found by compute-sanitizer racecheck, round 2)
         cp_async_wait<0>();
         __syncthreads();
     }

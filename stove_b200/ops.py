@@ -433,17 +433,6 @@ class LstmEncoder(torch.autograd.Function):
     grad_sink = None
 
     @staticmethod
-    def _recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt):
-        """W_hh and bias gradients on the current stream"""
-        H4 = 4 * H
-        if steps > 1:
-            tiles = (H4 // 128) * ((H + 127) // 128)
-            g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
-        else:
-            g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
-        return g_whh, sum_parts(bias_part)
-
-    @staticmethod
     def prepare(w_ih, w_hh, b_ih, b_hh):
         """Operand planes of the weights and the summed bias, on the library's side stream.  They depend on the
         parameters only: issued at the very start of a step (before the frames are even transformed) they are
@@ -577,31 +566,39 @@ class LstmEncoder(torch.autograd.Function):
                 # machine and the next cell kernel sums the parts
                 dh = tc3_gemm(g_pl, whhT_pl, parts=_split_k(((n + 127) // 128) * ((H + 127) // 128), H4 // 32))
                 g_c = g_c_prev
+            if t == 1:
+                # every gate gradient that W_hh sees exists now (steps 1 .. steps-1): g_W_hh = sum_t g_t^T h_{t-1}
+                # is ONE GEMM over the stacked transposed planes, on the side stream, under the last hidden-state
+                # GEMM and the last cell kernel -- not at the tail of the node, where it was the longest branch
+                # (profiles/r02_timeline_v1_lstm_planes.txt: 40 us + 17 us of reductions behind the W_ih GEMM)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    tiles = (H4 // 128) * ((H + 127) // 128)
+                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
+                for t_ in (gT_all, hT_all):
+                    t_.record_stream(side)
+        if steps == 1:
+            g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
         sink = LstmEncoder.grad_sink
         K = x.shape[1]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):              # bias gradient: fixed-order sum of the per-block column sums
+            g_b = sum_parts(bias_part)
+        bias_part.record_stream(side)
+        g_wih = None
         if sink is None:
-            # weight and bias gradients of the recurrence: nothing waits for them until the node returns -> side
-            # stream, beside the W_ih GEMM.  g_W_hh = sum_t g_t^T h_{t-1} is ONE GEMM over the stacked operands.
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                g_whh, g_b = LstmEncoder._recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt)
-            for t_ in (gT_all, hT_all, bias_part):
-                if t_ is not None:
-                    t_.record_stream(side)
-            g_wih = None
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
                 xT_pl.record_stream(cur)
                 tiles = (H4 // 128) * ((K + 127) // 128)
                 g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
-            cur.wait_stream(side)                  # every gradient is ready on the node's stream when it returns
+            cur.wait_stream(side)                  # head, W_hh and bias gradients
         else:
+            cur.wait_stream(side)                  # head, W_hh and bias gradients
             # data-parallel run: gradients are handed to the engine's sink the moment they exist, so their
-            # all-reduce overlaps what is still being computed.  These GEMMs are bound by L2 bandwidth, so running
-            # them one after the other costs nothing: W_hh / biases / head first, then W_ih in two halves -- the
-            # first half is on the wire while the second is computed; only the last 2 MB are exposed.
-            cur.wait_stream(side)                  # head gradients
-            g_whh, g_b = LstmEncoder._recurrent_grads(gT_all, hT_all, bias_part, steps, H, ldS, dev, dt)
+            # all-reduce overlaps what is still being computed: W_hh / biases / head are gathered into the bucket
+            # now, W_ih follows in two row blocks -- the first block (with everything before it) is on the wire
+            # while the second is computed; only the last 2 MB are exposed.
             sink('w_hh', g_whh)
             sink('b_ih', g_b)
             sink('b_hh', g_b)
@@ -609,7 +606,6 @@ class LstmEncoder(torch.autograd.Function):
                 if t_ is not None:
                     sink(name, t_)
             sink.flush()                           # gathered into the bucket; nothing on the wire yet
-            g_wih = None
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
                 xT_pl.record_stream(cur)
