@@ -377,10 +377,11 @@ int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t K, const float* A_pl, con
  * written as `parts` split-K partial products D[p][M][ldd] (part stride part_stride floats; the caller sums
  * them, stove_sum_parts).  The library may lower `parts` (never below 1): stove_tc3_gemm_parts returns the
  * count it will use for (M, N, K, want).  Used for the hidden-state gradient (gate gradient x W_hh) and for
- * both weight gradients of the LSTM (contractions over the frames: transposed planes as operands). */
+ * both weight gradients of the LSTM (contractions over the frames: transposed planes as operands).
+ * bn: tile width (0 = automatic: 128, or 64 for N <= 64; 256 = fewest operand bytes, half the CTAs). */
 int stove_tc3_gemm(int64_t M, int64_t N, int64_t K, const float* A_pl, int64_t lda, int64_t a_plane,
                    const float* B_pl, int64_t ldb, int64_t b_plane, float* D, int64_t ldd, int parts,
-                   int64_t part_stride, void* stream);
+                   int64_t part_stride, int bn, void* stream);
 int stove_tc3_gemm_parts(int64_t M, int64_t N, int64_t K, int want);
 
 /* Gate/state backward of one LSTM step.  g_h = g_h_a (row stride g_h_a_ld) + the g_h_b_parts split-K parts

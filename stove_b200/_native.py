@@ -102,7 +102,7 @@ SIGNATURES = {
     'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, vp]),
     'stove_split_planes': (C.c_int, [i64, C.c_int, vp, i64, vp, vp, i64, vp]),
-    'stove_tc3_gemm': (C.c_int, [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, C.c_int, i64, vp]),
+    'stove_tc3_gemm': (C.c_int, [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, C.c_int, i64, C.c_int, vp]),
     'stove_tc3_gemm_parts': (C.c_int, [i64, i64, i64, C.c_int]),
     'stove_lstm_cell_bwd_t': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, C.c_int, vp, vp, vp, i64, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp]),
     'stove_sum_parts': (C.c_int, [i64, C.c_int, i64, vp, vp, vp]),

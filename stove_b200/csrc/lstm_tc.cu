@@ -369,7 +369,7 @@ template <int BN>
 struct GemmPlan {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE = 2 * TILE_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE;
+    static constexpr int STAGES = (192 * 1024) / STAGE;       // BN = 64: 4, 128: 3, 256: 2
     static constexpr int RING = STAGES * STAGE;
     static constexpr int OFF_BAR = RING;
     static constexpr int SMEM = OFF_BAR + 256 + 1024;
@@ -737,7 +737,7 @@ extern "C" int stove_lstm_gemm_cell_fwd(int64_t n, int H, int64_t K, const float
 
 extern "C" int stove_tc3_gemm(int64_t M, int64_t Nn, int64_t K, const float* A_pl, int64_t lda, int64_t a_plane,
                               const float* B_pl, int64_t ldb, int64_t b_plane, float* D, int64_t ldd, int parts,
-                              int64_t part_stride, void* stream) {
+                              int64_t part_stride, int bn, void* stream) {
     using namespace lt;
     STOVE_CHECK_ARG(M > 0 && Nn > 0 && K > 0 && A_pl && B_pl && D && parts >= 1, "bad argument");
     STOVE_CHECK_ARG(lda >= K && ldb >= K && ldd >= Nn && lda % 4 == 0 && ldb % 4 == 0 && ldd % 4 == 0 &&
@@ -749,7 +749,11 @@ extern "C" int stove_tc3_gemm(int64_t M, int64_t Nn, int64_t K, const float* A_p
     const int kb_per = (num_kb + parts - 1) / parts;
     parts = (num_kb + kb_per - 1) / kb_per;                // no empty split
     STOVE_CHECK_ARG(parts == 1 || part_stride >= M * ldd, "part_stride too small");
-    const int BN = Nn > 64 ? 128 : 64;
+    // tile width: 128 x 256 tiles take a quarter less operand traffic than 128 x 128 ones (these GEMMs are bound
+    // by operand delivery from L2) but halve the CTA count; the caller asks for them where N >= 256 and split-K
+    // still fills the machine (the weight gradients)
+    STOVE_CHECK_ARG(bn == 0 || bn == 64 || bn == 128 || bn == 256, "bn must be 0 (auto), 64, 128 or 256");
+    const int BN = bn ? bn : (Nn > 64 ? 128 : 64);
     GemmMaps m;
     memset(&m, 0, sizeof(m));
     int rc = make_map(&m.A, A_pl, M, K, lda, BM, 2, a_plane);
@@ -757,6 +761,7 @@ extern "C" int stove_tc3_gemm(int64_t M, int64_t Nn, int64_t K, const float* A_p
     if (rc == STOVE_OK) rc = make_map(&m.D, D, M, Nn, ldd, BM, parts, parts > 1 ? part_stride : M * ldd);
     if (rc != STOVE_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (BN == 256) return launch_gemm<256>(m, M, Nn, num_kb, parts, s);
     return BN == 128 ? launch_gemm<128>(m, M, Nn, num_kb, parts, s) : launch_gemm<64>(m, M, Nn, num_kb, parts, s);
 }
 

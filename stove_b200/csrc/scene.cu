@@ -17,6 +17,7 @@
 struct SceneDims {
     int O, C, A, B, pa, pb, align;
 };
+constexpr int SCENE_MAXC = 4;       // scene_bwd keeps one column-sum register per 32 columns: B <= 128
 
 __device__ __forceinline__ float base_coord(int k, int n_out, int align) {
     if (align) return (n_out > 1) ? (2.f * k) / (float)(n_out - 1) - 1.f : -1.f;
@@ -194,7 +195,9 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
     float* tY = gpx + d.B;
     float* dY = tY + d.A;
     float* gpy = dY + d.A;
-    float* red = smem + ((((d.C + d.O + 1) * AB + 3 * (d.A + d.B)) + 3) & ~3);   // [32], 16-byte aligned
+    float* colp = gpy + d.A;            // [nwarp][B] column sums per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float* red = smem + ((((d.C + d.O + 1) * AB + 3 * (d.A + d.B) + nwarp * d.B) + 3) & ~3);   // [32], 16-byte aligned
     const int64_t f = blockIdx.x;
     const int tid = threadIdx.x;
     const int shB = (d.B & (d.B - 1)) == 0 ? __ffs(d.B) - 1 : -1;      // row index without a division when B = 2^k
@@ -231,30 +234,48 @@ __global__ void __launch_bounds__(256) scene_bwd_kernel(SceneDims d, const float
         const float* bgo = bgs + o * AB;
         paste_tents(d, sx, sy, tx, ty, tX, tY, dX, dY);
         __syncthreads();
-        // clamp backward: pass where 0 <= bg + paste <= 1
-        for (int i = tid; i < AB; i += blockDim.x) {
-            const int u = shB >= 0 ? i >> shB : i / d.B, v = i - u * d.B;
-            const float pre = bgo[i] + tY[u] * tX[v];
-            if (!(pre >= 0.f && pre <= 1.f)) Gb[i] = 0.f;
+        // One pass over the frame: clamp backward (pass where 0 <= bg + paste <= 1) and, with paste = tY[u] tX[v],
+        // the row sums (-> d/d tY) and column sums (-> d/d tX) of the surviving gradient.  Warp = rows u, u + 8, ...;
+        // lane = column: row sums by shuffle, column sums in registers, combined over the warps through `colp`.
+        // (Round 1 ran three passes -- clamp, row sums, then column sums on 32 of the 256 threads -- and was
+        // issue bound: 23 k warp instructions per frame, profiles/r01_ncu_full_spn_scene_v2.txt.)
+        {
+            float colacc[SCENE_MAXC];
+#pragma unroll
+            for (int c = 0; c < SCENE_MAXC; ++c) colacc[c] = 0.f;
+            for (int u = warp; u < d.A; u += nwarp) {
+                const float tyu = tY[u];
+                float racc = 0.f;
+#pragma unroll
+                for (int c = 0; c < SCENE_MAXC; ++c) {
+                    const int v = lane + 32 * c;
+                    if (v < d.B) {
+                        const int i = u * d.B + v;
+                        const float txv = tX[v];
+                        const float pre = bgo[i] + tyu * txv;
+                        float g = Gb[i];
+                        if (!(pre >= 0.f && pre <= 1.f)) {
+                            g = 0.f;
+                            Gb[i] = 0.f;
+                        }
+                        racc = fmaf(g, txv, racc);
+                        colacc[c] = fmaf(g, tyu, colacc[c]);
+                    }
+                }
+                racc = warp_sum(racc);
+                if (lane == 0) gpy[u] = racc * dY[u];
+            }
+#pragma unroll
+            for (int c = 0; c < SCENE_MAXC; ++c) {
+                const int v = lane + 32 * c;
+                if (v < d.B) colp[warp * d.B + v] = colacc[c];
+            }
         }
         __syncthreads();
-        // paste = tY[u] * tX[v]
-        // column sums: thread = column (conflict free); row sums: warp = row, lanes stride the row
-        // (a thread per row walks a stride-B column of banks: 54 % of this kernel's shared-memory
-        // wavefronts were bank conflicts)
-        {
-            const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-            for (int u = warp; u < d.A; u += nwarp) {
-                float acc = 0.f;
-                for (int v = lane; v < d.B; v += 32) acc = fmaf(Gb[u * d.B + v], tX[v], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) gpy[u] = acc * dY[u];
-            }
-            for (int k = tid; k < d.B; k += blockDim.x) {
-                float acc = 0.f;
-                for (int u = 0; u < d.A; ++u) acc = fmaf(Gb[u * d.B + k], tY[u], acc);
-                gpx[k] = acc * dX[k];
-            }
+        for (int k = tid; k < d.B; k += blockDim.x) {
+            float acc = 0.f;
+            for (int w = 0; w < nwarp; ++w) acc += colp[w * d.B + k];
+            gpx[k] = acc * dX[k];
         }
         __syncthreads();
         float gsx = 0.f, gsy = 0.f, gtx = 0.f, gty = 0.f;
@@ -348,9 +369,10 @@ extern "C" int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, in
     STOVE_CHECK_ARG(img && z && g_z, "null pointer");
     if (F == 0) return STOVE_OK;
     SceneDims d{O, C, A, B, pa, pb, align_corners};
-    const size_t smem = sizeof(float) * ((size_t)(C + O + 1) * A * B + 3 * (A + B) + 4 + 32);
-    if (smem > 227 * 1024) {
-        stove_set_error("stove_scene_bwd: frame/objects too large for shared memory (%zu B)", smem);
+    const size_t smem = sizeof(float) * ((size_t)(C + O + 1) * A * B + 3 * (A + B) + 8 * B + 4 + 32);
+    if (smem > 227 * 1024 || B > 32 * SCENE_MAXC) {
+        stove_set_error("stove_scene_bwd: frame/objects too large (%zu B of shared memory, last axis %d > %d)", smem, B,
+                        32 * SCENE_MAXC);
         return STOVE_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)

@@ -373,9 +373,10 @@ def split_planes(x, planes=True, transposed=False):
     return pl, plT
 
 
-def tc3_gemm(a_pl, b_pl, K=None, parts=1, out=None):
+def tc3_gemm(a_pl, b_pl, K=None, parts=1, out=None, bn=0):
     """a_pl (2, M, lda), b_pl (2, N, ldb): (hi, lo) planes -> a @ b.t() over the first K columns as
-    `parts` split-K partial products (parts, M, N) (parts may come back smaller), 3xTF32 on tcgen05."""
+    `parts` split-K partial products (parts, M, N) (parts may come back smaller), 3xTF32 on tcgen05.
+    bn: tile width (0 = automatic, 256 = fewest operand bytes)."""
     M, lda = a_pl.shape[1], a_pl.shape[2]
     Nn, ldb = b_pl.shape[1], b_pl.shape[2]
     K = min(lda, ldb) if K is None else K
@@ -383,7 +384,7 @@ def tc3_gemm(a_pl, b_pl, K=None, parts=1, out=None):
     if out is None:
         out = torch.empty(parts, M, Nn, device=a_pl.device, dtype=a_pl.dtype)
     N.check(N.lib().stove_tc3_gemm(M, Nn, K, N.ptr(a_pl), lda, a_pl.stride(0), N.ptr(b_pl), ldb, b_pl.stride(0),
-                                   N.ptr(out), Nn, parts, M * Nn, N.stream()))
+                                   N.ptr(out), Nn, parts, M * Nn, bn, N.stream()))
     return out
 
 
@@ -399,9 +400,10 @@ def sum_parts(parts_t, out=None):
     return out
 
 
-def _split_k(tiles, num_kb, sms=148):
-    """split-K factor that fills the machine: about one CTA per SM, at least 4 k-blocks per part"""
-    return max(1, min(sms // max(tiles, 1), num_kb // 4))
+def _split_k(tiles, num_kb, sms=148, cap=8):
+    """split-K factor that fills the machine: about one CTA per SM, at least 4 k-blocks per part, at most `cap`
+    parts (every part is another partial product to write and sum)"""
+    return max(1, min(sms // max(tiles, 1), num_kb // 4, cap))
 
 
 _AUX_STREAMS = {}
@@ -573,8 +575,9 @@ class LstmEncoder(torch.autograd.Function):
                 # (profiles/r02_timeline_v1_lstm_planes.txt: 40 us + 17 us of reductions behind the W_ih GEMM)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    tiles = (H4 // 128) * ((H + 127) // 128)
-                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
+                    bn = 256 if H % 256 == 0 else 0
+                    tiles = (H4 // 128) * ((H + (bn or 128) - 1) // (bn or 128))
+                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32, sms=64), bn=bn))
                 for t_ in (gT_all, hT_all):
                     t_.record_stream(side)
         if steps == 1:
@@ -590,8 +593,9 @@ class LstmEncoder(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
                 xT_pl.record_stream(cur)
-                tiles = (H4 // 128) * ((K + 127) // 128)
-                g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
+                bn = 256 if K >= 512 else 0
+                tiles = (H4 // 128) * ((K + (bn or 128) - 1) // (bn or 128))
+                g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32), bn=bn))
             cur.wait_stream(side)                  # head, W_hh and bias gradients
         else:
             cur.wait_stream(side)                  # head, W_hh and bias gradients
@@ -614,8 +618,9 @@ class LstmEncoder(torch.autograd.Function):
                 for lo, hi in ((0, half), (half, H4)):
                     if lo >= hi:
                         continue
-                    tiles = ((hi - lo + 127) // 128) * ((K + 127) // 128)
-                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)), out=g_wih[lo:hi])
+                    bn = 256 if K >= 512 else 0
+                    tiles = ((hi - lo + 127) // 128) * ((K + (bn or 128) - 1) // (bn or 128))
+                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4), bn=bn), out=g_wih[lo:hi])
                     sink('w_ih', g_wih, lo, hi)
                     sink.flush(send=True)          # all-reduce of everything gathered so far
         for t_ in (g_whh, g_b) + g_head:

@@ -59,9 +59,12 @@ def test_tc3_gemm_vs_fp64(M, Nn, K, parts):
     a_pl, aT_pl = ops.split_planes(a, True, True)
     assert torch.equal(a_pl[0] + a_pl[1], a) and torch.equal(a_pl[0], (a.view(torch.int32) & -8192).view(torch.float32))
     assert torch.equal(aT_pl[:, :, :M], a_pl.transpose(1, 2)) and not aT_pl[:, :, M:].any()
-    d = ops.sum_parts(ops.tc3_gemm(a_pl, ops.split_planes(b)[0], parts=parts))
+    b_pl = ops.split_planes(b)[0]
+    d = ops.sum_parts(ops.tc3_gemm(a_pl, b_pl, parts=parts))
     ref = a.double() @ b.double().t()
     assert _rel(d, ref) < 1e-5
+    for bn in (64, 256):                                # the other tile widths: same numbers up to summation order
+        assert _rel(ops.sum_parts(ops.tc3_gemm(a_pl, b_pl, parts=parts, bn=bn)), ref) < 1e-5
     if K % 4 == 0 and M % 4 == 0:
         # contraction over the rows through the transposed planes (the weight-gradient form): a^T a
         dt = ops.sum_parts(ops.tc3_gemm(ops.split_planes(a.t().contiguous())[0], aT_pl[:, :, :], parts=1))
