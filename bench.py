@@ -748,10 +748,11 @@ def dp_gradient_check(model, dev, world, rank):
         stacked = False
 
         def __init__(self, lo, hi):
-            self.d = [d[lo:hi].to(dev) for d in draws]
+            self.d, self.at = [d[lo:hi].to(dev) for d in draws], 0      # kept referenced: consumed on a side stream
 
         def __call__(self, shape, like):
-            return self.d.pop(0)
+            self.at += 1
+            return self.d[self.at - 1]
 
     eng = dp.DataParallel(model, broadcast=False)
     shard = full[rank * n_loc:(rank + 1) * n_loc]

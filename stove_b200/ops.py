@@ -575,9 +575,10 @@ class LstmEncoder(torch.autograd.Function):
                 # (profiles/r02_timeline_v1_lstm_planes.txt: 40 us + 17 us of reductions behind the W_ih GEMM)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
-                    bn = 256 if H % 256 == 0 else 0
-                    tiles = (H4 // 128) * ((H + (bn or 128) - 1) // (bn or 128))
-                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32, sms=64), bn=bn))
+                    # (128 x 256 tiles -- a quarter less operand traffic, two pipeline stages instead of three --
+                    # measured slower here: 40 vs 29 us, profiles/r02_timeline_v3_bn256.txt)
+                    tiles = (H4 // 128) * ((H + 127) // 128)
+                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
                 for t_ in (gT_all, hT_all):
                     t_.record_stream(side)
         if steps == 1:
@@ -593,9 +594,8 @@ class LstmEncoder(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
                 xT_pl.record_stream(cur)
-                bn = 256 if K >= 512 else 0
-                tiles = (H4 // 128) * ((K + (bn or 128) - 1) // (bn or 128))
-                g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32), bn=bn))
+                tiles = (H4 // 128) * ((K + 127) // 128)
+                g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
             cur.wait_stream(side)                  # head, W_hh and bias gradients
         else:
             cur.wait_stream(side)                  # head, W_hh and bias gradients
@@ -618,9 +618,8 @@ class LstmEncoder(torch.autograd.Function):
                 for lo, hi in ((0, half), (half, H4)):
                     if lo >= hi:
                         continue
-                    bn = 256 if K >= 512 else 0
-                    tiles = ((hi - lo + 127) // 128) * ((K + (bn or 128) - 1) // (bn or 128))
-                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4), bn=bn), out=g_wih[lo:hi])
+                    tiles = ((hi - lo + 127) // 128) * ((K + 127) // 128)
+                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4)), out=g_wih[lo:hi])
                     sink('w_ih', g_wih, lo, hi)
                     sink.flush(send=True)          # all-reduce of everything gathered so far
         for t_ in (g_whh, g_b) + g_head:

@@ -84,7 +84,15 @@ class Stove(nn.Module):
         fn = self._standard_normal
         if getattr(fn, 'stacked', True):
             return fn((count,) + tuple(shape), like)
-        return torch.stack([fn(tuple(shape), like) for _ in range(count)], 0)
+        draws = [fn(tuple(shape), like) for _ in range(count)]
+        if like.is_cuda:
+            # this runs on the packing side stream: tensors handed in from outside were allocated elsewhere and must
+            # not return to the allocator before the copy below has read them
+            here = torch.cuda.current_stream(like.device)
+            for d in draws:
+                if d.is_cuda:
+                    d.record_stream(here)
+        return torch.stack(draws, 0)
 
     # -- small sequence helpers ---------------------------------------------------------------
     def v_from_state(self, z_sup):

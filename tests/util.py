@@ -86,14 +86,23 @@ class Checker:
 
 class NoiseReplay:
     """Stands in for Stove._standard_normal: replays a list of draws (shape-checked), one draw per
-    call in the reference's order (`stacked = False`, see Stove._standard_normal_n)."""
+    call in the reference's order (`stacked = False`, see Stove._standard_normal_n).
+
+    The draws stay referenced for the life of the replay object: the model consumes them on a SIDE stream (the
+    packing stream, stove.py: stove_forward), and a draw that lost its last reference right after being handed
+    out would return to the caching allocator -- which may give the block to the next allocation on the main
+    stream before the side stream has read it.  (Found with compute-sanitizer racecheck slowing the GPU down:
+    the golden test failed only in sequence, never with CUDA_LAUNCH_BLOCKING=1 or without the caching allocator.
+    The product path draws its noise ON that side stream and is not affected.)"""
     stacked = False
 
     def __init__(self, draws, device):
         self.draws = [d.to(device=device, dtype=torch.float32) for d in draws]
+        self.at = 0
 
     def __call__(self, shape, like):
-        d = self.draws.pop(0)
+        d = self.draws[self.at]
+        self.at += 1
         assert tuple(d.shape) == tuple(shape), (d.shape, shape)
         return d
 
