@@ -298,7 +298,8 @@ __global__ void head_bwd_reduce_kernel(int K, int J, int P, int nslab, const flo
 
 static int par_ctas(int64_t R) {
     int64_t c = (R + PAR_ROWS - 1) / PAR_ROWS;
-    return (int)(c < 148 ? (c < 1 ? 1 : c) : 148);
+    const int cap = stove_opt(OPT_HEAD_PAR_CTAS) > 0 ? stove_opt(OPT_HEAD_PAR_CTAS) : 148;
+    return (int)(c < cap ? (c < 1 ? 1 : c) : cap);
 }
 static bool dims_ok(int K, int J, int P) { return K > 0 && K <= KMAX && K % 32 == 0 && J > 0 && J <= JP && P > 0 && P <= PMAX; }
 }  // namespace eh

@@ -531,7 +531,13 @@ __global__ void split_planes_kernel(int64_t rows, int cols, const float* __restr
     }
 }
 
-// Gate/state backward of one LSTM step.  Block (32, 8) owns 32 frames x 32 hidden units x 4 gates.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 hi4(float4 a) { return make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w)); }
+
+// Gate/state backward of one LSTM step.  A block of 256 threads owns 32 frames x 32 hidden units x 4 gates.
 //   g_h = g_h_a (strided slice of the stacked gradient) + split-K parts of the hidden-state GEMM
 //   g_pl  [2][n][4H]   : (hi, lo) planes of this step's gate gradient (left operand of the hidden-state GEMM) | null
 //   gT    [2][4H][ldT] : transposed planes (left operand of a weight-gradient GEMM) of this step's gate gradient,
@@ -539,68 +545,84 @@ __global__ void split_planes_kernel(int64_t rows, int cols, const float* __restr
 //                        written as zero (a step's block of a buffer stacked along the columns) | null
 //   g_acc [n][4H]      : running sum over steps (acc_mode 0: start, 1: add); not written back when emit_acc
 //   bias_part [gridDim.y][4H] : column sums of the (accumulated) gate gradient over this block's frames | null
-__global__ void lstm_cell_bwd_t_kernel(int64_t n, int H, const float* __restrict__ act, const float* __restrict__ c_prev,
-                                       const float* __restrict__ c_out, const float* __restrict__ g_h_a,
-                                       int64_t g_h_a_ld, const float* __restrict__ g_h_b, int g_h_b_parts,
-                                       const float* __restrict__ g_c, float* __restrict__ g_pl,
-                                       float* __restrict__ gT, int64_t ldT, int64_t spanT, int64_t gT_plane, float* __restrict__ g_acc,
-                                       int acc_mode, int emit_acc, float* __restrict__ bias_part,
-                                       float* __restrict__ g_c_prev) {
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_t_kernel(int64_t n, int H, const float* __restrict__ act, const float* __restrict__ c_prev,
+                       const float* __restrict__ c_out, const float* __restrict__ g_h_a, int64_t g_h_a_ld,
+                       const float* __restrict__ g_h_b, int g_h_b_parts, const float* __restrict__ g_c,
+                       float* __restrict__ g_pl, float* __restrict__ gT, int64_t ldT, int64_t spanT, int64_t gT_plane,
+                       float* __restrict__ g_acc, int acc_mode, int emit_acc, float* __restrict__ bias_part,
+                       float* __restrict__ g_c_prev) {
     __shared__ float sh[2][4][32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = threadIdx.x;
     const int64_t b0 = (int64_t)blockIdx.y * 32;
-    const int k0 = blockIdx.x * 32, k = k0 + tx;
+    const int k0 = blockIdx.x * 32;
     const int64_t H4 = 4 * (int64_t)H;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int bb = ty + 8 * i;
+    {
+        // phase 1: thread = (frame, four consecutive hidden units): 16-byte loads / stores, a warp covers four
+        // whole 128-byte rows of every operand
+        const int quad = tid & 7, bb = tid >> 3;
+        const int k = k0 + 4 * quad;
         const int64_t b = b0 + bb;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b < n) {
             const int64_t e = b * H + k;
-            const float* pa = act + b * H4;
-            const float ig = pa[k], fg = pa[H + k], gg = pa[2 * H + k], og = pa[3 * H + k];
-            const float tc = tanhf(c_out[e]);
-            float gh = g_h_a[b * g_h_a_ld + k];
+            const float* pa = act + b * H4 + k;
+            const float4 ig = ld4(pa), fg = ld4(pa + H), gg = ld4(pa + 2 * H), og = ld4(pa + 3 * H);
+            const float4 co = ld4(c_out + e);
+            float4 gh = ld4(g_h_a + b * g_h_a_ld + k);
             if (g_h_b)
-                for (int part = 0; part < g_h_b_parts; ++part) gh += g_h_b[(int64_t)part * n * H + e];
-            const float gc = (g_c ? g_c[e] : 0.f) + gh * og * (1.f - tc * tc);
-            const float cp = c_prev ? c_prev[e] : 0.f;
-            float g[4];
-            g[0] = gc * gg * ig * (1.f - ig);
-            g[1] = gc * cp * fg * (1.f - fg);
-            g[2] = gc * ig * (1.f - gg * gg);
-            g[3] = gh * tc * og * (1.f - og);
+                for (int part = 0; part < g_h_b_parts; ++part) gh = add4(gh, ld4(g_h_b + (int64_t)part * n * H + e));
+            const float4 gcn = g_c ? ld4(g_c + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 cp = c_prev ? ld4(c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g[4], gcp;
+#define LT_BWD(X)                                                           \
+    {                                                                       \
+        const float tc = tanhf(co.X);                                       \
+        const float gc = gcn.X + gh.X * og.X * (1.f - tc * tc);             \
+        g[0].X = gc * gg.X * ig.X * (1.f - ig.X);                           \
+        g[1].X = gc * cp.X * fg.X * (1.f - fg.X);                           \
+        g[2].X = gc * ig.X * (1.f - gg.X * gg.X);                           \
+        g[3].X = gh.X * tc * og.X * (1.f - og.X);                           \
+        gcp.X = gc * fg.X;                                                  \
+    }
+            LT_BWD(x) LT_BWD(y) LT_BWD(z) LT_BWD(w)
+#undef LT_BWD
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int64_t o = b * H4 + q * H + k;
-                const float a = acc_mode ? g_acc[o] + g[q] : g[q];
-                if (!emit_acc) g_acc[o] = a;
+                const float4 a = acc_mode ? add4(ld4(g_acc + o), g[q]) : g[q];
+                if (!emit_acc) st4(g_acc + o, a);
                 if (g_pl) {
-                    const float gh_ = tf32_hi(g[q]);
-                    g_pl[o] = gh_;
-                    g_pl[n * H4 + o] = g[q] - gh_;
+                    const float4 hi = hi4(g[q]);
+                    st4(g_pl + o, hi);
+                    st4(g_pl + n * H4 + o, sub4(g[q], hi));
                 }
                 v[q] = emit_acc ? a : g[q];
             }
-            if (g_c_prev) g_c_prev[e] = gc * fg;
+            if (g_c_prev) st4(g_c_prev + e, gcp);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float vh = tf32_hi(v[q]);
-            sh[0][q][bb][tx] = vh;
-            sh[1][q][bb][tx] = v[q] - vh;
+            const float4 hi = hi4(v[q]), lo = sub4(v[q], hi);
+            float* s0 = &sh[0][q][bb][4 * quad];
+            float* s1 = &sh[1][q][bb][4 * quad];
+            s0[0] = hi.x; s0[1] = hi.y; s0[2] = hi.z; s0[3] = hi.w;
+            s1[0] = lo.x; s1[1] = lo.y; s1[2] = lo.z; s1[3] = lo.w;
         }
     }
     if (!gT && !bias_part) return;
     __syncthreads();
+    // phase 2: lane = frame, warp = hidden unit (+ 8 i): transposed planes as coalesced 128-byte rows
+    const int lane = tid & 31, wp = tid >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int kk = ty + 8 * i;
-        const int64_t b = b0 + tx;
+        const int kk = wp + 8 * i;
+        const int64_t b = b0 + lane;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float vh = sh[0][q][tx][kk], vl = sh[1][q][tx][kk];
+            const float vh = sh[0][q][lane][kk], vl = sh[1][q][lane][kk];
             if (gT && b < spanT) {
                 const int64_t o = (int64_t)(q * H + k0 + kk) * ldT + b;
                 gT[o] = vh;
@@ -608,7 +630,7 @@ __global__ void lstm_cell_bwd_t_kernel(int64_t n, int H, const float* __restrict
             }
             if (bias_part) {
                 const float s = warp_sum(vh + vl);         // hi + lo is the fp32 value again, exactly
-                if (tx == 0) bias_part[(int64_t)blockIdx.y * H4 + q * H + k0 + kk] = s;
+                if (lane == 0) bias_part[(int64_t)blockIdx.y * H4 + q * H + k0 + kk] = s;
             }
         }
     }
@@ -795,6 +817,10 @@ extern "C" int stove_lstm_cell_bwd_t(int64_t n, int H, const float* act, const f
                                      void* stream) {
     STOVE_CHECK_ARG(n >= 0 && H > 0 && H % 32 == 0 && act && c_out && g_h_a && g_h_a_ld >= H, "bad argument");
     STOVE_CHECK_ARG(g_acc || (emit_acc && !acc_mode), "g_acc is required unless this is the only step");
+    STOVE_CHECK_ARG(g_h_a_ld % 4 == 0 && (((uintptr_t)act | (uintptr_t)c_prev | (uintptr_t)c_out | (uintptr_t)g_h_a |
+                                            (uintptr_t)g_h_b | (uintptr_t)g_c | (uintptr_t)g_pl | (uintptr_t)g_acc |
+                                            (uintptr_t)g_c_prev) & 15) == 0,
+                    "pointers must be 16-byte aligned and g_h_a_ld a multiple of 4");
     STOVE_CHECK_ARG(!g_h_b || g_h_b_parts >= 1, "g_h_b_parts must be >= 1");
     STOVE_CHECK_ARG(!gT_pl || (spanT >= n && ldT >= spanT && gT_plane >= 4 * (int64_t)H * ldT),
                     "gT_pl needs ldT >= spanT >= n and room for a plane");
@@ -802,7 +828,7 @@ extern "C" int stove_lstm_cell_bwd_t(int64_t n, int H, const float* act, const f
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t span = gT_pl && spanT > n ? spanT : n;
     const dim3 grid((unsigned)(H / 32), (unsigned)((span + 31) / 32));
-    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lt::lstm_cell_bwd_t_kernel<<<grid, dim3(32, 8), 0, s>>>(
+    STOVE_KERNEL(K_LSTM_CELL_BWD, s, lt::lstm_cell_bwd_t_kernel<<<grid, 256, 0, s>>>(
         n, H, act, c_prev, c_out, g_h_a, g_h_a_ld, g_h_b, g_h_b_parts, g_c, g_pl, gT_pl, ldT, spanT, gT_plane, g_acc, acc_mode,
         emit_acc, bias_part, g_c_prev));
     STOVE_LAUNCH_CHECK();

@@ -409,11 +409,11 @@ def _split_k(tiles, num_kb, sms=148, cap=8):
 _AUX_STREAMS = {}
 
 
-def _aux_stream(device):
-    """Library-wide side stream (per device) for work that is off the critical chain of a backward pass."""
+def _aux_stream(device, which=0):
+    """Library-wide side streams (per device) for work that is off the critical chain of a backward pass."""
     if not _FORK:                                    # serial execution (per-kernel timing passes)
         return torch.cuda.current_stream(device)
-    key = (device.type, device.index)
+    key = (device.type, device.index, which)
     if key not in _AUX_STREAMS:
         _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
     return _AUX_STREAMS[key]
@@ -443,12 +443,15 @@ class LstmEncoder(torch.autograd.Function):
         cur, side = torch.cuda.current_stream(dev), _aux_stream(dev)
         side.wait_stream(cur)
         with torch.cuda.stream(side), torch.no_grad():
+            # what step 0 needs comes first and has its own event: the chain starts ~5 us earlier
             wih_pl, _ = split_planes(w_ih.detach())
-            whh_pl, whhT_pl = split_planes(w_hh.detach(), True, True)
             bias = (b_ih.detach() + b_hh.detach()).contiguous()
+            ready0 = torch.cuda.Event()
+            ready0.record(side)
+            whh_pl, whhT_pl = split_planes(w_hh.detach(), True, True)
             done = torch.cuda.Event()
             done.record(side)
-        return wih_pl, whh_pl, whhT_pl, bias, done
+        return wih_pl, whh_pl, whhT_pl, bias, (ready0, done)
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, steps, w1=None, b1=None, w2=None, b2=None, prepared=None, x_pl=None):
@@ -462,13 +465,13 @@ class LstmEncoder(torch.autograd.Function):
         cur = torch.cuda.current_stream(dev)
         if prepared is None:
             prepared = LstmEncoder.prepare(w_ih, w_hh, b_ih, b_hh)
-        wih_pl, whh_pl, whhT_pl, bias, done = prepared
+        wih_pl, whh_pl, whhT_pl, bias, (ready0, done) = prepared
         x = x.contiguous()
         if x_pl is None:                                   # (bw_transform can emit the planes in its own pass)
             x_pl, _ = split_planes(x)
         # the transposed planes (right operand of g^T x) are only needed by the backward pass, which builds them
         # off the chain
-        cur.wait_event(done)
+        cur.wait_event(ready0)                             # W_ih planes and the bias; W_hh's are awaited before step 1
         for t_ in (wih_pl, whh_pl, whhT_pl, bias):
             t_.record_stream(cur)
         out = torch.empty(n, steps, H, device=dev, dtype=dt)
@@ -493,6 +496,8 @@ class LstmEncoder(torch.autograd.Function):
                                                      None, N.ptr(gx), out[:, t].data_ptr(), steps * H, N.ptr(c),
                                                      N.ptr(act), N.ptr(h_pl_next), hT, ldS, ldT, H * ldS, st))
             else:
+                if t == 1:
+                    cur.wait_event(done)
                 N.check(lib.stove_lstm_gemm_cell_fwd(n, H, H, N.ptr(h_pl), N.ptr(whh_pl), N.ptr(gx), 0,
                                                      N.ptr(c_prev), None, out[:, t].data_ptr(), steps * H, N.ptr(c),
                                                      N.ptr(act), N.ptr(h_pl_next), hT, ldS, ldT, H * ldS, st))
@@ -530,11 +535,13 @@ class LstmEncoder(torch.autograd.Function):
             hs, w1, w2, hidden = ctx.head
             g_zp = g_out.view(n * steps, w2.shape[0])
             g_hs, ws = _head_bwd_data(hs, w1, w2, hidden, g_zp)       # on the chain: the LSTM backward needs it
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):                              # off the chain: joined at the end
+            # off the chain, on a stream of its own (the W_hh gradient GEMM must not queue behind it), joined at the end
+            side2 = _aux_stream(dev, 1)
+            side2.wait_stream(cur)
+            with torch.cuda.stream(side2):
                 g_head = _head_bwd_params(hs, w1, w2, hidden, g_zp, ws)
             for t_ in (ws, g_zp, hs, hidden) + g_head:
-                t_.record_stream(side)
+                t_.record_stream(side2)
             g_out = g_hs.view(n, steps, H)
         if ctx.needs_input_grad[0]:
             raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
@@ -596,9 +603,11 @@ class LstmEncoder(torch.autograd.Function):
                 xT_pl.record_stream(cur)
                 tiles = (H4 // 128) * ((K + 127) // 128)
                 g_wih = sum_parts(tc3_gemm(gsumT, xT_pl, parts=_split_k(tiles, (ldT + 31) // 32)))
-            cur.wait_stream(side)                  # head, W_hh and bias gradients
+            cur.wait_stream(side)                  # W_hh and bias gradients
         else:
-            cur.wait_stream(side)                  # head, W_hh and bias gradients
+            cur.wait_stream(side)                  # W_hh and bias gradients
+            if ctx.head is not None:
+                cur.wait_stream(_aux_stream(dev, 1))   # head gradients
             # data-parallel run: gradients are handed to the engine's sink the moment they exist, so their
             # all-reduce overlaps what is still being computed: W_hh / biases / head are gathered into the bucket
             # now, W_ih follows in two row blocks -- the first block (with everything before it) is on the wire
@@ -622,6 +631,8 @@ class LstmEncoder(torch.autograd.Function):
                     sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4)), out=g_wih[lo:hi])
                     sink('w_ih', g_wih, lo, hi)
                     sink.flush(send=True)          # all-reduce of everything gathered so far
+        if ctx.head is not None:
+            cur.wait_stream(_aux_stream(dev, 1))   # head gradients
         for t_ in (g_whh, g_b) + g_head:
             if t_ is not None:
                 t_.record_stream(cur)
