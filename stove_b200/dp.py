@@ -208,6 +208,14 @@ class _Overlap:
         `multimem.st` kernel -- torch's symm_mem::multimem_all_reduce_ -- instead of NCCL's ring: 25 us instead
         of 62 us for the whole 5.6 MB bucket on 8 GPUs, 15 us instead of 36 us for 1.4 MB
         (profiles/r02_allreduce_bench_N8.json).  Falls back to NCCL when the fabric has no multicast."""
+        def agree(ok):
+            """every rank takes part, whatever happened locally: the ranks must not diverge on the collectives"""
+            t = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return float(t) == 1.0
+
+        buf = op = group = None
+        why = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
             group = dist.group.WORLD.group_name
@@ -216,7 +224,14 @@ class _Overlap:
             if not getattr(hdl, 'multicast_ptr', 0):
                 raise RuntimeError('no multicast support')
             op = torch.ops.symm_mem.multimem_all_reduce_
-            # trial on the two kinds of ranges the exchange uses (a prefix and the remainder), against NCCL
+        except Exception as e:                      # noqa: BLE001 -- any failure here means: use NCCL
+            why = repr(e)
+        if not agree(why is None):
+            if required:
+                raise RuntimeError('stove_b200.dp: symmetric-memory all-reduce is not available: %s' % (why or 'on another rank'))
+            return
+        # trial on the two kinds of ranges the exchange uses (a prefix and the remainder), against NCCL
+        try:
             cut = (self.total_padded // 2) // _ALIGN * _ALIGN
             buf.copy_(torch.arange(self.total_padded, device=dev, dtype=torch.float32) % 251 * (1 + rank()))
             ref = buf.clone()
@@ -224,17 +239,16 @@ class _Overlap:
             op(buf[:cut], 'sum', group)
             op(buf[cut:], 'sum', group)
             torch.cuda.synchronize(dev)
-            ok = torch.tensor([float(torch.equal(buf, ref) or bool(((buf - ref).abs() <= 1e-3 * ref.abs()).all()))], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if float(ok) != 1.0:
-                raise RuntimeError('trial all-reduce through symmetric memory disagrees with NCCL')
-            buf.zero_()
-            self.symm = (op, group)
-            self.symm_buf = buf
-        except Exception as e:                      # noqa: BLE001 -- any failure here means: use NCCL
-            self.symm = None
+            good = bool(((buf - ref).abs() <= 1e-3 * ref.abs()).all())
+        except Exception as e:                      # noqa: BLE001
+            good, why = False, repr(e)
+        if not agree(good):
             if required:
-                raise RuntimeError('stove_b200.dp: symmetric-memory all-reduce is not available: %r' % (e,))
+                raise RuntimeError('stove_b200.dp: trial all-reduce through symmetric memory failed: %s' % (why or 'mismatch'))
+            return
+        buf.zero_()
+        self.symm = (op, group)
+        self.symm_buf = buf
 
     def _all_reduce(self, lo, hi):
         """on the communication stream"""
