@@ -585,7 +585,7 @@ class LstmEncoder(torch.autograd.Function):
                     # (128 x 256 tiles -- a quarter less operand traffic, two pipeline stages instead of three --
                     # measured slower here: 40 vs 29 us, profiles/r02_timeline_v3_bn256.txt)
                     tiles = (H4 // 128) * ((H + 127) // 128)
-                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32)))
+                    g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32, cap=4)))
                 for t_ in (gT_all, hT_all):
                     t_.record_stream(side)
         if steps == 1:
