@@ -570,11 +570,6 @@ class LstmEncoder(torch.autograd.Function):
                                               ldT, plane, N.ptr(g_acc), 0 if t == steps - 1 else 1,
                                               1 if t == 0 else 0, N.ptr(bias_part) if t == 0 else None,
                                               N.ptr(g_c_prev), st))
-            if t > 0:
-                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain; split-K fills the
-                # machine and the next cell kernel sums the parts
-                dh = tc3_gemm(g_pl, whhT_pl, parts=_split_k(((n + 127) // 128) * ((H + 127) // 128), H4 // 32))
-                g_c = g_c_prev
             if t == 1:
                 # every gate gradient that W_hh sees exists now (steps 1 .. steps-1): g_W_hh = sum_t g_t^T h_{t-1}
                 # is ONE GEMM over the stacked transposed planes, on the side stream, under the last hidden-state
@@ -588,6 +583,11 @@ class LstmEncoder(torch.autograd.Function):
                     g_whh = sum_parts(tc3_gemm(gT_all, hT_all, parts=_split_k(tiles, (ldS + 31) // 32, cap=4)))
                 for t_ in (gT_all, hT_all):
                     t_.record_stream(side)
+            if t > 0:
+                # step t read h_{t-1}: the gradient flowing back into h_{t-1} stays on the chain; split-K fills the
+                # machine and the next cell kernel sums the parts
+                dh = tc3_gemm(g_pl, whhT_pl, parts=_split_k(((n + 127) // 128) * ((H + 127) // 128), H4 // 32))
+                g_c = g_c_prev
         if steps == 1:
             g_whh = torch.zeros(H4, H, device=dev, dtype=dt)
         sink = LstmEncoder.grad_sink
