@@ -47,7 +47,7 @@ int stove_kernel_count(void);
 /* Library options: alternative code paths kept for the parity tests and for per-kernel timing passes.
  * Nothing in the library reads the environment.  Names: "fork" (1: independent kernels of one call run on
  * library side streams), "spn2_nodes_stage", "dynloop_generic", "dynloop_nw", "dynloop_recompute",
- * "rollout_cta", "rollout_nw", "gnn_seq_fwd", "gnn_seq_bwd", "head_par_ctas".  set returns the previous value (or a
+ * "rollout_cta", "rollout_nw", "gnn_seq_fwd", "gnn_seq_bwd", "head_par_ctas", "wgrad_ctas".  set returns the previous value (or a
  * negative error code for an unknown name). */
 int stove_set_option(const char* name, int value);
 int stove_get_option(const char* name);

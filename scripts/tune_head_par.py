@@ -12,11 +12,12 @@ dev = torch.device('cuda', 0)
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 pool = [bench.make_frames(bench.BATCH, i).to(dev) for i in range(bench.POOL)]
-for cap in (0, 96, 64, 48, 32, 20):
-    N.set_option('head_par_ctas', cap)
+OPT = sys.argv[1] if len(sys.argv) > 1 else 'head_par_ctas'
+for cap in (0, 111, 96, 74, 64, 48):
+    N.set_option(OPT, cap)
     model = bench.build_model(dev)
     eng = dp.DataParallel(model)
     g = dp.GraphedStep(eng, pool[0])
     ms, reps = bench.timed(lambda i: g(pool[i % bench.POOL]), 20, 5, 1)
-    print('head_par_ctas %3d: %.4f ms/step (median of %d regions)' % (cap, ms / 20, reps), flush=True)
+    print('%s %3d: %.4f ms/step (median of %d regions)' % (OPT, cap, ms / 20, reps), flush=True)
     del g

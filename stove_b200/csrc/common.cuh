@@ -70,7 +70,10 @@ enum StoveOption {
     OPT_ROLLOUT_NW,           // warps per sequence of the rollout kernel (1 or 2; default 2)
     OPT_GNN_SEQ_FWD,          // sequences per CTA of the generic kernels (0 = automatic)
     OPT_GNN_SEQ_BWD,
-    OPT_HEAD_PAR_CTAS,        // CTAs of the head's parameter-gradient kernel (0 = one per SM); it runs beside the LSTM backward
+    OPT_HEAD_PAR_CTAS,
+    OPT_WGRAD_CTAS,           // CTAs of dynloop_wgrad (0 = one per SM): each takes a whole SM's registers for its lifetime,
+                              // so fewer CTAs leave SMs to the chain kernels that become ready while it runs
+        // CTAs of the head's parameter-gradient kernel (0 = one per SM); it runs beside the LSTM backward
     OPT_COUNT
 };
 int stove_opt(int id);

@@ -1357,7 +1357,8 @@ static DynloopBwdPlan dynloop_bwd_plan(const stove_gnn_cfg* cfg, const GnnLayout
     const int64_t groups = (n + p.tpc - 1) / p.tpc;
     p.ctas = (int)(groups < 148 ? groups : 148);
     const int64_t nrec = n * S;
-    p.wg_ctas = (int)(nrec < 148 ? nrec : 148);
+    const int wg_cap = stove_opt(OPT_WGRAD_CTAS) > 0 ? stove_opt(OPT_WGRAD_CTAS) : 148;
+    p.wg_ctas = (int)(nrec < wg_cap ? nrec : wg_cap);
     p.xrec_bytes = sizeof(float) * (size_t)nrec * tk::BwdLay::XREC;
     p.grec_bytes = sizeof(float) * (size_t)nrec * tk::BwdLay::GREC;
     p.slab_bytes = sizeof(float) * (size_t)p.wg_ctas * L.total;
