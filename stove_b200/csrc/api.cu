@@ -127,7 +127,7 @@ int stove_join(StoveFork* f, cudaStream_t s, int nside) {
     return STOVE_OK;
 }
 
-static int g_options[OPT_COUNT] = {1, 1, 0, 2, 0, 0, 2, 0, 0, 0, 0};
+static int g_options[OPT_COUNT] = {1, 1, 0, 2, 0, 0, 2, 0, 0, 0, 74};
 static const char* const kOptionNames[OPT_COUNT] = {"fork", "spn2_nodes_stage", "dynloop_generic", "dynloop_nw",
                                                     "dynloop_recompute", "rollout_cta", "rollout_nw", "gnn_seq_fwd",
                                                     "gnn_seq_bwd", "head_par_ctas", "wgrad_ctas"};

@@ -71,8 +71,9 @@ enum StoveOption {
     OPT_GNN_SEQ_FWD,          // sequences per CTA of the generic kernels (0 = automatic)
     OPT_GNN_SEQ_BWD,
     OPT_HEAD_PAR_CTAS,
-    OPT_WGRAD_CTAS,           // CTAs of dynloop_wgrad (0 = one per SM): each takes a whole SM's registers for its lifetime,
-                              // so fewer CTAs leave SMs to the chain kernels that become ready while it runs
+    OPT_WGRAD_CTAS,           // CTAs of dynloop_wgrad (0 = one per SM; default 74): each takes a whole SM's registers for
+                              // its lifetime, so half the SMs stay free for the chain kernels that become ready while it
+                              // runs (sweep in profiles/r02_tune_wgrad_ctas.txt: 0.697 ms/step at 148, 0.680 at 74)
         // CTAs of the head's parameter-gradient kernel (0 = one per SM); it runs beside the LSTM backward
     OPT_COUNT
 };
