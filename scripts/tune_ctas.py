@@ -1,4 +1,4 @@
-"""Step time of the captured config-1 training step for several CTA caps of the head's parameter-gradient kernel
+"""Step time of the captured config-1 training step for several CTA caps of a side-stream kernel
 (it runs beside the LSTM backward and cannot share an SM with the GEMM CTAs)."""
 import os
 import sys
