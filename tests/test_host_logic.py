@@ -140,3 +140,52 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == ('reference' if rh.available() else 'port') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and 'model' not in d['config']
+
+
+def test_shard_requires_an_even_split():
+    """dp.shard: equal shards only (the exchange averages per-rank mean gradients with equal weights)."""
+    import torch
+    from stove_b200 import dp
+    t = torch.arange(12).view(6, 2)
+    assert torch.equal(dp.shard(t), t)                     # single process: the whole batch
+    import unittest.mock as mock
+    with mock.patch.object(dp, 'world', return_value=4), mock.patch.object(dp, 'rank', return_value=1):
+        with pytest.raises(ValueError):
+            dp.shard(t)
+    with mock.patch.object(dp, 'world', return_value=3), mock.patch.object(dp, 'rank', return_value=2):
+        assert torch.equal(dp.shard(t), t[4:6])
+
+
+def test_split_k_heuristic():
+    """split-K of the tensor-core GEMMs: about one CTA per SM, at least four k-blocks per part, capped."""
+    from stove_b200.ops import _split_k
+    assert _split_k(32, 32) == 4            # hidden-state gradient: 16 x 2 tiles, K = 1024
+    assert _split_k(64, 64) == 2            # W_ih gradient: 8 x 8 tiles, K = 2048
+    assert _split_k(16, 128, cap=4) == 4    # W_hh gradient
+    assert _split_k(1, 1) == 1 and _split_k(200, 64) == 1
+
+
+def test_reference_staging_recipe():
+    """oracle/build_ref.py stages the unmodified modules of the path (git-ignored) where the reference is mounted."""
+    from oracle import build_ref, ref_harness as rh
+    dst = build_ref.build()
+    if not os.path.isdir('/root/reference'):
+        pytest.skip('reference not mounted')
+    for rel in build_ref.FILES:
+        src = os.path.join('/root/reference', rel)
+        if os.path.exists(src):
+            with open(src, 'rb') as a, open(os.path.join(dst, rel), 'rb') as b:
+                assert a.read() == b.read(), rel            # byte-identical: nothing is edited on the way
+    assert rh.available()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, '.gitignore')) as f:
+        assert 'oracle/_ref/' in f.read()
+
+
+def test_unsupported_debug_flags_raise():
+    """Flags whose semantics the fused kernels do not implement must not silently compute the default."""
+    from stove_b200 import Stove, StoveConfig
+    for flag in ('debug_no_latents', 'debug_no_velocity'):
+        cfg = StoveConfig(width=32, height=32, num_obj=3, action_conditioned=False, action_space=None, **{flag: True})
+        with pytest.raises(NotImplementedError):
+            Stove(cfg)
