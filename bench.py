@@ -411,8 +411,9 @@ def train_roofline(value_per_gpu, flop_per_seq, bytes_per_seq, pk):
             'frac': value_per_gpu * flop_per_seq / 1e12 / pk['fp32_tflops'], 'peak_source': pk['fp32_src'],
             'hbm': {'achieved_gbs': value_per_gpu * bytes_per_seq / 1e9, 'peak_gbs': pk['hbm_gbs'],
                     'frac': value_per_gpu * bytes_per_seq / 1e9 / pk['hbm_gbs']},
-            'note': 'per GPU, whole step: %.1f MFLOP (fwd+bwd, fp32-equivalent) and %.0f KB algorithmic bytes per sequence'
-                    % (flop_per_seq / 1e6, bytes_per_seq / 1e3)}
+            'note': 'per GPU, whole step: %.1f MFLOP (fwd+bwd, fp32-equivalent; the input GEMM of the recognition LSTM counted '
+                    'ONCE per frame -- the reference computes it num_obj times, which is how SURVEY 8d arrives at 203 MFLOP per '
+                    'sequence for config 1) and %.0f KB algorithmic bytes per sequence' % (flop_per_seq / 1e6, bytes_per_seq / 1e3)}
 
 
 def step_flops(num_obj, res, frames=T, ac=False):
@@ -718,8 +719,10 @@ def run_b200(args):
                    'optimizer': 'excluded (metric is fwd+bwd); gradient all-reduce of the flat bucket included when N>1',
                    'dp_exchange': None if world == 1 else (
                        'two pieces overlapped with the LSTM backward; ' +
-                       ('NVLS multimem all-reduce on a symmetric-memory bucket' if getattr(engine._overlap, 'symm', None)
-                        else 'NCCL all-reduce'))},
+                       ('%s on a symmetric-memory bucket (start-up race, ms per 2 MB piece: %s)' % (
+                           getattr(engine._overlap, 'symm_name', '?'),
+                           {k: round(v, 4) for k, v in getattr(engine._overlap, 'exchange_times_ms', {}).items()})
+                        if getattr(engine._overlap, 'symm', None) else 'NCCL all-reduce'))},
         'e2e': {'value': e2e_value, 'unit': 'sequences/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': frame_bytes, 'd2h_bytes_per_step': 4},
         'e2e_f32_frames': {'value': world * BATCH * args.steps / (ms_e2e32 * 1e-3), 'unit': 'sequences/s',

@@ -214,40 +214,75 @@ class _Overlap:
             dist.all_reduce(t, op=dist.ReduceOp.MIN)
             return float(t) == 1.0
 
-        buf = op = group = None
-        why = None
+        buf = group = None
+        why, has_mc = None, False
         try:
             import torch.distributed._symmetric_memory as symm_mem
             group = dist.group.WORLD.group_name
             buf = symm_mem.empty(self.total_padded, dtype=torch.float32, device=dev)
             hdl = symm_mem.rendezvous(buf, group=group)
-            if not getattr(hdl, 'multicast_ptr', 0):
-                raise RuntimeError('no multicast support')
-            op = torch.ops.symm_mem.multimem_all_reduce_
+            has_mc = bool(getattr(hdl, 'multicast_ptr', 0))
         except Exception as e:                      # noqa: BLE001 -- any failure here means: use NCCL
             why = repr(e)
         if not agree(why is None):
             if required:
                 raise RuntimeError('stove_b200.dp: symmetric-memory all-reduce is not available: %s' % (why or 'on another rank'))
             return
-        # trial on the two kinds of ranges the exchange uses (a prefix and the remainder), against NCCL
+        # trial on the two kinds of ranges the exchange uses (a prefix and the remainder), against NCCL -- and a
+        # start-up race between the candidates on the size of the exposed piece: the multimem kernel wins on 8 GPUs
+        # (17 vs 39 us for 2 MB), the two-shot peer-memory kernel on 2 (19 vs 27 vs 29 us); every rank times all of
+        # them and the slowest rank's numbers decide, so all ranks pick the same one
+        cands = [(name, getattr(torch.ops.symm_mem, name, None)) for name in ('multimem_all_reduce_', 'two_shot_all_reduce_')]
+        cands = [(name, f) for name, f in cands if f is not None and (has_mc or not name.startswith('multimem'))]
+        if not agree(len(cands) > 0):
+            return
+        times, good, why = [], True, None
         try:
             cut = (self.total_padded // 2) // _ALIGN * _ALIGN
-            buf.copy_(torch.arange(self.total_padded, device=dev, dtype=torch.float32) % 251 * (1 + rank()))
-            ref = buf.clone()
+            pattern = torch.arange(self.total_padded, device=dev, dtype=torch.float32) % 251 * (1 + rank())
+            ref = pattern.clone()
             dist.all_reduce(ref)
-            op(buf[:cut], 'sum', group)
-            op(buf[cut:], 'sum', group)
-            torch.cuda.synchronize(dev)
-            good = bool(((buf - ref).abs() <= 1e-3 * ref.abs()).all())
+            piece = min(self.total_padded, 524288)          # the exposed transfer: half of W_ih
+
+            def clock(fn):
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(dev)
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                return a.elapsed_time(b) / 10
+
+            scratch = torch.zeros(piece, device=dev)
+            times.append(clock(lambda: dist.all_reduce(scratch)))
+            for name, f in cands:
+                buf.copy_(pattern)
+                f(buf[:cut], 'sum', group)
+                f(buf[cut:], 'sum', group)
+                torch.cuda.synchronize(dev)
+                good = good and bool(((buf - ref).abs() <= 1e-3 * ref.abs()).all())
+                buf.zero_()
+                times.append(clock(lambda: f(buf[:piece], 'sum', group)))
         except Exception as e:                      # noqa: BLE001
             good, why = False, repr(e)
         if not agree(good):
             if required:
                 raise RuntimeError('stove_b200.dp: trial all-reduce through symmetric memory failed: %s' % (why or 'mismatch'))
             return
+        t = torch.tensor(times + [0.0] * (3 - len(times)), device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t[:1 + len(cands)].tolist()
+        best = min(range(len(t)), key=lambda i: t[i])
+        self.exchange_times_ms = dict(zip(['nccl'] + [name for name, _ in cands], t))
+        if best == 0 and not required:
+            return                                   # NCCL is the fastest here
+        name, op = cands[max(best, 1) - 1]
         buf.zero_()
         self.symm = (op, group)
+        self.symm_name = name
         self.symm_buf = buf
 
     def _all_reduce(self, lo, hi):
