@@ -397,8 +397,10 @@ int stove_lstm_cell_bwd_t(int64_t n, int H, const float* act, const float* c_pre
                           int64_t gT_plane, float* g_acc, int acc_mode, int emit_acc, float* bias_part,
                           float* g_c_prev, void* stream);
 
-/* out[i] = sum over p < parts of in[p * stride + i], fixed order; numel % 4 == 0, stride % 4 == 0. */
-int stove_sum_parts(int64_t numel, int parts, int64_t stride, const float* in, float* out, void* stream);
+/* out[i] = scale * sum over p < parts of in[p * stride + i], fixed order; numel % 4 == 0, stride % 4 == 0
+ * (scale = 1 / world size lets the last reduction of a weight gradient write straight into the data-parallel
+ * gradient bucket). */
+int stove_sum_parts(int64_t numel, int parts, int64_t stride, const float* in, float* out, float scale, void* stream);
 
 /* Output head of the recognition network (encoder.py:53-56): out = fc2(sigmoid(fc1(x))), x [R][K],
  * w1 [J][K], b1 [J], w2 [P][J], b2 [P] (nn.Linear layouts); hidden [R][J] = sigmoid(fc1(x)) is kept for the

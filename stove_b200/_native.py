@@ -105,7 +105,7 @@ SIGNATURES = {
     'stove_tc3_gemm': (C.c_int, [i64, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, C.c_int, i64, C.c_int, vp]),
     'stove_tc3_gemm_parts': (C.c_int, [i64, i64, i64, C.c_int]),
     'stove_lstm_cell_bwd_t': (C.c_int, [i64, C.c_int, vp, vp, vp, vp, i64, vp, C.c_int, vp, vp, vp, i64, i64, i64, vp, C.c_int, C.c_int, vp, vp, vp]),
-    'stove_sum_parts': (C.c_int, [i64, C.c_int, i64, vp, vp, vp]),
+    'stove_sum_parts': (C.c_int, [i64, C.c_int, i64, vp, vp, C.c_float, vp]),
     'stove_enc_head_fwd': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 7 + [vp]),
     'stove_enc_head_bwd_workspace': (sz, [i64, C.c_int, C.c_int, C.c_int]),
     'stove_enc_head_bwd_data': (C.c_int, [i64, C.c_int, C.c_int, C.c_int] + [vp] * 6 + [vp]),

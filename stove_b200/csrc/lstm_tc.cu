@@ -638,7 +638,7 @@ lstm_cell_bwd_t_kernel(int64_t n, int H, const float* __restrict__ act, const fl
 
 // out[i] = sum_p parts[p * stride + i], fixed order
 __global__ void sum_parts_kernel(int64_t n4, int parts, int64_t stride4, const float4* __restrict__ in,
-                                 float4* __restrict__ out) {
+                                 float4* __restrict__ out, float scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     float4 a = in[i];
@@ -647,6 +647,7 @@ __global__ void sum_parts_kernel(int64_t n4, int parts, int64_t stride4, const f
         const float4 b = __ldg(in + (int64_t)p * stride4 + i);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
+    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;      // scale = 1 is exact
     out[i] = a;
 }
 
@@ -835,13 +836,14 @@ extern "C" int stove_lstm_cell_bwd_t(int64_t n, int H, const float* act, const f
     return STOVE_OK;
 }
 
-extern "C" int stove_sum_parts(int64_t numel, int parts, int64_t stride, const float* in, float* out, void* stream) {
+extern "C" int stove_sum_parts(int64_t numel, int parts, int64_t stride, const float* in, float* out, float scale,
+                               void* stream) {
     STOVE_CHECK_ARG(numel >= 0 && numel % 4 == 0 && parts >= 1 && stride % 4 == 0 && in && out, "need numel % 4 == 0 and stride % 4 == 0");
     STOVE_CHECK_ARG((((uintptr_t)in | (uintptr_t)out) & 15) == 0, "pointers must be 16-byte aligned");
     if (numel == 0) return STOVE_OK;
     cudaStream_t s = (cudaStream_t)stream;
     STOVE_KERNEL(K_SUM_PARTS, s, lt::sum_parts_kernel<<<(unsigned)((numel / 4 + 255) / 256), 256, 0, s>>>(
-        numel / 4, parts, stride / 4, (const float4*)in, (float4*)out));
+        numel / 4, parts, stride / 4, (const float4*)in, (float4*)out, scale));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }

@@ -155,14 +155,15 @@ class _Overlap:
     """Exchange of the flat gradient bucket in TWO pieces, the first one under the tail of the backward pass
     (R > 1, CUDA).
 
-    Bucket order: [early | encoder rest | W_ih rows].  `early` = every parameter outside the recognition network
+    Bucket order: [W_ih rows | encoder rest | early].  `early` = every parameter outside the recognition network
     (SPN, GNN): their gradients are complete long before the LSTM backward ends; a post-accumulate hook counts
     them in and the last one gathers them into the bucket on the communication stream.  The recognition network
     hands its gradients over from inside its backward node (ops.LstmEncoder.grad_sink): head, W_hh and biases
-    first, then W_ih in two row blocks.  An all-reduce costs ~20 us however small it is (profiles/
+    first, then W_ih in two row blocks, upper rows first, written by the last reduction of the GEMM straight into
+    the bucket.  An all-reduce costs ~20 us however small it is (profiles/
     r02_timeline_dp2_v1_four_pieces.txt: four pieces made the exchange LONGER than the compute it hides
-    behind), so there are exactly two: everything up to the first W_ih block goes on the wire while the second
-    block's GEMM runs; the second block (2 MB) is the only exposed transfer.  Whatever did not arrive through a
+    behind), so there are exactly two: everything from the first W_ih block (the upper rows) to the end of the
+    bucket goes on the wire while the second block's GEMM runs; the second block (2 MB) is the only exposed transfer.  Whatever did not arrive through a
     hook or the sink is exchanged at the end (`finish`).  Works eagerly and under CUDA-graph capture (the
     communication stream forks from / joins the producing streams through events)."""
 
@@ -183,7 +184,9 @@ class _Overlap:
         early = [p for p in live if id(p) not in enc_ids]
         rest = [p for k, p in self.by_name.items() if k != 'w_ih']
         last = [self.by_name['w_ih']] if 'w_ih' in self.by_name else []
-        self.order = early + rest + last                    # the bucket layout (== engine.live from now on)
+        # the bucket layout (== engine.live from now on): W_ih first, so that its row blocks start on aligned offsets
+        # (its producer writes them in place) and the block computed FIRST -- the upper rows -- touches the rest
+        self.order = last + rest + early
         self.offset, at = {}, 0
         for p in self.order:
             self.offset[id(p)] = at
@@ -304,7 +307,8 @@ class _Overlap:
         else:
             self.flat = torch.empty(self.total, device=dev, dtype=torch.float32)
         self.pending, self.queue, self.sent = len(self.early), [], set()
-        self.gathered_to = self.reduced_to = 0        # the bucket is gathered / all-reduced up to these offsets
+        self.rows_done = {}
+        self.have, self.reduced = [], []              # delivered / all-reduced intervals of the bucket [lo, hi)
         self.active = True
         self.ops.LstmEncoder.grad_sink = self
 
@@ -316,7 +320,9 @@ class _Overlap:
         self.pending -= 1
         if self.pending == 0:
             self._gather([(q.grad, self.offset[id(q)], q.numel()) for q in self.early], wait=False)
-            self.gathered_to = self.n_early
+            if self.early:
+                lo = min(self.offset[id(q)] for q in self.early)
+                self._deliver(lo, lo + self.n_early)
             self.sent.update(id(q) for q in self.early)
 
     def __call__(self, name, tensor, row_lo=None, row_hi=None):       # ops.LstmEncoder.grad_sink
@@ -330,27 +336,84 @@ class _Overlap:
         else:
             cols = p.shape[1]
             self.queue.append((tensor[row_lo:row_hi], off + row_lo * cols, (row_hi - row_lo) * cols))
-            if row_hi == p.shape[0]:
+            self.rows_done[id(p)] = self.rows_done.get(id(p), 0) + (row_hi - row_lo)
+            if self.rows_done[id(p)] >= p.shape[0]:
                 self.sent.add(id(p))
 
+    @property
+    def scale(self):
+        return 1.0 / self.R
+
+    def slot(self, name, row_lo, row_hi):
+        """the rows [row_lo, row_hi) of parameter `name` inside the bucket, for a producer that writes its (already
+        1 / R scaled) gradient there itself; None if this parameter is not exchanged"""
+        p = self.by_name.get(name)
+        if p is None or not self.active:
+            return None
+        off, cols = self.offset[id(p)], p.shape[1]
+        return self.flat[off + row_lo * cols: off + row_hi * cols].view(row_hi - row_lo, cols)
+
+    def delivered(self, name, row_lo, row_hi):
+        """the producer has written `slot(name, row_lo, row_hi)` on the current stream"""
+        p = self.by_name[name]
+        off, cols = self.offset[id(p)], p.shape[1]
+        self.flush()                                          # what was queued before comes first
+        self.comm.wait_stream(torch.cuda.current_stream(self.flat.device))
+        self._deliver(off + row_lo * cols, off + row_hi * cols)
+        self.rows_done[id(p)] = self.rows_done.get(id(p), 0) + (row_hi - row_lo)
+        if self.rows_done[id(p)] >= p.shape[0]:
+            self.sent.add(id(p))
+
+    @staticmethod
+    def _merge(intervals):
+        out = []
+        for lo, hi in sorted(intervals):
+            if out and lo <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], hi)
+            else:
+                out.append([lo, hi])
+        return out
+
+    def _deliver(self, lo, hi):
+        self.have = self._merge(self.have + [[lo, hi]])
+
+    def _pending(self):
+        """delivered but not yet all-reduced, as maximal intervals"""
+        out = []
+        for lo, hi in self.have:
+            at = lo
+            for rlo, rhi in self.reduced:
+                if rhi <= at or rlo >= hi:
+                    continue
+                if rlo > at:
+                    out.append([at, rlo])
+                at = max(at, rhi)
+            if at < hi:
+                out.append([at, hi])
+        return out
+
     def flush(self, send=False):
-        """gather what the sink queued into the bucket; `send`: also all-reduce everything gathered so far that is
-        not on the wire yet (the bucket fills front to back)"""
+        """gather what the sink queued into the bucket; `send`: also all-reduce what has been delivered and is not on
+        the wire yet.  Piece boundaries inside the bucket stay aligned (the multimem kernels need it); the piece that
+        reaches the end of the bucket takes the padding with it."""
         if self.queue:
             lo = min(q[1] for q in self.queue)
             hi = max(q[1] + q[2] for q in self.queue)
             assert sum(q[2] for q in self.queue) == hi - lo, 'sink pieces must tile a contiguous bucket range'
             self._gather(self.queue)
-            if lo == self.gathered_to:
-                self.gathered_to = hi
+            self._deliver(lo, hi)
             self.queue = []
-        # piece boundaries stay aligned for the multimem kernels; the last piece takes the padding with it
-        done = self.gathered_to == self.total
-        hi = (self.total_padded if self.symm is not None else self.total) if done else self.gathered_to // _ALIGN * _ALIGN
-        if send and hi > self.reduced_to:
-            with torch.cuda.stream(self.comm):
-                self._all_reduce(self.reduced_to, hi)
-            self.reduced_to = self.total if done else hi
+        if not send:
+            return
+        for lo, hi in self._pending():
+            a = (lo + _ALIGN - 1) // _ALIGN * _ALIGN
+            b = hi // _ALIGN * _ALIGN
+            if hi == self.total:
+                b = self.total_padded if self.symm is not None else self.total
+            if b > a:
+                with torch.cuda.stream(self.comm):
+                    self._all_reduce(a, b)
+                self.reduced = self._merge(self.reduced + [[a, min(b, self.total)]])
 
     def _gather(self, pieces, wait=True):
         dev = self.flat.device
@@ -368,14 +431,19 @@ class _Overlap:
         self.active = False
         left = [p for p in self.order if id(p) not in self.sent]
         cur = torch.cuda.current_stream(self.flat.device)
+        left = [q for q in left if q.grad is not None]
         if left:
             self._gather([(q.grad, self.offset[id(q)], q.numel()) for q in left])
-        if self.reduced_to < self.total:
-            # (a gap between what the hooks / the sink delivered front to back and what arrived here is covered
-            # by reducing the whole remainder; delivered-but-unreduced ranges are inside it)
+            for q in left:
+                self._deliver(self.offset[id(q)], self.offset[id(q)] + q.numel())
+        self.flush(send=True)
+        # slivers between aligned pieces (not in the normal flow: the pieces are aligned by construction) and
+        # anything that was never delivered go through NCCL, which has no alignment constraint
+        self.have = [[0, self.total]]
+        for lo, hi in self._pending():
             with torch.cuda.stream(self.comm):
-                self._all_reduce(self.reduced_to, self.total_padded if self.symm is not None else self.total)
-            self.reduced_to = self.total
+                dist.all_reduce(self.flat[lo:hi])
+        self.reduced = [[0, self.total]]
         cur.wait_stream(self.comm)
         # the bucket order is the engine's `live` order from now on
         live[:] = self.order

@@ -388,15 +388,15 @@ def tc3_gemm(a_pl, b_pl, K=None, parts=1, out=None, bn=0):
     return out
 
 
-def sum_parts(parts_t, out=None):
-    """(P, ...) -> sum over the first dimension in a fixed order (split-K partials, bias partial sums)."""
+def sum_parts(parts_t, out=None, scale=1.0):
+    """(P, ...) -> scale * sum over the first dimension in a fixed order (split-K partials, bias partial sums)."""
     P = parts_t.shape[0]
     numel = parts_t[0].numel()
-    if P == 1 and out is None:
+    if P == 1 and out is None and scale == 1.0:
         return parts_t[0]
     if out is None:
         out = torch.empty(parts_t.shape[1:], device=parts_t.device, dtype=parts_t.dtype)
-    N.check(N.lib().stove_sum_parts(numel, P, numel, N.ptr(parts_t), N.ptr(out), N.stream()))
+    N.check(N.lib().stove_sum_parts(numel, P, numel, N.ptr(parts_t), N.ptr(out), float(scale), N.stream()))
     return out
 
 
@@ -622,15 +622,25 @@ class LstmEncoder(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 cur.wait_event(xT_ready)
                 xT_pl.record_stream(cur)
-                g_wih = torch.empty(H4, K, device=dev, dtype=dt)
                 half = (H4 // 2 + 127) // 128 * 128
-                for lo, hi in ((0, half), (half, H4)):
+                for lo, hi in ((half, H4), (0, half)):          # upper rows first: they touch the rest of the bucket
                     if lo >= hi:
                         continue
                     tiles = ((hi - lo + 127) // 128) * ((K + 127) // 128)
-                    sum_parts(tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4)), out=g_wih[lo:hi])
-                    sink('w_ih', g_wih, lo, hi)
-                    sink.flush(send=True)          # all-reduce of everything gathered so far
+                    parts = tc3_gemm(gsumT[:, lo:hi], xT_pl, parts=_split_k(tiles, (ldT + 31) // 32, cap=4))
+                    # the last reduction of the split-K parts writes these rows straight into the engine's bucket,
+                    # already scaled by 1 / world size: no gather launch between the GEMM and the wire.  (The node then
+                    # returns no W_ih gradient of its own; the engine hands out views of the bucket.)
+                    dst = sink.slot('w_ih', lo, hi)
+                    if dst is None:
+                        if g_wih is None:
+                            g_wih = torch.empty(H4, K, device=dev, dtype=dt)
+                        sum_parts(parts, out=g_wih[lo:hi])
+                        sink('w_ih', g_wih, lo, hi)
+                    else:
+                        sum_parts(parts, out=dst, scale=sink.scale)
+                        sink.delivered('w_ih', lo, hi)
+                    sink.flush(send=True)          # all-reduce of everything in the bucket so far
         if ctx.head is not None:
             cur.wait_stream(_aux_stream(dev, 1))   # head gradients
         for t_ in (g_whh, g_b) + g_head:
