@@ -165,6 +165,31 @@ int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int a
                     const float* g_overlap, float* g_z, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Fused scene likelihood (csrc/scene_ll.cu): stove_scene_fwd + stove_spn2_fwd + stove_spn1_fwd in ONE launch for
+ * single-channel frames -- the op sequence of Supair.likelihood, model/video_prediction/supair.py:62-76 (masks ->
+ * background SPN, glimpses -> object SPN).  A CTA owns a group of frames; glimpses and masks are produced into
+ * the object SPN's shared-memory tiles and consumed there, the background mask stays on chip for the background
+ * SPN's leaf pass.  Outputs are those of the three unfused calls, in their layouts:
+ *   patches / marg_patch (F*O, pa*pb), marg_bg (F, A*B), overlap (F, O)         [stove_scene_fwd]
+ *   leaf_val [2R*2*G][npad], sum_val [2R*S][npad], out_obj (F*O)  npad = roundup(F*O, 32)   [stove_spn2_fwd]
+ *   bleaf_val [R*2*G][npad_f], out_bg (F)                          npad_f = roundup(F, 32)   [stove_spn1_fwd]
+ * bg_scope [2R][D] / bg_cnt [2R]: pixels of background leaf l = 2 r + side, ascending (int32, device).
+ * stove_scene_ll_supported returns 1 when the configuration fits the fused kernels (C = 1, the D2 / D1
+ * structures with 10 Gaussians / 10 sums and 3 x 6, shared memory); otherwise use the unfused calls.
+ * ------------------------------------------------------------------------------------ */
+int stove_scene_ll_supported(int64_t F, int O, int C, int A, int B, int pa, int pb,
+                             const stove_spn2_struct* obj, const stove_spn1_struct* bg);
+int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb, int align_corners,
+                       const float* img, const float* z,
+                       const stove_spn2_struct* obj, const float* leaf, const float* wlin, const float* wlog,
+                       const float* rlin, const float* rlog,
+                       const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
+                       const float* bleaf, const float* brlin, const float* brlog,
+                       float* patches, float* marg_patch, float* marg_bg, float* overlap,
+                       float* leaf_val, float* sum_val, float* out_obj, float* bleaf_val, float* out_bg,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Sequence glue before the dynamics loop, one launch: Supair.constrain_zp (supair.py:112-149),
  * Stove.match_objects (stove.py:200-329 / 331-430 / 432-514), Stove.fix_supair
  * (stove.py:516-571), Stove.v_from_state / v_std_from_pos (stove.py:54-101).

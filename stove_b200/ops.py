@@ -310,6 +310,112 @@ class Scene(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------
+# fused scene likelihood: glimpses + masks + object SPN + background SPN (csrc/scene_ll.cu)
+# ----------------------------------------------------------------------------------------
+_SCENE_LL = True
+
+
+def set_scene_ll(enabled):
+    """Fused scene-likelihood kernels on / off (off = Scene -> Spn2 / Spn1, the unfused launch sequence that the
+    parity tests compare against).  Returns the previous setting."""
+    global _SCENE_LL
+    prev, _SCENE_LL = _SCENE_LL, bool(enabled)
+    return prev
+
+
+def scene_ll_supported(img, z, pa, pb, obj_tables, bg_tables):
+    if not _SCENE_LL or obj_tables is None or bg_tables is None or not img.is_cuda:
+        return False
+    if obj_tables.kind != 'D2' or bg_tables.kind != 'D1':
+        return False
+    F_, Cc, A, B = img.shape
+    return bool(N.lib().stove_scene_ll_supported(F_, z.shape[1], Cc, A, B, pa, pb, C.byref(obj_tables.cstruct),
+                                                 C.byref(bg_tables.cstruct)))
+
+
+class SceneLL(torch.autograd.Function):
+    """img (F, 1, A, B), z (F, O, 4), packed object / background SPN parameters ->
+    (bg_ll (F,), obj_ll (F*O,), overlap (F, O), patches, marg_patch (F*O, 1, pa, pb), marg_bg (F, 1, A, B)).
+    One forward launch; the last three outputs are by-products (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, obj_tables, bg_tables, pa, pb,
+                align_corners, obj_stream=None, bg_stream=None):
+        img, z = img.contiguous(), z.contiguous()
+        N.require_cuda_f32(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin)
+        F_, Cc, A, B = img.shape
+        O = z.shape[1]
+        st2, st1 = obj_tables.cstruct, bg_tables.cstruct
+        dev, dt = img.device, img.dtype
+        n = F_ * O
+        npad, npad_f = _npad(max(n, 1)), _npad(max(F_, 1))
+        Q, G, S = 2 * st2.R, st2.G, st2.S
+        patches = torch.empty(n, Cc, pa, pb, device=dev, dtype=dt)
+        marg_patch = torch.empty_like(patches)
+        marg_bg = torch.empty(F_, Cc, A, B, device=dev, dtype=dt)
+        overlap = torch.empty(F_, O, device=dev, dtype=dt)
+        leaf_val = torch.empty(Q * 2 * G, npad, device=dev, dtype=dt)
+        sum_val = torch.empty(Q * S, npad, device=dev, dtype=dt)
+        out_obj = torch.empty(n, device=dev, dtype=dt)
+        bleaf_val = torch.empty(st1.R * 2 * st1.G, npad_f, device=dev, dtype=dt)
+        out_bg = torch.empty(F_, device=dev, dtype=dt)
+        N.check(N.lib().stove_scene_ll_fwd(
+            F_, O, A, B, pa, pb, int(align_corners), N.ptr(img), N.ptr(z),
+            C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
+            C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
+            N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog),
+            N.ptr(patches), N.ptr(marg_patch), N.ptr(marg_bg), N.ptr(overlap),
+            N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val), N.ptr(out_bg), N.stream()))
+        ctx.save_for_backward(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch, marg_bg,
+                              leaf_val, sum_val, out_obj, bleaf_val, out_bg)
+        ctx.tables = (obj_tables, bg_tables)
+        ctx.meta = (F_, O, Cc, A, B, pa, pb, int(align_corners))
+        ctx.streams = (obj_stream, bg_stream)
+        ctx.mark_non_differentiable(patches, marg_patch, marg_bg)
+        return out_bg, out_obj, overlap, patches, marg_patch, marg_bg
+
+    @staticmethod
+    def backward(ctx, g_bg, g_obj, g_overlap, _gp, _gmp, _gmb):
+        (img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch, marg_bg, leaf_val, sum_val,
+         out_obj, bleaf_val, out_bg) = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
+                                      '(frames are data on the STOVE hot path)')
+        obj_tables, bg_tables = ctx.tables
+        st2, st1 = obj_tables.cstruct, bg_tables.cstruct
+        F_, O, Cc, A, B, pa, pb, ac = ctx.meta
+        obj_stream, bg_stream = ctx.streams
+        n = F_ * O
+        dev = img.device
+        g_bg = torch.zeros_like(out_bg) if g_bg is None else g_bg.contiguous()
+        g_obj = torch.zeros_like(out_obj) if g_obj is None else g_obj.contiguous()
+        g_overlap = None if g_overlap is None else g_overlap.contiguous()
+        g_leaf, g_wlog, g_rlog, g_bleaf, g_brlog = _zeros_views(leaf, leaf.shape, wlog.shape, rlog.shape, bleaf.shape,
+                                                               brlog.shape)
+        g_z = torch.empty_like(z)
+        x2, m2 = patches.view(n, -1), marg_patch.view(n, -1)
+        xb, mb = img.view(F_, -1), marg_bg.view(F_, -1)
+        ws2 = torch.empty(max(N.lib().stove_spn2_bwd_workspace(C.byref(st2), n), 4) // 4, device=dev, dtype=torch.float32)
+        ws1 = torch.empty(max(N.lib().stove_spn1_bwd_workspace(C.byref(st1), F_), 4) // 4, device=dev, dtype=torch.float32)
+        g_x, g_m = torch.empty_like(x2), torch.empty_like(m2)
+        g_mb = torch.empty_like(mb)
+        N.check(N.lib().stove_spn2_bwd(C.byref(st2), n, N.ptr(x2), N.ptr(m2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog),
+                                       N.ptr(rlin), N.ptr(rlog), N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj),
+                                       N.ptr(g_obj), N.ptr(g_x), N.ptr(g_m), N.ptr(g_leaf), N.ptr(g_wlog),
+                                       N.ptr(g_rlog), N.ptr(ws2), N.stream(), _join_handle(obj_stream)))
+        N.check(N.lib().stove_spn1_bwd(C.byref(st1), F_, N.ptr(xb), N.ptr(mb), N.ptr(bleaf), N.ptr(brlin),
+                                       N.ptr(brlog), N.ptr(bleaf_val), N.ptr(out_bg), N.ptr(g_bg), None,
+                                       N.ptr(g_mb), N.ptr(g_bleaf), N.ptr(g_brlog), N.ptr(ws1), N.stream(),
+                                       _join_handle(bg_stream)))
+        N.check(N.lib().stove_scene_bwd(F_, O, Cc, A, B, pa, pb, ac, N.ptr(img), N.ptr(z), N.ptr(g_x), N.ptr(g_m),
+                                        N.ptr(g_mb), N.ptr(g_overlap), N.ptr(g_z), N.stream()))
+        _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
+        _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
+        return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
+                None, None)
+
+
+# ----------------------------------------------------------------------------------------
 # fused sequence glue (constrain_zp + matching + fix_supair + velocities)
 # ----------------------------------------------------------------------------------------
 MATCH_KINDS = {'3_only': 0, 'greedy': 1, 'volatile': 2}

@@ -289,7 +289,15 @@ class RatSpn(nn.Module):
                 for leaf in (a, b):
                     order.append(leaf)
                     dst.extend(p * R + r for p in leaf.scope)
-            host = {'side': side, 'dst_row': np.asarray(dst, dtype=np.int32)}
+            # scope lists per leaf l = 2 r + side (ascending pixels), for the fused scene-likelihood kernels
+            bg_scope = np.zeros((2 * R, D), dtype=np.int32)
+            bg_cnt = np.zeros(2 * R, dtype=np.int32)
+            for r in range(R):
+                for h in (0, 1):
+                    px = np.nonzero(side[:, r] == h)[0]
+                    bg_scope[2 * r + h, :len(px)] = px
+                    bg_cnt[2 * r + h] = len(px)
+            host = {'side': side, 'dst_row': np.asarray(dst, dtype=np.int32), 'bg_scope': bg_scope, 'bg_cnt': bg_cnt}
             t = _Tables('D1', host, dict(D=D, R=R, G=G))
             t.leaf_order, t.prow_total, t.GP = order, D * R, (G + 3) // 4 * 4
             return t

@@ -86,6 +86,18 @@ class Supair(nn.Module):
         intermediate tensors: one glimpse/mask launch, one launch family per SPN."""
         c = self.c
         pk_obj, pk_bg = packed if packed is not None else self.pack()
+        if pk_obj is not None and pk_bg is not None and ops.scene_ll_supported(
+                x_img, z_img, c.patch_width, c.patch_height, pk_obj.tables, pk_bg.tables):
+            # one launch for the whole likelihood (csrc/scene_ll.cu): glimpses and masks never leave the SM
+            cur = torch.cuda.current_stream(x_img.device)
+            streams = [None if p.stream is None or p.stream == cur else p.stream for p in (pk_obj, pk_bg)]
+            bg_loglik, patches_loglik, overlap, patches, marg_patch, marg_bg = ops.SceneLL.apply(
+                x_img, z_img, pk_obj.leaf, pk_obj.wlog, pk_obj.wlin, pk_obj.rlog, pk_obj.rlin,
+                pk_bg.leaf, pk_bg.rlog, pk_bg.rlin, pk_obj.tables, pk_bg.tables,
+                c.patch_width, c.patch_height, self._align(), streams[0], streams[1])
+            extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marg_patch.flatten(start_dim=1),
+                         marginalise_bg=marg_bg)
+            return bg_loglik, patches_loglik, overlap, extra
         patches, marg_patch, marg_bg, overlap = ops.Scene.apply(
             x_img, z_img, c.patch_width, c.patch_height, self._align())
         img_flat, marg_flat = x_img.flatten(start_dim=1), marg_bg.flatten(start_dim=1)
