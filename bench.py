@@ -518,6 +518,8 @@ def run_b200(args):
     extra = {}
 
     def guarded(name, fn):
+        if args.headline_only:                   # quick iterations: config 1 only (the driver never passes this flag)
+            return
         try:
             extra[name] = fn()
         except Exception as e:                   # noqa: BLE001 -- an extra workload must not take the headline down
@@ -915,6 +917,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='run the training step eagerly (no CUDA graph)')
+    ap.add_argument('--headline-only', action='store_true', help='skip the extra workloads (configs 2-5, strong scaling)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

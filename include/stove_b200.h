@@ -189,6 +189,25 @@ int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb, int align
                        float* leaf_val, float* sum_val, float* out_obj, float* bleaf_val, float* out_bg,
                        void* stream);
 
+/* Backward of stove_scene_ll_fwd (csrc/scene_ll_bwd.cu): one chain launch replaces spn2_bwd (node + input pass),
+ * spn1_bwd (root + input pass) and stove_scene_bwd -- gradients of the glimpses and masks stay in shared memory --
+ * followed by the four parameter-gradient kernels of stove_spn2_bwd / stove_spn1_bwd on library side streams
+ * (joined into join_obj / join_bg, or into `stream` when those are NULL).  g_obj (F*O), g_bg (F), g_overlap (F, O) or
+ * NULL -> g_z (F, O, 4); g_leaf / g_wlog / g_rlog / g_bleaf / g_brlog are accumulated (zero them first).
+ * ws_obj / ws_bg: stove_spn2_bwd_workspace(obj, F*O) / stove_spn1_bwd_workspace(bg, F) bytes. */
+int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb, int align_corners,
+                       const float* img, const float* z,
+                       const stove_spn2_struct* obj, const float* leaf, const float* wlin, const float* wlog,
+                       const float* rlin, const float* rlog,
+                       const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
+                       const float* bleaf, const float* brlin, const float* brlog,
+                       const float* patches, const float* marg_patch, const float* marg_bg,
+                       const float* leaf_val, const float* sum_val, const float* out_obj,
+                       const float* bleaf_val, const float* out_bg,
+                       const float* g_obj, const float* g_bg, const float* g_overlap,
+                       float* g_z, float* g_leaf, float* g_wlog, float* g_rlog, float* g_bleaf, float* g_brlog,
+                       void* ws_obj, void* ws_bg, void* stream, void* join_obj, void* join_bg);
+
 /* ------------------------------------------------------------------------------------
  * Sequence glue before the dynamics loop, one launch: Supair.constrain_zp (supair.py:112-149),
  * Stove.match_objects (stove.py:200-329 / 331-430 / 432-514), Stove.fix_supair

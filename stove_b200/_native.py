@@ -100,6 +100,8 @@ SIGNATURES = {
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
     'stove_scene_ll_supported': (C.c_int, [i64] + [C.c_int] * 6 + [P2, P1]),
     'stove_scene_ll_fwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp] * 9 + [vp]),
+    'stove_scene_ll_bwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp] * 8 + [vp] * 3
+                           + [vp] * 6 + [vp, vp] + [vp, vp, vp]),
     'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, vp]),

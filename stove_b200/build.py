@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libstove_b200.so')
-SOURCES = ['api.cu', 'spn_pack.cu', 'spn_obj.cu', 'spn_bg.cu', 'scene.cu', 'scene_ll.cu', 'gnn.cu', 'dynloop.cu', 'glue.cu', 'lstm_tc.cu', 'enc_head.cu', 'optim.cu', 'microbench.cu']
+SOURCES = ['api.cu', 'spn_pack.cu', 'spn_obj.cu', 'spn_bg.cu', 'scene.cu', 'scene_ll.cu', 'scene_ll_bwd.cu', 'gnn.cu', 'dynloop.cu', 'glue.cu', 'lstm_tc.cu', 'enc_head.cu', 'optim.cu', 'microbench.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

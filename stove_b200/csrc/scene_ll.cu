@@ -51,47 +51,6 @@ __device__ __forceinline__ void bilinear_pair(const float2* fb, int B, const Cor
     mval = tm_ + c.fy * (bm_ - tm_);
 }
 
-// pixel position of a normalised coordinate is affine: unnorm(g) = g * slope + offset (scene_math.cuh: unnorm)
-__device__ __forceinline__ float unnorm_offset(int L, int align) { return align ? 0.5f * (float)(L - 1) : 0.5f * (float)L - 0.5f; }
-// base_coord with the reciprocal of the divisor precomputed (rn = 1 / (n - 1) if align else 1 / n)
-__device__ __forceinline__ float base_coord_r(int k, float rn, int align) {
-    return align ? 2.f * (float)k * rn - 1.f : (2.f * (float)k + 1.f) * rn - 1.f;
-}
-__device__ __forceinline__ float recip_n(int n, int align) { return align ? (n > 1 ? 1.f / (float)(n - 1) : 0.f) : 1.f / (float)n; }
-
-// tents of the paste of object (sx, sy, tx, ty) and the rows [ulo, uhi] they touch (value or derivative non-zero)
-__device__ __forceinline__ void warp_tents(const LLArgs& a, float sx, float sy, float tx, float ty, float* tX,
-                                           float* tY, float* dX, float* dY, int lane, int& ulo, int& uhi) {
-    const float isx = 1.f / sx, isy = 1.f / sy;
-    const float kB = unnorm_slope(a.B, a.align), kA = unnorm_slope(a.A, a.align);
-    const float mx = isx * kB, my = isy * kA;
-    const float ox = -tx * isx * kB + unnorm_offset(a.B, a.align), oy = -ty * isy * kA + unnorm_offset(a.A, a.align);
-    const float rB = recip_n(a.B, a.align), rA = recip_n(a.A, a.align);
-    int lo = 1 << 30, hi = -1;
-    for (int k = lane; k < a.A + a.B; k += 32) {
-        float val, der;
-        if (k < a.B) {
-            tent(fmaf(base_coord_r(k, rB, a.align), mx, ox), a.B, val, der);
-            tX[k] = val;
-            if (dX) dX[k] = der;
-        } else {
-            const int u = k - a.B;
-            tent(fmaf(base_coord_r(u, rA, a.align), my, oy), a.A, val, der);
-            tY[u] = val;
-            if (dY) dY[u] = der;
-            if (val != 0.f || der != 0.f) { lo = min(lo, u); hi = max(hi, u); }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    ulo = lo;
-    uhi = hi;          // rows outside [ulo, uhi] receive no paste (and no paste gradient)
-}
-
-
 __device__ void scene_frame_fwd(const LLArgs& a, int64_t f, int pl0, float2* fb, float* tX, float* tY, float2* xw,
                                 int lane) {
     const int AB = a.A * a.B, PP = a.pa * a.pb, D = a.st.D;
@@ -119,6 +78,7 @@ __device__ void scene_frame_fwd(const LLArgs& a, int64_t f, int pl0, float2* fb,
     } else {
         for (int i = lane; i < AB; i += 32) fb[i] = make_float2(__ldg(src + i), 0.f);
     }
+    if (lane == 0) fb[AB] = make_float2(0.f, 1.f);        // null pixel: weight 1 - mask = 0 (idle lanes of the background pass)
     // normalised glimpse coordinates of this lane's pixels (the same for every object)
     float xb[MAXIT], yb[MAXIT];
     {
@@ -208,18 +168,25 @@ __device__ __forceinline__ void bg_leaf_pass(const LLArgs& a, int task, int l, i
     float acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
+    const unsigned fb_s = (unsigned)__cvta_generic_to_shared(fb), fstride = (unsigned)a.fs * 8u;
     for (int ib = i0; ib < i1; ib += 32) {
         const int i = ib + lane;
         const bool ok = i < i1;
-        const int px = ok ? __ldg(sc + i) : 0;
-        const float4* p4 = reinterpret_cast<const float4*>(a.bleaf + ((int64_t)px * RB + r) * 3 * GPB + G0);
+        // lanes past the end of the slice read the frame's null pixel (x = 0, mask = 1: weight 0)
+        const int px = ok ? __ldg(sc + i) : a.Dbg;
+        const float4* p4 = reinterpret_cast<const float4*>(a.bleaf + ((int64_t)(ok ? px : 0) * RB + r) * 3 * GPB + G0);
         const float4 m4 = __ldg(p4), a4 = __ldg(p4 + GPB / 4), b4 = __ldg(p4 + 2 * (GPB / 4));
         const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        unsigned addr = fb_s + (unsigned)px * 8u;
+        // one address increment per frame instead of index arithmetic on the runtime frame stride (the first version
+        // spent a third of this phase's instructions on it and on selecting the weight of idle lanes)
 #pragma unroll
         for (int f = 0; f < MAXF; ++f) {
             if (f < nfr) {
-                const float2 v = fb[f * a.fs + px];                       // (x, final background mask in [0, 1])
-                const float wv = ok ? 1.f - v.y : 0.f;
+                float2 v;                                                 // (x, final background mask in [0, 1])
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+                addr += fstride;
+                const float wv = 1.f - v.y;
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     const float d = v.x - mu[g];
@@ -555,7 +522,7 @@ int sl_plan(sl::LLArgs& a, int G, int S, int RB, int GB, int* grid, size_t* smem
     const int nsm = sl_sm_count();
     *grid = (int)((a.F < nsm) ? a.F : nsm);
     const int cnt_max = (int)((a.F + *grid - 1) / *grid);
-    a.fs = up4(a.A * a.B);
+    a.fs = up4(a.A * a.B + 1);          // + the null pixel
     const int Q = 2 * a.st.R;
     for (int rf = cnt_max < MAXF ? cnt_max : MAXF; rf >= 1; --rf) {
         a.rf = rf;
@@ -567,9 +534,9 @@ int sl_plan(sl::LLArgs& a, int G, int S, int RB, int GB, int* grid, size_t* smem
         if (nw < 4) nw = 4;
         a.nw = nw;
         a.ns = nw / (2 * RB) > 0 ? nw / (2 * RB) : 1;
-        const Smem m = backward ? smem_layout_bwd(a, G, S, GB) : smem_layout(a, G, S, GB);
-        if ((size_t)m.total * sizeof(float) <= 227 * 1024) {
-            *smem_bytes = (size_t)m.total * sizeof(float);
+        const int total = backward ? smem_layout_bwd(a, G, S, GB, RB).total : smem_layout(a, G, S, GB).total;
+        if ((size_t)total * sizeof(float) <= 227 * 1024) {
+            *smem_bytes = (size_t)total * sizeof(float);
             return 1;
         }
     }

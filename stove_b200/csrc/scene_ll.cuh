@@ -1,6 +1,7 @@
 // Argument block and shared-memory plan of the fused scene-likelihood kernels (scene_ll.cu, scene_ll_bwd.cu).
 #pragma once
 #include "common.cuh"
+#include "scene_math.cuh"
 #include "spn_math.cuh"
 
 namespace sl {
@@ -72,9 +73,82 @@ __host__ __device__ inline Smem smem_layout(const LLArgs& a, int G, int S, int G
     return m;
 }
 
-__host__ __device__ inline Smem smem_layout_bwd(const LLArgs& a, int G, int S, int GB) {
-    return smem_layout(a, G, S, GB);       // placeholder until scene_ll_bwd.cu lands
+// backward (scene_ll_bwd.cu).  Union U holds, one after the other: the sum / root weights (node pass), the leaf
+// table + slot table (input-gradient pass), the frames as (x, gradient w.r.t. the background mask) pairs.
+// T: gradients of the sum values (node pass), then the (x, mask) tile that the input pass turns into (g_x, g_mask).
+// V: leaf-vector gradients [leaf][patch][12] (node -> input pass), then the tents of every object of every frame.
+struct SmemB {
+    int wl, rws, rwsT;          // U, node pass
+    int lf, slots;              // U, input pass
+    int fb;                     // U, background + scene pass
+    int t, v, bgl, rng, total;
+    int tent_stride;            // floats per object: tX, dX (B each, padded), tY, dY (A each, padded)
+};
+constexpr int GLP = 12;         // row of the leaf-vector gradients: G = 10 padded to 12 (16-byte rows)
+constexpr int BGLP = 8;         // background leaf vectors padded to 8
+
+__host__ __device__ inline SmemB smem_layout_bwd(const LLArgs& a, int G, int S, int GB, int RB) {
+    SmemB m;
+    const int GP = up4(G), SP = up4(S), Q = 2 * a.st.R;
+    m.wl = 0;
+    m.rws = m.wl + Q * G * G * SP;
+    m.rwsT = m.rws + up4(a.st.R * S * S);
+    const int w_sz = m.rwsT + up4(a.st.R * S * S);
+    m.lf = 0;
+    m.slots = m.lf + Q * a.st.pmax * 3 * GP;
+    const int l_sz = m.slots + up4(a.st.D * a.st.R);
+    m.fb = 0;
+    const int f_sz = a.rf * a.fs * 2;
+    const int U = up4(imax_(imax_(w_sz, l_sz), f_sz));
+    m.t = U;
+    m.v = m.t + up4(imax_(a.ntile * Q * S * HT, a.ntile * a.st.D * HT * 2));
+    m.tent_stride = 2 * (up4(a.B) + up4(a.A));
+    m.bgl = m.v + up4(imax_(a.ntile * Q * 2 * HT * GLP, a.rf * a.O * m.tent_stride));
+    m.rng = m.bgl + a.rf * 2 * RB * BGLP;
+    m.total = m.rng + up4(a.rf * a.O * 2);
+    return m;
 }
+
+// pixel position of a normalised coordinate is affine: unnorm(g) = g * slope + offset (scene_math.cuh: unnorm)
+__device__ __forceinline__ float unnorm_offset(int L, int align) { return align ? 0.5f * (float)(L - 1) : 0.5f * (float)L - 0.5f; }
+// base_coord with the reciprocal of the divisor precomputed (rn = 1 / (n - 1) if align else 1 / n)
+__device__ __forceinline__ float base_coord_r(int k, float rn, int align) {
+    return align ? 2.f * (float)k * rn - 1.f : (2.f * (float)k + 1.f) * rn - 1.f;
+}
+__device__ __forceinline__ float recip_n(int n, int align) { return align ? (n > 1 ? 1.f / (float)(n - 1) : 0.f) : 1.f / (float)n; }
+
+// tents of the paste of object (sx, sy, tx, ty) and the rows [ulo, uhi] they touch (value or derivative non-zero)
+__device__ __forceinline__ void warp_tents(const LLArgs& a, float sx, float sy, float tx, float ty, float* tX,
+                                           float* tY, float* dX, float* dY, int lane, int& ulo, int& uhi) {
+    const float isx = 1.f / sx, isy = 1.f / sy;
+    const float kB = unnorm_slope(a.B, a.align), kA = unnorm_slope(a.A, a.align);
+    const float mx = isx * kB, my = isy * kA;
+    const float ox = -tx * isx * kB + unnorm_offset(a.B, a.align), oy = -ty * isy * kA + unnorm_offset(a.A, a.align);
+    const float rB = recip_n(a.B, a.align), rA = recip_n(a.A, a.align);
+    int lo = 1 << 30, hi = -1;
+    for (int k = lane; k < a.A + a.B; k += 32) {
+        float val, der;
+        if (k < a.B) {
+            tent(fmaf(base_coord_r(k, rB, a.align), mx, ox), a.B, val, der);
+            tX[k] = val;
+            if (dX) dX[k] = der;
+        } else {
+            const int u = k - a.B;
+            tent(fmaf(base_coord_r(u, rA, a.align), my, oy), a.A, val, der);
+            tY[u] = val;
+            if (dY) dY[u] = der;
+            if (val != 0.f || der != 0.f) { lo = min(lo, u); hi = max(hi, u); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    ulo = lo;
+    uhi = hi;          // rows outside [ulo, uhi] receive no paste (and no paste gradient)
+}
+
 
 }  // namespace sl
 

@@ -1,0 +1,727 @@
+// Fused scene likelihood, backward chain: ONE launch takes the gradients of the per-frame / per-patch log-likelihoods
+// (and of the overlap ratios) to d/dz, and leaves the node gradients the parameter-gradient kernels of
+// spn_obj.cu / spn_bg.cu need in their workspaces.  Replaces spn2_bwd_nodes + spn2_bwd_input, spn1_bwd_root +
+// spn1_bwd_input and scene_bwd (5 launches, 4.3 + 7.3 + 7.3 MB of gradients handed through L2 and the glimpse
+// backward waiting for four SPN kernels) on the path of Supair.likelihood (supair.py:62-94).
+//
+// Same partition as the forward kernel (scene_ll.cu): a CTA owns a contiguous group of frames, rounds of <= MAXF.
+// Phases of a round (formulas: tests/kernel_spec.py, checked against autograd of the oracle):
+//   N1  (root partition r, tile): the two halves of a warp own the two mid regions of the partition; gradient of
+//       their sum values -> shared memory, (c, eA, eB) -> workspace for the sum-weight gradients.
+//   N2  (mid region q, tile): lane = (leaf h, patch).  Sums recomputed as in the forward pass; each half walks half of
+//       the 100 products and the halves exchange partial leaf-vector gradients by shuffle.  -> gl[leaf][patch][12]
+//       in shared memory (+ workspace copies for the leaf / sum parameter gradients).
+//   IN  (tile, pixel pair): lane = (pixel of the pair, patch): d/d glimpse pixel and d/d mask over the 6 leaves the
+//       pixel belongs to; the (x, mask) tile becomes the (g_x, g_mask) tile in place.
+//   BR  warp = frame: background root -> leaf-vector gradients (8-lane groups = root partitions).
+//   BI  lane = pixel (its 3 x 18 leaf parameters in registers, read ONCE from L2), loop over the frames of the round:
+//       d/d background mask -> the .y half of the frame buffer.
+//   SC  warp = frame: objects in reverse order: clamp backward + row / column sums of the paste gradient on the rows
+//       the box touches, then the 100 sample points (glimpse and mask gradients from the tile, bilinear derivatives,
+//       scatter into the background gradient).  The background state before each object is REPLAYED from the tents
+//       of the earlier objects (2 FMA + clamp per object) instead of stored: no O x frame buffer.
+#include "common.cuh"
+#include "scene_math.cuh"
+#include "spn_math.cuh"
+#include "scene_ll.cuh"
+
+int spn2_param_kernels(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg, const float* leaf,
+                       const float* wlin, const float* rlin, void* workspace, float* g_leaf, float* g_wlog,
+                       float* g_rlog, cudaStream_t s_leaf, cudaStream_t s_sum);
+int spn1_param_kernels(const stove_spn1_struct* st, int64_t N, const float* x, const float* marg, const float* leaf,
+                       const float* rlin, void* workspace, float* g_leaf, float* g_rlog, cudaStream_t s_leaf,
+                       cudaStream_t s_root);
+
+namespace sl {
+
+__device__ __forceinline__ int sum_of_b(int h, int c) { return c < 4 ? 4 * h + c : 8 + h; }     // see scene_ll.cu: sum_of
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------
+// N1: root partition -> gradients of the two regions' sum values
+// ------------------------------------------------------------------------------------
+template <int S>
+__device__ void bwd_root_task(const LLArgs& a, const SmemB& m, float* smem, int r, int tile, int npt, int64_t n0g,
+                              int lane) {
+    const int h = lane >> 4, pt = lane & (HT - 1);
+    const int R = a.st.R, Q = 2 * R;
+    const bool live = pt < npt;
+    const int64_t n = n0g + pt;
+    const int qo = 2 * r + h, qt = 2 * r + 1 - h;
+    float own[S], oth[S], eO[S], eT[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        own[i] = live ? a.sum_val[(int64_t)(qo * S + i) * a.npad_p + n] : 0.f;
+        oth[i] = live ? a.sum_val[(int64_t)(qt * S + i) * a.npad_p + n] : 0.f;
+    }
+    const float mO = shift_exp<S>(own, eO), mT = shift_exp<S>(oth, eT);
+    // h = 0 owns the A side (index i of w[j][i]) and needs columns: the transposed copy; h = 1 owns the B side: rows
+    const float* rw = smem + (h ? m.rws : m.rwsT) + r * S * S;
+    float vec[S];
+    float U = 0.f;
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        float v = 0.f;
+#pragma unroll
+        for (int l = 0; l < S; ++l) v = fmaf(eT[l], lds_f1(rw + k * S + l), v);
+        vec[k] = v;
+        U = fmaf(eO[k], v, U);
+    }
+    const float U0 = __shfl_sync(0xffffffffu, U, pt);          // both halves use the value of the h = 0 lane
+    const bool fast = U0 > LIN_SUM_FLOOR;
+    const float go = live ? a.g_obj[n] : 0.f, ov = live ? a.out_obj[n] : 0.f;
+    float c = 0.f;
+    if (fast) c = go * expf(mO + mT + logf(U0) - ov) / U0;
+    float* gs = smem + m.t + ((size_t)tile * Q * S + qo * S) * HT + pt;
+#pragma unroll
+    for (int k = 0; k < S; ++k) gs[k * HT] = c * eO[k] * vec[k];
+    if (live) {
+        float* ar = a.aux_root + (int64_t)r * (1 + 2 * S) * a.npad_p + n;
+        if (h == 0) ar[0] = c;
+#pragma unroll
+        for (int k = 0; k < S; ++k) ar[(int64_t)(1 + h * S + k) * a.npad_p] = fast ? eO[k] : 0.f;
+    }
+    __syncwarp();
+    if (!fast && h == 0 && live) {
+        const float* a0 = a.sum_val + (int64_t)((2 * r) * S) * a.npad_p + n;
+        const float* b0 = a.sum_val + (int64_t)((2 * r + 1) * S) * a.npad_p + n;
+        const float val = slow_logsumexp(a0, b0, (int)a.npad_p, S, a.rlog + r * S * S, 1);
+        const float gr = go * expf(val - ov);
+        if (gr != 0.f && val > -INFINITY)
+            slow_sum_backward(a0, b0, (int)a.npad_p, S, a.rlog + r * S * S, 1, val, gr,
+                              smem + m.t + ((size_t)tile * Q * S + (2 * r) * S) * HT + pt,
+                              smem + m.t + ((size_t)tile * Q * S + (2 * r + 1) * S) * HT + pt, HT, a.g_rlog + r * S * S);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// N2: mid region -> gradients of its two leaf vectors
+// ------------------------------------------------------------------------------------
+template <int G, int S>
+__device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, int q, int tile, int npt, int64_t n0g,
+                                int lane) {
+    constexpr int SP = GP_<S>::v, SH = 5, JH = G / 2;
+    static_assert(S > 8 && S <= 10 && SP == 12 && G == 10, "laid out for 10 Gaussians and 9-10 sums");
+    const int h = lane >> 4, pt = lane & (HT - 1);
+    const int Q = 2 * a.st.R;
+    const bool live = pt < npt;
+    const int64_t n = n0g + pt;
+    const float* lv0 = a.leaf_val + (int64_t)(q * 2) * G * a.npad_p + n;
+    float L[G], e[G], ep[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) L[g] = live ? lv0[(int64_t)(h * G + g) * a.npad_p] : 0.f;
+    shift_exp<G>(L, e);
+#pragma unroll
+    for (int g = 0; g < G; ++g) ep[g] = __shfl_xor_sync(0xffffffffu, e[g], 16);
+    float e0[G], e1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        e0[g] = h ? ep[g] : e[g];
+        e1[g] = h ? e[g] : ep[g];
+    }
+    // the sums this half owns, recomputed exactly as in the forward pass
+    float T[SH];
+#pragma unroll
+    for (int c = 0; c < SH; ++c) T[c] = 0.f;
+    {
+        const float* wq = smem + m.wl + q * G * G * SP + 4 * h;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const float pk = e0[i] * e1[j];
+                const float* wk = wq + (j * G + i) * SP;
+                const float4 w = lds_f4(wk);
+                const float w4 = lds_f1(wk + 8 - 3 * h);
+                T[0] = fmaf(pk, w.x, T[0]);
+                T[1] = fmaf(pk, w.y, T[1]);
+                T[2] = fmaf(pk, w.z, T[2]);
+                T[3] = fmaf(pk, w.w, T[3]);
+                T[4] = fmaf(pk, w4, T[4]);
+            }
+        }
+    }
+    const float* gsrow = smem + m.t + ((size_t)tile * Q * S + q * S) * HT + pt;
+    float qv[SH], qvp[SH];
+    unsigned slow_mask = 0;
+#pragma unroll
+    for (int c = 0; c < SH; ++c) {
+        const int s = sum_of_b(h, c);
+        const float gs = (s < S) ? gsrow[s * HT] : 0.f;
+        if (T[c] > LIN_SUM_FLOOR) {
+            qv[c] = gs / T[c];
+        } else {
+            qv[c] = 0.f;
+            if (gs != 0.f && live && s < S) slow_mask |= 1u << c;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SH; ++c) qvp[c] = __shfl_xor_sync(0xffffffffu, qv[c], 16);
+    float qall[12];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        qall[s] = h ? qvp[s] : qv[s];
+        qall[4 + s] = h ? qv[s] : qvp[s];
+    }
+    qall[8] = h ? qvp[4] : qv[4];
+    qall[9] = h ? qv[4] : qvp[4];
+    qall[10] = 0.f;
+    qall[11] = 0.f;
+    // this half walks the products with j in [JH h, JH h + JH)
+    float e1o[JH];
+#pragma unroll
+    for (int jj = 0; jj < JH; ++jj) e1o[jj] = h ? e1[JH + jj] : e1[jj];
+    float acc0[G], acc1[JH];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc0[g] = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < JH; ++jj) acc1[jj] = 0.f;
+    {
+        const float* wb = smem + m.wl + (q * G * G + JH * h * G) * SP;
+#pragma unroll
+        for (int jj = 0; jj < JH; ++jj) {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const float* wk = wb + (jj * G + i) * SP;
+                const float4 w0 = lds_f4(wk), w1 = lds_f4(wk + 4), w2 = lds_f4(wk + 8);
+                float v = qall[0] * w0.x;
+                v = fmaf(qall[1], w0.y, v); v = fmaf(qall[2], w0.z, v); v = fmaf(qall[3], w0.w, v);
+                v = fmaf(qall[4], w1.x, v); v = fmaf(qall[5], w1.y, v); v = fmaf(qall[6], w1.z, v);
+                v = fmaf(qall[7], w1.w, v); v = fmaf(qall[8], w2.x, v); v = fmaf(qall[9], w2.y, v);
+                acc0[i] = fmaf(e1o[jj], v, acc0[i]);
+                acc1[jj] = fmaf(e0[i], v, acc1[jj]);
+            }
+        }
+    }
+    float gl[GLP];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const float p0 = __shfl_xor_sync(0xffffffffu, acc0[g], 16);
+        const float p1 = __shfl_xor_sync(0xffffffffu, acc1[g < JH ? g : g - JH], 16);
+        // h = 0 owns leaf 0: both halves' partial sums over j; h = 1 owns leaf 1: j < JH from the partner, else its own
+        const float tot = h ? (g < JH ? p1 : acc1[g < JH ? 0 : g - JH]) : acc0[g] + p0;
+        gl[g] = e[g] * tot;
+    }
+    gl[10] = 0.f;
+    gl[11] = 0.f;
+    float* gt = smem + m.v + (((size_t)tile * Q * 2 + q * 2 + h) * HT + pt) * GLP;
+    reinterpret_cast<float4*>(gt)[0] = make_float4(gl[0], gl[1], gl[2], gl[3]);
+    reinterpret_cast<float4*>(gt)[1] = make_float4(gl[4], gl[5], gl[6], gl[7]);
+    reinterpret_cast<float4*>(gt)[2] = make_float4(gl[8], gl[9], 0.f, 0.f);
+    if (live) {
+        float* aq = a.aux_reg + (int64_t)q * (2 * G + S) * a.npad_p + n;
+#pragma unroll
+        for (int g = 0; g < G; ++g) aq[(int64_t)(h * G + g) * a.npad_p] = e[g];
+#pragma unroll
+        for (int c = 0; c < SH; ++c) {
+            const int s = sum_of_b(h, c);
+            if (s < S) aq[(int64_t)(2 * G + s) * a.npad_p] = qv[c];
+        }
+    }
+    if (__any_sync(0xffffffffu, slow_mask != 0)) {
+        // exact log-domain backward of the sums whose linear value underflowed (rare); the two halves of a patch take
+        // turns because both add into the two leaf vectors of the region
+        __syncwarp();
+        float* g0 = smem + m.v + (((size_t)tile * Q * 2 + q * 2) * HT + pt) * GLP;
+        for (int phase = 0; phase < 2; ++phase) {
+            if (h == phase && slow_mask)
+                for (int c = 0; c < SH; ++c)
+                    if (slow_mask & (1u << c)) {
+                        const int s = sum_of_b(h, c);
+                        const float sumv = a.sum_val[(int64_t)(q * S + s) * a.npad_p + n];
+                        if (sumv > -INFINITY)
+                            slow_sum_backward(lv0, lv0 + (int64_t)G * a.npad_p, (int)a.npad_p, G,
+                                              a.wlog + (int64_t)q * G * G * SP + s, SP, sumv, gsrow[s * HT], g0,
+                                              g0 + HT * GLP, 1, a.g_wlog + (int64_t)q * G * G * SP + s);
+                    }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) gl[g] = gt[g];
+    }
+    if (live) {
+        float* gg = a.gleaf + (int64_t)((q * 2 + h) * G) * a.npad_p + n;
+#pragma unroll
+        for (int g = 0; g < G; ++g) gg[(int64_t)g * a.npad_p] = gl[g];
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// IN: (x, mask) tile -> (g_x, g_mask) tile
+//   L = -w (a d^2 + b):  dL/dx = -2 w a d,  dL/dmask = +(a d^2 + b) where the mask is inside [0, 1]
+// ------------------------------------------------------------------------------------
+template <int G>
+__device__ void bwd_input_task(const LLArgs& a, const SmemB& m, float* smem, int tile, int pp, int lane) {
+    constexpr int GP = GP_<G>::v;
+    const int hh = lane >> 4, pt = lane & (HT - 1);
+    const int D = a.st.D, R = a.st.R, Q = 2 * R;
+    const int px = 2 * pp + hh;
+    if (px >= D) return;
+    float2* xe = reinterpret_cast<float2*>(smem + m.t) + (size_t)tile * D * HT + px * HT + ((pt + px) & (HT - 1));
+    const float2 v = *xe;
+    const float wv = 1.f - fminf(fmaxf(v.y, 0.f), 1.f);
+    const bool inside = v.y >= 0.f && v.y <= 1.f;
+    const int32_t* sl = reinterpret_cast<const int32_t*>(smem + m.slots) + px * R;
+    const float* glt = smem + m.v + ((size_t)tile * Q * 2 * HT + pt) * GLP;
+    float t1 = 0.f, t2 = 0.f;
+    for (int r = 0; r < R; ++r) {
+        const int pk = sl[r];
+        float mu[GP], aa[GP], bb[GP];
+        load_leaf_params<G, true>(smem + m.lf + (pk & 0xffff) * 3 * GP, mu, aa, bb);
+        const float* gp = glt + (size_t)(pk >> 16) * HT * GLP;
+        const float4 g0 = lds_f4(gp), g1 = lds_f4(gp + 4), g2 = lds_f4(gp + 8);
+        const float gv[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float d = v.x - mu[g];
+            const float ad = aa[g] * d;
+            t1 = fmaf(gv[g], ad, t1);
+            t2 = fmaf(gv[g], fmaf(ad, d, bb[g]), t2);
+        }
+    }
+    *xe = make_float2(-2.f * wv * t1, inside ? t2 : 0.f);
+}
+
+// ------------------------------------------------------------------------------------
+// BR: background root, warp = frame, 8-lane group = root partition, lane j = Gaussian index
+// ------------------------------------------------------------------------------------
+template <int RB, int GB>
+__device__ void bwd_bg_root_frame(const LLArgs& a, const SmemB& m, float* smem, int fi, int64_t f, int lane) {
+    static_assert(GB <= 8 && RB <= 4, "8-lane groups");
+    const int r = lane >> 3, j = lane & 7;
+    const bool on = r < RB && j < GB;
+    const int rr = on ? r : 0, jj = on ? j : 0;
+    const float av = on ? a.bleaf_val[(int64_t)((2 * rr) * GB + jj) * a.npad_f + f] : -INFINITY;
+    const float bv = on ? a.bleaf_val[(int64_t)((2 * rr + 1) * GB + jj) * a.npad_f + f] : -INFINITY;
+    float mA = av, mB = bv;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
+    }
+    const float eA = on ? expf(av - mA) : 0.f, eB = on ? expf(bv - mB) : 0.f;
+    float rowB = 0.f, colA = 0.f;          // rowB_j = sum_i eA_i w[j][i];  colA_i = sum_j eB_j w[j][i]  (lane index = j resp. i)
+#pragma unroll
+    for (int k = 0; k < GB; ++k) {
+        const float ea = __shfl_sync(0xffffffffu, eA, (lane & ~7) + k);
+        const float eb = __shfl_sync(0xffffffffu, eB, (lane & ~7) + k);
+        if (on) {
+            rowB = fmaf(ea, __ldg(a.brlin + rr * GB * GB + jj * GB + k), rowB);
+            colA = fmaf(eb, __ldg(a.brlin + rr * GB * GB + k * GB + jj), colA);
+        }
+    }
+    float U = eB * rowB;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) U += __shfl_xor_sync(0xffffffffu, U, o);
+    const float go = a.g_bg[f], ov = a.out_bg[f];
+    const bool fast = U > LIN_SUM_FLOOR;
+    float c = 0.f;
+    if (fast) c = go * expf(mA + mB + logf(U) - ov) / U;
+    const float gA = c * eA * colA, gB = c * eB * rowB;
+    float* bgl = smem + m.bgl + (size_t)fi * 2 * RB * BGLP;
+    if (r < RB) {
+        bgl[(2 * r) * BGLP + j] = on ? gA : 0.f;
+        bgl[(2 * r + 1) * BGLP + j] = on ? gB : 0.f;
+    }
+    if (on) {
+        a.bgleaf[(int64_t)((2 * r) * GB + j) * a.npad_f + f] = gA;
+        a.bgleaf[(int64_t)((2 * r + 1) * GB + j) * a.npad_f + f] = gB;
+        float* ar = a.baux_root + (int64_t)r * (1 + 2 * GB) * a.npad_f + f;
+        if (j == 0) ar[0] = c;
+        ar[(int64_t)(1 + j) * a.npad_f] = fast ? eA : 0.f;
+        ar[(int64_t)(1 + GB + j) * a.npad_f] = fast ? eB : 0.f;
+    }
+    __syncwarp();
+    if (!fast && r < RB && j == 0) {
+        // exact log-domain backward of this root partition (rare): one lane walks all pairs
+        const float* a0 = a.bleaf_val + (int64_t)((2 * r) * GB) * a.npad_f + f;
+        const float* b0 = a.bleaf_val + (int64_t)((2 * r + 1) * GB) * a.npad_f + f;
+        const float* wl = a.brlog + r * GB * GB;
+        float M = -INFINITY;
+        for (int y = 0; y < GB; ++y)
+            for (int x = 0; x < GB; ++x) M = fmaxf(M, a0[x * a.npad_f] + b0[y * a.npad_f] + wl[y * GB + x]);
+        if (M > -INFINITY) {
+            float acc = 0.f;
+            for (int y = 0; y < GB; ++y)
+                for (int x = 0; x < GB; ++x) acc += expf(a0[x * a.npad_f] + b0[y * a.npad_f] + wl[y * GB + x] - M);
+            const float val = M + logf(acc);
+            const float gr = go * expf(val - ov);
+            if (gr != 0.f)
+                for (int y = 0; y < GB; ++y)
+                    for (int x = 0; x < GB; ++x) {
+                        const float resp = gr * expf(a0[x * a.npad_f] + b0[y * a.npad_f] + wl[y * GB + x] - val);
+                        bgl[(2 * r) * BGLP + x] += resp;
+                        bgl[(2 * r + 1) * BGLP + y] += resp;
+                        a.bgleaf[(int64_t)((2 * r) * GB + x) * a.npad_f + f] += resp;
+                        a.bgleaf[(int64_t)((2 * r + 1) * GB + y) * a.npad_f + f] += resp;
+                        atomicAdd(a.g_brlog + r * GB * GB + y * GB + x, resp);
+                    }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// BI: d/d background mask; lane = pixel, its leaf parameters stay in registers for all frames of the round
+//   dL/dmask = + sum_{r, g} gl[r, side][g] (a d^2 + b)   (the final mask is inside [0, 1] by construction)
+// ------------------------------------------------------------------------------------
+template <int RB, int GB>
+__device__ void bwd_bg_input_task(const LLArgs& a, const SmemB& m, float* smem, int chunk, int nfr, int lane) {
+    constexpr int GPB = GP_<GB>::v;
+    static_assert(GPB == BGLP, "leaf-vector rows are padded like the parameter rows");
+    const int px = chunk * 32 + lane;
+    const bool ok = px < a.Dbg;
+    const int pxc = ok ? px : 0;
+    float mu[RB][GPB], aa[RB][GPB], bb[RB][GPB];
+    unsigned gaddr[RB];
+    const unsigned bgl_s = smem_u32(smem + m.bgl);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        load_leaf_params<GB, false>(a.bleaf + ((int64_t)pxc * RB + r) * 3 * GPB, mu[r], aa[r], bb[r]);
+        gaddr[r] = bgl_s + (unsigned)((2 * r + __ldg(a.bg_side + pxc * RB + r)) * BGLP) * 4u;
+    }
+    unsigned addr = smem_u32(smem + m.fb) + (unsigned)pxc * 8u;
+    const unsigned fstride = (unsigned)a.fs * 8u;
+#pragma unroll
+    for (int f = 0; f < MAXF; ++f) {
+        if (f < nfr) {
+            float xv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(addr));
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                float4 g0, g1;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(gaddr[r] + f * (2 * RB * BGLP * 4)));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(gaddr[r] + f * (2 * RB * BGLP * 4) + 16));
+                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int g = 0; g < GB; ++g) {
+                    const float d = xv - mu[r][g];
+                    t = fmaf(gv[g], fmaf(aa[r][g] * d, d, bb[r][g]), t);
+                }
+            }
+            if (ok) asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + 4u), "f"(t) : "memory");
+            addr += fstride;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// SC: glimpse / mask backward of one frame (warp = frame)
+// ------------------------------------------------------------------------------------
+// background mask before object o at pixel (u, v): the pastes of the earlier objects replayed from their tents
+__device__ __forceinline__ float replay_bg(const float* tt, int ts, int tXs, int o, int u, int v) {
+    float b = 0.f;
+    for (int k = 0; k < o; ++k) {
+        const float* t = tt + k * ts;
+        b = fminf(fmaxf(fmaf(t[2 * tXs + u], t[v], b), 0.f), 1.f);
+    }
+    return b;
+}
+
+__device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, int fi, int64_t f, int lane) {
+    const int AB = a.A * a.B, PP = a.pa * a.pb, D = a.st.D;
+    (void)AB;
+    const int tXs = up4(a.B), tYs = up4(a.A), ts = m.tent_stride;
+    float2* fb = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;       // (x, gradient w.r.t. the background mask)
+    float* tt = smem + m.v + (size_t)fi * a.O * ts;
+    int32_t* rng = reinterpret_cast<int32_t*>(smem + m.rng) + fi * a.O * 2;
+    const float4* zf = reinterpret_cast<const float4*>(a.z) + f * a.O;
+    for (int o = 0; o < a.O; ++o) {
+        const float4 zz = __ldg(zf + o);
+        float* t = tt + o * ts;
+        int ulo, uhi;
+        warp_tents(a, zz.x, zz.y, zz.z, zz.w, t, t + 2 * tXs, t + tXs, t + 2 * tXs + tYs, lane, ulo, uhi);
+        if (lane == 0) { rng[2 * o] = ulo; rng[2 * o + 1] = uhi; }
+    }
+    float xb[MAXIT], yb[MAXIT];
+    {
+        const float rb = recip_n(a.pb, a.align), ra = recip_n(a.pa, a.align);
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int idx = lane + 32 * it, i = idx / a.pb, j = idx - i * a.pb;
+            xb[it] = base_coord_r(j, rb, a.align);
+            yb[it] = base_coord_r(i, ra, a.align);
+        }
+    }
+    const float kB = unnorm_slope(a.B, a.align), kA = unnorm_slope(a.A, a.align);
+    const float oB = unnorm_offset(a.B, a.align), oA = unnorm_offset(a.A, a.align);
+    const float rB = recip_n(a.B, a.align), rA = recip_n(a.A, a.align);
+    const float rPP = 1.f / (float)PP;
+    const float2* xw = reinterpret_cast<const float2*>(smem + m.t);
+    __syncwarp();
+    for (int o = a.O - 1; o >= 0; --o) {
+        const float4 zz = __ldg(zf + o);
+        const float sx = zz.x, sy = zz.y, tx = zz.z, ty = zz.w;
+        const float* t = tt + o * ts;
+        const float *tX = t, *dX = t + tXs, *tY = t + 2 * tXs, *dY = t + 2 * tXs + tYs;
+        const int ulo = rng[2 * o], uhi = rng[2 * o + 1];
+        float gsx = 0.f, gsy = 0.f, gtx = 0.f, gty = 0.f;
+        // (1) clamp backward (gradient passes where 0 <= bg + paste <= 1) and, with paste = tY[u] tX[v], the row sums
+        //     (-> d/d tY) and column sums (-> d/d tX) of what passes.  Rows outside [ulo, uhi] get no paste: bg + 0 is
+        //     inside [0, 1] and the tent derivative is 0 there.
+        if (uhi >= ulo) {
+            float colacc[SCENE_MAXC], txv[SCENE_MAXC];
+#pragma unroll
+            for (int c = 0; c < SCENE_MAXC; ++c) {
+                colacc[c] = 0.f;
+                txv[c] = (lane + 32 * c < a.B) ? tX[lane + 32 * c] : 0.f;
+            }
+            const float isy = 1.f / sy;
+            for (int u = ulo; u <= uhi; ++u) {
+                const float tyu = tY[u];
+                float racc = 0.f;
+#pragma unroll
+                for (int c = 0; c < SCENE_MAXC; ++c) {
+                    const int v = lane + 32 * c;
+                    if (v < a.B) {
+                        const float pre = fmaf(tyu, txv[c], replay_bg(tt, ts, tXs, o, u, v));
+                        float g = fb[u * a.B + v].y;
+                        if (!(pre >= 0.f && pre <= 1.f)) {
+                            g = 0.f;
+                            fb[u * a.B + v].y = 0.f;
+                        }
+                        racc = fmaf(g, txv[c], racc);
+                        colacc[c] = fmaf(g, tyu, colacc[c]);
+                    }
+                }
+                racc = warp_sum(racc);
+                if (lane == 0) {
+                    const float gpy = racc * dY[u] * kA;
+                    const float ybu = base_coord_r(u, rA, a.align);
+                    gsy = fmaf(gpy, -(ybu - ty) * isy * isy, gsy);
+                    gty = fmaf(gpy, -isy, gty);
+                }
+            }
+            const float isx = 1.f / sx;
+#pragma unroll
+            for (int c = 0; c < SCENE_MAXC; ++c) {
+                const int v = lane + 32 * c;
+                if (v < a.B) {
+                    const float gpx = colacc[c] * dX[v] * kB;
+                    const float xbv = base_coord_r(v, rB, a.align);
+                    gsx = fmaf(gpx, -(xbv - tx) * isx * isx, gsx);
+                    gtx = fmaf(gpx, -isx, gtx);
+                }
+            }
+        }
+        __syncwarp();
+        // (2) the sample points of the glimpse and of the mask
+        const float gov = a.g_overlap ? __ldg(a.g_overlap + f * a.O + o) * rPP : 0.f;
+        const int pl = fi * a.O + o, tile = pl / HT, pt = pl - tile * HT;
+        const float2* xt = xw + (size_t)tile * D * HT;
+        const float mx = sx * kB, ox = fmaf(tx, kB, oB), my = sy * kA, oy = fmaf(ty, kA, oA);
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+            const int idx = lane + 32 * it;
+            if (idx < PP) {
+                const Corner c = corners(fmaf(yb[it], my, oy), fmaf(xb[it], mx, ox), a.A, a.B);
+                const float2 gt = xt[idx * HT + ((pt + idx) & (HT - 1))];       // (g_x, g_mask) of this glimpse pixel
+                const float gm = gov + gt.y, gp = gt.x;
+                // corner values of (1 - background before o) and of the frame, zero padded
+                float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f, q00 = 0.f, q01 = 0.f, q10 = 0.f, q11 = 0.f;
+                if (c.oky0 && c.okx0) { m00 = 1.f - replay_bg(tt, ts, tXs, o, c.y0, c.x0); q00 = fb[c.y0 * a.B + c.x0].x; }
+                if (c.oky0 && c.okx1) { m01 = 1.f - replay_bg(tt, ts, tXs, o, c.y0, c.x0 + 1); q01 = fb[c.y0 * a.B + c.x0 + 1].x; }
+                if (c.oky1 && c.okx0) { m10 = 1.f - replay_bg(tt, ts, tXs, o, c.y0 + 1, c.x0); q10 = fb[(c.y0 + 1) * a.B + c.x0].x; }
+                if (c.oky1 && c.okx1) { m11 = 1.f - replay_bg(tt, ts, tXs, o, c.y0 + 1, c.x0 + 1); q11 = fb[(c.y0 + 1) * a.B + c.x0 + 1].x; }
+                const float mdy = (m10 + c.fx * (m11 - m10)) - (m00 + c.fx * (m01 - m00));
+                const float mdx = (1.f - c.fy) * (m01 - m00) + c.fy * (m11 - m10);
+                const float qdy = (q10 + c.fx * (q11 - q10)) - (q00 + c.fx * (q01 - q00));
+                const float qdx = (1.f - c.fy) * (q01 - q00) + c.fy * (q11 - q10);
+                // marg = 1 - sample(1 - bg): d marg / d p = -d sample
+                const float dpx = fmaf(gp, qdx, -gm * mdx), dpy = fmaf(gp, qdy, -gm * mdy);
+                gsx = fmaf(dpx * kB, xb[it], gsx);
+                gtx = fmaf(dpx, kB, gtx);
+                gsy = fmaf(dpy * kA, yb[it], gsy);
+                gty = fmaf(dpy, kA, gty);
+                // d marg / d bg_o = + bilinear weights
+                if (gm != 0.f) {
+                    const float wy0 = 1.f - c.fy, wy1 = c.fy, wx0 = 1.f - c.fx, wx1 = c.fx;
+                    if (c.oky0 && c.okx0) atomicAdd(&fb[c.y0 * a.B + c.x0].y, gm * wy0 * wx0);
+                    if (c.oky0 && c.okx1) atomicAdd(&fb[c.y0 * a.B + c.x0 + 1].y, gm * wy0 * wx1);
+                    if (c.oky1 && c.okx0) atomicAdd(&fb[(c.y0 + 1) * a.B + c.x0].y, gm * wy1 * wx0);
+                    if (c.oky1 && c.okx1) atomicAdd(&fb[(c.y0 + 1) * a.B + c.x0 + 1].y, gm * wy1 * wx1);
+                }
+            }
+        }
+        gsx = warp_sum(gsx); gsy = warp_sum(gsy); gtx = warp_sum(gtx); gty = warp_sum(gty);
+        if (lane == 0) reinterpret_cast<float4*>(a.g_z)[f * a.O + o] = make_float4(gsx, gsy, gtx, gty);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------
+template <int G, int S, int RB, int GB>
+__global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __grid_constant__ LLArgs a) {
+    constexpr int GP = GP_<G>::v, SP = GP_<S>::v;
+    extern __shared__ __align__(16) float smem[];
+    const SmemB m = smem_layout_bwd(a, G, S, GB, RB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int R = a.st.R, Q = 2 * R, D = a.st.D, AB = a.A * a.B;
+    const int64_t per = a.F / gridDim.x, rem = a.F % gridDim.x;
+    const int64_t f0 = blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+    const int cnt = (int)(per + (blockIdx.x < rem ? 1 : 0));
+
+    for (int fr0 = 0; fr0 < cnt; fr0 += a.rf) {
+        const int nfr = min(a.rf, cnt - fr0);
+        const int64_t fbase = f0 + fr0;
+        const int npatch = nfr * a.O, ntile = (npatch + HT - 1) / HT;
+        const int64_t nbase = fbase * a.O;
+        // ---- sum / root weights -> U
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.wlin);
+            float4* dst = reinterpret_cast<float4*>(smem + m.wl);
+            for (int i = tid; i < Q * G * G * SP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
+            for (int i = tid; i < R * S * S; i += blockDim.x) cp_async4(smem + m.rws + i, a.rlin + i);
+            cp_async_commit();
+            for (int i = tid; i < R * S * S; i += blockDim.x) {
+                const int r = i / (S * S), k = i - r * S * S, x = k / S, y = k - x * S;     // rwsT[r][x][y] = w[r][y][x]
+                smem[m.rwsT + i] = __ldg(a.rlin + r * S * S + y * S + x);
+            }
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        // ---- N1, N2
+        for (int t = warp; t < R * ntile; t += nw) {
+            const int tile = t / R, r = t - tile * R;
+            bwd_root_task<S>(a, m, smem, r, tile, min(HT, npatch - tile * HT), nbase + tile * HT, lane);
+        }
+        __syncthreads();
+        for (int t = warp; t < Q * ntile; t += nw) {
+            const int tile = t / Q, q = t - tile * Q;
+            bwd_region_task<G, S>(a, m, smem, q, tile, min(HT, npatch - tile * HT), nbase + tile * HT, lane);
+        }
+        __syncthreads();
+        // ---- leaf table + slot table -> U, (x, mask) tile -> T
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.leaf);
+            float4* dst = reinterpret_cast<float4*>(smem + m.lf);
+            for (int i = tid; i < Q * a.st.pmax * 3 * GP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
+            cp_async_commit();
+            int32_t* sl = reinterpret_cast<int32_t*>(smem + m.slots);
+            for (int i = tid; i < D * R; i += blockDim.x) {
+                const int slot = __ldg(a.st.slot + i);
+                const int q = slot / a.st.pmax, p = slot - q * a.st.pmax;
+                sl[i] = slot | ((q * 2 + (p >= __ldg(a.st.n0 + q) ? 1 : 0)) << 16);
+            }
+            float2* xw = reinterpret_cast<float2*>(smem + m.t);
+            const float* xs = a.patches + nbase * D;
+            const float* ms = a.marg_patch + nbase * D;
+            for (int i = tid; i < npatch * D; i += blockDim.x) {
+                const int p = i / D, px = i - p * D, tile = p / HT, pt = p - tile * HT;
+                xw[(size_t)tile * D * HT + px * HT + ((pt + px) & (HT - 1))] = make_float2(__ldg(xs + i), __ldg(ms + i));
+            }
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        // ---- IN
+        {
+            const int npp = (D + 1) / 2;
+            for (int t = warp; t < ntile * npp; t += nw) {
+                const int tile = t / npp, pp = t - tile * npp;
+                bwd_input_task<G>(a, m, smem, tile, pp, lane);
+            }
+        }
+        __syncthreads();
+        // ---- frames -> U as (x, 0); background root meanwhile (reads global memory, writes bgl)
+        {
+            float2* fb = reinterpret_cast<float2*>(smem + m.fb);
+            const float* src = a.img + fbase * AB;
+            for (int i = tid; i < nfr * AB; i += blockDim.x) {
+                const int fi = i / AB, px = i - fi * AB;
+                fb[(size_t)fi * a.fs + px] = make_float2(__ldg(src + i), 0.f);
+            }
+        }
+        for (int fi = warp; fi < nfr; fi += nw) bwd_bg_root_frame<RB, GB>(a, m, smem, fi, fbase + fi, lane);
+        __syncthreads();
+        // ---- BI
+        for (int t = warp; t < (a.Dbg + 31) / 32; t += nw) bwd_bg_input_task<RB, GB>(a, m, smem, t, nfr, lane);
+        __syncthreads();
+        // ---- SC
+        for (int fi = warp; fi < nfr; fi += nw) scene_frame_bwd(a, m, smem, fi, fbase + fi, lane);
+        __syncthreads();
+    }
+}
+
+}  // namespace sl
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+extern "C" int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb, int align_corners, const float* img,
+                                  const float* z, const stove_spn2_struct* obj, const float* leaf, const float* wlin,
+                                  const float* wlog, const float* rlin, const float* rlog,
+                                  const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
+                                  const float* bleaf, const float* brlin, const float* brlog, const float* patches,
+                                  const float* marg_patch, const float* marg_bg, const float* leaf_val,
+                                  const float* sum_val, const float* out_obj, const float* bleaf_val,
+                                  const float* out_bg, const float* g_obj, const float* g_bg, const float* g_overlap,
+                                  float* g_z, float* g_leaf, float* g_wlog, float* g_rlog, float* g_bleaf,
+                                  float* g_brlog, void* ws_obj, void* ws_bg, void* stream, void* join_obj,
+                                  void* join_bg) {
+    sl::LLArgs a{};
+    STOVE_CHECK_ARG(obj && bg, "null structure");
+    STOVE_CHECK_ARG(F >= 0 && O > 0 && A > 0 && B > 0 && pa > 0 && pb > 0 && img && z && bg_scope && bg_cnt, "bad argument");
+    STOVE_CHECK_ARG(leaf && wlin && wlog && rlin && rlog && bleaf && brlin && brlog && patches && marg_patch && marg_bg &&
+                        leaf_val && sum_val && out_obj && bleaf_val && out_bg && g_obj && g_bg && g_z && g_leaf &&
+                        g_wlog && g_rlog && g_bleaf && g_brlog && ws_obj && ws_bg, "null pointer");
+    STOVE_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)g_z & 15) == 0, "z / g_z must be 16-byte aligned");
+    if (F == 0) return STOVE_OK;
+    a.O = O; a.A = A; a.B = B; a.pa = pa; a.pb = pb; a.align = align_corners; a.F = F;
+    a.img = img; a.z = z;
+    a.st.D = obj->D; a.st.R = obj->R; a.st.pmax = obj->pmax;
+    a.st.scope = obj->region_scope; a.st.n0 = obj->region_n0; a.st.nt = obj->region_n; a.st.slot = obj->pix_slot;
+    a.Np = F * O;
+    a.npad_p = round_up64(a.Np, 32);
+    a.npad_f = round_up64(F, 32);
+    a.Dbg = bg->D; a.bg_side = bg->side; a.bg_scope = bg_scope; a.bg_cnt = bg_cnt;
+    a.leaf = leaf; a.wlin = wlin; a.wlog = wlog; a.rlin = rlin; a.rlog = rlog;
+    a.bleaf = bleaf; a.brlin = brlin; a.brlog = brlog;
+    a.patches = const_cast<float*>(patches); a.marg_patch = const_cast<float*>(marg_patch);
+    a.marg_bg = const_cast<float*>(marg_bg);
+    a.leaf_val = const_cast<float*>(leaf_val); a.sum_val = const_cast<float*>(sum_val);
+    a.out_obj = const_cast<float*>(out_obj); a.bleaf_val = const_cast<float*>(bleaf_val);
+    a.out_bg = const_cast<float*>(out_bg);
+    a.g_obj = g_obj; a.g_bg = g_bg; a.g_overlap = g_overlap; a.g_z = g_z;
+    a.g_wlog = g_wlog; a.g_rlog = g_rlog; a.g_brlog = g_brlog;
+    {
+        // workspace layouts of spn_obj.cu (spn2_ws_layout) and spn_bg.cu (spn1_ws_layout)
+        const int Q = 2 * obj->R, G = obj->G, S = obj->S;
+        float* p = (float*)ws_obj;
+        a.gleaf = p; p += (int64_t)Q * 2 * G * a.npad_p;
+        a.aux_reg = p; p += (int64_t)Q * (2 * G + S) * a.npad_p;
+        a.aux_root = p;
+        float* b = (float*)ws_bg;
+        a.bgleaf = b; b += (int64_t)bg->R * 2 * bg->G * a.npad_f;
+        a.baux_root = b;
+    }
+    int grid;
+    size_t smem;
+    if (bg->side == nullptr || !sl_plan(a, obj->G, obj->S, bg->R, bg->G, &grid, &smem, true)) {
+        stove_set_error("stove_scene_ll_bwd: configuration not supported by the fused kernel (see stove_scene_ll_supported)");
+        return STOVE_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    auto kernel = sl::scene_ll_bwd_kernel<10, 10, 3, 6>;
+    STOVE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    STOVE_KERNEL(K_SCENE_LL_BWD, s, kernel<<<grid, a.nw * 32, smem, s>>>(a));
+    STOVE_LAUNCH_CHECK();
+    // parameter gradients: off the chain, on library side streams, joined where the packing's backward runs
+    int rc;
+    const int64_t Np = F * O;
+    StoveFork* fk0 = !stove_opt(OPT_FORK) ? nullptr : stove_fork_get(0);
+    if (fk0 && (rc = stove_fork(fk0, s, 2))) return rc;
+    if ((rc = spn2_param_kernels(obj, Np, patches, marg_patch, leaf, wlin, rlin, ws_obj, g_leaf, g_wlog, g_rlog,
+                                 fk0 ? fk0->side[0] : s, fk0 ? fk0->side[1] : s)))
+        return rc;
+    if (fk0 && (rc = stove_join(fk0, join_obj ? (cudaStream_t)join_obj : s, 2))) return rc;
+    StoveFork* fk1 = !stove_opt(OPT_FORK) ? nullptr : stove_fork_get(1);
+    if (fk1 && (rc = stove_fork(fk1, s, 2))) return rc;
+    if ((rc = spn1_param_kernels(bg, F, img, marg_bg, bleaf, brlin, ws_bg, g_bleaf, g_brlog, fk1 ? fk1->side[0] : s,
+                                 fk1 ? fk1->side[1] : s)))
+        return rc;
+    if (fk1 && (rc = stove_join(fk1, join_bg ? (cudaStream_t)join_bg : s, 2))) return rc;
+    return STOVE_OK;
+}

@@ -669,6 +669,54 @@ static Spn1Ws spn1_ws_layout(const stove_spn1_struct* st, int64_t N, void* base)
     return w;
 }
 
+// the two parameter-gradient kernels of the backward pass on a workspace filled by the root pass (spn1_bwd_root_kernel
+// here, or the fused chain kernel of scene_ll_bwd.cu)
+int spn1_param_kernels(const stove_spn1_struct* st, int64_t N, const float* x, const float* marg, const float* leaf,
+                       const float* rlin, void* workspace, float* g_leaf, float* g_rlog, cudaStream_t s_leaf,
+                       cudaStream_t s_root) {
+    const int D = st->D;
+    const int64_t npad = round_up64(N, 32);
+    Spn1Ws w = spn1_ws_layout(st, N, workspace);
+    int chunk = (int)round_up64((N + 23) / 24, 32);
+    if (chunk < 32) chunk = 32;
+    const int nchunk = (int)((N + chunk - 1) / chunk);
+    {
+        // leaf-parameter kernel: CTAs of 4 warps holding 66 KB of shared memory each.  With the chunking above the
+        // grid is ~150 CTAs = one per SM, 6 % of the warp slots (ncu) -- it runs at latency, not throughput.  A
+        // finer frame chunk (two 32-frame tiles per CTA, still pipelined) gives ~3 CTAs per SM.
+        int lchunk = chunk;
+        const int ctas_px = (D + 127) / 128;
+        while (lchunk > 64 && (int64_t)ctas_px * ((N + lchunk - 1) / lchunk) < 3 * 148) lchunk = round_up(lchunk / 2, 32);
+        const int lnchunk = (int)((N + lchunk - 1) / lchunk);
+        dim3 grid(ctas_px, lnchunk);
+        const int chunk_saved = chunk;
+        chunk = lchunk;
+        if (D % 4 == 0) {
+            const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 36);
+            if (marg) {
+                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, true><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, false><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
+        } else if (marg)
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+        else
+            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+        STOVE_LAUNCH_CHECK();
+        chunk = chunk_saved;
+    }
+    {
+        dim3 grid(st->R, nchunk);
+        STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s_root, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s_root>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
+        STOVE_LAUNCH_CHECK();
+    }
+    return STOVE_OK;
+}
+
 extern "C" size_t stove_spn1_bwd_workspace(const stove_spn1_struct* st, int64_t N) {
     if (!st || N <= 0) return 0;
     return spn1_ws_layout(st, N, nullptr).bytes;
@@ -709,43 +757,7 @@ extern "C" int stove_spn1_bwd(const stove_spn1_struct* st, int64_t N, const floa
         }
         STOVE_LAUNCH_CHECK();
     }
-    int chunk = (int)round_up64((N + 23) / 24, 32);
-    if (chunk < 32) chunk = 32;
-    const int nchunk = (int)((N + chunk - 1) / chunk);
-    {
-        // leaf-parameter kernel: CTAs of 4 warps holding 66 KB of shared memory each.  With the chunking above the
-        // grid is ~150 CTAs = one per SM, 6 % of the warp slots (ncu) -- it runs at latency, not throughput.  A
-        // finer frame chunk (two 32-frame tiles per CTA, still pipelined) gives ~3 CTAs per SM.
-        int lchunk = chunk;
-        const int ctas_px = (D + 127) / 128;
-        while (lchunk > 64 && (int64_t)ctas_px * ((N + lchunk - 1) / lchunk) < 3 * 148) lchunk = round_up(lchunk / 2, 32);
-        const int lnchunk = (int)((N + lchunk - 1) / lchunk);
-        dim3 grid(ctas_px, lnchunk);
-        const int chunk_saved = chunk;
-        chunk = lchunk;
-        if (D % 4 == 0) {
-            const size_t smem = sizeof(float) * (4 * 32 * 128 + 2 * 3 * 2 * 6 * 36);
-            if (marg) {
-                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, true><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            } else {
-                STOVE_CUDA(cudaFuncSetAttribute(spn1_bwd_leafparam_async_kernel<3, 6, false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_async_kernel<3, 6, false><<<grid, 128, smem, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            }
-        } else if (marg)
-            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, true><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-        else
-            STOVE_KERNEL(K_SPN1_BWD_LEAFPARAM, s_leaf, spn1_bwd_leafparam_kernel<3, 6, false><<<grid, 128, 0, s_leaf>>>(D, st->side, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-        STOVE_LAUNCH_CHECK();
-        chunk = chunk_saved;
-    }
-    {
-        dim3 grid(st->R, nchunk);
-        STOVE_KERNEL(K_SPN1_BWD_ROOTPARAM, s_root, spn1_bwd_rootparam_kernel<3, 6><<<grid, 64, 0, s_root>>>(N, npad, chunk, rlin, w.aux_root, g_rlog));
-        STOVE_LAUNCH_CHECK();
-    }
+    if ((rc = spn1_param_kernels(st, N, x, marg, leaf, rlin, workspace, g_leaf, g_rlog, s_leaf, s_root))) return rc;
     if (fk && (rc = stove_join(fk, join_stream ? (cudaStream_t)join_stream : s, 2))) return rc;   // see spn_obj.cu
     return STOVE_OK;
 }

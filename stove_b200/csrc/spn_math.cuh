@@ -97,3 +97,19 @@ __device__ __forceinline__ void load_leaf_params(const float* __restrict__ lp, f
     }
 }
 
+
+// exact log-domain backward of one sum node (slow path of the node passes): adds the responsibilities to the two
+// input vectors (stride gstride) and, atomically, to the gradient of the log weights
+static __device__ __noinline__ void slow_sum_backward(const float* in0, const float* in1, int stride, int G,
+                                               const float* wlog, int ldw, float sumv, float gs,
+                                               float* g0, float* g1, int gstride, float* g_wlog) {
+    for (int j = 0; j < G; ++j)
+        for (int i = 0; i < G; ++i) {
+            const int k = j * G + i;
+            const float resp = gs * expf(in0[i * stride] + in1[j * stride] + wlog[k * ldw] - sumv);
+            g0[i * gstride] += resp;
+            g1[j * gstride] += resp;
+            atomicAdd(g_wlog + k * ldw, resp);
+        }
+}
+

@@ -209,19 +209,6 @@ __global__ void __launch_bounds__(1024) spn2_fwd_kernel(
 //   writes gleaf [2R*2*G][npad], aux_reg [2R*(2G+S)][npad] = (e0, e1, qv), aux_root
 //   [R*(1+2S)][npad] = (c, eA, eB) for the parameter-gradient kernels.
 // ------------------------------------------------------------------------------------
-__device__ __noinline__ void slow_sum_backward(const float* in0, const float* in1, int stride, int G,
-                                               const float* wlog, int ldw, float sumv, float gs,
-                                               float* g0, float* g1, int gstride, float* g_wlog) {
-    for (int j = 0; j < G; ++j)
-        for (int i = 0; i < G; ++i) {
-            const int k = j * G + i;
-            const float resp = gs * expf(in0[i * stride] + in1[j * stride] + wlog[k * ldw] - sumv);
-            g0[i * gstride] += resp;
-            g1[j * gstride] += resp;
-            atomicAdd(g_wlog + k * ldw, resp);
-        }
-}
-
 template <int G, int S, bool STAGE>
 __global__ void __launch_bounds__(512) spn2_bwd_nodes_kernel(
     Spn2Dev st, int64_t N, int64_t npad, const float* __restrict__ wlin, const float* __restrict__ wlog,
@@ -799,6 +786,65 @@ static Spn2Ws spn2_ws_layout(const stove_spn2_struct* st, int64_t N, void* base)
     return w;
 }
 
+// the two parameter-gradient kernels of the backward pass: they read the workspace written by the node pass
+// (spn2_bwd_nodes_kernel here, or the fused chain kernel of scene_ll_bwd.cu)
+template <int G, int S>
+static int spn2_param_launch(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg,
+                             const float* leaf, const float* wlin, const float* rlin, void* workspace,
+                             float* g_leaf, float* g_wlog, float* g_rlog, cudaStream_t s_leaf, cudaStream_t s_sum) {
+    const int Q = 2 * st->R, D = st->D;
+    const int64_t npad = round_up64(N, 32);
+    Spn2Dev d = to_dev(st);
+    Spn2Ws w = spn2_ws_layout(st, N, workspace);
+    int rc;
+    // chunk the patch axis so that the grid has a few hundred CTAs
+    int chunk = (int)round_up64((N + 23) / 24, 32);
+    if (chunk < 32) chunk = 32;
+    const int nchunk = (int)((N + chunk - 1) / chunk);
+    {
+        const int threads = round_up(st->pmax * G, 32);
+        STOVE_CHECK_ARG(threads <= 1024, "region too large for the leaf-gradient kernel");
+        dim3 grid(Q, nchunk);
+        const size_t smem_async = sizeof(float) * ((size_t)4 * 32 * D + (size_t)2 * 2 * G * 36);
+        if (D % 4 == 0 && smem_async <= 227 * 1024) {
+            if (marg) {
+                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, true>, smem_async))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, true><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, false>, smem_async))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, false><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
+        } else {
+            const size_t smem = sizeof(float) * ((size_t)2 * 32 * (D + 1) + (size_t)2 * G * 33);
+            if (marg) {
+                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            } else {
+                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
+                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
+            }
+        }
+        STOVE_LAUNCH_CHECK();
+    }
+    {
+        const int need = (G * G > S * S) ? G * G : S * S;
+        STOVE_CHECK_ARG(need <= 256, "G*G or S*S > 256");
+        dim3 grid(Q + st->R, nchunk);
+        STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s_sum, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s_sum>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
+        STOVE_LAUNCH_CHECK();
+    }
+    return STOVE_OK;
+}
+
+int spn2_param_kernels(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg, const float* leaf,
+                       const float* wlin, const float* rlin, void* workspace, float* g_leaf, float* g_wlog,
+                       float* g_rlog, cudaStream_t s_leaf, cudaStream_t s_sum) {
+    if (st->G == 10 && st->S == 10)
+        return spn2_param_launch<10, 10>(st, N, x, marg, leaf, wlin, rlin, workspace, g_leaf, g_wlog, g_rlog, s_leaf, s_sum);
+    stove_set_error("spn2_param_kernels: (num_gauss, num_sums) = (%d, %d) is not instantiated", st->G, st->S);
+    return STOVE_ERR_UNSUPPORTED;
+}
+
 template <int G, int S>
 static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* x, const float* marg,
                            const float* leaf, const float* wlin, const float* wlog, const float* rlin,
@@ -856,42 +902,7 @@ static int spn2_bwd_launch(const stove_spn2_struct* st, int64_t N, const float* 
 #undef SPN2_BWD_INPUT_LAUNCH
         STOVE_LAUNCH_CHECK();
     }
-    // chunk the patch axis so that the grid has a few hundred CTAs
-    int chunk = (int)round_up64((N + 23) / 24, 32);
-    if (chunk < 32) chunk = 32;
-    const int nchunk = (int)((N + chunk - 1) / chunk);
-    {
-        const int threads = round_up(st->pmax * G, 32);
-        STOVE_CHECK_ARG(threads <= 1024, "region too large for the leaf-gradient kernel");
-        dim3 grid(Q, nchunk);
-        const size_t smem_async = sizeof(float) * ((size_t)4 * 32 * D + (size_t)2 * 2 * G * 36);
-        if (D % 4 == 0 && smem_async <= 227 * 1024) {
-            if (marg) {
-                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, true>, smem_async))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, true><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            } else {
-                if ((rc = set_smem(spn2_bwd_leafparam_async_kernel<G, false>, smem_async))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_async_kernel<G, false><<<grid, threads, smem_async, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            }
-        } else {
-            const size_t smem = sizeof(float) * ((size_t)2 * 32 * (D + 1) + (size_t)2 * G * 33);
-            if (marg) {
-                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, true>, smem))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, true><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            } else {
-                if ((rc = set_smem(spn2_bwd_leafparam_kernel<G, false>, smem))) return rc;
-                STOVE_KERNEL(K_SPN2_BWD_LEAFPARAM, s_leaf, spn2_bwd_leafparam_kernel<G, false><<<grid, threads, smem, s_leaf>>>(d, N, npad, chunk, x, marg, leaf, w.gleaf, g_leaf));
-            }
-        }
-        STOVE_LAUNCH_CHECK();
-    }
-    {
-        const int need = (G * G > S * S) ? G * G : S * S;
-        STOVE_CHECK_ARG(need <= 256, "G*G or S*S > 256");
-        dim3 grid(Q + st->R, nchunk);
-        STOVE_KERNEL(K_SPN2_BWD_SUMPARAM, s_sum, spn2_bwd_sumparam_kernel<G, S><<<grid, 256, 0, s_sum>>>(d, N, npad, chunk, wlin, rlin, w.aux_reg, w.aux_root, g_wlog, g_rlog));
-        STOVE_LAUNCH_CHECK();
-    }
+    if ((rc = spn2_param_launch<G, S>(st, N, x, marg, leaf, wlin, rlin, workspace, g_leaf, g_wlog, g_rlog, s_leaf, s_sum))) return rc;
     // the parameter gradients are consumed by the backward of the parameter packing: when the caller names the
     // stream that runs on, the side streams join THERE and the caller's stream continues right after the
     // input-gradient kernel (what the rest of the backward chain waits for)

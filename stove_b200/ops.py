@@ -313,6 +313,7 @@ class Scene(torch.autograd.Function):
 # fused scene likelihood: glimpses + masks + object SPN + background SPN (csrc/scene_ll.cu)
 # ----------------------------------------------------------------------------------------
 _SCENE_LL = True
+_SCENE_LL_BWD = True          # False: the fused forward is differentiated by the unfused backward kernels (tests)
 
 
 def set_scene_ll(enabled):
@@ -320,6 +321,12 @@ def set_scene_ll(enabled):
     parity tests compare against).  Returns the previous setting."""
     global _SCENE_LL
     prev, _SCENE_LL = _SCENE_LL, bool(enabled)
+    return prev
+
+
+def set_scene_ll_bwd(enabled):
+    global _SCENE_LL_BWD
+    prev, _SCENE_LL_BWD = _SCENE_LL_BWD, bool(enabled)
     return prev
 
 
@@ -397,6 +404,20 @@ class SceneLL(torch.autograd.Function):
         xb, mb = img.view(F_, -1), marg_bg.view(F_, -1)
         ws2 = torch.empty(max(N.lib().stove_spn2_bwd_workspace(C.byref(st2), n), 4) // 4, device=dev, dtype=torch.float32)
         ws1 = torch.empty(max(N.lib().stove_spn1_bwd_workspace(C.byref(st1), F_), 4) // 4, device=dev, dtype=torch.float32)
+        if _SCENE_LL_BWD:
+            N.check(N.lib().stove_scene_ll_bwd(
+                F_, O, A, B, pa, pb, ac, N.ptr(img), N.ptr(z),
+                C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
+                C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
+                N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog),
+                N.ptr(x2), N.ptr(m2), N.ptr(mb), N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val),
+                N.ptr(out_bg), N.ptr(g_obj), N.ptr(g_bg), N.ptr(g_overlap),
+                N.ptr(g_z), N.ptr(g_leaf), N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(g_bleaf), N.ptr(g_brlog),
+                N.ptr(ws2), N.ptr(ws1), N.stream(), _join_handle(obj_stream), _join_handle(bg_stream)))
+            _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
+            _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
+            return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
+                    None, None)
         g_x, g_m = torch.empty_like(x2), torch.empty_like(m2)
         g_mb = torch.empty_like(mb)
         N.check(N.lib().stove_spn2_bwd(C.byref(st2), n, N.ptr(x2), N.ptr(m2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog),

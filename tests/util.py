@@ -65,6 +65,24 @@ class Checker:
         err = float('inf') if bad_nan else diff / scale
         self.rows.append((name, err, tol, ''))
 
+    def mostly_close(self, name, got, want, tol, max_bad_frac=1e-4):
+        """Like close(), but a fraction of the entries may miss the tolerance: derivatives of bilinear sampling
+        have kinks where a sample point crosses a pixel centre, and two fp32 evaluations of the coordinate can
+        land on different sides (a handful of entries among millions of sample points)."""
+        got, want = got.detach().double().cpu(), want.detach().double().cpu()
+        if got.shape != want.shape:
+            self.rows.append((name, float('inf'), tol, 'shape %s vs %s' % (tuple(got.shape), tuple(want.shape))))
+            return
+        if not bool(torch.isfinite(got).all()):
+            self.rows.append((name, float('inf'), tol, 'non-finite'))
+            return
+        err = (got - want).abs() / (want.abs().max().item() + 1e-300)
+        bad = int((err > tol).sum())
+        allowed = int(max_bad_frac * err.numel())
+        worst = float(err.max())
+        self.rows.append((name, tol if bad <= allowed else worst, tol,
+                          '%d of %d entries above tolerance (allowed %d), worst %.2e' % (bad, err.numel(), allowed, worst)))
+
     def true(self, name, cond):
         self.rows.append((name, 0.0 if cond else float('inf'), 0.5, ''))
 
