@@ -169,7 +169,13 @@ __device__ __forceinline__ void bg_leaf_pass(const LLArgs& a, int task, int l, i
 #pragma unroll
     for (int k = 0; k < NV; ++k) acc[k] = 0.f;
     const unsigned fb_s = (unsigned)__cvta_generic_to_shared(fb), fstride = (unsigned)a.fs * 8u;
-    for (int ib = i0; ib < i1; ib += 32) {
+    // (the iterations of a slice start at a CTA-dependent position and wrap around: every CTA walks the whole leaf
+    // table, and 148 SMs asking the same L2 slices for the same sectors at the same moment serialise there)
+    const int nit = (i1 - i0 + 31) >> 5;
+    int itr = nit > 0 ? (int)(blockIdx.x % (unsigned)nit) : 0;
+    for (int k = 0; k < nit; ++k) {
+        const int ib = i0 + 32 * itr;
+        itr = (itr + 1 == nit) ? 0 : itr + 1;
         const int i = ib + lane;
         const bool ok = i < i1;
         // lanes past the end of the slice read the frame's null pixel (x = 0, mask = 1: weight 0)

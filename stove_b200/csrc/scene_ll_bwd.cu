@@ -410,6 +410,7 @@ __device__ void bwd_bg_input_task(const LLArgs& a, const SmemB& m, float* smem, 
 // SC: glimpse / mask backward of one frame (warp = frame)
 // ------------------------------------------------------------------------------------
 // background mask before object o at pixel (u, v): the pastes of the earlier objects replayed from their tents
+// (o is uniform over the warp: no divergence; 2 loads + FMA + clamp per earlier object)
 __device__ __forceinline__ float replay_bg(const float* tt, int ts, int tXs, int o, int u, int v) {
     float b = 0.f;
     for (int k = 0; k < o; ++k) {
@@ -419,9 +420,29 @@ __device__ __forceinline__ float replay_bg(const float* tt, int ts, int tXs, int
     return b;
 }
 
+// Branch-free corner set of a bilinear sample: clamped addresses + 0/1 validity factors.  (The first version
+// predicated every corner access and replay: 45 % of this phase's instructions were branches, predicate set-up and
+// reconvergence barriers, profiles/r02_ncu_scene_ll_bwd_v1.txt.)
+struct Corner4 {
+    int y0, y1, x0, x1;          // clamped into the frame
+    float fy, fx, k00, k01, k10, k11;
+};
+__device__ __forceinline__ Corner4 corners4(float py, float px, int A, int B) {
+    Corner4 c;
+    const float fy0 = floorf(py), fx0 = floorf(px);
+    c.fy = py - fy0;
+    c.fx = px - fx0;
+    const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)A), x0 = (int)fminf(fmaxf(fx0, -2.f), (float)B);
+    const float oy0 = (y0 >= 0 && y0 < A) ? 1.f : 0.f, oy1 = (y0 + 1 >= 0 && y0 + 1 < A) ? 1.f : 0.f;
+    const float ox0 = (x0 >= 0 && x0 < B) ? 1.f : 0.f, ox1 = (x0 + 1 >= 0 && x0 + 1 < B) ? 1.f : 0.f;
+    c.k00 = oy0 * ox0; c.k01 = oy0 * ox1; c.k10 = oy1 * ox0; c.k11 = oy1 * ox1;
+    c.y0 = min(max(y0, 0), A - 1); c.y1 = min(max(y0 + 1, 0), A - 1);
+    c.x0 = min(max(x0, 0), B - 1); c.x1 = min(max(x0 + 1, 0), B - 1);
+    return c;
+}
+
 __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, int fi, int64_t f, int lane) {
-    const int AB = a.A * a.B, PP = a.pa * a.pb, D = a.st.D;
-    (void)AB;
+    const int PP = a.pa * a.pb, D = a.st.D;
     const int tXs = up4(a.B), tYs = up4(a.A), ts = m.tent_stride;
     float2* fb = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;       // (x, gradient w.r.t. the background mask)
     float* tt = smem + m.v + (size_t)fi * a.O * ts;
@@ -448,62 +469,40 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
     const float oB = unnorm_offset(a.B, a.align), oA = unnorm_offset(a.A, a.align);
     const float rB = recip_n(a.B, a.align), rA = recip_n(a.A, a.align);
     const float rPP = 1.f / (float)PP;
+    const int nc = (a.B + 31) >> 5;                       // columns per lane (B <= 32 SCENE_MAXC)
     const float2* xw = reinterpret_cast<const float2*>(smem + m.t);
     __syncwarp();
     for (int o = a.O - 1; o >= 0; --o) {
         const float4 zz = __ldg(zf + o);
         const float sx = zz.x, sy = zz.y, tx = zz.z, ty = zz.w;
+        const float isx = 1.f / sx, isy = 1.f / sy;
         const float* t = tt + o * ts;
         const float *tX = t, *dX = t + tXs, *tY = t + 2 * tXs, *dY = t + 2 * tXs + tYs;
         const int ulo = rng[2 * o], uhi = rng[2 * o + 1];
-        float gsx = 0.f, gsy = 0.f, gtx = 0.f, gty = 0.f;
-        // (1) clamp backward (gradient passes where 0 <= bg + paste <= 1) and, with paste = tY[u] tX[v], the row sums
-        //     (-> d/d tY) and column sums (-> d/d tX) of what passes.  Rows outside [ulo, uhi] get no paste: bg + 0 is
-        //     inside [0, 1] and the tent derivative is 0 there.
-        if (uhi >= ulo) {
-            float colacc[SCENE_MAXC], txv[SCENE_MAXC];
-#pragma unroll
-            for (int c = 0; c < SCENE_MAXC; ++c) {
-                colacc[c] = 0.f;
-                txv[c] = (lane + 32 * c < a.B) ? tX[lane + 32 * c] : 0.f;
-            }
-            const float isy = 1.f / sy;
+        float gsx = 0.f, gsy = 0.f, gtx = 0.f, gty = 0.f;        // per-lane partial sums, reduced once per object
+        // (1) clamp backward (gradient passes where 0 <= bg + paste <= 1) and, with paste = tY[u] tX[v], the gradient of
+        //     the two tents.  Rows outside [ulo, uhi] get no paste: bg + 0 is inside [0, 1], the tent derivative is 0.
+        for (int c = 0; c < nc; ++c) {
+            const int v = lane + 32 * c;
+            const bool vok = v < a.B;
+            const int vc = vok ? v : 0;
+            const float txv = vok ? tX[vc] : 0.f;
+            float colacc = 0.f;
             for (int u = ulo; u <= uhi; ++u) {
                 const float tyu = tY[u];
-                float racc = 0.f;
-#pragma unroll
-                for (int c = 0; c < SCENE_MAXC; ++c) {
-                    const int v = lane + 32 * c;
-                    if (v < a.B) {
-                        const float pre = fmaf(tyu, txv[c], replay_bg(tt, ts, tXs, o, u, v));
-                        float g = fb[u * a.B + v].y;
-                        if (!(pre >= 0.f && pre <= 1.f)) {
-                            g = 0.f;
-                            fb[u * a.B + v].y = 0.f;
-                        }
-                        racc = fmaf(g, txv[c], racc);
-                        colacc[c] = fmaf(g, tyu, colacc[c]);
-                    }
-                }
-                racc = warp_sum(racc);
-                if (lane == 0) {
-                    const float gpy = racc * dY[u] * kA;
-                    const float ybu = base_coord_r(u, rA, a.align);
-                    gsy = fmaf(gpy, -(ybu - ty) * isy * isy, gsy);
-                    gty = fmaf(gpy, -isy, gty);
-                }
+                const float pre = fmaf(tyu, txv, replay_bg(tt, ts, tXs, o, u, vc));
+                float g = fb[u * a.B + vc].y;
+                if (!(pre >= 0.f && pre <= 1.f)) g = 0.f;
+                if (vok) fb[u * a.B + vc].y = g;
+                // d paste / d tY[u] = tX[v]; tY[u] = tent(p_u), p_u affine in 1 / sy and ty / sy
+                const float gy = g * txv * dY[u] * kA;
+                gsy = fmaf(gy, -(base_coord_r(u, rA, a.align) - ty) * isy * isy, gsy);
+                gty = fmaf(gy, -isy, gty);
+                colacc = fmaf(g, tyu, colacc);
             }
-            const float isx = 1.f / sx;
-#pragma unroll
-            for (int c = 0; c < SCENE_MAXC; ++c) {
-                const int v = lane + 32 * c;
-                if (v < a.B) {
-                    const float gpx = colacc[c] * dX[v] * kB;
-                    const float xbv = base_coord_r(v, rB, a.align);
-                    gsx = fmaf(gpx, -(xbv - tx) * isx * isx, gsx);
-                    gtx = fmaf(gpx, -isx, gtx);
-                }
-            }
+            const float gx = colacc * (vok ? dX[vc] : 0.f) * kB;
+            gsx = fmaf(gx, -(base_coord_r(vc, rB, a.align) - tx) * isx * isx, gsx);
+            gtx = fmaf(gx, -isx, gtx);
         }
         __syncwarp();
         // (2) the sample points of the glimpse and of the mask
@@ -515,15 +514,22 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
         for (int it = 0; it < MAXIT; ++it) {
             const int idx = lane + 32 * it;
             if (idx < PP) {
-                const Corner c = corners(fmaf(yb[it], my, oy), fmaf(xb[it], mx, ox), a.A, a.B);
+                const Corner4 c = corners4(fmaf(yb[it], my, oy), fmaf(xb[it], mx, ox), a.A, a.B);
                 const float2 gt = xt[idx * HT + ((pt + idx) & (HT - 1))];       // (g_x, g_mask) of this glimpse pixel
                 const float gm = gov + gt.y, gp = gt.x;
+                const int a00 = c.y0 * a.B + c.x0, a01 = c.y0 * a.B + c.x1, a10 = c.y1 * a.B + c.x0, a11 = c.y1 * a.B + c.x1;
                 // corner values of (1 - background before o) and of the frame, zero padded
-                float m00 = 0.f, m01 = 0.f, m10 = 0.f, m11 = 0.f, q00 = 0.f, q01 = 0.f, q10 = 0.f, q11 = 0.f;
-                if (c.oky0 && c.okx0) { m00 = 1.f - replay_bg(tt, ts, tXs, o, c.y0, c.x0); q00 = fb[c.y0 * a.B + c.x0].x; }
-                if (c.oky0 && c.okx1) { m01 = 1.f - replay_bg(tt, ts, tXs, o, c.y0, c.x0 + 1); q01 = fb[c.y0 * a.B + c.x0 + 1].x; }
-                if (c.oky1 && c.okx0) { m10 = 1.f - replay_bg(tt, ts, tXs, o, c.y0 + 1, c.x0); q10 = fb[(c.y0 + 1) * a.B + c.x0].x; }
-                if (c.oky1 && c.okx1) { m11 = 1.f - replay_bg(tt, ts, tXs, o, c.y0 + 1, c.x0 + 1); q11 = fb[(c.y0 + 1) * a.B + c.x0 + 1].x; }
+                float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+                for (int k = 0; k < o; ++k) {
+                    const float* tk = tt + k * ts;
+                    const float y0v = tk[2 * tXs + c.y0], y1v = tk[2 * tXs + c.y1], x0v = tk[c.x0], x1v = tk[c.x1];
+                    b00 = fminf(fmaxf(fmaf(y0v, x0v, b00), 0.f), 1.f);
+                    b01 = fminf(fmaxf(fmaf(y0v, x1v, b01), 0.f), 1.f);
+                    b10 = fminf(fmaxf(fmaf(y1v, x0v, b10), 0.f), 1.f);
+                    b11 = fminf(fmaxf(fmaf(y1v, x1v, b11), 0.f), 1.f);
+                }
+                const float m00 = c.k00 * (1.f - b00), m01 = c.k01 * (1.f - b01), m10 = c.k10 * (1.f - b10), m11 = c.k11 * (1.f - b11);
+                const float q00 = c.k00 * fb[a00].x, q01 = c.k01 * fb[a01].x, q10 = c.k10 * fb[a10].x, q11 = c.k11 * fb[a11].x;
                 const float mdy = (m10 + c.fx * (m11 - m10)) - (m00 + c.fx * (m01 - m00));
                 const float mdx = (1.f - c.fy) * (m01 - m00) + c.fy * (m11 - m10);
                 const float qdy = (q10 + c.fx * (q11 - q10)) - (q00 + c.fx * (q01 - q00));
@@ -534,13 +540,13 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
                 gtx = fmaf(dpx, kB, gtx);
                 gsy = fmaf(dpy * kA, yb[it], gsy);
                 gty = fmaf(dpy, kA, gty);
-                // d marg / d bg_o = + bilinear weights
+                // d marg / d bg_o = + bilinear weights (zero weight outside the frame)
                 if (gm != 0.f) {
                     const float wy0 = 1.f - c.fy, wy1 = c.fy, wx0 = 1.f - c.fx, wx1 = c.fx;
-                    if (c.oky0 && c.okx0) atomicAdd(&fb[c.y0 * a.B + c.x0].y, gm * wy0 * wx0);
-                    if (c.oky0 && c.okx1) atomicAdd(&fb[c.y0 * a.B + c.x0 + 1].y, gm * wy0 * wx1);
-                    if (c.oky1 && c.okx0) atomicAdd(&fb[(c.y0 + 1) * a.B + c.x0].y, gm * wy1 * wx0);
-                    if (c.oky1 && c.okx1) atomicAdd(&fb[(c.y0 + 1) * a.B + c.x0 + 1].y, gm * wy1 * wx1);
+                    if (c.k00 != 0.f) atomicAdd(&fb[a00].y, gm * wy0 * wx0);
+                    if (c.k01 != 0.f) atomicAdd(&fb[a01].y, gm * wy0 * wx1);
+                    if (c.k10 != 0.f) atomicAdd(&fb[a10].y, gm * wy1 * wx0);
+                    if (c.k11 != 0.f) atomicAdd(&fb[a11].y, gm * wy1 * wx1);
                 }
             }
         }
@@ -580,6 +586,8 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
                 const int r = i / (S * S), k = i - r * S * S, x = k / S, y = k - x * S;     // rwsT[r][x][y] = w[r][y][x]
                 smem[m.rwsT + i] = __ldg(a.rlin + r * S * S + y * S + x);
             }
+            // background root while the weights are in flight: global memory -> bgl + workspace, independent of the rest
+            for (int fi = warp; fi < nfr; fi += nw) bwd_bg_root_frame<RB, GB>(a, m, smem, fi, fbase + fi, lane);
             cp_async_wait<0>();
         }
         __syncthreads();
@@ -609,9 +617,26 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
             float2* xw = reinterpret_cast<float2*>(smem + m.t);
             const float* xs = a.patches + nbase * D;
             const float* ms = a.marg_patch + nbase * D;
-            for (int i = tid; i < npatch * D; i += blockDim.x) {
-                const int p = i / D, px = i - p * D, tile = p / HT, pt = p - tile * HT;
-                xw[(size_t)tile * D * HT + px * HT + ((pt + px) & (HT - 1))] = make_float2(__ldg(xs + i), __ldg(ms + i));
+            if ((D & 3) == 0) {
+                // warp = patch, lane = 4 pixels: two 16-byte loads, four tile entries
+                for (int p = warp; p < npatch; p += nw) {
+                    const int tile = p / HT, pt = p - tile * HT;
+                    float2* xt = xw + (size_t)tile * D * HT;
+                    for (int l = lane; l < D / 4; l += 32) {
+                        const float4 x4 = __ldg(reinterpret_cast<const float4*>(xs + (size_t)p * D) + l);
+                        const float4 m4 = __ldg(reinterpret_cast<const float4*>(ms + (size_t)p * D) + l);
+                        const int px = 4 * l;
+                        xt[px * HT + ((pt + px) & (HT - 1))] = make_float2(x4.x, m4.x);
+                        xt[(px + 1) * HT + ((pt + px + 1) & (HT - 1))] = make_float2(x4.y, m4.y);
+                        xt[(px + 2) * HT + ((pt + px + 2) & (HT - 1))] = make_float2(x4.z, m4.z);
+                        xt[(px + 3) * HT + ((pt + px + 3) & (HT - 1))] = make_float2(x4.w, m4.w);
+                    }
+                }
+            } else {
+                for (int i = tid; i < npatch * D; i += blockDim.x) {
+                    const int p = i / D, px = i - p * D, tile = p / HT, pt = p - tile * HT;
+                    xw[(size_t)tile * D * HT + px * HT + ((pt + px) & (HT - 1))] = make_float2(__ldg(xs + i), __ldg(ms + i));
+                }
             }
             cp_async_wait<0>();
         }
@@ -625,19 +650,32 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
             }
         }
         __syncthreads();
-        // ---- frames -> U as (x, 0); background root meanwhile (reads global memory, writes bgl)
-        {
-            float2* fb = reinterpret_cast<float2*>(smem + m.fb);
-            const float* src = a.img + fbase * AB;
-            for (int i = tid; i < nfr * AB; i += blockDim.x) {
-                const int fi = i / AB, px = i - fi * AB;
-                fb[(size_t)fi * a.fs + px] = make_float2(__ldg(src + i), 0.f);
+        // ---- frames -> U as (x, 0)
+        for (int fi = 0; fi < nfr; ++fi) {
+            float2* dst = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;
+            const float* src = a.img + (fbase + fi) * AB;
+            if ((AB & 3) == 0) {
+                for (int i = tid; i < AB / 4; i += blockDim.x) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
+                    float4* d4 = reinterpret_cast<float4*>(dst + 4 * i);
+                    d4[0] = make_float4(t.x, 0.f, t.y, 0.f);
+                    d4[1] = make_float4(t.z, 0.f, t.w, 0.f);
+                }
+            } else {
+                for (int i = tid; i < AB; i += blockDim.x) dst[i] = make_float2(__ldg(src + i), 0.f);
             }
         }
-        for (int fi = warp; fi < nfr; fi += nw) bwd_bg_root_frame<RB, GB>(a, m, smem, fi, fbase + fi, lane);
         __syncthreads();
         // ---- BI
-        for (int t = warp; t < (a.Dbg + 31) / 32; t += nw) bwd_bg_input_task<RB, GB>(a, m, smem, t, nfr, lane);
+        {
+            // every CTA walks the whole leaf table: start at a CTA-dependent chunk so that the 148 SMs do not ask the
+            // same L2 slices for the same sectors at the same moment
+            const int nch = (a.Dbg + 31) / 32, rot = (int)((blockIdx.x * 5u) % (unsigned)nch);
+            for (int t = warp; t < nch; t += nw) {
+                const int ch = t + rot;
+                bwd_bg_input_task<RB, GB>(a, m, smem, ch < nch ? ch : ch - nch, nfr, lane);
+            }
+        }
         __syncthreads();
         // ---- SC
         for (int fi = warp; fi < nfr; fi += nw) scene_frame_bwd(a, m, smem, fi, fbase + fi, lane);
