@@ -177,6 +177,11 @@ int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int a
  * stove_scene_ll_supported returns 1 when the configuration fits the fused kernels (C = 1, the D2 / D1
  * structures with 10 Gaussians / 10 sums and 3 x 6, shared memory); otherwise use the unfused calls.
  * ------------------------------------------------------------------------------------ */
+/* bleaf_il: lane-interleaved copy of the background leaf table (stove_spn_interleave_leaf) -- blocks of 32 rows laid
+ * out [6 float4 parts][32 rows] so that a warp whose lanes own consecutive rows loads it fully coalesced.  Row order
+ * of the forward pass: (leaf l, position in bg_scope[l]), leaves il_stride rows apart; of the backward pass:
+ * (repetition r, pixel), repetitions il_stride rows apart.  il_stride is a multiple of 32; unused rows are zero. */
+int stove_spn_interleave_leaf(const float* leaf, const int32_t* row_map, int64_t rows, float* out, void* stream);
 int stove_scene_ll_supported(int64_t F, int O, int C, int A, int B, int pa, int pb,
                              const stove_spn2_struct* obj, const stove_spn1_struct* bg);
 int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb, int align_corners,
@@ -185,6 +190,7 @@ int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb, int align
                        const float* rlin, const float* rlog,
                        const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
                        const float* bleaf, const float* brlin, const float* brlog,
+                       const float* bleaf_il, int il_stride,
                        float* patches, float* marg_patch, float* marg_bg, float* overlap,
                        float* leaf_val, float* sum_val, float* out_obj, float* bleaf_val, float* out_bg,
                        void* stream);
@@ -201,6 +207,7 @@ int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb, int align
                        const float* rlin, const float* rlog,
                        const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
                        const float* bleaf, const float* brlin, const float* brlog,
+                       const float* bleaf_il, int il_stride,
                        const float* patches, const float* marg_patch, const float* marg_bg,
                        const float* leaf_val, const float* sum_val, const float* out_obj,
                        const float* bleaf_val, const float* out_bg,

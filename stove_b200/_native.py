@@ -99,8 +99,9 @@ SIGNATURES = {
     'stove_scene_fwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 6 + [vp]),
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
     'stove_scene_ll_supported': (C.c_int, [i64] + [C.c_int] * 6 + [P2, P1]),
-    'stove_scene_ll_fwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp] * 9 + [vp]),
-    'stove_scene_ll_bwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp] * 8 + [vp] * 3
+    'stove_spn_interleave_leaf': (C.c_int, [vp, vp, i64, vp, vp]),
+    'stove_scene_ll_fwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp, C.c_int] + [vp] * 9 + [vp]),
+    'stove_scene_ll_bwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp, C.c_int] + [vp] * 8 + [vp] * 3
                            + [vp] * 6 + [vp, vp] + [vp, vp, vp]),
     'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),

@@ -180,8 +180,11 @@ __device__ __forceinline__ void bg_leaf_pass(const LLArgs& a, int task, int l, i
         const bool ok = i < i1;
         // lanes past the end of the slice read the frame's null pixel (x = 0, mask = 1: weight 0)
         const int px = ok ? __ldg(sc + i) : a.Dbg;
-        const float4* p4 = reinterpret_cast<const float4*>(a.bleaf + ((int64_t)(ok ? px : 0) * RB + r) * 3 * GPB + G0);
-        const float4 m4 = __ldg(p4), a4 = __ldg(p4 + GPB / 4), b4 = __ldg(p4 + 2 * (GPB / 4));
+        // interleaved table: block of 32 rows = [6 parts][32 lanes] float4, rows of leaf l start at l * il_stride;
+        // rows past the end of the scope are zero (slices start at multiples of 32)
+        const float4* p4 = reinterpret_cast<const float4*>(a.bleaf_il) + ((int64_t)(l * a.il_stride + ib) >> 5) * (6 * 32) + lane;
+        const float4 m4 = __ldg(p4 + (G0 / 4) * 32), a4 = __ldg(p4 + (GPB / 4 + G0 / 4) * 32),
+                     b4 = __ldg(p4 + (2 * (GPB / 4) + G0 / 4) * 32);
         const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
         unsigned addr = fb_s + (unsigned)px * 8u;
         // one address increment per frame instead of index arithmetic on the runtime frame stride (the first version
@@ -212,11 +215,11 @@ __device__ __forceinline__ void bg_leaf_pass(const LLArgs& a, int task, int l, i
 
 template <int RB, int GB>
 __device__ void bg_leaf_task(const LLArgs& a, int task, int nfr, const float2* fb, float* bgpart, int lane) {
-    static_assert(GB > 4 && GB <= 8, "two passes: Gaussians 0-3, then 4 .. GB-1");
+    static_assert(GB > 4 && GB <= 8 && GP_<GB>::v == 8, "two passes: Gaussians 0-3, then 4 .. GB-1; 8-float parameter rows");
     const int l = task / a.ns, s = task - l * a.ns, r = l >> 1;
     const int cnt = __ldg(a.bg_cnt + l);
-    const int per = (cnt + a.ns - 1) / a.ns;
-    const int i0 = s * per, i1 = min(cnt, i0 + per);
+    const int per = ((cnt + a.ns - 1) / a.ns + 31) & ~31;            // slices start at multiples of 32 (interleaved table)
+    const int i0 = min(cnt, s * per), i1 = min(cnt, i0 + per);
     // 13 frames x 6 Gaussians of accumulators + 18 parameters do not fit the 96 registers a 576-thread CTA gets
     // (the first version spilled inside the loop: profiles/r02_ncu_scene_ll_fwd_v1.txt)
     bg_leaf_pass<RB, GB, 0, 4>(a, task, l, r, i0, i1, nfr, fb, bgpart, lane);
@@ -585,15 +588,18 @@ extern "C" int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb
                                   const float* z, const stove_spn2_struct* obj, const float* leaf, const float* wlin,
                                   const float* wlog, const float* rlin, const float* rlog,
                                   const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
-                                  const float* bleaf, const float* brlin, const float* brlog, float* patches,
+                                  const float* bleaf, const float* brlin, const float* brlog, const float* bleaf_il,
+                                  int il_stride, float* patches,
                                   float* marg_patch, float* marg_bg, float* overlap, float* leaf_val, float* sum_val,
                                   float* out_obj, float* bleaf_val, float* out_bg, void* stream) {
     sl::LLArgs a{};
     int rc = sl_fill(a, F, O, A, B, pa, pb, align_corners, img, z, obj, bg, bg_scope, bg_cnt);
     if (rc) return rc;
     STOVE_CHECK_ARG(leaf && wlin && wlog && rlin && rlog && bleaf && brlin && brlog && patches && marg_patch && marg_bg &&
-                        overlap && leaf_val && sum_val && out_obj && bleaf_val && out_bg, "null pointer");
+                        overlap && leaf_val && sum_val && out_obj && bleaf_val && out_bg && bleaf_il, "null pointer");
+    STOVE_CHECK_ARG(il_stride > 0 && (il_stride & 31) == 0 && ((uintptr_t)bleaf_il & 15) == 0, "bad interleaved table");
     if (F == 0) return STOVE_OK;
+    a.bleaf_il = bleaf_il; a.il_stride = il_stride;
     a.leaf = leaf; a.wlin = wlin; a.wlog = wlog; a.rlin = rlin; a.rlog = rlog;
     a.bleaf = bleaf; a.brlin = brlin; a.brlog = brlog;
     a.patches = patches; a.marg_patch = marg_patch; a.marg_bg = marg_bg; a.overlap = overlap;

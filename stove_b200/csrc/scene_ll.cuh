@@ -34,6 +34,8 @@ struct LLArgs {
     const int32_t* bg_scope;     // [2R][D]: pixels of leaf l = 2 r + side, ascending
     const int32_t* bg_cnt;       // [2R]
     const float *bleaf, *brlin, *brlog;
+    const float* bleaf_il;       // lane-interleaved copy (stove_spn_interleave_leaf), row groups il_stride rows apart
+    int il_stride;
     float *bleaf_val, *out_bg;
     int64_t npad_f;
     // backward only

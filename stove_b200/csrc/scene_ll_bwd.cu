@@ -377,7 +377,13 @@ __device__ void bwd_bg_input_task(const LLArgs& a, const SmemB& m, float* smem, 
     const unsigned bgl_s = smem_u32(smem + m.bgl);
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-        load_leaf_params<GB, false>(a.bleaf + ((int64_t)pxc * RB + r) * 3 * GPB, mu[r], aa[r], bb[r]);
+        // interleaved table, rows (r, pixel): block of 32 pixels = [6 parts][32 lanes] float4 -> coalesced 512-byte loads
+        const float4* p4 = reinterpret_cast<const float4*>(a.bleaf_il) + ((int64_t)(r * a.il_stride + chunk * 32) >> 5) * (6 * 32) + lane;
+        const float4 m0 = __ldg(p4), m1 = __ldg(p4 + 32), a0 = __ldg(p4 + 64), a1 = __ldg(p4 + 96), b0 = __ldg(p4 + 128),
+                     b1 = __ldg(p4 + 160);
+        mu[r][0] = m0.x; mu[r][1] = m0.y; mu[r][2] = m0.z; mu[r][3] = m0.w; mu[r][4] = m1.x; mu[r][5] = m1.y; mu[r][6] = m1.z; mu[r][7] = m1.w;
+        aa[r][0] = a0.x; aa[r][1] = a0.y; aa[r][2] = a0.z; aa[r][3] = a0.w; aa[r][4] = a1.x; aa[r][5] = a1.y; aa[r][6] = a1.z; aa[r][7] = a1.w;
+        bb[r][0] = b0.x; bb[r][1] = b0.y; bb[r][2] = b0.z; bb[r][3] = b0.w; bb[r][4] = b1.x; bb[r][5] = b1.y; bb[r][6] = b1.z; bb[r][7] = b1.w;
         gaddr[r] = bgl_s + (unsigned)((2 * r + __ldg(a.bg_side + pxc * RB + r)) * BGLP) * 4u;
     }
     unsigned addr = smem_u32(smem + m.fb) + (unsigned)pxc * 8u;
@@ -650,18 +656,32 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
             }
         }
         __syncthreads();
-        // ---- frames -> U as (x, 0)
-        for (int fi = 0; fi < nfr; ++fi) {
-            float2* dst = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;
-            const float* src = a.img + (fbase + fi) * AB;
-            if ((AB & 3) == 0) {
-                for (int i = tid; i < AB / 4; i += blockDim.x) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(src) + i);
-                    float4* d4 = reinterpret_cast<float4*>(dst + 4 * i);
-                    d4[0] = make_float4(t.x, 0.f, t.y, 0.f);
-                    d4[1] = make_float4(t.z, 0.f, t.w, 0.f);
+        // ---- frames -> U as (x, 0): the frames of a round are contiguous in global memory; 8 loads in flight per thread
+        if ((AB & 3) == 0) {
+            const float4* src = reinterpret_cast<const float4*>(a.img + fbase * AB);
+            const int q4 = AB / 4, tot = nfr * q4;
+            for (int i0 = 0; i0 < tot; i0 += 8 * (int)blockDim.x) {
+                float4 t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * (int)blockDim.x + tid;
+                    t[k] = i < tot ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k * (int)blockDim.x + tid;
+                    if (i < tot) {
+                        const int fi = i / q4, j = i - fi * q4;
+                        float4* d4 = reinterpret_cast<float4*>(reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs + 4 * j);
+                        d4[0] = make_float4(t[k].x, 0.f, t[k].y, 0.f);
+                        d4[1] = make_float4(t[k].z, 0.f, t[k].w, 0.f);
+                    }
+                }
+            }
+        } else {
+            for (int fi = 0; fi < nfr; ++fi) {
+                float2* dst = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;
+                const float* src = a.img + (fbase + fi) * AB;
                 for (int i = tid; i < AB; i += blockDim.x) dst[i] = make_float2(__ldg(src + i), 0.f);
             }
         }
@@ -692,7 +712,8 @@ extern "C" int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb
                                   const float* z, const stove_spn2_struct* obj, const float* leaf, const float* wlin,
                                   const float* wlog, const float* rlin, const float* rlog,
                                   const stove_spn1_struct* bg, const int32_t* bg_scope, const int32_t* bg_cnt,
-                                  const float* bleaf, const float* brlin, const float* brlog, const float* patches,
+                                  const float* bleaf, const float* brlin, const float* brlog, const float* bleaf_il,
+                                  int il_stride, const float* patches,
                                   const float* marg_patch, const float* marg_bg, const float* leaf_val,
                                   const float* sum_val, const float* out_obj, const float* bleaf_val,
                                   const float* out_bg, const float* g_obj, const float* g_bg, const float* g_overlap,
@@ -706,7 +727,9 @@ extern "C" int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb
                         leaf_val && sum_val && out_obj && bleaf_val && out_bg && g_obj && g_bg && g_z && g_leaf &&
                         g_wlog && g_rlog && g_bleaf && g_brlog && ws_obj && ws_bg, "null pointer");
     STOVE_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)g_z & 15) == 0, "z / g_z must be 16-byte aligned");
+    STOVE_CHECK_ARG(bleaf_il && il_stride > 0 && (il_stride & 31) == 0 && ((uintptr_t)bleaf_il & 15) == 0, "bad interleaved table");
     if (F == 0) return STOVE_OK;
+    a.bleaf_il = bleaf_il; a.il_stride = il_stride;
     a.O = O; a.A = A; a.B = B; a.pa = pa; a.pb = pb; a.align = align_corners; a.F = F;
     a.img = img; a.z = z;
     a.st.D = obj->D; a.st.R = obj->R; a.st.pmax = obj->pmax;

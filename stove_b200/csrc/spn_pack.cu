@@ -111,3 +111,30 @@ extern "C" int stove_spn_pack_sum_bwd(const float* wlog, int nb, int K, int S, i
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
 }
+
+// Lane-interleaved copy of a packed leaf table with 8-float parameter rows (24 floats = 6 float4 per row): blocks of 32
+// rows stored [6 parts][32 rows] float4.  The fused scene-likelihood kernels (scene_ll*.cu) walk the whole background
+// leaf table in every CTA with lane = row: with the plain layout every 16-byte load of a warp touched 32 different
+// cache lines and the pass was bound by the load unit (43 % of its stall samples: lg_throttle).
+__global__ void interleave_leaf_kernel(const float4* __restrict__ src, const int32_t* __restrict__ row_map, int64_t rows,
+                                       float4* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;       // (block, part, lane)
+    const int64_t nblk = (rows + 31) / 32;
+    if (i >= nblk * 6 * 32) return;
+    const int lane = (int)(i & 31), part = (int)((i >> 5) % 6);
+    const int64_t row = (i / (6 * 32)) * 32 + lane;
+    const int sr = row < rows ? __ldg(row_map + row) : -1;
+    out[i] = sr >= 0 ? __ldg(src + (int64_t)sr * 6 + part) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+extern "C" int stove_spn_interleave_leaf(const float* leaf, const int32_t* row_map, int64_t rows, float* out, void* stream) {
+    STOVE_CHECK_ARG(leaf && row_map && out && rows >= 0, "bad argument");
+    STOVE_CHECK_ARG(((uintptr_t)leaf & 15) == 0 && ((uintptr_t)out & 15) == 0, "tables must be 16-byte aligned");
+    if (rows == 0) return STOVE_OK;
+    const int64_t n = (rows + 31) / 32 * 6 * 32;
+    cudaStream_t s = (cudaStream_t)stream;
+    STOVE_KERNEL(K_PACK_LEAF_FWD, s, interleave_leaf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(leaf), row_map, rows, reinterpret_cast<float4*>(out)));
+    STOVE_LAUNCH_CHECK();
+    return STOVE_OK;
+}

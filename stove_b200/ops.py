@@ -130,6 +130,18 @@ class PackSum(torch.autograd.Function):
         return g_raw, None
 
 
+def interleave_leaf(leaf, row_map):
+    """Lane-interleaved copy of a packed leaf table with 8-float parameter rows ([row][3][8] -> blocks of 32 rows laid
+    out [6 float4 parts][32 rows]): a warp whose lanes own consecutive rows reads it with fully coalesced 16-byte loads.
+    row_map (int32): source row of every destination row, -1 = zero row.  Not differentiable -- the fused
+    scene-likelihood kernels read it, parameter gradients are taken w.r.t. the plain table."""
+    N.require_cuda_f32(leaf)
+    n = row_map.numel()
+    out = torch.empty((n + 31) // 32 * 32 * 24, device=leaf.device, dtype=leaf.dtype)
+    N.check(N.lib().stove_spn_interleave_leaf(N.ptr(leaf.detach()), N.ptr(row_map), n, N.ptr(out), N.stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # fused SPNs
 # ----------------------------------------------------------------------------------------
@@ -347,7 +359,7 @@ class SceneLL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, obj_tables, bg_tables, pa, pb,
-                align_corners, obj_stream=None, bg_stream=None):
+                align_corners, obj_stream=None, bg_stream=None, bleaf_il_f=None, bleaf_il_b=None):
         img, z = img.contiguous(), z.contiguous()
         N.require_cuda_f32(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin)
         F_, Cc, A, B = img.shape
@@ -370,7 +382,7 @@ class SceneLL(torch.autograd.Function):
             F_, O, A, B, pa, pb, int(align_corners), N.ptr(img), N.ptr(z),
             C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
             C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
-            N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog),
+            N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog), N.ptr(bleaf_il_f), bg_tables.il_stride_f,
             N.ptr(patches), N.ptr(marg_patch), N.ptr(marg_bg), N.ptr(overlap),
             N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val), N.ptr(out_bg), N.stream()))
         ctx.save_for_backward(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch, marg_bg,
@@ -378,6 +390,7 @@ class SceneLL(torch.autograd.Function):
         ctx.tables = (obj_tables, bg_tables)
         ctx.meta = (F_, O, Cc, A, B, pa, pb, int(align_corners))
         ctx.streams = (obj_stream, bg_stream)
+        ctx.bleaf_il_b = bleaf_il_b
         ctx.mark_non_differentiable(patches, marg_patch, marg_bg)
         return out_bg, out_obj, overlap, patches, marg_patch, marg_bg
 
@@ -409,7 +422,7 @@ class SceneLL(torch.autograd.Function):
                 F_, O, A, B, pa, pb, ac, N.ptr(img), N.ptr(z),
                 C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
                 C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
-                N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog),
+                N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog), N.ptr(ctx.bleaf_il_b), bg_tables.il_stride_b,
                 N.ptr(x2), N.ptr(m2), N.ptr(mb), N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val),
                 N.ptr(out_bg), N.ptr(g_obj), N.ptr(g_bg), N.ptr(g_overlap),
                 N.ptr(g_z), N.ptr(g_leaf), N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(g_bleaf), N.ptr(g_brlog),
@@ -417,7 +430,7 @@ class SceneLL(torch.autograd.Function):
             _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
             _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
             return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
-                    None, None)
+                    None, None, None, None)
         g_x, g_m = torch.empty_like(x2), torch.empty_like(m2)
         g_mb = torch.empty_like(mb)
         N.check(N.lib().stove_spn2_bwd(C.byref(st2), n, N.ptr(x2), N.ptr(m2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog),
@@ -433,7 +446,7 @@ class SceneLL(torch.autograd.Function):
         _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
         _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
         return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
-                None, None)
+                None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------

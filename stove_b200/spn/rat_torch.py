@@ -208,6 +208,7 @@ class PackedSpn:
     def __init__(self, kind, tables, leaf, wlog=None, wlin=None, rlog=None, rlin=None):
         self.kind, self.tables = kind, tables
         self.leaf, self.wlog, self.wlin, self.rlog, self.rlin = leaf, wlog, wlin, rlog, rlin
+        self.leaf_il_f = self.leaf_il_b = None      # background SPN: lane-interleaved copies (fused scene likelihood)
         # stream the packing ran on: its backward runs there too, so the parameter-gradient kernels of the
         # SPN backward can be handed to it and leave the chain of the caller's stream (ops.Spn2 / ops.Spn1)
         self.stream = torch.cuda.current_stream(leaf.device) if leaf.is_cuda else None
@@ -297,8 +298,21 @@ class RatSpn(nn.Module):
                     px = np.nonzero(side[:, r] == h)[0]
                     bg_scope[2 * r + h, :len(px)] = px
                     bg_cnt[2 * r + h] = len(px)
-            host = {'side': side, 'dst_row': np.asarray(dst, dtype=np.int32), 'bg_scope': bg_scope, 'bg_cnt': bg_cnt}
+            # lane-interleaved copies of the packed leaf table for the fused kernels (ops.interleave_leaf): row order
+            # of the forward pass = (leaf, position in its scope list), of the backward pass = (repetition, pixel)
+            Ls = (int(bg_cnt.max()) + 31) // 32 * 32
+            Dp = (D + 31) // 32 * 32
+            il_f = np.full(2 * R * Ls, -1, dtype=np.int32)
+            il_b = np.full(R * Dp, -1, dtype=np.int32)
+            for r in range(R):
+                for h in (0, 1):
+                    l = 2 * r + h
+                    il_f[l * Ls:l * Ls + bg_cnt[l]] = bg_scope[l, :bg_cnt[l]] * R + r
+                il_b[r * Dp:r * Dp + D] = np.arange(D) * R + r
+            host = {'side': side, 'dst_row': np.asarray(dst, dtype=np.int32), 'bg_scope': bg_scope, 'bg_cnt': bg_cnt,
+                    'il_f': il_f, 'il_b': il_b}
             t = _Tables('D1', host, dict(D=D, R=R, G=G))
+            t.il_stride_f, t.il_stride_b = Ls, Dp
             t.leaf_order, t.prow_total, t.GP = order, D * R, (G + 3) // 4 * 4
             return t
         S = self.args.num_sums
@@ -360,7 +374,11 @@ class RatSpn(nn.Module):
                                   float(a.gauss_min_sigma), float(a.gauss_max_sigma))
         rlog, rlin = ops.PackSum.apply(self.output_vector.params.unsqueeze(0), 1)
         if t.kind == 'D1':
-            return PackedSpn('D1', t, leaf, rlog=rlog, rlin=rlin)
+            pk = PackedSpn('D1', t, leaf, rlog=rlog, rlin=rlin)
+            if (t.GP == 8) and leaf.is_cuda:
+                pk.leaf_il_f = ops.interleave_leaf(leaf, t.dev['il_f'])
+                pk.leaf_il_b = ops.interleave_leaf(leaf, t.dev['il_b'])
+            return pk
         wlog, wlin = ops.PackSum.apply(torch.stack([m.params for m in t.mid_sums], 0), t.SP)
         return PackedSpn('D2', t, leaf, wlog, wlin, rlog, rlin)
 

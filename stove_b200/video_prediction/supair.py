@@ -94,7 +94,7 @@ class Supair(nn.Module):
             bg_loglik, patches_loglik, overlap, patches, marg_patch, marg_bg = ops.SceneLL.apply(
                 x_img, z_img, pk_obj.leaf, pk_obj.wlog, pk_obj.wlin, pk_obj.rlog, pk_obj.rlin,
                 pk_bg.leaf, pk_bg.rlog, pk_bg.rlin, pk_obj.tables, pk_bg.tables,
-                c.patch_width, c.patch_height, self._align(), streams[0], streams[1])
+                c.patch_width, c.patch_height, self._align(), streams[0], streams[1], pk_bg.leaf_il_f, pk_bg.leaf_il_b)
             extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marg_patch.flatten(start_dim=1),
                          marginalise_bg=marg_bg)
             return bg_loglik, patches_loglik, overlap, extra
