@@ -512,7 +512,7 @@ def run_b200(args):
         roofline['whole_step'] = train_roofline(value / world, 3 * step_flops(O, RES), 142e3, pk)
         # the other tensor-core kernels of the recognition LSTM, for the record
         roofline['other_kernels'] = {k: kernel_roofline(k, per[k], n_steps_prof, pk, brief=True)
-                                     for k in ('lstm_gemm_cell_fwd', 'tc3_gemm', 'dynloop_fwd', 'dynloop_bwd', 'scene_bwd')
+                                     for k in ('lstm_gemm_cell_fwd', 'tc3_gemm', 'dynloop_fwd', 'dynloop_bwd', 'scene_ll_fwd', 'scene_ll_bwd')
                                      if k in per and k != top}
 
     extra = {}
@@ -835,6 +835,10 @@ def kernel_algorithmic_bytes(kernel, batch):
         'spn2_bwd_sumparam': patches * (12 * 30 + 6 * 21) * 4,
         'scene_fwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
         'scene_bwd': frames * (D_bg * 4 * 2 + O * (16 + 2 * D_obj * 4)),
+        # fused scene likelihood (4.2 KB per scored frame at 32x32, O = 3): frame + z in, 1 + 2 O scalars out,
+        # the packed SPN tables once (object leaf / sum / root weights, background leaf table)
+        'scene_ll_fwd': frames * (D_bg * 4 + O * 16 + (1 + 2 * O) * 4) + 4 * (21600 + 14400 + 600 + 3 * D_bg * 24),
+        'scene_ll_bwd': frames * (D_bg * 4 + O * 16 + (1 + 2 * O) * 4 + O * 16) + 4 * (21600 + 14400 + 600 + 3 * D_bg * 24),
         # z_init, sup, sup_std, eps in; z, z_std, z_dyn, z_dyn_std, logq, trans out; weights once
         'dynloop_fwd': 4 * (batch * O * Z + batch * S * O * (12 + Z) + batch * S * (O * (2 * Z + 2 * (Z - 2)) + 2) + W_DYN),
         'dynloop_bwd': 4 * (batch * S * (O * (Z + 12 + Z + Z) + 2) + batch * S * O * 12 + batch * O * Z + W_DYN),
@@ -863,7 +867,8 @@ def kernel_flops(kernel, batch):
     frames = batch * (T - 1)
     table = {'dynloop_fwd': batch * S * step_fwd, 'dynloop_bwd': batch * S * step_fwd,
              'dynloop_wgrad': batch * S * step_fwd,
-             'scene_fwd': frames * 345e3, 'scene_bwd': frames * 2 * 345e3}      # 345 kFLOP/frame
+             'scene_fwd': frames * 345e3, 'scene_bwd': frames * 2 * 345e3,      # 345 kFLOP/frame
+             'scene_ll_fwd': frames * 345e3, 'scene_ll_bwd': frames * 2 * 345e3}
     return table.get(kernel)
 
 
