@@ -360,6 +360,8 @@ class SceneLL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, obj_tables, bg_tables, pa, pb,
                 align_corners, obj_stream=None, bg_stream=None, bleaf_il_f=None, bleaf_il_b=None):
+        # no zero tensors for the gradients of the three by-product outputs (autograd would fill 11 MB per step)
+        ctx.set_materialize_grads(False)
         img, z = img.contiguous(), z.contiguous()
         N.require_cuda_f32(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin)
         F_, Cc, A, B = img.shape
@@ -1055,6 +1057,7 @@ class ElboAssemble(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, bg, patch, z_all, overlap, logq, trans, skip, beta):
+        ctx.set_materialize_grads(False)          # `stats` is a by-product: no zero gradient for it
         bg, patch, z_all, overlap = bg.contiguous(), patch.contiguous(), z_all.contiguous(), overlap.contiguous()
         logq, trans = logq.contiguous(), trans.contiguous()
         N.require_cuda_f32(bg, patch, z_all, overlap, logq, trans)
@@ -1071,6 +1074,8 @@ class ElboAssemble(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_elbo, _g_stats):
+        if g_elbo is None:
+            return (None,) * 8
         patch, z_all = ctx.saved_tensors
         skip, beta, bg_shape, ov_shape, lq_shape = ctx.meta
         n, Tm1, O, _ = z_all.shape
