@@ -497,7 +497,7 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
             for (int u = ulo; u <= uhi; ++u) {
                 const float tyu = tY[u];
                 const float pre = fmaf(tyu, txv, replay_bg(tt, ts, tXs, o, u, vc));
-                float g = fb[u * a.B + vc].y;
+                float g = vok ? fb[u * a.B + vc].y : 0.f;     // (idle lanes must not read what lane 0 is writing: racecheck)
                 if (!(pre >= 0.f && pre <= 1.f)) g = 0.f;
                 if (vok) fb[u * a.B + vc].y = g;
                 // d paste / d tY[u] = tX[v]; tY[u] = tent(p_u), p_u affine in 1 / sy and ty / sy
@@ -576,6 +576,19 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
     const int64_t f0 = blockIdx.x * per + min((int64_t)blockIdx.x, rem);
     const int cnt = (int)(per + (blockIdx.x < rem ? 1 : 0));
 
+    if (blockIdx.x == gridDim.x - 1) {
+        // columns [N, npad) of the workspaces belong to nobody; the parameter-gradient kernels copy whole 32-column
+        // tiles (and ignore those columns): give them defined values (compute-sanitizer initcheck)
+        for (int64_t n = a.Np + tid; n < a.npad_p; n += blockDim.x) {
+            for (int row = 0; row < Q * 2 * G; ++row) a.gleaf[(int64_t)row * a.npad_p + n] = 0.f;
+            for (int row = 0; row < Q * (2 * G + S); ++row) a.aux_reg[(int64_t)row * a.npad_p + n] = 0.f;
+            for (int row = 0; row < R * (1 + 2 * S); ++row) a.aux_root[(int64_t)row * a.npad_p + n] = 0.f;
+        }
+        for (int64_t n = a.F + tid; n < a.npad_f; n += blockDim.x) {
+            for (int row = 0; row < RB * 2 * GB; ++row) a.bgleaf[(int64_t)row * a.npad_f + n] = 0.f;
+            for (int row = 0; row < RB * (1 + 2 * GB); ++row) a.baux_root[(int64_t)row * a.npad_f + n] = 0.f;
+        }
+    }
     for (int fr0 = 0; fr0 < cnt; fr0 += a.rf) {
         const int nfr = min(a.rf, cnt - fr0);
         const int64_t fbase = f0 + fr0;
