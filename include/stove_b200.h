@@ -177,6 +177,29 @@ int stove_scene_bwd(int64_t F, int O, int C, int A, int B, int pa, int pb, int a
  * stove_scene_ll_supported returns 1 when the configuration fits the fused kernels (C = 1, the D2 / D1
  * structures with 10 Gaussians / 10 sums and 3 x 6, shared memory); otherwise use the unfused calls.
  * ------------------------------------------------------------------------------------ */
+/* Sequence mode of the fused scene likelihood (optional, NULL = plain mode): the kernels read the states of the
+ * scored frames straight from the sequence tensors (Stove.stove_forward, model/video_prediction/stove.py:731-736:
+ * z_sup for 1 <= t < skip, the sampled z for t >= skip, both as [sx, sy/sx, x, y]; frame f = b (T-1) + (t-1)) and
+ * weight the object terms by sx * sy themselves -- no stove_zall_* launches, no (F, O, 4) state tensor, and
+ * stove_elbo_fwd (z_all = NULL) only sums per-frame terms.  In this mode `z`, and in the backward pass g_obj / g_bg /
+ * g_overlap / g_z, are NULL: the backward kernel derives the per-frame weights from the scalar g_elbo (what
+ * stove_elbo_bwd does) and writes the gradients of z_sup (all rows), z_s (all Z components), logq and trans (what
+ * stove_zall_bwd and one gradient add did). */
+typedef struct {
+    int64_t n;                 /* sequences */
+    int32_t T, skip, Z;        /* frames per sequence, first dynamics frame, width of a z_s row (>= 4) */
+    float beta;                /* overlap prior: log Exponential(beta) */
+    const float* z_sup;        /* (n, T, O, 4) */
+    const float* z_s;          /* (n, T - skip, O, Z) */
+    float* patch_w;            /* forward out (F*O): object log-likelihoods weighted by sx * sy (supair.py:79), the
+                                  `patch` input of stove_elbo_fwd with z_all = NULL */
+    const float* g_elbo;       /* backward: d loss / d elbo (device scalar) */
+    float* g_z_sup;            /* backward out (n, T, O, 4) */
+    float* g_z_s;              /* backward out (n, T - skip, O, Z) */
+    float* g_logq;             /* backward out (n, T - skip) */
+    float* g_trans;            /* backward out (n, T - skip) */
+} stove_scene_seq;
+
 /* bleaf_il: lane-interleaved copy of the background leaf table (stove_spn_interleave_leaf) -- blocks of 32 rows laid
  * out [6 float4 parts][32 rows] so that a warp whose lanes own consecutive rows loads it fully coalesced.  Row order
  * of the forward pass: (leaf l, position in bg_scope[l]), leaves il_stride rows apart; of the backward pass:
@@ -193,7 +216,7 @@ int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb, int align
                        const float* bleaf_il, int il_stride,
                        float* patches, float* marg_patch, float* marg_bg, float* overlap,
                        float* leaf_val, float* sum_val, float* out_obj, float* bleaf_val, float* out_bg,
-                       void* stream);
+                       const stove_scene_seq* seq, void* stream);
 
 /* Backward of stove_scene_ll_fwd (csrc/scene_ll_bwd.cu): one chain launch replaces spn2_bwd (node + input pass),
  * spn1_bwd (root + input pass) and stove_scene_bwd -- gradients of the glimpses and masks stay in shared memory --
@@ -213,7 +236,8 @@ int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb, int align
                        const float* bleaf_val, const float* out_bg,
                        const float* g_obj, const float* g_bg, const float* g_overlap,
                        float* g_z, float* g_leaf, float* g_wlog, float* g_rlog, float* g_bleaf, float* g_brlog,
-                       void* ws_obj, void* ws_bg, void* stream, void* join_obj, void* join_bg);
+                       void* ws_obj, void* ws_bg, const stove_scene_seq* seq, void* stream, void* join_obj,
+                       void* join_bg);
 
 /* ------------------------------------------------------------------------------------
  * Sequence glue before the dynamics loop, one launch: Supair.constrain_zp (supair.py:112-149),
@@ -385,6 +409,7 @@ int64_t stove_dynloop_xrec_floats(const stove_gnn_cfg* cfg, int64_t n, int T, in
  *         mean overlap prior (frames t >= skip), mean log q, mean transition lik, mean SuPAIR-frame
  *         likelihood, 0}, elbo_out[1] = the average ELBO again (its own buffer);  backward: g = d loss / d ELBO (one float on the device).
  * ---------------------------------------------------------------------------------- */
+/* stove_elbo_fwd with z_all = NULL: `patch` already carries the sx * sy weight (sequence mode of stove_scene_ll_fwd). */
 int stove_zall_fwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,
                    float* z_all, void* stream);
 int stove_zall_bwd(int64_t n, int T, int skip, int O, int Z, const float* z_sup, const float* z_s,

@@ -25,6 +25,12 @@ class Spn1Struct(C.Structure):
     _fields_ = [('D', i32), ('R', i32), ('G', i32), ('side', vp)]
 
 
+class SceneSeq(C.Structure):                      # stove_scene_seq
+    _fields_ = [('n', i64), ('T', i32), ('skip', i32), ('Z', i32), ('beta', f32),
+                ('z_sup', vp), ('z_s', vp), ('patch_w', vp), ('g_elbo', vp), ('g_z_sup', vp), ('g_z_s', vp),
+                ('g_logq', vp), ('g_trans', vp)]
+
+
 class SupCfg(C.Structure):
     _fields_ = [('T', i32), ('num_obj', i32), ('match_kind', i32), ('app_dim', i32),
                 ('match_appearance', i32), ('fix_supair', i32), ('min_obj_scale', f32),
@@ -100,9 +106,9 @@ SIGNATURES = {
     'stove_scene_bwd': (C.c_int, [i64] + [C.c_int] * 7 + [vp] * 7 + [vp]),
     'stove_scene_ll_supported': (C.c_int, [i64] + [C.c_int] * 6 + [P2, P1]),
     'stove_spn_interleave_leaf': (C.c_int, [vp, vp, i64, vp, vp]),
-    'stove_scene_ll_fwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp, C.c_int] + [vp] * 9 + [vp]),
+    'stove_scene_ll_fwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp, C.c_int] + [vp] * 9 + [C.POINTER(SceneSeq)] + [vp]),
     'stove_scene_ll_bwd': (C.c_int, [i64] + [C.c_int] * 6 + [vp, vp, P2] + [vp] * 5 + [P1] + [vp] * 5 + [vp, C.c_int] + [vp] * 8 + [vp] * 3
-                           + [vp] * 6 + [vp, vp] + [vp, vp, vp]),
+                           + [vp] * 6 + [vp, vp] + [C.POINTER(SceneSeq)] + [vp, vp, vp]),
     'stove_sup_prepare_fwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_sup_prepare_bwd': (C.c_int, [PS, i64] + [vp] * 8 + [vp]),
     'stove_lstm_gemm_cell_fwd': (C.c_int, [i64, C.c_int, i64, vp, vp, vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, i64, i64, i64, vp]),

@@ -482,8 +482,12 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(int64_t n, int T
         const int tp = (int)(f % (T - 1));
         float p = 0.f, ov = 0.f;
         for (int o = 0; o < O; ++o) {
-            const float4 z = reinterpret_cast<const float4*>(z_all)[f * O + o];
-            p += __ldg(patch + f * O + o) * z.x * z.y;
+            float w = 1.f;                        // z_all == NULL: the patch terms are already weighted by sx * sy
+            if (z_all) {
+                const float4 z = reinterpret_cast<const float4*>(z_all)[f * O + o];
+                w = z.x * z.y;
+            }
+            p += __ldg(patch + f * O + o) * w;
             ov += logb - beta * __ldg(overlap + f * O + o);
         }
         const float b = __ldg(bg + f);
@@ -555,7 +559,7 @@ __global__ void elbo_bwd_kernel(int64_t n, int T, int skip, int O, float beta, c
 extern "C" int stove_elbo_fwd(int64_t n, int T, int skip, int O, float beta, const float* bg, const float* patch,
                               const float* z_all, const float* overlap, const float* logq, const float* trans,
                               float* stats, float* elbo_out, void* stream) {
-    STOVE_CHECK_ARG(n > 0 && T > skip && skip >= 1 && O > 0 && bg && patch && z_all && overlap && logq && trans && stats && elbo_out,
+    STOVE_CHECK_ARG(n > 0 && T > skip && skip >= 1 && O > 0 && bg && patch && overlap && logq && trans && stats && elbo_out,
                     "bad argument");
     STOVE_KERNEL(K_ELBO_FWD, (cudaStream_t)stream, elbo_fwd_kernel<<<1, ELBO_THREADS, 0, (cudaStream_t)stream>>>(
         n, T, skip, O, beta, bg, patch, z_all, overlap, logq, trans, stats, elbo_out));

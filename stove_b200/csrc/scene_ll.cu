@@ -96,7 +96,7 @@ __device__ void scene_frame_fwd(const LLArgs& a, int64_t f, int pl0, float2* fb,
     const int du = 32 / a.B, dv = 32 - du * a.B;
     __syncwarp();
     for (int o = 0; o < a.O; ++o) {
-        const float4 zz = __ldg(reinterpret_cast<const float4*>(a.z) + f * a.O + o);
+        const float4 zz = load_z(a, f, o);
         const float sx = zz.x, sy = zz.y, tx = zz.z, ty = zz.w;
         const float mx = sx * kB, ox = fmaf(tx, kB, oB), my = sy * kA, oy = fmaf(ty, kA, oA);
         const int pl = pl0 + o, tile = pl / HT, pt = pl - tile * HT;
@@ -502,7 +502,13 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_fwd_kernel(const __gri
             for (int r = 1; r < R; ++r) M = fmaxf(M, vr[r * HT]);
             float acc = 0.f;
             for (int r = 0; r < R; ++r) acc += expf(vr[r * HT] - M);
-            a.out_obj[nbase + i] = (M > -INFINITY) ? M + logf(acc) : M;
+            const float val = (M > -INFINITY) ? M + logf(acc) : M;
+            a.out_obj[nbase + i] = val;
+            if (a.seq) {             // the term of the ELBO: weighted by sx * sy (supair.py:79)
+                const int64_t f = (nbase + i) / a.O;
+                const float4 z = load_z(a, f, (int)(nbase + i - f * a.O));
+                a.sq.patch_w[nbase + i] = val * z.x * z.y;
+            }
         }
         __syncthreads();               // the next round overwrites the tables with frames
     }
@@ -591,8 +597,17 @@ extern "C" int stove_scene_ll_fwd(int64_t F, int O, int A, int B, int pa, int pb
                                   const float* bleaf, const float* brlin, const float* brlog, const float* bleaf_il,
                                   int il_stride, float* patches,
                                   float* marg_patch, float* marg_bg, float* overlap, float* leaf_val, float* sum_val,
-                                  float* out_obj, float* bleaf_val, float* out_bg, void* stream) {
+                                  float* out_obj, float* bleaf_val, float* out_bg, const stove_scene_seq* seq,
+                                  void* stream) {
     sl::LLArgs a{};
+    if (seq) {
+        STOVE_CHECK_ARG(!z && seq->n > 0 && seq->T > seq->skip && seq->skip >= 1 && seq->Z >= 4 && seq->z_sup && seq->z_s &&
+                            seq->patch_w, "bad sequence block");
+        STOVE_CHECK_ARG(F == seq->n * (seq->T - 1) && F * O < (1ll << 31), "F must be n * (T - 1) in sequence mode");
+        a.seq = 1;
+        a.sq = *seq;
+        z = seq->z_sup;              // (only checked for null / alignment below)
+    }
     int rc = sl_fill(a, F, O, A, B, pa, pb, align_corners, img, z, obj, bg, bg_scope, bg_cnt);
     if (rc) return rc;
     STOVE_CHECK_ARG(leaf && wlin && wlog && rlin && rlog && bleaf && brlin && brlog && patches && marg_patch && marg_bg &&

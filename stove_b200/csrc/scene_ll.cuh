@@ -38,6 +38,10 @@ struct LLArgs {
     int il_stride;
     float *bleaf_val, *out_bg;
     int64_t npad_f;
+    // sequence mode (stove_scene_seq): states read from the sequence tensors, ELBO assembled in the kernel
+    int seq;
+    stove_scene_seq sq;
+    float w_elbo, w_sup;         // 1 / (n S), 1 / (n (skip - 1)) (host-computed)
     // backward only
     const float *g_obj, *g_bg, *g_overlap;
     float* g_z;
@@ -118,6 +122,26 @@ __device__ __forceinline__ float base_coord_r(int k, float rn, int align) {
     return align ? 2.f * (float)k * rn - 1.f : (2.f * (float)k + 1.f) * rn - 1.f;
 }
 __device__ __forceinline__ float recip_n(int n, int align) { return align ? (n > 1 ? 1.f / (float)(n - 1) : 0.f) : 1.f / (float)n; }
+
+// state (sx, sy, x, y) of object o of scored frame f; *q receives sy / sx in sequence mode
+// (frame and sequence counts fit 32 bits: 64-bit divisions cost ~100 instructions each)
+__device__ __forceinline__ float4 load_z(const LLArgs& a, int64_t f, int o, float* q = nullptr) {
+    if (!a.seq) return __ldg(reinterpret_cast<const float4*>(a.z) + f * a.O + o);
+    const unsigned Tm1 = (unsigned)a.sq.T - 1u, fu = (unsigned)f;
+    const unsigned b = fu / Tm1;
+    const int t = (int)(fu - b * Tm1) + 1;
+    const float* src = t < a.sq.skip ? a.sq.z_sup + ((size_t)(b * (unsigned)a.sq.T + t) * a.O + o) * 4
+                                     : a.sq.z_s + ((size_t)(b * (unsigned)(a.sq.T - a.sq.skip) + (t - a.sq.skip)) * a.O + o) * a.sq.Z;
+    const float sx = __ldg(src), qq = __ldg(src + 1);
+    if (q) *q = qq;
+    return make_float4(sx, sx * qq, __ldg(src + 2), __ldg(src + 3));
+}
+// sequence mode: d loss / d (likelihood of frame f) = g / (n S) for t >= skip, g / (n (skip - 1)) before (stove.py:747-748)
+__device__ __forceinline__ float frame_weight(const LLArgs& a, int64_t f) {
+    const unsigned Tm1 = (unsigned)a.sq.T - 1u, fu = (unsigned)f;
+    const int tp = (int)(fu % Tm1), nsup = a.sq.skip - 1;
+    return __ldg(a.sq.g_elbo) * (tp >= nsup ? a.w_elbo : a.w_sup);
+}
 
 // tents of the paste of object (sx, sy, tx, ty) and the rows [ulo, uhi] they touch (value or derivative non-zero)
 __device__ __forceinline__ void warp_tents(const LLArgs& a, float sx, float sy, float tx, float ty, float* tX,

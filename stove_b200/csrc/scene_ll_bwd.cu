@@ -70,7 +70,18 @@ __device__ void bwd_root_task(const LLArgs& a, const SmemB& m, float* smem, int 
     }
     const float U0 = __shfl_sync(0xffffffffu, U, pt);          // both halves use the value of the h = 0 lane
     const bool fast = U0 > LIN_SUM_FLOOR;
-    const float go = live ? a.g_obj[n] : 0.f, ov = live ? a.out_obj[n] : 0.f;
+    float go = 0.f;
+    if (live) {
+        if (a.seq) {             // d loss / d (raw object log-likelihood) = frame weight * sx * sy (supair.py:79)
+            const unsigned fu = (unsigned)n / (unsigned)a.O;
+            const int64_t f = fu;
+            const float4 z = load_z(a, f, (int)((unsigned)n - fu * (unsigned)a.O));
+            go = frame_weight(a, f) * z.x * z.y;
+        } else {
+            go = a.g_obj[n];
+        }
+    }
+    const float ov = live ? a.out_obj[n] : 0.f;
     float c = 0.f;
     if (fast) c = go * expf(mO + mT + logf(U0) - ov) / U0;
     float* gs = smem + m.t + ((size_t)tile * Q * S + qo * S) * HT + pt;
@@ -314,7 +325,7 @@ __device__ void bwd_bg_root_frame(const LLArgs& a, const SmemB& m, float* smem, 
     float U = eB * rowB;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) U += __shfl_xor_sync(0xffffffffu, U, o);
-    const float go = a.g_bg[f], ov = a.out_bg[f];
+    const float go = a.seq ? frame_weight(a, f) : a.g_bg[f], ov = a.out_bg[f];
     const bool fast = U > LIN_SUM_FLOOR;
     float c = 0.f;
     if (fast) c = go * expf(mA + mB + logf(U) - ov) / U;
@@ -453,9 +464,8 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
     float2* fb = reinterpret_cast<float2*>(smem + m.fb) + (size_t)fi * a.fs;       // (x, gradient w.r.t. the background mask)
     float* tt = smem + m.v + (size_t)fi * a.O * ts;
     int32_t* rng = reinterpret_cast<int32_t*>(smem + m.rng) + fi * a.O * 2;
-    const float4* zf = reinterpret_cast<const float4*>(a.z) + f * a.O;
     for (int o = 0; o < a.O; ++o) {
-        const float4 zz = __ldg(zf + o);
+        const float4 zz = load_z(a, f, o);
         float* t = tt + o * ts;
         int ulo, uhi;
         warp_tents(a, zz.x, zz.y, zz.z, zz.w, t, t + 2 * tXs, t + tXs, t + 2 * tXs + tYs, lane, ulo, uhi);
@@ -479,7 +489,8 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
     const float2* xw = reinterpret_cast<const float2*>(smem + m.t);
     __syncwarp();
     for (int o = a.O - 1; o >= 0; --o) {
-        const float4 zz = __ldg(zf + o);
+        float zq = 0.f;                                           // sy / sx (sequence mode)
+        const float4 zz = load_z(a, f, o, &zq);
         const float sx = zz.x, sy = zz.y, tx = zz.z, ty = zz.w;
         const float isx = 1.f / sx, isy = 1.f / sy;
         const float* t = tt + o * ts;
@@ -512,7 +523,8 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
         }
         __syncwarp();
         // (2) the sample points of the glimpse and of the mask
-        const float gov = a.g_overlap ? __ldg(a.g_overlap + f * a.O + o) * rPP : 0.f;
+        const float fw = a.seq ? frame_weight(a, f) : 0.f;
+        const float gov = a.seq ? -a.sq.beta * fw * rPP : (a.g_overlap ? __ldg(a.g_overlap + f * a.O + o) * rPP : 0.f);
         const int pl = fi * a.O + o, tile = pl / HT, pt = pl - tile * HT;
         const float2* xt = xw + (size_t)tile * D * HT;
         const float mx = sx * kB, ox = fmaf(tx, kB, oB), my = sy * kA, oy = fmaf(ty, kA, oA);
@@ -557,7 +569,29 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
             }
         }
         gsx = warp_sum(gsx); gsy = warp_sum(gsy); gtx = warp_sum(gtx); gty = warp_sum(gty);
-        if (lane == 0) reinterpret_cast<float4*>(a.g_z)[f * a.O + o] = make_float4(gsx, gsy, gtx, gty);
+        if (!a.seq) {
+            if (lane == 0) reinterpret_cast<float4*>(a.g_z)[f * a.O + o] = make_float4(gsx, gsy, gtx, gty);
+        } else {
+            // + the sx * sy weighting of the object term, then (sx, sy) -> (sx, q = sy / sx) and straight into the
+            // gradients of the sequence tensors (what stove_elbo_bwd + stove_zall_bwd + one add used to do)
+            const float lo = a.out_obj[f * a.O + o];
+            gsx = fmaf(fw * lo, sy, gsx);
+            gsy = fmaf(fw * lo, sx, gsy);
+            const float g0 = fmaf(gsy, zq, gsx), g1 = gsy * sx;
+            const int T = a.sq.T, S_ = T - a.sq.skip;
+            const unsigned bu = (unsigned)f / (unsigned)(T - 1);
+            const int64_t b = bu;
+            const int t = (int)((unsigned)f - bu * (unsigned)(T - 1)) + 1;
+            float4* gsup = reinterpret_cast<float4*>(a.sq.g_z_sup);
+            if (lane == 0) {
+                gsup[(b * T + t) * a.O + o] = t < a.sq.skip ? make_float4(g0, g1, gtx, gty) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t == 1) gsup[(b * T) * a.O + o] = make_float4(0.f, 0.f, 0.f, 0.f);       // frame 0 is not scored
+            }
+            if (t >= a.sq.skip) {
+                float* dst = a.sq.g_z_s + ((b * S_ + (t - a.sq.skip)) * a.O + o) * a.sq.Z;
+                for (int k = lane; k < a.sq.Z; k += 32) dst[k] = k == 0 ? g0 : k == 1 ? g1 : k == 2 ? gtx : k == 3 ? gty : 0.f;
+            }
+        }
         __syncwarp();
     }
 }
@@ -576,6 +610,15 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
     const int64_t f0 = blockIdx.x * per + min((int64_t)blockIdx.x, rem);
     const int cnt = (int)(per + (blockIdx.x < rem ? 1 : 0));
 
+    if (a.seq) {
+        // d elbo / d log q = -1 / (n S), d elbo / d trans = +1 / (n S)   (stove.py:747)
+        const int64_t nS = a.sq.n * (a.sq.T - a.sq.skip);
+        const float we = __ldg(a.sq.g_elbo) * a.w_elbo;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < nS; i += (int64_t)gridDim.x * blockDim.x) {
+            a.sq.g_logq[i] = -we;
+            a.sq.g_trans[i] = we;
+        }
+    }
     if (blockIdx.x == gridDim.x - 1) {
         // columns [N, npad) of the workspaces belong to nobody; the parameter-gradient kernels copy whole 32-column
         // tiles (and ignore those columns): give them defined values (compute-sanitizer initcheck)
@@ -731,15 +774,29 @@ extern "C" int stove_scene_ll_bwd(int64_t F, int O, int A, int B, int pa, int pb
                                   const float* sum_val, const float* out_obj, const float* bleaf_val,
                                   const float* out_bg, const float* g_obj, const float* g_bg, const float* g_overlap,
                                   float* g_z, float* g_leaf, float* g_wlog, float* g_rlog, float* g_bleaf,
-                                  float* g_brlog, void* ws_obj, void* ws_bg, void* stream, void* join_obj,
-                                  void* join_bg) {
+                                  float* g_brlog, void* ws_obj, void* ws_bg, const stove_scene_seq* seq, void* stream,
+                                  void* join_obj, void* join_bg) {
     sl::LLArgs a{};
     STOVE_CHECK_ARG(obj && bg, "null structure");
-    STOVE_CHECK_ARG(F >= 0 && O > 0 && A > 0 && B > 0 && pa > 0 && pb > 0 && img && z && bg_scope && bg_cnt, "bad argument");
+    if (seq) {
+        STOVE_CHECK_ARG(!z && !g_obj && !g_bg && !g_overlap && !g_z, "sequence mode: z and the per-term gradients must be NULL");
+        STOVE_CHECK_ARG(seq->n > 0 && seq->T > seq->skip && seq->skip >= 1 && seq->Z >= 4 && seq->z_sup && seq->z_s && seq->g_elbo &&
+                            seq->g_z_sup && seq->g_z_s && seq->g_logq && seq->g_trans && F == seq->n * (seq->T - 1),
+                        "bad sequence block");
+        STOVE_CHECK_ARG(((uintptr_t)seq->g_z_sup & 15) == 0, "g_z_sup must be 16-byte aligned");
+        STOVE_CHECK_ARG(F * O < (1ll << 31), "too many patches for the sequence mode");
+        a.seq = 1;
+        a.sq = *seq;
+        a.w_elbo = (float)(1.0 / ((double)seq->n * (seq->T - seq->skip)));
+        a.w_sup = seq->skip > 1 ? (float)(1.0 / ((double)seq->n * (seq->skip - 1))) : 0.f;
+    } else {
+        STOVE_CHECK_ARG(z && g_obj && g_bg && g_z, "null pointer");
+        STOVE_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)g_z & 15) == 0, "z / g_z must be 16-byte aligned");
+    }
+    STOVE_CHECK_ARG(F >= 0 && O > 0 && A > 0 && B > 0 && pa > 0 && pb > 0 && img && bg_scope && bg_cnt, "bad argument");
     STOVE_CHECK_ARG(leaf && wlin && wlog && rlin && rlog && bleaf && brlin && brlog && patches && marg_patch && marg_bg &&
-                        leaf_val && sum_val && out_obj && bleaf_val && out_bg && g_obj && g_bg && g_z && g_leaf &&
+                        leaf_val && sum_val && out_obj && bleaf_val && out_bg && g_leaf &&
                         g_wlog && g_rlog && g_bleaf && g_brlog && ws_obj && ws_bg, "null pointer");
-    STOVE_CHECK_ARG(((uintptr_t)z & 15) == 0 && ((uintptr_t)g_z & 15) == 0, "z / g_z must be 16-byte aligned");
     STOVE_CHECK_ARG(bleaf_il && il_stride > 0 && (il_stride & 31) == 0 && ((uintptr_t)bleaf_il & 15) == 0, "bad interleaved table");
     if (F == 0) return STOVE_OK;
     a.bleaf_il = bleaf_il; a.il_stride = il_stride;

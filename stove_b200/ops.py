@@ -336,6 +336,19 @@ def set_scene_ll(enabled):
     return prev
 
 
+_SCENE_SEQ = True             # False: Stove.stove_forward goes ZAll -> SceneLL -> ElboAssemble instead of SceneElbo
+
+
+def set_scene_seq(enabled):
+    global _SCENE_SEQ
+    prev, _SCENE_SEQ = _SCENE_SEQ, bool(enabled)
+    return prev
+
+
+def scene_seq_enabled():
+    return _SCENE_SEQ and _SCENE_LL and _SCENE_LL_BWD
+
+
 def set_scene_ll_bwd(enabled):
     global _SCENE_LL_BWD
     prev, _SCENE_LL_BWD = _SCENE_LL_BWD, bool(enabled)
@@ -386,7 +399,7 @@ class SceneLL(torch.autograd.Function):
             C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
             N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog), N.ptr(bleaf_il_f), bg_tables.il_stride_f,
             N.ptr(patches), N.ptr(marg_patch), N.ptr(marg_bg), N.ptr(overlap),
-            N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val), N.ptr(out_bg), N.stream()))
+            N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val), N.ptr(out_bg), None, N.stream()))
         ctx.save_for_backward(img, z, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch, marg_bg,
                               leaf_val, sum_val, out_obj, bleaf_val, out_bg)
         ctx.tables = (obj_tables, bg_tables)
@@ -428,7 +441,7 @@ class SceneLL(torch.autograd.Function):
                 N.ptr(x2), N.ptr(m2), N.ptr(mb), N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val),
                 N.ptr(out_bg), N.ptr(g_obj), N.ptr(g_bg), N.ptr(g_overlap),
                 N.ptr(g_z), N.ptr(g_leaf), N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(g_bleaf), N.ptr(g_brlog),
-                N.ptr(ws2), N.ptr(ws1), N.stream(), _join_handle(obj_stream), _join_handle(bg_stream)))
+                N.ptr(ws2), N.ptr(ws1), None, N.stream(), _join_handle(obj_stream), _join_handle(bg_stream)))
             _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
             _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
             return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
@@ -449,6 +462,104 @@ class SceneLL(torch.autograd.Function):
         _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
         return (None, g_z, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None, None, None, None, None, None,
                 None, None, None, None)
+
+
+class SceneElbo(torch.autograd.Function):
+    """The sequence ELBO's likelihood half (sequence mode of csrc/scene_ll*.cu + stove_elbo_fwd): the fused kernels read
+    the states from z_sup / z_s and weight the object terms themselves; the backward kernel derives the per-frame
+    weights from d loss / d elbo and writes the gradients of z_sup, z_s, log q and the transition likelihood -- what
+    ZAll -> SceneLL -> ElboAssemble do with three launches forward and five on the backward chain (+ 2 fills, 1 add).
+    img (n*(T-1), 1, A, B) = x[:, 1:]; z_sup (n, T, O, 4), z_s (n, S, O, Z) as [sx, sy/sx, x, y, ...]; logq, trans (n, S).
+    Returns (elbo (), stats (8,), bg (F,), obj (F*O,) raw, overlap (F, O), patches, marg_patch, marg_bg); everything
+    but the ELBO is a by-product (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, img, z_sup, z_s, logq, trans, skip, beta, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin,
+                obj_tables, bg_tables, pa, pb, align_corners, obj_stream, bg_stream, bleaf_il_f, bleaf_il_b):
+        ctx.set_materialize_grads(False)
+        img, z_sup, z_s, logq, trans = (t.contiguous() for t in (img, z_sup, z_s, logq, trans))
+        N.require_cuda_f32(img, z_sup, z_s, logq, trans, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin)
+        F_, Cc, A, B = img.shape
+        n, T, O, _ = z_sup.shape
+        Z = z_s.shape[-1]
+        if F_ != n * (T - 1) or z_s.shape[1] != T - skip:
+            raise ValueError('SceneElbo: frames must be x[:, 1:] of the sequences of z_sup / z_s')
+        st2, st1 = obj_tables.cstruct, bg_tables.cstruct
+        dev, dt = img.device, img.dtype
+        npt = F_ * O
+        npad, npad_f = _npad(max(npt, 1)), _npad(max(F_, 1))
+        Q, G, S = 2 * st2.R, st2.G, st2.S
+        patches = torch.empty(npt, Cc, pa, pb, device=dev, dtype=dt)
+        marg_patch = torch.empty_like(patches)
+        marg_bg = torch.empty(F_, Cc, A, B, device=dev, dtype=dt)
+        overlap = torch.empty(F_, O, device=dev, dtype=dt)
+        leaf_val = torch.empty(Q * 2 * G, npad, device=dev, dtype=dt)
+        sum_val = torch.empty(Q * S, npad, device=dev, dtype=dt)
+        out_obj = torch.empty(npt, device=dev, dtype=dt)
+        bleaf_val = torch.empty(st1.R * 2 * st1.G, npad_f, device=dev, dtype=dt)
+        out_bg = torch.empty(F_, device=dev, dtype=dt)
+        patch_w = torch.empty(npt, device=dev, dtype=dt)
+        stats = torch.empty(8, device=dev, dtype=dt)
+        elbo = torch.empty((), device=dev, dtype=dt)
+        seq = N.SceneSeq(n, T, skip, Z, float(beta), N.ptr(z_sup), N.ptr(z_s), N.ptr(patch_w), None, None, None, None, None)
+        N.check(N.lib().stove_scene_ll_fwd(
+            F_, O, A, B, pa, pb, int(align_corners), N.ptr(img), None,
+            C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
+            C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
+            N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog), N.ptr(bleaf_il_f), bg_tables.il_stride_f,
+            N.ptr(patches), N.ptr(marg_patch), N.ptr(marg_bg), N.ptr(overlap),
+            N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val), N.ptr(out_bg), C.byref(seq), N.stream()))
+        N.check(N.lib().stove_elbo_fwd(n, T, skip, O, float(beta), N.ptr(out_bg), N.ptr(patch_w), None, N.ptr(overlap),
+                                       N.ptr(logq), N.ptr(trans), N.ptr(stats), N.ptr(elbo), N.stream()))
+        ctx.save_for_backward(img, z_sup, z_s, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch,
+                              marg_bg, leaf_val, sum_val, out_obj, bleaf_val, out_bg)
+        ctx.tables = (obj_tables, bg_tables)
+        ctx.meta = (F_, O, Cc, A, B, pa, pb, int(align_corners), n, T, skip, Z, float(beta), tuple(logq.shape))
+        ctx.streams = (obj_stream, bg_stream)
+        ctx.bleaf_il_b = bleaf_il_b
+        ctx.mark_non_differentiable(stats, out_bg, out_obj, overlap, patches, marg_patch, marg_bg)
+        return elbo, stats, out_bg, out_obj, overlap, patches, marg_patch, marg_bg
+
+    @staticmethod
+    def backward(ctx, g_elbo, *_unused):
+        (img, z_sup, z_s, leaf, wlog, wlin, rlog, rlin, bleaf, brlog, brlin, patches, marg_patch, marg_bg, leaf_val,
+         sum_val, out_obj, bleaf_val, out_bg) = ctx.saved_tensors
+        if g_elbo is None:
+            return (None,) * 24
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('stove_b200: gradient w.r.t. the frames is not implemented '
+                                      '(frames are data on the STOVE hot path)')
+        obj_tables, bg_tables = ctx.tables
+        st2, st1 = obj_tables.cstruct, bg_tables.cstruct
+        F_, O, Cc, A, B, pa, pb, ac, n, T, skip, Z, beta, lq_shape = ctx.meta
+        obj_stream, bg_stream = ctx.streams
+        npt = F_ * O
+        dev = img.device
+        g_elbo = g_elbo.contiguous()
+        g_leaf, g_wlog, g_rlog, g_bleaf, g_brlog = _zeros_views(leaf, leaf.shape, wlog.shape, rlog.shape, bleaf.shape,
+                                                               brlog.shape)
+        g_z_sup, g_z_s = torch.empty_like(z_sup), torch.empty_like(z_s)
+        g_lq = torch.empty(lq_shape, device=dev, dtype=img.dtype)
+        g_tr = torch.empty(lq_shape, device=dev, dtype=img.dtype)
+        x2, m2 = patches.view(npt, -1), marg_patch.view(npt, -1)
+        xb, mb = img.view(F_, -1), marg_bg.view(F_, -1)
+        ws2 = torch.empty(max(N.lib().stove_spn2_bwd_workspace(C.byref(st2), npt), 4) // 4, device=dev, dtype=torch.float32)
+        ws1 = torch.empty(max(N.lib().stove_spn1_bwd_workspace(C.byref(st1), F_), 4) // 4, device=dev, dtype=torch.float32)
+        seq = N.SceneSeq(n, T, skip, Z, beta, N.ptr(z_sup), N.ptr(z_s), None, N.ptr(g_elbo), N.ptr(g_z_sup), N.ptr(g_z_s),
+                         N.ptr(g_lq), N.ptr(g_tr))
+        N.check(N.lib().stove_scene_ll_bwd(
+            F_, O, A, B, pa, pb, ac, N.ptr(img), None,
+            C.byref(st2), N.ptr(leaf), N.ptr(wlin), N.ptr(wlog), N.ptr(rlin), N.ptr(rlog),
+            C.byref(st1), N.ptr(bg_tables.dev['bg_scope']), N.ptr(bg_tables.dev['bg_cnt']),
+            N.ptr(bleaf), N.ptr(brlin), N.ptr(brlog), N.ptr(ctx.bleaf_il_b), bg_tables.il_stride_b,
+            N.ptr(x2), N.ptr(m2), N.ptr(mb), N.ptr(leaf_val), N.ptr(sum_val), N.ptr(out_obj), N.ptr(bleaf_val),
+            N.ptr(out_bg), None, None, None,
+            None, N.ptr(g_leaf), N.ptr(g_wlog), N.ptr(g_rlog), N.ptr(g_bleaf), N.ptr(g_brlog),
+            N.ptr(ws2), N.ptr(ws1), C.byref(seq), N.stream(), _join_handle(obj_stream), _join_handle(bg_stream)))
+        _keep_for(obj_stream, x2, m2, leaf, wlin, rlin, ws2, g_leaf, g_wlog, g_rlog)
+        _keep_for(bg_stream, xb, mb, bleaf, brlin, ws1, g_bleaf, g_brlog)
+        return (None, g_z_sup, g_z_s, g_lq, g_tr, None, None, g_leaf, g_wlog, None, g_rlog, None, g_bleaf, g_brlog, None,
+                None, None, None, None, None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------

@@ -290,11 +290,17 @@ class Stove(nn.Module):
         # p(x_t | z_t) for t >= skip and p(x_t | z_sup_t) for 1 <= t < skip (stove.py:731-736) share one
         # pass over the frames x[:, 1:]: a single glimpse/mask launch and one launch family per SPN;
         # the per-frame terms are reduced to the ELBO by one kernel (csrc/glue.cu)
-        z_all = ops.ZAll.apply(z_sup, z_s, skip)                                    # (n, T-1, O, 4) [sx, sy, x, y]
-        bg, patch_raw, overlap, extra = self.sup.likelihood_raw(x_scored,
-                                                                z_all.flatten(end_dim=1), packed=packed_spn)
-        average_elbo, stats = ops.ElboAssemble.apply(bg, patch_raw, z_all, overlap, log_z_n, trans_n, skip,
-                                                     float(c.overlap_beta))
+        fused = self.sup.sequence_elbo(x_scored, z_sup, z_s, log_z_n, trans_n, skip, packed_spn)
+        if fused is not None:
+            # one launch each way: states read from z_sup / z_s, ELBO assembled by the kernel (ops.SceneElbo)
+            average_elbo, stats, bg, patch_raw, overlap, extra = fused
+            z_all = None
+        else:
+            z_all = ops.ZAll.apply(z_sup, z_s, skip)                                # (n, T-1, O, 4) [sx, sy, x, y]
+            bg, patch_raw, overlap, extra = self.sup.likelihood_raw(x_scored,
+                                                                    z_all.flatten(end_dim=1), packed=packed_spn)
+            average_elbo, stats = ops.ElboAssemble.apply(bg, patch_raw, z_all, overlap, log_z_n, trans_n, skip,
+                                                         float(c.overlap_beta))
         logging = (self.step_counter % c.print_every == 0) or (self.step_counter % c.plot_every == 0)
         if logging and c.debug:
             p = self.prop_dict
@@ -302,6 +308,8 @@ class Stove(nn.Module):
             if c.debug_extend_plots:
                 n_sup = skip - 1
                 with torch.no_grad():
+                    if z_all is None:
+                        z_all = ops.ZAll.apply(z_sup.detach(), z_s.detach(), skip)
                     za = z_all.flatten(end_dim=1)
                     pl = (patch_raw.view(-1, O) * za[..., 0] * za[..., 1]).sum(1)
                 p['overlap_ratios'] = extra['overlap_ratios'].detach()

@@ -124,6 +124,24 @@ class Supair(nn.Module):
                      marginalise_bg=marg_bg)
         return bg_loglik, patches_loglik, overlap, extra
 
+    def sequence_elbo(self, x_img, z_sup, z_s, logq, trans, skip, packed):
+        """The likelihood half of the sequence ELBO (stove.py:731-748) in one launch each way (ops.SceneElbo), or
+        None when the configuration has no fused kernel.  Returns (elbo, stats, bg, raw object ll, overlap, extra)."""
+        c = self.c
+        pk_obj, pk_bg = packed
+        if not ops.scene_seq_enabled() or pk_obj is None or pk_bg is None or pk_bg.leaf_il_f is None or not ops.scene_ll_supported(
+                x_img, z_s[:, 0], c.patch_width, c.patch_height, pk_obj.tables, pk_bg.tables):
+            return None
+        cur = torch.cuda.current_stream(x_img.device)
+        streams = [None if p.stream is None or p.stream == cur else p.stream for p in (pk_obj, pk_bg)]
+        elbo, stats, bg, obj, overlap, patches, marg_patch, marg_bg = ops.SceneElbo.apply(
+            x_img, z_sup, z_s, logq, trans, skip, float(c.overlap_beta), pk_obj.leaf, pk_obj.wlog, pk_obj.wlin,
+            pk_obj.rlog, pk_obj.rlin, pk_bg.leaf, pk_bg.rlog, pk_bg.rlin, pk_obj.tables, pk_bg.tables,
+            c.patch_width, c.patch_height, self._align(), streams[0], streams[1], pk_bg.leaf_il_f, pk_bg.leaf_il_b)
+        extra = dict(overlap_ratios=overlap, patches=patches, marginalise_flat=marg_patch.flatten(start_dim=1),
+                     marginalise_bg=marg_bg)
+        return elbo, stats, bg, obj, overlap, extra
+
     def likelihood_parts(self, x_img, z_img, packed=None):
         """Per-frame (bg, patch, overlap) log-likelihood terms of supair.py:84-110 plus the
         intermediate tensors."""

@@ -110,3 +110,60 @@ def test_unsupported_configurations_take_the_unfused_kernels():
     z = torch.rand(4, 3, 4, device='cuda')
     assert not ops.scene_ll_supported(img3, z, 10, 10, t2, t1)
     assert ops.scene_ll_supported(img3[:, :1].contiguous(), z, 10, 10, t2, t1)
+
+
+@pytest.mark.parametrize('kw,n,T', [({}, 5, 8), ({}, 256, 8), (dict(num_obj=6, width=50, height=50, max_obj_scale=0.22,
+                                                                       debug_match_objects='greedy'), 9, 5)])
+def test_sequence_elbo_vs_composition(kw, n, T):
+    """ops.SceneElbo (states read from z_sup / z_s, ELBO assembled in the kernel: one launch each way) against
+    ZAll -> Scene -> Spn2 / Spn1 -> ElboAssemble (stove.py:731-748) on the same inputs: ELBO, the logging statistics
+    and the gradients of z_sup, z_s, log q, the transition likelihood and every SPN parameter."""
+    from stove_b200 import ops
+    oc, sd, model = make_model(kw, 33)
+    O, skip, Z = oc.num_obj, 2, oc.cl // 2 + 2
+    S = T - skip
+    img, z, _ = _inputs(oc, n * (T - 1), 8)
+    gen = torch.Generator().manual_seed(9)
+    zq = z.clone().view(n, T - 1, O, 4)
+    zq[..., 1] = zq[..., 1] / zq[..., 0]                       # [sx, sy, x, y] -> [sx, sy / sx, x, y]
+    z_sup = torch.cat([torch.rand(n, 1, O, 4, generator=gen, dtype=torch.float64) * 0.5 + 0.1, zq], 1)
+    z_sup[:, skip:] = torch.rand(n, S, O, 4, generator=gen, dtype=torch.float64) * 0.5 + 0.1      # unused rows
+    z_s = torch.cat([zq[:, skip - 1:], torch.randn(n, S, O, Z - 4, generator=gen, dtype=torch.float64)], -1)
+    logq = torch.randn(n, S, generator=gen, dtype=torch.float64) * 3
+    trans = torch.randn(n, S, generator=gen, dtype=torch.float64) * 3
+    x_img = img.float().cuda()
+    packed_done = []
+
+    def run(fused):
+        model.zero_grad()
+        leaves = [t.float().cuda().requires_grad_(True) for t in (z_sup, z_s, logq, trans)]
+        zs_, zz_, lq_, tr_ = leaves
+        packed = model.sup.pack()
+        packed_done.append(packed)
+        if fused:
+            out = model.sup.sequence_elbo(x_img, zs_, zz_, lq_, tr_, skip, packed)
+            assert out is not None, 'fused sequence path not taken'
+            elbo, stats = out[0], out[1]
+        else:
+            prev = ops.set_scene_ll(False)
+            try:
+                z_all = ops.ZAll.apply(zs_, zz_, skip)
+                bg, obj, ov, _ = model.sup.likelihood_raw(x_img, z_all.flatten(end_dim=1), packed=packed)
+                elbo, stats = ops.ElboAssemble.apply(bg, obj, z_all, ov, lq_, tr_, skip, float(oc.overlap_beta))
+            finally:
+                ops.set_scene_ll(prev)
+        (-elbo).backward()
+        torch.cuda.synchronize()
+        grads = {k: p.grad.clone() for k, p in model.sup.named_parameters() if p.grad is not None}
+        return elbo.detach(), stats.detach(), [t.grad.clone() for t in leaves], grads
+
+    ea, sa, ga, pa_ = run(True)
+    eb, sb, gb, pb_ = run(False)
+    ck = Checker('scene_elbo_vs_composition_%s_%d' % ('_'.join(kw), n))
+    ck.close('elbo', ea, eb, 2e-6)
+    ck.close('stats', sa[:7], sb[:7], 2e-6)
+    for name, a, b in zip(('g_z_sup', 'g_z_s', 'g_logq', 'g_trans'), ga, gb):
+        ck.mostly_close(name, a, b, 2e-4)
+    for k in pb_:
+        ck.close('g.' + k, pa_[k], pb_[k], 2e-4)
+    ck.finish()
