@@ -507,13 +507,19 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(int64_t n, int T
         if (lane == 0) red[q][wp] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot[6];
+    // second stage by the first warp as a shuffle tree (a serial loop of 6 x 32 double additions in one thread
+    // was half of this kernel's 6 us: fp64 latency); the order is fixed, the result deterministic
+    double tot[6];
+    if (wp == 0) {
+#pragma unroll
         for (int q = 0; q < 6; ++q) {
-            double v = 0.;
-            for (int w = 0; w < ELBO_THREADS / 32; ++w) v += red[q][w];
+            double v = red[q][lane];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
             tot[q] = v;
         }
+    }
+    if (threadIdx.x == 0) {
         const double ne = (double)n * S, ns = (double)n * nsup;
         const double lik_sup = nsup > 0 ? tot[3] / ns : 0.;
         stats[0] = (float)((tot[0] + tot[1] + tot[2] + tot[5] - tot[4]) / ne + lik_sup);
