@@ -122,7 +122,8 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
     float L[G], e[G], ep[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) L[g] = live ? lv0[(int64_t)(h * G + g) * a.npad_p] : 0.f;
-    shift_exp<G>(L, e);
+    const float mo = shift_exp<G>(L, e);
+    const float mp = __shfl_xor_sync(0xffffffffu, mo, 16);
 #pragma unroll
     for (int g = 0; g < G; ++g) ep[g] = __shfl_xor_sync(0xffffffffu, e[g], 16);
     float e0[G], e1[G];
@@ -131,27 +132,14 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
         e0[g] = h ? ep[g] : e[g];
         e1[g] = h ? e[g] : ep[g];
     }
-    // the sums this half owns, recomputed exactly as in the forward pass
+    // linear-domain value of the sums this half owns: sum_val = m0 + m1 + log T  =>  T = exp(sum_val - m0 - m1), 5
+    // exponentials instead of recomputing 100 products x 5 sums (a third of this pass); the difference of two numbers
+    // of magnitude ~1e2 costs ~2e-5 of relative accuracy in T, far inside the gradient tolerance
     float T[SH];
 #pragma unroll
-    for (int c = 0; c < SH; ++c) T[c] = 0.f;
-    {
-        const float* wq = smem + m.wl + q * G * G * SP + 4 * h;
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-#pragma unroll
-            for (int i = 0; i < G; ++i) {
-                const float pk = e0[i] * e1[j];
-                const float* wk = wq + (j * G + i) * SP;
-                const float4 w = lds_f4(wk);
-                const float w4 = lds_f1(wk + 8 - 3 * h);
-                T[0] = fmaf(pk, w.x, T[0]);
-                T[1] = fmaf(pk, w.y, T[1]);
-                T[2] = fmaf(pk, w.z, T[2]);
-                T[3] = fmaf(pk, w.w, T[3]);
-                T[4] = fmaf(pk, w4, T[4]);
-            }
-        }
+    for (int c = 0; c < SH; ++c) {
+        const int s = sum_of_b(h, c);
+        T[c] = (live && s < S) ? expf(a.sum_val[(int64_t)(q * S + s) * a.npad_p + n] - mo - mp) : 1.f;
     }
     const float* gsrow = smem + m.t + ((size_t)tile * Q * S + q * S) * HT + pt;
     float qv[SH], qvp[SH];
