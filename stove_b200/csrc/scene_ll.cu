@@ -327,12 +327,14 @@ __device__ void obj_region_task(const LLArgs& a, const Smem& m, float* smem, int
         const int px = sc[pp];
         const float2 v = xt[px * HT + ((pt + px) & (HT - 1))];
         const float wv = ok ? v.y : 0.f;
-        float mu[GP], aa[GP], bb[GP];
-        load_leaf_params<G, true>(leaf_q + pp * 3 * GP, mu, aa, bb);
+        const float wx = wv * v.x, wx2 = wx * v.x;
+        float c1[GP], c2[GP], c0[GP];
+        load_leaf_params<G, true>(leaf_q + pp * 3 * GP, c1, c2, c0);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            const float d = v.x - mu[g];
-            L[g] = fmaf(-wv, fmaf(d * d, aa[g], bb[g]), L[g]);
+        for (int g = 0; g < G; ++g) {            // L -= w (c2 x^2 - c1 x + c0) = w (a (x - mu)^2 + b)
+            L[g] = fmaf(-wx2, c2[g], L[g]);
+            L[g] = fmaf(wx, c1[g], L[g]);
+            L[g] = fmaf(-wv, c0[g], L[g]);
         }
     }
     const bool live = pt < npt;
@@ -468,14 +470,12 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_fwd_kernel(const __gri
         __syncthreads();
         // ---- stage the object SPN's tables over the frame buffers; background root meanwhile
         {
-            const float4* src = reinterpret_cast<const float4*>(a.leaf);
-            float4* dst = reinterpret_cast<float4*>(smem + m.lf);
-            for (int i = tid; i < Q * a.st.pmax * 3 * GP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
-            src = reinterpret_cast<const float4*>(a.wlin);
-            dst = reinterpret_cast<float4*>(smem + m.wl);
+            const float4* src = reinterpret_cast<const float4*>(a.wlin);
+            float4* dst = reinterpret_cast<float4*>(smem + m.wl);
             for (int i = tid; i < Q * G * G * SP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
             for (int i = tid; i < R * S * S; i += blockDim.x) cp_async4(smem + m.rws + i, a.rlin + i);
             cp_async_commit();
+            stage_leaf_poly(smem + m.lf, a.leaf, Q * a.st.pmax, GP, tid, blockDim.x);      // (c1, c2, c0) rows, see scene_ll.cuh
             int32_t* scs = reinterpret_cast<int32_t*>(smem + m.scs);
             for (int i = tid; i < Q * a.st.pmax; i += blockDim.x) scs[i] = max(__ldg(a.st.scope + i), 0);
         }

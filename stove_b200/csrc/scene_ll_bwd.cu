@@ -263,23 +263,25 @@ __device__ void bwd_input_task(const LLArgs& a, const SmemB& m, float* smem, int
     const bool inside = v.y >= 0.f && v.y <= 1.f;
     const int32_t* sl = reinterpret_cast<const int32_t*>(smem + m.slots) + px * R;
     const float* glt = smem + m.v + ((size_t)tile * Q * 2 * HT + pt) * GLP;
-    float t1 = 0.f, t2 = 0.f;
+    // u = a (x - mu)^2 + b = c2 x^2 - c1 x + c0 and du/dx = 2 c2 x - c1 (polynomial leaf table): the sums over the
+    // Gaussians and over the R leaves of the pixel are three FMAs per (leaf, Gaussian); x enters once at the end
+    float A1 = 0.f, A2 = 0.f, A3 = 0.f;          // sum gl c2, sum gl c1, sum gl c0
     for (int r = 0; r < R; ++r) {
         const int pk = sl[r];
-        float mu[GP], aa[GP], bb[GP];
-        load_leaf_params<G, true>(smem + m.lf + (pk & 0xffff) * 3 * GP, mu, aa, bb);
+        float c1[GP], c2[GP], c0[GP];
+        load_leaf_params<G, true>(smem + m.lf + (pk & 0xffff) * 3 * GP, c1, c2, c0);
         const float* gp = glt + (size_t)(pk >> 16) * HT * GLP;
         const float4 g0 = lds_f4(gp), g1 = lds_f4(gp + 4), g2 = lds_f4(gp + 8);
         const float gv[12] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y, g2.z, g2.w};
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const float d = v.x - mu[g];
-            const float ad = aa[g] * d;
-            t1 = fmaf(gv[g], ad, t1);
-            t2 = fmaf(gv[g], fmaf(ad, d, bb[g]), t2);
+            A1 = fmaf(gv[g], c2[g], A1);
+            A2 = fmaf(gv[g], c1[g], A2);
+            A3 = fmaf(gv[g], c0[g], A3);
         }
     }
-    *xe = make_float2(-2.f * wv * t1, inside ? t2 : 0.f);
+    // L = -w u:  dL/dx = -w (2 x A1 - A2),  dL/dmask = +u summed = x^2 A1 - x A2 + A3 where the mask is inside [0, 1]
+    *xe = make_float2(-wv * fmaf(2.f * v.x, A1, -A2), inside ? fmaf(v.x, fmaf(v.x, A1, -A2), A3) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------
@@ -654,10 +656,7 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
         __syncthreads();
         // ---- leaf table + slot table -> U, (x, mask) tile -> T
         {
-            const float4* src = reinterpret_cast<const float4*>(a.leaf);
-            float4* dst = reinterpret_cast<float4*>(smem + m.lf);
-            for (int i = tid; i < Q * a.st.pmax * 3 * GP / 4; i += blockDim.x) cp_async16(dst + i, src + i);
-            cp_async_commit();
+            stage_leaf_poly(smem + m.lf, a.leaf, Q * a.st.pmax, GP, tid, blockDim.x);      // (c1, c2, c0) rows, see scene_ll.cuh
             int32_t* sl = reinterpret_cast<int32_t*>(smem + m.slots);
             for (int i = tid; i < D * R; i += blockDim.x) {
                 const int slot = __ldg(a.st.slot + i);
@@ -688,7 +687,6 @@ __global__ void __launch_bounds__(MAXNW * 32, 1) scene_ll_bwd_kernel(const __gri
                     xw[(size_t)tile * D * HT + px * HT + ((pt + px) & (HT - 1))] = make_float2(__ldg(xs + i), __ldg(ms + i));
                 }
             }
-            cp_async_wait<0>();
         }
         __syncthreads();
         // ---- IN
