@@ -24,7 +24,10 @@
 //        shuffle and each computes half of the region's sums (max-shifted linear domain, exact log-domain slow path).
 //        Half-warp tiles keep 81-94 % of the lanes busy for the 36-39 patches a CTA owns; the 32-patch tiles of
 //        spn_obj.cu would leave 40 % idle and cost the same issue slots.
+//        The leaf table is staged in polynomial form (scene_ll.cuh: stage_leaf_poly): three FMAs per (pixel, Gaussian).
 //   root partitions per (r, tile), final logsumexp per patch.
+// Sequence mode (stove_scene_seq): the states come straight from the sequence tensors z_sup / z_s of
+// Stove.stove_forward (stove.py:731-736) and the object terms also leave weighted by sx * sy (supair.py:79).
 // Everything the backward pass needs is written once (leaf / sum values, root values) in the layouts of
 // spn_obj.cu / spn_bg.cu, so the unfused kernels remain usable on the fused forward's outputs (tests do that).
 #include "common.cuh"
@@ -300,10 +303,6 @@ __device__ void bg_root_frame(const LLArgs& a, int fi, int64_t f, const float* b
 // ------------------------------------------------------------------------------------
 // phase OBJ
 // ------------------------------------------------------------------------------------
-// which sums of a region a half-warp owns: s = 4 h + c for c < 4 and s = 8 + h for c = 4 (one aligned float4 and
-// one float of the 12-float weight row per product)
-__device__ __forceinline__ int sum_of(int h, int c) { return c < 4 ? 4 * h + c : 8 + h; }
-
 template <int G, int S>
 __device__ void obj_region_task(const LLArgs& a, const Smem& m, float* smem, int q, int tile, int npt, int64_t n0g,
                                 int lane) {

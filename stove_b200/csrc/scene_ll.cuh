@@ -51,7 +51,7 @@ struct LLArgs {
 };
 
 struct Smem {                  // offsets in floats
-    int frames_img, frames_bg, frames_tx, frames_ty;     // union U, phases S / BG
+    int frames_img, frames_tx, frames_ty;                // union U, phases S / BG: (x, background) pairs, tents
     int lf, wl, rws, scs;                                 // union U, phase OBJ
     int xw, ss, vr, total;
 };
@@ -63,7 +63,6 @@ __host__ __device__ inline Smem smem_layout(const LLArgs& a, int G, int S, int G
     const int GP = up4(G), SP = up4(S), Q = 2 * a.st.R;
     const int tXs = up4(a.B), tYs = up4(a.A);
     m.frames_img = 0;
-    m.frames_bg = a.rf * a.fs;
     m.frames_tx = 2 * a.rf * a.fs;
     m.frames_ty = m.frames_tx + a.rf * tXs;
     const int frames_sz = m.frames_ty + a.rf * tYs;
@@ -122,6 +121,10 @@ __device__ __forceinline__ float base_coord_r(int k, float rn, int align) {
     return align ? 2.f * (float)k * rn - 1.f : (2.f * (float)k + 1.f) * rn - 1.f;
 }
 __device__ __forceinline__ float recip_n(int n, int align) { return align ? (n > 1 ? 1.f / (float)(n - 1) : 0.f) : 1.f / (float)n; }
+
+// which sums of a mid region a half-warp owns: s = 4 h + c for c < 4 and s = 8 + h for c = 4 (one aligned float4 and
+// one float of the 12-float weight row per product)
+__device__ __forceinline__ int sum_of(int h, int c) { return c < 4 ? 4 * h + c : 8 + h; }
 
 // Leaf table of the object SPN staged in POLYNOMIAL form: a row (mu[GP], a[GP], b[GP]) of spn_pack.cu becomes
 // (c1 = 2 a mu, c2 = a, c0 = a mu^2 + b) in the same slots, so that  a (x - mu)^2 + b = c2 x^2 - c1 x + c0  costs three

@@ -8,11 +8,12 @@
 // Phases of a round (formulas: tests/kernel_spec.py, checked against autograd of the oracle):
 //   N1  (root partition r, tile): the two halves of a warp own the two mid regions of the partition; gradient of
 //       their sum values -> shared memory, (c, eA, eB) -> workspace for the sum-weight gradients.
-//   N2  (mid region q, tile): lane = (leaf h, patch).  Sums recomputed as in the forward pass; each half walks half of
-//       the 100 products and the halves exchange partial leaf-vector gradients by shuffle.  -> gl[leaf][patch][12]
-//       in shared memory (+ workspace copies for the leaf / sum parameter gradients).
+//   N2  (mid region q, tile): lane = (leaf h, patch).  Linear-domain sums from the saved values (T = exp(sum - m0 - m1));
+//       each half walks half of the 100 products and the halves exchange partial leaf-vector gradients by shuffle.
+//       -> gl[leaf][patch][12] in shared memory (+ workspace copies for the leaf / sum parameter gradients).
 //   IN  (tile, pixel pair): lane = (pixel of the pair, patch): d/d glimpse pixel and d/d mask over the 6 leaves the
-//       pixel belongs to; the (x, mask) tile becomes the (g_x, g_mask) tile in place.
+//       pixel belongs to (polynomial leaf table: three sums, x enters at the end); the (x, mask) tile becomes the
+//       (g_x, g_mask) tile in place.
 //   BR  warp = frame: background root -> leaf-vector gradients (8-lane groups = root partitions).
 //   BI  lane = pixel (its 3 x 18 leaf parameters in registers, read ONCE from L2), loop over the frames of the round:
 //       d/d background mask -> the .y half of the frame buffer.
@@ -20,6 +21,8 @@
 //       the box touches, then the 100 sample points (glimpse and mask gradients from the tile, bilinear derivatives,
 //       scatter into the background gradient).  The background state before each object is REPLAYED from the tents
 //       of the earlier objects (2 FMA + clamp per object) instead of stored: no O x frame buffer.
+// Sequence mode (stove_scene_seq): per-frame weights from the scalar d loss / d elbo (what elbo_bwd_kernel computes),
+// gradients written straight into those of z_sup / z_s / log q / trans (what zall_bwd_kernel and an add did).
 #include "common.cuh"
 #include "scene_math.cuh"
 #include "spn_math.cuh"
@@ -33,8 +36,6 @@ int spn1_param_kernels(const stove_spn1_struct* st, int64_t N, const float* x, c
                        cudaStream_t s_root);
 
 namespace sl {
-
-__device__ __forceinline__ int sum_of_b(int h, int c) { return c < 4 ? 4 * h + c : 8 + h; }     // see scene_ll.cu: sum_of
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -138,7 +139,7 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
     float T[SH];
 #pragma unroll
     for (int c = 0; c < SH; ++c) {
-        const int s = sum_of_b(h, c);
+        const int s = sum_of(h, c);
         T[c] = (live && s < S) ? expf(a.sum_val[(int64_t)(q * S + s) * a.npad_p + n] - mo - mp) : 1.f;
     }
     const float* gsrow = smem + m.t + ((size_t)tile * Q * S + q * S) * HT + pt;
@@ -146,7 +147,7 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
     unsigned slow_mask = 0;
 #pragma unroll
     for (int c = 0; c < SH; ++c) {
-        const int s = sum_of_b(h, c);
+        const int s = sum_of(h, c);
         const float gs = (s < S) ? gsrow[s * HT] : 0.f;
         if (T[c] > LIN_SUM_FLOOR) {
             qv[c] = gs / T[c];
@@ -214,7 +215,7 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
         for (int g = 0; g < G; ++g) aq[(int64_t)(h * G + g) * a.npad_p] = e[g];
 #pragma unroll
         for (int c = 0; c < SH; ++c) {
-            const int s = sum_of_b(h, c);
+            const int s = sum_of(h, c);
             if (s < S) aq[(int64_t)(2 * G + s) * a.npad_p] = qv[c];
         }
     }
@@ -227,7 +228,7 @@ __device__ void bwd_region_task(const LLArgs& a, const SmemB& m, float* smem, in
             if (h == phase && slow_mask)
                 for (int c = 0; c < SH; ++c)
                     if (slow_mask & (1u << c)) {
-                        const int s = sum_of_b(h, c);
+                        const int s = sum_of(h, c);
                         const float sumv = a.sum_val[(int64_t)(q * S + s) * a.npad_p + n];
                         if (sumv > -INFINITY)
                             slow_sum_backward(lv0, lv0 + (int64_t)G * a.npad_p, (int)a.npad_p, G,
