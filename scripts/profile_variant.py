@@ -1,5 +1,5 @@
 """Per-kernel device time of one eager training step of a bench variant (library event profiler, side streams
-off): python scripts/profile_variant.py o6 [batch]   -> gpurun_out/profile_<variant>.txt"""
+off): python scripts/profile_variant.py o6 [batch] [option=value ...]   -> gpurun_out/profile_<variant>.txt"""
 import os
 import sys
 
@@ -8,8 +8,13 @@ import torch
 import bench
 from stove_b200 import _native as N, dp, ops, synth
 
-variant = sys.argv[1] if len(sys.argv) > 1 else 'o6'
-batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+args = [a for a in sys.argv[1:] if '=' not in a]
+for a in sys.argv[1:]:
+    if '=' in a:                                   # library options, e.g. gnn_threads=512
+        k, v = a.split('=')
+        N.set_option(k, int(v))
+variant = args[0] if len(args) > 0 else 'o6'
+batch = int(args[1]) if len(args) > 1 else 256
 dev = torch.device('cuda', 0)
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False

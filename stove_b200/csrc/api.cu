@@ -127,10 +127,10 @@ int stove_join(StoveFork* f, cudaStream_t s, int nside) {
     return STOVE_OK;
 }
 
-static int g_options[OPT_COUNT] = {1, 1, 0, 2, 0, 0, 2, 0, 0, 0, 74};
+static int g_options[OPT_COUNT] = {1, 1, 0, 2, 0, 0, 2, 0, 0, 0, 74, 0};
 static const char* const kOptionNames[OPT_COUNT] = {"fork", "spn2_nodes_stage", "dynloop_generic", "dynloop_nw",
                                                     "dynloop_recompute", "rollout_cta", "rollout_nw", "gnn_seq_fwd",
-                                                    "gnn_seq_bwd", "head_par_ctas", "wgrad_ctas"};
+                                                    "gnn_seq_bwd", "head_par_ctas", "wgrad_ctas", "gnn_threads"};
 int stove_opt(int id) { return g_options[id]; }
 extern "C" int stove_set_option(const char* name, int value) {
     for (int i = 0; i < OPT_COUNT; ++i)

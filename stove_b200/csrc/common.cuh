@@ -75,6 +75,7 @@ enum StoveOption {
                               // its lifetime, so half the SMs stay free for the chain kernels that become ready while it
                               // runs (sweep in profiles/r02_tune_wgrad_ctas.txt: 0.697 ms/step at 148, 0.680 at 74)
         // CTAs of the head's parameter-gradient kernel (0 = one per SM); it runs beside the LSTM backward
+    OPT_GNN_THREADS,          // threads per CTA of the generic dynamics kernels (gnn_fwd/bwd, dynstep_fwd/bwd): 256, 384, 512; 0 = by object count
     OPT_COUNT
 };
 int stove_opt(int id);

@@ -113,7 +113,7 @@ __device__ __forceinline__ float4 act4(float4 v, int act, int nonlin) {
 }
 
 // out[n][row] = act(b[n] + sum_k W[k][n] in[k][row]) (+ res[n][row]);  W is [K][N]
-__device__ void dense(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
+__device__ __noinline__ void dense(const float* __restrict__ W, const float* __restrict__ bias, int K, int N,
                       const float* in, int ldi, float* out, int ldo, int rows, int act, int nonlin,
                       const float* res, int ldr) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -184,7 +184,7 @@ __device__ void dense(const float* __restrict__ W, const float* __restrict__ bia
 
 // gin[k][row] (=, +=) sum_n W[k][n] gp[n][row], optionally scaled by act'(ymul[k][row]);
 // gin may alias ymul (each element is read and written by the same thread)
-__device__ void dense_bwd_input(const float* __restrict__ W, int K, int N, const float* gp, int ldg,
+__device__ __noinline__ void dense_bwd_input(const float* __restrict__ W, int K, int N, const float* gp, int ldg,
                                 float* gin, int ldi, int rows, bool accumulate,
                                 const float* ymul = nullptr, int ldy = 0, int act = ACT_NONE, int nonlin = 0) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -233,7 +233,7 @@ __device__ void dense_bwd_input(const float* __restrict__ W, int K, int N, const
 }
 
 // slab_w[k][n] (=, +=) sum_row x[k][row] gp[n][row];  slab_b[n] (=, +=) sum_row gp[n][row]
-__device__ void dense_bwd_weight(float* __restrict__ slab_w, float* __restrict__ slab_b, int K, int N,
+__device__ __noinline__ void dense_bwd_weight(float* __restrict__ slab_w, float* __restrict__ slab_b, int K, int N,
                                  const float* x, int ldx, const float* gp, int ldg, int rows, bool accumulate) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int full = rows >> 2;
@@ -432,7 +432,7 @@ __device__ __forceinline__ void load_inputs(const stove_gnn_cfg& c, const GnnBuf
 // ------------------------------------------------------------------------------------
 // forward kernel (one dynamics step)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gnn_fwd_kernel(stove_gnn_cfg c, GnnLayout L, int seq, int64_t n,
+__global__ void __launch_bounds__(512) gnn_fwd_kernel(stove_gnn_cfg c, GnnLayout L, int seq, int64_t n,
                                                       const float* __restrict__ s,
                                                       const float* __restrict__ actions,
                                                       const float* __restrict__ app,
@@ -745,7 +745,7 @@ __device__ void gnn_backward_core(const stove_gnn_cfg& c, const GnnLayout& L, co
 // ------------------------------------------------------------------------------------
 // backward kernel: recompute forward on chip, then reverse.  slab = per-CTA weight gradients.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout L, int seq, int64_t n,
+__global__ void __launch_bounds__(512) gnn_bwd_kernel(stove_gnn_cfg c, GnnLayout L, int seq, int64_t n,
                                                       int stage_w, const float* __restrict__ s,
                                                       const float* __restrict__ actions,
                                                       const float* __restrict__ app,
@@ -854,7 +854,7 @@ __device__ __forceinline__ FuseVal fuse_forward(const stove_gnn_cfg& c, const Fu
     return v;
 }
 
-__global__ void __launch_bounds__(256) dynstep_fwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
+__global__ void __launch_bounds__(512) dynstep_fwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
                                                           int64_t n, stove_dynstep_io io,
                                                           const float* __restrict__ weights) {
     extern __shared__ __align__(16) float smem[];
@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(256) dynstep_fwd_kernel(stove_gnn_cfg c, GnnLa
     }
 }
 
-__global__ void __launch_bounds__(256) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
+__global__ void __launch_bounds__(512) dynstep_bwd_kernel(stove_gnn_cfg c, GnnLayout L, FuseCfg f, int seq,
                                                           int64_t n, int stage_w, int slab_accumulate,
                                                           stove_dynstep_io io,
                                                           const float* __restrict__ weights,
@@ -1033,6 +1033,15 @@ __global__ void gnn_reduce_slabs_kernel(const float* __restrict__ slabs, int nsl
 
 // largest number of sequences per CTA that fits (optionally with staged weights), <= want
 
+// threads per CTA of the step kernels: the device code only uses blockDim.x.  One CTA per SM (shared memory), so more
+// warps only hide latency: 512 threads pay from 5 objects on (multiball, 25+ pair rows per sequence: dynstep_bwd
+// 0.85 -> 0.81 ms per step at 6 objects, 2.52 -> 2.31 ms at 9); option gnn_threads overrides (256 / 384 / 512)
+static int gnn_threads(const stove_gnn_cfg* c) {
+    const int t = stove_opt(OPT_GNN_THREADS);
+    if (t == 256 || t == 384 || t == 512) return t;
+    return c->num_obj >= 5 ? 512 : 256;
+}
+
 static int pick_seq(const stove_gnn_cfg* c, const GnnLayout& L, bool bwd, bool stage, int want) {
     // tuning override (sequences per CTA): options gnn_seq_fwd / gnn_seq_bwd
     if (stove_opt(bwd ? OPT_GNN_SEQ_BWD : OPT_GNN_SEQ_FWD) > 0) want = stove_opt(bwd ? OPT_GNN_SEQ_BWD : OPT_GNN_SEQ_FWD);
@@ -1086,7 +1095,7 @@ extern "C" int stove_gnn_fwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     GnnBuf b = gnn_buffers(*cfg, L.in_dim, seq, false);
     const size_t smem = sizeof(float) * ((size_t)b.total + L.total);
     STOVE_CUDA(cudaFuncSetAttribute(gnn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    STOVE_KERNEL(K_GNN_FWD, (cudaStream_t)stream, gnn_fwd_kernel<<<gnn_target_ctas(n, seq), 256, smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, s, actions, app,
+    STOVE_KERNEL(K_GNN_FWD, (cudaStream_t)stream, gnn_fwd_kernel<<<gnn_target_ctas(n, seq), gnn_threads(cfg), smem, (cudaStream_t)stream>>>(*cfg, L, seq, n, s, actions, app,
                                                                                    weights, out, reward));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
@@ -1143,7 +1152,7 @@ extern "C" int stove_gnn_bwd(const stove_gnn_cfg* cfg, int64_t n, const float* s
     STOVE_CUDA(cudaFuncSetAttribute(gnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     // padding floats of the slabs are never written: clear them once so the reduction is clean
     STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
-    STOVE_KERNEL(K_GNN_BWD, st, gnn_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(*cfg, L, p.seq, n, p.stage, s, actions, app, weights, g_out, g_reward,
+    STOVE_KERNEL(K_GNN_BWD, st, gnn_bwd_kernel<<<p.ctas, gnn_threads(cfg), p.smem, st>>>(*cfg, L, p.seq, n, p.stage, s, actions, app, weights, g_out, g_reward,
                                                 g_s, (float*)workspace));
     STOVE_LAUNCH_CHECK();
     STOVE_KERNEL(K_GNN_REDUCE_SLABS, st, gnn_reduce_slabs_kernel<<<(L.total + 255) / 256, 256, 0, st>>>((const float*)workspace, p.ctas, L.total, g_weights));
@@ -1174,7 +1183,7 @@ extern "C" int stove_dynstep_fwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     const size_t smem = sizeof(float) * ((size_t)b.total + L.total);
     STOVE_CUDA(cudaFuncSetAttribute(dynstep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaStream_t st = (cudaStream_t)stream;
-    STOVE_KERNEL(K_DYNSTEP_FWD, st, dynstep_fwd_kernel<<<gnn_target_ctas(n, seq), 256, smem, st>>>(
+    STOVE_KERNEL(K_DYNSTEP_FWD, st, dynstep_fwd_kernel<<<gnn_target_ctas(n, seq), gnn_threads(cfg), smem, st>>>(
         *cfg, L, make_fuse(cfg, fuse), seq, n, *io, weights));
     STOVE_LAUNCH_CHECK();
     return STOVE_OK;
@@ -1200,7 +1209,7 @@ extern "C" int stove_dynstep_bwd(const stove_gnn_cfg* cfg, const stove_fuse_cfg*
     // the per-CTA slabs accumulate over the time steps of one backward pass (same n => same grid):
     // cleared before the first call, reduced into g_weights after the last
     if (first) STOVE_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)p.ctas * L.total, st));
-    STOVE_KERNEL(K_DYNSTEP_BWD, st, dynstep_bwd_kernel<<<p.ctas, 256, p.smem, st>>>(
+    STOVE_KERNEL(K_DYNSTEP_BWD, st, dynstep_bwd_kernel<<<p.ctas, gnn_threads(cfg), p.smem, st>>>(
         *cfg, L, make_fuse(cfg, fuse), p.seq, n, p.stage, first ? 0 : 1, *io, weights, (float*)workspace));
     STOVE_LAUNCH_CHECK();
     if (last) {
