@@ -806,7 +806,10 @@ def kernel_roofline(kernel, times, n_steps, pk, brief=False):
     elif flops:
         ach = flops / (avg_ms * 1e-3) / 1e12
         out.update({'bound': 'fp32', 'achieved': ach, 'peak': pk['fp32_tflops'], 'unit': 'TFLOP/s', 'frac': ach / pk['fp32_tflops'],
-                    'frac_useful': ach / pk['fp32_tflops'], 'peak_source': pk['fp32_src']})
+                    'frac_useful': ach / pk['fp32_tflops'], 'peak_source': pk['fp32_src'],
+                    'note': 'neither HBM nor tensor bound (SURVEY 8d: ~80 FLOP per algorithmic byte, fp32 SIMT arithmetic): `achieved` = '
+                            'the reference operation count of the launch / its duration against the measured FP32-FMA peak; the HBM '
+                            'fraction of the same launch is under `hbm`'})
     else:
         out.update({'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                     'frac': (achieved / pk['hbm_gbs']) if achieved else None, 'peak_source': pk['hbm_src']})
