@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -81,6 +82,21 @@ def test_structure_tables():
         else:
             assert t.kind == 'D1'
             assert t.host['side'].sum(0).tolist() == [g['n'] // 2] * 3
+            # tables of the fused scene-likelihood kernels (csrc/scene_ll*.cu): scope lists per background leaf and the
+            # row maps of the two lane-interleaved copies of the leaf table
+            h, D, R = t.host, g['n'], 3
+            for r in range(R):
+                for side in (0, 1):
+                    l, cnt = 2 * r + side, int(h['bg_cnt'][2 * r + side])
+                    px = h['bg_scope'][l, :cnt]
+                    assert (px[1:] > px[:-1]).all() and (h['side'][px, r] == side).all()
+                    rows = h['il_f'][l * t.il_stride_f:l * t.il_stride_f + cnt]
+                    assert (rows == px * R + r).all()                       # forward copy: (leaf, position in scope)
+                    assert (h['il_f'][l * t.il_stride_f + cnt:(l + 1) * t.il_stride_f] == -1).all()
+                assert int(h['bg_cnt'][2 * r]) + int(h['bg_cnt'][2 * r + 1]) == D
+                rows = h['il_b'][r * t.il_stride_b:r * t.il_stride_b + D]
+                assert (rows == np.arange(D) * R + r).all()                 # backward copy: (repetition, pixel)
+            assert t.il_stride_f % 32 == 0 and t.il_stride_b % 32 == 0
 
 
 @pytest.mark.parametrize('kind,O', [('3_only', 3), ('greedy', 6), ('volatile', 4), ('greedy', 3)])
