@@ -15,5 +15,6 @@ run() {
 }
 run memcheck_scene_ll memcheck tests/test_gpu_scene_ll.py
 run racecheck_scene_ll racecheck tests/test_gpu_scene_ll.py -k "kw0-1 or kw1-5 or kw2-33 or kw5-40 or kw6-70 or kw8-7 or oracle"
-run initcheck_scene_ll initcheck tests/test_gpu_scene_ll.py -k "kw2-33 or kw6-70"
+run racecheck_scene_seq racecheck tests/test_gpu_scene_ll.py -k "sequence and (kw0-5 or kw2-9)"
+run initcheck_scene_ll initcheck tests/test_gpu_scene_ll.py -k "kw2-33 or kw6-70 or (sequence and kw0-5)"
 cat $OUT
