@@ -17,6 +17,9 @@ __global__ void pack_leaf_fwd_kernel(const float* __restrict__ means, const floa
     dst[g] = means[i];
     dst[GP + g] = 0.5f / var;
     dst[2 * GP + g] = 0.5f * logf(var) + HALF_LOG_2PI;
+    // the padding Gaussians of the row (G .. GP - 1) are zero: written here, so the caller need not clear the table
+    if (g == 0)
+        for (int k = G; k < GP; ++k) { dst[k] = 0.f; dst[GP + k] = 0.f; dst[2 * GP + k] = 0.f; }
 }
 
 __global__ void pack_leaf_bwd_kernel(const float* __restrict__ sig, const int32_t* __restrict__ dst_row,
@@ -53,6 +56,9 @@ __global__ void pack_sum_fwd_kernel(const float* __restrict__ raw, int nb, int K
         int64_t o = ((int64_t)b * K + k) * SP + s;
         wlog[o] = lw;
         wlin[o] = expf(lw);
+        // padding columns (S .. SP - 1) of the row: zero, written by the warp of column 0
+        if (s == 0)
+            for (int c = S; c < SP; ++c) { wlog[o + c] = 0.f; wlin[o + c] = 0.f; }
     }
 }
 

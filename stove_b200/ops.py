@@ -85,7 +85,10 @@ class PackLeaf(torch.autograd.Function):
         means, sigma = means.contiguous(), sigma.contiguous()
         N.require_cuda_f32(means, sigma)
         rows, G = means.shape
-        packed = torch.zeros(prow_total, 3, GP, device=means.device, dtype=means.dtype)
+        # when every row of the table is some leaf's row (dst_row is a permutation: the SuPAIR structures) nothing needs
+        # clearing -- the kernel writes the padding Gaussians; structures with unequal regions leave unused rows
+        alloc = torch.empty if rows == prow_total else torch.zeros
+        packed = alloc(prow_total, 3, GP, device=means.device, dtype=means.dtype)
         N.check(N.lib().stove_spn_pack_leaf_fwd(N.ptr(means), N.ptr(sigma), N.ptr(dst_row), rows, G, GP,
                                                 vmin, vmax, N.ptr(packed), N.stream()))
         ctx.save_for_backward(sigma, dst_row)
@@ -112,8 +115,8 @@ class PackSum(torch.autograd.Function):
         raw = raw.contiguous()
         N.require_cuda_f32(raw)
         nb, K, S = raw.shape
-        wlog = torch.zeros(nb, K, SP, device=raw.device, dtype=raw.dtype)
-        wlin = torch.zeros_like(wlog)
+        wlog = torch.empty(nb, K, SP, device=raw.device, dtype=raw.dtype)       # padding columns written by the kernel
+        wlin = torch.empty_like(wlog)
         N.check(N.lib().stove_spn_pack_sum_fwd(N.ptr(raw), nb, K, S, SP, N.ptr(wlog), N.ptr(wlin), N.stream()))
         ctx.save_for_backward(wlog)
         ctx.meta = (nb, K, S, SP)
