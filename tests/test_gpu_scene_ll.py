@@ -167,3 +167,24 @@ def test_sequence_elbo_vs_composition(kw, n, T):
     for k in pb_:
         ck.close('g.' + k, pa_[k], pb_[k], 2e-4)
     ck.finish()
+
+
+def test_fused_forward_with_unfused_backward():
+    """The fused forward kernel leaves the saved activations in the layouts of spn_obj.cu / spn_bg.cu: differentiating it
+    with the UNFUSED backward kernels (ops.set_scene_ll_bwd(False)) gives the gradients of the fused backward kernel."""
+    from stove_b200 import ops
+    oc, sd, model = make_model({}, 34)
+    img, z, w = _inputs(oc, 45, 11)
+    a = _run(model, img, z, w, fused=True)
+    prev = ops.set_scene_ll_bwd(False)
+    try:
+        b = _run(model, img, z, w, fused=True)
+    finally:
+        ops.set_scene_ll_bwd(prev)
+    ck = Checker('scene_ll_fused_fwd_unfused_bwd')
+    ck.close('bg', a['bg'], b['bg'], 1e-7)
+    ck.close('obj', a['obj'], b['obj'], 1e-7)
+    ck.mostly_close('gz', a['gz'], b['gz'], 2e-4)
+    for k in b['grads']:
+        ck.close('g.' + k, a['grads'][k], b['grads'][k], 2e-4)
+    ck.finish()
