@@ -122,3 +122,38 @@ def scene_frame_bwd(img, z, pa, pb, g_patch, g_marg, g_bg, align=False):
                             Gp[yy, xx] += g_marg[o, i, j] * wgt
         G = Gp
     return gz
+
+
+# ------------------------------------------------------------------------------------------------
+# Identities the fused scene-likelihood kernels (csrc/scene_ll.cu, scene_ll_bwd.cu) rely on
+# ------------------------------------------------------------------------------------------------
+def leaf_poly_table(mu, a, b):
+    """(mu, a, b) -> (c1, c2, c0) with  a (x - mu)^2 + b = c2 x^2 - c1 x + c0  (scene_ll.cuh: stage_leaf_poly)."""
+    return 2 * a * mu, a, a * mu * mu + b
+
+
+def leaf_poly_backward(x, w, gl, c1, c2, c0):
+    """Input pass of the object SPN in polynomial form: leaf value L_g = -w u_g(x); given gl_g = dloss/dL_g returns
+    (dloss/dx, dloss/dmask) with w = 1 - mask: three sums over the Gaussians, x enters at the end."""
+    A1, A2, A3 = (gl * c2).sum(-1), (gl * c1).sum(-1), (gl * c0).sum(-1)
+    return -w * (2 * x * A1 - A2), x * x * A1 - x * A2 + A3
+
+
+def sums_from_saved(sum_val, leaf0, leaf1):
+    """Linear-domain value of a sum node from what the forward pass saved: sum = m0 + m1 + log T (max-shifted form of
+    rat_torch.py:202-222)  =>  T = exp(sum - m0 - m1), m = max of the leaf vector."""
+    return torch.exp(sum_val - leaf0.max(-1, keepdim=True)[0] - leaf1.max(-1, keepdim=True)[0])
+
+
+def sequence_mode_backward(g_elbo, n, T, skip, t, z4, out_obj, g_state, beta):
+    """What the backward kernel does in sequence mode for one object of frame t (1 <= t < T): z4 = (sx, q = sy / sx, x, y)
+    as stored in z_sup / z_s, out_obj = raw object log-likelihood, g_state = dloss / d(sx, sy, x, y) through glimpse and
+    masks computed with the unit-free frame weight.  Returns (frame weight, d loss / d raw object ll, d loss / d overlap,
+    d loss / d (sx, q, x, y)) -- stove.py:731-748, supair.py:79, 84-85, 151-158."""
+    S, nsup = T - skip, skip - 1
+    w = g_elbo / (n * S) if t >= skip else g_elbo / (n * nsup)
+    sx, q = z4[0], z4[1]
+    sy = sx * q
+    gsx = g_state[0] + w * out_obj * sy
+    gsy = g_state[1] + w * out_obj * sx
+    return w, w * sx * sy, -beta * w, torch.stack([gsx + gsy * q, gsy * sx, g_state[2], g_state[3]])
