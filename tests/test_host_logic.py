@@ -205,3 +205,23 @@ def test_unsupported_debug_flags_raise():
         cfg = StoveConfig(width=32, height=32, num_obj=3, action_conditioned=False, action_space=None, **{flag: True})
         with pytest.raises(NotImplementedError):
             Stove(cfg)
+
+
+def test_scene_ll_planner_without_a_gpu():
+    """stove_scene_ll_supported only plans (frames per round, tiles, shared memory): callable on the CPU.  The fused
+    kernels take single-channel frames with the SuPAIR SPN sizes and give way to the unfused kernels otherwise."""
+    import ctypes as C
+    lib = _native.lib()
+    obj = _native.Spn2Struct(100, 6, 10, 10, 50, None, None, None, None)
+    bg32 = _native.Spn1Struct(32 * 32, 3, 6, None)
+    bg50 = _native.Spn1Struct(50 * 50, 3, 6, None)
+    sup = lambda F, O, Cc, A, B, o, b: lib.stove_scene_ll_supported(F, O, Cc, A, B, 10, 10, C.byref(o), C.byref(b))
+    assert sup(1792, 3, 1, 32, 32, obj, bg32) == 1                  # BASELINE config 1
+    assert sup(3584, 3, 1, 32, 32, obj, bg32) == 1                  # config 3 (two rounds per CTA)
+    assert sup(1792, 9, 1, 50, 50, obj, bg50) == 1                  # config 4
+    assert sup(1, 3, 1, 32, 32, obj, bg32) == 1
+    assert sup(1792, 3, 3, 32, 32, obj, bg32) == 0                  # colour glimpses (object_embedding): unfused kernels
+    assert sup(1792, 3, 1, 32, 32, _native.Spn2Struct(100, 6, 8, 8, 50, None, None, None, None), bg32) == 0
+    assert sup(1792, 3, 1, 32, 32, obj, bg50) == 0                  # background SPN of another frame size
+    big = _native.Spn1Struct(200 * 200, 3, 6, None)
+    assert sup(64, 3, 1, 200, 200, obj, big) == 0                   # a frame does not fit shared memory
