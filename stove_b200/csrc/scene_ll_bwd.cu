@@ -390,27 +390,29 @@ __device__ void bwd_bg_input_task(const LLArgs& a, const SmemB& m, float* smem, 
     }
     unsigned addr = smem_u32(smem + m.fb) + (unsigned)pxc * 8u;
     const unsigned fstride = (unsigned)a.fs * 8u;
+    // a real loop over the frames (two per trip): fully unrolled, the 13 copies of the body were 19 KB of straight-line
+    // code that every warp runs twice -- 37 % of this phase's stall samples were instruction fetch
+    unsigned goff = 0;
+#pragma unroll 2
+    for (int f = 0; f < nfr; ++f) {
+        float xv;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(addr));
+        float t = 0.f;
 #pragma unroll
-    for (int f = 0; f < MAXF; ++f) {
-        if (f < nfr) {
-            float xv;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(addr));
-            float t = 0.f;
+        for (int r = 0; r < RB; ++r) {
+            float4 g0, g1;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(gaddr[r] + goff));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(gaddr[r] + goff + 16u));
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-            for (int r = 0; r < RB; ++r) {
-                float4 g0, g1;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(gaddr[r] + f * (2 * RB * BGLP * 4)));
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(gaddr[r] + f * (2 * RB * BGLP * 4) + 16));
-                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                for (int g = 0; g < GB; ++g) {
-                    const float d = xv - mu[r][g];
-                    t = fmaf(gv[g], fmaf(aa[r][g] * d, d, bb[r][g]), t);
-                }
+            for (int g = 0; g < GB; ++g) {
+                const float d = xv - mu[r][g];
+                t = fmaf(gv[g], fmaf(aa[r][g] * d, d, bb[r][g]), t);
             }
-            if (ok) asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + 4u), "f"(t) : "memory");
-            addr += fstride;
         }
+        if (ok) asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr + 4u), "f"(t) : "memory");
+        addr += fstride;
+        goff += 2 * RB * BGLP * 4;
     }
 }
 
@@ -462,16 +464,7 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
         warp_tents(a, zz.x, zz.y, zz.z, zz.w, t, t + 2 * tXs, t + tXs, t + 2 * tXs + tYs, lane, ulo, uhi);
         if (lane == 0) { rng[2 * o] = ulo; rng[2 * o + 1] = uhi; }
     }
-    float xb[MAXIT], yb[MAXIT];
-    {
-        const float rb = recip_n(a.pb, a.align), ra = recip_n(a.pa, a.align);
-#pragma unroll
-        for (int it = 0; it < MAXIT; ++it) {
-            const int idx = lane + 32 * it, i = idx / a.pb, j = idx - i * a.pb;
-            xb[it] = base_coord_r(j, rb, a.align);
-            yb[it] = base_coord_r(i, ra, a.align);
-        }
-    }
+    const float rpb = recip_n(a.pb, a.align), rpa = recip_n(a.pa, a.align);
     const float kB = unnorm_slope(a.B, a.align), kA = unnorm_slope(a.A, a.align);
     const float oB = unnorm_offset(a.B, a.align), oA = unnorm_offset(a.A, a.align);
     const float rB = recip_n(a.B, a.align), rA = recip_n(a.A, a.align);
@@ -519,11 +512,14 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
         const int pl = fi * a.O + o, tile = pl / HT, pt = pl - tile * HT;
         const float2* xt = xw + (size_t)tile * D * HT;
         const float mx = sx * kB, ox = fmaf(tx, kB, oB), my = sy * kA, oy = fmaf(ty, kA, oA);
-#pragma unroll
-        for (int it = 0; it < MAXIT; ++it) {
-            const int idx = lane + 32 * it;
-            if (idx < PP) {
-                const Corner4 c = corners4(fmaf(yb[it], my, oy), fmaf(xb[it], mx, ox), a.A, a.B);
+        // (a real loop: the unrolled copies of this body made the phase 53 KB of straight-line code, 30 % of its stall
+        //  samples were instruction fetch; the glimpse coordinates are recomputed per pixel instead of kept in registers)
+#pragma unroll 1
+        for (int idx = lane; idx < PP; idx += 32) {
+            {
+                const int gi = idx / a.pb, gj = idx - gi * a.pb;
+                const float xbi = base_coord_r(gj, rpb, a.align), ybi = base_coord_r(gi, rpa, a.align);
+                const Corner4 c = corners4(fmaf(ybi, my, oy), fmaf(xbi, mx, ox), a.A, a.B);
                 const float2 gt = xt[idx * HT + ((pt + idx) & (HT - 1))];       // (g_x, g_mask) of this glimpse pixel
                 const float gm = gov + gt.y, gp = gt.x;
                 const int a00 = c.y0 * a.B + c.x0, a01 = c.y0 * a.B + c.x1, a10 = c.y1 * a.B + c.x0, a11 = c.y1 * a.B + c.x1;
@@ -545,9 +541,9 @@ __device__ void scene_frame_bwd(const LLArgs& a, const SmemB& m, float* smem, in
                 const float qdx = (1.f - c.fy) * (q01 - q00) + c.fy * (q11 - q10);
                 // marg = 1 - sample(1 - bg): d marg / d p = -d sample
                 const float dpx = fmaf(gp, qdx, -gm * mdx), dpy = fmaf(gp, qdy, -gm * mdy);
-                gsx = fmaf(dpx * kB, xb[it], gsx);
+                gsx = fmaf(dpx * kB, xbi, gsx);
                 gtx = fmaf(dpx, kB, gtx);
-                gsy = fmaf(dpy * kA, yb[it], gsy);
+                gsy = fmaf(dpy * kA, ybi, gsy);
                 gty = fmaf(dpy, kA, gty);
                 // d marg / d bg_o = + bilinear weights (zero weight outside the frame)
                 if (gm != 0.f) {
