@@ -359,11 +359,16 @@ __device__ void obj_region_task(const LLArgs& a, const Smem& m, float* smem, int
 #pragma unroll
     for (int c = 0; c < SH; ++c) T[c] = 0.f;
     const float* wq = smem + m.wl + q * G * G * SP + 4 * h;
-#pragma unroll
+    // j as a real loop (e1[j] picked by a select chain): fully unrolled, the 100 products were 900 straight-line
+    // instructions that a warp runs twice -- a quarter of this phase's stall samples were instruction fetch
+#pragma unroll 1
     for (int j = 0; j < G; ++j) {
+        float e1j = e1[0];
+#pragma unroll
+        for (int t = 1; t < G; ++t) e1j = (j == t) ? e1[t] : e1j;
 #pragma unroll
         for (int i = 0; i < G; ++i) {
-            const float pk = e0[i] * e1[j];
+            const float pk = e0[i] * e1j;
             const float* wk = wq + (j * G + i) * SP;
             const float4 w = lds_f4(wk);
             const float w4 = lds_f1(wk + 8 - 3 * h);                // element 8 + h of the row
