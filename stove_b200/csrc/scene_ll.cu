@@ -98,8 +98,10 @@ __device__ void scene_frame_fwd(const LLArgs& a, int64_t f, int pl0, float2* fb,
     const float rPP = 1.f / (float)PP;
     const int du = 32 / a.B, dv = 32 - du * a.B;
     __syncwarp();
+    float4 znext = load_z(a, f, 0);
     for (int o = 0; o < a.O; ++o) {
-        const float4 zz = load_z(a, f, o);
+        const float4 zz = znext;
+        if (o + 1 < a.O) znext = load_z(a, f, o + 1);        // the next object's state travels while this one is composited
         const float sx = zz.x, sy = zz.y, tx = zz.z, ty = zz.w;
         const float mx = sx * kB, ox = fmaf(tx, kB, oB), my = sy * kA, oy = fmaf(ty, kA, oA);
         const int pl = pl0 + o, tile = pl / HT, pt = pl - tile * HT;
