@@ -927,12 +927,16 @@ def main():
     ap.add_argument('--no-graph', action='store_true', help='run the training step eagerly (no CUDA graph)')
     ap.add_argument('--headline-only', action='store_true', help='skip the extra workloads (configs 2-5, strong scaling)')
     ap.add_argument('--no-scene-seq', action='store_true', help='A/B: ZAll -> SceneLL -> ElboAssemble instead of SceneElbo')
+    ap.add_argument('--no-dyn-stream', action='store_true', help='A/B: dynamics weights packed on the SPN packing stream')
     ap.add_argument('--option', action='append', default=[], help='A/B: library option name=value (stove_set_option)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.no_scene_seq:
         from stove_b200 import ops
         ops.set_scene_seq(False)
+    if args.no_dyn_stream:
+        from stove_b200 import ops
+        ops.set_dyn_stream(False)
     for kv in args.option:
         from stove_b200 import _native
         k, v = kv.split('=')

@@ -164,6 +164,25 @@ def fork_enabled():
     return _FORK
 
 
+_DYN_STREAM = True
+
+
+def set_dyn_stream(enabled):
+    """The dynamics weights are packed on a side stream of their own (True) or on the stream that packs the SPN
+    parameters (False).  autograd runs a node's backward on the stream of its forward, and DynamicsLoop.backward
+    joins its weight-gradient kernels into the stream that packed the weights: with one stream for both, the
+    backward of the SPN packing (ready as soon as the SPN parameter-gradient kernels are) queues behind the
+    weight-gradient kernels of the dynamics loop and ends up as the tail of the step.  Returns the previous
+    setting."""
+    global _DYN_STREAM
+    prev, _DYN_STREAM = _DYN_STREAM, bool(enabled)
+    return prev
+
+
+def dyn_stream_enabled():
+    return _DYN_STREAM
+
+
 def _zeros_views(ref, *shapes):
     """Zero tensors of the given shapes carved out of ONE buffer (one fill launch instead of one each);
     every view starts on a 256-byte boundary."""

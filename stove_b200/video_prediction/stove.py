@@ -253,10 +253,16 @@ class Stove(nn.Module):
         # encoder -> (constrain, match, smooth, velocities) in one kernel (csrc/glue.cu)
         zp = self.sup.encoder(x.flatten(end_dim=1), planes=x_planes).view(n, T, O, 8)
 
+        # the dynamics weights on a stream of their own: their backward (and the weight-gradient kernels that
+        # DynamicsLoop.backward joins into this stream) must not sit in front of the backward of the SPN packing
+        dyn_stream = self.sup._side_stream(x.device, 'pack_dyn') if ops.dyn_stream_enabled() else pack_stream
         pack_stream.wait_event(forked)
+        if dyn_stream is not pack_stream:
+            dyn_stream.wait_event(forked)
+        with torch.cuda.stream(dyn_stream):
+            packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
         with torch.cuda.stream(pack_stream):
             packed_spn = self.sup.pack()
-            packed_dyn = self.dyn.pack_weights(0, actions is not None, c.debug_core_appearance)
             # initial latents ~ N(0, 0.01^2) (stove.py:672-680).  The reference draws a second sample of the same
             # shape for the initial dynamics std (logging only); both come from one generator launch
             prior_shape = (n, O, cl // 2 - 4, 1)
@@ -276,6 +282,8 @@ class Stove(nn.Module):
 
         # dynamics loop: the whole loop is one persistent kernel (csrc/dynloop.cu), chained on the device
         cur.wait_stream(pack_stream)
+        if dyn_stream is not pack_stream:
+            cur.wait_stream(dyn_stream)
         cfg_dyn, w_dyn = packed_dyn
         for t in (w_dyn, lat0, eps, x_scored) + tuple(v for pk in packed_spn if pk is not None
                                                         for v in vars(pk).values() if isinstance(v, torch.Tensor)):
@@ -283,7 +291,7 @@ class Stove(nn.Module):
         z_s, z_dyn_s, z_dyn_std_s, z_std_s, log_z_n, trans_n, rewards = ops.DynamicsLoop.apply(
             z_sup_full, z_sup_std_full, lat0, eps, actions,
             obj_appearances if c.debug_core_appearance else None, w_dyn, cfg_dyn, self._fuse_cfg(), skip,
-            pack_stream)
+            dyn_stream)
         if not c.action_conditioned:
             rewards = torch.zeros(T - skip)
 
