@@ -225,3 +225,14 @@ def test_scene_ll_planner_without_a_gpu():
     assert sup(1792, 3, 1, 32, 32, obj, bg50) == 0                  # background SPN of another frame size
     big = _native.Spn1Struct(200 * 200, 3, 6, None)
     assert sup(64, 3, 1, 200, 200, obj, big) == 0                   # a frame does not fit shared memory
+
+
+def test_schedule_switches_return_the_previous_setting():
+    """The A/B switches of the step schedule (bench.py --no-scene-seq / --no-dyn-stream) are plain host flags: each setter
+    returns the previous value, so a test can restore it.  Defaults: sequence-mode scene likelihood, fused backward and the
+    dynamics weights packed on a stream of their own."""
+    from stove_b200 import ops
+    for setter, getter in ((ops.set_dyn_stream, ops.dyn_stream_enabled), (ops.set_scene_seq, ops.scene_seq_enabled)):
+        assert getter() is True
+        assert setter(False) is True and getter() is False
+        assert setter(True) is False and getter() is True
